@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""Benchmark of the orbital-update hot path (BASELINE.json metric:
+"H psi grid-pt*orbital updates/s").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload h2o64|synth256|sih4] [--dtype f64|f32] [--lap 0|2]
+
+A step is one Hamiltonian::applyLocal over the whole orbital block (the fused
+H psi kernel).  Default workload = BASELINE configs[1], examples/H2O_64:
+128^3 grid, 256 orbitals, ORBDTYPE double, FDtype=4th (lap_type 2); at N > 1
+GPUs every rank owns a 128^3 box of a domain split along x (weak scaling) and
+exchanges x-halo planes over NCCL every step.  Prints ONE JSON line.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (local dims, lattice of the local box, orbitals, lap_type, description)
+    "h2o64": ((128, 128, 128), 23.4884, 256, 2,
+              "examples/H2O_64 H psi: 128^3 grid x 256 orbitals, FDtype=4th"),
+    "synth256": ((256, 256, 256), 46.9768, 64, 0,
+                 "synthetic sweep: 256^3 grid, Mehrstellen"),
+    "sih4": ((40, 40, 40), 14.0, 4, 0, "examples/SiH4: 40^3 grid x 4 orbitals, Mehrstellen"),
+}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop_evt = threading.Event()
+
+    def run(self):
+        while not self.stop_evt.is_set():
+            try:
+                out = subprocess.run(
+                    ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                     "--format=csv,noheader,nounits"],
+                    capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop_evt.wait(0.2)
+
+    def summary(self):
+        self.stop_evt.set()
+        self.join(timeout=6)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names)
+                   if any(len(s) > 2 + i and s[2 + i].lower().startswith("active")
+                          for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+                "sm_max_mhz": float(self.samples[0][1]) if self.samples[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+# ---------------------------------------------------------------------------
+# CPU reference arm: the reference's own compiled sources (oracle/_ref) or,
+# if they were not built, our restatement.  P worker processes each own a
+# 1/P sub-box of the sample (the reference's MPI decomposition, halo = local
+# wrap) and run its serial H psi.
+# ---------------------------------------------------------------------------
+def _cpu_worker(args):
+    kind, lap_type, dims, ll, nfunc, dt, reps = args
+    os.environ["OMP_NUM_THREADS"] = "1"
+    from oracle.oracle import Port, Ref, synthetic_potential
+    impl = Ref() if kind == "reference" else Port()
+    rng = np.random.default_rng(11)
+    phi = rng.standard_normal((nfunc,) + tuple(dims)).astype(dt)
+    v = synthetic_potential(dims)
+    impl.hpsi(lap_type, phi[:1], v, ll)  # warm
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        impl.hpsi(lap_type, phi, v, ll)
+    return time.perf_counter() - t0
+
+
+def cpu_hpsi_rate(lap_type, dims, ll, dt, budget_s=12.0):
+    """grid-pt*orbital updates/s of the CPU reference on all host cores."""
+    import multiprocessing as mp
+    from oracle.oracle import Ref
+    kind = "reference" if Ref.available() else "port"
+    cores = os.cpu_count() or 1
+    # split the box along x over P workers like a px x 1 x 1 PEenv
+    P = 1
+    while P * 2 <= cores and dims[0] % (P * 2) == 0 and dims[0] // (P * 2) >= 4:
+        P *= 2
+    sub = (dims[0] // P, dims[1], dims[2])
+    subll = (ll[0] / P, ll[1], ll[2])
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(P) as pool:
+        t1 = max(pool.map(_cpu_worker, [(kind, lap_type, sub, subll, 1, dt, 1)] * P))
+        nfunc = int(max(1, min(64, budget_s / max(t1, 1e-4) / 2)))
+        t = max(pool.map(_cpu_worker, [(kind, lap_type, sub, subll, nfunc, dt, 1)] * P))
+    updates = float(np.prod(dims)) * nfunc
+    sample = ("%s H psi (Hamiltonian::applyLocal sequence), %dx%dx%d box split over %d "
+              "single-thread ranks, %d orbitals" % (kind, dims[0], dims[1], dims[2], P, nfunc))
+    return updates / t, P, kind, sample
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    dims, cell, norb, lap_default, desc = WORKLOADS[args.workload]
+    lap_type = lap_default if args.lap is None else args.lap
+    dt = np.float64 if args.dtype == "f64" else np.float32
+    ll = (cell,) * 3
+    vals = []
+    info = None
+    for _ in range(args.warmup + args.steps):
+        rate, P, kind, sample = cpu_hpsi_rate(lap_type, dims, ll, dt,
+                                              budget_s=60.0 / max(1, args.steps + args.warmup))
+        vals.append(rate)
+        info = (P, kind, sample)
+    vals = vals[args.warmup:]
+    value = float(np.mean(vals))
+    line = {
+        "impl": "reference", "metric": "hpsi_gridpt_orbital_updates_per_s", "value": value,
+        "unit": "updates/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": args.dtype, "data": "synthetic",
+        "config": {"workload": desc, "lap_type": lap_type, "grid": list(dims),
+                   "orbitals": norb},
+        "cpu_baseline": {"value": value, "unit": "updates/s", "cores": info[0],
+                         "kind": info[1], "sample": info[2]},
+        "e2e": {"value": value, "unit": "updates/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from mgmol_b200 import host as H
+    from mgmol_b200._lib import lib, check
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    comm = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        from mgmol_b200.parallel import Communicator
+        comm = Communicator(rank, world)
+
+    dims, cell, norb, lap_default, desc = WORKLOADS[args.workload]
+    if args.orbitals:
+        norb = args.orbitals
+    lap_type = lap_default if args.lap is None else args.lap
+    tdt = torch.float64 if args.dtype == "f64" else torch.float32
+    S = 8 if args.dtype == "f64" else 4
+    g = H.ghosts_for(lap_type)
+    gdims = (dims[0] * world, dims[1], dims[2])
+    grid = H.Grid(gdims, (cell * world, cell, cell), g, (1, 1, 1), (world, 1, 1), (rank, 0, 0))
+    npt = grid.size()
+
+    gen = torch.Generator(device="cuda").manual_seed(1234 + rank)
+    phi = H.Orbitals(grid, norb, tdt)
+    x = torch.arange(dims[2], device="cuda", dtype=torch.float64) / dims[2]
+    for j in range(norb):
+        phi.psi()[j] = (0.1 * (torch.rand(dims, generator=gen, device="cuda",
+                                          dtype=torch.float64) * 2 - 1)
+                        + torch.cos(2 * np.pi * ((j % 5) + 1) * x)[None, None, :]).to(tdt)
+    vtot = (torch.rand(dims, generator=gen, device="cuda", dtype=torch.float64) * 0.1 - 0.75)
+    ham = H.Hamiltonian()
+    ham.setup(grid, lap_type)
+    ham.potential(H.Potentials(vtot))
+
+    xh_phi = xh_v = None
+    if world > 1:
+        xh_phi = torch.zeros((norb, 2 * g) + dims[1:], dtype=tdt, device="cuda")
+        xh_v = torch.zeros((1, 2 * g) + dims[1:], dtype=torch.float64, device="cuda")
+        comm.halo_exchange_x(grid, g, vtot[None], xh_v)
+
+    def step():
+        if world > 1:
+            comm.halo_exchange_x(grid, g, phi.psi(), xh_phi)
+        return ham.applyLocal(phi, True, xh_phi, xh_v)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    n0 = lib().mgb_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    barrier()
+    launches = lib().mgb_launch_count() - n0
+    ms = ev0.elapsed_time(ev1)
+    path = lib().mgb_hpsi_last_path()
+
+    # kernel-only duration (no halo exchange) for the roofline
+    evs = []
+    for _ in range(min(args.steps, 10)):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        ham.applyLocal(phi, True, xh_phi, xh_v)
+        b.record()
+        evs.append((a, b))
+    torch.cuda.synchronize()
+    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+    clocks = sampler.summary() if sampler else None
+
+    # end-to-end through the plugin call with HOST buffers: pinned H2D of the
+    # orbital block, H psi, D2H of the result, all inside the timed region
+    h_phi = torch.empty(phi.psi().shape, dtype=tdt).pin_memory()
+    h_phi.copy_(phi.psi())
+    h_out = torch.empty_like(h_phi).pin_memory()
+    e2e_steps = max(2, min(args.steps, 5))
+
+    def e2e_step():
+        phi.psi().copy_(h_phi, non_blocking=True)
+        out = step()
+        h_out.copy_(out.psi(), non_blocking=True)
+
+    e2e_step()
+    barrier()
+    ev0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    ev1.record()
+    barrier()
+    e2e_ms = ev0.elapsed_time(ev1)
+
+    t = torch.tensor([ms, e2e_ms, kern_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_ms, kern_ms = (float(v) for v in t.cpu())
+
+    if rank == 0:
+        updates_per_step = float(npt) * norb * world
+        value = updates_per_step * args.steps / (ms * 1e-3)
+        e2e = updates_per_step * e2e_steps / (e2e_ms * 1e-3)
+        peak, peak_src = measured_peaks()
+        achieved = 2.0 * S * npt * norb / (kern_ms * 1e-3) / 1e9
+        cpu_rate, cores, kind, sample = cpu_hpsi_rate(
+            lap_type, dims, (cell,) * 3, np.float64 if args.dtype == "f64" else np.float32)
+        line = {
+            "metric": "hpsi_gridpt_orbital_updates_per_s", "value": value, "unit": "updates/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": desc, "lap_type": lap_type, "grid_per_gpu": list(dims),
+                       "orbitals": norb, "decomposition": "%dx1x1" % world,
+                       "hpsi_path": {1: "tma_fused", 2: "generic_fused", 3: "ghosted"}.get(path),
+                       "l2": "inputs larger than L2 (%.1f GB per step)" %
+                             (2.0 * S * npt * norb / 1e9)},
+            "e2e": {"value": e2e, "unit": "updates/s",
+                    "h2d_bytes_per_step": int(S * npt * norb),
+                    "d2h_bytes_per_step": int(S * npt * norb)},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None,
+                         "kernel": "k_hpsi_tma" if path == 1 else "k_hpsi_generic",
+                         "kernel_ms": kern_ms, "peak_source": peak_src,
+                         "algorithmic_bytes_per_update": 2 * S},
+            "cpu_baseline": {"value": cpu_rate, "unit": "updates/s", "cores": cores,
+                             "kind": kind, "sample": sample},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="h2o64", choices=sorted(WORKLOADS))
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--lap", type=int, default=None)
+    ap.add_argument("--orbitals", type=int, default=0)
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,243 @@
+/*
+ * mgmol_b200 -- C ABI of the B200-native orbital-update hot path of MGmol.
+ *
+ * This is the drop-in boundary: a C++ host (MGmol's own classes, specialised
+ * for MemorySpace::Device) calls these entry points with plain device
+ * pointers.  Every entry point names the reference interface it backs
+ * (file:line into the MGmol source tree).  See INTEGRATION.md for the
+ * reference-side stubs.
+ *
+ * Conventions
+ *  - All array pointers are DEVICE pointers unless the name says host.
+ *  - Orbital blocks without ghosts: column-major npt x nfunc, leading dimension
+ *    `ld` (>= npt) elements, point (ix,iy,iz) at ix*ny*nz + iy*nz + iz
+ *    (BlockVector storage, src/BlockVector.cc:79, src/pb/GridFunc.cc:610-626).
+ *  - Ghosted blocks: nfunc x sizeg, function k at k*sizeg, point (ix,iy,iz) at
+ *    (ix+g)*inc0 + (iy+g)*inc1 + iz+g with inc1 = nz+2g, inc0 = (ny+2g)*inc1
+ *    (pb::GridFuncVector, src/pb/GridFuncVector.h:222-225, src/pb/Grid.cc:80-82).
+ *  - dtype: MGB_F32 / MGB_F64 = ORBDTYPE float / double (src/global.h:18-22).
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default
+ *    stream).  Calls are asynchronous with respect to the host; like the
+ *    reference's single MAGMA queue (src/magma_singleton.h:32-33) all work
+ *    of one call is ordered on that one stream.
+ *  - Return value: MGB_OK (0) or a negative MGB_E* code; mgb_last_error()
+ *    gives the message.  The reference aborts on these conditions
+ *    (src/pb/Lap.h:37-38, src/pb/FDkernels.h:42-45); the C++ shim is expected
+ *    to do the same on a non-zero return.
+ *  - There is NO CPU fallback: without a CUDA device every compute entry
+ *    point returns MGB_ENODEVICE.
+ */
+#ifndef MGMOL_B200_H
+#define MGMOL_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MGB_OK 0
+#define MGB_EINVAL (-1)      /* bad argument (reference: assert / abort)      */
+#define MGB_ENOTSUP (-2)     /* valid in the reference, not built here        */
+#define MGB_ECUDA (-3)       /* CUDA runtime / driver error                   */
+#define MGB_ENODEVICE (-4)   /* no CUDA device                                */
+#define MGB_ENCCL (-5)       /* NCCL error                                    */
+
+#define MGB_F32 0
+#define MGB_F64 1
+
+/* lap_type values of LapFactory<T>::createLap (src/LapFactory.h:26-56) */
+#define MGB_LAP_4M 0   /* Laph4M  : 4th-order Mehrstellen (default FDtype) */
+#define MGB_LAP_2 1    /* Laph2   : 2nd order (MG coarse levels)           */
+#define MGB_LAP_4 2    /* Laph4   : classical 4th order                    */
+#define MGB_LAP_6 3    /* Laph6                                             */
+#define MGB_LAP_8 4    /* Laph8                                             */
+#define MGB_LAP_4MP 10 /* Laph4MP : SPD Mehrstellen (same A, other B)      */
+
+/* FD kernel selector for mgb_fd_apply */
+#define MGB_FD_DEL2_4TH_MEHR 0
+#define MGB_FD_DEL2_2ND 1
+#define MGB_FD_DEL2_4TH 2
+#define MGB_FD_DEL2_6TH 3
+#define MGB_FD_DEL2_8TH 4
+#define MGB_FD_RHS_4TH_MEHR1 100
+
+/*
+ * Local box of one rank: the data pb::Grid + pb::PEenv carry
+ * (src/pb/Grid.h:24-121, src/pb/PEenv.h:34-203).
+ */
+typedef struct mgb_grid
+{
+    int dim[3];    /* local dims nx,ny,nz            (Grid::dim)            */
+    int gdim[3];   /* global dims                    (Grid::gdim)           */
+    int ghosts;    /* ghost width of ghosted blocks  (Grid::ghost_pt)       */
+    double h[3];   /* mesh spacing                   (Grid::hgrid)          */
+    int bc[3];     /* 1 periodic, 0 Dirichlet-0      (ct.bcWF)              */
+    int nproc[3];  /* ranks per direction            (PEenv::n_mpi_task)    */
+    int coord[3];  /* this rank's coordinates        (PEenv::my_mpi)        */
+} mgb_grid;
+
+const char* mgb_last_error(void);
+int mgb_version(void);
+/* number of kernels launched by this library since load (all streams) */
+unsigned long long mgb_launch_count(void);
+int mgb_device_count(void);
+
+/* ---- memory: MemorySpace::Memory<T,Device> (src/tools/memory_space.h:253-333)
+ *      allocate / free / copy_to_dev / copy_to_host / set                    */
+int mgb_malloc(void** dptr, size_t bytes);
+int mgb_free(void* dptr);
+int mgb_copy_to_dev(void* dst_dev, const void* src_host, size_t bytes, void* stream);
+int mgb_copy_to_host(void* dst_host, const void* src_dev, size_t bytes, void* stream);
+int mgb_copy_dev(void* dst_dev, const void* src_dev, size_t bytes, void* stream);
+int mgb_memset(void* dptr, int value, size_t bytes, void* stream);
+int mgb_stream_sync(void* stream);
+
+/* ---- batched FD kernels on ghosted blocks
+ * FDkernelDel2_{2nd,4th,4th_Mehr,6th,8th}(grid, v, b, nfunc, Device) and
+ * FDkernelRHS_4th_Mehr1(grid, v, rhs, rhs_ghosts, nfunc, Device)
+ * (src/pb/FDkernels.h:14-75; Host bodies src/pb/FDkernels.cc:18-584).
+ * v: nfunc x sizeg ghosted, ghosts already exchanged.  out: interior written,
+ * ghosted with grid->ghosts (or `rhs_ghosts` for the RHS kernel; 0 = no-ghost
+ * npt x nfunc output).                                                       */
+int mgb_fd_apply(int kind, int dtype, const mgb_grid* grid, const void* v,
+    void* out, int nfunc, int rhs_ghosts, void* stream);
+
+/* ---- fused local Hamiltonian
+ * Hamiltonian<T>::applyLocal(ncolors, phi, hphi) body (src/Hamiltonian.cc:
+ * 85-159) and Lap<T>::applyWithPot (src/pb/Lap.h:35, src/pb/FDoper.cc:321-399):
+ *   lap_type 0/10: hphi = A_Mehr phi + B (vtot .* phi)     (:106-132)
+ *   lap_type 2   : hphi = A_4th  phi + vtot .* phi         (:133-156)
+ * phi, hphi: no-ghost npt x nfunc blocks (ld elements apart); vtot: POTDTYPE
+ * double[npt] without ghosts (src/Potentials.h:141).  One pass over phi: the
+ * ghost-add, halo, V*psi, B, Laplacian, axpy and ghost-strip sweeps of the
+ * reference are fused.  Directions with nproc > 1 take their neighbour planes
+ * from the halo set given by mgb_halo_* (x split only on the fused path; y/z
+ * splits go through the ghosted-block composition below).
+ * xhalo_phi / xhalo_v: NULL when grid->nproc[0]==1; otherwise device buffers
+ * [nfunc][2g][ny][nz] (phi) and [2g][ny][nz] (vtot): the g planes below the
+ * box then the g planes above it, as filled by mgb_halo_exchange_x.         */
+int mgb_hpsi(int lap_type, int dtype, const mgb_grid* grid, const void* phi,
+    size_t ld, const double* vtot, void* hphi, size_t ldh, int nfunc,
+    const void* xhalo_phi, const double* xhalo_v, void* stream);
+
+/* Which implementation mgb_hpsi picked last (for tests and the bench):
+ * 1 TMA-pipelined fused kernel, 2 generic fused kernel, 3 ghosted-block
+ * composition.                                                              */
+int mgb_hpsi_last_path(void);
+/* Force a path (0 = automatic).  Test hook. */
+int mgb_hpsi_force_path(int path);
+
+/* ---- GridFuncVector<T,Device> batch operations (src/pb/GridFuncVector.h:
+ *      445-479) on ghosted blocks                                           */
+/* BlockVector::setDataWithGhosts + GridFunc::assign (src/BlockVector.cc:
+ * 489-517, src/pb/GridFunc.cc:577-630): zero the block, copy interiors in,
+ * converting in_dtype -> out_dtype.                                         */
+int mgb_gfv_set_with_ghosts(int in_dtype, int out_dtype, const mgb_grid* grid,
+    const void* noghost, size_t ld, void* ghosted, int nfunc, void* stream);
+/* BlockVector::assign(GridFuncVector) + GridFunc::getValues
+ * (src/BlockVector.cc:303-311, src/pb/GridFunc.cc:1457-1496)               */
+int mgb_gfv_get_values(int in_dtype, int out_dtype, const mgb_grid* grid,
+    const void* ghosted, void* noghost, size_t ld, int nfunc, void* stream);
+/* GridFuncVector::trade_boundaries (src/pb/GridFuncVector.cc:1544-1622) for
+ * directions owned by a single rank: Dirichlet zeroing (src/pb/GridFunc.cc:
+ * 2192-2336) then the local periodic wraps in Y, Z, X order (:586-603).
+ * Directions with nproc > 1 are exchanged by mgb_halo_exchange_ghosted.     */
+int mgb_gfv_trade_boundaries(int dtype, const mgb_grid* grid, void* ghosted,
+    int nfunc, void* stream);
+/* GridFuncVector::pointwiseProduct (src/pb/GridFuncVector.cc:90-136):
+ * out_j = A_j .* V over the whole ghosted extent, V a ghosted double field. */
+int mgb_gfv_pointwise_product(int dtype, const mgb_grid* grid, const void* A,
+    const double* Vghost, void* out, int nfunc, void* stream);
+/* GridFuncVector::axpy / operator-= (src/pb/GridFuncVector.cc:1645-1668) =
+ * MPaxpy over nfunc*sizeg elements (n given explicitly).                    */
+int mgb_axpy(int dtype, size_t n, double alpha, const void* x, void* y, void* stream);
+/* LinearAlgebraUtils::MPscal / MPdot (src/linear_algebra/mputils.cc:53-215) */
+int mgb_scal(int dtype, size_t n, double alpha, void* x, void* stream);
+int mgb_dot(int dtype, size_t n, const void* x, const void* y, double* result_dev,
+    void* stream);
+/* GridFuncVector::jacobi (src/pb/GridFuncVector.cc:2416-2425):
+ * w = A v ; w -= f ; v += -omega w, v's ghosts must be up to date.          */
+int mgb_gfv_jacobi(int lap_type, const mgb_grid* grid, float* v, const float* f,
+    float* w, int nfunc, double omega, void* stream);
+/* GridFuncVector::restrict3D / extend3D (src/pb/GridFuncVector.cc:1624-1641,
+ * kernels src/pb/MGkernels.cc:28-283).  `fine` describes the fine grid; the
+ * coarse grid is dims/2 with the same ghost width (src/pb/Grid.cc:214-231).
+ * Ghosts of the source block must be up to date.                            */
+int mgb_gfv_restrict3D(int dtype, const mgb_grid* fine, const void* ufine,
+    void* ucoarse, int nfunc, void* stream);
+int mgb_gfv_extend3D(int dtype, const mgb_grid* fine, const void* ucoarse,
+    void* ufine, int nfunc, void* stream);
+
+/* ---- multigrid preconditioner
+ * Preconditioning<float> (src/Preconditioning.h:22-64, .cc:15-216) and
+ * OrbitalsPreconditioning<T>::precond_mg / setGamma
+ * (src/OrbitalsPreconditioning.cc:87-145).  The handle owns the float work
+ * blocks of every level (v, f, work, rcoarse, newv).                        */
+typedef struct mgb_precond mgb_precond;
+int mgb_precond_create(mgb_precond** out, int lap_type, int mg_levels,
+    const mgb_grid* grid, int nfunc_max);
+int mgb_precond_destroy(mgb_precond* p);
+/* res (no-ghost, dtype) <- M^-1 res : v0 = gamma*res, mg(v, f=res) in float */
+int mgb_precond_mg(mgb_precond* p, int dtype, void* res, size_t ld, int nfunc,
+    double gamma, void* stream);
+/* Preconditioning<float>::mg on caller-owned ghosted float blocks           */
+int mgb_precond_vcycle(mgb_precond* p, float* v, const float* f, int nfunc,
+    void* stream);
+/* diagEl, invDiagEl, jacobiFactor of pb::Lap (src/pb/Laph4M.h:80,
+ * Laph4.h:106, Laph2.h:95); out[3] on host.                                 */
+int mgb_lap_constants(int lap_type, const double h[3], double out[3]);
+/* OrbitalsPreconditioning::setGamma arithmetic (host)                       */
+double mgb_gamma(double inv_diag, int mg_levels, double vmax, double small_eig);
+
+/* ---- dense contractions: LinearAlgebraUtils<Device>::MPgemm / MPsyrk /
+ *      MPgemmNN (src/linear_algebra/mputils.cc:295-1067), as the Orbitals
+ *      classes call them.                                                   */
+/* C(m x n, double, ldc) = alpha * A^T B + beta C, A: k x m (lda), B: k x n
+ * (ldb), both `dtype`, accumulated in double.  ExtendedGridOrbitals::
+ * computeLocalProduct (src/ExtendedGridOrbitals.cc:1049-1083), getLocalOverlap
+ * / computeGram (:985-1010) with A==B, addDotWithNcol2Matrix (:1704-1752).  */
+int mgb_gemm_tn(int dtype, int m, int n, size_t k, double alpha, const void* A,
+    size_t lda, const void* B, size_t ldb, double beta, double* C, int ldc,
+    void* stream);
+/* Gram: C = alpha * A^T A (full symmetric matrix written, as
+ * syrk('l','t') + fillUpperWithLower do, src/local_matrices/LocalMatrices.cc:
+ * 210-247)                                                                  */
+int mgb_syrk_t(int dtype, int n, size_t k, double alpha, const void* A,
+    size_t lda, double* C, int ldc, void* stream);
+/* Cout(m x n, dtype, ldc) = alpha * A(m x k, dtype, lda) * M(k x n, double,
+ * ldm) + beta*Cout : ExtendedGridOrbitals::multiplyByMatrix
+ * (src/ExtendedGridOrbitals.cc:448-498), MPgemmNN.  Cout must not alias A.  */
+int mgb_gemm_nn(int dtype, size_t m, int n, int k, double alpha, const void* A,
+    size_t lda, const double* M, int ldm, double beta, void* Cout, size_t ldc,
+    void* stream);
+
+/* ---- multi-GPU: one process per GPU, 3-D block decomposition of pb::PEenv.
+ * The communicator wraps NCCL; the unique id (128 bytes) is created on rank 0
+ * with mgb_comm_unique_id and distributed by the caller (MPI_Bcast in MGmol,
+ * torch.distributed in the tests).                                          */
+typedef struct mgb_comm mgb_comm;
+int mgb_comm_unique_id(void* id128);
+int mgb_comm_create(mgb_comm** out, const void* id128, int rank, int nranks);
+int mgb_comm_destroy(mgb_comm* c);
+/* MGmol_MPI::allreduce(double*, n, MPI_SUM) at src/ExtendedGridOrbitals.cc:
+ * 1746 and ReplicatedMatrix::consolidate (src/ReplicatedMatrix.cc:108-127):
+ * in-place sum of a device array over all ranks.                            */
+int mgb_allreduce_sum_f64(mgb_comm* c, double* data, size_t n, void* stream);
+/* x-direction halo for the fused H path: sends this rank's first/last g
+ * planes of every function to the west/east neighbours and fills
+ * xhalo[nfunc][2g][ny][nz] (replaces initiate/finishEastWestComm,
+ * src/pb/GridFuncVector.cc:1195-1256, for no-ghost blocks).                 */
+int mgb_halo_exchange_x(mgb_comm* c, int dtype, const mgb_grid* grid, int g,
+    const void* noghost, size_t ld, void* xhalo, int nfunc, void* stream);
+/* GridFuncVector::trade_boundaries for a ghosted block on a general
+ * px x py x pz decomposition: Y, then Z, then X faces (src/pb/
+ * GridFuncVector.cc:1544-1622) so edges and corners propagate.              */
+int mgb_halo_exchange_ghosted(mgb_comm* c, int dtype, const mgb_grid* grid,
+    void* ghosted, int nfunc, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* MGMOL_B200_H */

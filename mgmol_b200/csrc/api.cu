@@ -1,0 +1,301 @@
+// C-ABI glue: error state, device memory (MemorySpace::Memory<T,Device>), the
+// mgb_hpsi dispatcher and its reference-shaped composition on ghosted blocks.
+#include <cstdarg>
+#include <cstring>
+#include <mutex>
+
+#include "hpsi.h"
+
+namespace mgb
+{
+
+std::atomic<unsigned long long> g_launch_count{ 0 };
+static thread_local char g_err[512] = "";
+static int g_last_path  = 0;
+static int g_force_path = 0;
+
+void set_error(const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int require_device()
+{
+    static int state = 0; // 0 unknown, 1 ok, -1 none
+    if (state == 0)
+    {
+        int n         = 0;
+        cudaError_t e = cudaGetDeviceCount(&n);
+        state         = (e == cudaSuccess && n > 0) ? 1 : -1;
+        if (state < 0) (void)cudaGetLastError();
+    }
+    if (state < 0)
+    {
+        set_error("no CUDA device: mgmol_b200 has no CPU fallback");
+        return MGB_ENODEVICE;
+    }
+    return MGB_OK;
+}
+
+int check_grid(const mgb_grid* gr)
+{
+    MGB_REQUIRE(gr != nullptr, "grid is null");
+    for (int d = 0; d < 3; d++)
+    {
+        MGB_REQUIRE(gr->dim[d] > 0 && gr->dim[d] < 10000,
+            "grid dim[%d]=%d out of range", d, gr->dim[d]); // pb/Grid.cc:33-35
+        MGB_REQUIRE(gr->h[d] > 1.e-8, "grid h[%d] too small", d);
+        MGB_REQUIRE(gr->bc[d] == 0 || gr->bc[d] == 1,
+            "bc[%d]=%d: only periodic (1) and Dirichlet-0 (0) orbitals' "
+            "boundary conditions are supported",
+            d, gr->bc[d]);
+        MGB_REQUIRE(gr->nproc[d] >= 1 && gr->coord[d] >= 0
+                        && gr->coord[d] < gr->nproc[d],
+            "bad process coordinates in direction %d", d);
+    }
+    MGB_REQUIRE(gr->ghosts >= 0 && gr->ghosts < 10, "bad ghost width %d",
+        gr->ghosts); // pb/Grid.h:80
+    return MGB_OK;
+}
+
+// grow-only scratch slots
+static void* g_scratch[8]      = { nullptr };
+static size_t g_scratch_sz[8]  = { 0 };
+static std::mutex g_scratch_mu;
+void* scratch(int slot, size_t bytes)
+{
+    std::lock_guard<std::mutex> lk(g_scratch_mu);
+    if (bytes <= g_scratch_sz[slot]) return g_scratch[slot];
+    if (g_scratch[slot]) cudaFree(g_scratch[slot]); // implicit device sync
+    g_scratch[slot]    = nullptr;
+    g_scratch_sz[slot] = 0;
+    void* p            = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess)
+    {
+        set_error("scratch allocation of %zu bytes failed", bytes);
+        (void)cudaGetLastError();
+        return nullptr;
+    }
+    g_scratch[slot]    = p;
+    g_scratch_sz[slot] = bytes;
+    return p;
+}
+
+// Path 3: the reference's own sequence (src/Hamiltonian.cc:101-156) on ghosted
+// blocks, built from the bit-exact batch kernels.  Used for mixed boundary
+// conditions and boxes the fused kernels do not take; y/z splits additionally
+// need mgb_halo_exchange_ghosted between set_with_ghosts and the stencils and
+// are driven by the host wrapper, not from here.
+int hpsi_ghosted(const HpsiArgs& a, cudaStream_t st)
+{
+    const mgb_grid* gr0 = a.grid;
+    MGB_REQUIRE(gr0->nproc[0] == 1 && gr0->nproc[1] == 1 && gr0->nproc[2] == 1,
+        "mgb_hpsi: the ghosted-block composition handles single-rank boxes; "
+        "for split directions exchange halos with mgb_halo_exchange_ghosted "
+        "and call the mgb_gfv_* / mgb_fd_apply entry points");
+    mgb_grid gr = *gr0;
+    gr.ghosts   = a.g;
+    Box b       = box_of(&gr, a.g);
+    const size_t es   = a.dtype == MGB_F64 ? 8 : 4;
+    const size_t blk  = (size_t)b.sizeg * a.nfunc * es;
+    void* stream      = (void*)st;
+    unsigned char* ws = (unsigned char*)scratch(1, 3 * blk + (size_t)b.sizeg * 8);
+    if (!ws) return MGB_ECUDA;
+    void* gphi   = ws;
+    void* w1     = ws + blk;
+    void* work1  = ws + 2 * blk;
+    double* gpot = (double*)(ws + 3 * blk);
+    int rc;
+    // phi.setDataWithGhosts(); phi.trade_boundaries();            (:101-102)
+    if ((rc = mgb_gfv_set_with_ghosts(
+             a.dtype, a.dtype, &gr, a.phi, a.ld, gphi, a.nfunc, stream)))
+        return rc;
+    if ((rc = mgb_gfv_trade_boundaries(a.dtype, &gr, gphi, a.nfunc, stream)))
+        return rc;
+    if (a.lap_type == MGB_LAP_4)
+        // per-orbital Laph4::applyWithPot                          (:138-155)
+        return del2_4th_withpot(
+            a.dtype, &gr, gphi, a.vtot, a.hphi, a.ldh, a.nfunc, st);
+    // gfpot.assign(vtot); gfpot.trade_boundaries();               (:108-111)
+    if ((rc = mgb_gfv_set_with_ghosts(
+             MGB_F64, MGB_F64, &gr, a.vtot, (size_t)b.npt, gpot, 1, stream)))
+        return rc;
+    if ((rc = mgb_gfv_trade_boundaries(MGB_F64, &gr, gpot, 1, stream))) return rc;
+    // gfvw1.pointwiseProduct(gfvphi, gfpot)                        (:117)
+    if ((rc = mgb_gfv_pointwise_product(a.dtype, &gr, gphi, gpot, w1, a.nfunc, stream)))
+        return rc;
+    // gfv_work1 (fresh, zeroed) = B * gfvw1                        (:119-122)
+    if ((rc = mgb_memset(work1, 0, blk, stream))) return rc;
+    if ((rc = mgb_fd_apply(
+             MGB_FD_RHS_4TH_MEHR1, a.dtype, &gr, w1, work1, a.nfunc, a.g, stream)))
+        return rc;
+    // gfvw1 = -Lap phi                                             (:127)
+    if ((rc = mgb_fd_apply(
+             MGB_FD_DEL2_4TH_MEHR, a.dtype, &gr, gphi, w1, a.nfunc, 0, stream)))
+        return rc;
+    // gfv_work1.axpy(1., gfvw1)                                    (:129)
+    if ((rc = mgb_axpy(a.dtype, (size_t)b.sizeg * a.nfunc, 1., w1, work1, stream)))
+        return rc;
+    // hphi.setPsi(gfv_work1)                                       (:131)
+    return mgb_gfv_get_values(
+        a.dtype, a.dtype, &gr, work1, a.hphi, a.ldh, a.nfunc, stream);
+}
+
+} // namespace mgb
+
+using namespace mgb;
+
+extern "C"
+{
+
+const char* mgb_last_error(void) { return g_err; }
+int mgb_version(void) { return 100; }
+unsigned long long mgb_launch_count(void)
+{
+    return g_launch_count.load(std::memory_order_relaxed);
+}
+int mgb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess)
+    {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int mgb_malloc(void** dptr, size_t bytes)
+{
+    if (int rc = require_device()) return rc;
+    MGB_REQUIRE(dptr, "mgb_malloc: null out pointer");
+    MGB_CUDA(cudaMalloc(dptr, bytes ? bytes : 1));
+    return MGB_OK;
+}
+int mgb_free(void* dptr)
+{
+    if (!dptr) return MGB_OK;
+    MGB_CUDA(cudaFree(dptr));
+    return MGB_OK;
+}
+int mgb_copy_to_dev(void* dst, const void* src, size_t bytes, void* stream)
+{
+    if (int rc = require_device()) return rc;
+    MGB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, as_stream(stream)));
+    return MGB_OK;
+}
+int mgb_copy_to_host(void* dst, const void* src, size_t bytes, void* stream)
+{
+    if (int rc = require_device()) return rc;
+    MGB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, as_stream(stream)));
+    return MGB_OK;
+}
+int mgb_copy_dev(void* dst, const void* src, size_t bytes, void* stream)
+{
+    if (int rc = require_device()) return rc;
+    MGB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, as_stream(stream)));
+    return MGB_OK;
+}
+int mgb_memset(void* dptr, int value, size_t bytes, void* stream)
+{
+    if (int rc = require_device()) return rc;
+    MGB_CUDA(cudaMemsetAsync(dptr, value, bytes, as_stream(stream)));
+    return MGB_OK;
+}
+int mgb_stream_sync(void* stream)
+{
+    if (int rc = require_device()) return rc;
+    MGB_CUDA(cudaStreamSynchronize(as_stream(stream)));
+    return MGB_OK;
+}
+
+int mgb_hpsi_last_path(void) { return g_last_path; }
+int mgb_hpsi_force_path(int path)
+{
+    MGB_REQUIRE(path >= 0 && path <= 3, "mgb_hpsi_force_path: path %d", path);
+    g_force_path = path;
+    return MGB_OK;
+}
+
+int mgb_hpsi(int lap_type, int dtype, const mgb_grid* grid, const void* phi,
+    size_t ld, const double* vtot, void* hphi, size_t ldh, int nfunc,
+    const void* xhalo_phi, const double* xhalo_v, void* stream)
+{
+    if (int rc = require_device()) return rc;
+    if (int rc = check_grid(grid)) return rc;
+    MGB_REQUIRE(phi && vtot && hphi, "mgb_hpsi: null pointer");
+    MGB_REQUIRE(phi != hphi, "mgb_hpsi: hphi must not alias phi");
+    MGB_REQUIRE(dtype == MGB_F32 || dtype == MGB_F64, "mgb_hpsi: bad dtype %d", dtype);
+    MGB_REQUIRE(nfunc >= 0, "mgb_hpsi: nfunc < 0");
+    // Only Laph4M, Laph4MP and Laph4 can apply H: the other operators have no
+    // applyWithPot and the reference aborts (src/pb/Lap.h:35-39).
+    MGB_REQUIRE(lap_type == MGB_LAP_4M || lap_type == MGB_LAP_4MP
+                    || lap_type == MGB_LAP_4,
+        "mgb_hpsi: lap_type %d has no applyWithPot (Lap::applyWithPot aborts)",
+        lap_type);
+    const size_t npt = (size_t)grid->dim[0] * grid->dim[1] * grid->dim[2];
+    MGB_REQUIRE(ld >= npt && ldh >= npt, "mgb_hpsi: leading dimension < npt");
+    if (nfunc == 0) return MGB_OK;
+
+    HpsiArgs a;
+    a.lap_type  = lap_type;
+    a.dtype     = dtype;
+    a.grid      = grid;
+    a.g         = (lap_type == MGB_LAP_4) ? 2 : 1;
+    a.phi       = phi;
+    a.ld        = ld;
+    a.vtot      = vtot;
+    a.hphi      = hphi;
+    a.ldh       = ldh;
+    a.nfunc     = nfunc;
+    a.xhalo_phi = xhalo_phi;
+    a.xhalo_v   = xhalo_v;
+    cudaStream_t st = as_stream(stream);
+
+    const bool uniform_bc = (grid->bc[0] == grid->bc[1] && grid->bc[1] == grid->bc[2]);
+    const bool yz_single  = grid->nproc[1] == 1 && grid->nproc[2] == 1;
+    MGB_REQUIRE(grid->nproc[0] == 1 || (xhalo_phi && xhalo_v),
+        "mgb_hpsi: x is split over %d ranks but no x-halo buffers were given",
+        grid->nproc[0]);
+    MGB_REQUIRE(grid->dim[0] >= a.g && grid->dim[1] >= a.g && grid->dim[2] >= a.g,
+        "mgb_hpsi: local dims smaller than the stencil radius");
+
+    if (uniform_bc && yz_single)
+    {
+        if (g_force_path == 0 || g_force_path == 1)
+        {
+            int rc = hpsi_tma(a, st);
+            if (rc == MGB_OK)
+            {
+                g_last_path = 1;
+                return MGB_OK;
+            }
+            if (rc != MGB_ENOTSUP) return rc;
+            if (g_force_path == 1)
+            {
+                set_error("mgb_hpsi: box not eligible for the TMA kernel");
+                return MGB_ENOTSUP;
+            }
+        }
+        if (g_force_path == 0 || g_force_path == 2)
+        {
+            g_last_path = 2;
+            return hpsi_generic(a, st);
+        }
+    }
+    if (g_force_path == 1 || g_force_path == 2)
+    {
+        set_error("mgb_hpsi: forced path %d cannot serve this box", g_force_path);
+        return MGB_ENOTSUP;
+    }
+    MGB_REQUIRE(yz_single,
+        "mgb_hpsi: y/z are split over ranks; use the ghosted-block entry "
+        "points with mgb_halo_exchange_ghosted");
+    g_last_path = 3;
+    return hpsi_ghosted(a, st);
+}
+
+} // extern "C"

@@ -1,0 +1,384 @@
+// Multi-GPU exchange for the hot path: one process per GPU, the 3-D block
+// decomposition of pb::PEenv (src/pb/PEenv.cc:56-139), NCCL over NVLink for
+//   * the x-direction halo planes feeding the fused H kernel,
+//   * the Y -> Z -> X ghost exchange of a ghosted block
+//     (GridFuncVector::trade_boundaries, src/pb/GridFuncVector.cc:1544-1622),
+//   * the all-reduce of partial N x N matrices
+//     (MGmol_MPI::allreduce at src/ExtendedGridOrbitals.cc:1746).
+// NCCL is loaded with dlopen so that the library also loads on a single-GPU
+// host that has no NCCL (under PyTorch the already-loaded libnccl.so.2 is
+// reused).
+#include <dlfcn.h>
+
+#include <cstring>
+#include <mutex>
+
+#include "hpsi.h"
+
+// minimal NCCL surface (matches nccl.h 2.x; no header dependency at build)
+typedef struct ncclComm* ncclComm_t;
+typedef struct
+{
+    char internal[128];
+} ncclUniqueId;
+typedef int ncclResult_t;
+enum
+{
+    kNcclFloat32 = 7,
+    kNcclFloat64 = 8,
+    kNcclSum     = 0
+};
+
+namespace mgb
+{
+struct Nccl
+{
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*)                                  = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int)           = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t)                                     = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t,
+        cudaStream_t)                                                           = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t)     = nullptr;
+    ncclResult_t (*GroupStart)()                                                = nullptr;
+    ncclResult_t (*GroupEnd)()                                                  = nullptr;
+    const char* (*GetErrorString)(ncclResult_t)                                 = nullptr;
+};
+
+static Nccl* nccl()
+{
+    static Nccl n;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const char* names[] = { "libnccl.so.2", "libnccl.so" };
+        for (const char* nm : names)
+        {
+            n.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+            if (n.handle) break;
+        }
+        if (!n.handle) return;
+#define MGB_SYM(field, name) *(void**)(&n.field) = dlsym(n.handle, name)
+        MGB_SYM(GetUniqueId, "ncclGetUniqueId");
+        MGB_SYM(CommInitRank, "ncclCommInitRank");
+        MGB_SYM(CommDestroy, "ncclCommDestroy");
+        MGB_SYM(AllReduce, "ncclAllReduce");
+        MGB_SYM(Send, "ncclSend");
+        MGB_SYM(Recv, "ncclRecv");
+        MGB_SYM(GroupStart, "ncclGroupStart");
+        MGB_SYM(GroupEnd, "ncclGroupEnd");
+        MGB_SYM(GetErrorString, "ncclGetErrorString");
+#undef MGB_SYM
+    });
+    if (!n.handle || !n.GetUniqueId || !n.CommInitRank || !n.AllReduce || !n.Send
+        || !n.Recv || !n.GroupStart || !n.GroupEnd)
+        return nullptr;
+    return &n;
+}
+
+#define MGB_NCCL(call)                                                         \
+    do                                                                         \
+    {                                                                          \
+        ncclResult_t r__ = (call);                                             \
+        if (r__ != 0)                                                          \
+        {                                                                      \
+            ::mgb::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call,     \
+                nccl()->GetErrorString ? nccl()->GetErrorString(r__) : "?");   \
+            return MGB_ENCCL;                                                  \
+        }                                                                      \
+    } while (0)
+
+} // namespace mgb
+
+struct mgb_comm
+{
+    ncclComm_t comm;
+    int rank, nranks;
+    void* buf[4];
+    size_t buf_sz[4];
+};
+
+namespace mgb
+{
+static void* comm_buf(mgb_comm* c, int i, size_t bytes)
+{
+    if (bytes <= c->buf_sz[i]) return c->buf[i];
+    if (c->buf[i]) cudaFree(c->buf[i]);
+    c->buf[i]    = nullptr;
+    c->buf_sz[i] = 0;
+    if (cudaMalloc(&c->buf[i], bytes) != cudaSuccess)
+    {
+        set_error("comm buffer allocation of %zu bytes failed", bytes);
+        (void)cudaGetLastError();
+        return nullptr;
+    }
+    c->buf_sz[i] = bytes;
+    return c->buf[i];
+}
+
+// rank of the process at Cartesian coordinates (row-major, as
+// MPI_Cart_create orders them; src/pb/PEenv.cc:89)
+static int rank_of(const mgb_grid* gr, int cx, int cy, int cz)
+{
+    const int px = gr->nproc[0], py = gr->nproc[1], pz = gr->nproc[2];
+    cx = (cx + px) % px;
+    cy = (cy + py) % py;
+    cz = (cz + pz) % pz;
+    return (cx * py + cy) * pz + cz;
+}
+
+// first / last g planes of every function of a no-ghost block -> packed
+// [nfunc][g][ny*nz] send buffers (one launch packs both sides)
+template <typename T>
+__global__ void k_pack_x(int nx, long long plane, int g, long long ld,
+    const T* __restrict__ u, T* __restrict__ lo, T* __restrict__ hi)
+{
+    const long long per = (long long)g * plane;
+    const long long t   = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= per) return;
+    const int f   = blockIdx.y;
+    const T* src  = u + (long long)f * ld;
+    lo[(long long)f * per + t] = src[t];                                  // x = 0..g-1
+    hi[(long long)f * per + t] = src[(long long)(nx - g) * plane + t];    // x = nx-g..nx-1
+}
+// received buffers -> xhalo[nfunc][2g][ny*nz] (g planes below, g planes above)
+template <typename T>
+__global__ void k_unpack_x(long long plane, int g, const T* __restrict__ from_west,
+    const T* __restrict__ from_east, T* __restrict__ xhalo, int have_w, int have_e)
+{
+    const long long per = (long long)g * plane;
+    const long long t   = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= per) return;
+    const int f = blockIdx.y;
+    T* dst      = xhalo + (long long)f * 2 * per;
+    dst[t]       = have_w ? from_west[(long long)f * per + t] : (T)0;
+    dst[per + t] = have_e ? from_east[(long long)f * per + t] : (T)0;
+}
+
+template <typename T>
+static int halo_x_t(mgb_comm* c, const mgb_grid* gr, int g, const T* u, size_t ld,
+    T* xhalo, int nfunc, cudaStream_t st)
+{
+    Nccl* N = nccl();
+    const int nx = gr->dim[0];
+    const long long plane = (long long)gr->dim[1] * gr->dim[2];
+    const size_t cnt      = (size_t)nfunc * g * plane;
+    const size_t bytes    = cnt * sizeof(T);
+    T* s_w = (T*)comm_buf(c, 0, bytes);
+    T* s_e = (T*)comm_buf(c, 1, bytes);
+    T* r_w = (T*)comm_buf(c, 2, bytes);
+    T* r_e = (T*)comm_buf(c, 3, bytes);
+    if (!s_w || !s_e || !r_w || !r_e) return MGB_ECUDA;
+    const bool periodic = gr->bc[0] == 1;
+    const bool have_w   = periodic || gr->coord[0] > 0;
+    const bool have_e   = periodic || gr->coord[0] < gr->nproc[0] - 1;
+    const int west = rank_of(gr, gr->coord[0] - 1, gr->coord[1], gr->coord[2]);
+    const int east = rank_of(gr, gr->coord[0] + 1, gr->coord[1], gr->coord[2]);
+    const int dt   = sizeof(T) == 8 ? kNcclFloat64 : kNcclFloat32;
+    for (int f0 = 0; f0 < nfunc; f0 += 65535)
+    {
+        const int nf = (nfunc - f0 < 65535) ? nfunc - f0 : 65535;
+        dim3 grid((unsigned)(((long long)g * plane + 255) / 256), (unsigned)nf);
+        k_pack_x<T><<<grid, 256, 0, st>>>(nx, plane, g, (long long)ld,
+            u + (size_t)f0 * ld, s_w + (size_t)f0 * g * plane,
+            s_e + (size_t)f0 * g * plane);
+        MGB_LAUNCHED("k_pack_x");
+    }
+    // Sends in the order west, east; receives in the order east, west: with two
+    // ranks both neighbours are the same peer and NCCL pairs the k-th send with
+    // the peer's k-th receive.
+    MGB_NCCL(N->GroupStart());
+    if (have_w) MGB_NCCL(N->Send(s_w, cnt, dt, west, c->comm, st));
+    if (have_e) MGB_NCCL(N->Send(s_e, cnt, dt, east, c->comm, st));
+    if (have_e) MGB_NCCL(N->Recv(r_e, cnt, dt, east, c->comm, st));
+    if (have_w) MGB_NCCL(N->Recv(r_w, cnt, dt, west, c->comm, st));
+    MGB_NCCL(N->GroupEnd());
+    for (int f0 = 0; f0 < nfunc; f0 += 65535)
+    {
+        const int nf = (nfunc - f0 < 65535) ? nfunc - f0 : 65535;
+        dim3 grid((unsigned)(((long long)g * plane + 255) / 256), (unsigned)nf);
+        k_unpack_x<T><<<grid, 256, 0, st>>>(plane, g, r_w + (size_t)f0 * g * plane,
+            r_e + (size_t)f0 * g * plane, xhalo + (size_t)f0 * 2 * g * plane,
+            have_w ? 1 : 0, have_e ? 1 : 0);
+        MGB_LAUNCHED("k_unpack_x");
+    }
+    return MGB_OK;
+}
+
+// One direction of the ghosted exchange: faces with the reference's extents
+// (Y: interior x and z; Z: interior x, all y; X: whole planes).
+static int exchange_dir(mgb_comm* c, int dtype, const mgb_grid* gr, void* u,
+    int nfunc, int d, cudaStream_t st)
+{
+    Nccl* N     = nccl();
+    const int g = gr->ghosts;
+    const int n[3]  = { gr->dim[0], gr->dim[1], gr->dim[2] };
+    // extents of a face slab in ghosted coordinates
+    int lo[3], ext[3];
+    lo[0] = g, ext[0] = n[0];
+    lo[1] = g, ext[1] = n[1];
+    lo[2] = g, ext[2] = n[2];
+    if (d == 2) lo[1] = 0, ext[1] = n[1] + 2 * g;
+    if (d == 0) lo[1] = 0, ext[1] = n[1] + 2 * g, lo[2] = 0, ext[2] = n[2] + 2 * g;
+    ext[d] = g;
+    const size_t es  = dtype == MGB_F64 ? 8 : 4;
+    const size_t cnt = (size_t)nfunc * ext[0] * ext[1] * ext[2];
+    void* s_lo = comm_buf(c, 0, cnt * es); // my low interior layers -> low neighbour
+    void* s_hi = comm_buf(c, 1, cnt * es);
+    void* r_lo = comm_buf(c, 2, cnt * es); // from low neighbour -> my low ghosts
+    void* r_hi = comm_buf(c, 3, cnt * es);
+    if (!s_lo || !s_hi || !r_lo || !r_hi) return MGB_ECUDA;
+    const bool periodic = gr->bc[d] == 1;
+    const bool have_lo  = periodic || gr->coord[d] > 0;
+    const bool have_hi  = periodic || gr->coord[d] < gr->nproc[d] - 1;
+    int cl[3] = { gr->coord[0], gr->coord[1], gr->coord[2] };
+    int ch[3] = { gr->coord[0], gr->coord[1], gr->coord[2] };
+    cl[d] -= 1;
+    ch[d] += 1;
+    const int rlo = rank_of(gr, cl[0], cl[1], cl[2]);
+    const int rhi = rank_of(gr, ch[0], ch[1], ch[2]);
+    const int dt  = dtype == MGB_F64 ? kNcclFloat64 : kNcclFloat32;
+    int rc;
+    int l[3] = { lo[0], lo[1], lo[2] };
+    l[d]     = g; // first interior layers
+    if ((rc = subbox_copy(dtype, true, gr, l, ext, u, s_lo, nfunc, st))) return rc;
+    l[d] = n[d]; // last interior layers (ghosted index n+g-g)
+    if ((rc = subbox_copy(dtype, true, gr, l, ext, u, s_hi, nfunc, st))) return rc;
+    MGB_NCCL(N->GroupStart());
+    if (have_lo) MGB_NCCL(N->Send(s_lo, cnt, dt, rlo, c->comm, st));
+    if (have_hi) MGB_NCCL(N->Send(s_hi, cnt, dt, rhi, c->comm, st));
+    if (have_hi) MGB_NCCL(N->Recv(r_hi, cnt, dt, rhi, c->comm, st));
+    if (have_lo) MGB_NCCL(N->Recv(r_lo, cnt, dt, rlo, c->comm, st));
+    MGB_NCCL(N->GroupEnd());
+    l[d] = 0; // low ghosts
+    if (have_lo)
+        if ((rc = subbox_copy(dtype, false, gr, l, ext, u, r_lo, nfunc, st))) return rc;
+    l[d] = n[d] + g; // high ghosts
+    if (have_hi)
+        if ((rc = subbox_copy(dtype, false, gr, l, ext, u, r_hi, nfunc, st))) return rc;
+    return MGB_OK;
+}
+
+} // namespace mgb
+
+using namespace mgb;
+
+extern "C"
+{
+
+int mgb_comm_unique_id(void* id128)
+{
+    MGB_REQUIRE(id128, "mgb_comm_unique_id: null pointer");
+    Nccl* N = nccl();
+    if (!N)
+    {
+        set_error("NCCL (libnccl.so.2) could not be loaded");
+        return MGB_ENCCL;
+    }
+    ncclUniqueId id;
+    MGB_NCCL(N->GetUniqueId(&id));
+    memcpy(id128, &id, sizeof(id));
+    return MGB_OK;
+}
+
+int mgb_comm_create(mgb_comm** out, const void* id128, int rank, int nranks)
+{
+    if (int rc = require_device()) return rc;
+    MGB_REQUIRE(out && id128, "mgb_comm_create: null pointer");
+    MGB_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, "bad rank %d/%d", rank, nranks);
+    Nccl* N = nccl();
+    if (!N)
+    {
+        set_error("NCCL (libnccl.so.2) could not be loaded");
+        return MGB_ENCCL;
+    }
+    ncclUniqueId id;
+    memcpy(&id, id128, sizeof(id));
+    mgb_comm* c = new mgb_comm();
+    memset(c, 0, sizeof(*c));
+    c->rank   = rank;
+    c->nranks = nranks;
+    ncclResult_t r = N->CommInitRank(&c->comm, nranks, id, rank);
+    if (r != 0)
+    {
+        set_error("ncclCommInitRank failed: %s",
+            N->GetErrorString ? N->GetErrorString(r) : "?");
+        delete c;
+        return MGB_ENCCL;
+    }
+    *out = c;
+    return MGB_OK;
+}
+
+int mgb_comm_destroy(mgb_comm* c)
+{
+    if (!c) return MGB_OK;
+    Nccl* N = nccl();
+    for (int i = 0; i < 4; i++)
+        if (c->buf[i]) cudaFree(c->buf[i]);
+    if (N && c->comm) N->CommDestroy(c->comm);
+    delete c;
+    return MGB_OK;
+}
+
+int mgb_allreduce_sum_f64(mgb_comm* c, double* data, size_t n, void* stream)
+{
+    if (int rc = require_device()) return rc;
+    MGB_REQUIRE(c && data, "mgb_allreduce_sum_f64: null pointer");
+    if (n == 0 || c->nranks == 1) return MGB_OK;
+    MGB_NCCL(nccl()->AllReduce(
+        data, data, n, kNcclFloat64, kNcclSum, c->comm, as_stream(stream)));
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    return MGB_OK;
+}
+
+int mgb_halo_exchange_x(mgb_comm* c, int dtype, const mgb_grid* grid, int g,
+    const void* noghost, size_t ld, void* xhalo, int nfunc, void* stream)
+{
+    if (int rc = require_device()) return rc;
+    if (int rc = check_grid(grid)) return rc;
+    MGB_REQUIRE(c && noghost && xhalo, "mgb_halo_exchange_x: null pointer");
+    MGB_REQUIRE(g >= 1 && g <= grid->dim[0], "mgb_halo_exchange_x: bad halo width %d", g);
+    MGB_REQUIRE(grid->nproc[0] * grid->nproc[1] * grid->nproc[2] == c->nranks,
+        "mgb_halo_exchange_x: grid decomposition does not match the communicator");
+    MGB_REQUIRE(grid->nproc[0] > 1, "mgb_halo_exchange_x: x is not split");
+    if (nfunc == 0) return MGB_OK;
+    if (dtype == MGB_F64)
+        return halo_x_t<double>(c, grid, g, (const double*)noghost, ld,
+            (double*)xhalo, nfunc, as_stream(stream));
+    if (dtype == MGB_F32)
+        return halo_x_t<float>(c, grid, g, (const float*)noghost, ld, (float*)xhalo,
+            nfunc, as_stream(stream));
+    set_error("mgb_halo_exchange_x: bad dtype");
+    return MGB_EINVAL;
+}
+
+int mgb_halo_exchange_ghosted(mgb_comm* c, int dtype, const mgb_grid* grid,
+    void* ghosted, int nfunc, void* stream)
+{
+    if (int rc = require_device()) return rc;
+    if (int rc = check_grid(grid)) return rc;
+    MGB_REQUIRE(ghosted, "mgb_halo_exchange_ghosted: null pointer");
+    MGB_REQUIRE(dtype == MGB_F32 || dtype == MGB_F64, "bad dtype");
+    const int np = grid->nproc[0] * grid->nproc[1] * grid->nproc[2];
+    MGB_REQUIRE(np == 1 || (c && np == c->nranks),
+        "mgb_halo_exchange_ghosted: decomposition does not match the communicator");
+    if (nfunc == 0 || grid->ghosts == 0) return MGB_OK;
+    cudaStream_t st = as_stream(stream);
+    int rc;
+    // zero the Dirichlet ghosts and first low layers  (GridFuncVector.cc:1554-1557)
+    if ((rc = trade_dirichlet(dtype, grid, ghosted, nfunc, st))) return rc;
+    const int order[3] = { 1, 2, 0 }; // Y (north/south), Z (up/down), X (east/west)
+    for (int o = 0; o < 3; o++)
+    {
+        const int d = order[o];
+        if (grid->nproc[d] > 1)
+            rc = exchange_dir(c, dtype, grid, ghosted, nfunc, d, st);
+        else
+            rc = trade_wrap(dtype, grid, ghosted, nfunc, d, st);
+        if (rc) return rc;
+    }
+    return MGB_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,50 @@
+// Internal interface between the mgb_hpsi dispatcher and its three paths.
+#pragma once
+#include "common.cuh"
+
+namespace mgb
+{
+
+struct HpsiArgs
+{
+    int lap_type; // MGB_LAP_4M / MGB_LAP_4MP / MGB_LAP_4
+    int dtype;
+    const mgb_grid* grid;
+    int g; // stencil radius: 1 Mehrstellen, 2 4th order (src/GridFactory.h:23-51)
+    const void* phi;
+    size_t ld;
+    const double* vtot;
+    void* hphi;
+    size_t ldh;
+    int nfunc;
+    const void* xhalo_phi;
+    const double* xhalo_v;
+};
+
+// path 1: TMA-pipelined x-streaming kernel (hpsi_fused.cu).  Returns
+// MGB_ENOTSUP (without setting an error) when the box is not eligible.
+int hpsi_tma(const HpsiArgs& a, cudaStream_t st);
+// path 2: generic fused kernel (hpsi_generic.cu), bit-exact.
+int hpsi_generic(const HpsiArgs& a, cudaStream_t st);
+// path 3: reference-shaped composition on ghosted blocks (api.cu).
+int hpsi_ghosted(const HpsiArgs& a, cudaStream_t st);
+
+// literal Jacobi sweep on ghosted float blocks (fd_ghosted.cu)
+int jacobi_literal(int lap_type, const mgb_grid* gr, float* v, const float* f,
+    float* w, int nfunc, double omega, cudaStream_t st);
+
+// Laph4::applyWithPot on a ghosted block (fd_ghosted.cu)
+int del2_4th_withpot(int dtype, const mgb_grid* gr, const void* v,
+    const double* pot, void* out, size_t ldo, int nfunc, cudaStream_t st);
+
+// phases of GridFuncVector::trade_boundaries on a ghosted block (fd_ghosted.cu)
+int trade_dirichlet(int dtype, const mgb_grid* gr, void* u, int nfunc, cudaStream_t st);
+int trade_wrap(int dtype, const mgb_grid* gr, void* u, int nfunc, int d, cudaStream_t st);
+// pack (ghosted -> buf) or unpack a sub-box of every function
+int subbox_copy(int dtype, bool pack, const mgb_grid* gr, const int lo[3],
+    const int ext[3], void* u, void* buf, int nfunc, cudaStream_t st);
+
+// grow-only device scratch owned by the library (workspaces, never user data)
+void* scratch(int slot, size_t bytes);
+
+} // namespace mgb

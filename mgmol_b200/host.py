@@ -1,0 +1,473 @@
+"""Host-side mirror of the reference's operator API for the hot path, over the C
+ABI.  Same class and method names as MGmol (file:line in the docstrings) so
+the parity tests read like the reference's own unit tests.  PyTorch appears
+only as the owner of device memory and streams; every number is produced by a
+kernel of libmgmol_b200.so.
+
+The production host for a C++ caller is include/mgmol_b200.hpp (same mirror in
+C++); this module is what tests/ and bench.py drive.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import MGB_F32, MGB_F64, MgbGrid, check, lib
+
+
+def _dt(t):
+    if t.dtype == torch.float64:
+        return MGB_F64
+    if t.dtype == torch.float32:
+        return MGB_F32
+    raise TypeError("ORBDTYPE must be float32 or float64")
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def ghosts_for(lap_type):
+    """GridFactory (src/GridFactory.h:23-51): ghost width per operator."""
+    return {0: 1, 10: 1, 1: 1, 2: 2, 3: 3, 4: 4}[lap_type]
+
+
+class Grid:
+    """pb::Grid + pb::PEenv for one rank (src/pb/Grid.h:24-121)."""
+
+    def __init__(self, gdim, lattice, ghosts=1, bc=(1, 1, 1), nproc=(1, 1, 1),
+                 coord=(0, 0, 0), level=0):
+        self.gdim_ = tuple(int(n) for n in gdim)
+        self.ll_ = tuple(float(l) for l in lattice)
+        self.nproc = tuple(nproc)
+        self.coord = tuple(coord)
+        for n, p in zip(self.gdim_, self.nproc):
+            if n % p:
+                raise ValueError("global dims must divide by ranks (Grid.cc:52-54)")
+        self.dim_ = tuple(n // p for n, p in zip(self.gdim_, self.nproc))
+        self.ghost_pt_ = int(ghosts)
+        self.bc = tuple(bc)
+        self.level_ = level
+        self.c = MgbGrid()
+        for d in range(3):
+            self.c.dim[d] = self.dim_[d]
+            self.c.gdim[d] = self.gdim_[d]
+            self.c.h[d] = self.ll_[d] / self.gdim_[d]
+            self.c.bc[d] = self.bc[d]
+            self.c.nproc[d] = self.nproc[d]
+            self.c.coord[d] = self.coord[d]
+        self.c.ghosts = self.ghost_pt_
+
+    def dim(self, i):
+        return self.dim_[i]
+
+    def gdim(self, i):
+        return self.gdim_[i]
+
+    def ghost_pt(self):
+        return self.ghost_pt_
+
+    def hgrid(self, i):
+        return self.ll_[i] / self.gdim_[i]
+
+    def vel(self):
+        return self.hgrid(0) * self.hgrid(1) * self.hgrid(2)
+
+    def size(self):
+        return self.dim_[0] * self.dim_[1] * self.dim_[2]
+
+    def sizeg(self):
+        g = self.ghost_pt_
+        return (self.dim_[0] + 2 * g) * (self.dim_[1] + 2 * g) * (self.dim_[2] + 2 * g)
+
+    def shape(self):
+        return self.dim_
+
+    def shapeg(self):
+        g = self.ghost_pt_
+        return tuple(d + 2 * g for d in self.dim_)
+
+    def coarse_grid(self):
+        """Grid::coarse_grid (src/pb/Grid.cc:214-231): same ghosts, half dims."""
+        return Grid(tuple(n // 2 for n in self.gdim_), self.ll_, self.ghost_pt_,
+                    self.bc, self.nproc, self.coord, self.level_ - 1)
+
+    def with_ghosts(self, g):
+        return Grid(self.gdim_, self.ll_, g, self.bc, self.nproc, self.coord,
+                    self.level_)
+
+    def ref(self):
+        return ctypes.byref(self.c)
+
+
+class GridFuncVector:
+    """pb::GridFuncVector<T, MemorySpace::Device> (src/pb/GridFuncVector.h):
+    nfunc ghosted functions in one device allocation."""
+
+    def __init__(self, grid, nfunc, dtype=torch.float64, data=None):
+        self.grid_ = grid
+        self.nfunc_ = nfunc
+        shape = (nfunc,) + grid.shapeg()
+        self.data = (torch.zeros(shape, dtype=dtype, device="cuda")
+                     if data is None else data)
+        assert self.data.shape == shape and self.data.is_contiguous()
+        self.updated_boundaries_ = False
+
+    def grid(self):
+        return self.grid_
+
+    def size(self):
+        return self.nfunc_
+
+    def resetData(self):
+        self.data.zero_()
+        self.updated_boundaries_ = True
+
+    def set_updated_boundaries(self, flag):
+        self.updated_boundaries_ = bool(flag)
+
+    def assign(self, noghost):
+        """BlockVector::setDataWithGhosts (src/BlockVector.cc:489-517)."""
+        assert noghost.is_contiguous() and noghost.shape[0] == self.nfunc_
+        check(lib().mgb_gfv_set_with_ghosts(
+            _dt(noghost), _dt(self.data), self.grid_.ref(), _p(noghost),
+            self.grid_.size(), _p(self.data), self.nfunc_, _stream()))
+        self.updated_boundaries_ = False
+
+    def getValues(self, out):
+        """BlockVector::assign(GridFuncVector) (src/BlockVector.cc:303-311)."""
+        check(lib().mgb_gfv_get_values(
+            _dt(self.data), _dt(out), self.grid_.ref(), _p(self.data), _p(out),
+            self.grid_.size(), self.nfunc_, _stream()))
+        return out
+
+    def trade_boundaries(self):
+        """src/pb/GridFuncVector.cc:1544-1622."""
+        if self.updated_boundaries_:
+            return
+        check(lib().mgb_gfv_trade_boundaries(
+            _dt(self.data), self.grid_.ref(), _p(self.data), self.nfunc_, _stream()))
+        self.updated_boundaries_ = True
+
+    def _fd(self, kind, rhs, rhs_ghosts=0):
+        self.trade_boundaries()
+        check(lib().mgb_fd_apply(kind, _dt(self.data), self.grid_.ref(),
+                                 _p(self.data), _p(rhs.data), self.nfunc_,
+                                 rhs_ghosts, _stream()))
+        rhs.set_updated_boundaries(False)
+
+    def applyLap(self, lap_type, rhs):
+        """src/pb/GridFuncVector.cc:2370-2397."""
+        kinds = {0: _lib.FD_DEL2_4TH_MEHR, 1: _lib.FD_DEL2_2ND, 2: _lib.FD_DEL2_4TH,
+                 3: _lib.FD_DEL2_6TH, 4: _lib.FD_DEL2_8TH}
+        if lap_type not in kinds:
+            raise ValueError("LapFactory::createLap() --- option invalid: %d" % lap_type)
+        self._fd(kinds[lap_type], rhs)
+
+    def applyRHS(self, lap_type, rhs):
+        """src/pb/GridFuncVector.cc:2400-2413."""
+        if lap_type == 0:
+            self._fd(_lib.FD_RHS_4TH_MEHR1, rhs, self.grid_.ghost_pt())
+        else:
+            self.data.copy_(rhs.data)
+
+    def pointwiseProduct(self, A, Vghost):
+        """src/pb/GridFuncVector.cc:90-136; Vghost: ghosted double field."""
+        check(lib().mgb_gfv_pointwise_product(
+            _dt(self.data), self.grid_.ref(), _p(A.data), _p(Vghost), _p(self.data),
+            self.nfunc_, _stream()))
+        self.updated_boundaries_ = A.updated_boundaries_
+
+    def axpy(self, alpha, other):
+        """src/pb/GridFuncVector.cc:1660-1668."""
+        check(lib().mgb_axpy(_dt(self.data), self.data.numel(), float(alpha),
+                             _p(other.data), _p(self.data), _stream()))
+        self.updated_boundaries_ = other.updated_boundaries_ and self.updated_boundaries_
+
+    def __isub__(self, other):
+        self.axpy(-1.0, other)
+        return self
+
+    def jacobi(self, lap_type, B, w, jacobi_factor):
+        """src/pb/GridFuncVector.cc:2416-2425."""
+        self.trade_boundaries()
+        check(lib().mgb_gfv_jacobi(lap_type, self.grid_.ref(), _p(self.data),
+                                   _p(B.data), _p(w.data), self.nfunc_,
+                                   float(jacobi_factor), _stream()))
+        self.updated_boundaries_ = False
+        w.set_updated_boundaries(False)
+
+    def restrict3D(self, ucoarse):
+        """src/pb/GridFuncVector.cc:1624-1631."""
+        self.trade_boundaries()
+        check(lib().mgb_gfv_restrict3D(_dt(self.data), self.grid_.ref(),
+                                       _p(self.data), _p(ucoarse.data),
+                                       self.nfunc_, _stream()))
+
+    def extend3D(self, ucoarse):
+        """src/pb/GridFuncVector.cc:1633-1641."""
+        ucoarse.trade_boundaries()
+        check(lib().mgb_gfv_extend3D(_dt(self.data), self.grid_.ref(),
+                                     _p(ucoarse.data), _p(self.data), self.nfunc_,
+                                     _stream()))
+        self.updated_boundaries_ = False
+
+
+class Lap:
+    """pb::Lap<T> family (src/pb/Lap.h:19-54) as created by LapFactory."""
+
+    def __init__(self, grid, lap_type):
+        self.grid_ = grid
+        self.type_ = lap_type
+        h = (ctypes.c_double * 3)(*(grid.hgrid(i) for i in range(3)))
+        out = (ctypes.c_double * 3)()
+        check(lib().mgb_lap_constants(lap_type, h, out))
+        self.diagEl_, self.invDiagEl_, self.jacobiFactor_ = out[0], out[1], out[2]
+
+    def diagEl(self):
+        return self.diagEl_
+
+    def invDiagEl(self):
+        return self.invDiagEl_
+
+    def jacobiFactor(self):
+        return self.jacobiFactor_
+
+    def minNumberGhosts(self):
+        return ghosts_for(self.type_)
+
+    def apply(self, A, B):
+        """Lap::apply on a block (Laph4::apply(grid, A, B, nfunc),
+        src/pb/Laph4.h:99-102, and the GridFuncVector analogue)."""
+        A.applyLap(0 if self.type_ == 10 else self.type_, B)
+
+    def applyWithPot(self, phi, vtot, hphi, xhalo_phi=None, xhalo_v=None):
+        """Lap<T>::applyWithPot (src/pb/Lap.h:35; Laph4.h:95-98) generalised
+        to the whole block = Hamiltonian::applyLocal body."""
+        nfunc = phi.shape[0]
+        check(lib().mgb_hpsi(
+            self.type_, _dt(phi), self.grid_.ref(), _p(phi), self.grid_.size(),
+            _p(vtot), _p(hphi), self.grid_.size(), nfunc,
+            _p(xhalo_phi) if xhalo_phi is not None else None,
+            _p(xhalo_v) if xhalo_v is not None else None, _stream()))
+        return hphi
+
+
+class LapFactory:
+    """src/LapFactory.h:26-56."""
+
+    @staticmethod
+    def createLap(grid, lap_type):
+        if lap_type not in (0, 1, 2, 3, 4, 10):
+            raise ValueError("LapFactory::createLap() --- option invalid:%d" % lap_type)
+        return Lap(grid, lap_type)
+
+
+class Potentials:
+    """The slice of Potentials the path reads: vtot (POTDTYPE double, no
+    ghosts, src/Potentials.h:141) and its iterative index."""
+
+    def __init__(self, vtot):
+        assert vtot.dtype == torch.float64 and vtot.is_contiguous()
+        self.vtot_ = vtot
+        self.itindex_ = 0
+
+    def vtot(self):
+        return self.vtot_
+
+    def getIterativeIndex(self):
+        return self.itindex_
+
+    def update(self, vtot):
+        self.vtot_.copy_(vtot)
+        self.itindex_ += 1
+
+    def max(self):
+        return float(self.vtot_.max())
+
+
+class Orbitals:
+    """ExtendedGridOrbitals (src/ExtendedGridOrbitals.h:43-404) reduced to the
+    hot path: psi as a no-ghost column-major npt x numst block (here a
+    contiguous (numst, nx, ny, nz) tensor, lda = npt) plus the iterative index
+    that keys Hamiltonian's cache (src/Orbitals.h:43-70)."""
+
+    def __init__(self, grid, numst, dtype=torch.float64, psi=None):
+        self.grid_ = grid
+        self.numst_ = numst
+        shape = (numst,) + grid.shape()
+        self.psi_ = (torch.zeros(shape, dtype=dtype, device="cuda")
+                     if psi is None else psi)
+        assert self.psi_.shape == shape and self.psi_.is_contiguous()
+        self.iterative_index_ = 0
+
+    def chromatic_number(self):
+        return self.numst_
+
+    def getIterativeIndex(self):
+        return self.iterative_index_
+
+    def incrementIterativeIndex(self):
+        self.iterative_index_ += 1
+
+    def psi(self):
+        return self.psi_
+
+    def getNumpt(self):
+        return self.grid_.size()
+
+    # -- BLAS-1 (src/ExtendedGridOrbitals.cc:202-212, BlockVector.h:112-126) --
+    def axpy(self, alpha, other):
+        check(lib().mgb_axpy(_dt(self.psi_), self.psi_.numel(), float(alpha),
+                             _p(other.psi_), _p(self.psi_), _stream()))
+        self.incrementIterativeIndex()
+
+    def scal(self, alpha):
+        check(lib().mgb_scal(_dt(self.psi_), self.psi_.numel(), float(alpha),
+                             _p(self.psi_), _stream()))
+        self.incrementIterativeIndex()
+
+    # -- contractions ---------------------------------------------------------
+    def computeLocalProduct(self, other, comm=None):
+        """vel * Phi^T A  (src/ExtendedGridOrbitals.cc:1049-1083); with a
+        communicator the partial matrices are summed over ranks
+        (addDotWithNcol2Matrix, :1704-1752)."""
+        a = other.psi_ if isinstance(other, Orbitals) else other
+        n = self.numst_
+        ss = torch.empty((n, n), dtype=torch.float64, device="cuda")
+        # column-major C(i,j) = <phi_i, a_j>; the row-major view is C^T
+        check(lib().mgb_gemm_tn(_dt(self.psi_), n, n, self.grid_.size(),
+                                self.grid_.vel(), _p(self.psi_), self.grid_.size(),
+                                _p(a), self.grid_.size(), 0.0, _p(ss), n, _stream()))
+        if comm is not None:
+            comm.allreduce(ss)
+        return ss.t()
+
+    def computeGram(self, comm=None):
+        """S = vel * Phi^T Phi (src/ExtendedGridOrbitals.cc:985-1010,1138-1162)."""
+        n = self.numst_
+        ss = torch.empty((n, n), dtype=torch.float64, device="cuda")
+        check(lib().mgb_syrk_t(_dt(self.psi_), n, self.grid_.size(), self.grid_.vel(),
+                               _p(self.psi_), self.grid_.size(), _p(ss), n, _stream()))
+        if comm is not None:
+            comm.allreduce(ss)
+        return ss
+
+    def multiplyByMatrix(self, matrix, product=None):
+        """Phi * M (src/ExtendedGridOrbitals.cc:448-498).  matrix[l, j] is a
+        (numst, n) double tensor (row-major = the transpose of the reference's
+        column-major storage is handled here)."""
+        n = matrix.shape[1]
+        inplace = product is None
+        out = torch.empty((n,) + self.grid_.shape(), dtype=self.psi_.dtype,
+                          device="cuda") if inplace else product.psi_
+        mcol = matrix.t().contiguous()  # column-major k x n
+        check(lib().mgb_gemm_nn(_dt(self.psi_), self.grid_.size(), n, self.numst_,
+                                1.0, _p(self.psi_), self.grid_.size(), _p(mcol),
+                                self.numst_, 0.0, _p(out), self.grid_.size(),
+                                _stream()))
+        if inplace:
+            self.psi_.copy_(out)
+            self.incrementIterativeIndex()
+        return out
+
+
+class Hamiltonian:
+    """Hamiltonian<T> (src/Hamiltonian.h:20-52, .cc:43-159): caches
+    hlphi_ = H_loc * phi keyed by 100*phi.index + pot.index."""
+
+    def __init__(self):
+        self.lapOper_ = None
+        self.pot_ = None
+        self.hlphi_ = None
+        self.itindex_ = -1
+
+    def setup(self, grid, lap_type):
+        self.lapOper_ = LapFactory.createLap(grid, lap_type)
+        self.grid_ = grid
+
+    def potential(self, pot=None):
+        if pot is not None:
+            self.pot_ = pot
+        return self.pot_
+
+    def lapOper(self):
+        return self.lapOper_
+
+    def applyLocal(self, phi, force=False, xhalo_phi=None, xhalo_v=None):
+        """src/Hamiltonian.cc:43-83."""
+        assert phi.getIterativeIndex() >= 0 and self.pot_.getIterativeIndex() >= 0
+        if (self.hlphi_ is None or self.hlphi_.psi_.shape != phi.psi_.shape
+                or self.hlphi_.psi_.dtype != phi.psi_.dtype):
+            self.hlphi_ = Orbitals(phi.grid_, phi.numst_, phi.psi_.dtype)
+            self.itindex_ = -1
+        new_index = 100 * phi.getIterativeIndex() + self.pot_.getIterativeIndex()
+        if force or new_index != self.itindex_:
+            self.lapOper_.applyWithPot(phi.psi_, self.pot_.vtot(), self.hlphi_.psi_,
+                                       xhalo_phi, xhalo_v)
+            self.itindex_ = new_index
+        return self.hlphi_
+
+    def addHlocalij(self, phi1, phi2=None, comm=None):
+        """Phi1^T H_loc Phi2 (src/Hamiltonian.cc:214-239)."""
+        if phi2 is not None:
+            self.applyLocal(phi2)
+        return phi1.computeLocalProduct(self.hlphi_, comm)
+
+
+class OrbitalsPreconditioning:
+    """OrbitalsPreconditioning<T> (src/OrbitalsPreconditioning.h:27-70,
+    .cc:44-145) over Preconditioning<float> (src/Preconditioning.cc)."""
+
+    def __init__(self):
+        self.handle_ = None
+        self.gamma_ = -1.0
+        self.is_set_ = False
+
+    def setup(self, orbitals, mg_levels, lap_type):
+        assert not self.is_set_
+        grid = orbitals.grid_.with_ghosts(ghosts_for(lap_type))
+        h = ctypes.c_void_p()
+        check(lib().mgb_precond_create(ctypes.byref(h), lap_type, mg_levels,
+                                       grid.ref(), orbitals.chromatic_number()))
+        self.handle_ = h
+        self.lap_type_ = lap_type
+        self.mg_levels_ = mg_levels
+        self.grid_ = grid
+        self.is_set_ = True
+
+    def setGamma(self, lapOper, pot, mg_levels, small_eig):
+        """src/OrbitalsPreconditioning.cc:120-145."""
+        self.gamma_ = lib().mgb_gamma(lapOper.invDiagEl(), mg_levels, pot.max(),
+                                      float(small_eig))
+        return self.gamma_
+
+    def precond_mg(self, orbitals):
+        """src/OrbitalsPreconditioning.cc:87-117: res <- M^-1 res."""
+        assert self.is_set_ and self.gamma_ > 0.0
+        psi = orbitals.psi_
+        check(lib().mgb_precond_mg(self.handle_, _dt(psi), _p(psi),
+                                   orbitals.getNumpt(), orbitals.chromatic_number(),
+                                   self.gamma_, _stream()))
+        orbitals.incrementIterativeIndex()
+
+    def vcycle(self, gfv_v, gfv_f):
+        """Preconditioning<float>::mg (src/Preconditioning.cc:155-216)."""
+        check(lib().mgb_precond_vcycle(self.handle_, _p(gfv_v.data), _p(gfv_f.data),
+                                       gfv_v.size(), _stream()))
+
+    def close(self):
+        if self.handle_ is not None:
+            lib().mgb_precond_destroy(self.handle_)
+            self.handle_ = None
+            self.is_set_ = False
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
