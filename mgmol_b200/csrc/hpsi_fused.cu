@@ -184,6 +184,13 @@ __device__ __forceinline__ T coef(const FusedParams& P, int i)
         return P.cf[i];
 }
 
+// product rounded on its own (never contracted into a following add): the
+// reference rounds V*psi before B is applied (GridFuncVector.cc:131), and a
+// contraction that depends on the lane's position inside its vector would
+// break bit-exact translation covariance
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+
 template <typename T, int VEC>
 __device__ __forceinline__ void store_vec_streaming(T* p, const T (&v)[VEC])
 {
@@ -426,10 +433,10 @@ __global__ void __launch_bounds__(MAXT, 1)
                                 PR = (CT)0;
                             }
                         }
-                        const CT wL = VL * PL, wR = VR * PR;
+                        const CT wL = mul_rn(VL, PL), wR = mul_rn(VR, PR);
 #pragma unroll
                         for (int e = 0; e < VEC; e++)
-                            wq[e] = Vq[e] * Pq[e];
+                            wq[e] = mul_rn(Vq[e], Pq[e]);
 #pragma unroll
                         for (int e = 0; e < VEC; e++)
                         {
