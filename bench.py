@@ -35,6 +35,20 @@ WORKLOADS = {
 }
 
 
+def measured_traffic(kernel_prefix, workload, dtype, lap_type):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant
+    kernel, from the committed ncu --set full capture (profiles/); None when no
+    capture matches this configuration."""
+    p = os.path.join(ROOT, "profiles", "hpsi_traffic.json")
+    if not os.path.exists(p):
+        return None
+    d = json.load(open(p))
+    if d.get("workload") == "%s %s lap%d" % (workload, dtype, 4 if lap_type == 2 else 0) \
+            and d.get("kernel", "").startswith(kernel_prefix):
+        return d.get("traffic_bytes_per_launch")
+    return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -191,13 +205,19 @@ def run_ours(args):
     grid = H.Grid(gdims, (cell * world, cell, cell), g, (1, 1, 1), (world, 1, 1), (rank, 0, 0))
     npt = grid.size()
 
+    # synthetic orbitals: plane wave along z with orbital-dependent wavevector
+    # + 0.1 U(-1,1) noise; potential a noisy constant.  A handful of large
+    # launches (chunks of <= 64 orbitals) so the ncu launch list stays short.
     gen = torch.Generator(device="cuda").manual_seed(1234 + rank)
     phi = H.Orbitals(grid, norb, tdt)
     x = torch.arange(dims[2], device="cuda", dtype=torch.float64) / dims[2]
-    for j in range(norb):
-        phi.psi()[j] = (0.1 * (torch.rand(dims, generator=gen, device="cuda",
-                                          dtype=torch.float64) * 2 - 1)
-                        + torch.cos(2 * np.pi * ((j % 5) + 1) * x)[None, None, :]).to(tdt)
+    for j0 in range(0, norb, 64):
+        j1 = min(norb, j0 + 64)
+        k = (torch.arange(j0, j1, device="cuda") % 5 + 1).to(torch.float64)
+        wave = torch.cos(2 * np.pi * k[:, None] * x[None, :])[:, None, None, :]
+        noise = torch.rand((j1 - j0,) + dims, generator=gen, device="cuda", dtype=tdt)
+        phi.psi()[j0:j1] = (noise * 0.2 - 0.1) + wave.to(tdt)
+        del noise
     vtot = (torch.rand(dims, generator=gen, device="cuda", dtype=torch.float64) * 0.1 - 0.75)
     ham = H.Hamiltonian()
     ham.setup(grid, lap_type)
@@ -298,7 +318,10 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None,
+                         "frac": achieved / peak,
+                         "traffic": measured_traffic("k_hpsi_tma" if path == 1 else "k_hpsi_generic",
+                                                     args.workload, args.dtype, lap_type)
+                         if world == 1 and not args.orbitals else None,
                          "kernel": "k_hpsi_tma" if path == 1 else "k_hpsi_generic",
                          "kernel_ms": kern_ms, "peak_source": peak_src,
                          "algorithmic_bytes_per_update": 2 * S},
