@@ -181,6 +181,13 @@ int mgb_precond_destroy(mgb_precond* p);
 /* res (no-ghost, dtype) <- M^-1 res : v0 = gamma*res, mg(v, f=res) in float */
 int mgb_precond_mg(mgb_precond* p, int dtype, void* res, size_t ld, int nfunc,
     double gamma, void* stream);
+/* Implementation selector (test / profiling hook): 0 automatic, 1 the literal
+ * reference-shaped sequence on ghosted blocks (bit-identical to the reference
+ * CPU build), 2 the fused kernels on no-ghost blocks (one pass per Jacobi
+ * sweep; float difference-form stencils, agrees with the reference to ~1e-7
+ * relative).  mgb_precond_last_mode: what the last mgb_precond_mg used.      */
+int mgb_precond_set_mode(mgb_precond* p, int mode);
+int mgb_precond_last_mode(mgb_precond* p);
 /* Preconditioning<float>::mg on caller-owned ghosted float blocks           */
 int mgb_precond_vcycle(mgb_precond* p, float* v, const float* f, int nfunc,
     void* stream);

@@ -75,6 +75,8 @@ _SIGS = {
     "mgb_precond_destroy": (c_int, [c_void_p]),
     "mgb_precond_mg": (c_int, [c_void_p, c_int, c_void_p, c_size_t, c_int, c_double,
                                c_void_p]),
+    "mgb_precond_set_mode": (c_int, [c_void_p, c_int]),
+    "mgb_precond_last_mode": (c_int, [c_void_p]),
     "mgb_precond_vcycle": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "mgb_lap_constants": (c_int, [c_int, ctypes.POINTER(c_double),
                                   ctypes.POINTER(c_double)]),

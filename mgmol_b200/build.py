@@ -29,6 +29,7 @@ SOURCES = {
     "hpsi_generic.cu": ["-fmad=false"],
     "hpsi_fused.cu": [],
     "mg_precond.cu": [],
+    "mg_fused.cu": [],
     "contractions.cu": [],
     "comm.cu": [],
 }

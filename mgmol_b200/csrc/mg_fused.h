@@ -1,0 +1,43 @@
+// Internal interface of the fused multigrid kernels (mg_fused.cu) used by the
+// V-cycle driver in mg_precond.cu.  All blocks are no-ghost float arrays
+// [function][x][y][z] with an explicit leading dimension between functions.
+#pragma once
+#include "common.cuh"
+
+namespace mgb
+{
+
+struct MgJacobiArgs
+{
+    int lap_type;         // MGB_LAP_4M, MGB_LAP_2 or MGB_LAP_4
+    const mgb_grid* grid; // dims, h, bc of this level
+    const float* in;      // v (or f when scale != 1: v = scale * f on the fly)
+    size_t ld_in;
+    const float* f;       // right-hand side
+    size_t ld_f;
+    float* out;           // v' as float (may be null when out64 is set)
+    double* out64;        // v' as double (exit of precond_mg for ORBDTYPE double)
+    size_t ld_out;
+    float* w;             // A v - f (null: not needed)
+    size_t ld_w;
+    int nfunc;
+    double omega;         // jacobiFactor of this level
+    double scale;         // 1, or the factor applied to `in` while it is loaded
+    int zero_low[3];      // store zeros on the low layer (Dirichlet trade)
+};
+
+// true when the fused kernels can run this level (z extent a multiple of 4,
+// a tile configuration exists)
+bool mg_fused_level_ok(const mgb_grid& g, int lap_type);
+
+int mg_jacobi(const MgJacobiArgs& a, cudaStream_t st);
+int mg_restrict(const mgb_grid& fine, const float* w, size_t ldf, float* coarse, size_t ldc,
+    int nfunc, cudaStream_t st);
+int mg_prolong_correct(const mgb_grid& fine, const float* coarse, size_t ldc, float* v,
+    size_t ldv, int nfunc, const int zero_low[3], cudaStream_t st);
+int mg_convert(size_t npt, const double* in, size_t ldi, float* out, size_t ldo, int nfunc,
+    cudaStream_t st);
+int mg_scale(const mgb_grid& gr, double c, const float* f, size_t ldf, float* v, size_t ldv,
+    int nfunc, const int zero_low[3], cudaStream_t st);
+
+} // namespace mgb

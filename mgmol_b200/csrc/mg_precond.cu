@@ -7,10 +7,12 @@
 // for the lifetime of the handle, as the reference's gfv_work_/gfv_rcoarse_/
 // gfv_newv_ vectors do.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
 #include "hpsi.h"
+#include "mg_fused.h"
 
 struct mgb_precond
 {
@@ -25,6 +27,15 @@ struct mgb_precond
     std::vector<float*> newv;    // gfv_newv_[level]
     float* v0;                   // OrbitalsPreconditioning::gfv_work_
     float* f0;                   // OrbitalsPreconditioning::gfv_work2_
+    bool literal_ready;          // the ghosted blocks above are allocated
+    // fused path (mg_fused.cu): no-ghost float blocks per level
+    bool fused_ok;               // every level can run the fused kernels
+    int mode;                    // 0 automatic, 1 literal, 2 fused
+    int last_mode;               // what the last precond_mg call used (1 / 2)
+    bool fused_ready;
+    std::vector<float*> fa, fb;  // ping-pong iterates
+    std::vector<float*> fw;      // residual of the last pre-smoothing sweep
+    std::vector<float*> ff;      // right-hand side (level 0: converted residual)
 };
 
 namespace mgb
@@ -196,8 +207,16 @@ int mgb_precond_create(mgb_precond** out, int lap_type, int mg_levels,
     p->nfunc_max   = nfunc_max;
     p->g           = grid->ghosts;
     p->v0 = p->f0 = nullptr;
-    mgb_grid g    = *grid;
-    int rc        = MGB_OK;
+    p->literal_ready = p->fused_ready = false;
+    p->mode = p->last_mode = 0;
+    if (const char* env = getenv("MGB_MG_MODE")) p->mode = atoi(env);
+    mgb_grid g = *grid;
+    int rc     = MGB_OK;
+    // Mixed periodic/Dirichlet boxes stay on the literal path: there the
+    // reference's zeroing skips the first x/y layers "to avoid setting values
+    // twice" (src/pb/GridFunc.cc:2222-2236), so its result depends on stale
+    // ghost values that only the ghosted layout reproduces.
+    p->fused_ok = (grid->bc[0] == grid->bc[1] && grid->bc[1] == grid->bc[2]);
     for (int l = 0; l <= mg_levels && rc == MGB_OK; l++)
     {
         if (l > 0)
@@ -214,38 +233,174 @@ int mgb_precond_create(mgb_precond** out, int lap_type, int mg_levels,
         // Preconditioning.cc:26-27 (level 0: lap_type), :122-123 (coarse: 1)
         rc = lap_constants(l == 0 ? lap_type : MGB_LAP_2, g.h, c);
         p->jf.push_back(c[2]);
-        const size_t bytes = sizeof(float) * sizeg_of(g) * nfunc_max;
-        float* w           = nullptr;
-        if (rc == MGB_OK && cudaMalloc(&w, bytes) != cudaSuccess) rc = MGB_ECUDA;
-        p->work.push_back(w);
-        if (l > 0)
-        {
-            float *r = nullptr, *n = nullptr;
-            if (rc == MGB_OK && cudaMalloc(&r, bytes) != cudaSuccess) rc = MGB_ECUDA;
-            if (rc == MGB_OK && cudaMalloc(&n, bytes) != cudaSuccess) rc = MGB_ECUDA;
-            p->rcoarse.push_back(r);
-            p->newv.push_back(n);
-        }
+        if (!mg_fused_level_ok(g, l == 0 ? lap_type : MGB_LAP_2)) p->fused_ok = false;
     }
-    const size_t bytes0 = sizeof(float) * sizeg_of(p->grid[0]) * nfunc_max;
-    if (rc == MGB_OK && cudaMalloc(&p->v0, bytes0) != cudaSuccess) rc = MGB_ECUDA;
-    if (rc == MGB_OK && cudaMalloc(&p->f0, bytes0) != cudaSuccess) rc = MGB_ECUDA;
     if (rc != MGB_OK)
     {
-        if (rc == MGB_ECUDA)
-        {
-            set_error("mgb_precond_create: device allocation failed");
-            (void)cudaGetLastError();
-        }
-        mgb_precond_destroy(p);
+        delete p;
         return rc;
     }
-    // work blocks start zeroed like freshly constructed GridFuncVectors
-    for (size_t l = 0; l < p->work.size(); l++)
-        cudaMemset(p->work[l], 0, sizeof(float) * sizeg_of(p->grid[l]) * nfunc_max);
     *out = p;
     return MGB_OK;
 }
+
+} // extern "C"
+
+namespace mgb
+{
+static int dev_alloc(float** q, size_t bytes)
+{
+    if (cudaMalloc(q, bytes) != cudaSuccess)
+    {
+        *q = nullptr;
+        set_error("mgb_precond: device allocation of %zu bytes failed", bytes);
+        (void)cudaGetLastError();
+        return MGB_ECUDA;
+    }
+    return MGB_OK;
+}
+
+// ghosted work blocks of the literal path (gfv_work_[l], gfv_rcoarse_[l],
+// gfv_newv_[l], and OrbitalsPreconditioning's two level-0 blocks)
+static int ensure_literal(mgb_precond* p)
+{
+    if (p->literal_ready) return MGB_OK;
+    for (int l = 0; l <= p->max_levels; l++)
+    {
+        const size_t bytes = sizeof(float) * sizeg_of(p->grid[l]) * p->nfunc_max;
+        float *w = nullptr, *r = nullptr, *n = nullptr;
+        if (int rc = dev_alloc(&w, bytes)) return rc;
+        p->work.push_back(w);
+        // work blocks start zeroed like freshly constructed GridFuncVectors
+        MGB_CUDA(cudaMemset(w, 0, bytes));
+        if (l > 0)
+        {
+            if (int rc = dev_alloc(&r, bytes)) return rc;
+            p->rcoarse.push_back(r);
+            if (int rc = dev_alloc(&n, bytes)) return rc;
+            p->newv.push_back(n);
+        }
+    }
+    const size_t bytes0 = sizeof(float) * sizeg_of(p->grid[0]) * p->nfunc_max;
+    if (int rc = dev_alloc(&p->v0, bytes0)) return rc;
+    if (int rc = dev_alloc(&p->f0, bytes0)) return rc;
+    p->literal_ready = true;
+    return MGB_OK;
+}
+
+static size_t npt_of(const mgb_grid& g)
+{
+    return (size_t)g.dim[0] * g.dim[1] * g.dim[2];
+}
+
+static int ensure_fused(mgb_precond* p)
+{
+    if (p->fused_ready) return MGB_OK;
+    for (int l = 0; l <= p->max_levels; l++)
+    {
+        const size_t bytes = sizeof(float) * npt_of(p->grid[l]) * p->nfunc_max;
+        float *a = nullptr, *b = nullptr, *w = nullptr, *f = nullptr;
+        if (int rc = dev_alloc(&a, bytes)) return rc;
+        p->fa.push_back(a);
+        if (int rc = dev_alloc(&b, bytes)) return rc;
+        p->fb.push_back(b);
+        if (l < p->max_levels)
+            if (int rc = dev_alloc(&w, bytes)) return rc;
+        p->fw.push_back(w);
+        p->ff.push_back(f); // level 0: allocated on the first double-precision call
+        if (l > 0)
+            if (int rc = dev_alloc(&p->ff[l], bytes)) return rc;
+    }
+    p->fused_ready = true;
+    return MGB_OK;
+}
+
+// One level of Preconditioning<float>::mg (src/Preconditioning.cc:155-216) on
+// no-ghost blocks with the fused kernels.  The start vector of the level is
+// s * f: gamma * res at level 0 (OrbitalsPreconditioning.cc:104) and, on the
+// coarse levels, the result omega * f of the first sweep from v = 0; `npre` is
+// the number of pre-smoothing sweeps still to do.  The last sweep of level 0
+// writes the caller's block (fout / fout64, leading dimension ldo).
+static int cycle_fused(mgb_precond* p, int l, const float* f, size_t ldf, double s,
+    int npre, float* fout, double* fout64, size_t ldo, int nfunc, float** result,
+    cudaStream_t st)
+{
+    const mgb_grid& gr = p->grid[l];
+    const size_t ld    = npt_of(gr);
+    const int lap      = (l == 0) ? p->lap_type : MGB_LAP_2;
+    const bool coarsest = (l == p->max_levels);
+    const bool periodic = gr.bc[0] == 1 && gr.bc[1] == 1 && gr.bc[2] == 1;
+    int zl[3], nozero[3] = { 0, 0, 0 };
+    for (int d = 0; d < 3; d++)
+        zl[d] = gr.bc[d] != 1;
+    // the last sweep of level 0 is followed by a trade only on the path through
+    // Preconditioning.cc:215, whose test reads bc_[0], bc_[2], bc_[2]
+    const bool final_trade = !coarsest && (gr.bc[0] != 1 || gr.bc[2] != 1);
+    float* cur = nullptr;
+    bool pending_scale = true;
+    if (!periodic)
+    {
+        if (int rc = mg_scale(gr, s, f, ldf, p->fa[l], ld, nfunc, zl, st)) return rc;
+        cur           = p->fa[l];
+        pending_scale = false;
+    }
+    auto sweep = [&](bool emit_w, bool final_out) -> int {
+        MgJacobiArgs a;
+        a.lap_type = lap;
+        a.grid     = &gr;
+        a.in       = pending_scale ? f : cur;
+        a.ld_in    = pending_scale ? ldf : ld;
+        a.scale    = pending_scale ? s : 1.0;
+        a.f        = f;
+        a.ld_f     = ldf;
+        float* nxt = (cur == p->fa[l]) ? p->fb[l] : p->fa[l];
+        a.out      = final_out ? fout : nxt;
+        a.out64    = final_out ? fout64 : nullptr;
+        a.ld_out   = final_out ? ldo : ld;
+        a.w        = emit_w ? p->fw[l] : nullptr;
+        a.ld_w     = ld;
+        a.nfunc    = nfunc;
+        a.omega    = p->jf[l];
+        const int* z = (final_out && !final_trade) ? nozero : zl;
+        for (int d = 0; d < 3; d++)
+            a.zero_low[d] = z[d];
+        if (int rc = mg_jacobi(a, st)) return rc;
+        cur           = final_out ? nullptr : nxt;
+        pending_scale = false;
+        return MGB_OK;
+    };
+    for (int it = 0; it < npre; it++) // :173-177
+    {
+        const bool last = (it == npre - 1);
+        if (int rc = sweep(last && !coarsest, last && coarsest && l == 0)) return rc;
+    }
+    if (coarsest) // :179
+    {
+        *result = cur;
+        return MGB_OK;
+    }
+    // :189-192 restriction of the residual of the last pre-smoothing sweep
+    if (int rc = mg_restrict(gr, p->fw[l], ld, p->ff[l + 1], npt_of(p->grid[l + 1]), nfunc, st))
+        return rc;
+    // :198-199 coarse correction from a zero start: its first sweep gives
+    // omega * f, folded into the start vector
+    const int ncycl_c = (l + 1 == p->max_levels) ? 4 : 2;
+    float* e          = nullptr;
+    if (int rc = cycle_fused(p, l + 1, p->ff[l + 1], npt_of(p->grid[l + 1]), p->jf[l + 1],
+            ncycl_c - 1, nullptr, nullptr, 0, nfunc, &e, st))
+        return rc;
+    // :201-206 v -= P e
+    if (int rc = mg_prolong_correct(gr, e, npt_of(p->grid[l + 1]), cur, ld, nfunc, zl, st))
+        return rc;
+    for (int it = 0; it < 2; it++) // :209-213
+        if (int rc = sweep(false, it == 1 && l == 0)) return rc;
+    *result = cur;
+    return MGB_OK;
+}
+} // namespace mgb
+
+extern "C"
+{
 
 int mgb_precond_destroy(mgb_precond* p)
 {
@@ -258,9 +413,24 @@ int mgb_precond_destroy(mgb_precond* p)
         if (q) cudaFree(q);
     if (p->v0) cudaFree(p->v0);
     if (p->f0) cudaFree(p->f0);
+    for (auto* vec : { &p->fa, &p->fb, &p->fw, &p->ff })
+        for (float* q : *vec)
+            if (q) cudaFree(q);
     delete p;
     return MGB_OK;
 }
+
+int mgb_precond_set_mode(mgb_precond* p, int mode)
+{
+    MGB_REQUIRE(p, "mgb_precond_set_mode: null handle");
+    MGB_REQUIRE(mode >= 0 && mode <= 2, "mgb_precond_set_mode: mode %d", mode);
+    MGB_REQUIRE(mode != 2 || p->fused_ok,
+        "mgb_precond_set_mode: the fused kernels cannot run this grid");
+    p->mode = mode;
+    return MGB_OK;
+}
+
+int mgb_precond_last_mode(mgb_precond* p) { return p ? p->last_mode : 0; }
 
 int mgb_precond_vcycle(mgb_precond* p, float* v, const float* f, int nfunc, void* stream)
 {
@@ -269,6 +439,7 @@ int mgb_precond_vcycle(mgb_precond* p, float* v, const float* f, int nfunc, void
     MGB_REQUIRE(nfunc >= 0 && nfunc <= p->nfunc_max, "nfunc %d > nfunc_max %d",
         nfunc, p->nfunc_max);
     if (nfunc == 0) return MGB_OK;
+    if (int rc = ensure_literal(p)) return rc;
     bool v_upd = false;
     return vcycle(p, v, v_upd, f, p->lap_type, 0, nfunc, as_stream(stream));
 }
@@ -284,9 +455,39 @@ int mgb_precond_mg(mgb_precond* p, int dtype, void* res, size_t ld, int nfunc,
     MGB_REQUIRE(gamma > 0., "gamma must be > 0 (assert in precond_mg)");
     if (nfunc == 0) return MGB_OK;
     const mgb_grid& gr = p->grid[0];
-    const size_t n     = sizeg_of(gr) * nfunc;
     cudaStream_t st    = as_stream(stream);
     int rc;
+    const size_t es = dtype == MGB_F64 ? 8 : 4;
+    const bool can_fuse = p->fused_ok && ld % 4 == 0 && ((uintptr_t)res & 15) == 0
+                          && ld * es % 16 == 0;
+    MGB_REQUIRE(p->mode != 2 || can_fuse,
+        "mgb_precond_mg: fused mode forced but this grid/block is not eligible");
+    if (p->mode == 2 || (p->mode == 0 && can_fuse))
+    {
+        if ((rc = ensure_fused(p))) return rc;
+        const float* f = (const float*)res;
+        size_t ldf     = ld;
+        if (dtype == MGB_F64)
+        {
+            // orbitals.setDataWithGhosts(gfv_work2_): ORBDTYPE -> float  (:103)
+            if (!p->ff[0])
+                if ((rc = dev_alloc(&p->ff[0], sizeof(float) * npt_of(gr) * p->nfunc_max)))
+                    return rc;
+            if ((rc = mg_convert(npt_of(gr), (const double*)res, ld, p->ff[0], npt_of(gr),
+                     nfunc, st)))
+                return rc;
+            f   = p->ff[0];
+            ldf = npt_of(gr);
+        }
+        float* unused  = nullptr;
+        const int ncyc = (p->max_levels == 0) ? 4 : 2;
+        p->last_mode   = 2;
+        return cycle_fused(p, 0, f, ldf, gamma, ncyc, dtype == MGB_F32 ? (float*)res : nullptr,
+            dtype == MGB_F64 ? (double*)res : nullptr, ld, nfunc, &unused, st);
+    }
+    p->last_mode = 1;
+    if ((rc = ensure_literal(p))) return rc;
+    const size_t n = sizeg_of(gr) * nfunc;
     // gfv_work_->resetData()                           (OrbitalsPrecond.cc:99)
     MGB_CUDA(cudaMemsetAsync(p->v0, 0, sizeof(float) * n, st));
     // orbitals.setDataWithGhosts(gfv_work2_)  ORBDTYPE -> float        (:103)

@@ -440,6 +440,13 @@ class OrbitalsPreconditioning:
         self.grid_ = grid
         self.is_set_ = True
 
+    def set_mode(self, mode):
+        """0 automatic, 1 literal (bit-identical to the reference), 2 fused."""
+        check(lib().mgb_precond_set_mode(self.handle_, int(mode)))
+
+    def last_mode(self):
+        return lib().mgb_precond_last_mode(self.handle_)
+
     def setGamma(self, lapOper, pot, mg_levels, small_eig):
         """src/OrbitalsPreconditioning.cc:120-145."""
         self.gamma_ = lib().mgb_gamma(lapOper.invDiagEl(), mg_levels, pot.max(),

@@ -286,8 +286,10 @@ def test_precond_mg_bit_exact(H, port, dt, lap_type, bc, levels):
     orb = H.Orbitals(grid, N, TDT[dt], dev(res))
     pc = H.OrbitalsPreconditioning()
     pc.setup(orb, levels, lap_type)
+    pc.set_mode(1)  # the literal reference-shaped sequence
     pc.gamma_ = 0.31
     pc.precond_mg(orb)
+    assert pc.last_mode() == 1
     ref = port.precond_mg(lap_type, levels, res, ll, 0.31, bc)
     assert bits_equal(host(orb.psi()), ref)
     # a second application reuses the resident work blocks
@@ -309,11 +311,122 @@ def test_precond_against_golden(H, golden, dt, tag):
                 orb = H.Orbitals(grid, N, TDT[dt], dev(res))
                 pc = H.OrbitalsPreconditioning()
                 pc.setup(orb, lev, lap_type)
+                pc.set_mode(1)
                 pc.gamma_ = 0.37
                 pc.precond_mg(orb)
                 ref = golden["precond_lap%d_lev%d_%s_bc%d%d%d" % ((lap_type, lev, tag) + bc)]
                 assert bits_equal(host(orb.psi()), ref)
                 pc.close()
+                # the fused kernels (float difference-form stencils): 1e-6 of the
+                # per-function max norm, ten times inside the FP32 bar of 1e-5
+                orb = H.Orbitals(grid, N, TDT[dt], dev(res))
+                pc = H.OrbitalsPreconditioning()
+                pc.setup(orb, lev, lap_type)
+                pc.gamma_ = 0.37
+                pc.precond_mg(orb)
+                if pc.last_mode() == 2:
+                    assert rel_inf(host(orb.psi()), ref) <= MG_TOL
+                else:
+                    assert bits_equal(host(orb.psi()), ref)
+                pc.close()
+
+
+MG_TOL = 1e-6
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("lap_type", [0, 2])
+@pytest.mark.parametrize("bc", [(1, 1, 1), (0, 0, 0)])
+@pytest.mark.parametrize("levels,dims", [(0, (8, 8, 8)), (1, (16, 24, 32)), (2, (16, 24, 32)),
+                                         (2, (32, 16, 64)), (1, (8, 12, 16))])
+def test_precond_mg_fused(H, port, dt, lap_type, bc, levels, dims):
+    """Fused V-cycle (one pass per Jacobi sweep, no-ghost blocks) against the
+    oracle's literal Preconditioning<float>::mg."""
+    ll, N = tuple(0.25 * d for d in dims), 5
+    res = synthetic_orbitals(N, dims, dt)
+    grid = H.Grid(dims, ll, H.ghosts_for(lap_type), bc)
+    orb = H.Orbitals(grid, N, TDT[dt], dev(res))
+    pc = H.OrbitalsPreconditioning()
+    pc.setup(orb, levels, lap_type)
+    pc.set_mode(2)
+    pc.gamma_ = 0.31
+    pc.precond_mg(orb)
+    assert pc.last_mode() == 2
+    ref = port.precond_mg(lap_type, levels, res, ll, 0.31, bc)
+    assert rel_inf(host(orb.psi()), ref) <= MG_TOL
+    pc.precond_mg(orb)  # resident work blocks are reused
+    ref2 = port.precond_mg(lap_type, levels, ref, ll, 0.31, bc)
+    assert rel_inf(host(orb.psi()), ref2) <= 2 * MG_TOL
+    pc.close()
+
+
+@pytest.mark.parametrize("bc", [(1, 0, 1), (0, 1, 1), (1, 1, 0)])
+def test_precond_mg_mixed_bc_stays_literal(H, port, bc):
+    """Mixed periodic/Dirichlet boxes: the reference's result depends on ghost
+    values its zeroing skips, so these boxes run the literal sequence
+    (bit-identical) and refuse the fused mode."""
+    from mgmol_b200._lib import MgbError
+    dims, ll, N = (16, 24, 32), (4.0, 6.0, 8.0), 3
+    res = synthetic_orbitals(N, dims, np.float32)
+    grid = H.Grid(dims, ll, 1, bc)
+    orb = H.Orbitals(grid, N, torch.float32, dev(res))
+    pc = H.OrbitalsPreconditioning()
+    pc.setup(orb, 2, 0)
+    with pytest.raises(MgbError):
+        pc.set_mode(2)
+    pc.gamma_ = 0.31
+    pc.precond_mg(orb)
+    assert pc.last_mode() == 1
+    assert bits_equal(host(orb.psi()), port.precond_mg(0, 2, res, ll, 0.31, bc))
+    pc.close()
+
+
+@pytest.mark.parametrize("cfg", ["4,1,1,5,0", "2,2,2,4,5", "4,2,3,6,7", "2,4,1,7,4"])
+@pytest.mark.parametrize("lap_type", [0, 2])
+def test_precond_mg_fused_tile_configs(H, port, lap_type, cfg):
+    """Every tile shape of the Jacobi kernel (rows per thread, row groups,
+    functions per CTA, ring depth, x chunk) gives the same numbers."""
+    dims, ll, N = (16, 16, 32), (4.0, 4.0, 8.0), 4
+    res = synthetic_orbitals(N, dims, np.float32)
+    ref = port.precond_mg(lap_type, 1, res, ll, 0.31, (1, 1, 1))
+    os.environ["MGB_MG_CFG"] = cfg
+    try:
+        grid = H.Grid(dims, ll, H.ghosts_for(lap_type))
+        orb = H.Orbitals(grid, N, torch.float32, dev(res))
+        pc = H.OrbitalsPreconditioning()
+        pc.setup(orb, 1, lap_type)
+        pc.set_mode(2)
+        pc.gamma_ = 0.31
+        pc.precond_mg(orb)
+        assert rel_inf(host(orb.psi()), ref) <= MG_TOL
+        pc.close()
+    finally:
+        del os.environ["MGB_MG_CFG"]
+
+
+@pytest.mark.parametrize("lap_type", [0, 2])
+def test_precond_mg_fused_equals_literal_full_size(H, lap_type):
+    """128^3 (H2O_64's grid): fused against the literal path, which the small
+    tests pin bit-for-bit to the reference."""
+    n, N = 128, 3
+    grid = H.Grid((n, n, n), (23.5,) * 3, H.ghosts_for(lap_type))
+    g = torch.Generator(device="cuda").manual_seed(5)
+    res = torch.rand((N, n, n, n), generator=g, device="cuda", dtype=torch.float32) - 0.5
+    x = torch.arange(n, device="cuda", dtype=torch.float32) / n
+    res += torch.cos(2 * np.pi * x)[None, :, None, None] * torch.sin(4 * np.pi * x)[None, None, None, :]
+    outs = {}
+    for mode in (1, 2):
+        orb = H.Orbitals(grid, N, torch.float32, res.clone())
+        pc = H.OrbitalsPreconditioning()
+        pc.setup(orb, 2, lap_type)
+        pc.set_mode(mode)
+        pc.gamma_ = 0.2
+        pc.precond_mg(orb)
+        assert pc.last_mode() == mode
+        outs[mode] = orb.psi().double()
+        pc.close()
+    scale = outs[1].abs().amax(dim=(1, 2, 3), keepdim=True)
+    assert float(((outs[1] - outs[2]).abs() / scale).max()) <= MG_TOL
 
 
 def test_precond_errors(H):
