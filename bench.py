@@ -176,6 +176,78 @@ def run_reference(args):
 # ---------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------
+def _time_cuda(torch, fn, reps=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    return float(np.median(ts))
+
+
+def measure_pieces(H, grid, phi, ham, lap_type, tdt, S, norb, npt):
+    """The other three pieces of the path on the same orbital block (outside the
+    timed region of the headline metric): multigrid-preconditioned residual,
+    Gram, projected Hamiltonian, orbital mixing; each with the roofline that
+    bounds it.  FP64 tensor peak = cuBLAS DGEMM measured here (MEASURED_PEAKS
+    has no FP64 entry)."""
+    import torch
+    hbm, _ = measured_peaks()
+    out = {}
+    # FP64 tensor (DMMA) peak: large square cuBLAS DGEMM, best of 5
+    m = 4096
+    x = torch.rand((m, m), device="cuda", dtype=torch.float64)
+    y = torch.rand((m, m), device="cuda", dtype=torch.float64)
+    best = min(_time_cuda(torch, lambda: torch.matmul(x, y), reps=3, warm=1) for _ in range(2))
+    fp64_peak = 2.0 * m ** 3 / (best * 1e-3) / 1e12
+    del x, y
+    out["fp64_tensor_peak_tflops"] = {"value": fp64_peak,
+                                      "how": "cuBLAS DGEMM 4096^3 via torch.matmul, measured in this run"}
+    upd = float(npt) * norb
+    hphi = ham.applyLocal(phi)
+    # multigrid-preconditioned residual (OrbitalsPreconditioning::precond_mg)
+    res = H.Orbitals(grid, norb, tdt)
+    res.psi().copy_(hphi.psi())
+    pc = H.OrbitalsPreconditioning()
+    pc.setup(res, 2, lap_type)
+    pc.gamma_ = 0.3
+    ms = _time_cuda(torch, lambda: pc.precond_mg(res))
+    model = (74.0 + 2 * S) * upd  # SURVEY.md 8(d): streaming model of the V-cycle
+    out["precond_mg"] = {"ms": ms, "updates_per_s": upd / (ms * 1e-3), "mg_levels": 2,
+                         "mode": {1: "literal", 2: "fused"}.get(pc.last_mode()),
+                         "roofline": {"bound": "hbm", "achieved": model / (ms * 1e-3) / 1e9,
+                                      "peak": hbm, "unit": "GB/s",
+                                      "frac": model / (ms * 1e-3) / 1e9 / hbm,
+                                      "model_bytes_per_update": 74.0 + 2 * S}}
+    pc.close()
+    del res
+    fl = float(norb) * norb * npt
+    ms = _time_cuda(torch, lambda: phi.computeGram())
+    out["gram"] = {"ms": ms, "roofline": {"bound": "tensor", "achieved": fl / (ms * 1e-3) / 1e12,
+                                          "peak": fp64_peak, "unit": "TFLOP/s",
+                                          "frac": fl / (ms * 1e-3) / 1e12 / fp64_peak,
+                                          "flops": "N^2 K (syrk)"}}
+    ms = _time_cuda(torch, lambda: phi.computeLocalProduct(hphi))
+    out["phiT_H_phi"] = {"ms": ms, "roofline": {"bound": "tensor", "achieved": 2 * fl / (ms * 1e-3) / 1e12,
+                                                "peak": fp64_peak, "unit": "TFLOP/s",
+                                                "frac": 2 * fl / (ms * 1e-3) / 1e12 / fp64_peak,
+                                                "flops": "2 N^2 K"}}
+    M = torch.rand((norb, norb), device="cuda", dtype=torch.float64) - 0.5
+    prod = H.Orbitals(grid, norb, tdt)
+    ms = _time_cuda(torch, lambda: phi.multiplyByMatrix(M, prod))
+    out["phi_M"] = {"ms": ms, "roofline": {"bound": "tensor", "achieved": 2 * fl / (ms * 1e-3) / 1e12,
+                                           "peak": fp64_peak, "unit": "TFLOP/s",
+                                           "frac": 2 * fl / (ms * 1e-3) / 1e12 / fp64_peak,
+                                           "flops": "2 N^2 K"}}
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -268,31 +340,43 @@ def run_ours(args):
     kern_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
     clocks = sampler.summary() if sampler else None
 
-    # end-to-end through the plugin call with HOST buffers: pinned H2D of the
-    # orbital block, H psi, D2H of the result, all inside the timed region
+    # end-to-end through the reference-facing call with HOST buffers: pinned
+    # host orbitals in, pinned host H psi out.  N = 1: one mgb_hpsi_host call per
+    # step (H2D, kernel and D2H pipelined over orbital blocks inside the
+    # library).  N > 1: copy in, halo exchange + kernel, copy out.
     h_phi = torch.empty(phi.psi().shape, dtype=tdt).pin_memory()
     h_phi.copy_(phi.psi())
     h_out = torch.empty_like(h_phi).pin_memory()
+    h_v = torch.empty(vtot.shape, dtype=torch.float64).pin_memory()
+    h_v.copy_(vtot)
     e2e_steps = max(2, min(args.steps, 5))
 
     def e2e_step():
-        phi.psi().copy_(h_phi, non_blocking=True)
-        out = step()
-        h_out.copy_(out.psi(), non_blocking=True)
+        if world == 1:
+            ham.lapOper().applyWithPotHost(h_phi, h_v, h_out)
+        else:
+            phi.psi().copy_(h_phi, non_blocking=True)
+            out = step()
+            h_out.copy_(out.psi(), non_blocking=True)
 
     e2e_step()
     barrier()
+    t0 = time.perf_counter()
     ev0.record()
     for _ in range(e2e_steps):
         e2e_step()
     ev1.record()
     barrier()
-    e2e_ms = ev0.elapsed_time(ev1)
+    e2e_ms = max(ev0.elapsed_time(ev1), (time.perf_counter() - t0) * 1e3)
 
     t = torch.tensor([ms, e2e_ms, kern_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, e2e_ms, kern_ms = (float(v) for v in t.cpu())
+
+    pieces = None
+    if world == 1 and not args.no_pieces:
+        pieces = measure_pieces(H, grid, phi, ham, lap_type, tdt, S, norb, npt)
 
     if rank == 0:
         updates_per_step = float(npt) * norb * world
@@ -328,6 +412,8 @@ def run_ours(args):
             "cpu_baseline": {"value": cpu_rate, "unit": "updates/s", "cores": cores,
                              "kind": kind, "sample": sample},
         }
+        if pieces:
+            line["pieces"] = pieces
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -343,6 +429,8 @@ def main():
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--lap", type=int, default=None)
     ap.add_argument("--orbitals", type=int, default=0)
+    ap.add_argument("--no-pieces", action="store_true",
+                    help="skip the per-piece measurements (V-cycle, contractions)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

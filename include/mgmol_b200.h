@@ -121,6 +121,21 @@ int mgb_hpsi(int lap_type, int dtype, const mgb_grid* grid, const void* phi,
     size_t ld, const double* vtot, void* hphi, size_t ldh, int nfunc,
     const void* xhalo_phi, const double* xhalo_v, void* stream);
 
+/* The same operator for a caller whose orbitals live in HOST memory (MGmol's
+ * default MemorySpace::Host build: BlockVector storage, src/BlockVector.cc:
+ * 138-218): phi_host, vtot_host and hphi_host are host pointers.  The call
+ * pipelines host->device copy, fused kernel and device->host copy over blocks
+ * of `chunk` orbitals (0 = automatic, ~128 MB) on three internal streams so
+ * that both PCIe directions and the GPU are busy at once, and returns when
+ * hphi_host holds the result (synchronous, like the reference call).  Pin the
+ * buffers once with mgb_host_register (cudaHostRegister) for full PCIe rate;
+ * pageable buffers work but are staged by the driver.  Single-rank boxes.   */
+int mgb_hpsi_host(int lap_type, int dtype, const mgb_grid* grid, const void* phi_host,
+    size_t ld, const double* vtot_host, void* hphi_host, size_t ldh, int nfunc,
+    int chunk);
+int mgb_host_register(void* ptr, size_t bytes);
+int mgb_host_unregister(void* ptr);
+
 /* Which implementation mgb_hpsi picked last (for tests and the bench):
  * 1 TMA-pipelined fused kernel, 2 generic fused kernel, 3 ghosted-block
  * composition.                                                              */

@@ -1,0 +1,555 @@
+// mgmol_b200.hpp -- C++ host side of the B200 hot path, above the C ABI of
+// mgmol_b200.h.  Header-only; needs only a C++11 compiler (no CUDA headers) and
+// libmgmol_b200.so at link time.
+//
+// The classes mirror the reference's operator API for this path -- same names,
+// same method names, same argument meaning, same error behaviour (the reference
+// aborts: src/pb/Lap.h:37-38, src/pb/FDkernels.h:42-45) -- so MGmol's driver
+// code (src/computeHij.cc:404-455, src/MGmol.cc:1191-1291, src/ABPG.cc:73-140)
+// reads the same against either implementation.  INTEGRATION.md shows where
+// each one slots into the MGmol tree.
+//
+//   reference class (file)                          here
+//   MemorySpace::Memory<T,Device> (tools/memory_space.h:253-333)  DeviceMemory<T>
+//   pb::Grid + pb::PEenv (pb/Grid.h:24-121)                       Grid
+//   pb::GridFuncVector<T,Device> (pb/GridFuncVector.h:30-493)     GridFuncVector<T>
+//   pb::Lap<T>, LapFactory<T> (pb/Lap.h:19-54, LapFactory.h:26-56) Lap<T>, LapFactory<T>
+//   Potentials (Potentials.h:141: vtot, iterative index)          Potentials
+//   ExtendedGridOrbitals (ExtendedGridOrbitals.h:43-404)          ExtendedGridOrbitals<T>
+//   Hamiltonian<T> (Hamiltonian.h:20-52)                          Hamiltonian<T>
+//   OrbitalsPreconditioning<T> (OrbitalsPreconditioning.h:27-70)  OrbitalsPreconditioning<T>
+#ifndef MGMOL_B200_HPP
+#define MGMOL_B200_HPP
+
+#include <cassert>
+#include <cstdio>
+#include <cstdlib>
+#include <memory>
+#include <vector>
+
+#include "mgmol_b200.h"
+
+namespace mgmol_b200
+{
+
+// The reference has no error codes on this path: a failed precondition ends
+// the run.  Same here, with the library's message.
+inline void check(int rc, const char* where)
+{
+    if (rc != MGB_OK)
+    {
+        std::fprintf(stderr, "mgmol_b200: %s failed (%d): %s\n", where, rc, mgb_last_error());
+        std::abort();
+    }
+}
+#define MGB_CHECK(call) ::mgmol_b200::check((call), #call)
+
+template <typename T>
+struct dtype_of;
+template <>
+struct dtype_of<float>
+{
+    static const int value = MGB_F32;
+};
+template <>
+struct dtype_of<double>
+{
+    static const int value = MGB_F64;
+};
+
+// MemorySpace::Memory<T, MemorySpace::Device>: allocate / free / copy / set.
+template <typename T>
+class DeviceMemory
+{
+public:
+    DeviceMemory() : ptr_(nullptr), size_(0) {}
+    explicit DeviceMemory(size_t n) : ptr_(nullptr), size_(0) { allocate(n); }
+    ~DeviceMemory() { free(); }
+    DeviceMemory(const DeviceMemory&) = delete;
+    DeviceMemory& operator=(const DeviceMemory&) = delete;
+    void allocate(size_t n)
+    {
+        free();
+        void* p = nullptr;
+        MGB_CHECK(mgb_malloc(&p, n * sizeof(T)));
+        ptr_  = static_cast<T*>(p);
+        size_ = n;
+    }
+    void free()
+    {
+        if (ptr_) MGB_CHECK(mgb_free(ptr_));
+        ptr_  = nullptr;
+        size_ = 0;
+    }
+    void set(int value, void* stream = nullptr)
+    {
+        MGB_CHECK(mgb_memset(ptr_, value, size_ * sizeof(T), stream));
+    }
+    void copy_to_dev(const T* host, size_t n, void* stream = nullptr)
+    {
+        assert(n <= size_);
+        MGB_CHECK(mgb_copy_to_dev(ptr_, host, n * sizeof(T), stream));
+    }
+    void copy_to_host(T* host, size_t n, void* stream = nullptr) const
+    {
+        assert(n <= size_);
+        MGB_CHECK(mgb_copy_to_host(host, ptr_, n * sizeof(T), stream));
+        MGB_CHECK(mgb_stream_sync(stream));
+    }
+    T* data() { return ptr_; }
+    const T* data() const { return ptr_; }
+    size_t size() const { return size_; }
+
+private:
+    T* ptr_;
+    size_t size_;
+};
+
+// GridFactory (src/GridFactory.h:23-51): ghost width per operator
+inline short ghostsFor(const int lap_type)
+{
+    switch (lap_type)
+    {
+        case MGB_LAP_4: return 2;
+        case MGB_LAP_6: return 3;
+        case MGB_LAP_8: return 4;
+        default: return 1;
+    }
+}
+
+// pb::Grid + the slice of pb::PEenv the path needs
+class Grid
+{
+public:
+    Grid(const unsigned gdim[3], const double lattice[3], const short nghosts,
+        const int bc[3] = nullptr, const int nproc[3] = nullptr,
+        const int coord[3] = nullptr)
+    {
+        for (int d = 0; d < 3; d++)
+        {
+            c_.nproc[d] = nproc ? nproc[d] : 1;
+            c_.coord[d] = coord ? coord[d] : 0;
+            c_.bc[d]    = bc ? bc[d] : 1;
+            c_.gdim[d]  = (int)gdim[d];
+            // Grid.cc:49-54: dim = gdim / n_mpi_task, exact
+            if (gdim[d] % c_.nproc[d] != 0)
+            {
+                std::fprintf(stderr, "Grid: gdim[%d]=%u not divisible by %d tasks\n", d,
+                    gdim[d], c_.nproc[d]);
+                std::abort();
+            }
+            c_.dim[d] = (int)gdim[d] / c_.nproc[d];
+            ll_[d]    = lattice[d];
+            c_.h[d]   = lattice[d] / gdim[d];
+        }
+        c_.ghosts = nghosts;
+    }
+    int dim(const short i) const { return c_.dim[i]; }
+    int gdim(const short i) const { return c_.gdim[i]; }
+    short ghost_pt() const { return (short)c_.ghosts; }
+    double hgrid(const short i) const { return c_.h[i]; }
+    double vel() const { return c_.h[0] * c_.h[1] * c_.h[2]; }
+    size_t size() const { return (size_t)c_.dim[0] * c_.dim[1] * c_.dim[2]; }
+    size_t sizeg() const
+    {
+        const size_t g = 2 * c_.ghosts;
+        return (c_.dim[0] + g) * (c_.dim[1] + g) * (c_.dim[2] + g);
+    }
+    // Grid::coarse_grid (src/pb/Grid.cc:214-231): half the points, same ghosts
+    Grid coarse_grid() const
+    {
+        unsigned gd[3] = { (unsigned)c_.gdim[0] / 2, (unsigned)c_.gdim[1] / 2,
+            (unsigned)c_.gdim[2] / 2 };
+        return Grid(gd, ll_, (short)c_.ghosts, c_.bc, c_.nproc, c_.coord);
+    }
+    Grid with_ghosts(const short g) const
+    {
+        Grid r(*this);
+        r.c_.ghosts = g;
+        return r;
+    }
+    const mgb_grid* c() const { return &c_; }
+
+private:
+    mgb_grid c_;
+    double ll_[3];
+};
+
+// pb::GridFuncVector<T, MemorySpace::Device>: nfunc ghosted functions in one
+// device allocation, with the updated_boundaries_ bookkeeping of the reference.
+template <typename T>
+class GridFuncVector
+{
+public:
+    GridFuncVector(const Grid& grid, const int nfunc)
+        : grid_(grid), nfunc_(nfunc), mem_(grid.sizeg() * (size_t)nfunc),
+          updated_boundaries_(false)
+    {
+        resetData();
+    }
+    const Grid& grid() const { return grid_; }
+    int size() const { return nfunc_; }
+    T* data() { return mem_.data(); }
+    void resetData(void* stream = nullptr)
+    {
+        mem_.set(0, stream);
+        updated_boundaries_ = true;
+    }
+    void set_updated_boundaries(const bool f) { updated_boundaries_ = f; }
+    // BlockVector::setDataWithGhosts (src/BlockVector.cc:489-517)
+    template <typename T2>
+    void assign(const T2* noghost_dev, const size_t ld, void* stream = nullptr)
+    {
+        MGB_CHECK(mgb_gfv_set_with_ghosts(dtype_of<T2>::value, dtype_of<T>::value, grid_.c(),
+            noghost_dev, ld, mem_.data(), nfunc_, stream));
+        updated_boundaries_ = false;
+    }
+    // BlockVector::assign(GridFuncVector) (src/BlockVector.cc:303-311)
+    template <typename T2>
+    void getValues(T2* noghost_dev, const size_t ld, void* stream = nullptr)
+    {
+        MGB_CHECK(mgb_gfv_get_values(dtype_of<T>::value, dtype_of<T2>::value, grid_.c(),
+            mem_.data(), noghost_dev, ld, nfunc_, stream));
+    }
+    // src/pb/GridFuncVector.cc:1544-1622 (directions owned by one rank)
+    void trade_boundaries(void* stream = nullptr)
+    {
+        if (updated_boundaries_) return;
+        MGB_CHECK(mgb_gfv_trade_boundaries(
+            dtype_of<T>::value, grid_.c(), mem_.data(), nfunc_, stream));
+        updated_boundaries_ = true;
+    }
+    // src/pb/GridFuncVector.cc:2370-2397
+    void applyLap(const int type, GridFuncVector<T>& rhs, void* stream = nullptr)
+    {
+        static const int kinds[5] = { MGB_FD_DEL2_4TH_MEHR, MGB_FD_DEL2_2ND, MGB_FD_DEL2_4TH,
+            MGB_FD_DEL2_6TH, MGB_FD_DEL2_8TH };
+        if (type < 0 || type > 4)
+        {
+            std::fprintf(stderr, "GridFuncVector::applyLap: option invalid: %d\n", type);
+            std::abort();
+        }
+        trade_boundaries(stream);
+        MGB_CHECK(mgb_fd_apply(kinds[type], dtype_of<T>::value, grid_.c(), mem_.data(),
+            rhs.data(), nfunc_, 0, stream));
+        rhs.set_updated_boundaries(false);
+    }
+    // src/pb/GridFuncVector.cc:2400-2413
+    void applyRHS(const int type, GridFuncVector<T>& rhs, void* stream = nullptr)
+    {
+        trade_boundaries(stream);
+        if (type == 0)
+            MGB_CHECK(mgb_fd_apply(MGB_FD_RHS_4TH_MEHR1, dtype_of<T>::value, grid_.c(),
+                mem_.data(), rhs.data(), nfunc_, grid_.ghost_pt(), stream));
+        else
+            MGB_CHECK(mgb_copy_dev(
+                rhs.data(), mem_.data(), grid_.sizeg() * nfunc_ * sizeof(T), stream));
+        rhs.set_updated_boundaries(false);
+    }
+    // src/pb/GridFuncVector.cc:90-136; V: ghosted double field on the device
+    void pointwiseProduct(GridFuncVector<T>& A, const double* Vghost, void* stream = nullptr)
+    {
+        MGB_CHECK(mgb_gfv_pointwise_product(dtype_of<T>::value, grid_.c(), A.data(), Vghost,
+            mem_.data(), nfunc_, stream));
+        updated_boundaries_ = A.updated_boundaries_;
+    }
+    // src/pb/GridFuncVector.cc:1645-1668
+    void axpy(const double alpha, GridFuncVector<T>& x, void* stream = nullptr)
+    {
+        MGB_CHECK(mgb_axpy(dtype_of<T>::value, grid_.sizeg() * (size_t)nfunc_, alpha, x.data(),
+            mem_.data(), stream));
+        updated_boundaries_ = updated_boundaries_ && x.updated_boundaries_;
+    }
+    GridFuncVector<T>& operator-=(GridFuncVector<T>& x)
+    {
+        axpy(-1., x);
+        return *this;
+    }
+    // src/pb/GridFuncVector.cc:1624-1641
+    void restrict3D(GridFuncVector<T>& coarse, void* stream = nullptr)
+    {
+        trade_boundaries(stream);
+        MGB_CHECK(mgb_gfv_restrict3D(
+            dtype_of<T>::value, grid_.c(), mem_.data(), coarse.data(), nfunc_, stream));
+        coarse.set_updated_boundaries(false);
+    }
+    void extend3D(GridFuncVector<T>& coarse, void* stream = nullptr)
+    {
+        coarse.trade_boundaries(stream);
+        MGB_CHECK(mgb_gfv_extend3D(
+            dtype_of<T>::value, grid_.c(), coarse.data(), mem_.data(), nfunc_, stream));
+        updated_boundaries_ = false;
+    }
+
+private:
+    Grid grid_;
+    int nfunc_;
+    DeviceMemory<T> mem_;
+    bool updated_boundaries_;
+};
+
+// Potentials: the slice the path reads -- vtot (POTDTYPE double, no ghosts,
+// src/Potentials.h:141) on the device and its iterative index
+class Potentials
+{
+public:
+    explicit Potentials(const size_t npt) : vtot_(npt), itindex_(0) {}
+    void setVtot(const double* host, void* stream = nullptr)
+    {
+        vtot_.copy_to_dev(host, vtot_.size(), stream);
+        itindex_++;
+    }
+    const double* vtot() const { return vtot_.data(); }
+    double* vtot() { return vtot_.data(); }
+    int getIterativeIndex() const { return itindex_; }
+    void incrementIterativeIndex() { itindex_++; }
+
+private:
+    DeviceMemory<double> vtot_;
+    int itindex_;
+};
+
+// ExtendedGridOrbitals reduced to the hot path: psi is the no-ghost
+// column-major numpt x numst block (lda = numpt, src/BlockVector.cc:79) in
+// device memory; the iterative index keys Hamiltonian's cache
+// (src/Orbitals.h:43-70).
+template <typename T>
+class ExtendedGridOrbitals
+{
+public:
+    ExtendedGridOrbitals(const Grid& grid, const int numst)
+        : grid_(grid), numst_(numst), numpt_(grid.size()), lda_(grid.size()),
+          psi_(grid.size() * (size_t)numst), iterative_index_(0)
+    {
+        psi_.set(0);
+    }
+    int numst() const { return numst_; }
+    int chromatic_number() const { return numst_; }
+    size_t getNumpt() const { return numpt_; }
+    size_t getLda() const { return lda_; }
+    const Grid& grid() const { return grid_; }
+    T* getPsi(const int i = 0) { return psi_.data() + (size_t)i * lda_; }
+    const T* getPsi(const int i = 0) const { return psi_.data() + (size_t)i * lda_; }
+    int getIterativeIndex() const { return iterative_index_; }
+    void incrementIterativeIndex() { iterative_index_++; }
+    // host <-> device of the whole block (BlockVector storage)
+    void setPsi(const T* host, void* stream = nullptr)
+    {
+        psi_.copy_to_dev(host, psi_.size(), stream);
+        incrementIterativeIndex();
+    }
+    void getPsiHost(T* host, void* stream = nullptr) const
+    {
+        psi_.copy_to_host(host, psi_.size(), stream);
+    }
+    // src/ExtendedGridOrbitals.cc:202-212 and BlockVector.h:112-126
+    void axpy(const double alpha, const ExtendedGridOrbitals<T>& x, void* stream = nullptr)
+    {
+        MGB_CHECK(mgb_axpy(dtype_of<T>::value, psi_.size(), alpha, x.getPsi(), getPsi(), stream));
+        incrementIterativeIndex();
+    }
+    void scal(const double alpha, void* stream = nullptr)
+    {
+        MGB_CHECK(mgb_scal(dtype_of<T>::value, psi_.size(), alpha, getPsi(), stream));
+        incrementIterativeIndex();
+    }
+    // computeGram / getLocalOverlap (src/ExtendedGridOrbitals.cc:985-1010,
+    // 1138-1162): ss_dev(numst x numst, column-major double) = vel Phi^T Phi
+    void computeGram(double* ss_dev, mgb_comm* comm = nullptr, void* stream = nullptr) const
+    {
+        MGB_CHECK(mgb_syrk_t(dtype_of<T>::value, numst_, numpt_, grid_.vel(), getPsi(), lda_,
+            ss_dev, numst_, stream));
+        if (comm)
+            MGB_CHECK(mgb_allreduce_sum_f64(comm, ss_dev, (size_t)numst_ * numst_, stream));
+    }
+    // computeLocalProduct / addDotWithNcol2Matrix
+    // (src/ExtendedGridOrbitals.cc:1049-1083, 1704-1752): vel Phi^T A
+    void computeLocalProduct(const ExtendedGridOrbitals<T>& A, double* ss_dev,
+        mgb_comm* comm = nullptr, void* stream = nullptr) const
+    {
+        MGB_CHECK(mgb_gemm_tn(dtype_of<T>::value, numst_, A.numst(), numpt_, grid_.vel(),
+            getPsi(), lda_, A.getPsi(), A.getLda(), 0., ss_dev, numst_, stream));
+        if (comm)
+            MGB_CHECK(mgb_allreduce_sum_f64(comm, ss_dev, (size_t)numst_ * A.numst(), stream));
+    }
+    // multiplyByMatrix (src/ExtendedGridOrbitals.cc:448-498): product = Phi M,
+    // M column-major numst x n on the device
+    void multiplyByMatrix(const double* matrix_dev, const int n,
+        ExtendedGridOrbitals<T>& product, void* stream = nullptr) const
+    {
+        MGB_CHECK(mgb_gemm_nn(dtype_of<T>::value, numpt_, n, numst_, 1., getPsi(), lda_,
+            matrix_dev, numst_, 0., product.getPsi(), product.getLda(), stream));
+        product.incrementIterativeIndex();
+    }
+
+private:
+    Grid grid_;
+    int numst_;
+    size_t numpt_, lda_;
+    DeviceMemory<T> psi_;
+    int iterative_index_;
+};
+
+// pb::Lap<T> as LapFactory creates it
+template <typename T>
+class Lap
+{
+public:
+    Lap(const Grid& grid, const int type) : grid_(grid), type_(type)
+    {
+        double h[3] = { grid.hgrid(0), grid.hgrid(1), grid.hgrid(2) }, out[3];
+        MGB_CHECK(mgb_lap_constants(type, h, out));
+        diagEl_ = out[0], invDiagEl_ = out[1], jacobiFactor_ = out[2];
+    }
+    double diagEl() const { return diagEl_; }
+    double invDiagEl() const { return invDiagEl_; }
+    double jacobiFactor() const { return jacobiFactor_; }
+    short minNumberGhosts() const { return ghostsFor(type_); }
+    int type() const { return type_; }
+    // Lap<T>::apply on a block (src/pb/Laph4.h:99-102)
+    void apply(GridFuncVector<T>& A, GridFuncVector<T>& B, void* stream = nullptr)
+    {
+        A.applyLap(type_ == MGB_LAP_4MP ? 0 : type_, B, stream);
+    }
+    // Lap<T>::applyWithPot (src/pb/Lap.h:35; only Laph4M/4MP/4 implement it,
+    // the others abort) for the whole block = Hamiltonian::applyLocal body
+    void applyWithPot(const T* phi, const size_t ld, const double* vtot, T* hphi,
+        const size_t ldh, const int nfunc, const void* xhalo_phi = nullptr,
+        const double* xhalo_v = nullptr, void* stream = nullptr)
+    {
+        MGB_CHECK(mgb_hpsi(type_, dtype_of<T>::value, grid_.c(), phi, ld, vtot, hphi, ldh,
+            nfunc, xhalo_phi, xhalo_v, stream));
+    }
+
+private:
+    Grid grid_;
+    int type_;
+    double diagEl_, invDiagEl_, jacobiFactor_;
+};
+
+// src/LapFactory.h:26-56
+template <typename T>
+struct LapFactory
+{
+    static Lap<T>* createLap(const Grid& grid, const int lap_type)
+    {
+        switch (lap_type)
+        {
+            case 0:
+            case 1:
+            case 2:
+            case 3:
+            case 4:
+            case 10:
+                return new Lap<T>(grid, lap_type);
+            default:
+                std::fprintf(stderr, "LapFactory::createLap() --- option invalid:%d\n", lap_type);
+                std::abort();
+        }
+        return nullptr;
+    }
+};
+
+// Hamiltonian<OrbitalsType> (src/Hamiltonian.h:20-52, .cc:43-260)
+template <typename T>
+class Hamiltonian
+{
+public:
+    Hamiltonian() : itindex_(-1) {}
+    void setup(const Grid& myGrid, const int lap_type)
+    {
+        lapOper_.reset(LapFactory<T>::createLap(myGrid, lap_type));
+        pot_.reset(new Potentials(myGrid.size()));
+    }
+    Lap<T>* lapOper() { return lapOper_.get(); }
+    Potentials& potential() { return *pot_; }
+    // src/Hamiltonian.cc:43-83: recompute only when 100*phi.index + pot.index
+    // changed (or force)
+    const ExtendedGridOrbitals<T>& applyLocal(
+        ExtendedGridOrbitals<T>& phi, const bool force = false, void* stream = nullptr)
+    {
+        if (!hlphi_ || hlphi_->numst() != phi.numst())
+        {
+            hlphi_.reset(new ExtendedGridOrbitals<T>(phi.grid(), phi.numst()));
+            itindex_ = -1;
+        }
+        const int new_index = 100 * phi.getIterativeIndex() + pot_->getIterativeIndex();
+        if (force || new_index != itindex_)
+        {
+            applyLocal(phi.chromatic_number(), phi, *hlphi_, stream);
+            itindex_ = new_index;
+        }
+        return *hlphi_;
+    }
+    // src/Hamiltonian.cc:85-159: one fused pass
+    void applyLocal(const int ncolors, ExtendedGridOrbitals<T>& phi,
+        ExtendedGridOrbitals<T>& hphi, void* stream = nullptr)
+    {
+        lapOper_->applyWithPot(phi.getPsi(), phi.getLda(), pot_->vtot(), hphi.getPsi(),
+            hphi.getLda(), ncolors, nullptr, nullptr, stream);
+        hphi.incrementIterativeIndex();
+    }
+    // src/Hamiltonian.cc:214-239: hij_dev = vel Phi1^T (H_loc Phi2)
+    void addHlocalij(ExtendedGridOrbitals<T>& phi1, ExtendedGridOrbitals<T>& phi2,
+        double* hij_dev, mgb_comm* comm = nullptr, void* stream = nullptr)
+    {
+        applyLocal(phi2, false, stream);
+        phi1.computeLocalProduct(*hlphi_, hij_dev, comm, stream);
+    }
+
+private:
+    std::unique_ptr<Lap<T>> lapOper_;
+    std::unique_ptr<Potentials> pot_;
+    std::unique_ptr<ExtendedGridOrbitals<T>> hlphi_;
+    int itindex_;
+};
+
+// OrbitalsPreconditioning<OrbitalsType> (src/OrbitalsPreconditioning.h:27-70)
+template <typename T>
+class OrbitalsPreconditioning
+{
+public:
+    OrbitalsPreconditioning() : handle_(nullptr), gamma_(-1.), is_set_(false) {}
+    ~OrbitalsPreconditioning()
+    {
+        if (handle_) mgb_precond_destroy(handle_);
+    }
+    // src/OrbitalsPreconditioning.cc:44-84
+    void setup(ExtendedGridOrbitals<T>& orbitals, const short mg_levels, const short lap_type)
+    {
+        assert(!is_set_);
+        const Grid g = orbitals.grid().with_ghosts(ghostsFor(lap_type));
+        MGB_CHECK(mgb_precond_create(
+            &handle_, lap_type, mg_levels, g.c(), orbitals.chromatic_number()));
+        mg_levels_ = mg_levels;
+        is_set_    = true;
+    }
+    // src/OrbitalsPreconditioning.cc:120-145
+    void setGamma(const Lap<T>& lapOper, const double vmax, const short mg_levels,
+        const double small_eig)
+    {
+        gamma_ = mgb_gamma(lapOper.invDiagEl(), mg_levels, vmax, small_eig);
+    }
+    void setGamma(const double gamma) { gamma_ = gamma; }
+    double gamma() const { return gamma_; }
+    // src/OrbitalsPreconditioning.cc:87-117: orbitals <- M^-1 orbitals
+    void precond_mg(ExtendedGridOrbitals<T>& orbitals, void* stream = nullptr)
+    {
+        assert(is_set_);
+        assert(gamma_ > 0.);
+        MGB_CHECK(mgb_precond_mg(handle_, dtype_of<T>::value, orbitals.getPsi(),
+            orbitals.getLda(), orbitals.chromatic_number(), gamma_, stream));
+        orbitals.incrementIterativeIndex();
+    }
+    mgb_precond* handle() { return handle_; }
+
+private:
+    mgb_precond* handle_;
+    double gamma_;
+    short mg_levels_;
+    bool is_set_;
+};
+
+} // namespace mgmol_b200
+
+#endif // MGMOL_B200_HPP

@@ -298,4 +298,101 @@ int mgb_hpsi(int lap_type, int dtype, const mgb_grid* grid, const void* phi,
     return hpsi_ghosted(a, st);
 }
 
+
+/* ---- host-buffer entry: H2D copy, fused kernel and D2H copy pipelined over
+ * blocks of orbitals on three streams (full-duplex PCIe) ------------------- */
+int mgb_host_register(void* ptr, size_t bytes)
+{
+    if (int rc = require_device()) return rc;
+    MGB_REQUIRE(ptr && bytes, "mgb_host_register: null pointer or zero size");
+    MGB_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+    return MGB_OK;
+}
+int mgb_host_unregister(void* ptr)
+{
+    if (!ptr) return MGB_OK;
+    MGB_CUDA(cudaHostUnregister(ptr));
+    return MGB_OK;
+}
+
+int mgb_hpsi_host(int lap_type, int dtype, const mgb_grid* grid, const void* phi_host,
+    size_t ld, const double* vtot_host, void* hphi_host, size_t ldh, int nfunc,
+    int chunk)
+{
+    if (int rc = require_device()) return rc;
+    if (int rc = check_grid(grid)) return rc;
+    MGB_REQUIRE(phi_host && vtot_host && hphi_host, "mgb_hpsi_host: null pointer");
+    MGB_REQUIRE(dtype == MGB_F32 || dtype == MGB_F64, "mgb_hpsi_host: bad dtype %d", dtype);
+    MGB_REQUIRE(nfunc >= 0 && chunk >= 0, "mgb_hpsi_host: negative count");
+    MGB_REQUIRE(grid->nproc[0] == 1 && grid->nproc[1] == 1 && grid->nproc[2] == 1,
+        "mgb_hpsi_host: the host-buffer entry serves single-rank boxes; a split "
+        "domain keeps its orbitals resident and uses mgb_hpsi + mgb_halo_*");
+    const size_t npt = (size_t)grid->dim[0] * grid->dim[1] * grid->dim[2];
+    MGB_REQUIRE(ld >= npt && ldh >= npt, "mgb_hpsi_host: leading dimension < npt");
+    if (nfunc == 0) return MGB_OK;
+
+    constexpr int NS = 3; // ring slots per direction
+    static cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
+    static cudaEvent_t ev_in[NS], ev_k[NS], ev_out[NS];
+    if (!s_in)
+    {
+        MGB_CUDA(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
+        MGB_CUDA(cudaStreamCreateWithFlags(&s_k, cudaStreamNonBlocking));
+        MGB_CUDA(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+        for (int i = 0; i < NS; i++)
+        {
+            MGB_CUDA(cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming));
+            MGB_CUDA(cudaEventCreateWithFlags(&ev_k[i], cudaEventDisableTiming));
+            MGB_CUDA(cudaEventCreateWithFlags(&ev_out[i], cudaEventDisableTiming));
+        }
+    }
+    const size_t es = dtype == MGB_F64 ? 8 : 4;
+    // padded so that every slot and every orbital inside it is 16-byte aligned
+    const size_t ldd = (npt + 3) / 4 * 4;
+    if (chunk == 0)
+    {
+        // ~128 MB per block: large enough for full PCIe rate, small enough that
+        // the pipeline fill (one block in, one block out) stays negligible
+        chunk = (int)((size_t)(128u << 20) / (ldd * es));
+        if (chunk < 1) chunk = 1;
+    }
+    if (chunk > nfunc) chunk = nfunc;
+    const size_t slot_bytes = (size_t)chunk * ldd * es;
+    unsigned char* din  = (unsigned char*)scratch(3, NS * slot_bytes);
+    unsigned char* dout = (unsigned char*)scratch(4, NS * slot_bytes);
+    double* dv          = (double*)scratch(5, npt * sizeof(double));
+    if (!din || !dout || !dv) return MGB_ECUDA;
+    MGB_CUDA(cudaMemcpyAsync(dv, vtot_host, npt * sizeof(double), cudaMemcpyHostToDevice, s_in));
+
+    const int nchunks = (nfunc + chunk - 1) / chunk;
+    for (int i = 0; i < nchunks; i++)
+    {
+        const int slot = i % NS;
+        const int f0   = i * chunk;
+        const int nf   = (nfunc - f0 < chunk) ? nfunc - f0 : chunk;
+        unsigned char* in  = din + (size_t)slot * slot_bytes;
+        unsigned char* out = dout + (size_t)slot * slot_bytes;
+        // the kernel that last read this input slot must be done
+        if (i >= NS) MGB_CUDA(cudaStreamWaitEvent(s_in, ev_k[slot], 0));
+        MGB_CUDA(cudaMemcpy2DAsync(in, ldd * es, (const unsigned char*)phi_host + (size_t)f0 * ld * es,
+            ld * es, npt * es, (size_t)nf, cudaMemcpyHostToDevice, s_in));
+        MGB_CUDA(cudaEventRecord(ev_in[slot], s_in));
+        MGB_CUDA(cudaStreamWaitEvent(s_k, ev_in[slot], 0));
+        // the copy-out that last read this output slot must be done
+        if (i >= NS) MGB_CUDA(cudaStreamWaitEvent(s_k, ev_out[slot], 0));
+        if (int rc = mgb_hpsi(lap_type, dtype, grid, in, ldd, dv, out, ldd, nf, nullptr,
+                nullptr, (void*)s_k))
+            return rc;
+        MGB_CUDA(cudaEventRecord(ev_k[slot], s_k));
+        MGB_CUDA(cudaStreamWaitEvent(s_out, ev_k[slot], 0));
+        MGB_CUDA(cudaMemcpy2DAsync((unsigned char*)hphi_host + (size_t)f0 * ldh * es, ldh * es, out,
+            ldd * es, npt * es, (size_t)nf, cudaMemcpyDeviceToHost, s_out));
+        MGB_CUDA(cudaEventRecord(ev_out[slot], s_out));
+    }
+    MGB_CUDA(cudaStreamSynchronize(s_out));
+    MGB_CUDA(cudaStreamSynchronize(s_k));
+    MGB_CUDA(cudaStreamSynchronize(s_in));
+    return MGB_OK;
+}
+
 } // extern "C"

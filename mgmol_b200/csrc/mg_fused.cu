@@ -254,6 +254,16 @@ __global__ void __launch_bounds__(MAXT, 1) k_mg_jacobi(const __grid_constant__ J
         return x * m;
     };
 
+    // right-hand side of the first output plane (see the prefetch below)
+    float4 fnext[RY];
+    if (!SCALE && active)
+    {
+        const float* fp = P.f + (long long)orb * P.ld_f + (long long)xb * plane + pt0;
+#pragma unroll
+        for (int r = 0; r < RY; r++)
+            fnext[r] = __ldg(reinterpret_cast<const float4*>(fp + (long long)r * P.nz));
+    }
+
     int st_new = 0;       // stage of the plane arriving in this iteration
     uint32_t par_new = 0;
     int st_old = 0;       // stage of the oldest plane still needed
@@ -278,15 +288,37 @@ __global__ void __launch_bounds__(MAXT, 1) k_mg_jacobi(const __grid_constant__ J
                     }
                 }
                 const long long o0 = (long long)q * plane + pt0;
-                const float* fp    = P.f + (long long)orb * P.ld_f + o0;
                 const bool zx      = P.zero_low[0] && q == 0;
 
-                // right-hand side of all RY rows first: the loads are in
-                // flight while the taps come out of shared memory
+                // Right-hand side.  SCALE: the tile IS f (unscaled), read it
+                // back from shared memory.  Otherwise the values of this plane
+                // were requested one iteration ago (fnext) and the next
+                // plane's are requested now, so the global loads are in flight
+                // during a whole plane of shared-memory work.
                 float4 fv[RY];
+                if constexpr (SCALE)
+                {
 #pragma unroll
-                for (int r = 0; r < RY; r++)
-                    fv[r] = __ldg(reinterpret_cast<const float4*>(fp + (long long)r * P.nz));
+                    for (int r = 0; r < RY; r++)
+                    {
+                        float t[4];
+                        lds4(tb[G] + rowoff[r + G] + zoff, t);
+                        fv[r] = make_float4(t[0], t[1], t[2], t[3]);
+                    }
+                }
+                else
+                {
+#pragma unroll
+                    for (int r = 0; r < RY; r++)
+                        fv[r] = fnext[r];
+                    if (it + 1 < nplanes)
+                    {
+                        const float* fp = P.f + (long long)orb * P.ld_f + o0 + plane;
+#pragma unroll
+                        for (int r = 0; r < RY; r++)
+                            fnext[r] = __ldg(reinterpret_cast<const float4*>(fp + (long long)r * P.nz));
+                    }
+                }
 
                 auto finish = [&](int r, const float(&cen)[4], const float(&av)[4]) {
                     const float fr[4] = { fv[r].x, fv[r].y, fv[r].z, fv[r].w };
@@ -506,14 +538,15 @@ __global__ void k_mg_restrict(int nxc, int nyc, int nzc, int perx, int pery, int
     const float* __restrict__ fine, long long ldf, float* __restrict__ coarse,
     long long ldc)
 {
+    // block (zx, zy): zx threads along the coarse k-vectors, zy coarse rows;
+    // grid.x tiles (k-vector, row), grid.y = coarse plane, grid.z = function
     const int nzv = nzc >> 2;
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long per_f = (long long)nxc * nyc * nzv;
-    if (t >= per_f) return;
-    const int f  = blockIdx.y;
-    const int kv = (int)(t % nzv);
-    const int j  = (int)((t / nzv) % nyc);
-    const int i  = (int)(t / ((long long)nzv * nyc));
+    const int tz  = (nzv + blockDim.x - 1) / blockDim.x;
+    const int kv  = (blockIdx.x % tz) * blockDim.x + threadIdx.x;
+    const int j   = (blockIdx.x / tz) * blockDim.y + threadIdx.y;
+    const int i   = blockIdx.y;
+    const int f   = blockIdx.z;
+    if (kv >= nzv || j >= nyc) return;
     const int nx = 2 * nxc, ny = 2 * nyc, nz = 2 * nzc;
     const float* F = fine + (long long)f * ldf;
     const int k0 = kv * 4;
@@ -582,12 +615,12 @@ __global__ void k_mg_prolong_correct(int nx, int ny, int nz, int perx, int pery,
     float* __restrict__ v, long long ldv)
 {
     const int nzv = nz >> 2;
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (long long)nx * ny * nzv) return;
-    const int f  = blockIdx.y;
-    const int zv = (int)(t % nzv);
-    const int y  = (int)((t / nzv) % ny);
-    const int x  = (int)(t / ((long long)nzv * ny));
+    const int tz  = (nzv + blockDim.x - 1) / blockDim.x;
+    const int zv  = (blockIdx.x % tz) * blockDim.x + threadIdx.x;
+    const int y   = (blockIdx.x / tz) * blockDim.y + threadIdx.y;
+    const int x   = blockIdx.y;
+    const int f   = blockIdx.z;
+    if (zv >= nzv || y >= ny) return;
     const int nxc = nx >> 1, nyc = ny >> 1, nzc = nz >> 1;
     const int z0 = zv * 4;
     const int ox = x & 1, oy = y & 1;
@@ -687,12 +720,12 @@ __global__ void k_mg_scale(int nx, int ny, int nz, int zlx, int zly, int zlz, fl
     long long ldv)
 {
     const int nzv = nz >> 2;
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (long long)nx * ny * nzv) return;
-    const int fn = blockIdx.y;
-    const int zv = (int)(t % nzv);
-    const int y  = (int)((t / nzv) % ny);
-    const int x  = (int)(t / ((long long)nzv * ny));
+    const int tz  = (nzv + blockDim.x - 1) / blockDim.x;
+    const int zv  = (blockIdx.x % tz) * blockDim.x + threadIdx.x;
+    const int y   = (blockIdx.x / tz) * blockDim.y + threadIdx.y;
+    const int x   = blockIdx.y;
+    const int fn  = blockIdx.z;
+    if (zv >= nzv || y >= ny) return;
     const long long o = ((long long)x * ny + y) * nz + zv * 4;
     const float4 a = __ldg(reinterpret_cast<const float4*>(f + (long long)fn * ldf + o));
     float4 r = make_float4(mul_split(ch, cl, a.x), mul_split(ch, cl, a.y),
@@ -757,7 +790,7 @@ static bool jacobi_choose(int G, int nx, int ny, int nz, int nfunc, JacobiCfg& b
     for (int ry = 4; ry >= 2; ry -= 2)
         for (int yg = 1; yg <= 64; yg++)
             for (int nb = 1; nb <= 8; nb++)
-                for (int s = 2 * G + 3; s >= 2 * G + 2; s--)
+                for (int s = 14; s >= 2 * G + 2; s--)
                 {
                     JacobiCfg c = { ry, yg, nb, s, nx };
                     if (nb > nfunc && nb > 1) continue;
@@ -771,7 +804,11 @@ static bool jacobi_choose(int G, int nx, int ny, int nz, int nfunc, JacobiCfg& b
                     if (threads < 256) cost *= 1.0 + 0.3 * (256 - threads) / 256.;
                     if (ry == 2) cost *= 1.05;
                     if (threads > 416) cost *= 1.15; // 96-register class
-                    if (s == 2 * G + 2) cost *= 1.05;
+                    // bytes the TMA ring keeps in flight per SM beyond the 2G+1
+                    // resident planes; below ~64 KB the HBM latency shows
+                    const double inflight = (double)(s - (2 * G + 1)) * tmp.stage_bytes;
+                    if (inflight < 65536.) cost *= 1.0 + 0.4 * (65536. - inflight) / 65536.;
+                    cost *= 1.0 + 0.002 * s; // no deeper than useful
                     if (cost < best_cost)
                     {
                         best_cost = cost;
@@ -922,16 +959,32 @@ int mg_jacobi(const MgJacobiArgs& a, cudaStream_t st)
 #undef MGB_J
 }
 
+// launch shape for the (k-vector, row, plane, function) kernels
+struct VecLaunch
+{
+    dim3 block, grid;
+};
+static VecLaunch vec_launch(int nx, int ny, int nzv, int nf)
+{
+    VecLaunch L;
+    int bx = 1;
+    while (bx < nzv && bx < 64) bx *= 2;
+    const int by = 256 / bx;
+    L.block      = dim3(bx, by, 1);
+    L.grid       = dim3((unsigned)(((nzv + bx - 1) / bx) * ((ny + by - 1) / by)), (unsigned)nx,
+        (unsigned)nf);
+    return L;
+}
+
 int mg_restrict(const mgb_grid& fine, const float* w, size_t ldf, float* coarse, size_t ldc,
     int nfunc, cudaStream_t st)
 {
     const int nxc = fine.dim[0] / 2, nyc = fine.dim[1] / 2, nzc = fine.dim[2] / 2;
-    const long long per_f = (long long)nxc * nyc * (nzc / 4);
     for (int f0 = 0; f0 < nfunc; f0 += 65535)
     {
         const int nf = (nfunc - f0 < 65535) ? nfunc - f0 : 65535;
-        dim3 grid((unsigned)((per_f + 255) / 256), (unsigned)nf);
-        k_mg_restrict<<<grid, 256, 0, st>>>(nxc, nyc, nzc, fine.bc[0] == 1, fine.bc[1] == 1,
+        const VecLaunch L = vec_launch(nxc, nyc, nzc / 4, nf);
+        k_mg_restrict<<<L.grid, L.block, 0, st>>>(nxc, nyc, nzc, fine.bc[0] == 1, fine.bc[1] == 1,
             fine.bc[2] == 1, w + (size_t)f0 * ldf, (long long)ldf,
             coarse + (size_t)f0 * ldc, (long long)ldc);
         MGB_LAUNCHED("k_mg_restrict");
@@ -943,12 +996,11 @@ int mg_prolong_correct(const mgb_grid& fine, const float* coarse, size_t ldc, fl
     size_t ldv, int nfunc, const int zero_low[3], cudaStream_t st)
 {
     const int nx = fine.dim[0], ny = fine.dim[1], nz = fine.dim[2];
-    const long long per_f = (long long)nx * ny * (nz / 4);
     for (int f0 = 0; f0 < nfunc; f0 += 65535)
     {
         const int nf = (nfunc - f0 < 65535) ? nfunc - f0 : 65535;
-        dim3 grid((unsigned)((per_f + 255) / 256), (unsigned)nf);
-        k_mg_prolong_correct<<<grid, 256, 0, st>>>(nx, ny, nz, fine.bc[0] == 1,
+        const VecLaunch L = vec_launch(nx, ny, nz / 4, nf);
+        k_mg_prolong_correct<<<L.grid, L.block, 0, st>>>(nx, ny, nz, fine.bc[0] == 1,
             fine.bc[1] == 1, fine.bc[2] == 1, zero_low[0], zero_low[1], zero_low[2],
             coarse + (size_t)f0 * ldc, (long long)ldc, v + (size_t)f0 * ldv, (long long)ldv);
         MGB_LAUNCHED("k_mg_prolong_correct");
@@ -974,14 +1026,13 @@ int mg_scale(const mgb_grid& gr, double c, const float* f, size_t ldf, float* v,
     int nfunc, const int zero_low[3], cudaStream_t st)
 {
     const int nx = gr.dim[0], ny = gr.dim[1], nz = gr.dim[2];
-    const long long per_f = (long long)nx * ny * (nz / 4);
     float ch, cl;
     split_double(c, ch, cl);
     for (int f0 = 0; f0 < nfunc; f0 += 65535)
     {
         const int nf = (nfunc - f0 < 65535) ? nfunc - f0 : 65535;
-        dim3 grid((unsigned)((per_f + 255) / 256), (unsigned)nf);
-        k_mg_scale<<<grid, 256, 0, st>>>(nx, ny, nz, zero_low[0], zero_low[1], zero_low[2],
+        const VecLaunch L = vec_launch(nx, ny, nz / 4, nf);
+        k_mg_scale<<<L.grid, L.block, 0, st>>>(nx, ny, nz, zero_low[0], zero_low[1], zero_low[2],
             ch, cl, f + (size_t)f0 * ldf, (long long)ldf, v + (size_t)f0 * ldv,
             (long long)ldv);
         MGB_LAUNCHED("k_mg_scale");

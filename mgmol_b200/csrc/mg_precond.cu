@@ -248,6 +248,9 @@ int mgb_precond_create(mgb_precond** out, int lap_type, int mg_levels,
 
 namespace mgb
 {
+// zero-filled like a freshly allocated GridFuncVector
+// (src/pb/GridFuncVector.cc:22-43): with mixed boundary conditions the
+// reference's result depends on ghost values that are never written again
 static int dev_alloc(float** q, size_t bytes)
 {
     if (cudaMalloc(q, bytes) != cudaSuccess)
@@ -257,6 +260,7 @@ static int dev_alloc(float** q, size_t bytes)
         (void)cudaGetLastError();
         return MGB_ECUDA;
     }
+    MGB_CUDA(cudaMemset(*q, 0, bytes));
     return MGB_OK;
 }
 
@@ -271,8 +275,6 @@ static int ensure_literal(mgb_precond* p)
         float *w = nullptr, *r = nullptr, *n = nullptr;
         if (int rc = dev_alloc(&w, bytes)) return rc;
         p->work.push_back(w);
-        // work blocks start zeroed like freshly constructed GridFuncVectors
-        MGB_CUDA(cudaMemset(w, 0, bytes));
         if (l > 0)
         {
             if (int rc = dev_alloc(&r, bytes)) return rc;

@@ -257,6 +257,19 @@ class Lap:
         return hphi
 
 
+    def applyWithPotHost(self, phi_host, vtot_host, hphi_host, chunk=0):
+        """The same operator on HOST blocks (MGmol's MemorySpace::Host build):
+        pinned CPU tensors in, pinned CPU tensor out, copies and kernel
+        pipelined inside the library (mgb_hpsi_host)."""
+        assert not phi_host.is_cuda and not hphi_host.is_cuda and not vtot_host.is_cuda
+        assert phi_host.is_contiguous() and hphi_host.is_contiguous()
+        nfunc = phi_host.shape[0]
+        check(lib().mgb_hpsi_host(
+            self.type_, _dt(phi_host), self.grid_.ref(), _p(phi_host), self.grid_.size(),
+            _p(vtot_host), _p(hphi_host), self.grid_.size(), nfunc, int(chunk)))
+        return hphi_host
+
+
 class LapFactory:
     """src/LapFactory.h:26-56."""
 

@@ -1,0 +1,50 @@
+"""The C++ host side (include/mgmol_b200.hpp): compiles with a plain C++11
+compiler against the C ABI (no CUDA headers), and -- on a GPU -- reproduces the
+oracle through the reference's own class/method names."""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = os.path.join(ROOT, "tests", "cpp", "test_host_mirror.cc")
+EXE = os.path.join(ROOT, "tests", "cpp", "test_host_mirror")
+
+
+def build_cpp_test():
+    from mgmol_b200 import build as b
+    from oracle import oracle as orc
+    b.build()
+    orc.build(ref=False, port=True)
+    cmd = ["g++", "-std=c++11", "-O1", "-Wall", "-I", os.path.join(ROOT, "include"), SRC,
+           "-L", os.path.join(ROOT, "mgmol_b200"), "-lmgmol_b200",
+           "-L", os.path.join(ROOT, "oracle"), "-lmgmol_oracle",
+           "-Wl,-rpath,$ORIGIN/../../mgmol_b200", "-Wl,-rpath,$ORIGIN/../../oracle",
+           "-o", EXE]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return EXE
+
+
+def test_cpp_host_header_compiles_without_cuda():
+    exe = build_cpp_test()
+    assert os.path.exists(exe)
+    # without a GPU the program reports "no CUDA device" (exit 77), it does not
+    # fall back to anything
+    import torch
+    if not torch.cuda.is_available():
+        r = subprocess.run([exe], capture_output=True, text=True)
+        assert r.returncode == 77, (r.returncode, r.stdout, r.stderr)
+
+
+@pytest.mark.gpu
+def test_cpp_host_mirror_parity():
+    stale = (not os.path.exists(EXE)
+             or os.path.getmtime(EXE) < os.path.getmtime(SRC)
+             or os.path.getmtime(EXE) < os.path.getmtime(
+                 os.path.join(ROOT, "include", "mgmol_b200.hpp")))
+    exe = build_cpp_test() if stale else EXE
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    print(r.stdout)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "ok" in r.stdout
