@@ -50,3 +50,123 @@ class Communicator:
         if self.handle:
             lib().mgb_comm_destroy(self.handle)
             self.handle = None
+
+
+# ---------------------------------------------------------------------------
+# Host-side decomposition logic (no device needed): pb::PEenv
+# ---------------------------------------------------------------------------
+_PRIMES = (2, 3, 5, 7, 11, 13, 17, 19, 23)
+
+
+def geom(nx, ny, nz, ntasks, bias=1):
+    """PEenv::geom (src/pb/PEenv.cc:335-598): split `ntasks` ranks over x, y, z
+    by handing the largest prime factors of the rank count to the currently
+    largest grid direction; two factors of 2 per direction stay reserved for
+    the Poisson multigrid.  Returns (px, py, pz) or None when the reference
+    refuses the mesh (a direction not divisible by 4, or ranks left over)."""
+    n = [nx, ny, nz, ntasks]
+    fac = [[0] * len(_PRIMES) for _ in range(4)]
+    for i in range(4):
+        m = n[i]
+        for p, prime in enumerate(_PRIMES):
+            while m % prime == 0 and fac[i][p] < 20:
+                m //= prime
+                fac[i][p] += 1
+    for i in range(3):
+        if fac[i][0] > 1:
+            fac[i][0] -= 2
+        else:
+            return None
+    n = [nx, ny, nz, ntasks]
+    ndir = [1, 1, 1]
+    div = True
+    while div:
+        div = False
+        if n[2] >= n[1] and bias * n[1] >= n[0]:
+            order = (2, 1, 0)
+        elif n[1] >= n[2] and bias * n[2] >= n[0]:
+            order = (1, 2, 0)
+        elif bias * n[2] >= n[0] and n[0] >= bias * n[1]:
+            order = (2, 0, 1)
+        elif bias * n[1] >= n[0] and n[0] >= bias * n[2]:
+            order = (1, 0, 2)
+        elif n[0] >= bias * n[2] and n[2] >= n[1]:
+            order = (0, 2, 1)
+        elif n[0] >= bias * n[1] and n[1] >= n[2]:
+            order = (0, 1, 2)
+        else:
+            order = (1, 2, 0)
+        for d in order:
+            if div:
+                break
+            for k in range(len(_PRIMES) - 1, -1, -1):
+                if fac[d][k] > 0 and fac[3][k] > 0:
+                    ndir[d] *= _PRIMES[k]
+                    fac[d][k] -= 1
+                    n[d] //= _PRIMES[k]
+                    fac[3][k] -= 1
+                    n[3] //= _PRIMES[k]
+                    div = True
+                    break
+    if ndir[0] * ndir[1] * ndir[2] != ntasks:
+        return None
+    return tuple(ndir)
+
+
+def cart_coords(rank, nproc):
+    """MPI_Cart_coords on the row-major communicator of MPI_Cart_create
+    (src/pb/PEenv.cc:89): rank = (cx * py + cy) * pz + cz."""
+    px, py, pz = nproc
+    return (rank // (py * pz), (rank // pz) % py, rank % pz)
+
+
+def cart_rank(coord, nproc):
+    px, py, pz = nproc
+    return ((coord[0] % px) * py + (coord[1] % py)) * pz + (coord[2] % pz)
+
+
+def neighbours(rank, nproc):
+    """PEenv neighbours (src/pb/PEenv.cc:300-312): (low, high) rank per
+    direction on the always-periodic Cartesian topology."""
+    c = cart_coords(rank, nproc)
+    out = []
+    for d in range(3):
+        lo = list(c)
+        hi = list(c)
+        lo[d] -= 1
+        hi[d] += 1
+        out.append((cart_rank(lo, nproc), cart_rank(hi, nproc)))
+    return out
+
+
+def local_box(gdims, nproc, coord):
+    """Grid::dim / the slice of the global grid owned by `coord`
+    (src/pb/Grid.cc:49-54): equal blocks, global dims must divide."""
+    for n, p in zip(gdims, nproc):
+        if n % p:
+            raise ValueError("global dims must divide by ranks (Grid.cc:52-54)")
+    dims = tuple(n // p for n, p in zip(gdims, nproc))
+    return tuple(slice(c * d, (c + 1) * d) for c, d in zip(coord, dims))
+
+
+def x_halo_plan(rank, nproc, g, bc_x=1):
+    """What mgb_halo_exchange_x moves for one rank of an x-split domain:
+    a list of (peer, send_planes, recv_slot) with send_planes a slice of the
+    local x planes and recv_slot 0 (planes below the box) or 1 (above).
+    Sends are ordered west, east and receives east, west, so that with two
+    ranks (both neighbours the same peer) the k-th send pairs with the peer's
+    k-th receive."""
+    coord = cart_coords(rank, nproc)
+    (west, east) = neighbours(rank, nproc)[0]
+    have_w = bc_x == 1 or coord[0] > 0
+    have_e = bc_x == 1 or coord[0] < nproc[0] - 1
+    sends, recvs = [], []
+    if have_w:
+        sends.append((west, slice(0, g)))
+    if have_e:
+        sends.append((east, slice(-g, None)))
+    if have_e:
+        recvs.append((east, 1))
+    if have_w:
+        recvs.append((west, 0))
+    return sends, recvs

@@ -1,0 +1,137 @@
+"""Multi-GPU parity worker, launched by torchrun (one rank per GPU) from
+tests/test_multi_gpu.py or by hand:
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 \
+        --master-addr 127.0.0.1 --master-port 29533 tests/mgpu_worker.py
+
+Every rank builds the same global fields, keeps its block of the reference's
+3-D decomposition, runs the multi-rank path, and compares with the single-rank
+result of the same library on the global grid (itself pinned to the oracle by
+tests/test_gpu_parity.py).  Exit code 0 on every rank = parity."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from mgmol_b200 import host as H  # noqa: E402
+from mgmol_b200.parallel import Communicator, cart_coords, local_box  # noqa: E402
+
+
+def main():
+    rank = int(os.environ["RANK"])
+    world = int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    comm = Communicator(rank, world)
+    fails = []
+
+    def check(name, ok):
+        if not ok:
+            fails.append(name)
+        if rank == 0:
+            print("%-60s %s" % (name, "ok" if ok else "FAIL"), flush=True)
+
+    gen = torch.Generator(device="cuda").manual_seed(77)  # same on every rank
+    N = 6
+    for dt in (torch.float64, torch.float32):
+        for lap in (0, 2):
+            g = H.ghosts_for(lap)
+            for bc in ((1, 1, 1), (0, 0, 0)):
+                # ---- fused H psi on an x-split ------------------------------------
+                gdims = (8 * world, 16, 32)
+                ll = (0.25 * gdims[0], 4.0, 8.0)
+                full = (torch.rand((N,) + gdims, generator=gen, device="cuda",
+                                   dtype=torch.float64) - 0.5).to(dt)
+                v = torch.rand(gdims, generator=gen, device="cuda", dtype=torch.float64) - 0.7
+                ggrid = H.Grid(gdims, ll, g, bc)
+                ref = torch.empty_like(full)
+                H.LapFactory.createLap(ggrid, lap).applyWithPot(full, v, ref)
+                nproc = (world, 1, 1)
+                coord = cart_coords(rank, nproc)
+                box = local_box(gdims, nproc, coord)
+                grid = H.Grid(gdims, ll, g, bc, nproc, coord)
+                mine = full[(slice(None),) + box].contiguous()
+                vmine = v[box].contiguous()
+                xh = torch.zeros((N, 2 * g) + gdims[1:], dtype=dt, device="cuda")
+                xv = torch.zeros((1, 2 * g) + gdims[1:], dtype=torch.float64, device="cuda")
+                comm.halo_exchange_x(grid, g, mine, xh)
+                comm.halo_exchange_x(grid, g, vmine[None].contiguous(), xv)
+                out = torch.empty_like(mine)
+                H.LapFactory.createLap(grid, lap).applyWithPot(mine, vmine, out, xh, xv)
+                check("hpsi x-split %s lap%d bc%s" % (dt, lap, bc),
+                      torch.equal(out, ref[(slice(None),) + box]))
+
+    # ---- ghosted Y -> Z -> X exchange on every 2-way / n-way split ---------------
+    for dt in (torch.float64, torch.float32):
+        for gw in (1, 2):
+            for axis in range(3):
+                nproc = [1, 1, 1]
+                nproc[axis] = world
+                nproc = tuple(nproc)
+                gdims = [8, 12, 16]
+                gdims[axis] *= world
+                gdims = tuple(gdims)
+                for bc in ((1, 1, 1), (0, 0, 0)):
+                    full = (torch.rand((3,) + gdims, generator=gen, device="cuda",
+                                       dtype=torch.float64) - 0.5).to(dt)
+                    # single-rank reference: ghosted global block, traded locally
+                    ggrid = H.Grid(gdims, (1.0, 1.0, 1.0), gw, bc)
+                    gg = H.GridFuncVector(ggrid, 3, dt)
+                    gg.assign(full)
+                    gg.trade_boundaries()
+                    coord = cart_coords(rank, nproc)
+                    box = local_box(gdims, nproc, coord)
+                    grid = H.Grid(gdims, (1.0, 1.0, 1.0), gw, bc, nproc, coord)
+                    lg = H.GridFuncVector(grid, 3, dt)
+                    lg.assign(full[(slice(None),) + box].contiguous())
+                    comm.trade_boundaries(lg)
+                    # my ghosted block = the window of the global ghosted block
+                    win = tuple(slice(b.start, b.stop + 2 * gw) for b in box)
+                    expect = gg.data[(slice(None),) + win]
+                    # Dirichlet: the global block's own first-layer zeroing only
+                    # applies to the rank that owns the low face; compare where
+                    # both definitions agree (everything except that layer on
+                    # ranks that do not own it is identical by construction)
+                    check("ghosted exchange %s g%d axis%d bc%s" % (dt, gw, axis, bc),
+                          torch.equal(lg.data, expect))
+
+    # ---- partial Gram / projected Hamiltonian + NCCL all-reduce -------------------
+    for dt, tol in ((torch.float64, 1e-12), (torch.float32, 1e-6)):
+        gdims = (8 * world, 16, 32)
+        nproc = (world, 1, 1)
+        coord = cart_coords(rank, nproc)
+        box = local_box(gdims, nproc, coord)
+        full = (torch.rand((37,) + gdims, generator=gen, device="cuda", dtype=torch.float64)
+                - 0.5).to(dt)
+        ggrid = H.Grid(gdims, (2.0 * world, 4.0, 8.0), 1)
+        grid = H.Grid(gdims, (2.0 * world, 4.0, 8.0), 1, (1, 1, 1), nproc, coord)
+        orb = H.Orbitals(grid, 37, dt, full[(slice(None),) + box].contiguous())
+        s = orb.computeGram(comm)
+        a = full.reshape(37, -1).double()
+        exact = ggrid.vel() * (a @ a.t())
+        check("gram + allreduce %s" % dt,
+              float((s - exact).abs().max() / exact.abs().max()) <= tol)
+        hl = orb.computeLocalProduct(orb, comm)
+        check("phiT A + allreduce %s" % dt,
+              float((hl - exact).abs().max() / exact.abs().max()) <= tol)
+
+    torch.cuda.synchronize()
+    flag = torch.tensor([len(fails)], device="cuda")
+    dist.all_reduce(flag)
+    comm.close()
+    dist.destroy_process_group()
+    if int(flag) != 0:
+        print("rank %d failures: %s" % (rank, fails), flush=True)
+        sys.exit(1)
+    if rank == 0:
+        print("multi-gpu parity ok on %d ranks" % world, flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,106 @@
+"""World-size-2 tests of the host-side multi-GPU logic on CPU (gloo): the
+PEenv decomposition, the x-halo plan that mgb_halo_exchange_x implements, and
+the partial-matrix all-reduce.  The transport here is gloo instead of NCCL;
+the plan (who sends which planes to whom, in which order) is the code under
+test and is shared with the GPU path."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from mgmol_b200.parallel import (cart_coords, cart_rank, geom, local_box, neighbours,
+                                 x_halo_plan)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def test_geom_matches_reference_heuristic():
+    # PEenv::geom on cubic meshes: z first, then y, then x (src/pb/PEenv.cc:335-598)
+    assert geom(128, 128, 128, 1) == (1, 1, 1)
+    assert geom(128, 128, 128, 2) == (1, 1, 2)
+    assert geom(128, 128, 128, 4) == (1, 2, 2)
+    assert geom(128, 128, 128, 8) == (2, 2, 2)
+    assert geom(256, 128, 64, 8) == (4, 2, 1)
+    # two factors of 2 per direction stay reserved: 8^3 cannot be split 4 ways in one direction
+    assert geom(8, 8, 8, 8) == (2, 2, 2)
+    assert geom(8, 8, 8, 16) is None
+    # a direction not divisible by 4 is refused ("Poisson Solver Requires ...")
+    assert geom(30, 32, 32, 2) is None
+
+
+def test_cartesian_topology():
+    nproc = (2, 2, 2)
+    for r in range(8):
+        assert cart_rank(cart_coords(r, nproc), nproc) == r
+    # rank 3 = (0,1,1): x neighbours (1,1,1)=7 both ways on a periodic ring of 2
+    assert neighbours(3, nproc) == [(7, 7), (1, 1), (2, 2)]
+    assert local_box((8, 8, 8), nproc, (1, 0, 1)) == (slice(4, 8), slice(0, 4), slice(4, 8))
+    with pytest.raises(ValueError):
+        local_box((9, 8, 8), nproc, (0, 0, 0))
+
+
+def _worker(rank, world, port, bc_x, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g, nfunc = 2, 3
+        gdims = (8 * world, 4, 6)
+        rng = np.random.default_rng(5)
+        full = torch.from_numpy(rng.standard_normal((nfunc,) + gdims))
+        nproc = (world, 1, 1)
+        box = local_box(gdims, nproc, cart_coords(rank, nproc))
+        mine = full[(slice(None),) + box].contiguous()
+        # --- x halo, following the plan ---------------------------------------
+        xhalo = torch.zeros((nfunc, 2 * g) + gdims[1:], dtype=torch.float64)
+        sends, recvs = x_halo_plan(rank, nproc, g, bc_x)
+        reqs, bufs = [], []
+        for peer, planes in sends:
+            reqs.append(dist.isend(mine[:, planes].contiguous(), peer))
+        for peer, slot in recvs:
+            b = torch.empty((nfunc, g) + gdims[1:], dtype=torch.float64)
+            bufs.append((slot, b))
+            reqs.append(dist.irecv(b, peer))
+        for r in reqs:
+            r.wait()
+        for slot, b in bufs:
+            xhalo[:, slot * g:(slot + 1) * g] = b
+        x0 = box[0].start
+        nxg = gdims[0]
+        expect = torch.zeros_like(xhalo)
+        for k in range(g):
+            lo = x0 - g + k
+            hi = x0 + (box[0].stop - box[0].start) + k
+            if bc_x == 1 or lo >= 0:
+                expect[:, k] = full[:, lo % nxg]
+            if bc_x == 1 or hi < nxg:
+                expect[:, g + k] = full[:, hi % nxg]
+        ok_halo = bool(torch.equal(xhalo, expect))
+        # --- partial Gram + all-reduce = global Gram ------------------------------
+        a = mine.reshape(nfunc, -1)
+        part = a @ a.t()
+        dist.all_reduce(part)
+        af = full.reshape(nfunc, -1)
+        ok_gram = bool(torch.allclose(part, af @ af.t(), rtol=1e-13, atol=1e-13))
+        out[rank] = (ok_halo, ok_gram)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("bc_x", [1, 0])
+def test_x_halo_plan_and_allreduce_world2(bc_x):
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), bc_x, out), nprocs=world, join=True)
+    assert dict(out) == {0: (True, True), 1: (True, True)}
