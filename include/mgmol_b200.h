@@ -184,6 +184,42 @@ int mgb_gfv_restrict3D(int dtype, const mgb_grid* fine, const void* ufine,
 int mgb_gfv_extend3D(int dtype, const mgb_grid* fine, const void* ucoarse,
     void* ufine, int nfunc, void* stream);
 
+/* ---- localization masks of LocGridOrbitals
+ * The data Map2Masks / GridMask hold (src/Map2Masks.cc:25-61, src/GridMask.h:
+ * 41-52), flattened per color: the caller resolves overlapping_gids_[iloc]
+ * [color] -> GridMask when it fills the set.  For every multigrid level
+ * (0..mg_levels), x-slab iloc (subdivx slabs of dim[0]/subdivx planes, src/
+ * Mesh.cc:57-77) and color:
+ *   state -1 / 0  zero the slab  (mask_not_zero_ <= 0, or gid == -1:
+ *                                 src/Map2Masks.cc:53-58)
+ *   state 1       keep
+ *   state 2       apply `values` (host pointer, lmasktype `dtype`, the no-ghost
+ *                 slab sub0_l x ny_l x nz_l of GridMask::lmask_[level][iloc])
+ * op: how values are applied -- MGB_MASK_MULT  u *= mask  (GridMaskMult, src/
+ * GridMaskMult.cc:30-88; the "corrected" masks) or MGB_MASK_MAX  clip |u| <=
+ * mask (GridMaskMax, src/GridMaskMax.cc:30-90, GridMask::limitAbsValue; the
+ * default orbital masks, src/MasksSet.cc:15,158-182).
+ * mgb_masks_commit uploads the tables; call it after the last mgb_masks_set
+ * (MasksSet::setup / update, src/MasksSet.cc:136-157,206-217).               */
+#define MGB_MASK_MULT 0
+#define MGB_MASK_MAX 1
+typedef struct mgb_masks mgb_masks;
+int mgb_masks_create(mgb_masks** out, const mgb_grid* grid, int mg_levels,
+    int subdivx, int ncolors, int op);
+int mgb_masks_set(mgb_masks* m, int level, int iloc, int color, int state,
+    int dtype, const void* values_host);
+int mgb_masks_commit(mgb_masks* m);
+int mgb_masks_destroy(mgb_masks* m);
+/* GridFuncVector::app_mask(level) (src/pb/GridFuncVector.cc:2428-2438) on a
+ * ghosted block of the level-`level` grid (dims >> level, `ghosts` ghosts).
+ * m == NULL: no-op, like map2masks_ == nullptr.                             */
+int mgb_gfv_app_mask(int dtype, const mgb_masks* m, int level, int ghosts,
+    void* ghosted, int nfunc, void* stream);
+/* LocGridOrbitals::applyMask / app_mask(color, u, level) (src/
+ * LocGridOrbitals.cc:427-452,487-509) on a no-ghost block.                  */
+int mgb_app_mask(int dtype, const mgb_masks* m, int level, void* noghost,
+    size_t ld, int nfunc, void* stream);
+
 /* ---- multigrid preconditioner
  * Preconditioning<float> (src/Preconditioning.h:22-64, .cc:15-216) and
  * OrbitalsPreconditioning<T>::precond_mg / setGamma
@@ -193,6 +229,11 @@ typedef struct mgb_precond mgb_precond;
 int mgb_precond_create(mgb_precond** out, int lap_type, int mg_levels,
     const mgb_grid* grid, int nfunc_max);
 int mgb_precond_destroy(mgb_precond* p);
+/* OrbitalsPreconditioning::setup with currentMasks != nullptr (src/
+ * OrbitalsPreconditioning.cc:59-67 -> GridFuncVector::setMasks): every
+ * app_mask of Preconditioning<float>::mg (src/Preconditioning.cc:176,184,192,
+ * 204,212) uses this set.  NULL removes it.  The set must outlive the calls. */
+int mgb_precond_set_masks(mgb_precond* p, const mgb_masks* m);
 /* res (no-ghost, dtype) <- M^-1 res : v0 = gamma*res, mg(v, f=res) in float */
 int mgb_precond_mg(mgb_precond* p, int dtype, void* res, size_t ld, int nfunc,
     double gamma, void* stream);

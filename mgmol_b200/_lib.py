@@ -79,6 +79,16 @@ _SIGS = {
     "mgb_precond_destroy": (c_int, [c_void_p]),
     "mgb_precond_mg": (c_int, [c_void_p, c_int, c_void_p, c_size_t, c_int, c_double,
                                c_void_p]),
+    "mgb_precond_set_masks": (c_int, [c_void_p, c_void_p]),
+    "mgb_masks_create": (c_int, [ctypes.POINTER(c_void_p), ctypes.POINTER(MgbGrid),
+                                 c_int, c_int, c_int, c_int]),
+    "mgb_masks_set": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "mgb_masks_commit": (c_int, [c_void_p]),
+    "mgb_masks_destroy": (c_int, [c_void_p]),
+    "mgb_gfv_app_mask": (c_int, [c_int, c_void_p, c_int, c_int, c_void_p, c_int,
+                                 c_void_p]),
+    "mgb_app_mask": (c_int, [c_int, c_void_p, c_int, c_void_p, c_size_t, c_int,
+                             c_void_p]),
     "mgb_precond_set_mode": (c_int, [c_void_p, c_int]),
     "mgb_precond_last_mode": (c_int, [c_void_p]),
     "mgb_precond_vcycle": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),

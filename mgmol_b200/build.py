@@ -30,6 +30,7 @@ SOURCES = {
     "hpsi_fused.cu": [],
     "mg_precond.cu": [],
     "mg_fused.cu": [],
+    "masks.cu": [],
     "contractions.cu": [],
     "comm.cu": [],
 }

@@ -40,6 +40,7 @@
 #include <cstring>
 
 #include "hpsi.h"
+#include "masks.h"
 #include "mg_fused.h"
 #include "tma_ptx.cuh"
 
@@ -70,6 +71,7 @@ struct alignas(64) JacobiParams
     float sh, sl;    // two-float split of the input scaling (SCALE variant)
     float oh, ol;    // two-float split of -omega
     float c[8];      // stencil coefficients
+    MaskView mask;   // app_mask(level) applied to the stored v' and w (MASK)
 };
 
 constexpr int kMgBarBytes = 1024;
@@ -109,7 +111,7 @@ __device__ __forceinline__ float dd(float a, float b, float c)
 // chunk.  Warp 0 is the TMA producer; the consumers keep the 2G+1 planes a
 // stencil needs resident in a ring of S stages and read every tap from shared
 // memory.
-template <int LAP, int RY, bool SCALE, int MAXT>
+template <int LAP, int RY, bool SCALE, int MAXT, bool MASK>
 __global__ void __launch_bounds__(MAXT, 1) k_mg_jacobi(const __grid_constant__ JacobiParams P)
 {
     constexpr int G  = (LAP == kLap4) ? 2 : 1;
@@ -290,6 +292,24 @@ __global__ void __launch_bounds__(MAXT, 1) k_mg_jacobi(const __grid_constant__ J
                 const long long o0 = (long long)q * plane + pt0;
                 const bool zx      = P.zero_low[0] && q == 0;
 
+                // localization mask of this plane (slab q / sub0 of this
+                // color): requested now, consumed when the rows are stored
+                int mo = -1;
+                float4 mv[MASK ? RY : 1];
+                if constexpr (MASK)
+                {
+                    const int iloc = q / P.mask.sub0;
+                    mo             = __ldg(P.mask.off + (long long)orb * P.mask.subdivx + iloc);
+                    if (mo >= 0)
+                    {
+                        const float* mp = P.mask.pool + (long long)mo * P.mask.slab
+                                          + (long long)(q - iloc * P.mask.sub0) * plane + pt0;
+#pragma unroll
+                        for (int r = 0; r < RY; r++)
+                            mv[r] = __ldg(reinterpret_cast<const float4*>(mp + (long long)r * P.nz));
+                    }
+                }
+
                 // Right-hand side.  SCALE: the tile IS f (unscaled), read it
                 // back from shared memory.  Otherwise the values of this plane
                 // were requested one iteration ago (fnext) and the next
@@ -328,6 +348,27 @@ __global__ void __launch_bounds__(MAXT, 1) k_mg_jacobi(const __grid_constant__ J
                     {
                         wn[e] = __fsub_rn(av[e], fr[e]);                        // w -= f
                         vn[e] = __fadd_rn(cen[e], mul_split(oh, ol, wn[e])); // v += -omega w
+                    }
+                    if constexpr (MASK)
+                    {
+                        // v.app_mask(level) after the sweep, work.app_mask(level)
+                        // before the restriction (Preconditioning.cc:176,184)
+                        if (mo == -2)
+                        {
+#pragma unroll
+                            for (int e = 0; e < 4; e++)
+                                vn[e] = wn[e] = 0.f;
+                        }
+                        else if (mo >= 0)
+                        {
+                            const float mm[4] = { mv[r].x, mv[r].y, mv[r].z, mv[r].w };
+#pragma unroll
+                            for (int e = 0; e < 4; e++)
+                            {
+                                vn[e] = mask_apply(P.mask.op, vn[e], mm[e]);
+                                wn[e] = mask_apply(P.mask.op, wn[e], mm[e]);
+                            }
+                        }
                     }
                     const bool zrow = zx || (P.zero_low[1] && (y0 + rr0 + r) == 0);
                     if (zrow)
@@ -536,7 +577,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_mg_jacobi(const __grid_constant__ J
 // ---------------------------------------------------------------------------
 __global__ void k_mg_restrict(int nxc, int nyc, int nzc, int perx, int pery, int perz,
     const float* __restrict__ fine, long long ldf, float* __restrict__ coarse,
-    long long ldc)
+    long long ldc, MaskView mask)
 {
     // block (zx, zy): zx threads along the coarse k-vectors, zy coarse rows;
     // grid.x tiles (k-vector, row), grid.y = coarse plane, grid.z = function
@@ -599,8 +640,27 @@ __global__ void k_mg_restrict(int nxc, int nyc, int nzc, int perx, int pery, int
             acc[e] = fmaf(wx, ay[e], acc[e]);
     }
     float* C = coarse + (long long)f * ldc + ((long long)i * nyc + j) * nzc + k0;
-    *reinterpret_cast<float4*>(C) = make_float4(acc[0] * 0.015625f, acc[1] * 0.015625f,
-        acc[2] * 0.015625f, acc[3] * 0.015625f);
+    float r[4] = { acc[0] * 0.015625f, acc[1] * 0.015625f, acc[2] * 0.015625f,
+        acc[3] * 0.015625f };
+    if (mask.off)
+    {
+        // rcoarse->app_mask(level + 1)  (Preconditioning.cc:192)
+        const int iloc = i / mask.sub0;
+        const int mo   = __ldg(mask.off + (long long)f * mask.subdivx + iloc);
+        if (mo == -2)
+            r[0] = r[1] = r[2] = r[3] = 0.f;
+        else if (mo >= 0)
+        {
+            const float4 m = __ldg(reinterpret_cast<const float4*>(mask.pool
+                + (long long)mo * mask.slab
+                + ((long long)(i - iloc * mask.sub0) * nyc + j) * nzc + k0));
+            r[0] = mask_apply(mask.op, r[0], m.x);
+            r[1] = mask_apply(mask.op, r[1], m.y);
+            r[2] = mask_apply(mask.op, r[2], m.z);
+            r[3] = mask_apply(mask.op, r[3], m.w);
+        }
+    }
+    *reinterpret_cast<float4*>(C) = make_float4(r[0], r[1], r[2], r[3]);
 }
 
 // ---------------------------------------------------------------------------
@@ -612,7 +672,7 @@ __global__ void k_mg_restrict(int nxc, int nyc, int nzc, int perx, int pery, int
 // ---------------------------------------------------------------------------
 __global__ void k_mg_prolong_correct(int nx, int ny, int nz, int perx, int pery, int perz,
     int zlx, int zly, int zlz, const float* __restrict__ coarse, long long ldc,
-    float* __restrict__ v, long long ldv)
+    float* __restrict__ v, long long ldv, MaskView mask)
 {
     const int nzv = nz >> 2;
     const int tz  = (nzv + blockDim.x - 1) / blockDim.x;
@@ -688,6 +748,24 @@ __global__ void k_mg_prolong_correct(int nx, int ny, int nz, int perx, int pery,
         }
         w[e] = val;
     }
+    if (mask.off)
+    {
+        // gfv_work_[level]->app_mask(level) on P e  (Preconditioning.cc:204)
+        const int iloc = x / mask.sub0;
+        const int mo   = __ldg(mask.off + (long long)f * mask.subdivx + iloc);
+        if (mo == -2)
+            w[0] = w[1] = w[2] = w[3] = 0.f;
+        else if (mo >= 0)
+        {
+            const float4 m = __ldg(reinterpret_cast<const float4*>(mask.pool
+                + (long long)mo * mask.slab
+                + ((long long)(x - iloc * mask.sub0) * ny + y) * nz + z0));
+            w[0] = mask_apply(mask.op, w[0], m.x);
+            w[1] = mask_apply(mask.op, w[1], m.y);
+            w[2] = mask_apply(mask.op, w[2], m.z);
+            w[3] = mask_apply(mask.op, w[3], m.w);
+        }
+    }
     float* pv = v + (long long)f * ldv + ((long long)x * ny + y) * nz + z0;
     float4 vv = *reinterpret_cast<float4*>(pv);
     vv.x = __fsub_rn(vv.x, w[0]);
@@ -717,7 +795,7 @@ __global__ void k_mg_convert(long long npt, const double* __restrict__ in, long 
 // the first sweep's tile loads)
 __global__ void k_mg_scale(int nx, int ny, int nz, int zlx, int zly, int zlz, float ch,
     float cl, const float* __restrict__ f, long long ldf, float* __restrict__ v,
-    long long ldv)
+    long long ldv, MaskView mask)
 {
     const int nzv = nz >> 2;
     const int tz  = (nzv + blockDim.x - 1) / blockDim.x;
@@ -730,6 +808,25 @@ __global__ void k_mg_scale(int nx, int ny, int nz, int zlx, int zly, int zlz, fl
     const float4 a = __ldg(reinterpret_cast<const float4*>(f + (long long)fn * ldf + o));
     float4 r = make_float4(mul_split(ch, cl, a.x), mul_split(ch, cl, a.y),
         mul_split(ch, cl, a.z), mul_split(ch, cl, a.w));
+    if (mask.off)
+    {
+        // coarse levels: the first sweep from v = 0 gives omega * f, then
+        // v.app_mask(level)  (Preconditioning.cc:175-176)
+        const int iloc = x / mask.sub0;
+        const int mo   = __ldg(mask.off + (long long)fn * mask.subdivx + iloc);
+        if (mo == -2)
+            r = make_float4(0.f, 0.f, 0.f, 0.f);
+        else if (mo >= 0)
+        {
+            const float4 m = __ldg(reinterpret_cast<const float4*>(mask.pool
+                + (long long)mo * mask.slab
+                + ((long long)(x - iloc * mask.sub0) * ny + y) * nz + zv * 4));
+            r.x = mask_apply(mask.op, r.x, m.x);
+            r.y = mask_apply(mask.op, r.y, m.y);
+            r.z = mask_apply(mask.op, r.z, m.z);
+            r.w = mask_apply(mask.op, r.w, m.w);
+        }
+    }
     if ((zlx && x == 0) || (zly && y == 0)) r = make_float4(0.f, 0.f, 0.f, 0.f);
     if (zlz && zv == 0) r.x = 0.f;
     *reinterpret_cast<float4*>(v + (long long)fn * ldv + o) = r;
@@ -848,14 +945,14 @@ bool mg_fused_level_ok(const mgb_grid& g, int lap_type)
     return jacobi_choose(G, nx, ny, nz, 1, c);
 }
 
-template <int LAP, bool SCALE>
+template <int LAP, bool SCALE, bool MASK>
 static int launch_jacobi(const JacobiParams& P, const JacobiCfg& c, dim3 grid, int threads,
     size_t smem, cudaStream_t st)
 {
     // launch-bound classes: 9 / 13 / 17 warps -> 168 / 128 / 96 registers
 #define MGB_LAUNCH_J(RYV, MT)                                                  \
     {                                                                          \
-        auto kern = k_mg_jacobi<LAP, RYV, SCALE, MT>;                          \
+        auto kern = k_mg_jacobi<LAP, RYV, SCALE, MT, MASK>;                    \
         MGB_CUDA(cudaFuncSetAttribute(                                         \
             kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
         kern<<<grid, threads, smem, st>>>(P);                                  \
@@ -950,9 +1047,13 @@ int mg_jacobi(const MgJacobiArgs& a, cudaStream_t st)
     if (grid.y > 65535 || grid.z > 65535) return MGB_ENOTSUP;
     const int threads = 32 + c.NB * P.tpo;
     const bool scale  = a.scale != 1.0;
+    P.mask            = a.mask;
+    const bool masked = a.mask.off != nullptr;
 #define MGB_J(LAP)                                                                     \
-    (scale ? launch_jacobi<LAP, true>(P, c, grid, threads, smem, st)                   \
-           : launch_jacobi<LAP, false>(P, c, grid, threads, smem, st))
+    (masked ? (scale ? launch_jacobi<LAP, true, true>(P, c, grid, threads, smem, st)   \
+                     : launch_jacobi<LAP, false, true>(P, c, grid, threads, smem, st)) \
+            : (scale ? launch_jacobi<LAP, true, false>(P, c, grid, threads, smem, st)  \
+                     : launch_jacobi<LAP, false, false>(P, c, grid, threads, smem, st)))
     if (a.lap_type == MGB_LAP_4) return MGB_J(kLap4);
     if (a.lap_type == MGB_LAP_2) return MGB_J(kLap2);
     return MGB_J(kLapMehr);
@@ -976,8 +1077,15 @@ static VecLaunch vec_launch(int nx, int ny, int nzv, int nf)
     return L;
 }
 
+static MaskView mask_from(const MaskView& m, int f0)
+{
+    MaskView v = m;
+    if (v.off) v.off += (size_t)f0 * v.subdivx;
+    return v;
+}
+
 int mg_restrict(const mgb_grid& fine, const float* w, size_t ldf, float* coarse, size_t ldc,
-    int nfunc, cudaStream_t st)
+    int nfunc, const MaskView& mask, cudaStream_t st)
 {
     const int nxc = fine.dim[0] / 2, nyc = fine.dim[1] / 2, nzc = fine.dim[2] / 2;
     for (int f0 = 0; f0 < nfunc; f0 += 65535)
@@ -986,14 +1094,14 @@ int mg_restrict(const mgb_grid& fine, const float* w, size_t ldf, float* coarse,
         const VecLaunch L = vec_launch(nxc, nyc, nzc / 4, nf);
         k_mg_restrict<<<L.grid, L.block, 0, st>>>(nxc, nyc, nzc, fine.bc[0] == 1, fine.bc[1] == 1,
             fine.bc[2] == 1, w + (size_t)f0 * ldf, (long long)ldf,
-            coarse + (size_t)f0 * ldc, (long long)ldc);
+            coarse + (size_t)f0 * ldc, (long long)ldc, mask_from(mask, f0));
         MGB_LAUNCHED("k_mg_restrict");
     }
     return MGB_OK;
 }
 
 int mg_prolong_correct(const mgb_grid& fine, const float* coarse, size_t ldc, float* v,
-    size_t ldv, int nfunc, const int zero_low[3], cudaStream_t st)
+    size_t ldv, int nfunc, const int zero_low[3], const MaskView& mask, cudaStream_t st)
 {
     const int nx = fine.dim[0], ny = fine.dim[1], nz = fine.dim[2];
     for (int f0 = 0; f0 < nfunc; f0 += 65535)
@@ -1002,7 +1110,8 @@ int mg_prolong_correct(const mgb_grid& fine, const float* coarse, size_t ldc, fl
         const VecLaunch L = vec_launch(nx, ny, nz / 4, nf);
         k_mg_prolong_correct<<<L.grid, L.block, 0, st>>>(nx, ny, nz, fine.bc[0] == 1,
             fine.bc[1] == 1, fine.bc[2] == 1, zero_low[0], zero_low[1], zero_low[2],
-            coarse + (size_t)f0 * ldc, (long long)ldc, v + (size_t)f0 * ldv, (long long)ldv);
+            coarse + (size_t)f0 * ldc, (long long)ldc, v + (size_t)f0 * ldv, (long long)ldv,
+            mask_from(mask, f0));
         MGB_LAUNCHED("k_mg_prolong_correct");
     }
     return MGB_OK;
@@ -1023,7 +1132,7 @@ int mg_convert(size_t npt, const double* in, size_t ldi, float* out, size_t ldo,
 }
 
 int mg_scale(const mgb_grid& gr, double c, const float* f, size_t ldf, float* v, size_t ldv,
-    int nfunc, const int zero_low[3], cudaStream_t st)
+    int nfunc, const int zero_low[3], const MaskView& mask, cudaStream_t st)
 {
     const int nx = gr.dim[0], ny = gr.dim[1], nz = gr.dim[2];
     float ch, cl;
@@ -1034,7 +1143,7 @@ int mg_scale(const mgb_grid& gr, double c, const float* f, size_t ldf, float* v,
         const VecLaunch L = vec_launch(nx, ny, nz / 4, nf);
         k_mg_scale<<<L.grid, L.block, 0, st>>>(nx, ny, nz, zero_low[0], zero_low[1], zero_low[2],
             ch, cl, f + (size_t)f0 * ldf, (long long)ldf, v + (size_t)f0 * ldv,
-            (long long)ldv);
+            (long long)ldv, mask_from(mask, f0));
         MGB_LAUNCHED("k_mg_scale");
     }
     return MGB_OK;

@@ -3,6 +3,7 @@
 // [function][x][y][z] with an explicit leading dimension between functions.
 #pragma once
 #include "common.cuh"
+#include "masks.h"
 
 namespace mgb
 {
@@ -24,6 +25,8 @@ struct MgJacobiArgs
     double omega;         // jacobiFactor of this level
     double scale;         // 1, or the factor applied to `in` while it is loaded
     int zero_low[3];      // store zeros on the low layer (Dirichlet trade)
+    MaskView mask;        // localization mask of this level applied to the
+                          // stored v' and w (off == nullptr: none)
 };
 
 // true when the fused kernels can run this level (z extent a multiple of 4,
@@ -31,13 +34,15 @@ struct MgJacobiArgs
 bool mg_fused_level_ok(const mgb_grid& g, int lap_type);
 
 int mg_jacobi(const MgJacobiArgs& a, cudaStream_t st);
+// `mask`: of the COARSE level (applied to the restricted block)
 int mg_restrict(const mgb_grid& fine, const float* w, size_t ldf, float* coarse, size_t ldc,
-    int nfunc, cudaStream_t st);
+    int nfunc, const MaskView& mask, cudaStream_t st);
+// `mask`: of the fine level (applied to P e before the subtraction)
 int mg_prolong_correct(const mgb_grid& fine, const float* coarse, size_t ldc, float* v,
-    size_t ldv, int nfunc, const int zero_low[3], cudaStream_t st);
+    size_t ldv, int nfunc, const int zero_low[3], const MaskView& mask, cudaStream_t st);
 int mg_convert(size_t npt, const double* in, size_t ldi, float* out, size_t ldo, int nfunc,
     cudaStream_t st);
 int mg_scale(const mgb_grid& gr, double c, const float* f, size_t ldf, float* v, size_t ldv,
-    int nfunc, const int zero_low[3], cudaStream_t st);
+    int nfunc, const int zero_low[3], const MaskView& mask, cudaStream_t st);
 
 } // namespace mgb

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "hpsi.h"
+#include "masks.h"
 #include "mg_fused.h"
 
 struct mgb_precond
@@ -36,6 +37,7 @@ struct mgb_precond
     std::vector<float*> fa, fb;  // ping-pong iterates
     std::vector<float*> fw;      // residual of the last pre-smoothing sweep
     std::vector<float*> ff;      // right-hand side (level 0: converted residual)
+    const mgb_masks* masks;      // GridFuncVector::map2masks_ (null: none)
 };
 
 namespace mgb
@@ -98,10 +100,11 @@ static int jacobi(mgb_precond* p, int lap_type, int level, float* v, bool& v_upd
             p->jf[level], st))
         return rc;
     v_upd = false;
-    return MGB_OK;
+    // gfv_v.app_mask(level)  (Preconditioning.cc:176,212)
+    return mgb_gfv_app_mask(MGB_F32, p->masks, level, gr.ghosts, v, nfunc, (void*)st);
 }
 
-// Preconditioning<float>::mg, src/Preconditioning.cc:155-216 (no masks)
+// Preconditioning<float>::mg, src/Preconditioning.cc:155-216
 static int vcycle(mgb_precond* p, float* v, bool& v_upd, const float* f,
     int lap_type, int level, int nfunc, cudaStream_t st)
 {
@@ -112,10 +115,17 @@ static int vcycle(mgb_precond* p, float* v, bool& v_upd, const float* f,
     if (level == p->max_levels) return MGB_OK; // :179
 
     float* w = p->work[level];
+    // :184 LOCALIZATION of the residual
+    if (int rc = mgb_gfv_app_mask(MGB_F32, p->masks, level, gr.ghosts, w, nfunc, (void*)st))
+        return rc;
     // :189 restrict3D trades w first (GridFuncVector.cc:1624-1631)
     if (int rc = mgb_gfv_trade_boundaries(MGB_F32, &gr, w, nfunc, (void*)st)) return rc;
     float* rc_ = p->rcoarse[level];
     if (int rc = mgb_gfv_restrict3D(MGB_F32, &gr, w, rc_, nfunc, (void*)st)) return rc;
+    // :192
+    if (int rc = mgb_gfv_app_mask(
+            MGB_F32, p->masks, level + 1, gr.ghosts, rc_, nfunc, (void*)st))
+        return rc;
 
     float* nv            = p->newv[level];
     const mgb_grid& cgr  = p->grid[level + 1];
@@ -129,6 +139,9 @@ static int vcycle(mgb_precond* p, float* v, bool& v_upd, const float* f,
         if (int rc = mgb_gfv_trade_boundaries(MGB_F32, &cgr, nv, nfunc, (void*)st))
             return rc;
     if (int rc = mgb_gfv_extend3D(MGB_F32, &gr, nv, w, nfunc, (void*)st)) return rc;
+    // :204
+    if (int rc = mgb_gfv_app_mask(MGB_F32, p->masks, level, gr.ghosts, w, nfunc, (void*)st))
+        return rc;
 
     // :206  v -= w
     if (int rc = mgb_axpy(MGB_F32, sizeg_of(gr) * nfunc, -1., w, v, (void*)st))
@@ -209,6 +222,7 @@ int mgb_precond_create(mgb_precond** out, int lap_type, int mg_levels,
     p->v0 = p->f0 = nullptr;
     p->literal_ready = p->fused_ready = false;
     p->mode = p->last_mode = 0;
+    p->masks = nullptr;
     if (const char* env = getenv("MGB_MG_MODE")) p->mode = atoi(env);
     mgb_grid g = *grid;
     int rc     = MGB_OK;
@@ -338,11 +352,21 @@ static int cycle_fused(mgb_precond* p, int l, const float* f, size_t ldf, double
     // the last sweep of level 0 is followed by a trade only on the path through
     // Preconditioning.cc:215, whose test reads bc_[0], bc_[2], bc_[2]
     const bool final_trade = !coarsest && (gr.bc[0] != 1 || gr.bc[2] != 1);
+    int mrc = MGB_OK;
+    const MaskView mk  = mask_view(p->masks, l, &mrc);
+    if (mrc) return mrc;
+    const MaskView mkc = coarsest ? no_mask() : mask_view(p->masks, l + 1, &mrc);
+    if (mrc) return mrc;
     float* cur = nullptr;
     bool pending_scale = true;
-    if (!periodic)
+    // The start vector can be formed while the first sweep loads its tiles
+    // unless low layers must be stored as zeros (Dirichlet) or, on a coarse
+    // level, the start vector omega * f is itself masked (it is the result of
+    // the reference's first sweep, followed by app_mask): then it is stored.
+    if (!periodic || (l > 0 && mk.off))
     {
-        if (int rc = mg_scale(gr, s, f, ldf, p->fa[l], ld, nfunc, zl, st)) return rc;
+        if (int rc = mg_scale(gr, s, f, ldf, p->fa[l], ld, nfunc, zl, l > 0 ? mk : no_mask(), st))
+            return rc;
         cur           = p->fa[l];
         pending_scale = false;
     }
@@ -366,6 +390,7 @@ static int cycle_fused(mgb_precond* p, int l, const float* f, size_t ldf, double
         const int* z = (final_out && !final_trade) ? nozero : zl;
         for (int d = 0; d < 3; d++)
             a.zero_low[d] = z[d];
+        a.mask = mk;
         if (int rc = mg_jacobi(a, st)) return rc;
         cur           = final_out ? nullptr : nxt;
         pending_scale = false;
@@ -382,7 +407,8 @@ static int cycle_fused(mgb_precond* p, int l, const float* f, size_t ldf, double
         return MGB_OK;
     }
     // :189-192 restriction of the residual of the last pre-smoothing sweep
-    if (int rc = mg_restrict(gr, p->fw[l], ld, p->ff[l + 1], npt_of(p->grid[l + 1]), nfunc, st))
+    if (int rc = mg_restrict(
+            gr, p->fw[l], ld, p->ff[l + 1], npt_of(p->grid[l + 1]), nfunc, mkc, st))
         return rc;
     // :198-199 coarse correction from a zero start: its first sweep gives
     // omega * f, folded into the start vector
@@ -392,7 +418,7 @@ static int cycle_fused(mgb_precond* p, int l, const float* f, size_t ldf, double
             ncycl_c - 1, nullptr, nullptr, 0, nfunc, &e, st))
         return rc;
     // :201-206 v -= P e
-    if (int rc = mg_prolong_correct(gr, e, npt_of(p->grid[l + 1]), cur, ld, nfunc, zl, st))
+    if (int rc = mg_prolong_correct(gr, e, npt_of(p->grid[l + 1]), cur, ld, nfunc, zl, mk, st))
         return rc;
     for (int it = 0; it < 2; it++) // :209-213
         if (int rc = sweep(false, it == 1 && l == 0)) return rc;
@@ -419,6 +445,24 @@ int mgb_precond_destroy(mgb_precond* p)
         for (float* q : *vec)
             if (q) cudaFree(q);
     delete p;
+    return MGB_OK;
+}
+
+int mgb_precond_set_masks(mgb_precond* p, const mgb_masks* m)
+{
+    MGB_REQUIRE(p, "mgb_precond_set_masks: null handle");
+    if (m)
+    {
+        MGB_REQUIRE(masks_match(m, &p->grid[0]),
+            "mgb_precond_set_masks: mask set built for another grid");
+        MGB_REQUIRE(masks_nlevels(m) >= p->max_levels + 1,
+            "mgb_precond_set_masks: mask set has %d levels, the V-cycle needs %d",
+            masks_nlevels(m), p->max_levels + 1);
+        MGB_REQUIRE(masks_ncolors(m) >= p->nfunc_max,
+            "mgb_precond_set_masks: mask set has %d colors, the block up to %d",
+            masks_ncolors(m), p->nfunc_max);
+    }
+    p->masks = m;
     return MGB_OK;
 }
 

@@ -389,6 +389,163 @@ class Orbitals:
         return out
 
 
+class Masks:
+    """The localization masks one rank holds for its colors: what MasksSet /
+    Map2Masks / GridMask provide to the path (src/Map2Masks.cc:25-61,
+    src/GridMask.h:41-52), as plain tables.  `op` 0 = GridMaskMult (u *= m),
+    1 = GridMaskMax (clip |u| <= m), the default orbital masks
+    (src/MasksSet.cc:15,158-182)."""
+
+    MULT, MAX = 0, 1
+
+    def __init__(self, grid, mg_levels, subdivx, ncolors, op):
+        h = ctypes.c_void_p()
+        check(lib().mgb_masks_create(ctypes.byref(h), grid.ref(), mg_levels, subdivx,
+                                     ncolors, op))
+        self.handle_ = h
+        self.mg_levels_, self.subdivx_, self.ncolors_, self.op_ = (
+            mg_levels, subdivx, ncolors, op)
+
+    @classmethod
+    def from_tables(cls, grid, tables):
+        """tables: .mg_levels .subdivx .ncolors .op, .state[level][iloc, color],
+        .values[level][(iloc, color)] -> numpy slab (float32 / float64)."""
+        m = cls(grid, tables.mg_levels, tables.subdivx, tables.ncolors, tables.op)
+        for level in range(tables.mg_levels + 1):
+            for iloc in range(tables.subdivx):
+                for color in range(tables.ncolors):
+                    m.set(level, iloc, color, int(tables.state[level][iloc, color]),
+                          tables.values[level].get((iloc, color)))
+        m.commit()
+        return m
+
+    def set(self, level, iloc, color, state, values=None):
+        ptr, dt = None, 1
+        if state == 2:
+            import numpy as np
+            values = np.ascontiguousarray(values)
+            dt = {np.dtype(np.float32): 0, np.dtype(np.float64): 1}[values.dtype]
+            ptr = values.ctypes.data_as(ctypes.c_void_p)
+        check(lib().mgb_masks_set(self.handle_, level, iloc, color, state, dt, ptr))
+
+    def commit(self):
+        check(lib().mgb_masks_commit(self.handle_))
+
+    def apply_ghosted(self, gfv, level=0):
+        """GridFuncVector::app_mask(level) (src/pb/GridFuncVector.cc:2428-2438)."""
+        check(lib().mgb_gfv_app_mask(_dt(gfv.data), self.handle_, level,
+                                     gfv.grid().ghost_pt(), _p(gfv.data), gfv.size(),
+                                     _stream()))
+        gfv.set_updated_boundaries(False)
+
+    def close(self):
+        if self.handle_ is not None:
+            lib().mgb_masks_destroy(self.handle_)
+            self.handle_ = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class LocGridOrbitals(Orbitals):
+    """LocGridOrbitals (src/LocGridOrbitals.h:60-, .cc) reduced to the hot
+    path: storage npt x chromatic_number "colors"; in x-slab iloc (subdivx slabs
+    of the local box) color c holds global orbital overlapping_gids[iloc][c] or
+    nothing (-1).  The stencils, the V-cycle and the BLAS-1 run on the color
+    block exactly as for ExtendedGridOrbitals; the contractions run per slab
+    (LocalMatrices with subdivx sub-matrices) and the masks localize."""
+
+    def __init__(self, grid, numst, overlapping_gids, dtype=torch.float64, psi=None,
+                 masks=None):
+        import numpy as np
+        self.overlapping_gids_ = np.asarray(overlapping_gids, dtype=np.int64)
+        self.subdivx_, ncolors = self.overlapping_gids_.shape
+        super().__init__(grid, ncolors, dtype, psi)
+        self.numst_global_ = numst            # numst_ of the reference
+        self.chromatic_number_ = ncolors
+        assert grid.dim(0) % self.subdivx_ == 0
+        self.loc_numpt_ = grid.size() // self.subdivx_
+        self.masks_ = masks
+
+    def getOverlappingGids(self):
+        return self.overlapping_gids_
+
+    def _slab(self, t, iloc):
+        return t.view(t.shape[0], -1)[:, iloc * self.loc_numpt_:(iloc + 1) * self.loc_numpt_]
+
+    def applyMask(self, first_time=False):
+        """src/LocGridOrbitals.cc:427-452."""
+        if self.masks_ is not None:
+            check(lib().mgb_app_mask(_dt(self.psi_), self.masks_.handle_, 0, _p(self.psi_),
+                                     self.grid_.size(), self.chromatic_number_, _stream()))
+        self.incrementIterativeIndex()
+
+    def getLocalOverlap(self):
+        """ss[iloc] = vel * Phi_iloc^T Phi_iloc (src/LocGridOrbitals.cc:1504-1530:
+        LocalMatrices::syrk per slab + fillUpperWithLower + scal)."""
+        n = self.chromatic_number_
+        ss = torch.empty((self.subdivx_, n, n), dtype=torch.float64, device="cuda")
+        for iloc in range(self.subdivx_):
+            a = self._slab(self.psi_, iloc)
+            check(lib().mgb_syrk_t(_dt(self.psi_), n, self.loc_numpt_, self.grid_.vel(),
+                                   a.data_ptr(), self.grid_.size(), _p(ss[iloc]), n,
+                                   _stream()))
+        return ss
+
+    def computeLocalProduct(self, other, transpose=False):
+        """ss[iloc] = vel * Phi_iloc^T A_iloc, or its transpose
+        (src/LocGridOrbitals.cc:1554-1604); returned as row-major
+        ss[iloc][i, j] = <a_i, b_j>."""
+        arr = other.psi_ if isinstance(other, Orbitals) else other
+        a, b = (arr, self.psi_) if transpose else (self.psi_, arr)
+        m, n = a.shape[0], b.shape[0]
+        ss = torch.empty((self.subdivx_, n, m), dtype=torch.float64, device="cuda")
+        for iloc in range(self.subdivx_):
+            check(lib().mgb_gemm_tn(_dt(self.psi_), m, n, self.loc_numpt_,
+                                    self.grid_.vel(), self._slab(a, iloc).data_ptr(),
+                                    self.grid_.size(), self._slab(b, iloc).data_ptr(),
+                                    self.grid_.size(), 0.0, _p(ss[iloc]), m, _stream()))
+        return ss.transpose(1, 2)
+
+    def matrixToLocalMatrix(self, iloc, matrix):
+        """lmatrix[icolor, jcolor] = matrix[gid_i, gid_j] where both slots are
+        occupied, else 0 (src/LocGridOrbitals.cc:1400-1424).  matrix: (numst,
+        numst) tensor indexed [i, j]."""
+        g = torch.as_tensor(self.overlapping_gids_[iloc], device=matrix.device)
+        ok = g >= 0
+        gi = torch.where(ok, g, torch.zeros_like(g))
+        lm = matrix[gi][:, gi]
+        return lm * (ok[:, None] & ok[None, :]).to(lm.dtype)
+
+    def multiplyByMatrix(self, local_matrices, product=None):
+        """Per slab Phi_iloc <- Phi_iloc * M_iloc (src/LocGridOrbitals.cc:793-898);
+        local_matrices: (subdivx, n, n) with [iloc][l, j]."""
+        n = self.chromatic_number_
+        inplace = product is None
+        out = torch.empty_like(self.psi_) if inplace else product.psi_
+        for iloc in range(self.subdivx_):
+            mcol = local_matrices[iloc].t().contiguous()
+            check(lib().mgb_gemm_nn(_dt(self.psi_), self.loc_numpt_, n, n, 1.0,
+                                    self._slab(self.psi_, iloc).data_ptr(),
+                                    self.grid_.size(), _p(mcol), n, 0.0,
+                                    self._slab(out, iloc).data_ptr(), self.grid_.size(),
+                                    _stream()))
+        if inplace:
+            self.psi_.copy_(out)
+            self.incrementIterativeIndex()
+        return out
+
+    def multiply_by_matrix(self, matrix, product=None):
+        """Phi * M for a global numst x numst matrix: per slab the block of M
+        over the gids present there (src/LocGridOrbitals.cc:750-791)."""
+        lms = torch.stack([self.matrixToLocalMatrix(i, matrix)
+                           for i in range(self.subdivx_)])
+        return self.multiplyByMatrix(lms, product)
+
+
 class Hamiltonian:
     """Hamiltonian<T> (src/Hamiltonian.h:20-52, .cc:43-159): caches
     hlphi_ = H_loc * phi keyed by 100*phi.index + pot.index."""
@@ -441,13 +598,17 @@ class OrbitalsPreconditioning:
         self.gamma_ = -1.0
         self.is_set_ = False
 
-    def setup(self, orbitals, mg_levels, lap_type):
+    def setup(self, orbitals, mg_levels, lap_type, masks=None):
+        """masks: the `currentMasks` argument of the reference (a Masks set, or
+        None for ExtendedGridOrbitals)."""
         assert not self.is_set_
         grid = orbitals.grid_.with_ghosts(ghosts_for(lap_type))
         h = ctypes.c_void_p()
         check(lib().mgb_precond_create(ctypes.byref(h), lap_type, mg_levels,
                                        grid.ref(), orbitals.chromatic_number()))
-        self.handle_ = h
+        if masks is not None:
+            check(lib().mgb_precond_set_masks(h, masks.handle_))
+        self.masks_ = masks
         self.lap_type_ = lap_type
         self.mg_levels_ = mg_levels
         self.grid_ = grid

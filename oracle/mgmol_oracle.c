@@ -153,9 +153,25 @@ typedef struct
     float* work[16];
     float* rcoarse[16];
     float* newv[16];
+    /* localization masks (NULL state: none), tables indexed
+     * [level][iloc][color] */
+    int subdivx, ncolors, mask_op;
+    const int* mstate;
+    const long long* mvoff;
+    const double* mvalues;
 } orc_mg;
 
-/* Preconditioning<float>::mg (Preconditioning.cc:155-216), no masks.
+/* GridFuncVector::app_mask(level) (pb/GridFuncVector.cc:2428-2438) */
+static void orc_mg_mask(const orc_mg* M, int level, float* u)
+{
+    if (!M->mstate) return;
+    const size_t per = (size_t)M->subdivx * M->ncolors;
+    orc_app_mask_f32(M->lev[level].dims, M->g, M->subdivx, M->ncolors,
+        M->mask_op, M->mstate + level * per, M->mvoff + level * per,
+        M->mvalues, u, M->nfunc);
+}
+
+/* Preconditioning<float>::mg (Preconditioning.cc:155-216).
  * Returns nonzero where the reference would abort. */
 static int orc_mg_cycle(orc_mg* M, float* v, int* v_upd, const float* f,
     int lap_type, int level)
@@ -167,16 +183,22 @@ static int orc_mg_cycle(orc_mg* M, float* v, int* v_upd, const float* f,
     int w_upd       = 0;
 
     for (int it = 0; it < ncycl; it++) /* :173-177 */
+    {
         if (orc_jacobi_f32(lap_type, L->dims, L->h, g, M->bc, v, v_upd, f, w,
                 nf, M->jf[level]))
             return 1;
+        orc_mg_mask(M, level, v);
+    }
     if (level == M->max_levels) return 0; /* :179 */
+
+    orc_mg_mask(M, level, w); /* :184 LOCALIZATION */
 
     /* :189 restrict3D trades w first (pb/GridFuncVector.cc:1624-1631);
      * w's flag is false after applyLap (GridFuncVector.h:297) */
     if (!w_upd) orc_trade_boundaries_f32(L->dims, g, M->bc, w, nf);
     float* rc = M->rcoarse[level];
     orc_restrict3D_f32(L->dims, g, w, rc, nf);
+    orc_mg_mask(M, level + 1, rc); /* :192 */
 
     float* nv          = M->newv[level];
     const orc_level* C = &M->lev[level + 1];
@@ -187,14 +209,18 @@ static int orc_mg_cycle(orc_mg* M, float* v, int* v_upd, const float* f,
     /* :201 extend3D trades the coarse block first (:1633-1641) */
     if (!nv_upd) orc_trade_boundaries_f32(C->dims, g, M->bc, nv, nf);
     orc_extend3D_f32(L->dims, g, nv, w, nf);
+    orc_mg_mask(M, level, w); /* :204 */
 
     orc_axpy_f32(L->sizeg * nf, -1., w, v); /* :206  v -= w */
     *v_upd = 0;                             /* extend3D left w un-traded */
 
     for (int it = 0; it < 2; it++) /* :209-213 */
+    {
         if (orc_jacobi_f32(lap_type, L->dims, L->h, g, M->bc, v, v_upd, f, w,
                 nf, M->jf[level]))
             return 1;
+        orc_mg_mask(M, level, v);
+    }
 
     /* :215 (the reference tests bc_[0], bc_[2], bc_[2]) */
     if (M->bc[0] != 1 || M->bc[2] != 1 || M->bc[2] != 1)
@@ -207,12 +233,19 @@ static int orc_mg_cycle(orc_mg* M, float* v, int* v_upd, const float* f,
 
 /* Preconditioning<float>::mg on caller-provided ghosted float blocks
  * v (in/out) and f.  dims must be divisible by 2^mg_levels. */
-int orc_mg_f32(int lap_type, int mg_levels, const int dims[3],
+int orc_mg_masked_f32(int lap_type, int mg_levels, const int dims[3],
     const double ll[3], const int bc[3], int g, float* v, const float* f,
-    int nfunc)
+    int nfunc, int subdivx, int ncolors, int mask_op, const int* mstate,
+    const long long* mvoff, const double* mvalues)
 {
     orc_mg M;
     memset(&M, 0, sizeof(M));
+    M.subdivx = subdivx;
+    M.ncolors = ncolors;
+    M.mask_op = mask_op;
+    M.mstate  = mstate;
+    M.mvoff   = mvoff;
+    M.mvalues = mvalues;
     if (mg_levels > 14) return 1;
     M.max_levels = mg_levels;
     M.g          = g;
@@ -256,11 +289,21 @@ int orc_mg_f32(int lap_type, int mg_levels, const int dims[3],
     return rc;
 }
 
-/* OrbitalsPreconditioning<T>::precond_mg (OrbitalsPreconditioning.cc:87-117),
- * no masks: res (no-ghost, ORBDTYPE) <- M^-1 res in float.
- * dtype: 0 float, 1 double. */
-int orc_precond_mg(int lap_type, int mg_levels, int dtype, const int dims[3],
-    const double ll[3], const int bc[3], void* res, int nfunc, double gamma)
+int orc_mg_f32(int lap_type, int mg_levels, const int dims[3],
+    const double ll[3], const int bc[3], int g, float* v, const float* f,
+    int nfunc)
+{
+    return orc_mg_masked_f32(lap_type, mg_levels, dims, ll, bc, g, v, f, nfunc,
+        1, nfunc, 0, NULL, NULL, NULL);
+}
+
+/* OrbitalsPreconditioning<T>::precond_mg (OrbitalsPreconditioning.cc:87-117):
+ * res (no-ghost, ORBDTYPE) <- M^-1 res in float.  dtype: 0 float, 1 double.
+ * mstate == NULL: no masks (ExtendedGridOrbitals). */
+int orc_precond_mg_masked(int lap_type, int mg_levels, int dtype,
+    const int dims[3], const double ll[3], const int bc[3], void* res,
+    int nfunc, double gamma, int subdivx, int ncolors, int mask_op,
+    const int* mstate, const long long* mvoff, const double* mvalues)
 {
     const int mehr = (lap_type == 0 || lap_type == 10);
     const int g    = mehr ? 1 : 2;
@@ -278,7 +321,8 @@ int orc_precond_mg(int lap_type, int mg_levels, int dtype, const int dims[3],
         memcpy(in, res, sizeof(float) * npt * nfunc);
     orc_add_ghosts_f32(dims, g, in, f, nfunc);
     orc_axpy_f32(sizeg * nfunc, gamma, f, v); /* :104 */
-    int rc = orc_mg_f32(lap_type, mg_levels, dims, ll, bc, g, v, f, nfunc);
+    int rc = orc_mg_masked_f32(lap_type, mg_levels, dims, ll, bc, g, v, f,
+        nfunc, subdivx, ncolors, mask_op, mstate, mvoff, mvalues);
     /* :109 setPsi(*gfv_work_): float -> ORBDTYPE, strip ghosts */
     orc_strip_ghosts_f32(dims, g, v, in, nfunc);
     if (dtype == 1)
@@ -292,4 +336,11 @@ int orc_precond_mg(int lap_type, int mg_levels, int dtype, const int dims[3],
     return rc;
 }
 
-int orc_version(void) { return 1; }
+int orc_precond_mg(int lap_type, int mg_levels, int dtype, const int dims[3],
+    const double ll[3], const int bc[3], void* res, int nfunc, double gamma)
+{
+    return orc_precond_mg_masked(lap_type, mg_levels, dtype, dims, ll, bc, res,
+        nfunc, gamma, 1, nfunc, 0, NULL, NULL, NULL);
+}
+
+int orc_version(void) { return 2; }

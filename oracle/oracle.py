@@ -61,6 +61,122 @@ def _sfx(dtype):
     return "_f64" if _dt(dtype) else "_f32"
 
 
+class MaskTables:
+    """Localization masks as plain data (what the path consumes): for every
+    multigrid level l, x-slab iloc and color c
+
+      state[l][iloc, c]  <= 0 zero the slab (GridMask::mask_not_zero_ -1 / 0,
+                         or gid == -1), 1 keep, 2 apply values
+      values[l][(iloc, c)]  no-ghost slab (sub0_l, ny_l, nz_l) of mask values
+                         for state 2 (lmasktype)
+
+    op: 0 multiply (GridMaskMult), 1 cut |u| <= mask (GridMaskMax)."""
+
+    def __init__(self, dims, mg_levels, subdivx, ncolors, op):
+        self.dims = tuple(dims)
+        self.mg_levels = mg_levels
+        self.subdivx = subdivx
+        self.ncolors = ncolors
+        self.op = op
+        self.state = [np.ones((subdivx, ncolors), np.int32) for _ in range(mg_levels + 1)]
+        self.values = [dict() for _ in range(mg_levels + 1)]
+
+    def slab_shape(self, level):
+        nx, ny, nz = (d >> level for d in self.dims)
+        return (nx // self.subdivx, ny, nz)
+
+    def set(self, level, iloc, color, state, values=None):
+        self.state[level][iloc, color] = state
+        self.values[level].pop((iloc, color), None)
+        if state == 2:
+            v = np.ascontiguousarray(values, dtype=np.float64).reshape(self.slab_shape(level))
+            self.values[level][(iloc, color)] = v
+
+    def flat(self):
+        """(state int32 [L, subdivx, ncolors], voff int64 same shape, values
+        float64 pool) for the C entry points."""
+        L = self.mg_levels + 1
+        state = np.stack(self.state).astype(np.int32)
+        voff = -np.ones((L, self.subdivx, self.ncolors), np.int64)
+        chunks, pos = [], 0
+        for l in range(L):
+            for (iloc, c), v in sorted(self.values[l].items()):
+                voff[l, iloc, c] = pos
+                chunks.append(v.ravel())
+                pos += v.size
+        pool = np.concatenate(chunks) if chunks else np.zeros(1, np.float64)
+        return np.ascontiguousarray(state), np.ascontiguousarray(voff), np.ascontiguousarray(pool)
+
+    def dense(self, level, dtype=np.float64):
+        """(ncolors, nx_l, ny_l, nz_l) multiplier view (only meaningful for
+        op 0); zero slabs 0, kept slabs 1."""
+        s0, ny, nz = self.slab_shape(level)
+        out = np.ones((self.ncolors, s0 * self.subdivx, ny, nz), dtype)
+        for iloc in range(self.subdivx):
+            for c in range(self.ncolors):
+                st = self.state[level][iloc, c]
+                sl = out[c, iloc * s0:(iloc + 1) * s0]
+                if st <= 0:
+                    sl[...] = 0
+                elif st == 2:
+                    sl[...] = self.values[level][(iloc, c)]
+        return out
+
+
+def synthetic_masks(dims, ll, mg_levels, subdivx, gid_table, centers, radii, op, ghosts=1):
+    """Mask tables built the way GridMask::init does (src/GridMask.cc:139-262:
+    minimum-image distance to a centre, profile of r / rcut inside rcut, zero
+    up to rcut + delta, slab states from what was found) -- a numpy
+    restatement of the mask GENERATION, which is outside the hot path; it only
+    has to produce realistic data (tests pin the path against the reference
+    with the reference's own masks, see Ref.masks_create).  gid_table:
+    (subdivx, ncolors) ints, -1 = empty slot."""
+    gid_table = np.asarray(gid_table, np.int64)
+    ncolors = gid_table.shape[1]
+    mt = MaskTables(dims, mg_levels, subdivx, ncolors, op)
+    h = [ll[d] / dims[d] for d in range(3)]
+    delta0 = (np.sqrt(sum(x * x for x in h)) + 1e-8) * ghosts
+    for l in range(mg_levels + 1):
+        s0, ny, nz = mt.slab_shape(l)
+        hl = [x * (1 << l) for x in h]
+        delta = delta0 * (1 << l)
+        for iloc in range(subdivx):
+            xs = (np.arange(s0) + iloc * s0) * hl[0]
+            ys = np.arange(ny) * hl[1]
+            zs = np.arange(nz) * hl[2]
+            for c in range(ncolors):
+                gid = gid_table[iloc, c]
+                if gid < 0:
+                    mt.set(l, iloc, c, 0)
+                    continue
+                ctr, rc = centers[gid], radii[gid]
+                d = []
+                for a, cc, L in ((xs, ctr[0], ll[0]), (ys, ctr[1], ll[1]), (zs, ctr[2], ll[2])):
+                    t = a - cc
+                    t -= L * np.round(t / L)
+                    d.append(t)
+                r = np.sqrt(d[0][:, None, None] ** 2 + d[1][None, :, None] ** 2
+                            + d[2][None, None, :] ** 2)
+                inside = r <= rc
+                if rc > 100.0 and (r < rc + delta).any():
+                    mt.set(l, iloc, c, 1)
+                elif not (r < rc + delta).any():
+                    mt.set(l, iloc, c, -1)
+                elif not inside.any():
+                    mt.set(l, iloc, c, 0)
+                else:
+                    x = np.clip(r / rc, 0, 1)
+                    if op == 0:
+                        prof = np.where(x < 0.99999, 1.0, (1.0 - x) / (1.0 - 0.99999))
+                    else:
+                        fac = 2.0 / (0.25 * 0.25)
+                        e_rc = np.exp(-fac * 0.25 * 0.25)
+                        prof = np.where(x > 0.75, np.float32(
+                            (np.exp(-fac * (x - 0.75) ** 2) - e_rc) / (1 - e_rc)), 1.0)
+                    mt.set(l, iloc, c, 2, np.where(inside, prof, 0.0))
+    return mt
+
+
 class Port:
     """Our restatement (kind "port")."""
 
@@ -194,6 +310,42 @@ class Port:
             raise ValueError("precond_mg: unsupported configuration (rc=%d)" % rc)
         return res
 
+
+    def app_mask_noghost(self, u, masks, level=0):
+        """LocGridOrbitals::applyMask on a no-ghost block (ncolors, nx, ny, nz)."""
+        u = np.array(u, order="C")
+        nf, nx, ny, nz = u.shape
+        st, vo, pool = masks.flat()
+        getattr(self.lib, "orc_app_mask_noghost" + _sfx(u.dtype))(
+            _c_int3(nx, ny, nz), masks.subdivx, masks.ncolors, masks.op,
+            _ptr(st[level]), _ptr(vo[level]), _ptr(pool), _ptr(u),
+            ctypes.c_size_t(nx * ny * nz), nf)
+        return u
+
+    def app_mask_ghosted(self, u, g, masks, level=0):
+        """GridFuncVector::app_mask(level) on a ghosted block."""
+        u = np.array(u, order="C")
+        nf = u.shape[0]
+        dims = _c_int3(*(x - 2 * g for x in u.shape[1:]))
+        st, vo, pool = masks.flat()
+        getattr(self.lib, "orc_app_mask" + _sfx(u.dtype))(
+            dims, g, masks.subdivx, masks.ncolors, masks.op, _ptr(st[level]),
+            _ptr(vo[level]), _ptr(pool), _ptr(u), nf)
+        return u
+
+    def precond_mg_masked(self, lap_type, mg_levels, res, ll, gamma, masks, bc=(1, 1, 1)):
+        res = np.array(res, order="C")
+        nf, nx, ny, nz = res.shape
+        st, vo, pool = masks.flat()
+        assert masks.mg_levels >= mg_levels and masks.ncolors == nf
+        rc = self.lib.orc_precond_mg_masked(
+            lap_type, mg_levels, _dt(res.dtype), _c_int3(nx, ny, nz),
+            _c_dbl3(*ll), _c_int3(*bc), _ptr(res), nf, ctypes.c_double(gamma),
+            masks.subdivx, masks.ncolors, masks.op, _ptr(st), _ptr(vo), _ptr(pool))
+        if rc:
+            raise ValueError("precond_mg: unsupported configuration (rc=%d)" % rc)
+        return res
+
     def gamma(self, inv_diag, mg_levels, vmax, small_eig):
         return self.lib.orc_gamma(
             ctypes.c_double(inv_diag), mg_levels, ctypes.c_double(vmax),
@@ -322,6 +474,66 @@ class Ref:
         self.lib.ref_precond_mg(
             lap_type, mg_levels, _dt(res.dtype), _c_int3(nx, ny, nz),
             _c_dbl3(*ll), _c_int3(*bc), _ptr(res), nf, ctypes.c_double(gamma))
+        return res
+
+
+    # -- localization masks (GridMask / Map2Masks of the reference) ------------
+    def masks_create(self, dims, ll, ghosts, mg_levels, subdivx, op, gids, centers, radii):
+        """Reference mask objects for `gids` (GridMaskMult op 0 / GridMaskMax
+        op 1), values generated by GridMask::init.  Returns an opaque handle."""
+        self.lib.ref_masks_create.restype = ctypes.c_void_p
+        gids = np.ascontiguousarray(gids, np.int32)
+        centers = np.ascontiguousarray(centers, np.float64)
+        radii = np.ascontiguousarray(radii, np.float64)
+        h = self.lib.ref_masks_create(
+            _c_int3(*dims), _c_dbl3(*ll), ghosts, mg_levels, subdivx, op,
+            len(gids), _ptr(gids), _ptr(centers), _ptr(radii))
+        return (ctypes.c_void_p(h), tuple(dims), mg_levels, subdivx, op)
+
+    def masks_tables(self, handle, gid_table):
+        """MaskTables (plain data) of a reference mask set for a
+        (subdivx, ncolors) gid table."""
+        h, dims, mg_levels, subdivx, op = handle
+        gid_table = np.asarray(gid_table, np.int64)
+        ncolors = gid_table.shape[1]
+        mt = MaskTables(dims, mg_levels, subdivx, ncolors, op)
+        for l in range(mg_levels + 1):
+            n = self.lib.ref_masks_loc_numpt(h, l)
+            buf = np.empty(n, np.float64)
+            for iloc in range(subdivx):
+                for c in range(ncolors):
+                    gid = int(gid_table[iloc, c])
+                    if gid < 0:
+                        mt.set(l, iloc, c, 0)
+                        continue
+                    st = self.lib.ref_masks_state(h, gid, l, iloc)
+                    if st == 2:
+                        got = self.lib.ref_masks_values(h, gid, l, iloc, _ptr(buf))
+                        assert got == n
+                        mt.set(l, iloc, c, 2, buf.copy())
+                    else:
+                        mt.set(l, iloc, c, st)
+        return mt
+
+    def app_mask_noghost(self, u, handle, gid_table, level=0):
+        u = np.array(u, order="C")
+        nf, nx, ny, nz = u.shape
+        gt = np.ascontiguousarray(gid_table, np.int32)
+        self.lib.ref_app_mask_noghost(
+            handle[0], _dt(u.dtype), level, nf, _ptr(gt), _ptr(u),
+            ctypes.c_long(nx * ny * nz))
+        return u
+
+    def precond_mg_masked(self, lap_type, res, gamma, handle, gid_table, bc=(1, 1, 1)):
+        """precond_mg with the reference's Map2Masks set; grid, levels and
+        ghosts are those of the mask handle."""
+        res = np.array(res, order="C")
+        nf = res.shape[0]
+        gt = np.ascontiguousarray(gid_table, np.int32)
+        assert gt.shape == (handle[3], nf)
+        self.lib.ref_precond_mg_masked(
+            handle[0], lap_type, _dt(res.dtype), _c_int3(*bc), nf, _ptr(gt),
+            _ptr(res), ctypes.c_double(gamma))
         return res
 
     def gemm_tn(self, a, b, alpha=1.0):
