@@ -609,6 +609,7 @@ class OrbitalsPreconditioning:
         if masks is not None:
             check(lib().mgb_precond_set_masks(h, masks.handle_))
         self.masks_ = masks
+        self.handle_ = h
         self.lap_type_ = lap_type
         self.mg_levels_ = mg_levels
         self.grid_ = grid
