@@ -268,6 +268,18 @@ int mgb_gemm_tn(int dtype, int m, int n, size_t k, double alpha, const void* A,
  * 210-247)                                                                  */
 int mgb_syrk_t(int dtype, int n, size_t k, double alpha, const void* A,
     size_t lda, double* C, int ldc, void* stream);
+/* The same per x-slab, as LocGridOrbitals does (src/LocGridOrbitals.cc:
+ * 1504-1530 getLocalOverlap: LocalMatrices::syrk(iloc, loc_numpt, psi + iloc *
+ * loc_numpt, lda); :1554-1604 computeLocalProduct: LocalMatrices::gemm(iloc,
+ * ...)): slab s uses rows [s*k, (s+1)*k) of every column of A (and B) and
+ * writes the s-th matrix of C (nslabs matrices, ldc*n doubles apart:
+ * LocalMatrices storage, src/local_matrices/LocalMatrices.h:37-62).  One
+ * launch for all slabs.                                                      */
+int mgb_gemm_tn_slabs(int dtype, int m, int n, size_t k, int nslabs, double alpha,
+    const void* A, size_t lda, const void* B, size_t ldb, double beta, double* C,
+    int ldc, void* stream);
+int mgb_syrk_t_slabs(int dtype, int n, size_t k, int nslabs, double alpha,
+    const void* A, size_t lda, double* C, int ldc, void* stream);
 /* Cout(m x n, dtype, ldc) = alpha * A(m x k, dtype, lda) * M(k x n, double,
  * ldm) + beta*Cout : ExtendedGridOrbitals::multiplyByMatrix
  * (src/ExtendedGridOrbitals.cc:448-498), MPgemmNN.  Cout must not alias A.  */

@@ -100,6 +100,11 @@ _SIGS = {
                             c_void_p]),
     "mgb_syrk_t": (c_int, [c_int, c_int, c_size_t, c_double, c_void_p, c_size_t,
                            c_void_p, c_int, c_void_p]),
+    "mgb_gemm_tn_slabs": (c_int, [c_int, c_int, c_int, c_size_t, c_int, c_double, c_void_p,
+                                  c_size_t, c_void_p, c_size_t, c_double, c_void_p, c_int,
+                                  c_void_p]),
+    "mgb_syrk_t_slabs": (c_int, [c_int, c_int, c_size_t, c_int, c_double, c_void_p, c_size_t,
+                                 c_void_p, c_int, c_void_p]),
     "mgb_gemm_nn": (c_int, [c_int, c_size_t, c_int, c_int, c_double, c_void_p,
                             c_size_t, c_void_p, c_int, c_double, c_void_p, c_size_t,
                             c_void_p]),

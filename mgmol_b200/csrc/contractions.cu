@@ -16,6 +16,7 @@
 // partial tiles are combined by a second kernel in a fixed order, so results
 // are run-to-run deterministic.
 #include <cstdint>
+#include <cstdlib>
 
 #include "hpsi.h"
 
@@ -78,57 +79,127 @@ __device__ __forceinline__ void load_kmajor(T* sm, const T* base, long long ld,
     }
 }
 
-// C(m x n) (+)= A^T B over K range of this CTA.  A rows = m index, B rows = n.
-template <typename T, bool SYRK>
-__global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tn(int m, int n, long long k,
-    long long kper, const T* __restrict__ A, long long lda, const T* __restrict__ B,
-    long long ldb, double alpha, double beta, double* __restrict__ C, int ldc,
-    double* __restrict__ partial, int nsplit)
+// ---------------------------------------------------------------------------
+// C_b(m x n) = alpha * A_b^T B_b + beta * C_b for b < nbatch  (A rows = m index,
+// B rows = n index, K contiguous).
+//
+// Work decomposition ("stream-K"): the (batch, tile) list times the K range is
+// one linear space of k-iterations (KC wide), weighted by what an iteration
+// costs -- a diagonal tile of the Gram matrix only needs about half the tensor
+// work of a full tile (below).  Each of the G CTAs (one per SM) takes an equal
+// share of that space, so there is no wave quantisation and no tail; a share
+// covers one or more segments (tile, k-iteration range).  A segment that is a
+// whole off-diagonal tile writes C directly; every other segment writes its
+// 128x128 partial into its own slot and k_tn_fixup adds the slots of a tile in
+// CTA order, i.e. the summation order is fixed: results are deterministic.
+//
+// Diagonal tiles of S = A^T A (SYRK).  View the 128x128 tile as 16x16 subtiles
+// of 8x8 (one DMMA each).  Subtile (I, J) and its mirror (J, I) hold transposed
+// values, so each is accumulated over only HALF of the k4 steps -- (I > J) on
+// the even steps, (I < J) on the odd ones -- and S(I, J) = P(I, J) + P(J, I)^T
+// is formed by the fix-up; diagonal subtiles take every step.  Every warp of
+// the CTA does 32 or 40 of its 64 DMMAs per slab and the four SM sub-partitions
+// stay balanced (each holds one diagonal warp and three off-diagonal ones).
+// ---------------------------------------------------------------------------
+struct TnWork
 {
-    extern __shared__ __align__(16) unsigned char smraw[];
-    T* As = reinterpret_cast<T*>(smraw);
-    T* Bs = As + STAGES * 128 * PITCH_K;
+    long long nkt; // k-iterations per tile
+    long long tot; // total cost units
+    int ND, NT;    // diagonal-class tiles (listed first), all tiles
+    int G, smax;   // CTAs, partial slots per CTA
+    int tm, tn, nbatch;
+    int cd, cf;    // cost units of one k-iteration: diagonal / full tile
+};
 
-    const int tile_n = blockIdx.x, tile_m = blockIdx.y, split = blockIdx.z;
-    if (SYRK && tile_n > tile_m) return; // lower triangle of tiles only
-    const int m0 = tile_m * BM, n0 = tile_n * BN;
-    const long long kb = (long long)split * kper;
-    const long long ke = (kb + kper < k) ? kb + kper : k;
-    const int nkt      = (int)((ke - kb + KC - 1) / KC);
+__host__ __device__ inline long long tn_tile_start(const TnWork& W, int u)
+{
+    return u < W.ND ? (long long)u * W.cd * W.nkt
+                    : (long long)W.ND * W.cd * W.nkt + (long long)(u - W.ND) * W.cf * W.nkt;
+}
+__host__ __device__ inline int tn_tile_of(const TnWork& W, long long b)
+{
+    const long long dspan = (long long)W.ND * W.cd * W.nkt;
+    int u = b < dspan ? (int)(b / (W.cd * W.nkt)) : W.ND + (int)((b - dspan) / (W.cf * W.nkt));
+    return u < W.NT ? u : W.NT - 1;
+}
+__host__ __device__ inline void tn_cta_bounds(const TnWork& W, int g, long long& b0, long long& b1)
+{
+    b0 = W.tot * g / W.G;
+    b1 = W.tot * (g + 1) / W.G;
+}
+// k-iterations [it0, it1) of tile u inside the cost interval [b0, b1)
+__host__ __device__ inline void tn_seg(const TnWork& W, int u, long long b0, long long b1,
+    long long& it0, long long& it1)
+{
+    const long long s = tn_tile_start(W, u);
+    const int c       = u < W.ND ? W.cd : W.cf;
+    const long long r0 = b0 - s, r1 = b1 - s;
+    it0 = r0 <= 0 ? 0 : (r0 + c - 1) / c;
+    it1 = r1 <= 0 ? 0 : (r1 + c - 1) / c;
+    if (it0 > W.nkt) it0 = W.nkt;
+    if (it1 > W.nkt) it1 = W.nkt;
+}
+// tile u -> (batch, tile_m, tile_n)
+template <bool SYRK>
+__host__ __device__ inline void tn_decode(const TnWork& W, int u, int& batch, int& tile_m,
+    int& tile_n)
+{
+    if (SYRK)
+    {
+        if (u < W.ND)
+        {
+            batch  = u / W.tm;
+            tile_m = tile_n = u % W.tm;
+            return;
+        }
+        const int noff = W.tm * (W.tm - 1) / 2;
+        const int o    = u - W.ND;
+        batch          = o / noff;
+        const int idx  = o % noff;
+        int r          = 1;
+        while ((r + 1) * r / 2 <= idx) r++; // row r holds indices r(r-1)/2 .. r(r+1)/2-1
+        tile_m = r;
+        tile_n = idx - r * (r - 1) / 2;
+    }
+    else
+    {
+        const int per = W.tm * W.tn;
+        batch         = u / per;
+        const int r   = u % per;
+        tile_m        = r % W.tm;
+        tile_n        = r / W.tm;
+    }
+}
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = warp >> 2, wn = warp & 3; // 4 x 4 warps, 32 x 32 each
-    const int fr = lane >> 2, fc = lane & 3;
-
-    double acc[4][4][2];
-#pragma unroll
-    for (int i = 0; i < 4; i++)
-#pragma unroll
-        for (int j = 0; j < 4; j++)
-            acc[i][j][0] = acc[i][j][1] = 0.;
-
-    // prologue
+template <typename T, bool DIAG>
+__device__ __forceinline__ void tn_segment(double (&acc)[4][4][2], T* As, T* Bs, const T* A,
+    long long lda, const T* B, long long ldb, int m0, int m, int n0, int n, long long it0,
+    long long it1, long long kend, int tid, int wm, int wn, int fr, int fc)
+{
+    const int nit = (int)(it1 - it0);
+    // the ring is reused by the next segment: everybody must be done reading
+    __syncthreads();
 #pragma unroll
     for (int s = 0; s < STAGES - 1; s++)
     {
-        if (s < nkt)
+        if (s < nit)
         {
-            load_kmajor<T>(As + s * 128 * PITCH_K, A, lda, m0, m, kb + (long long)s * KC, ke, tid);
-            load_kmajor<T>(Bs + s * 128 * PITCH_K, B, ldb, n0, n, kb + (long long)s * KC, ke, tid);
+            load_kmajor<T>(As + s * 128 * PITCH_K, A, lda, m0, m, (it0 + s) * KC, kend, tid);
+            load_kmajor<T>(Bs + s * 128 * PITCH_K, B, ldb, n0, n, (it0 + s) * KC, kend, tid);
         }
         cp_async_commit();
     }
-    for (int kt = 0; kt < nkt; kt++)
+    for (int kt = 0; kt < nit; kt++)
     {
         cp_async_wait<STAGES - 2>();
         __syncthreads();
         {
             const int nx = kt + STAGES - 1;
-            if (nx < nkt)
+            if (nx < nit)
             {
                 const int s = nx % STAGES;
-                load_kmajor<T>(As + s * 128 * PITCH_K, A, lda, m0, m, kb + (long long)nx * KC, ke, tid);
-                load_kmajor<T>(Bs + s * 128 * PITCH_K, B, ldb, n0, n, kb + (long long)nx * KC, ke, tid);
+                load_kmajor<T>(As + s * 128 * PITCH_K, A, lda, m0, m, (it0 + nx) * KC, kend, tid);
+                load_kmajor<T>(Bs + s * 128 * PITCH_K, B, ldb, n0, n, (it0 + nx) * KC, kend, tid);
             }
             cp_async_commit();
         }
@@ -148,61 +219,156 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tn(int m, int n, long long
             for (int i = 0; i < 4; i++)
 #pragma unroll
                 for (int j = 0; j < 4; j++)
-                    dmma(acc[i][j], a[i], b[j]);
+                {
+                    if (DIAG)
+                    {
+                        const int I = wm * 4 + i, J = wn * 4 + j;
+                        if (I == J || ((I > J) == ((kk & 1) == 0))) dmma(acc[i][j], a[i], b[j]);
+                    }
+                    else
+                        dmma(acc[i][j], a[i], b[j]);
+                }
         }
     }
     cp_async_wait<0>();
-
-    // epilogue: thread holds C(m0 + wm*32 + i*8 + fr, n0 + wn*32 + j*8 + fc*2 + e)
-    double* dst   = (nsplit > 1) ? partial + (size_t)split * (size_t)m * n : C;
-    const int ldd = (nsplit > 1) ? m : ldc;
-#pragma unroll
-    for (int i = 0; i < 4; i++)
-#pragma unroll
-        for (int j = 0; j < 4; j++)
-#pragma unroll
-            for (int e = 0; e < 2; e++)
-            {
-                const int mm = m0 + wm * 32 + i * 8 + fr;
-                const int nn = n0 + wn * 32 + j * 8 + fc * 2 + e;
-                if (mm < m && nn < n)
-                {
-                    if (nsplit > 1)
-                        dst[(size_t)nn * ldd + mm] = acc[i][j][e];
-                    else
-                    {
-                        const double old
-                            = (beta == 0.) ? 0. : beta * C[(size_t)nn * ldc + mm];
-                        const double val = alpha * acc[i][j][e] + old;
-                        C[(size_t)nn * ldc + mm] = val;
-                        // tiles above the tile diagonal are filled by mirroring
-                        if (SYRK && tile_m > tile_n) C[(size_t)mm * ldc + nn] = val;
-                    }
-                }
-            }
 }
 
-// C = alpha * sum_s partial[s] + beta*C in a fixed order; SYRK mirrors the
-// lower triangle (LocalMatrices::fillUpperWithLower)
-template <bool SYRK>
-__global__ void k_splitk_reduce(int m, int n, int nsplit, const double* __restrict__ partial,
-    double alpha, double beta, double* __restrict__ C, int ldc)
+template <typename T, bool SYRK>
+__global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tn(TnWork W, int m, int n, long long k,
+    const T* __restrict__ A, long long lda, long long strideA, const T* __restrict__ B,
+    long long ldb, long long strideB, double alpha, double beta, double* __restrict__ C,
+    int ldc, long long strideC, double* __restrict__ partial)
 {
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (long long)m * n) return;
-    const int mm = (int)(t % m), nn = (int)(t / m);
-    if (SYRK)
+    extern __shared__ __align__(16) unsigned char smraw[];
+    T* As = reinterpret_cast<T*>(smraw);
+    T* Bs = As + STAGES * 128 * PITCH_K;
+
+    const int g = blockIdx.x;
+    long long b0, b1;
+    tn_cta_bounds(W, g, b0, b1);
+    if (b1 <= b0) return;
+    const int u_first = tn_tile_of(W, b0), u_last = tn_tile_of(W, b1 - 1);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp >> 2, wn = warp & 3; // 4 x 4 warps, 32 x 32 each
+    const int fr = lane >> 2, fc = lane & 3;
+
+    for (int u = u_first; u <= u_last; u++)
     {
-        // tiles strictly above the tile diagonal were not computed
-        if (nn / BN > mm / BM) return;
+        long long it0, it1;
+        tn_seg(W, u, b0, b1, it0, it1);
+        if (it0 >= it1) continue;
+        int batch, tile_m, tile_n;
+        tn_decode<SYRK>(W, u, batch, tile_m, tile_n);
+        const int m0 = tile_m * BM, n0 = tile_n * BN;
+        const bool diag = SYRK && u < W.ND;
+        const T* Ab = A + (long long)batch * strideA;
+        const T* Bb = B + (long long)batch * strideB;
+
+        double acc[4][4][2];
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                acc[i][j][0] = acc[i][j][1] = 0.;
+
+        if (diag)
+            tn_segment<T, true>(acc, As, Bs, Ab, lda, Bb, ldb, m0, m, n0, n, it0, it1, k, tid,
+                wm, wn, fr, fc);
+        else
+            tn_segment<T, false>(acc, As, Bs, Ab, lda, Bb, ldb, m0, m, n0, n, it0, it1, k, tid,
+                wm, wn, fr, fc);
+
+        // thread holds C(m0 + wm*32 + i*8 + fr, n0 + wn*32 + j*8 + fc*2 + e)
+        const bool direct = !diag && it0 == 0 && it1 == W.nkt;
+        if (direct)
+        {
+            double* Cb = C + (long long)batch * strideC;
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+#pragma unroll
+                    for (int e = 0; e < 2; e++)
+                    {
+                        const int mm = m0 + wm * 32 + i * 8 + fr;
+                        const int nn = n0 + wn * 32 + j * 8 + fc * 2 + e;
+                        if (mm < m && nn < n)
+                        {
+                            const double old
+                                = (beta == 0.) ? 0. : beta * Cb[(size_t)nn * ldc + mm];
+                            const double val          = alpha * acc[i][j][e] + old;
+                            Cb[(size_t)nn * ldc + mm] = val;
+                            // LocalMatrices::fillUpperWithLower
+                            if (SYRK) Cb[(size_t)mm * ldc + nn] = val;
+                        }
+                    }
+        }
+        else
+        {
+            double* dst = partial + ((size_t)g * W.smax + (size_t)(u - u_first)) * (BM * BN);
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                {
+                    const int ml = wm * 32 + i * 8 + fr;
+                    const int nl = wn * 32 + j * 8 + fc * 2;
+                    dst[(size_t)nl * BM + ml]       = acc[i][j][0];
+                    dst[(size_t)(nl + 1) * BM + ml] = acc[i][j][1];
+                }
+        }
     }
-    double s = 0.;
-    for (int sp = 0; sp < nsplit; sp++)
-        s += partial[(size_t)sp * m * n + (size_t)nn * m + mm];
-    const double old = (beta == 0.) ? 0. : beta * C[(size_t)nn * ldc + mm];
-    const double val = alpha * s + old;
-    C[(size_t)nn * ldc + mm] = val;
-    if (SYRK && mm / BM > nn / BN) C[(size_t)mm * ldc + nn] = val;
+}
+
+// Adds the partial slots of every tile that was not written directly, in CTA
+// order; for diagonal Gram tiles it also folds the mirrored half-sums,
+// S(r, c) = P(r, c) + P(c, r) unless both lie in the same 8x8 subtile.
+// grid: (tiles, 16 column blocks of 8), block 128 x 2.
+template <bool SYRK>
+__global__ void k_tn_fixup(TnWork W, int m, int n, const double* __restrict__ partial,
+    double alpha, double beta, double* __restrict__ C, int ldc, long long strideC)
+{
+    const int u = blockIdx.x;
+    const long long s0 = tn_tile_start(W, u);
+    const long long s1 = s0 + (long long)(u < W.ND ? W.cd : W.cf) * W.nkt;
+    // CTAs whose interval meets [s0, s1)
+    int gf = (int)(s0 * W.G / W.tot), gl = (int)((s1 - 1) * W.G / W.tot);
+    if (gf > 0) gf--;
+    if (gl < W.G - 1) gl++;
+    const bool diag = SYRK && u < W.ND;
+    int batch, tile_m, tile_n;
+    tn_decode<SYRK>(W, u, batch, tile_m, tile_n);
+    const int ml = threadIdx.x;
+    const int mm = tile_m * BM + ml;
+    double* Cb   = C + (long long)batch * strideC;
+    for (int nl = blockIdx.y * 8 + threadIdx.y; nl < blockIdx.y * 8 + 8; nl += blockDim.y)
+    {
+        const int nn = tile_n * BN + nl;
+        if (diag && nl > ml) continue; // lower triangle of the diagonal tile
+        const bool fold = diag && (ml >> 3) != (nl >> 3);
+        double s = 0.;
+        bool any = false;
+        for (int g = gf; g <= gl; g++)
+        {
+            long long b0, b1, it0, it1;
+            tn_cta_bounds(W, g, b0, b1);
+            if (b1 <= b0) continue;
+            tn_seg(W, u, b0, b1, it0, it1);
+            if (it0 >= it1) continue;
+            if (!diag && it0 == 0 && it1 == W.nkt) return; // written directly
+            const int uf = tn_tile_of(W, b0);
+            const double* src = partial + ((size_t)g * W.smax + (size_t)(u - uf)) * (BM * BN);
+            s += src[(size_t)nl * BM + ml];
+            if (fold) s += src[(size_t)ml * BM + nl];
+            any = true;
+        }
+        if (!any || mm >= m || nn >= n) continue;
+        const double old = (beta == 0.) ? 0. : beta * Cb[(size_t)nn * ldc + mm];
+        const double val = alpha * s + old;
+        Cb[(size_t)nn * ldc + mm] = val;
+        if (SYRK) Cb[(size_t)mm * ldc + nn] = val;
+    }
 }
 
 // Out(n x npt) = alpha * M^T Phi + beta*Out : rows of Out/Phi are orbitals
@@ -210,19 +376,24 @@ __global__ void k_splitk_reduce(int m, int n, int nsplit, const double* __restri
 // l + j*ldm), B' = Phi tile [KC l][128 p] (N-major).
 constexpr int PITCH_P = 128 + 8;
 
+// Persistent: one CTA per SM walks a contiguous range of (point tile, orbital
+// tile) items; the cp.async ring runs across item boundaries, so the operand
+// stream never drains while a tile's results are written out.
 template <typename T>
 __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_nn(long long npt, int n, int k,
     const T* __restrict__ Phi, long long lda, const double* __restrict__ M, int ldm,
-    double alpha, double beta, T* __restrict__ Out, long long ldc)
+    double alpha, double beta, T* __restrict__ Out, long long ldc, long long nitems,
+    int jtiles)
 {
     extern __shared__ __align__(16) unsigned char smraw[];
     double* Ms = reinterpret_cast<double*>(smraw);               // [STAGES][128][PITCH_K]
     T* Ps      = reinterpret_cast<T*>(Ms + STAGES * 128 * PITCH_K); // [STAGES][KC][PITCH_P]
 
-    const int tile_j = blockIdx.x;
-    const long long p0 = (long long)blockIdx.y * 128;
-    const int j0  = tile_j * 128;
-    const int nkt = (k + KC - 1) / KC;
+    const long long i0 = nitems * blockIdx.x / gridDim.x;
+    const long long i1 = nitems * (blockIdx.x + 1) / gridDim.x;
+    if (i1 <= i0) return;
+    const int nkt         = (k + KC - 1) / KC;
+    const long long total = (i1 - i0) * nkt;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp >> 2, wn = warp & 3;
     const int fr = lane >> 2, fc = lane & 3;
@@ -234,55 +405,60 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_nn(long long npt, int n, i
         for (int j = 0; j < 4; j++)
             acc[i][j][0] = acc[i][j][1] = 0.;
 
-    auto load_phi = [&](int s, int kt) {
-        constexpr int CH  = 16 / (int)sizeof(T);
-        constexpr int CPR = 128 / CH; // chunks per row of 128 points
-        constexpr int TOT = KC * CPR;
-        T* sm = Ps + s * KC * PITCH_P;
-#pragma unroll
-        for (int c = tid; c < TOT; c += NTHREADS)
+    // producer position (item, k-slab, ring stage) of the next load to issue
+    long long p_item = i0, p_issued = 0;
+    int p_kt = 0, p_stage = 0;
+    auto issue = [&]() {
+        if (p_issued < total)
         {
-            const int r  = c / CPR;
-            const int cc = c % CPR;
-            const int l  = kt * KC + r;
-            const long long p = p0 + (long long)cc * CH;
-            int valid = 0;
-            if (l < k && p < npt)
+            const int j0       = (int)(p_item % jtiles) * 128;
+            const long long p0 = (p_item / jtiles) * 128;
+            load_kmajor<double>(
+                Ms + p_stage * 128 * PITCH_K, M, ldm, j0, n, (long long)p_kt * KC, k, tid);
+            constexpr int CH  = 16 / (int)sizeof(T);
+            constexpr int CPR = 128 / CH; // chunks per row of 128 points
+            constexpr int TOT = KC * CPR;
+            T* sm = Ps + p_stage * KC * PITCH_P;
+#pragma unroll
+            for (int c = tid; c < TOT; c += NTHREADS)
             {
-                const long long rem = npt - p;
-                valid = rem >= CH ? 16 : (int)rem * (int)sizeof(T);
+                const int r  = c / CPR;
+                const int cc = c % CPR;
+                const int l  = p_kt * KC + r;
+                const long long p = p0 + (long long)cc * CH;
+                int valid = 0;
+                if (l < k && p < npt)
+                {
+                    const long long rem = npt - p;
+                    valid = rem >= CH ? 16 : (int)rem * (int)sizeof(T);
+                }
+                const T* src = Phi + (long long)(l < k ? l : 0) * lda + (valid ? p : 0);
+                cp_async16(sm + r * PITCH_P + cc * CH, src, valid);
             }
-            const T* src = Phi + (long long)(l < k ? l : 0) * lda + (valid ? p : 0);
-            cp_async16(sm + r * PITCH_P + cc * CH, src, valid);
+            p_issued++;
+            if (++p_kt == nkt)
+            {
+                p_kt = 0;
+                p_item++;
+            }
+            if (++p_stage == STAGES) p_stage = 0;
         }
+        cp_async_commit();
     };
 
 #pragma unroll
     for (int s = 0; s < STAGES - 1; s++)
-    {
-        if (s < nkt)
-        {
-            load_kmajor<double>(Ms + s * 128 * PITCH_K, M, ldm, j0, n, (long long)s * KC, k, tid);
-            load_phi(s, s);
-        }
-        cp_async_commit();
-    }
-    for (int kt = 0; kt < nkt; kt++)
+        issue();
+
+    long long item = i0;
+    int kt = 0, stage = 0;
+    for (long long it = 0; it < total; it++)
     {
         cp_async_wait<STAGES - 2>();
         __syncthreads();
-        {
-            const int nx = kt + STAGES - 1;
-            if (nx < nkt)
-            {
-                const int s = nx % STAGES;
-                load_kmajor<double>(Ms + s * 128 * PITCH_K, M, ldm, j0, n, (long long)nx * KC, k, tid);
-                load_phi(s, nx);
-            }
-            cp_async_commit();
-        }
-        const double* as = Ms + (kt % STAGES) * 128 * PITCH_K + (wm * 32 + fr) * PITCH_K + fc;
-        const T* bs      = Ps + (kt % STAGES) * KC * PITCH_P + fc * PITCH_P + wn * 32 + fr;
+        issue();
+        const double* as = Ms + stage * 128 * PITCH_K + (wm * 32 + fr) * PITCH_K + fc;
+        const T* bs      = Ps + stage * KC * PITCH_P + fc * PITCH_P + wn * 32 + fr;
 #pragma unroll
         for (int kk = 0; kk < KC / 4; kk++)
         {
@@ -299,30 +475,39 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_nn(long long npt, int n, i
                 for (int j = 0; j < 4; j++)
                     dmma(acc[i][j], a[i], b[j]);
         }
-    }
-    cp_async_wait<0>();
-
-    // thread holds Out(j0 + wm*32 + i*8 + fr, p0 + wn*32 + j*8 + fc*2 + {0,1})
-#pragma unroll
-    for (int i = 0; i < 4; i++)
-    {
-        const int jj = j0 + wm * 32 + i * 8 + fr;
-        if (jj >= n) continue;
-#pragma unroll
-        for (int j = 0; j < 4; j++)
+        if (++stage == STAGES) stage = 0;
+        if (++kt == nkt)
         {
-            const long long pp = p0 + wn * 32 + j * 8 + fc * 2;
-            T* o = Out + (long long)jj * ldc + pp;
+            // thread holds Out(j0 + wm*32 + i*8 + fr, p0 + wn*32 + j*8 + fc*2 + {0,1})
+            const int j0       = (int)(item % jtiles) * 128;
+            const long long p0 = (item / jtiles) * 128;
 #pragma unroll
-            for (int e = 0; e < 2; e++)
-                if (pp + e < npt)
+            for (int i = 0; i < 4; i++)
+            {
+                const int jj = j0 + wm * 32 + i * 8 + fr;
+#pragma unroll
+                for (int j = 0; j < 4; j++)
                 {
-                    // MPscal(beta) then += (T)buff  (mputils.cc:750-759)
-                    T base = (beta == 0.) ? (T)0 : (T)(beta * (double)o[e]);
-                    o[e]   = base + (T)(alpha * acc[i][j][e]);
+                    const long long pp = p0 + wn * 32 + j * 8 + fc * 2;
+                    T* o = Out + (long long)jj * ldc + pp;
+#pragma unroll
+                    for (int e = 0; e < 2; e++)
+                    {
+                        if (jj < n && pp + e < npt)
+                        {
+                            // MPscal(beta) then += (T)buff  (mputils.cc:750-759)
+                            T base = (beta == 0.) ? (T)0 : (T)(beta * (double)o[e]);
+                            o[e]   = base + (T)(alpha * acc[i][j][e]);
+                        }
+                        acc[i][j][e] = 0.;
+                    }
                 }
+            }
+            kt = 0;
+            item++;
         }
     }
+    cp_async_wait<0>();
 }
 
 // slow, always-applicable fallbacks (unaligned operands): one thread per
@@ -357,69 +542,111 @@ __global__ void k_gemm_nn_ref(long long npt, int n, int k, const T* Phi, long lo
     *o     = base + (T)s;
 }
 
+static int num_sms()
+{
+    static int n = 0;
+    if (n == 0)
+    {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess
+            || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess
+            || n <= 0)
+            n = 148;
+    }
+    return n;
+}
+
 template <typename T>
 static int gemm_tn_t(bool syrk, int m, int n, size_t k, double alpha, const T* A,
-    size_t lda, const T* B, size_t ldb, double beta, double* C, int ldc, cudaStream_t st)
+    size_t lda, size_t strideA, const T* B, size_t ldb, size_t strideB, double beta, double* C,
+    int ldc, size_t strideC, int nbatch, cudaStream_t st)
 {
     const bool aligned = (((uintptr_t)A | (uintptr_t)B) & 15) == 0
-                         && (lda * sizeof(T)) % 16 == 0 && (ldb * sizeof(T)) % 16 == 0;
+                         && (lda * sizeof(T)) % 16 == 0 && (ldb * sizeof(T)) % 16 == 0
+                         && (nbatch == 1
+                             || ((strideA * sizeof(T)) % 16 == 0 && (strideB * sizeof(T)) % 16 == 0));
     if (!aligned || k < 64)
     {
         const long long tot = (long long)m * n;
-        k_gemm_tn_ref<T><<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(m, n,
-            (long long)k, A, (long long)lda, B, (long long)ldb, alpha, beta, C, ldc,
-            syrk ? 1 : 0);
-        MGB_LAUNCHED("k_gemm_tn_ref");
+        for (int b = 0; b < nbatch; b++)
+        {
+            k_gemm_tn_ref<T><<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(m, n, (long long)k,
+                A + b * strideA, (long long)lda, B + b * strideB, (long long)ldb, alpha, beta,
+                C + b * strideC, ldc, syrk ? 1 : 0);
+            MGB_LAUNCHED("k_gemm_tn_ref");
+        }
         return MGB_OK;
     }
-    const int tm = (m + BM - 1) / BM, tn = (n + BN - 1) / BN;
-    const long long tiles = syrk ? (long long)tm * (tm + 1) / 2 : (long long)tm * tn;
-    // split K so that about two waves of CTAs exist
-    int nsplit = 1;
-    if (tiles < 2 * 148)
+    TnWork W;
+    W.tm     = (m + BM - 1) / BM;
+    W.tn     = (n + BN - 1) / BN;
+    W.nbatch = nbatch;
+    W.nkt    = (long long)((k + KC - 1) / KC);
+    // cost of one k-iteration: a diagonal Gram tile issues 136 of the 256 DMMAs
+    // of a full tile but stages the same operands (9/16 measured best)
+    W.cf = 16;
+    W.cd = 9;
+    if (const char* env = getenv("MGB_SYRK_DIAG_COST"))
     {
-        nsplit = (int)((2 * 148 + tiles - 1) / tiles);
-        const long long maxsplit = (long long)(k / (KC * 64)) > 0 ? (long long)(k / (KC * 64)) : 1;
-        if (nsplit > maxsplit) nsplit = (int)maxsplit;
-        if (nsplit > 512) nsplit = 512;
+        const int c = atoi(env);
+        if (c >= 1 && c <= 16) W.cd = c;
     }
-    long long kper = ((long long)k + nsplit - 1) / nsplit;
-    kper           = (kper + KC - 1) / KC * KC;
-    nsplit         = (int)(((long long)k + kper - 1) / kper);
-    double* partial = nullptr;
-    if (nsplit > 1)
+    if (syrk)
     {
-        partial = (double*)scratch(2, (size_t)nsplit * m * n * sizeof(double));
-        if (!partial) return MGB_ECUDA;
+        W.ND = W.tm * nbatch;
+        W.NT = W.tm * (W.tm + 1) / 2 * nbatch;
     }
+    else
+    {
+        W.ND = 0;
+        W.NT = W.tm * W.tn * nbatch;
+    }
+    W.tot = ((long long)W.ND * W.cd + (long long)(W.NT - W.ND) * W.cf) * W.nkt;
+    // one CTA per SM, but at least ~32 full-tile iterations each
+    long long G = W.tot / ((long long)W.cf * 32);
+    if (G < 1) G = 1;
+    if (G > num_sms()) G = num_sms();
+    W.G = (int)G;
+    // partial slots per CTA = the most tiles one CTA's share touches
+    int smax = 1;
+    for (int g = 0; g < W.G; g++)
+    {
+        long long b0, b1;
+        tn_cta_bounds(W, g, b0, b1);
+        if (b1 <= b0) continue;
+        const int span = tn_tile_of(W, b1 - 1) - tn_tile_of(W, b0) + 1;
+        if (span > smax) smax = span;
+    }
+    W.smax = smax;
+    double* partial
+        = (double*)scratch(2, (size_t)W.G * W.smax * BM * BN * sizeof(double));
+    if (!partial) return MGB_ECUDA;
     const size_t smem = (size_t)2 * STAGES * 128 * PITCH_K * sizeof(T);
-    dim3 grid((unsigned)tn, (unsigned)tm, (unsigned)nsplit);
     if (syrk)
     {
         auto kern = k_gemm_tn<T, true>;
         MGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, NTHREADS, smem, st>>>(m, n, (long long)k, kper, A, (long long)lda, B,
-            (long long)ldb, alpha, beta, C, ldc, partial, nsplit);
+        kern<<<W.G, NTHREADS, smem, st>>>(W, m, n, (long long)k, A, (long long)lda,
+            (long long)strideA, B, (long long)ldb, (long long)strideB, alpha, beta, C, ldc,
+            (long long)strideC, partial);
     }
     else
     {
         auto kern = k_gemm_tn<T, false>;
         MGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, NTHREADS, smem, st>>>(m, n, (long long)k, kper, A, (long long)lda, B,
-            (long long)ldb, alpha, beta, C, ldc, partial, nsplit);
+        kern<<<W.G, NTHREADS, smem, st>>>(W, m, n, (long long)k, A, (long long)lda,
+            (long long)strideA, B, (long long)ldb, (long long)strideB, alpha, beta, C, ldc,
+            (long long)strideC, partial);
     }
     MGB_LAUNCHED("k_gemm_tn");
-    if (nsplit > 1)
-    {
-        const long long tot = (long long)m * n;
-        if (syrk)
-            k_splitk_reduce<true><<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(
-                m, n, nsplit, partial, alpha, beta, C, ldc);
-        else
-            k_splitk_reduce<false><<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(
-                m, n, nsplit, partial, alpha, beta, C, ldc);
-        MGB_LAUNCHED("k_splitk_reduce");
-    }
+    dim3 fgrid((unsigned)W.NT, 16), fblock(128, 2);
+    if (syrk)
+        k_tn_fixup<true><<<fgrid, fblock, 0, st>>>(
+            W, m, n, partial, alpha, beta, C, ldc, (long long)strideC);
+    else
+        k_tn_fixup<false><<<fgrid, fblock, 0, st>>>(
+            W, m, n, partial, alpha, beta, C, ldc, (long long)strideC);
+    MGB_LAUNCHED("k_tn_fixup");
     return MGB_OK;
 }
 
@@ -439,20 +666,15 @@ static int gemm_nn_t(size_t m, int n, int k, double alpha, const T* A, size_t ld
     }
     const size_t smem = (size_t)STAGES * 128 * PITCH_K * sizeof(double)
                         + (size_t)STAGES * KC * PITCH_P * sizeof(T);
-    const size_t ptiles = (m + 127) / 128;
-    MGB_REQUIRE(ptiles <= 65535u * 32768u, "mgb_gemm_nn: too many points");
-    // grid.y is limited to 65535: fold the point tiles over several launches
+    const long long ptiles = (long long)((m + 127) / 128);
+    const int jtiles       = (n + 127) / 128;
+    const long long nitems = ptiles * jtiles;
     auto kern = k_gemm_nn<T>;
     MGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    for (size_t t0 = 0; t0 < ptiles; t0 += 65535)
-    {
-        const size_t nt = (ptiles - t0 < 65535) ? ptiles - t0 : 65535;
-        dim3 grid((unsigned)((n + 127) / 128), (unsigned)nt);
-        const size_t poff = t0 * 128;
-        kern<<<grid, NTHREADS, smem, st>>>((long long)(m - poff), n, k, A + poff,
-            (long long)lda, M, ldm, alpha, beta, Out + poff, (long long)ldc);
-        MGB_LAUNCHED("k_gemm_nn");
-    }
+    const unsigned grid = (unsigned)(nitems < num_sms() ? nitems : num_sms());
+    kern<<<grid, NTHREADS, smem, st>>>((long long)m, n, k, A, (long long)lda, M, ldm, alpha,
+        beta, Out, (long long)ldc, nitems, jtiles);
+    MGB_LAUNCHED("k_gemm_nn");
     return MGB_OK;
 }
 
@@ -472,12 +694,52 @@ int mgb_gemm_tn(int dtype, int m, int n, size_t k, double alpha, const void* A,
         "mgb_gemm_tn: bad dimensions");
     if (m == 0 || n == 0) return MGB_OK;
     if (dtype == MGB_F64)
-        return gemm_tn_t<double>(false, m, n, k, alpha, (const double*)A, lda,
-            (const double*)B, ldb, beta, C, ldc, as_stream(stream));
+        return gemm_tn_t<double>(false, m, n, k, alpha, (const double*)A, lda, 0,
+            (const double*)B, ldb, 0, beta, C, ldc, 0, 1, as_stream(stream));
     if (dtype == MGB_F32)
-        return gemm_tn_t<float>(false, m, n, k, alpha, (const float*)A, lda,
-            (const float*)B, ldb, beta, C, ldc, as_stream(stream));
+        return gemm_tn_t<float>(false, m, n, k, alpha, (const float*)A, lda, 0,
+            (const float*)B, ldb, 0, beta, C, ldc, 0, 1, as_stream(stream));
     set_error("mgb_gemm_tn: bad dtype");
+    return MGB_EINVAL;
+}
+
+int mgb_gemm_tn_slabs(int dtype, int m, int n, size_t k, int nslabs, double alpha,
+    const void* A, size_t lda, const void* B, size_t ldb, double beta, double* C, int ldc,
+    void* stream)
+{
+    if (int rc = require_device()) return rc;
+    MGB_REQUIRE(A && B && C, "mgb_gemm_tn_slabs: null pointer");
+    MGB_REQUIRE(m >= 0 && n >= 0 && nslabs >= 1 && ldc >= m && lda >= k * nslabs
+                    && ldb >= k * nslabs,
+        "mgb_gemm_tn_slabs: bad dimensions");
+    if (m == 0 || n == 0) return MGB_OK;
+    const size_t sc = (size_t)ldc * n;
+    if (dtype == MGB_F64)
+        return gemm_tn_t<double>(false, m, n, k, alpha, (const double*)A, lda, k,
+            (const double*)B, ldb, k, beta, C, ldc, sc, nslabs, as_stream(stream));
+    if (dtype == MGB_F32)
+        return gemm_tn_t<float>(false, m, n, k, alpha, (const float*)A, lda, k,
+            (const float*)B, ldb, k, beta, C, ldc, sc, nslabs, as_stream(stream));
+    set_error("mgb_gemm_tn_slabs: bad dtype");
+    return MGB_EINVAL;
+}
+
+int mgb_syrk_t_slabs(int dtype, int n, size_t k, int nslabs, double alpha, const void* A,
+    size_t lda, double* C, int ldc, void* stream)
+{
+    if (int rc = require_device()) return rc;
+    MGB_REQUIRE(A && C, "mgb_syrk_t_slabs: null pointer");
+    MGB_REQUIRE(n >= 0 && nslabs >= 1 && ldc >= n && lda >= k * nslabs,
+        "mgb_syrk_t_slabs: bad dimensions");
+    if (n == 0) return MGB_OK;
+    const size_t sc = (size_t)ldc * n;
+    if (dtype == MGB_F64)
+        return gemm_tn_t<double>(true, n, n, k, alpha, (const double*)A, lda, k,
+            (const double*)A, lda, k, 0., C, ldc, sc, nslabs, as_stream(stream));
+    if (dtype == MGB_F32)
+        return gemm_tn_t<float>(true, n, n, k, alpha, (const float*)A, lda, k,
+            (const float*)A, lda, k, 0., C, ldc, sc, nslabs, as_stream(stream));
+    set_error("mgb_syrk_t_slabs: bad dtype");
     return MGB_EINVAL;
 }
 
@@ -489,11 +751,11 @@ int mgb_syrk_t(int dtype, int n, size_t k, double alpha, const void* A, size_t l
     MGB_REQUIRE(n >= 0 && ldc >= n && lda >= k, "mgb_syrk_t: bad dimensions");
     if (n == 0) return MGB_OK;
     if (dtype == MGB_F64)
-        return gemm_tn_t<double>(true, n, n, k, alpha, (const double*)A, lda,
-            (const double*)A, lda, 0., C, ldc, as_stream(stream));
+        return gemm_tn_t<double>(true, n, n, k, alpha, (const double*)A, lda, 0,
+            (const double*)A, lda, 0, 0., C, ldc, 0, 1, as_stream(stream));
     if (dtype == MGB_F32)
-        return gemm_tn_t<float>(true, n, n, k, alpha, (const float*)A, lda,
-            (const float*)A, lda, 0., C, ldc, as_stream(stream));
+        return gemm_tn_t<float>(true, n, n, k, alpha, (const float*)A, lda, 0,
+            (const float*)A, lda, 0, 0., C, ldc, 0, 1, as_stream(stream));
     set_error("mgb_syrk_t: bad dtype");
     return MGB_EINVAL;
 }

@@ -421,7 +421,7 @@ class Masks:
 
     def set(self, level, iloc, color, state, values=None):
         ptr, dt = None, 1
-        if state == 2:
+        if state == 2 and values is not None:
             import numpy as np
             values = np.ascontiguousarray(values)
             dt = {np.dtype(np.float32): 0, np.dtype(np.float64): 1}[values.dtype]
@@ -488,11 +488,9 @@ class LocGridOrbitals(Orbitals):
         LocalMatrices::syrk per slab + fillUpperWithLower + scal)."""
         n = self.chromatic_number_
         ss = torch.empty((self.subdivx_, n, n), dtype=torch.float64, device="cuda")
-        for iloc in range(self.subdivx_):
-            a = self._slab(self.psi_, iloc)
-            check(lib().mgb_syrk_t(_dt(self.psi_), n, self.loc_numpt_, self.grid_.vel(),
-                                   a.data_ptr(), self.grid_.size(), _p(ss[iloc]), n,
-                                   _stream()))
+        check(lib().mgb_syrk_t_slabs(_dt(self.psi_), n, self.loc_numpt_, self.subdivx_,
+                                     self.grid_.vel(), _p(self.psi_), self.grid_.size(),
+                                     _p(ss), n, _stream()))
         return ss
 
     def computeLocalProduct(self, other, transpose=False):
@@ -503,11 +501,9 @@ class LocGridOrbitals(Orbitals):
         a, b = (arr, self.psi_) if transpose else (self.psi_, arr)
         m, n = a.shape[0], b.shape[0]
         ss = torch.empty((self.subdivx_, n, m), dtype=torch.float64, device="cuda")
-        for iloc in range(self.subdivx_):
-            check(lib().mgb_gemm_tn(_dt(self.psi_), m, n, self.loc_numpt_,
-                                    self.grid_.vel(), self._slab(a, iloc).data_ptr(),
-                                    self.grid_.size(), self._slab(b, iloc).data_ptr(),
-                                    self.grid_.size(), 0.0, _p(ss[iloc]), m, _stream()))
+        check(lib().mgb_gemm_tn_slabs(_dt(self.psi_), m, n, self.loc_numpt_, self.subdivx_,
+                                      self.grid_.vel(), _p(a), self.grid_.size(), _p(b),
+                                      self.grid_.size(), 0.0, _p(ss), m, _stream()))
         return ss.transpose(1, 2)
 
     def matrixToLocalMatrix(self, iloc, matrix):

@@ -526,6 +526,71 @@ def test_multiply_by_matrix(H, port, dt, N, n, dims):
         assert np.abs(got.astype(np.float64) - ref).max() <= tol * scale
 
 
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("N,dims", [(300, (32, 32, 32)), (520, (16, 32, 64)), (129, (64, 64, 16))])
+def test_contractions_many_tiles_streamk(H, dt, N, dims):
+    """Several 128-wide tiles with ragged edges and a K range long enough to
+    be shared between CTAs (stream-K segments, half-work diagonal Gram tiles,
+    fix-up): K*eps-scaled bound against the exact FP64 contraction, exact
+    symmetry, run-to-run determinism, and beta accumulation."""
+    from mgmol_b200._lib import lib, check
+    a = synthetic_orbitals(N, dims, dt)
+    b = synthetic_orbitals(N, dims, dt, first=2000)
+    grid = H.Grid(dims, (2.0, 2.0, 2.0), 1)
+    A = H.Orbitals(grid, N, TDT[dt], dev(a))
+    B = H.Orbitals(grid, N, TDT[dt], dev(b))
+    K = a[0].size
+    eps = np.finfo(np.float64).eps
+    ex = _exact_tn(a, a, grid.vel())
+    na = np.sqrt(np.diag(ex))
+    S = host(A.computeGram())
+    assert (np.abs(S - ex) <= 4 * K * eps * np.outer(na, na) + 1e-300).all()
+    assert np.array_equal(S, S.T)
+    assert bits_equal(S, host(A.computeGram())), "deterministic summation order"
+    exp = _exact_tn(a, b, grid.vel())
+    nb = np.sqrt(np.diag(_exact_tn(b, b, grid.vel())))
+    bound = 4 * K * eps * np.outer(na, nb) + 1e-300
+    P = host(A.computeLocalProduct(B))
+    assert (np.abs(P - exp) <= bound).all()
+    assert bits_equal(P, host(A.computeLocalProduct(B)))
+    # C = alpha A^T B + beta C
+    C0 = np.random.default_rng(5).standard_normal((N, N))
+    c = dev(C0.T.copy())  # column-major C(i, j)
+    check(lib().mgb_gemm_tn(0 if dt == np.float32 else 1, N, N, K, 0.5 * grid.vel(),
+                            A.psi().data_ptr(), K, B.psi().data_ptr(), K, -2.0,
+                            c.data_ptr(), N, None))
+    got = host(c).T
+    assert (np.abs(got - (0.5 * exp - 2.0 * C0)) <= bound + 4 * eps * np.abs(C0)).all()
+
+
+def test_contractions_full_size_against_cublas(H):
+    """H2O_64 shape (128^3 x 256, FP64): Gram, Phi^T H Phi-shaped product and
+    Phi M against cuBLAS DGEMM on the same operands, K*eps-scaled."""
+    n, N = 128, 256
+    K = n ** 3
+    g = torch.Generator(device="cuda").manual_seed(11)
+    phi = torch.rand((N, n, n, n), generator=g, device="cuda", dtype=torch.float64) - 0.5
+    grid = H.Grid((n, n, n), (23.5, 23.5, 23.5), 2)
+    A = H.Orbitals(grid, N, torch.float64, phi)
+    S = A.computeGram()
+    a2 = phi.view(N, -1)
+    ref = grid.vel() * (a2 @ a2.t())
+    eps = np.finfo(np.float64).eps
+    nrm = torch.sqrt(torch.diag(ref))
+    bound = 4 * K * eps * torch.outer(nrm, nrm)
+    assert bool(((S - ref).abs() <= bound).all())
+    assert torch.equal(S, S.t())
+    hphi = torch.roll(phi, 1, dims=0).contiguous()
+    P = A.computeLocalProduct(hphi)
+    refp = grid.vel() * (a2 @ hphi.view(N, -1).t())
+    assert bool(((P - refp).abs() <= bound.max()).all())
+    M = torch.randn((N, N), generator=g, device="cuda", dtype=torch.float64) / np.sqrt(N)
+    out = H.Orbitals(grid, N, torch.float64)
+    A.multiplyByMatrix(M, out)
+    refm = (M.t() @ a2).view_as(phi)
+    assert float((out.psi() - refm).abs().max()) <= 1e-13 * float(refm.abs().max()) * (N / 64)
+
+
 # --------------------------------------------------------------------------
 # full-size, size-independent properties (BASELINE configs: 128^3 and 256^3)
 # --------------------------------------------------------------------------
