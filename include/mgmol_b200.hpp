@@ -382,12 +382,149 @@ public:
         product.incrementIterativeIndex();
     }
 
-private:
+protected:
     Grid grid_;
     int numst_;
     size_t numpt_, lda_;
     DeviceMemory<T> psi_;
     int iterative_index_;
+};
+
+// The localization masks one rank holds for its colors: the data of MasksSet /
+// Map2Masks / GridMask (src/Map2Masks.cc:25-61, src/GridMask.h:41-52) as the
+// path consumes it.  op: MGB_MASK_MULT (GridMaskMult) or MGB_MASK_MAX
+// (GridMaskMax, the default orbital masks, src/MasksSet.cc:15,158-182).
+class Masks
+{
+public:
+    Masks(const Grid& grid, const short mg_levels, const short subdivx, const int ncolors,
+        const int op)
+        : handle_(nullptr)
+    {
+        MGB_CHECK(mgb_masks_create(&handle_, grid.c(), mg_levels, subdivx, ncolors, op));
+    }
+    ~Masks()
+    {
+        if (handle_) mgb_masks_destroy(handle_);
+    }
+    Masks(const Masks&)            = delete;
+    Masks& operator=(const Masks&) = delete;
+    // state: GridMask::mask_not_zero_ (-1 / 0 zero, 1 one, 2 values) of the
+    // mask of overlapping_gids[iloc][color]; 0 for an empty slot (gid -1)
+    template <typename M>
+    void set(const short level, const short iloc, const int color, const short state,
+        const M* values_host = nullptr)
+    {
+        MGB_CHECK(mgb_masks_set(
+            handle_, level, iloc, color, state, dtype_of<M>::value, values_host));
+    }
+    void commit() { MGB_CHECK(mgb_masks_commit(handle_)); }
+    // GridFuncVector::app_mask(level) (src/pb/GridFuncVector.cc:2428-2438)
+    template <typename T>
+    void apply(GridFuncVector<T>& gfv, const short level, void* stream = nullptr) const
+    {
+        MGB_CHECK(mgb_gfv_app_mask(dtype_of<T>::value, handle_, level, gfv.grid().ghost_pt(),
+            gfv.data(), gfv.size(), stream));
+    }
+    const mgb_masks* handle() const { return handle_; }
+
+private:
+    mgb_masks* handle_;
+};
+
+// LocGridOrbitals reduced to the hot path (src/LocGridOrbitals.h:60-, .cc):
+// numpt x chromatic_number colors; in x-slab iloc color c holds the global
+// orbital overlapping_gids[iloc][c] or nothing (-1).  Stencils, V-cycle and
+// BLAS-1 are those of the color block; contractions run per slab
+// (LocalMatrices with subdivx sub-matrices), masks localize.
+template <typename T>
+class LocGridOrbitals : public ExtendedGridOrbitals<T>
+{
+public:
+    LocGridOrbitals(const Grid& grid, const int numst,
+        const std::vector<std::vector<int>>& overlapping_gids, const Masks* masks = nullptr)
+        : ExtendedGridOrbitals<T>(grid, (int)overlapping_gids.at(0).size()),
+          numst_global_(numst), overlapping_gids_(overlapping_gids),
+          subdivx_((short)overlapping_gids.size()), masks_(masks)
+    {
+        assert(grid.dim(0) % subdivx_ == 0);
+        loc_numpt_ = this->numpt_ / subdivx_;
+    }
+    short subdivx() const { return subdivx_; }
+    size_t getLocNumpt() const { return loc_numpt_; }
+    const std::vector<std::vector<int>>& getOverlappingGids() const
+    {
+        return overlapping_gids_;
+    }
+    // src/LocGridOrbitals.cc:427-452
+    void applyMask(void* stream = nullptr)
+    {
+        if (masks_)
+            MGB_CHECK(mgb_app_mask(dtype_of<T>::value, masks_->handle(), 0, this->getPsi(),
+                this->lda_, this->chromatic_number(), stream));
+        this->incrementIterativeIndex();
+    }
+    // getLocalOverlap (src/LocGridOrbitals.cc:1504-1530): ss_dev holds subdivx
+    // column-major n x n matrices (LocalMatrices storage), all slabs in one
+    // launch
+    void getLocalOverlap(double* ss_dev, void* stream = nullptr) const
+    {
+        const int n = this->chromatic_number();
+        MGB_CHECK(mgb_syrk_t_slabs(dtype_of<T>::value, n, loc_numpt_, subdivx_,
+            this->grid_.vel(), this->getPsi(), this->lda_, ss_dev, n, stream));
+    }
+    // computeLocalProduct (src/LocGridOrbitals.cc:1554-1604)
+    void computeLocalProduct(const ExtendedGridOrbitals<T>& A, double* ss_dev,
+        const bool transpose = false, void* stream = nullptr) const
+    {
+        const T* a   = transpose ? A.getPsi() : this->getPsi();
+        const T* b   = transpose ? this->getPsi() : A.getPsi();
+        const size_t la = transpose ? A.getLda() : this->lda_;
+        const size_t lb = transpose ? this->lda_ : A.getLda();
+        const int m  = transpose ? A.chromatic_number() : this->chromatic_number();
+        const int n  = transpose ? this->chromatic_number() : A.chromatic_number();
+        MGB_CHECK(mgb_gemm_tn_slabs(dtype_of<T>::value, m, n, loc_numpt_, subdivx_,
+            this->grid_.vel(), a, la, b, lb, 0., ss_dev, m, stream));
+    }
+    // matrixToLocalMatrix (src/LocGridOrbitals.cc:1400-1424), host side:
+    // lmatrix (column-major chromatic x ncolor) from the global numst x numst
+    // column-major matrix
+    void matrixToLocalMatrix(const short iloc, const double* matrix, double* lmatrix) const
+    {
+        const int nc = this->chromatic_number();
+        for (int j = 0; j < nc; j++)
+        {
+            const int gidj = overlapping_gids_[iloc][j];
+            for (int i = 0; i < nc; i++)
+            {
+                const int gidi      = overlapping_gids_[iloc][i];
+                lmatrix[j * nc + i] = (gidi != -1 && gidj != -1)
+                                          ? matrix[(size_t)gidj * numst_global_ + gidi]
+                                          : 0.;
+            }
+        }
+    }
+    // multiplyByMatrix (src/LocGridOrbitals.cc:793-825): per slab product =
+    // Phi_iloc * M_iloc, matrices_dev = subdivx column-major n x n matrices
+    void multiplyByMatrix(const double* matrices_dev, ExtendedGridOrbitals<T>& product,
+        void* stream = nullptr) const
+    {
+        const int n = this->chromatic_number();
+        for (short iloc = 0; iloc < subdivx_; iloc++)
+            MGB_CHECK(mgb_gemm_nn(dtype_of<T>::value, loc_numpt_, n, n, 1.,
+                this->getPsi() + iloc * loc_numpt_, this->lda_,
+                matrices_dev + (size_t)iloc * n * n, n, 0., product.getPsi() + iloc * loc_numpt_,
+                product.getLda(), stream));
+        product.incrementIterativeIndex();
+    }
+    const Masks* masks() const { return masks_; }
+
+private:
+    int numst_global_;
+    std::vector<std::vector<int>> overlapping_gids_;
+    short subdivx_;
+    size_t loc_numpt_;
+    const Masks* masks_;
 };
 
 // pb::Lap<T> as LapFactory creates it
@@ -523,6 +660,14 @@ public:
             &handle_, lap_type, mg_levels, g.c(), orbitals.chromatic_number()));
         mg_levels_ = mg_levels;
         is_set_    = true;
+    }
+    // the same with `currentMasks` (LocGridOrbitals): :59-67 Map2Masks +
+    // GridFuncVector::setMasks
+    void setup(ExtendedGridOrbitals<T>& orbitals, const short mg_levels, const short lap_type,
+        const Masks* currentMasks)
+    {
+        setup(orbitals, mg_levels, lap_type);
+        MGB_CHECK(mgb_precond_set_masks(handle_, currentMasks ? currentMasks->handle() : nullptr));
     }
     // src/OrbitalsPreconditioning.cc:120-145
     void setGamma(const Lap<T>& lapOper, const double vmax, const short mg_levels,

@@ -54,12 +54,13 @@ __device__ __forceinline__ void dmma(double (&c)[2], double a, double b)
 // load a [128 rows][KC] slab of a K-major operand (row r at base + r*ld, K
 // contiguous) into smem rows of PITCH_K elements; rows >= nrows and K >= kend
 // are zero-filled.
-template <typename T>
+template <typename T, int KCv = KC>
 __device__ __forceinline__ void load_kmajor(T* sm, const T* base, long long ld,
     int row0, int nrows, long long k0, long long kend, int tid)
 {
+    constexpr int PITCH_K = KCv + PADK;
     constexpr int CH  = 16 / (int)sizeof(T);      // elements per 16B chunk
-    constexpr int CPR = KC / CH;                   // chunks per row
+    constexpr int CPR = KCv / CH;                  // chunks per row
     constexpr int TOT = 128 * CPR;
 #pragma unroll
     for (int c = tid; c < TOT; c += NTHREADS)
@@ -171,69 +172,98 @@ __host__ __device__ inline void tn_decode(const TnWork& W, int u, int& batch, in
     }
 }
 
-template <typename T, bool DIAG>
+// one k4 step of a warp: 4 + 4 fragment loads, then the DMMAs MODE selects
+//   0 all 16 subtiles, 1 diagonal warp on an even step (i >= j),
+//   2 diagonal warp on an odd step (i <= j)
+template <typename T, int MODE, int PITCH>
+__device__ __forceinline__ void tn_k4(double (&acc)[4][4][2], const T* as, const T* bs)
+{
+    double a[4], b[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+    {
+        a[i] = (double)as[i * 8 * PITCH];
+        b[i] = (double)bs[i * 8 * PITCH];
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (MODE == 0 || (MODE == 1 && i >= j) || (MODE == 2 && i <= j))
+                dmma(acc[i][j], a[i], b[j]);
+}
+
+template <typename T, bool DIAG, int KCv, int ST>
 __device__ __forceinline__ void tn_segment(double (&acc)[4][4][2], T* As, T* Bs, const T* A,
     long long lda, const T* B, long long ldb, int m0, int m, int n0, int n, long long it0,
     long long it1, long long kend, int tid, int wm, int wn, int fr, int fc)
 {
+    constexpr int PITCH = KCv + PADK;
     const int nit = (int)(it1 - it0);
     // the ring is reused by the next segment: everybody must be done reading
     __syncthreads();
 #pragma unroll
-    for (int s = 0; s < STAGES - 1; s++)
+    for (int s = 0; s < ST - 1; s++)
     {
         if (s < nit)
         {
-            load_kmajor<T>(As + s * 128 * PITCH_K, A, lda, m0, m, (it0 + s) * KC, kend, tid);
-            load_kmajor<T>(Bs + s * 128 * PITCH_K, B, ldb, n0, n, (it0 + s) * KC, kend, tid);
+            load_kmajor<T, KCv>(As + s * 128 * PITCH, A, lda, m0, m, (it0 + s) * KCv, kend, tid);
+            load_kmajor<T, KCv>(Bs + s * 128 * PITCH, B, ldb, n0, n, (it0 + s) * KCv, kend, tid);
         }
         cp_async_commit();
     }
     for (int kt = 0; kt < nit; kt++)
     {
-        cp_async_wait<STAGES - 2>();
+        cp_async_wait<ST - 2>();
         __syncthreads();
         {
-            const int nx = kt + STAGES - 1;
+            const int nx = kt + ST - 1;
             if (nx < nit)
             {
-                const int s = nx % STAGES;
-                load_kmajor<T>(As + s * 128 * PITCH_K, A, lda, m0, m, (it0 + nx) * KC, kend, tid);
-                load_kmajor<T>(Bs + s * 128 * PITCH_K, B, ldb, n0, n, (it0 + nx) * KC, kend, tid);
+                const int s = nx % ST;
+                load_kmajor<T, KCv>(
+                    As + s * 128 * PITCH, A, lda, m0, m, (it0 + nx) * KCv, kend, tid);
+                load_kmajor<T, KCv>(
+                    Bs + s * 128 * PITCH, B, ldb, n0, n, (it0 + nx) * KCv, kend, tid);
             }
             cp_async_commit();
         }
-        const T* as = As + (kt % STAGES) * 128 * PITCH_K + (wm * 32 + fr) * PITCH_K + fc;
-        const T* bs = Bs + (kt % STAGES) * 128 * PITCH_K + (wn * 32 + fr) * PITCH_K + fc;
-#pragma unroll
-        for (int kk = 0; kk < KC / 4; kk++)
+        const T* as = As + (kt % ST) * 128 * PITCH + (wm * 32 + fr) * PITCH + fc;
+        const T* bs = Bs + (kt % ST) * 128 * PITCH + (wn * 32 + fr) * PITCH + fc;
+        if (!DIAG)
         {
-            double a[4], b[4];
 #pragma unroll
-            for (int i = 0; i < 4; i++)
+            for (int kk = 0; kk < KCv / 4; kk++)
+                tn_k4<T, 0, PITCH>(acc, as + kk * 4, bs + kk * 4);
+        }
+        else if (wm > wn)
+        {
+            // lower warp block: every subtile has I > J -> even steps only
+#pragma unroll
+            for (int kk = 0; kk < KCv / 4; kk += 2)
+                tn_k4<T, 0, PITCH>(acc, as + kk * 4, bs + kk * 4);
+        }
+        else if (wm < wn)
+        {
+#pragma unroll
+            for (int kk = 1; kk < KCv / 4; kk += 2)
+                tn_k4<T, 0, PITCH>(acc, as + kk * 4, bs + kk * 4);
+        }
+        else
+        {
+            // diagonal warp block: I - J = i - j
+#pragma unroll
+            for (int kk = 0; kk < KCv / 4; kk += 2)
             {
-                a[i] = (double)as[i * 8 * PITCH_K + kk * 4];
-                b[i] = (double)bs[i * 8 * PITCH_K + kk * 4];
+                tn_k4<T, 1, PITCH>(acc, as + kk * 4, bs + kk * 4);
+                tn_k4<T, 2, PITCH>(acc, as + (kk + 1) * 4, bs + (kk + 1) * 4);
             }
-#pragma unroll
-            for (int i = 0; i < 4; i++)
-#pragma unroll
-                for (int j = 0; j < 4; j++)
-                {
-                    if (DIAG)
-                    {
-                        const int I = wm * 4 + i, J = wn * 4 + j;
-                        if (I == J || ((I > J) == ((kk & 1) == 0))) dmma(acc[i][j], a[i], b[j]);
-                    }
-                    else
-                        dmma(acc[i][j], a[i], b[j]);
-                }
         }
     }
     cp_async_wait<0>();
 }
 
-template <typename T, bool SYRK>
+template <typename T, bool SYRK, int KCv, int ST>
 __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tn(TnWork W, int m, int n, long long k,
     const T* __restrict__ A, long long lda, long long strideA, const T* __restrict__ B,
     long long ldb, long long strideB, double alpha, double beta, double* __restrict__ C,
@@ -241,7 +271,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tn(TnWork W, int m, int n,
 {
     extern __shared__ __align__(16) unsigned char smraw[];
     T* As = reinterpret_cast<T*>(smraw);
-    T* Bs = As + STAGES * 128 * PITCH_K;
+    T* Bs = As + ST * 128 * (KCv + PADK);
 
     const int g = blockIdx.x;
     long long b0, b1;
@@ -273,11 +303,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tn(TnWork W, int m, int n,
                 acc[i][j][0] = acc[i][j][1] = 0.;
 
         if (diag)
-            tn_segment<T, true>(acc, As, Bs, Ab, lda, Bb, ldb, m0, m, n0, n, it0, it1, k, tid,
-                wm, wn, fr, fc);
+            tn_segment<T, true, KCv, ST>(acc, As, Bs, Ab, lda, Bb, ldb, m0, m, n0, n, it0, it1,
+                k, tid, wm, wn, fr, fc);
         else
-            tn_segment<T, false>(acc, As, Bs, Ab, lda, Bb, ldb, m0, m, n0, n, it0, it1, k, tid,
-                wm, wn, fr, fc);
+            tn_segment<T, false, KCv, ST>(acc, As, Bs, Ab, lda, Bb, ldb, m0, m, n0, n, it0, it1,
+                k, tid, wm, wn, fr, fc);
 
         // thread holds C(m0 + wm*32 + i*8 + fr, n0 + wn*32 + j*8 + fc*2 + e)
         const bool direct = !diag && it0 == 0 && it1 == W.nkt;
@@ -374,18 +404,29 @@ __global__ void k_tn_fixup(TnWork W, int m, int n, const double* __restrict__ pa
 // Out(n x npt) = alpha * M^T Phi + beta*Out : rows of Out/Phi are orbitals
 // (points contiguous).  A' = M^T tile [128 j][KC l] (K-major: M is column-major
 // l + j*ldm), B' = Phi tile [KC l][128 p] (N-major).
-constexpr int PITCH_P = 128 + 8;
+// row pitch of the point-major Phi slab: the four k rows a fragment load touches
+// must fall into different bank groups (8-byte elements: pitch = 4 mod 16;
+// 4-byte: pitch = 8 mod 32)
+template <typename T>
+struct PitchP
+{
+    static constexpr int value = sizeof(T) == 8 ? 128 + 4 : 128 + 8;
+};
 
 // Persistent: one CTA per SM walks a contiguous range of (point tile, orbital
 // tile) items; the cp.async ring runs across item boundaries, so the operand
 // stream never drains while a tile's results are written out.
-template <typename T>
+template <typename T, int KCv, int ST>
 __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_nn(long long npt, int n, int k,
     const T* __restrict__ Phi, long long lda, const double* __restrict__ M, int ldm,
     double alpha, double beta, T* __restrict__ Out, long long ldc, long long nitems,
     int jtiles)
 {
     extern __shared__ __align__(16) unsigned char smraw[];
+    constexpr int PITCH_K = KCv + PADK;
+    constexpr int PITCH_P = PitchP<T>::value;
+    constexpr int KC      = KCv;
+    constexpr int STAGES  = ST;
     double* Ms = reinterpret_cast<double*>(smraw);               // [STAGES][128][PITCH_K]
     T* Ps      = reinterpret_cast<T*>(Ms + STAGES * 128 * PITCH_K); // [STAGES][KC][PITCH_P]
 
@@ -397,6 +438,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_nn(long long npt, int n, i
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp >> 2, wn = warp & 3;
     const int fr = lane >> 2, fc = lane & 3;
+    // pairs of results go out as one 2-element store when every row allows it
+    const bool vec2 = (((uintptr_t)Out) % (2 * sizeof(T)) == 0) && (ldc % 2 == 0);
 
     double acc[4][4][2];
 #pragma unroll
@@ -413,7 +456,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_nn(long long npt, int n, i
         {
             const int j0       = (int)(p_item % jtiles) * 128;
             const long long p0 = (p_item / jtiles) * 128;
-            load_kmajor<double>(
+            load_kmajor<double, KCv>(
                 Ms + p_stage * 128 * PITCH_K, M, ldm, j0, n, (long long)p_kt * KC, k, tid);
             constexpr int CH  = 16 / (int)sizeof(T);
             constexpr int CPR = 128 / CH; // chunks per row of 128 points
@@ -490,16 +533,31 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_nn(long long npt, int n, i
                 {
                     const long long pp = p0 + wn * 32 + j * 8 + fc * 2;
                     T* o = Out + (long long)jj * ldc + pp;
+                    // MPscal(beta) then += (T)buff  (mputils.cc:750-759)
+                    T r[2];
 #pragma unroll
                     for (int e = 0; e < 2; e++)
                     {
-                        if (jj < n && pp + e < npt)
-                        {
-                            // MPscal(beta) then += (T)buff  (mputils.cc:750-759)
-                            T base = (beta == 0.) ? (T)0 : (T)(beta * (double)o[e]);
-                            o[e]   = base + (T)(alpha * acc[i][j][e]);
-                        }
+                        T base = (T)0;
+                        if (beta != 0. && jj < n && pp + e < npt)
+                            base = (T)(beta * (double)o[e]);
+                        r[e]         = base + (T)(alpha * acc[i][j][e]);
                         acc[i][j][e] = 0.;
+                    }
+                    if (jj < n)
+                    {
+                        if (vec2 && pp + 1 < npt)
+                        {
+                            if (sizeof(T) == 8)
+                                *reinterpret_cast<double2*>(o) = make_double2(r[0], r[1]);
+                            else
+                                *reinterpret_cast<float2*>(o) = make_float2(r[0], r[1]);
+                        }
+                        else
+                        {
+                            if (pp < npt) o[0] = r[0];
+                            if (pp + 1 < npt) o[1] = r[1];
+                        }
                     }
                 }
             }
@@ -581,11 +639,15 @@ static int gemm_tn_t(bool syrk, int m, int n, size_t k, double alpha, const T* A
     W.tm     = (m + BM - 1) / BM;
     W.tn     = (n + BN - 1) / BN;
     W.nbatch = nbatch;
-    W.nkt    = (long long)((k + KC - 1) / KC);
+    // slab width / ring depth: 16 x 4 or 32 x 3 (MGB_TN_KC, tuning hook)
+    int kcv = 32;
+    if (const char* env = getenv("MGB_TN_KC")) kcv = atoi(env) == 16 ? 16 : 32;
+    const int st_ = kcv == 32 ? 3 : 4;
+    W.nkt    = (long long)((k + kcv - 1) / kcv);
     // cost of one k-iteration: a diagonal Gram tile issues 136 of the 256 DMMAs
-    // of a full tile but stages the same operands (9/16 measured best)
+    // of a full tile but stages the same operands (10/16 measured best on B200)
     W.cf = 16;
-    W.cd = 9;
+    W.cd = 10;
     if (const char* env = getenv("MGB_SYRK_DIAG_COST"))
     {
         const int c = atoi(env);
@@ -603,7 +665,7 @@ static int gemm_tn_t(bool syrk, int m, int n, size_t k, double alpha, const T* A
     }
     W.tot = ((long long)W.ND * W.cd + (long long)(W.NT - W.ND) * W.cf) * W.nkt;
     // one CTA per SM, but at least ~32 full-tile iterations each
-    long long G = W.tot / ((long long)W.cf * 32);
+    long long G = W.tot / ((long long)W.cf * (512 / kcv));
     if (G < 1) G = 1;
     if (G > num_sms()) G = num_sms();
     W.G = (int)G;
@@ -621,23 +683,31 @@ static int gemm_tn_t(bool syrk, int m, int n, size_t k, double alpha, const T* A
     double* partial
         = (double*)scratch(2, (size_t)W.G * W.smax * BM * BN * sizeof(double));
     if (!partial) return MGB_ECUDA;
-    const size_t smem = (size_t)2 * STAGES * 128 * PITCH_K * sizeof(T);
+    const size_t smem = (size_t)2 * st_ * 128 * (kcv + PADK) * sizeof(T);
+#define MGB_TN_LAUNCH(SY, KV, STV)                                                        \
+    {                                                                                     \
+        auto kern = k_gemm_tn<T, SY, KV, STV>;                                            \
+        MGB_CUDA(cudaFuncSetAttribute(                                                    \
+            kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));               \
+        kern<<<W.G, NTHREADS, smem, st>>>(W, m, n, (long long)k, A, (long long)lda,      \
+            (long long)strideA, B, (long long)ldb, (long long)strideB, alpha, beta, C,   \
+            ldc, (long long)strideC, partial);                                            \
+    }
     if (syrk)
     {
-        auto kern = k_gemm_tn<T, true>;
-        MGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<W.G, NTHREADS, smem, st>>>(W, m, n, (long long)k, A, (long long)lda,
-            (long long)strideA, B, (long long)ldb, (long long)strideB, alpha, beta, C, ldc,
-            (long long)strideC, partial);
+        if (kcv == 32)
+            MGB_TN_LAUNCH(true, 32, 3)
+        else
+            MGB_TN_LAUNCH(true, 16, 4)
     }
     else
     {
-        auto kern = k_gemm_tn<T, false>;
-        MGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<W.G, NTHREADS, smem, st>>>(W, m, n, (long long)k, A, (long long)lda,
-            (long long)strideA, B, (long long)ldb, (long long)strideB, alpha, beta, C, ldc,
-            (long long)strideC, partial);
+        if (kcv == 32)
+            MGB_TN_LAUNCH(false, 32, 3)
+        else
+            MGB_TN_LAUNCH(false, 16, 4)
     }
+#undef MGB_TN_LAUNCH
     MGB_LAUNCHED("k_gemm_tn");
     dim3 fgrid((unsigned)W.NT, 16), fblock(128, 2);
     if (syrk)
@@ -664,16 +734,29 @@ static int gemm_nn_t(size_t m, int n, int k, double alpha, const T* A, size_t ld
         MGB_LAUNCHED("k_gemm_nn_ref");
         return MGB_OK;
     }
-    const size_t smem = (size_t)STAGES * 128 * PITCH_K * sizeof(double)
-                        + (size_t)STAGES * KC * PITCH_P * sizeof(T);
+    int kcv = 32;
+    if (const char* env = getenv("MGB_NN_KC")) kcv = atoi(env) == 16 ? 16 : 32;
+    const int st_     = kcv == 32 ? 3 : 4;
+    const size_t smem = (size_t)st_ * 128 * (kcv + PADK) * sizeof(double)
+                        + (size_t)st_ * kcv * PitchP<T>::value * sizeof(T);
     const long long ptiles = (long long)((m + 127) / 128);
     const int jtiles       = (n + 127) / 128;
     const long long nitems = ptiles * jtiles;
-    auto kern = k_gemm_nn<T>;
-    MGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const unsigned grid = (unsigned)(nitems < num_sms() ? nitems : num_sms());
-    kern<<<grid, NTHREADS, smem, st>>>((long long)m, n, k, A, (long long)lda, M, ldm, alpha,
-        beta, Out, (long long)ldc, nitems, jtiles);
+    const unsigned grid    = (unsigned)(nitems < num_sms() ? nitems : num_sms());
+    if (kcv == 32)
+    {
+        auto kern = k_gemm_nn<T, 32, 3>;
+        MGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, NTHREADS, smem, st>>>((long long)m, n, k, A, (long long)lda, M, ldm, alpha,
+            beta, Out, (long long)ldc, nitems, jtiles);
+    }
+    else
+    {
+        auto kern = k_gemm_nn<T, 16, 4>;
+        MGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, NTHREADS, smem, st>>>((long long)m, n, k, A, (long long)lda, M, ldm, alpha,
+            beta, Out, (long long)ldc, nitems, jtiles);
+    }
     MGB_LAUNCHED("k_gemm_nn");
     return MGB_OK;
 }

@@ -21,6 +21,15 @@ int orc_hpsi_f32(int lap_type, const int dims[3], const double ll[3], const int 
     const float* phi, const double* vtot, float* hphi, int nfunc);
 int orc_precond_mg(int lap_type, int mg_levels, int dtype, const int dims[3],
     const double ll[3], const int bc[3], void* res, int nfunc, double gamma);
+int orc_precond_mg_masked(int lap_type, int mg_levels, int dtype, const int dims[3],
+    const double ll[3], const int bc[3], void* res, int nfunc, double gamma, int subdivx,
+    int ncolors, int mask_op, const int* mstate, const long long* mvoff, const double* mvalues);
+void orc_app_mask_noghost_f64(const int dims[3], int subdivx, int ncolors, int op,
+    const int* state, const long long* voff, const double* values, double* u, size_t ld,
+    int nfunc);
+void orc_app_mask_noghost_f32(const int dims[3], int subdivx, int ncolors, int op,
+    const int* state, const long long* voff, const double* values, float* u, size_t ld,
+    int nfunc);
 void orc_gemm_tn_f64(int m, int n, int k, double alpha, const double* a, int lda,
     const double* b, int ldb, double* c, int ldc);
 void orc_gemm_tn_f32(int m, int n, int k, double alpha, const float* a, int lda,
@@ -154,6 +163,145 @@ static int run(const int lap_type, const double tol, const double mg_tol)
     return fails;
 }
 
+static void oracle_app_mask(const int dims[3], int subdivx, int nc, int op, const int* st,
+    const long long* vo, const double* val, double* u, size_t ld)
+{
+    orc_app_mask_noghost_f64(dims, subdivx, nc, op, st, vo, val, u, ld, nc);
+}
+static void oracle_app_mask(const int dims[3], int subdivx, int nc, int op, const int* st,
+    const long long* vo, const double* val, float* u, size_t ld)
+{
+    orc_app_mask_noghost_f32(dims, subdivx, nc, op, st, vo, val, u, ld, nc);
+}
+
+// LocGridOrbitals the way MGmol uses it: colors with per-slab gids, masks from
+// a centre and a radius (here: a ball profile per color and level), applyMask,
+// per-slab overlap matrices, masked preconditioner.
+template <typename T>
+static int run_localized(const int lap_type, const int op, const double mg_tol)
+{
+    const int dims[3]      = { 16, 16, 32 };
+    const unsigned gdim[3] = { 16, 16, 32 };
+    const double ll[3]     = { 4.0, 4.0, 8.0 };
+    const int bc[3]        = { 1, 1, 1 };
+    const int N = 4, subdivx = 2, levels = 2, numst = 6;
+    const size_t npt = (size_t)dims[0] * dims[1] * dims[2];
+    const std::vector<std::vector<int>> gids = { { 0, 1, -1, 3 }, { 2, 1, 4, 5 } };
+    unsigned long long seed = 99 + lap_type + 7 * op;
+    std::vector<T> phi(npt * N);
+    for (size_t i = 0; i < phi.size(); i++)
+        phi[i] = (T)lcg(seed);
+
+    Grid grid(gdim, ll, ghostsFor(lap_type), bc);
+    Masks masks(grid, levels, subdivx, N, op);
+    // oracle tables [level][iloc][color]
+    std::vector<int> st((levels + 1) * subdivx * N);
+    std::vector<long long> vo(st.size(), -1);
+    std::vector<double> pool;
+    for (int l = 0; l <= levels; l++)
+    {
+        const int d[3] = { dims[0] >> l, dims[1] >> l, dims[2] >> l };
+        const int s0   = d[0] / subdivx;
+        for (int iloc = 0; iloc < subdivx; iloc++)
+            for (int c = 0; c < N; c++)
+            {
+                const size_t t = ((size_t)l * subdivx + iloc) * N + c;
+                const int gid  = gids[iloc][c];
+                if (gid == -1)
+                    st[t] = 0;
+                else if (gid == 3)
+                    st[t] = 1;
+                else
+                {
+                    st[t] = 2;
+                    vo[t] = (long long)pool.size();
+                    std::vector<double> v((size_t)s0 * d[1] * d[2]);
+                    for (int ix = 0; ix < s0; ix++)
+                        for (int iy = 0; iy < d[1]; iy++)
+                            for (int iz = 0; iz < d[2]; iz++)
+                            {
+                                const double x = (ix + iloc * s0 + 0.5) / d[0] - 0.3 - 0.1 * gid;
+                                const double y = (iy + 0.5) / d[1] - 0.5;
+                                const double z = (iz + 0.5) / d[2] - 0.2 * gid;
+                                const double r = std::sqrt(x * x + y * y + z * z) / 0.45;
+                                v[((size_t)ix * d[1] + iy) * d[2] + iz]
+                                    = r < 0.75 ? 1. : (r < 1. ? (float)(4. * (1. - r)) : 0.);
+                            }
+                    pool.insert(pool.end(), v.begin(), v.end());
+                    masks.set(l, iloc, c, 2, v.data());
+                    continue;
+                }
+                masks.set<double>(l, iloc, c, (short)st[t]);
+            }
+    }
+    masks.commit();
+
+    int fails = 0;
+    LocGridOrbitals<T> orbitals(grid, numst, gids, &masks);
+    orbitals.setPsi(phi.data());
+    orbitals.applyMask();
+    std::vector<T> got(npt * N), ref(phi);
+    orbitals.getPsiHost(got.data());
+    oracle_app_mask(dims, subdivx, N, op, st.data(), vo.data(), pool.data(), ref.data(), npt);
+    for (size_t i = 0; i < got.size(); i++)
+        if (got[i] != ref[i])
+        {
+            fails++;
+            break;
+        }
+    std::printf("lap %2d %s op %d  applyMask   %s\n", lap_type, sizeof(T) == 8 ? "f64" : "f32", op,
+        fails ? "DIFFERS" : "bit-identical");
+
+    // per-slab overlap: ss[iloc] = vel Phi_iloc^T Phi_iloc
+    DeviceMemory<double> ss_dev((size_t)subdivx * N * N);
+    std::vector<double> ss(subdivx * N * N), ss_ref(N * N);
+    orbitals.getLocalOverlap(ss_dev.data());
+    ss_dev.copy_to_host(ss.data(), ss.size());
+    const size_t lnp = npt / subdivx;
+    double serr = 0., smax = 0.;
+    for (int iloc = 0; iloc < subdivx; iloc++)
+    {
+        std::vector<T> slab(lnp * N);
+        for (int c = 0; c < N; c++)
+            for (size_t i = 0; i < lnp; i++)
+                slab[c * lnp + i] = ref[c * npt + iloc * lnp + i];
+        oracle_gemm_tn(N, N, (int)lnp, grid.vel(), slab.data(), slab.data(), ss_ref.data());
+        for (int i = 0; i < N * N; i++)
+        {
+            smax = std::fmax(smax, std::fabs(ss_ref[i]));
+            serr = std::fmax(serr, std::fabs(ss[iloc * N * N + i] - ss_ref[i]));
+        }
+    }
+    const double stol = sizeof(T) == 8 ? 1e-12 : 1e-6;
+    std::printf("lap %2d %s op %d  slab Gram   rel err %.3e (tol %.0e)\n", lap_type,
+        sizeof(T) == 8 ? "f64" : "f32", op, serr / smax, stol);
+    if (!(serr <= stol * smax)) fails++;
+
+    // masked preconditioner
+    OrbitalsPreconditioning<T> precond;
+    precond.setup(orbitals, levels, (short)lap_type, &masks);
+    precond.setGamma(0.3);
+    precond.precond_mg(orbitals);
+    orbitals.getPsiHost(got.data());
+    orc_precond_mg_masked(lap_type, levels, dtype_of<T>::value, dims, ll, bc, ref.data(), N, 0.3,
+        subdivx, N, op, st.data(), vo.data(), pool.data());
+    double worst = 0.;
+    for (int j = 0; j < N; j++)
+    {
+        double scale = 0., err = 0.;
+        for (size_t i = 0; i < npt; i++)
+        {
+            scale = std::fmax(scale, std::fabs((double)ref[j * npt + i]));
+            err   = std::fmax(err, std::fabs((double)got[j * npt + i] - (double)ref[j * npt + i]));
+        }
+        worst = std::fmax(worst, scale > 0 ? err / scale : err);
+    }
+    std::printf("lap %2d %s op %d  precond_mg  rel err %.3e (tol %.0e)\n", lap_type,
+        sizeof(T) == 8 ? "f64" : "f32", op, worst, mg_tol);
+    if (!(worst <= mg_tol)) fails++;
+    return fails;
+}
+
 int main()
 {
     if (mgb_device_count() < 1)
@@ -166,6 +314,11 @@ int main()
     {
         fails += run<double>(lap, 1e-12, 5e-6);
         fails += run<float>(lap, 1e-5, 5e-6);
+        for (int op : { MGB_MASK_MULT, MGB_MASK_MAX })
+        {
+            fails += run_localized<double>(lap, op, 5e-6);
+            fails += run_localized<float>(lap, op, 5e-6);
+        }
     }
     std::printf(fails ? "FAILED (%d)\n" : "ok\n", fails);
     return fails ? 1 : 0;
