@@ -299,6 +299,26 @@ int mgb_comm_destroy(mgb_comm* c);
  * 1746 and ReplicatedMatrix::consolidate (src/ReplicatedMatrix.cc:108-127):
  * in-place sum of a device array over all ranks.                            */
 int mgb_allreduce_sum_f64(mgb_comm* c, double* data, size_t n, void* stream);
+/* Stream-ordered barrier over the ranks (a one-element all-reduce).            */
+int mgb_comm_barrier(mgb_comm* c, void* stream);
+/* Direct peer reads over NVLink.  Every rank registers ITS array (collective:
+ * each rank passes its own pointer, e.g. its orbital block) and the library
+ * maps the other ranks' arrays into this process with CUDA IPC
+ * (cudaIpcGetMemHandle / cudaIpcOpenMemHandle, peer access over NVLink /
+ * NVSwitch).  Kernels then read the neighbours' boundary planes in place:
+ * this replaces the pack / MPI_Isend / unpack of initiate/finishEastWestComm
+ * (src/pb/GridFuncVector.cc:1195-1256) for arrays that stay resident.
+ * Returns MGB_ENOTSUP if an array is not in IPC-exportable (cudaMalloc)
+ * memory; the packed exchange below then remains available.                 */
+int mgb_peer_register(mgb_comm* c, const void* ptr, void* stream);
+int mgb_peer_unregister(mgb_comm* c, const void* ptr);
+/* mgb_hpsi on an x-split domain with the neighbours' boundary planes of phi
+ * read directly from their registered blocks (no x-halo buffer for phi; V's
+ * halo xhalo_v is exchanged once per potential update with
+ * mgb_halo_exchange_x).  Collective: rank barrier, fused kernel, rank barrier. */
+int mgb_hpsi_peer(mgb_comm* c, int lap_type, int dtype, const mgb_grid* grid,
+    const void* phi, size_t ld, const double* vtot, void* hphi, size_t ldh,
+    int nfunc, const double* xhalo_v, void* stream);
 /* x-direction halo for the fused H path: sends this rank's first/last g
  * planes of every function to the west/east neighbours and fills
  * xhalo[nfunc][2g][ny][nz] (replaces initiate/finishEastWestComm,

@@ -112,6 +112,12 @@ _SIGS = {
     "mgb_comm_create": (c_int, [ctypes.POINTER(c_void_p), c_void_p, c_int, c_int]),
     "mgb_comm_destroy": (c_int, [c_void_p]),
     "mgb_allreduce_sum_f64": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    "mgb_comm_barrier": (c_int, [c_void_p, c_void_p]),
+    "mgb_peer_register": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "mgb_peer_unregister": (c_int, [c_void_p, c_void_p]),
+    "mgb_hpsi_peer": (c_int, [c_void_p, c_int, c_int, ctypes.POINTER(MgbGrid), c_void_p,
+                              c_size_t, c_void_p, c_void_p, c_size_t, c_int, c_void_p,
+                              c_void_p]),
     "mgb_halo_exchange_x": (c_int, [c_void_p, c_int, ctypes.POINTER(MgbGrid), c_int,
                                     c_void_p, c_size_t, c_void_p, c_int, c_void_p]),
     "mgb_halo_exchange_ghosted": (c_int, [c_void_p, c_int, ctypes.POINTER(MgbGrid),

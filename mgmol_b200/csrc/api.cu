@@ -220,9 +220,10 @@ int mgb_hpsi_force_path(int path)
     return MGB_OK;
 }
 
-int mgb_hpsi(int lap_type, int dtype, const mgb_grid* grid, const void* phi,
+static int hpsi_entry(int lap_type, int dtype, const mgb_grid* grid, const void* phi,
     size_t ld, const double* vtot, void* hphi, size_t ldh, int nfunc,
-    const void* xhalo_phi, const double* xhalo_v, void* stream)
+    const void* xhalo_phi, const double* xhalo_v, const void* peer_w, const void* peer_e,
+    void* stream)
 {
     if (int rc = require_device()) return rc;
     if (int rc = check_grid(grid)) return rc;
@@ -253,11 +254,13 @@ int mgb_hpsi(int lap_type, int dtype, const mgb_grid* grid, const void* phi,
     a.nfunc     = nfunc;
     a.xhalo_phi = xhalo_phi;
     a.xhalo_v   = xhalo_v;
+    a.peer_w    = peer_w;
+    a.peer_e    = peer_e;
     cudaStream_t st = as_stream(stream);
 
     const bool uniform_bc = (grid->bc[0] == grid->bc[1] && grid->bc[1] == grid->bc[2]);
     const bool yz_single  = grid->nproc[1] == 1 && grid->nproc[2] == 1;
-    MGB_REQUIRE(grid->nproc[0] == 1 || (xhalo_phi && xhalo_v),
+    MGB_REQUIRE(grid->nproc[0] == 1 || ((xhalo_phi || (peer_w && peer_e)) && xhalo_v),
         "mgb_hpsi: x is split over %d ranks but no x-halo buffers were given",
         grid->nproc[0]);
     MGB_REQUIRE(grid->dim[0] >= a.g && grid->dim[1] >= a.g && grid->dim[2] >= a.g,
@@ -296,6 +299,48 @@ int mgb_hpsi(int lap_type, int dtype, const mgb_grid* grid, const void* phi,
         "points with mgb_halo_exchange_ghosted");
     g_last_path = 3;
     return hpsi_ghosted(a, st);
+}
+
+int mgb_hpsi(int lap_type, int dtype, const mgb_grid* grid, const void* phi,
+    size_t ld, const double* vtot, void* hphi, size_t ldh, int nfunc,
+    const void* xhalo_phi, const double* xhalo_v, void* stream)
+{
+    return hpsi_entry(lap_type, dtype, grid, phi, ld, vtot, hphi, ldh, nfunc, xhalo_phi,
+        xhalo_v, nullptr, nullptr, stream);
+}
+
+int mgb_hpsi_peer(mgb_comm* comm, int lap_type, int dtype, const mgb_grid* grid,
+    const void* phi, size_t ld, const double* vtot, void* hphi, size_t ldh, int nfunc,
+    const double* xhalo_v, void* stream)
+{
+    if (int rc = require_device()) return rc;
+    if (int rc = check_grid(grid)) return rc;
+    MGB_REQUIRE(comm && phi, "mgb_hpsi_peer: null pointer");
+    MGB_REQUIRE(grid->nproc[0] > 1 && grid->nproc[1] == 1 && grid->nproc[2] == 1,
+        "mgb_hpsi_peer: the direct peer path serves x-split domains");
+    MGB_REQUIRE(grid->dim[0] * grid->nproc[0] == grid->gdim[0],
+        "mgb_hpsi_peer: x must be split evenly (neighbours' blocks have my shape)");
+    const int west = comm_rank_of(grid, grid->coord[0] - 1, grid->coord[1], grid->coord[2]);
+    const int east = comm_rank_of(grid, grid->coord[0] + 1, grid->coord[1], grid->coord[2]);
+    const void* pw = peer_view(comm, phi, west);
+    const void* pe = peer_view(comm, phi, east);
+    if (!pw || !pe)
+    {
+        set_error("mgb_hpsi_peer: phi is not registered with mgb_peer_register (or the "
+                  "neighbours' blocks cannot be mapped)");
+        return MGB_ENOTSUP;
+    }
+    cudaStream_t st = as_stream(stream);
+    // every rank's phi is complete before anybody reads boundary planes ...
+    if (int rc = comm_barrier(comm, st)) return rc;
+    const int force = g_force_path;
+    g_force_path    = 1; // only the TMA kernel reads peers
+    const int rc    = hpsi_entry(lap_type, dtype, grid, phi, ld, vtot, hphi, ldh, nfunc,
+        nullptr, xhalo_v, pw, pe, stream);
+    g_force_path = force;
+    if (rc) return rc;
+    // ... and nobody overwrites its phi while a neighbour still reads it
+    return comm_barrier(comm, st);
 }
 
 

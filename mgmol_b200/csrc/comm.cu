@@ -8,10 +8,13 @@
 // NCCL is loaded with dlopen so that the library also loads on a single-GPU
 // host that has no NCCL (under PyTorch the already-loaded libnccl.so.2 is
 // reused).
+#include <cuda.h>
 #include <dlfcn.h>
 
 #include <cstring>
+#include <map>
 #include <mutex>
+#include <vector>
 
 #include "hpsi.h"
 
@@ -24,6 +27,7 @@ typedef struct
 typedef int ncclResult_t;
 enum
 {
+    kNcclInt8    = 0,
     kNcclFloat32 = 7,
     kNcclFloat64 = 8,
     kNcclSum     = 0
@@ -38,6 +42,8 @@ struct Nccl
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int)           = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t)                                     = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t,
+        cudaStream_t)                                                           = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t,
         cudaStream_t)                                                           = nullptr;
     ncclResult_t (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t)     = nullptr;
@@ -63,6 +69,7 @@ static Nccl* nccl()
         MGB_SYM(CommInitRank, "ncclCommInitRank");
         MGB_SYM(CommDestroy, "ncclCommDestroy");
         MGB_SYM(AllReduce, "ncclAllReduce");
+        MGB_SYM(AllGather, "ncclAllGather");
         MGB_SYM(Send, "ncclSend");
         MGB_SYM(Recv, "ncclRecv");
         MGB_SYM(GroupStart, "ncclGroupStart");
@@ -90,12 +97,24 @@ static Nccl* nccl()
 
 } // namespace mgb
 
+// one array registered for direct peer reads: what every rank published
+struct PeerEntry
+{
+    std::vector<cudaIpcMemHandle_t> handle; // per rank: IPC handle of the allocation
+    std::vector<unsigned long long> offset; // per rank: offset of the array inside it
+    std::vector<void*> mapped;              // per rank: the array in MY address space
+};
+
 struct mgb_comm
 {
     ncclComm_t comm;
     int rank, nranks;
     void* buf[4];
     size_t buf_sz[4];
+    float* flag;                                  // 1-element all-reduce = rank barrier
+    std::map<const void*, PeerEntry>* peers;      // local array -> peer views
+    // opened IPC allocations, keyed by (rank, handle bytes): one mapping each
+    std::vector<std::pair<std::pair<int, cudaIpcMemHandle_t>, void*>>* opened;
 };
 
 namespace mgb
@@ -259,12 +278,133 @@ static int exchange_dir(mgb_comm* c, int dtype, const mgb_grid* gr, void* u,
     return MGB_OK;
 }
 
+// the array `local` of rank `rank` as seen from this process (nullptr if it
+// was not registered or cannot be mapped)
+const void* peer_view(mgb_comm* c, const void* local, int rank)
+{
+    if (!c || !c->peers) return nullptr;
+    auto it = c->peers->find(local);
+    if (it == c->peers->end()) return nullptr;
+    PeerEntry& e = it->second;
+    if (rank == c->rank) return local;
+    if (e.mapped[rank]) return e.mapped[rank];
+    void* base = nullptr;
+    for (auto& o : *c->opened)
+        if (o.first.first == rank
+            && memcmp(&o.first.second, &e.handle[rank], sizeof(cudaIpcMemHandle_t)) == 0)
+            base = o.second;
+    if (!base)
+    {
+        if (cudaIpcOpenMemHandle(&base, e.handle[rank], cudaIpcMemLazyEnablePeerAccess)
+            != cudaSuccess)
+        {
+            (void)cudaGetLastError();
+            return nullptr;
+        }
+        c->opened->push_back({ { rank, e.handle[rank] }, base });
+    }
+    e.mapped[rank] = (char*)base + e.offset[rank];
+    return e.mapped[rank];
+}
+
+int comm_barrier(mgb_comm* c, cudaStream_t st)
+{
+    if (!c || c->nranks == 1) return MGB_OK;
+    MGB_NCCL(nccl()->AllReduce(c->flag, c->flag, 1, kNcclFloat32, kNcclSum, c->comm, st));
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    return MGB_OK;
+}
+
+int comm_rank_of(const mgb_grid* gr, int cx, int cy, int cz) { return rank_of(gr, cx, cy, cz); }
+
 } // namespace mgb
 
 using namespace mgb;
 
 extern "C"
 {
+
+int mgb_comm_barrier(mgb_comm* c, void* stream)
+{
+    if (int rc = require_device()) return rc;
+    MGB_REQUIRE(c, "mgb_comm_barrier: null communicator");
+    return comm_barrier(c, as_stream(stream));
+}
+
+int mgb_peer_register(mgb_comm* c, const void* ptr, void* stream)
+{
+    if (int rc = require_device()) return rc;
+    MGB_REQUIRE(c && ptr, "mgb_peer_register: null pointer");
+    Nccl* N = nccl();
+    MGB_REQUIRE(N && N->AllGather, "mgb_peer_register: ncclAllGather not available");
+    cudaStream_t st = as_stream(stream);
+    struct Rec
+    {
+        cudaIpcMemHandle_t h;
+        unsigned long long off;
+        int ok, pad;
+    } mine;
+    memset(&mine, 0, sizeof(mine));
+    CUdeviceptr base = 0;
+    size_t size      = 0;
+    mine.ok = 1;
+    typedef CUresult (*PFN_range)(CUdeviceptr*, size_t*, CUdeviceptr);
+    static PFN_range get_range = nullptr;
+    if (!get_range)
+    {
+        void* fp = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &fp, cudaEnableDefault, &q)
+                == cudaSuccess
+            && q == cudaDriverEntryPointSuccess)
+            get_range = (PFN_range)fp;
+    }
+    if (!get_range || get_range(&base, &size, (CUdeviceptr)ptr) != CUDA_SUCCESS)
+        mine.ok = 0;
+    else if (cudaIpcGetMemHandle(&mine.h, (void*)base) != cudaSuccess)
+    {
+        // e.g. memory from a virtual-memory (expandable segments) allocator
+        (void)cudaGetLastError();
+        mine.ok = 0;
+    }
+    mine.off = (unsigned long long)((CUdeviceptr)ptr - base);
+    // publish (collective; every rank must call with its own array)
+    Rec* dev = (Rec*)comm_buf(c, 0, sizeof(Rec) * (c->nranks + 1));
+    if (!dev) return MGB_ECUDA;
+    MGB_CUDA(cudaMemcpyAsync(dev, &mine, sizeof(Rec), cudaMemcpyHostToDevice, st));
+    MGB_NCCL(N->AllGather(dev, dev + 1, sizeof(Rec), kNcclInt8, c->comm, st));
+    std::vector<Rec> all(c->nranks);
+    MGB_CUDA(cudaMemcpyAsync(
+        all.data(), dev + 1, sizeof(Rec) * c->nranks, cudaMemcpyDeviceToHost, st));
+    MGB_CUDA(cudaStreamSynchronize(st));
+    bool ok = true;
+    for (auto& r : all)
+        ok = ok && r.ok;
+    if (!ok)
+    {
+        set_error("mgb_peer_register: an array is not in CUDA-IPC-exportable memory "
+                  "(cudaMalloc); use the packed halo exchange instead");
+        return MGB_ENOTSUP;
+    }
+    PeerEntry e;
+    e.handle.resize(c->nranks);
+    e.offset.resize(c->nranks);
+    e.mapped.assign(c->nranks, nullptr);
+    for (int r = 0; r < c->nranks; r++)
+    {
+        e.handle[r] = all[r].h;
+        e.offset[r] = all[r].off;
+    }
+    (*c->peers)[ptr] = e;
+    return MGB_OK;
+}
+
+int mgb_peer_unregister(mgb_comm* c, const void* ptr)
+{
+    MGB_REQUIRE(c && ptr, "mgb_peer_unregister: null pointer");
+    c->peers->erase(ptr);
+    return MGB_OK;
+}
 
 int mgb_comm_unique_id(void* id128)
 {
@@ -298,11 +438,25 @@ int mgb_comm_create(mgb_comm** out, const void* id128, int rank, int nranks)
     memset(c, 0, sizeof(*c));
     c->rank   = rank;
     c->nranks = nranks;
+    c->peers  = new std::map<const void*, PeerEntry>();
+    c->opened = new std::vector<std::pair<std::pair<int, cudaIpcMemHandle_t>, void*>>();
+    if (cudaMalloc(&c->flag, sizeof(float)) != cudaSuccess
+        || cudaMemset(c->flag, 0, sizeof(float)) != cudaSuccess)
+    {
+        set_error("mgb_comm_create: device allocation failed");
+        delete c->peers;
+        delete c->opened;
+        delete c;
+        return MGB_ECUDA;
+    }
     ncclResult_t r = N->CommInitRank(&c->comm, nranks, id, rank);
     if (r != 0)
     {
         set_error("ncclCommInitRank failed: %s",
             N->GetErrorString ? N->GetErrorString(r) : "?");
+        cudaFree(c->flag);
+        delete c->peers;
+        delete c->opened;
         delete c;
         return MGB_ENCCL;
     }
@@ -316,6 +470,12 @@ int mgb_comm_destroy(mgb_comm* c)
     Nccl* N = nccl();
     for (int i = 0; i < 4; i++)
         if (c->buf[i]) cudaFree(c->buf[i]);
+    if (c->flag) cudaFree(c->flag);
+    if (c->opened)
+        for (auto& o : *c->opened)
+            cudaIpcCloseMemHandle(o.second);
+    delete c->opened;
+    delete c->peers;
     if (N && c->comm) N->CommDestroy(c->comm);
     delete c;
     return MGB_OK;

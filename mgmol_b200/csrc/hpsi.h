@@ -19,6 +19,11 @@ struct HpsiArgs
     int nfunc;
     const void* xhalo_phi;
     const double* xhalo_v;
+    // direct peer reads of the x neighbours' blocks (same layout as phi): the
+    // g planes below come from the last planes of peer_w, the g planes above
+    // from the first planes of peer_e; null = use xhalo_phi
+    const void* peer_w;
+    const void* peer_e;
 };
 
 // path 1: TMA-pipelined x-streaming kernel (hpsi_fused.cu).  Returns
@@ -43,6 +48,13 @@ int trade_wrap(int dtype, const mgb_grid* gr, void* u, int nfunc, int d, cudaStr
 // pack (ghosted -> buf) or unpack a sub-box of every function
 int subbox_copy(int dtype, bool pack, const mgb_grid* gr, const int lo[3],
     const int ext[3], void* u, void* buf, int nfunc, cudaStream_t st);
+
+// multi-GPU (comm.cu): the registered array `local` of rank `rank` mapped into
+// this process (CUDA IPC over NVLink), a stream-ordered barrier over the ranks,
+// and the rank at Cartesian coordinates
+const void* peer_view(mgb_comm* c, const void* local, int rank);
+int comm_barrier(mgb_comm* c, cudaStream_t st);
+int comm_rank_of(const mgb_grid* gr, int cx, int cy, int cz);
 
 // grow-only device scratch owned by the library (workspaces, never user data)
 void* scratch(int slot, size_t bytes);

@@ -92,6 +92,9 @@ struct alignas(64) FusedParams
     CUtensorMap v_mid, v_halo;       // vtot (z, y, x)
     CUtensorMap xpsi_mid, xpsi_halo; // x-halo buffer of phi  (z, y, 2g, orbital)
     CUtensorMap xv_mid, xv_halo;     // x-halo buffer of vtot (z, y, 2g)
+    CUtensorMap pw_mid, pw_halo;     // west neighbour's phi block (peer memory)
+    CUtensorMap pe_mid, pe_halo;     // east neighbour's phi block (peer memory)
+    int peer;                        // x-halo planes of phi come from pw / pe
     void* out;
     long long ldh;
     int nx, ny, nz, nfunc;
@@ -226,6 +229,16 @@ __global__ void __launch_bounds__(MAXT, 1)
                 const CUtensorMap* vh = (src == 1) ? &P.v_halo : &P.xv_halo;
                 const CUtensorMap* pm = (src == 1) ? &P.psi_mid : &P.xpsi_mid;
                 const CUtensorMap* ph = (src == 1) ? &P.psi_halo : &P.xpsi_halo;
+                int xcp = xc;
+                if (src == 2 && P.peer)
+                {
+                    // read the neighbour's boundary plane straight from its
+                    // block over NVLink: last planes of the west rank, first
+                    // planes of the east rank
+                    pm  = (p < 0) ? &P.pw_mid : &P.pe_mid;
+                    ph  = (p < 0) ? &P.pw_halo : &P.pe_halo;
+                    xcp = (p < 0) ? P.nx + p : p - P.nx;
+                }
                 // potential tile, shared by the NB orbitals of this CTA
                 tma_load_3d(sb + P.off_mid, vm, &full[stage], 0, y0, xc, pol_keep);
                 if (!LAP4)
@@ -236,10 +249,10 @@ __global__ void __launch_bounds__(MAXT, 1)
                 for (int o = 0; o < norb; o++)
                 {
                     unsigned char* tb = sb + (size_t)(1 + o) * P.tile_bytes;
-                    tma_load_4d(tb + P.off_mid, pm, &full[stage], 0, y0, xc,
+                    tma_load_4d(tb + P.off_mid, pm, &full[stage], 0, y0, xcp,
                         orb0 + o, pol_stream);
-                    tma_load_4d(tb, ph, &full[stage], 0, ylo, xc, orb0 + o, pol_stream);
-                    tma_load_4d(tb + P.off_hi, ph, &full[stage], 0, yhi, xc,
+                    tma_load_4d(tb, ph, &full[stage], 0, ylo, xcp, orb0 + o, pol_stream);
+                    tma_load_4d(tb + P.off_hi, ph, &full[stage], 0, yhi, xcp,
                         orb0 + o, pol_stream);
                 }
             }
@@ -826,9 +839,11 @@ int hpsi_tma(const HpsiArgs& a, cudaStream_t st)
         return MGB_ENOTSUP;
     if (nx < G || ny < 2 * G) return MGB_ENOTSUP;
     const bool split_x = gr->nproc[0] > 1;
-    if (split_x && (!a.xhalo_phi || !a.xhalo_v)) return MGB_ENOTSUP;
+    const bool peer = split_x && a.peer_w && a.peer_e;
+    if (split_x && ((!a.xhalo_phi && !peer) || !a.xhalo_v)) return MGB_ENOTSUP;
     if (split_x && (((uintptr_t)a.xhalo_phi | (uintptr_t)a.xhalo_v) & 15))
         return MGB_ENOTSUP;
+    if (peer && (((uintptr_t)a.peer_w | (uintptr_t)a.peer_e) & 15)) return MGB_ENOTSUP;
     FusedCfg c;
     if (!choose_cfg(lap4, es, nx, ny, nz, a.nfunc, c)) return MGB_ENOTSUP;
 
@@ -868,10 +883,29 @@ int hpsi_tma(const HpsiArgs& a, cudaStream_t st)
     if (split_x)
     {
         const long long hs = (long long)2 * G * ny * nz;
-        if ((rc = make_map(&P.xpsi_mid, f64, a.xhalo_phi, 4, nz, ny, 2 * G, hs, a.nfunc, TY)))
-            return rc;
-        if ((rc = make_map(&P.xpsi_halo, f64, a.xhalo_phi, 4, nz, ny, 2 * G, hs, a.nfunc, G)))
-            return rc;
+        if (peer)
+        {
+            P.peer = 1;
+            if ((rc = make_map(&P.pw_mid, f64, a.peer_w, 4, nz, ny, nx, (long long)a.ld, a.nfunc, TY)))
+                return rc;
+            if ((rc = make_map(&P.pw_halo, f64, a.peer_w, 4, nz, ny, nx, (long long)a.ld, a.nfunc, G)))
+                return rc;
+            if ((rc = make_map(&P.pe_mid, f64, a.peer_e, 4, nz, ny, nx, (long long)a.ld, a.nfunc, TY)))
+                return rc;
+            if ((rc = make_map(&P.pe_halo, f64, a.peer_e, 4, nz, ny, nx, (long long)a.ld, a.nfunc, G)))
+                return rc;
+            P.xpsi_mid  = P.psi_mid;
+            P.xpsi_halo = P.psi_halo;
+        }
+        else
+        {
+            if ((rc = make_map(
+                     &P.xpsi_mid, f64, a.xhalo_phi, 4, nz, ny, 2 * G, hs, a.nfunc, TY)))
+                return rc;
+            if ((rc = make_map(
+                     &P.xpsi_halo, f64, a.xhalo_phi, 4, nz, ny, 2 * G, hs, a.nfunc, G)))
+                return rc;
+        }
         if ((rc = make_map(&P.xv_mid, f64, xvsrc, 3, nz, ny, 2 * G, 0, 0, TY)))
             return rc;
         if ((rc = make_map(&P.xv_halo, f64, xvsrc, 3, nz, ny, 2 * G, 0, 0, G)))

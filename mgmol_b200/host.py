@@ -12,7 +12,7 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import MGB_F32, MGB_F64, MgbGrid, check, lib
+from ._lib import MGB_F32, MGB_F64, MgbError, MgbGrid, check, lib  # noqa: F401
 
 
 def _dt(t):
@@ -256,6 +256,14 @@ class Lap:
             _p(xhalo_v) if xhalo_v is not None else None, _stream()))
         return hphi
 
+
+    def applyWithPotPeer(self, comm, phi, vtot, hphi, xhalo_v):
+        """applyWithPot on an x-split domain, the neighbours' boundary planes of
+        phi read directly from their (registered) blocks over NVLink."""
+        check(lib().mgb_hpsi_peer(
+            comm.handle, self.type_, _dt(phi), self.grid_.ref(), _p(phi), self.grid_.size(),
+            _p(vtot), _p(hphi), self.grid_.size(), phi.shape[0], _p(xhalo_v), _stream()))
+        return hphi
 
     def applyWithPotHost(self, phi_host, vtot_host, hphi_host, chunk=0):
         """The same operator on HOST blocks (MGmol's MemorySpace::Host build):
@@ -564,8 +572,9 @@ class Hamiltonian:
     def lapOper(self):
         return self.lapOper_
 
-    def applyLocal(self, phi, force=False, xhalo_phi=None, xhalo_v=None):
-        """src/Hamiltonian.cc:43-83."""
+    def applyLocal(self, phi, force=False, xhalo_phi=None, xhalo_v=None, peer_comm=None):
+        """src/Hamiltonian.cc:43-83.  peer_comm: x-split domain whose orbital
+        block is registered for direct peer reads (Communicator.register)."""
         assert phi.getIterativeIndex() >= 0 and self.pot_.getIterativeIndex() >= 0
         if (self.hlphi_ is None or self.hlphi_.psi_.shape != phi.psi_.shape
                 or self.hlphi_.psi_.dtype != phi.psi_.dtype):
@@ -573,8 +582,12 @@ class Hamiltonian:
             self.itindex_ = -1
         new_index = 100 * phi.getIterativeIndex() + self.pot_.getIterativeIndex()
         if force or new_index != self.itindex_:
-            self.lapOper_.applyWithPot(phi.psi_, self.pot_.vtot(), self.hlphi_.psi_,
-                                       xhalo_phi, xhalo_v)
+            if peer_comm is not None:
+                self.lapOper_.applyWithPotPeer(peer_comm, phi.psi_, self.pot_.vtot(),
+                                               self.hlphi_.psi_, xhalo_v)
+            else:
+                self.lapOper_.applyWithPot(phi.psi_, self.pot_.vtot(), self.hlphi_.psi_,
+                                           xhalo_phi, xhalo_v)
             self.itindex_ = new_index
         return self.hlphi_
 

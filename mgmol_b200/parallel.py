@@ -32,6 +32,19 @@ class Communicator:
         check(lib().mgb_allreduce_sum_f64(self.handle, _p(t), t.numel(), _stream()))
         return t
 
+    def barrier(self):
+        """Stream-ordered barrier over the ranks."""
+        check(lib().mgb_comm_barrier(self.handle, _stream()))
+
+    def register(self, t):
+        """Collective: publish this rank's array so that the neighbours'
+        kernels can read its boundary planes in place over NVLink (CUDA IPC).
+        Raises MgbError(-2) when the memory cannot be exported."""
+        check(lib().mgb_peer_register(self.handle, _p(t), _stream()))
+
+    def unregister(self, t):
+        check(lib().mgb_peer_unregister(self.handle, _p(t)))
+
     def halo_exchange_x(self, grid, g, noghost, xhalo):
         nfunc = noghost.shape[0]
         check(lib().mgb_halo_exchange_x(self.handle, _dt(noghost), grid.ref(), g,

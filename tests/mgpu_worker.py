@@ -66,6 +66,18 @@ def main():
                 H.LapFactory.createLap(grid, lap).applyWithPot(mine, vmine, out, xh, xv)
                 check("hpsi x-split %s lap%d bc%s" % (dt, lap, bc),
                       torch.equal(out, ref[(slice(None),) + box]))
+                # ---- the same with the neighbours' planes read in place (peer
+                # mapping over NVLink): no packed exchange of phi
+                try:
+                    comm.register(mine)
+                    out2 = torch.full_like(mine, float("nan"))
+                    H.LapFactory.createLap(grid, lap).applyWithPotPeer(
+                        comm, mine, vmine, out2, xv)
+                    check("hpsi x-split peer reads %s lap%d bc%s" % (dt, lap, bc),
+                          torch.equal(out2, ref[(slice(None),) + box]))
+                    comm.unregister(mine)
+                except H.MgbError as e:
+                    check("hpsi x-split peer reads %s lap%d bc%s: %s" % (dt, lap, bc, e), False)
 
     # ---- ghosted Y -> Z -> X exchange on every 2-way / n-way split ---------------
     for dt in (torch.float64, torch.float32):
