@@ -229,6 +229,15 @@ typedef struct mgb_precond mgb_precond;
 int mgb_precond_create(mgb_precond** out, int lap_type, int mg_levels,
     const mgb_grid* grid, int nfunc_max);
 int mgb_precond_destroy(mgb_precond* p);
+/* Boxes that are one rank of a decomposition (grid->nproc): the communicator the
+ * V-cycle exchanges ghosts over -- every GridFuncVector::trade_boundaries of
+ * Preconditioning<float>::mg (MPI_Isend/Irecv in the reference, src/pb/
+ * GridFuncVector.cc:1544-1622).  x-split boxes run the fused kernels, reading
+ * the neighbours' boundary planes in place over NVLink; other decompositions
+ * run the literal sequence with the packed Y -> Z -> X exchange.  Calls are
+ * then collective over the communicator.                                     */
+typedef struct mgb_comm mgb_comm;
+int mgb_precond_set_comm(mgb_precond* p, mgb_comm* comm);
 /* OrbitalsPreconditioning::setup with currentMasks != nullptr (src/
  * OrbitalsPreconditioning.cc:59-67 -> GridFuncVector::setMasks): every
  * app_mask of Preconditioning<float>::mg (src/Preconditioning.cc:176,184,192,
@@ -291,7 +300,6 @@ int mgb_gemm_nn(int dtype, size_t m, int n, int k, double alpha, const void* A,
  * The communicator wraps NCCL; the unique id (128 bytes) is created on rank 0
  * with mgb_comm_unique_id and distributed by the caller (MPI_Bcast in MGmol,
  * torch.distributed in the tests).                                          */
-typedef struct mgb_comm mgb_comm;
 int mgb_comm_unique_id(void* id128);
 int mgb_comm_create(mgb_comm** out, const void* id128, int rank, int nranks);
 int mgb_comm_destroy(mgb_comm* c);

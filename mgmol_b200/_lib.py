@@ -80,6 +80,7 @@ _SIGS = {
     "mgb_precond_mg": (c_int, [c_void_p, c_int, c_void_p, c_size_t, c_int, c_double,
                                c_void_p]),
     "mgb_precond_set_masks": (c_int, [c_void_p, c_void_p]),
+    "mgb_precond_set_comm": (c_int, [c_void_p, c_void_p]),
     "mgb_masks_create": (c_int, [ctypes.POINTER(c_void_p), ctypes.POINTER(MgbGrid),
                                  c_int, c_int, c_int, c_int]),
     "mgb_masks_set": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),

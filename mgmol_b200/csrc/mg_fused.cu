@@ -57,6 +57,9 @@ enum
 struct alignas(64) JacobiParams
 {
     CUtensorMap in_mid, in_halo; // source block (z, y, x, function), float
+    CUtensorMap pw_mid, pw_halo; // west / east neighbour's source block (peer
+    CUtensorMap pe_mid, pe_halo; // memory over NVLink) on an x-split domain
+    int split_x, have_w, have_e;
     const float* f;              // right-hand side
     float* vout;                 // float output (or null)
     double* vout64;              // double output (exit of precond_mg, or null)
@@ -162,7 +165,25 @@ __global__ void __launch_bounds__(MAXT, 1) k_mg_jacobi(const __grid_constant__ J
         for (int it = 0; it < nplanes; it++)
         {
             int xc = xb - G + it;
-            if (P.per[0])
+            const CUtensorMap* mm = &P.in_mid;
+            const CUtensorMap* mh = &P.in_halo;
+            if (P.split_x)
+            {
+                // planes outside my box: the neighbour's block, read in place
+                if (xc < 0 && P.have_w)
+                {
+                    mm = &P.pw_mid;
+                    mh = &P.pw_halo;
+                    xc += P.nx;
+                }
+                else if (xc >= P.nx && P.have_e)
+                {
+                    mm = &P.pe_mid;
+                    mh = &P.pe_halo;
+                    xc -= P.nx;
+                }
+            }
+            else if (P.per[0])
             {
                 xc %= P.nx;
                 if (xc < 0) xc += P.nx;
@@ -175,9 +196,9 @@ __global__ void __launch_bounds__(MAXT, 1) k_mg_jacobi(const __grid_constant__ J
             for (int o = 0; o < norb; o++)
             {
                 unsigned char* tb = sb + (size_t)o * P.tile_bytes;
-                tma_load_4d(tb + P.off_mid, &P.in_mid, &full[stage], 0, y0, xc, orb0 + o, pol);
-                tma_load_4d(tb, &P.in_halo, &full[stage], 0, ylo, xc, orb0 + o, pol);
-                tma_load_4d(tb + P.off_hi, &P.in_halo, &full[stage], 0, yhi, xc, orb0 + o, pol);
+                tma_load_4d(tb + P.off_mid, mm, &full[stage], 0, y0, xc, orb0 + o, pol);
+                tma_load_4d(tb, mh, &full[stage], 0, ylo, xc, orb0 + o, pol);
+                tma_load_4d(tb + P.off_hi, mh, &full[stage], 0, yhi, xc, orb0 + o, pol);
             }
             if (++stage == S)
             {
@@ -577,7 +598,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_mg_jacobi(const __grid_constant__ J
 // ---------------------------------------------------------------------------
 __global__ void k_mg_restrict(int nxc, int nyc, int nzc, int perx, int pery, int perz,
     const float* __restrict__ fine, long long ldf, float* __restrict__ coarse,
-    long long ldc, MaskView mask)
+    long long ldc, MaskView mask, const float* __restrict__ fine_w)
 {
     // block (zx, zy): zx threads along the coarse k-vectors, zy coarse rows;
     // grid.x tiles (k-vector, row), grid.y = coarse plane, grid.z = function
@@ -597,9 +618,17 @@ __global__ void k_mg_restrict(int nxc, int nyc, int nzc, int perx, int pery, int
     {
         int x = 2 * i + dx;
         float wx = (dx == 0) ? 2.f : 1.f;
+        const float* Fx = F;
         if (x < 0)
         {
-            if (perx)
+            // fine plane -1: my own last plane (periodic, x not split), the
+            // west neighbour's last plane (x split), or nothing (Dirichlet)
+            if (fine_w)
+            {
+                Fx = fine_w + (long long)f * ldf;
+                x += nx;
+            }
+            else if (perx)
                 x += nx;
             else
                 wx = 0.f;
@@ -617,7 +646,7 @@ __global__ void k_mg_restrict(int nxc, int nyc, int nzc, int perx, int pery, int
                 else
                     wy = 0.f;
             }
-            const float* row = F + ((long long)(x < 0 ? 0 : x) * ny + (y < 0 ? 0 : y)) * nz;
+            const float* row = Fx + ((long long)(x < 0 ? 0 : x) * ny + (y < 0 ? 0 : y)) * nz;
             const float4 a = __ldg(reinterpret_cast<const float4*>(row + 2 * k0));
             const float4 b = __ldg(reinterpret_cast<const float4*>(row + 2 * k0 + 4));
             float lft;
@@ -672,7 +701,7 @@ __global__ void k_mg_restrict(int nxc, int nyc, int nzc, int perx, int pery, int
 // ---------------------------------------------------------------------------
 __global__ void k_mg_prolong_correct(int nx, int ny, int nz, int perx, int pery, int perz,
     int zlx, int zly, int zlz, const float* __restrict__ coarse, long long ldc,
-    float* __restrict__ v, long long ldv, MaskView mask)
+    float* __restrict__ v, long long ldv, MaskView mask, const float* __restrict__ coarse_e)
 {
     const int nzv = nz >> 2;
     const int tz  = (nzv + blockDim.x - 1) / blockDim.x;
@@ -687,10 +716,17 @@ __global__ void k_mg_prolong_correct(int nx, int ny, int nz, int perx, int pery,
     const int cx0 = x >> 1, cy0 = y >> 1, cz0 = z0 >> 1;
     int cx1 = cx0 + 1, cy1 = cy0 + 1, cz2 = cz0 + 2;
     float mx = 1.f, my = 1.f, mz = 1.f;
+    const float* C = coarse + (long long)f * ldc;
+    const float* Cx1 = C; // block holding coarse plane cx1
     if (cx1 == nxc)
     {
+        // coarse plane nxc: my own plane 0 (periodic, x not split), the east
+        // neighbour's plane 0 (x split), or nothing (Dirichlet)
         cx1 = 0;
-        if (!perx) mx = 0.f;
+        if (coarse_e)
+            Cx1 = coarse_e + (long long)f * ldc;
+        else if (!perx)
+            mx = 0.f;
     }
     if (cy1 == nyc)
     {
@@ -702,20 +738,19 @@ __global__ void k_mg_prolong_correct(int nx, int ny, int nz, int perx, int pery,
         cz2 = 0;
         if (!perz) mz = 0.f;
     }
-    const float* C = coarse + (long long)f * ldc;
     // coarse rows (x0,y0), (x0,y1), (x1,y0), (x1,y1): values at cz0, cz0+1, cz0+2
     float c00[3], c01[3], c10[3], c11[3];
-    auto row3 = [&](int cx, int cy, float m, float(&o)[3]) {
-        const float* r = C + ((long long)cx * nyc + cy) * nzc;
+    auto row3 = [&](const float* Cb, int cx, int cy, float m, float(&o)[3]) {
+        const float* r = Cb + ((long long)cx * nyc + cy) * nzc;
         const float2 a = __ldg(reinterpret_cast<const float2*>(r + cz0));
         o[0] = a.x * m;
         o[1] = a.y * m;
         o[2] = __ldg(r + cz2) * (m * mz);
     };
-    row3(cx0, cy0, 1.f, c00);
-    if (oy) row3(cx0, cy1, my, c01);
-    if (ox) row3(cx1, cy0, mx, c10);
-    if (ox && oy) row3(cx1, cy1, mx * my, c11);
+    row3(C, cx0, cy0, 1.f, c00);
+    if (oy) row3(C, cx0, cy1, my, c01);
+    if (ox) row3(Cx1, cx1, cy0, mx, c10);
+    if (ox && oy) row3(Cx1, cx1, cy1, mx * my, c11);
     float w[4];
 #pragma unroll
     for (int e = 0; e < 4; e++)
@@ -998,6 +1033,31 @@ int mg_jacobi(const MgJacobiArgs& a, cudaStream_t st)
         return rc;
     if ((rc = make_map(&P.in_halo, false, a.in, 4, nz, ny, nx, (long long)a.ld_in, a.nfunc, G)))
         return rc;
+    P.split_x = gr.nproc[0] > 1;
+    if (P.split_x)
+    {
+        const bool per = gr.bc[0] == 1;
+        P.have_w = (per || gr.coord[0] > 0) && a.peer_w;
+        P.have_e = (per || gr.coord[0] < gr.nproc[0] - 1) && a.peer_e;
+        if (P.have_w)
+        {
+            if ((rc = make_map(&P.pw_mid, false, a.peer_w, 4, nz, ny, nx, (long long)a.ld_in,
+                     a.nfunc, P.TY)))
+                return rc;
+            if ((rc = make_map(
+                     &P.pw_halo, false, a.peer_w, 4, nz, ny, nx, (long long)a.ld_in, a.nfunc, G)))
+                return rc;
+        }
+        if (P.have_e)
+        {
+            if ((rc = make_map(&P.pe_mid, false, a.peer_e, 4, nz, ny, nx, (long long)a.ld_in,
+                     a.nfunc, P.TY)))
+                return rc;
+            if ((rc = make_map(
+                     &P.pe_halo, false, a.peer_e, 4, nz, ny, nx, (long long)a.ld_in, a.nfunc, G)))
+                return rc;
+        }
+    }
     P.f      = a.f;
     P.vout   = a.out;
     P.vout64 = a.out64;
@@ -1085,7 +1145,7 @@ static MaskView mask_from(const MaskView& m, int f0)
 }
 
 int mg_restrict(const mgb_grid& fine, const float* w, size_t ldf, float* coarse, size_t ldc,
-    int nfunc, const MaskView& mask, cudaStream_t st)
+    int nfunc, const MaskView& mask, const float* w_west, cudaStream_t st)
 {
     const int nxc = fine.dim[0] / 2, nyc = fine.dim[1] / 2, nzc = fine.dim[2] / 2;
     for (int f0 = 0; f0 < nfunc; f0 += 65535)
@@ -1094,14 +1154,16 @@ int mg_restrict(const mgb_grid& fine, const float* w, size_t ldf, float* coarse,
         const VecLaunch L = vec_launch(nxc, nyc, nzc / 4, nf);
         k_mg_restrict<<<L.grid, L.block, 0, st>>>(nxc, nyc, nzc, fine.bc[0] == 1, fine.bc[1] == 1,
             fine.bc[2] == 1, w + (size_t)f0 * ldf, (long long)ldf,
-            coarse + (size_t)f0 * ldc, (long long)ldc, mask_from(mask, f0));
+            coarse + (size_t)f0 * ldc, (long long)ldc, mask_from(mask, f0),
+            w_west ? w_west + (size_t)f0 * ldf : nullptr);
         MGB_LAUNCHED("k_mg_restrict");
     }
     return MGB_OK;
 }
 
 int mg_prolong_correct(const mgb_grid& fine, const float* coarse, size_t ldc, float* v,
-    size_t ldv, int nfunc, const int zero_low[3], const MaskView& mask, cudaStream_t st)
+    size_t ldv, int nfunc, const int zero_low[3], const MaskView& mask, const float* coarse_east,
+    cudaStream_t st)
 {
     const int nx = fine.dim[0], ny = fine.dim[1], nz = fine.dim[2];
     for (int f0 = 0; f0 < nfunc; f0 += 65535)
@@ -1111,7 +1173,7 @@ int mg_prolong_correct(const mgb_grid& fine, const float* coarse, size_t ldc, fl
         k_mg_prolong_correct<<<L.grid, L.block, 0, st>>>(nx, ny, nz, fine.bc[0] == 1,
             fine.bc[1] == 1, fine.bc[2] == 1, zero_low[0], zero_low[1], zero_low[2],
             coarse + (size_t)f0 * ldc, (long long)ldc, v + (size_t)f0 * ldv, (long long)ldv,
-            mask_from(mask, f0));
+            mask_from(mask, f0), coarse_east ? coarse_east + (size_t)f0 * ldc : nullptr);
         MGB_LAUNCHED("k_mg_prolong_correct");
     }
     return MGB_OK;

@@ -38,6 +38,8 @@ struct mgb_precond
     std::vector<float*> fw;      // residual of the last pre-smoothing sweep
     std::vector<float*> ff;      // right-hand side (level 0: converted residual)
     const mgb_masks* masks;      // GridFuncVector::map2masks_ (null: none)
+    mgb_comm* comm;              // multi-rank boxes: halo exchange / peer reads
+    bool peers_ready;            // the fused work blocks are registered
 };
 
 namespace mgb
@@ -87,6 +89,20 @@ static int lap_constants(int lap_type, const double h[3], double out[3])
     return MGB_OK;
 }
 
+static bool multi_rank(const mgb_grid& g)
+{
+    return g.nproc[0] * g.nproc[1] * g.nproc[2] > 1;
+}
+
+// GridFuncVector::trade_boundaries: local wraps on one rank, the Y -> Z -> X
+// exchange over the communicator otherwise
+static int trade(mgb_precond* p, const mgb_grid& gr, float* u, int nfunc, cudaStream_t st)
+{
+    if (multi_rank(gr))
+        return mgb_halo_exchange_ghosted(p->comm, MGB_F32, &gr, u, nfunc, (void*)st);
+    return mgb_gfv_trade_boundaries(MGB_F32, &gr, u, nfunc, (void*)st);
+}
+
 // GridFuncVector::jacobi with the updated_boundaries_ bookkeeping of the
 // reference: applyLap trades v's boundaries unless they are flagged current.
 static int jacobi(mgb_precond* p, int lap_type, int level, float* v, bool& v_upd,
@@ -94,8 +110,7 @@ static int jacobi(mgb_precond* p, int lap_type, int level, float* v, bool& v_upd
 {
     const mgb_grid& gr = p->grid[level];
     if (!v_upd)
-        if (int rc = mgb_gfv_trade_boundaries(MGB_F32, &gr, v, nfunc, (void*)st))
-            return rc;
+        if (int rc = trade(p, gr, v, nfunc, st)) return rc;
     if (int rc = jacobi_literal(lap_type, &gr, v, f, p->work[level], nfunc,
             p->jf[level], st))
         return rc;
@@ -119,7 +134,7 @@ static int vcycle(mgb_precond* p, float* v, bool& v_upd, const float* f,
     if (int rc = mgb_gfv_app_mask(MGB_F32, p->masks, level, gr.ghosts, w, nfunc, (void*)st))
         return rc;
     // :189 restrict3D trades w first (GridFuncVector.cc:1624-1631)
-    if (int rc = mgb_gfv_trade_boundaries(MGB_F32, &gr, w, nfunc, (void*)st)) return rc;
+    if (int rc = trade(p, gr, w, nfunc, st)) return rc;
     float* rc_ = p->rcoarse[level];
     if (int rc = mgb_gfv_restrict3D(MGB_F32, &gr, w, rc_, nfunc, (void*)st)) return rc;
     // :192
@@ -136,8 +151,7 @@ static int vcycle(mgb_precond* p, float* v, bool& v_upd, const float* f,
 
     // :201 extend3D trades the coarse block first (GridFuncVector.cc:1633-1641)
     if (!nv_upd)
-        if (int rc = mgb_gfv_trade_boundaries(MGB_F32, &cgr, nv, nfunc, (void*)st))
-            return rc;
+        if (int rc = trade(p, cgr, nv, nfunc, st)) return rc;
     if (int rc = mgb_gfv_extend3D(MGB_F32, &gr, nv, w, nfunc, (void*)st)) return rc;
     // :204
     if (int rc = mgb_gfv_app_mask(MGB_F32, p->masks, level, gr.ghosts, w, nfunc, (void*)st))
@@ -155,8 +169,7 @@ static int vcycle(mgb_precond* p, float* v, bool& v_upd, const float* f,
     if (gr.bc[0] != 1 || gr.bc[2] != 1 || gr.bc[2] != 1)
     {
         if (!v_upd)
-            if (int rc = mgb_gfv_trade_boundaries(MGB_F32, &gr, v, nfunc, (void*)st))
-                return rc;
+            if (int rc = trade(p, gr, v, nfunc, st)) return rc;
         v_upd = true;
     }
     return MGB_OK;
@@ -210,9 +223,6 @@ int mgb_precond_create(mgb_precond** out, int lap_type, int mg_levels,
         MGB_REQUIRE(grid->dim[d] % (1 << mg_levels) == 0,
             "mgb_precond_create: dim[%d]=%d not divisible by 2^%d", d,
             grid->dim[d], mg_levels);
-    MGB_REQUIRE(grid->nproc[0] == 1 && grid->nproc[1] == 1 && grid->nproc[2] == 1,
-        "mgb_precond_create: multi-rank V-cycle is driven through "
-        "mgb_halo_exchange_ghosted by the host wrapper");
 
     mgb_precond* p = new mgb_precond();
     p->lap_type    = lap_type;
@@ -223,6 +233,8 @@ int mgb_precond_create(mgb_precond** out, int lap_type, int mg_levels,
     p->literal_ready = p->fused_ready = false;
     p->mode = p->last_mode = 0;
     p->masks = nullptr;
+    p->comm  = nullptr;
+    p->peers_ready = false;
     if (const char* env = getenv("MGB_MG_MODE")) p->mode = atoi(env);
     mgb_grid g = *grid;
     int rc     = MGB_OK;
@@ -231,6 +243,11 @@ int mgb_precond_create(mgb_precond** out, int lap_type, int mg_levels,
     // twice" (src/pb/GridFunc.cc:2222-2236), so its result depends on stale
     // ghost values that only the ghosted layout reproduces.
     p->fused_ok = (grid->bc[0] == grid->bc[1] && grid->bc[1] == grid->bc[2]);
+    // the fused kernels read x neighbours in place; y / z splits go through
+    // the ghosted exchange of the literal sequence
+    if (grid->nproc[1] != 1 || grid->nproc[2] != 1) p->fused_ok = false;
+    if (grid->nproc[0] > 1 && grid->dim[0] * grid->nproc[0] != grid->gdim[0])
+        p->fused_ok = false;
     for (int l = 0; l <= mg_levels && rc == MGB_OK; l++)
     {
         if (l > 0)
@@ -324,11 +341,55 @@ static int ensure_fused(mgb_precond* p)
             if (int rc = dev_alloc(&w, bytes)) return rc;
         p->fw.push_back(w);
         p->ff.push_back(f); // level 0: allocated on the first double-precision call
-        if (l > 0)
+        // (x-split domains: always, so that it is registered with the others)
+        if (l > 0 || p->grid[0].nproc[0] > 1)
             if (int rc = dev_alloc(&p->ff[l], bytes)) return rc;
     }
     p->fused_ready = true;
     return MGB_OK;
+}
+
+// x-split domains: publish every fused work block so that the neighbours'
+// kernels can read boundary planes in place (collective, once per handle)
+static int ensure_peers(mgb_precond* p, cudaStream_t st)
+{
+    if (p->peers_ready || p->grid[0].nproc[0] == 1) return MGB_OK;
+    for (int l = 0; l <= p->max_levels; l++)
+        for (float* q : { p->fa[l], p->fb[l], p->fw[l], p->ff[l] })
+            if (q)
+                if (int rc = mgb_peer_register(p->comm, q, (void*)st)) return rc;
+    p->peers_ready = true;
+    return MGB_OK;
+}
+
+struct XPeers
+{
+    const float* w;
+    const float* e;
+};
+// the west / east neighbours' copies of a registered work block (null where
+// the domain ends, or on a single rank)
+static int x_peers(mgb_precond* p, const mgb_grid& gr, const float* q, XPeers& out)
+{
+    out.w = out.e = nullptr;
+    if (gr.nproc[0] == 1) return MGB_OK;
+    const bool per = gr.bc[0] == 1;
+    if (per || gr.coord[0] > 0)
+    {
+        out.w = (const float*)peer_view(
+            p->comm, q, comm_rank_of(&gr, gr.coord[0] - 1, gr.coord[1], gr.coord[2]));
+        if (!out.w) goto fail;
+    }
+    if (per || gr.coord[0] < gr.nproc[0] - 1)
+    {
+        out.e = (const float*)peer_view(
+            p->comm, q, comm_rank_of(&gr, gr.coord[0] + 1, gr.coord[1], gr.coord[2]));
+        if (!out.e) goto fail;
+    }
+    return MGB_OK;
+fail:
+    set_error("mgb_precond: a neighbour's work block cannot be mapped (CUDA IPC)");
+    return MGB_ENOTSUP;
 }
 
 // One level of Preconditioning<float>::mg (src/Preconditioning.cc:155-216) on
@@ -348,7 +409,8 @@ static int cycle_fused(mgb_precond* p, int l, const float* f, size_t ldf, double
     const bool periodic = gr.bc[0] == 1 && gr.bc[1] == 1 && gr.bc[2] == 1;
     int zl[3], nozero[3] = { 0, 0, 0 };
     for (int d = 0; d < 3; d++)
-        zl[d] = gr.bc[d] != 1;
+        zl[d] = gr.bc[d] != 1 && gr.coord[d] == 0; // the rank owning the low face
+    const bool split = gr.nproc[0] > 1;
     // the last sweep of level 0 is followed by a trade only on the path through
     // Preconditioning.cc:215, whose test reads bc_[0], bc_[2], bc_[2]
     const bool final_trade = !coarsest && (gr.bc[0] != 1 || gr.bc[2] != 1);
@@ -363,7 +425,7 @@ static int cycle_fused(mgb_precond* p, int l, const float* f, size_t ldf, double
     // unless low layers must be stored as zeros (Dirichlet) or, on a coarse
     // level, the start vector omega * f is itself masked (it is the result of
     // the reference's first sweep, followed by app_mask): then it is stored.
-    if (!periodic || (l > 0 && mk.off))
+    if (!periodic || (l > 0 && mk.off) || (split && l == 0 && f != p->ff[0]))
     {
         if (int rc = mg_scale(gr, s, f, ldf, p->fa[l], ld, nfunc, zl, l > 0 ? mk : no_mask(), st))
             return rc;
@@ -391,6 +453,13 @@ static int cycle_fused(mgb_precond* p, int l, const float* f, size_t ldf, double
         for (int d = 0; d < 3; d++)
             a.zero_low[d] = z[d];
         a.mask = mk;
+        XPeers xp;
+        if (int rc = x_peers(p, gr, a.in, xp)) return rc;
+        a.peer_w = xp.w;
+        a.peer_e = xp.e;
+        // every rank has finished writing (and reading) the blocks involved
+        if (split)
+            if (int rc = comm_barrier(p->comm, st)) return rc;
         if (int rc = mg_jacobi(a, st)) return rc;
         cur           = final_out ? nullptr : nxt;
         pending_scale = false;
@@ -407,9 +476,15 @@ static int cycle_fused(mgb_precond* p, int l, const float* f, size_t ldf, double
         return MGB_OK;
     }
     // :189-192 restriction of the residual of the last pre-smoothing sweep
-    if (int rc = mg_restrict(
-            gr, p->fw[l], ld, p->ff[l + 1], npt_of(p->grid[l + 1]), nfunc, mkc, st))
-        return rc;
+    {
+        XPeers xp;
+        if (int rc = x_peers(p, gr, p->fw[l], xp)) return rc;
+        if (split)
+            if (int rc = comm_barrier(p->comm, st)) return rc;
+        if (int rc = mg_restrict(
+                gr, p->fw[l], ld, p->ff[l + 1], npt_of(p->grid[l + 1]), nfunc, mkc, xp.w, st))
+            return rc;
+    }
     // :198-199 coarse correction from a zero start: its first sweep gives
     // omega * f, folded into the start vector
     const int ncycl_c = (l + 1 == p->max_levels) ? 4 : 2;
@@ -418,8 +493,15 @@ static int cycle_fused(mgb_precond* p, int l, const float* f, size_t ldf, double
             ncycl_c - 1, nullptr, nullptr, 0, nfunc, &e, st))
         return rc;
     // :201-206 v -= P e
-    if (int rc = mg_prolong_correct(gr, e, npt_of(p->grid[l + 1]), cur, ld, nfunc, zl, mk, st))
-        return rc;
+    {
+        XPeers xp;
+        if (int rc = x_peers(p, p->grid[l + 1], e, xp)) return rc;
+        if (split)
+            if (int rc = comm_barrier(p->comm, st)) return rc;
+        if (int rc = mg_prolong_correct(
+                gr, e, npt_of(p->grid[l + 1]), cur, ld, nfunc, zl, mk, xp.e, st))
+            return rc;
+    }
     for (int it = 0; it < 2; it++) // :209-213
         if (int rc = sweep(false, it == 1 && l == 0)) return rc;
     *result = cur;
@@ -466,6 +548,13 @@ int mgb_precond_set_masks(mgb_precond* p, const mgb_masks* m)
     return MGB_OK;
 }
 
+int mgb_precond_set_comm(mgb_precond* p, mgb_comm* comm)
+{
+    MGB_REQUIRE(p, "mgb_precond_set_comm: null handle");
+    p->comm = comm;
+    return MGB_OK;
+}
+
 int mgb_precond_set_mode(mgb_precond* p, int mode)
 {
     MGB_REQUIRE(p, "mgb_precond_set_mode: null handle");
@@ -504,13 +593,31 @@ int mgb_precond_mg(mgb_precond* p, int dtype, void* res, size_t ld, int nfunc,
     cudaStream_t st    = as_stream(stream);
     int rc;
     const size_t es = dtype == MGB_F64 ? 8 : 4;
-    const bool can_fuse = p->fused_ok && ld % 4 == 0 && ((uintptr_t)res & 15) == 0
-                          && ld * es % 16 == 0;
+    MGB_REQUIRE(!multi_rank(gr) || p->comm,
+        "mgb_precond_mg: the box is one of %d x %d x %d ranks but no communicator was "
+        "attached (mgb_precond_set_comm)",
+        gr.nproc[0], gr.nproc[1], gr.nproc[2]);
+    bool can_fuse = p->fused_ok && ld % 4 == 0 && ((uintptr_t)res & 15) == 0
+                    && ld * es % 16 == 0;
+    if (can_fuse && gr.nproc[0] > 1)
+    {
+        // x-split: the neighbours' work blocks must be mappable (CUDA IPC);
+        // otherwise the literal sequence with the packed exchange serves
+        if ((rc = ensure_fused(p))) return rc;
+        rc = ensure_peers(p, st);
+        if (rc == MGB_ENOTSUP)
+            can_fuse = false;
+        else if (rc)
+            return rc;
+    }
     MGB_REQUIRE(p->mode != 2 || can_fuse,
         "mgb_precond_mg: fused mode forced but this grid/block is not eligible");
     if (p->mode == 2 || (p->mode == 0 && can_fuse))
     {
         if ((rc = ensure_fused(p))) return rc;
+        // nobody is still reading my work blocks from the previous call
+        if (gr.nproc[0] > 1)
+            if ((rc = comm_barrier(p->comm, st))) return rc;
         const float* f = (const float*)res;
         size_t ldf     = ld;
         if (dtype == MGB_F64)

@@ -624,6 +624,11 @@ class OrbitalsPreconditioning:
         self.grid_ = grid
         self.is_set_ = True
 
+    def set_comm(self, comm):
+        """Multi-rank boxes: the communicator the V-cycle exchanges ghosts over."""
+        check(lib().mgb_precond_set_comm(self.handle_, comm.handle if comm else None))
+        self.comm_ = comm
+
     def set_mode(self, mode):
         """0 automatic, 1 literal (bit-identical to the reference), 2 fused."""
         check(lib().mgb_precond_set_mode(self.handle_, int(mode)))
