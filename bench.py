@@ -141,6 +141,71 @@ def cpu_hpsi_rate(lap_type, dims, ll, dt, budget_s=12.0):
     return updates / t, P, kind, sample
 
 
+def _cpu_iter_worker(args):
+    """One rank of the CPU reference doing the in-scope work of one orbital-update
+    iteration on its sub-box: H psi, Phi^T (H Phi), multigrid-preconditioned
+    residual, Gram, Phi M (the reference's own kernels / mputils + BLAS)."""
+    kind, lap_type, dims, ll, nfunc, dt = args
+    os.environ["OMP_NUM_THREADS"] = "1"
+    os.environ["OPENBLAS_NUM_THREADS"] = "1"
+    from oracle.oracle import Port, Ref, synthetic_potential
+    impl = Ref() if kind == "reference" else Port()
+    rng = np.random.default_rng(11)
+    phi = rng.standard_normal((nfunc,) + tuple(dims)).astype(dt)
+    v = synthetic_potential(dims)
+    M = rng.standard_normal((nfunc, nfunc)) / np.sqrt(nfunc)
+    t = {}
+    t0 = time.perf_counter()
+    hphi = impl.hpsi(lap_type, phi, v, ll)
+    t["hpsi"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    impl.gemm_tn(phi, hphi, 1.0)
+    t["phiT_H_phi"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    impl.precond_mg(lap_type, 2, hphi, ll, 0.3)
+    t["precond_mg"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    (impl.syrk if hasattr(impl, "syrk") else (lambda a, al: impl.gemm_tn(a, a, al)))(phi, 1.0)
+    t["gram"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    impl.gemm_nn(phi, M)
+    t["phi_M"] = time.perf_counter() - t0
+    return t
+
+
+def cpu_iteration(lap_type, dims, ll, dt, norb):
+    """Seconds the CPU reference needs for the same pieces on the same box with
+    all host cores: P single-thread ranks, each on a 1/P x-slab with all
+    orbitals (no communication counted -- favourable to the CPU)."""
+    import multiprocessing as mp
+    from oracle.oracle import Ref
+    kind = "reference" if Ref.available() else "port"
+    cores = os.cpu_count() or 1
+    P = 1
+    # x slabs of >= 8 planes, divisible by 4 (two multigrid levels)
+    while (P * 2 <= cores and dims[0] % (P * 2) == 0 and (dims[0] // (P * 2)) % 4 == 0
+           and dims[0] // (P * 2) >= 8):
+        P *= 2
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+        per = 12.0 * np.prod(dims) / P * norb * np.dtype(dt).itemsize
+        while P > 1 and per * P > 0.5 * avail:
+            P //= 2
+    except Exception:
+        pass
+    sub = (dims[0] // P, dims[1], dims[2])
+    subll = (ll[0] / P, ll[1], ll[2])
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(P) as pool:
+        res = pool.map(_cpu_iter_worker, [(kind, lap_type, sub, subll, norb, dt)] * P)
+    pieces = {k: max(r[k] for r in res) for k in res[0]}
+    return {"seconds": sum(pieces.values()), "pieces_s": pieces, "cores": P, "kind": kind,
+            "sample": "%s kernels, %dx%dx%d box as %d single-thread ranks (x slabs), all %d "
+                      "orbitals, one pass, no communication counted"
+                      % (kind, dims[0], dims[1], dims[2], P, norb)}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -191,7 +256,7 @@ def _time_cuda(torch, fn, reps=5, warm=2):
     return float(np.median(ts))
 
 
-def measure_pieces(H, grid, phi, ham, lap_type, tdt, S, norb, npt):
+def measure_pieces(H, grid, phi, ham, lap_type, tdt, S, norb, npt, comm=None, hstep=None):
     """The other three pieces of the path on the same orbital block (outside the
     timed region of the headline metric): multigrid-preconditioned residual,
     Gram, projected Hamiltonian, orbital mixing; each with the roofline that
@@ -210,12 +275,14 @@ def measure_pieces(H, grid, phi, ham, lap_type, tdt, S, norb, npt):
     out["fp64_tensor_peak_tflops"] = {"value": fp64_peak,
                                       "how": "cuBLAS DGEMM 4096^3 via torch.matmul, measured in this run"}
     upd = float(npt) * norb
-    hphi = ham.applyLocal(phi)
+    hphi = hstep() if hstep else ham.applyLocal(phi)
     # multigrid-preconditioned residual (OrbitalsPreconditioning::precond_mg)
     res = H.Orbitals(grid, norb, tdt)
     res.psi().copy_(hphi.psi())
     pc = H.OrbitalsPreconditioning()
     pc.setup(res, 2, lap_type)
+    if comm is not None:
+        pc.set_comm(comm)
     pc.gamma_ = 0.3
     ms = _time_cuda(torch, lambda: pc.precond_mg(res))
     model = (74.0 + 2 * S) * upd  # streaming model of the V-cycle
@@ -225,15 +292,13 @@ def measure_pieces(H, grid, phi, ham, lap_type, tdt, S, norb, npt):
                                       "peak": hbm, "unit": "GB/s",
                                       "frac": model / (ms * 1e-3) / 1e9 / hbm,
                                       "model_bytes_per_update": 74.0 + 2 * S}}
-    pc.close()
-    del res
     fl = float(norb) * norb * npt
-    ms = _time_cuda(torch, lambda: phi.computeGram())
+    ms = _time_cuda(torch, lambda: phi.computeGram(comm))
     out["gram"] = {"ms": ms, "roofline": {"bound": "tensor", "achieved": fl / (ms * 1e-3) / 1e12,
                                           "peak": fp64_peak, "unit": "TFLOP/s",
                                           "frac": fl / (ms * 1e-3) / 1e12 / fp64_peak,
                                           "flops": "N^2 K (syrk)"}}
-    ms = _time_cuda(torch, lambda: phi.computeLocalProduct(hphi))
+    ms = _time_cuda(torch, lambda: phi.computeLocalProduct(hphi, comm))
     out["phiT_H_phi"] = {"ms": ms, "roofline": {"bound": "tensor", "achieved": 2 * fl / (ms * 1e-3) / 1e12,
                                                 "peak": fp64_peak, "unit": "TFLOP/s",
                                                 "frac": 2 * fl / (ms * 1e-3) / 1e12 / fp64_peak,
@@ -245,6 +310,22 @@ def measure_pieces(H, grid, phi, ham, lap_type, tdt, S, norb, npt):
                                            "peak": fp64_peak, "unit": "TFLOP/s",
                                            "frac": 2 * fl / (ms * 1e-3) / 1e12 / fp64_peak,
                                            "flops": "2 N^2 K"}}
+
+    # one orbital-update iteration's worth of the in-scope path, back to back on
+    # one stream the way an SCF step orders it: H psi (with the
+    # halo), Phi^T H Phi (+ all-reduce), preconditioned residual, Gram
+    # (+ all-reduce), Phi M
+    def iteration():
+        h = hstep() if hstep else ham.applyLocal(phi, True)
+        phi.computeLocalProduct(h, comm)
+        pc.precond_mg(res)
+        phi.computeGram(comm)
+        phi.multiplyByMatrix(M, prod)
+    ms = _time_cuda(torch, iteration, reps=3, warm=1)
+    out["orbital_update_iteration"] = {
+        "ms": ms, "sequence": "H psi, Phi^T H Phi, precond_mg (2 levels), Gram, Phi M"}
+    pc.close()
+    del res
     return out
 
 
@@ -401,8 +482,16 @@ def run_ours(args):
     ms, e2e_ms, kern_ms = (float(v) for v in t.cpu())
 
     pieces = None
-    if world == 1 and not args.no_pieces:
-        pieces = measure_pieces(H, grid, phi, ham, lap_type, tdt, S, norb, npt)
+    if not args.no_pieces:
+        pieces = measure_pieces(H, grid, phi, ham, lap_type, tdt, S, norb, npt, comm,
+                                step if world > 1 else None)
+        if world > 1:
+            # max over ranks of every timing
+            keys = ["precond_mg", "gram", "phiT_H_phi", "phi_M", "orbital_update_iteration"]
+            tt = torch.tensor([pieces[k]["ms"] for k in keys], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            for k, v in zip(keys, tt.cpu().tolist()):
+                pieces[k]["ms_max_over_ranks"] = v
 
     if rank == 0:
         updates_per_step = float(npt) * norb * world
@@ -440,6 +529,12 @@ def run_ours(args):
                              "kind": kind, "sample": sample},
         }
         if pieces:
+            if world == 1 and not args.no_cpu_iteration:
+                ci = cpu_iteration(lap_type, dims, (cell,) * 3,
+                                   np.float64 if args.dtype == "f64" else np.float32, norb)
+                it = pieces["orbital_update_iteration"]
+                it["cpu_reference"] = ci
+                it["speedup_vs_cpu_reference"] = ci["seconds"] * 1e3 / it["ms"]
             line["pieces"] = pieces
         print(json.dumps(line))
     if world > 1:
@@ -449,6 +544,8 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--no-cpu-iteration", action="store_true",
+                    help="skip the CPU reference timing of the orbital-update iteration")
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
