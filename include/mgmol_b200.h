@@ -320,6 +320,20 @@ int mgb_comm_barrier(mgb_comm* c, void* stream);
  * memory; the packed exchange below then remains available.                 */
 int mgb_peer_register(mgb_comm* c, const void* ptr, void* stream);
 int mgb_peer_unregister(mgb_comm* c, const void* ptr);
+/* LocGridOrbitals on an x-split domain: the reference's halo packets are
+ * addressed by global orbital id, not by color slot -- the sender tags every
+ * face with gid_[0][color] (west-bound) / gid_[nsubdivx-1][color] (east-bound)
+ * and the receiver stores it in ITS slot of that gid, if its boundary slab
+ * holds it (src/pb/GridFuncVector.cc:1225-1246, 1374-1419).  For the in-place
+ * peer reads this is a per-color index translation: map_west[c] / map_east[c]
+ * = the color slot on the west / east rank whose boundary slab holds the
+ * orbital of my color c in my boundary slab, or -1 (then the ghost planes read
+ * as zero: what a freshly reset ghosted block keeps in the reference).  Host
+ * arrays of ncolors ints; NULL, NULL restores the identity
+ * (ExtendedGridOrbitals).  The caller builds them from its own and its
+ * neighbours' overlapping_gids (one MPI_Sendrecv of ncolors ints).           */
+int mgb_peer_set_color_maps(mgb_comm* c, const int* map_west, const int* map_east,
+    int ncolors);
 /* mgb_hpsi on an x-split domain with the neighbours' boundary planes of phi
  * read directly from their registered blocks (no x-halo buffer for phi; V's
  * halo xhalo_v is exchanged once per potential update with

@@ -116,6 +116,7 @@ _SIGS = {
     "mgb_comm_barrier": (c_int, [c_void_p, c_void_p]),
     "mgb_peer_register": (c_int, [c_void_p, c_void_p, c_void_p]),
     "mgb_peer_unregister": (c_int, [c_void_p, c_void_p]),
+    "mgb_peer_set_color_maps": (c_int, [c_void_p, c_void_p, c_void_p, c_int]),
     "mgb_hpsi_peer": (c_int, [c_void_p, c_int, c_int, ctypes.POINTER(MgbGrid), c_void_p,
                               c_size_t, c_void_p, c_void_p, c_size_t, c_int, c_void_p,
                               c_void_p]),

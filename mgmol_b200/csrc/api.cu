@@ -223,7 +223,7 @@ int mgb_hpsi_force_path(int path)
 static int hpsi_entry(int lap_type, int dtype, const mgb_grid* grid, const void* phi,
     size_t ld, const double* vtot, void* hphi, size_t ldh, int nfunc,
     const void* xhalo_phi, const double* xhalo_v, const void* peer_w, const void* peer_e,
-    void* stream)
+    const int* map_w, const int* map_e, void* stream)
 {
     if (int rc = require_device()) return rc;
     if (int rc = check_grid(grid)) return rc;
@@ -256,6 +256,8 @@ static int hpsi_entry(int lap_type, int dtype, const mgb_grid* grid, const void*
     a.xhalo_v   = xhalo_v;
     a.peer_w    = peer_w;
     a.peer_e    = peer_e;
+    a.map_w     = map_w;
+    a.map_e     = map_e;
     cudaStream_t st = as_stream(stream);
 
     const bool uniform_bc = (grid->bc[0] == grid->bc[1] && grid->bc[1] == grid->bc[2]);
@@ -306,7 +308,7 @@ int mgb_hpsi(int lap_type, int dtype, const mgb_grid* grid, const void* phi,
     const void* xhalo_phi, const double* xhalo_v, void* stream)
 {
     return hpsi_entry(lap_type, dtype, grid, phi, ld, vtot, hphi, ldh, nfunc, xhalo_phi,
-        xhalo_v, nullptr, nullptr, stream);
+        xhalo_v, nullptr, nullptr, nullptr, nullptr, stream);
 }
 
 int mgb_hpsi_peer(mgb_comm* comm, int lap_type, int dtype, const mgb_grid* grid,
@@ -330,13 +332,18 @@ int mgb_hpsi_peer(mgb_comm* comm, int lap_type, int dtype, const mgb_grid* grid,
                   "neighbours' blocks cannot be mapped)");
         return MGB_ENOTSUP;
     }
+    const int *map_w = nullptr, *map_e = nullptr;
+    int map_n = 0;
+    comm_color_maps(comm, &map_w, &map_e, &map_n);
+    MGB_REQUIRE(!map_w || map_n >= nfunc,
+        "mgb_hpsi_peer: color maps cover %d colors, the block has %d", map_n, nfunc);
     cudaStream_t st = as_stream(stream);
     // every rank's phi is complete before anybody reads boundary planes ...
     if (int rc = comm_barrier(comm, st)) return rc;
     const int force = g_force_path;
     g_force_path    = 1; // only the TMA kernel reads peers
     const int rc    = hpsi_entry(lap_type, dtype, grid, phi, ld, vtot, hphi, ldh, nfunc,
-        nullptr, xhalo_v, pw, pe, stream);
+        nullptr, xhalo_v, pw, pe, map_w, map_e, stream);
     g_force_path = force;
     if (rc) return rc;
     // ... and nobody overwrites its phi while a neighbour still reads it

@@ -112,6 +112,9 @@ struct mgb_comm
     void* buf[4];
     size_t buf_sz[4];
     float* flag;                                  // 1-element all-reduce = rank barrier
+    int* map_w;                                   // my color -> west / east rank's color
+    int* map_e;                                   // (device, ncolors each) or null = same
+    int map_n;
     std::map<const void*, PeerEntry>* peers;      // local array -> peer views
     // opened IPC allocations, keyed by (rank, handle bytes): one mapping each
     std::vector<std::pair<std::pair<int, cudaIpcMemHandle_t>, void*>>* opened;
@@ -317,6 +320,13 @@ int comm_barrier(mgb_comm* c, cudaStream_t st)
 
 int comm_rank_of(const mgb_grid* gr, int cx, int cy, int cz) { return rank_of(gr, cx, cy, cz); }
 
+void comm_color_maps(mgb_comm* c, const int** map_w, const int** map_e, int* n)
+{
+    *map_w = c ? c->map_w : nullptr;
+    *map_e = c ? c->map_e : nullptr;
+    *n     = c ? c->map_n : 0;
+}
+
 } // namespace mgb
 
 using namespace mgb;
@@ -399,6 +409,25 @@ int mgb_peer_register(mgb_comm* c, const void* ptr, void* stream)
     return MGB_OK;
 }
 
+int mgb_peer_set_color_maps(mgb_comm* c, const int* map_west, const int* map_east, int ncolors)
+{
+    if (int rc = require_device()) return rc;
+    MGB_REQUIRE(c, "mgb_peer_set_color_maps: null communicator");
+    if (c->map_w) cudaFree(c->map_w);
+    if (c->map_e) cudaFree(c->map_e);
+    c->map_w = c->map_e = nullptr;
+    c->map_n = 0;
+    if (!map_west && !map_east) return MGB_OK;
+    MGB_REQUIRE(map_west && map_east && ncolors > 0,
+        "mgb_peer_set_color_maps: both maps and ncolors > 0 are needed");
+    MGB_CUDA(cudaMalloc(&c->map_w, sizeof(int) * ncolors));
+    MGB_CUDA(cudaMalloc(&c->map_e, sizeof(int) * ncolors));
+    MGB_CUDA(cudaMemcpy(c->map_w, map_west, sizeof(int) * ncolors, cudaMemcpyHostToDevice));
+    MGB_CUDA(cudaMemcpy(c->map_e, map_east, sizeof(int) * ncolors, cudaMemcpyHostToDevice));
+    c->map_n = ncolors;
+    return MGB_OK;
+}
+
 int mgb_peer_unregister(mgb_comm* c, const void* ptr)
 {
     MGB_REQUIRE(c && ptr, "mgb_peer_unregister: null pointer");
@@ -471,6 +500,8 @@ int mgb_comm_destroy(mgb_comm* c)
     for (int i = 0; i < 4; i++)
         if (c->buf[i]) cudaFree(c->buf[i]);
     if (c->flag) cudaFree(c->flag);
+    if (c->map_w) cudaFree(c->map_w);
+    if (c->map_e) cudaFree(c->map_e);
     if (c->opened)
         for (auto& o : *c->opened)
             cudaIpcCloseMemHandle(o.second);

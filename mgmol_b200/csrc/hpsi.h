@@ -24,6 +24,8 @@ struct HpsiArgs
     // from the first planes of peer_e; null = use xhalo_phi
     const void* peer_w;
     const void* peer_e;
+    const int* map_w; // color slot of my color's orbital on that rank (or null)
+    const int* map_e;
 };
 
 // path 1: TMA-pipelined x-streaming kernel (hpsi_fused.cu).  Returns
@@ -55,6 +57,9 @@ int subbox_copy(int dtype, bool pack, const mgb_grid* gr, const int lo[3],
 const void* peer_view(mgb_comm* c, const void* local, int rank);
 int comm_barrier(mgb_comm* c, cudaStream_t st);
 int comm_rank_of(const mgb_grid* gr, int cx, int cy, int cz);
+// LocGridOrbitals on split domains: the color slot of my color's orbital on the
+// west / east rank (device arrays, -1 = not held there), null = same slot
+void comm_color_maps(mgb_comm* c, const int** map_w, const int** map_e, int* n);
 
 // grow-only device scratch owned by the library (workspaces, never user data)
 void* scratch(int slot, size_t bytes);

@@ -95,6 +95,8 @@ struct alignas(64) FusedParams
     CUtensorMap pw_mid, pw_halo;     // west neighbour's phi block (peer memory)
     CUtensorMap pe_mid, pe_halo;     // east neighbour's phi block (peer memory)
     int peer;                        // x-halo planes of phi come from pw / pe
+    const int* map_w;                // color slot on that rank (-1: absent), or null
+    const int* map_e;
     void* out;
     long long ldh;
     int nx, ny, nz, nfunc;
@@ -230,8 +232,10 @@ __global__ void __launch_bounds__(MAXT, 1)
                 const CUtensorMap* pm = (src == 1) ? &P.psi_mid : &P.xpsi_mid;
                 const CUtensorMap* ph = (src == 1) ? &P.psi_halo : &P.xpsi_halo;
                 int xcp = xc;
+                const int* cmap = nullptr;
                 if (src == 2 && P.peer)
                 {
+                    cmap = (p < 0) ? P.map_w : P.map_e;
                     // read the neighbour's boundary plane straight from its
                     // block over NVLink: last planes of the west rank, first
                     // planes of the east rank
@@ -249,11 +253,19 @@ __global__ void __launch_bounds__(MAXT, 1)
                 for (int o = 0; o < norb; o++)
                 {
                     unsigned char* tb = sb + (size_t)(1 + o) * P.tile_bytes;
-                    tma_load_4d(tb + P.off_mid, pm, &full[stage], 0, y0, xcp,
-                        orb0 + o, pol_stream);
-                    tma_load_4d(tb, ph, &full[stage], 0, ylo, xcp, orb0 + o, pol_stream);
-                    tma_load_4d(tb + P.off_hi, ph, &full[stage], 0, yhi, xcp,
-                        orb0 + o, pol_stream);
+                    // the orbital may sit in another color slot on the
+                    // neighbour (gid-addressed packets, src/pb/GridFuncVector.cc:
+                    // 1225-1246,1374-1393); absent there: an out-of-range
+                    // function index makes TMA deliver zeros
+                    int fo = orb0 + o;
+                    if (cmap)
+                    {
+                        fo = cmap[fo];
+                        if (fo < 0) fo = P.nfunc;
+                    }
+                    tma_load_4d(tb + P.off_mid, pm, &full[stage], 0, y0, xcp, fo, pol_stream);
+                    tma_load_4d(tb, ph, &full[stage], 0, ylo, xcp, fo, pol_stream);
+                    tma_load_4d(tb + P.off_hi, ph, &full[stage], 0, yhi, xcp, fo, pol_stream);
                 }
             }
             if (++stage == S)
@@ -885,7 +897,9 @@ int hpsi_tma(const HpsiArgs& a, cudaStream_t st)
         const long long hs = (long long)2 * G * ny * nz;
         if (peer)
         {
-            P.peer = 1;
+            P.peer  = 1;
+            P.map_w = a.map_w;
+            P.map_e = a.map_e;
             if ((rc = make_map(&P.pw_mid, f64, a.peer_w, 4, nz, ny, nx, (long long)a.ld, a.nfunc, TY)))
                 return rc;
             if ((rc = make_map(&P.pw_halo, f64, a.peer_w, 4, nz, ny, nx, (long long)a.ld, a.nfunc, G)))

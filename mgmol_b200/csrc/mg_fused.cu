@@ -60,6 +60,8 @@ struct alignas(64) JacobiParams
     CUtensorMap pw_mid, pw_halo; // west / east neighbour's source block (peer
     CUtensorMap pe_mid, pe_halo; // memory over NVLink) on an x-split domain
     int split_x, have_w, have_e;
+    const int* map_w;            // color slot of my color's orbital on that rank
+    const int* map_e;            // (-1: absent), or null = same slot
     const float* f;              // right-hand side
     float* vout;                 // float output (or null)
     double* vout64;              // double output (exit of precond_mg, or null)
@@ -167,19 +169,22 @@ __global__ void __launch_bounds__(MAXT, 1) k_mg_jacobi(const __grid_constant__ J
             int xc = xb - G + it;
             const CUtensorMap* mm = &P.in_mid;
             const CUtensorMap* mh = &P.in_halo;
+            const int* cmap       = nullptr;
             if (P.split_x)
             {
                 // planes outside my box: the neighbour's block, read in place
                 if (xc < 0 && P.have_w)
                 {
-                    mm = &P.pw_mid;
-                    mh = &P.pw_halo;
+                    mm   = &P.pw_mid;
+                    mh   = &P.pw_halo;
+                    cmap = P.map_w;
                     xc += P.nx;
                 }
                 else if (xc >= P.nx && P.have_e)
                 {
-                    mm = &P.pe_mid;
-                    mh = &P.pe_halo;
+                    mm   = &P.pe_mid;
+                    mh   = &P.pe_halo;
+                    cmap = P.map_e;
                     xc -= P.nx;
                 }
             }
@@ -196,9 +201,17 @@ __global__ void __launch_bounds__(MAXT, 1) k_mg_jacobi(const __grid_constant__ J
             for (int o = 0; o < norb; o++)
             {
                 unsigned char* tb = sb + (size_t)o * P.tile_bytes;
-                tma_load_4d(tb + P.off_mid, mm, &full[stage], 0, y0, xc, orb0 + o, pol);
-                tma_load_4d(tb, mh, &full[stage], 0, ylo, xc, orb0 + o, pol);
-                tma_load_4d(tb + P.off_hi, mh, &full[stage], 0, yhi, xc, orb0 + o, pol);
+                int fo = orb0 + o;
+                if (cmap)
+                {
+                    // gid-addressed: the neighbour may hold this orbital in
+                    // another color slot, or not at all (-> zero fill)
+                    fo = cmap[fo];
+                    if (fo < 0) fo = P.nfunc;
+                }
+                tma_load_4d(tb + P.off_mid, mm, &full[stage], 0, y0, xc, fo, pol);
+                tma_load_4d(tb, mh, &full[stage], 0, ylo, xc, fo, pol);
+                tma_load_4d(tb + P.off_hi, mh, &full[stage], 0, yhi, xc, fo, pol);
             }
             if (++stage == S)
             {
@@ -598,7 +611,8 @@ __global__ void __launch_bounds__(MAXT, 1) k_mg_jacobi(const __grid_constant__ J
 // ---------------------------------------------------------------------------
 __global__ void k_mg_restrict(int nxc, int nyc, int nzc, int perx, int pery, int perz,
     const float* __restrict__ fine, long long ldf, float* __restrict__ coarse,
-    long long ldc, MaskView mask, const float* __restrict__ fine_w)
+    long long ldc, MaskView mask, const float* __restrict__ fine_w,
+    const int* __restrict__ map_w, int f0)
 {
     // block (zx, zy): zx threads along the coarse k-vectors, zy coarse rows;
     // grid.x tiles (k-vector, row), grid.y = coarse plane, grid.z = function
@@ -623,11 +637,15 @@ __global__ void k_mg_restrict(int nxc, int nyc, int nzc, int perx, int pery, int
         {
             // fine plane -1: my own last plane (periodic, x not split), the
             // west neighbour's last plane (x split), or nothing (Dirichlet)
-            if (fine_w)
+            // index in the neighbour's (whole) block; f is relative to f0
+            const int fw = (fine_w && map_w) ? map_w[f] : f + f0;
+            if (fine_w && fw >= 0)
             {
-                Fx = fine_w + (long long)f * ldf;
+                Fx = fine_w + (long long)fw * ldf;
                 x += nx;
             }
+            else if (fine_w)
+                wx = 0.f; // the west rank does not hold this orbital
             else if (perx)
                 x += nx;
             else
@@ -701,7 +719,8 @@ __global__ void k_mg_restrict(int nxc, int nyc, int nzc, int perx, int pery, int
 // ---------------------------------------------------------------------------
 __global__ void k_mg_prolong_correct(int nx, int ny, int nz, int perx, int pery, int perz,
     int zlx, int zly, int zlz, const float* __restrict__ coarse, long long ldc,
-    float* __restrict__ v, long long ldv, MaskView mask, const float* __restrict__ coarse_e)
+    float* __restrict__ v, long long ldv, MaskView mask, const float* __restrict__ coarse_e,
+    const int* __restrict__ map_e, int f0)
 {
     const int nzv = nz >> 2;
     const int tz  = (nzv + blockDim.x - 1) / blockDim.x;
@@ -723,10 +742,11 @@ __global__ void k_mg_prolong_correct(int nx, int ny, int nz, int perx, int pery,
         // coarse plane nxc: my own plane 0 (periodic, x not split), the east
         // neighbour's plane 0 (x split), or nothing (Dirichlet)
         cx1 = 0;
-        if (coarse_e)
-            Cx1 = coarse_e + (long long)f * ldc;
-        else if (!perx)
-            mx = 0.f;
+        const int fe = (coarse_e && map_e) ? map_e[f] : f + f0;
+        if (coarse_e && fe >= 0)
+            Cx1 = coarse_e + (long long)fe * ldc;
+        else if (coarse_e || !perx)
+            mx = 0.f; // the east rank does not hold it, or the domain ends
     }
     if (cy1 == nyc)
     {
@@ -1058,6 +1078,8 @@ int mg_jacobi(const MgJacobiArgs& a, cudaStream_t st)
                 return rc;
         }
     }
+    P.map_w  = a.map_w;
+    P.map_e  = a.map_e;
     P.f      = a.f;
     P.vout   = a.out;
     P.vout64 = a.out64;
@@ -1145,7 +1167,7 @@ static MaskView mask_from(const MaskView& m, int f0)
 }
 
 int mg_restrict(const mgb_grid& fine, const float* w, size_t ldf, float* coarse, size_t ldc,
-    int nfunc, const MaskView& mask, const float* w_west, cudaStream_t st)
+    int nfunc, const MaskView& mask, const float* w_west, const int* map_w, cudaStream_t st)
 {
     const int nxc = fine.dim[0] / 2, nyc = fine.dim[1] / 2, nzc = fine.dim[2] / 2;
     for (int f0 = 0; f0 < nfunc; f0 += 65535)
@@ -1155,7 +1177,7 @@ int mg_restrict(const mgb_grid& fine, const float* w, size_t ldf, float* coarse,
         k_mg_restrict<<<L.grid, L.block, 0, st>>>(nxc, nyc, nzc, fine.bc[0] == 1, fine.bc[1] == 1,
             fine.bc[2] == 1, w + (size_t)f0 * ldf, (long long)ldf,
             coarse + (size_t)f0 * ldc, (long long)ldc, mask_from(mask, f0),
-            w_west ? w_west + (size_t)f0 * ldf : nullptr);
+            w_west, map_w ? map_w + f0 : nullptr, f0);
         MGB_LAUNCHED("k_mg_restrict");
     }
     return MGB_OK;
@@ -1163,7 +1185,7 @@ int mg_restrict(const mgb_grid& fine, const float* w, size_t ldf, float* coarse,
 
 int mg_prolong_correct(const mgb_grid& fine, const float* coarse, size_t ldc, float* v,
     size_t ldv, int nfunc, const int zero_low[3], const MaskView& mask, const float* coarse_east,
-    cudaStream_t st)
+    const int* map_e, cudaStream_t st)
 {
     const int nx = fine.dim[0], ny = fine.dim[1], nz = fine.dim[2];
     for (int f0 = 0; f0 < nfunc; f0 += 65535)
@@ -1173,7 +1195,7 @@ int mg_prolong_correct(const mgb_grid& fine, const float* coarse, size_t ldc, fl
         k_mg_prolong_correct<<<L.grid, L.block, 0, st>>>(nx, ny, nz, fine.bc[0] == 1,
             fine.bc[1] == 1, fine.bc[2] == 1, zero_low[0], zero_low[1], zero_low[2],
             coarse + (size_t)f0 * ldc, (long long)ldc, v + (size_t)f0 * ldv, (long long)ldv,
-            mask_from(mask, f0), coarse_east ? coarse_east + (size_t)f0 * ldc : nullptr);
+            mask_from(mask, f0), coarse_east, map_e ? map_e + f0 : nullptr, f0);
         MGB_LAUNCHED("k_mg_prolong_correct");
     }
     return MGB_OK;

@@ -31,6 +31,10 @@ struct MgJacobiArgs
     // (peer memory, same layout); null where there is no neighbour
     const float* peer_w;
     const float* peer_e;
+    // LocGridOrbitals: color slot of my color's orbital on that rank (device
+    // arrays, -1 = absent), or null = same slot
+    const int* map_w;
+    const int* map_e;
 };
 
 // true when the fused kernels can run this level (z extent a multiple of 4,
@@ -42,11 +46,11 @@ int mg_jacobi(const MgJacobiArgs& a, cudaStream_t st);
 // w_west: the west neighbour's copy of `w` on an x-split domain (its last
 // fine plane is my plane -1), or null
 int mg_restrict(const mgb_grid& fine, const float* w, size_t ldf, float* coarse, size_t ldc,
-    int nfunc, const MaskView& mask, const float* w_west, cudaStream_t st);
+    int nfunc, const MaskView& mask, const float* w_west, const int* map_w, cudaStream_t st);
 // `mask`: of the fine level (applied to P e before the subtraction)
 int mg_prolong_correct(const mgb_grid& fine, const float* coarse, size_t ldc, float* v,
     size_t ldv, int nfunc, const int zero_low[3], const MaskView& mask, const float* coarse_east,
-    cudaStream_t st);
+    const int* map_e, cudaStream_t st);
 int mg_convert(size_t npt, const double* in, size_t ldi, float* out, size_t ldo, int nfunc,
     cudaStream_t st);
 int mg_scale(const mgb_grid& gr, double c, const float* f, size_t ldf, float* v, size_t ldv,

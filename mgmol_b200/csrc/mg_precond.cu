@@ -411,6 +411,11 @@ static int cycle_fused(mgb_precond* p, int l, const float* f, size_t ldf, double
     for (int d = 0; d < 3; d++)
         zl[d] = gr.bc[d] != 1 && gr.coord[d] == 0; // the rank owning the low face
     const bool split = gr.nproc[0] > 1;
+    const int *map_w = nullptr, *map_e = nullptr;
+    int map_n = 0;
+    if (split) comm_color_maps(p->comm, &map_w, &map_e, &map_n);
+    MGB_REQUIRE(!map_w || map_n >= nfunc, "mgb_precond_mg: color maps cover %d colors, need %d",
+        map_n, nfunc);
     // the last sweep of level 0 is followed by a trade only on the path through
     // Preconditioning.cc:215, whose test reads bc_[0], bc_[2], bc_[2]
     const bool final_trade = !coarsest && (gr.bc[0] != 1 || gr.bc[2] != 1);
@@ -457,6 +462,8 @@ static int cycle_fused(mgb_precond* p, int l, const float* f, size_t ldf, double
         if (int rc = x_peers(p, gr, a.in, xp)) return rc;
         a.peer_w = xp.w;
         a.peer_e = xp.e;
+        a.map_w  = map_w;
+        a.map_e  = map_e;
         // every rank has finished writing (and reading) the blocks involved
         if (split)
             if (int rc = comm_barrier(p->comm, st)) return rc;
@@ -482,7 +489,7 @@ static int cycle_fused(mgb_precond* p, int l, const float* f, size_t ldf, double
         if (split)
             if (int rc = comm_barrier(p->comm, st)) return rc;
         if (int rc = mg_restrict(
-                gr, p->fw[l], ld, p->ff[l + 1], npt_of(p->grid[l + 1]), nfunc, mkc, xp.w, st))
+                gr, p->fw[l], ld, p->ff[l + 1], npt_of(p->grid[l + 1]), nfunc, mkc, xp.w, map_w, st))
             return rc;
     }
     // :198-199 coarse correction from a zero start: its first sweep gives
@@ -499,7 +506,7 @@ static int cycle_fused(mgb_precond* p, int l, const float* f, size_t ldf, double
         if (split)
             if (int rc = comm_barrier(p->comm, st)) return rc;
         if (int rc = mg_prolong_correct(
-                gr, e, npt_of(p->grid[l + 1]), cur, ld, nfunc, zl, mk, xp.e, st))
+                gr, e, npt_of(p->grid[l + 1]), cur, ld, nfunc, zl, mk, xp.e, map_e, st))
             return rc;
     }
     for (int it = 0; it < 2; it++) // :209-213

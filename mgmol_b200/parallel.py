@@ -45,6 +45,19 @@ class Communicator:
     def unregister(self, t):
         check(lib().mgb_peer_unregister(self.handle, _p(t)))
 
+    def set_color_maps(self, map_west, map_east):
+        """LocGridOrbitals on an x-split domain: color slot of my colors' orbitals
+        on the west / east rank (see color_maps); None, None = identity."""
+        if map_west is None:
+            check(lib().mgb_peer_set_color_maps(self.handle, None, None, 0))
+            return
+        import numpy as np
+        mw = np.ascontiguousarray(map_west, dtype=np.int32)
+        me = np.ascontiguousarray(map_east, dtype=np.int32)
+        check(lib().mgb_peer_set_color_maps(
+            self.handle, mw.ctypes.data_as(ctypes.c_void_p),
+            me.ctypes.data_as(ctypes.c_void_p), len(mw)))
+
     def halo_exchange_x(self, grid, g, noghost, xhalo):
         nfunc = noghost.shape[0]
         check(lib().mgb_halo_exchange_x(self.handle, _dt(noghost), grid.ref(), g,
@@ -160,6 +173,26 @@ def local_box(gdims, nproc, coord):
             raise ValueError("global dims must divide by ranks (Grid.cc:52-54)")
     dims = tuple(n // p for n, p in zip(gdims, nproc))
     return tuple(slice(c * d, (c + 1) * d) for c, d in zip(coord, dims))
+
+
+def color_maps(my_gids, west_gids, east_gids):
+    """The gid-addressed halo of GridFuncVector (src/pb/GridFuncVector.cc:
+    1225-1246,1374-1419) as index translations for in-place peer reads.
+    *_gids: (subdivx, ncolors) tables overlapping_gids_[iloc][color] of this
+    rank and of its west / east neighbours (None where the domain ends).
+
+    The west rank tags the planes it sends east with the gid of its LAST slab;
+    I store them in my color whose FIRST slab holds that gid.  Hence
+    map_west[c] = c' with west_gids[-1][c'] == my_gids[0][c], or -1; and
+    map_east[c] = c' with east_gids[0][c'] == my_gids[-1][c], or -1."""
+    def one(mine, theirs):
+        out = []
+        lookup = {} if theirs is None else {int(g): i for i, g in enumerate(theirs) if g >= 0}
+        for g in mine:
+            out.append(lookup.get(int(g), -1) if g >= 0 else -1)
+        return out
+    return (one(my_gids[0], None if west_gids is None else west_gids[-1]),
+            one(my_gids[-1], None if east_gids is None else east_gids[0]))
 
 
 def x_halo_plan(rank, nproc, g, bc_x=1):

@@ -104,3 +104,20 @@ def test_x_halo_plan_and_allreduce_world2(bc_x):
     out = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), bc_x, out), nprocs=world, join=True)
     assert dict(out) == {0: (True, True), 1: (True, True)}
+
+
+def test_color_maps_follow_gid_addressed_packets():
+    """color_maps = which slot of the neighbour the reference's receiver would
+    take a face from (src/pb/GridFuncVector.cc:1225-1246,1374-1419)."""
+    from mgmol_b200.parallel import color_maps
+    mine = [[4, 7, -1, 2], [4, 9, 3, 2]]       # slabs 0 .. last, 4 colors
+    west = [[1, 4, 7, 0], [7, 4, 5, -1]]       # its LAST slab faces me
+    east = [[2, -1, 9, 6], [2, 8, 9, 6]]       # its FIRST slab faces me
+    mw, me = color_maps(mine, west, east)
+    # my first-slab gids 4, 7, -1, 2 in the west rank's last slab [7, 4, 5, -1]
+    assert mw == [1, 0, -1, -1]
+    # my last-slab gids 4, 9, 3, 2 in the east rank's first slab [2, -1, 9, 6]
+    assert me == [-1, 2, -1, 0]
+    assert color_maps(mine, None, east)[0] == [-1, -1, -1, -1]
+    ident = [[0, 1, 2]]
+    assert color_maps(ident, ident, ident) == ([0, 1, 2], [0, 1, 2])
