@@ -103,6 +103,17 @@ struct PeerEntry
     std::vector<cudaIpcMemHandle_t> handle; // per rank: IPC handle of the allocation
     std::vector<unsigned long long> offset; // per rank: offset of the array inside it
     std::vector<void*> mapped;              // per rank: the array in MY address space
+    std::vector<int> opened_id;             // per rank: which opened allocation (-1: none)
+};
+
+// one peer allocation opened with cudaIpcOpenMemHandle, shared by every
+// registered array that lives in it
+struct OpenedAlloc
+{
+    int rank;
+    cudaIpcMemHandle_t handle;
+    void* base;
+    int refs;
 };
 
 struct mgb_comm
@@ -116,8 +127,7 @@ struct mgb_comm
     int* map_e;                                   // (device, ncolors each) or null = same
     int map_n;
     std::map<const void*, PeerEntry>* peers;      // local array -> peer views
-    // opened IPC allocations, keyed by (rank, handle bytes): one mapping each
-    std::vector<std::pair<std::pair<int, cudaIpcMemHandle_t>, void*>>* opened;
+    std::vector<OpenedAlloc>* opened; // slots are reused, never compacted
 };
 
 namespace mgb
@@ -291,22 +301,41 @@ const void* peer_view(mgb_comm* c, const void* local, int rank)
     PeerEntry& e = it->second;
     if (rank == c->rank) return local;
     if (e.mapped[rank]) return e.mapped[rank];
-    void* base = nullptr;
-    for (auto& o : *c->opened)
-        if (o.first.first == rank
-            && memcmp(&o.first.second, &e.handle[rank], sizeof(cudaIpcMemHandle_t)) == 0)
-            base = o.second;
-    if (!base)
+    int id = -1;
+    for (size_t i = 0; i < c->opened->size(); i++)
     {
+        OpenedAlloc& o = (*c->opened)[i];
+        if (o.refs > 0 && o.rank == rank
+            && memcmp(&o.handle, &e.handle[rank], sizeof(cudaIpcMemHandle_t)) == 0)
+            id = (int)i;
+    }
+    if (id < 0)
+    {
+        void* base = nullptr;
         if (cudaIpcOpenMemHandle(&base, e.handle[rank], cudaIpcMemLazyEnablePeerAccess)
             != cudaSuccess)
         {
             (void)cudaGetLastError();
             return nullptr;
         }
-        c->opened->push_back({ { rank, e.handle[rank] }, base });
+        OpenedAlloc o;
+        o.rank   = rank;
+        o.handle = e.handle[rank];
+        o.base   = base;
+        o.refs   = 0;
+        for (size_t i = 0; i < c->opened->size() && id < 0; i++)
+            if ((*c->opened)[i].refs == 0) id = (int)i;
+        if (id < 0)
+        {
+            c->opened->push_back(o);
+            id = (int)c->opened->size() - 1;
+        }
+        else
+            (*c->opened)[id] = o;
     }
-    e.mapped[rank] = (char*)base + e.offset[rank];
+    (*c->opened)[id].refs++;
+    e.opened_id[rank] = id;
+    e.mapped[rank]    = (char*)(*c->opened)[id].base + e.offset[rank];
     return e.mapped[rank];
 }
 
@@ -400,6 +429,8 @@ int mgb_peer_register(mgb_comm* c, const void* ptr, void* stream)
     e.handle.resize(c->nranks);
     e.offset.resize(c->nranks);
     e.mapped.assign(c->nranks, nullptr);
+    e.opened_id.assign(c->nranks, -1);
+    mgb_peer_unregister(c, ptr); // a stale entry of a freed array at this address
     for (int r = 0; r < c->nranks; r++)
     {
         e.handle[r] = all[r].h;
@@ -431,7 +462,19 @@ int mgb_peer_set_color_maps(mgb_comm* c, const int* map_west, const int* map_eas
 int mgb_peer_unregister(mgb_comm* c, const void* ptr)
 {
     MGB_REQUIRE(c && ptr, "mgb_peer_unregister: null pointer");
-    c->peers->erase(ptr);
+    auto it = c->peers->find(ptr);
+    if (it == c->peers->end()) return MGB_OK;
+    // close the peer allocations nobody else uses any more (after my kernels
+    // that may still read them); the owner may free its array only after every
+    // rank has done this (see mgb_precond_destroy)
+    bool any = false;
+    for (int id : it->second.opened_id)
+        any = any || id >= 0;
+    if (any) cudaDeviceSynchronize();
+    for (int id : it->second.opened_id)
+        if (id >= 0 && --(*c->opened)[id].refs == 0)
+            cudaIpcCloseMemHandle((*c->opened)[id].base);
+    c->peers->erase(it);
     return MGB_OK;
 }
 
@@ -468,7 +511,7 @@ int mgb_comm_create(mgb_comm** out, const void* id128, int rank, int nranks)
     c->rank   = rank;
     c->nranks = nranks;
     c->peers  = new std::map<const void*, PeerEntry>();
-    c->opened = new std::vector<std::pair<std::pair<int, cudaIpcMemHandle_t>, void*>>();
+    c->opened = new std::vector<OpenedAlloc>();
     if (cudaMalloc(&c->flag, sizeof(float)) != cudaSuccess
         || cudaMemset(c->flag, 0, sizeof(float)) != cudaSuccess)
     {
@@ -504,7 +547,7 @@ int mgb_comm_destroy(mgb_comm* c)
     if (c->map_e) cudaFree(c->map_e);
     if (c->opened)
         for (auto& o : *c->opened)
-            cudaIpcCloseMemHandle(o.second);
+            if (o.refs > 0) cudaIpcCloseMemHandle(o.base);
     delete c->opened;
     delete c->peers;
     if (N && c->comm) N->CommDestroy(c->comm);

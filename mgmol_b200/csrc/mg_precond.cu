@@ -522,6 +522,18 @@ extern "C"
 int mgb_precond_destroy(mgb_precond* p)
 {
     if (!p) return MGB_OK;
+    if (p->peers_ready && p->comm)
+    {
+        // collective: nobody reads my work blocks any more, every rank closes its
+        // mappings of its neighbours' blocks, and only then are they freed
+        comm_barrier(p->comm, nullptr);
+        cudaDeviceSynchronize();
+        for (auto* vec : { &p->fa, &p->fb, &p->fw, &p->ff })
+            for (float* q : *vec)
+                if (q) mgb_peer_unregister(p->comm, q);
+        comm_barrier(p->comm, nullptr);
+        cudaDeviceSynchronize();
+    }
     for (float* q : p->work)
         if (q) cudaFree(q);
     for (float* q : p->rcoarse)
