@@ -121,6 +121,24 @@ int mgb_hpsi(int lap_type, int dtype, const mgb_grid* grid, const void* phi,
     size_t ld, const double* vtot, void* hphi, size_t ldh, int nfunc,
     const void* xhalo_phi, const double* xhalo_v, void* stream);
 
+/* B phi on a no-ghost block: pb::Lap<T>::rhs (src/pb/Lap.h:32) = FDoper::
+ * rhs_4th_Mehr1 / FDkernelRHS_4th_Mehr1 (src/pb/FDkernels.cc:522-584) for
+ * Laph4M after setDataWithGhosts + trade_boundaries, the identity for the
+ * non-compact operators; every orbital at once, boundary condition folded into
+ * the index (bit-identical).  xhalo_phi: [nfunc][2][ny][nz] on x-split boxes.  */
+int mgb_apply_b(int lap_type, int dtype, const mgb_grid* grid, const void* phi,
+    size_t ld, void* bphi, size_t ldb, int nfunc, const void* xhalo_phi,
+    void* stream);
+/* MGmol::computeResidualUsingHPhi (src/MGmol.cc:1227-1287):
+ *     res = (B phi) theta - hphi          [Ry]
+ * theta = localT (column-major nfunc x nfunc double on the device), B applied
+ * when the operator is Mehrstellen (ct.Mehrstellen()).  The reference's four
+ * sweeps (ghost-add, B per orbital, multiplyByMatrix, axpy) become B phi into a
+ * library workspace and ONE contraction pass whose epilogue subtracts hphi.   */
+int mgb_residual(int lap_type, int dtype, const mgb_grid* grid, const void* phi,
+    size_t ld, const void* hphi, size_t ldh, const double* theta, int ldt,
+    void* res, size_t ldr, int nfunc, const void* xhalo_phi, void* stream);
+
 /* The same operator for a caller whose orbitals live in HOST memory (MGmol's
  * default MemorySpace::Host build: BlockVector storage, src/BlockVector.cc:
  * 138-218): phi_host, vtot_host and hphi_host are host pointers.  The call
@@ -171,6 +189,13 @@ int mgb_axpy(int dtype, size_t n, double alpha, const void* x, void* y, void* st
 int mgb_scal(int dtype, size_t n, double alpha, void* x, void* stream);
 int mgb_dot(int dtype, size_t n, const void* x, const void* y, double* result_dev,
     void* stream);
+/* ExtendedGridOrbitals::computeDiagonalElementsDotProduct (src/
+ * ExtendedGridOrbitals.cc:1085-1106): result[i] = alpha * <x_i, y_i> for every
+ * orbital of two no-ghost blocks (alpha = grid.vel()), one launch; the input of
+ * Orbitals::dotProduct (dotProductDiagonal, :1205-1213) used by the residual
+ * norm (src/MGmol.cc:1316) and by AndersonMix (src/AndersonMix.cc:88-110).   */
+int mgb_dot_cols(int dtype, size_t n, int nfunc, double alpha, const void* x,
+    size_t ldx, const void* y, size_t ldy, double* result_dev, void* stream);
 /* GridFuncVector::jacobi (src/pb/GridFuncVector.cc:2416-2425):
  * w = A v ; w -= f ; v += -omega w, v's ghosts must be up to date.          */
 int mgb_gfv_jacobi(int lap_type, const mgb_grid* grid, float* v, const float* f,

@@ -51,6 +51,11 @@ _SIGS = {
     "mgb_hpsi": (c_int, [c_int, c_int, ctypes.POINTER(MgbGrid), c_void_p, c_size_t,
                          c_void_p, c_void_p, c_size_t, c_int, c_void_p, c_void_p,
                          c_void_p]),
+    "mgb_apply_b": (c_int, [c_int, c_int, ctypes.POINTER(MgbGrid), c_void_p, c_size_t,
+                            c_void_p, c_size_t, c_int, c_void_p, c_void_p]),
+    "mgb_residual": (c_int, [c_int, c_int, ctypes.POINTER(MgbGrid), c_void_p, c_size_t,
+                             c_void_p, c_size_t, c_void_p, c_int, c_void_p, c_size_t, c_int,
+                             c_void_p, c_void_p]),
     "mgb_hpsi_host": (c_int, [c_int, c_int, ctypes.POINTER(MgbGrid), c_void_p, c_size_t,
                               c_void_p, c_void_p, c_size_t, c_int, c_int]),
     "mgb_host_register": (c_int, [c_void_p, c_size_t]),
@@ -68,6 +73,8 @@ _SIGS = {
     "mgb_axpy": (c_int, [c_int, c_size_t, c_double, c_void_p, c_void_p, c_void_p]),
     "mgb_scal": (c_int, [c_int, c_size_t, c_double, c_void_p, c_void_p]),
     "mgb_dot": (c_int, [c_int, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mgb_dot_cols": (c_int, [c_int, c_size_t, c_int, c_double, c_void_p, c_size_t, c_void_p,
+                             c_size_t, c_void_p, c_void_p]),
     "mgb_gfv_jacobi": (c_int, [c_int, ctypes.POINTER(MgbGrid), c_void_p, c_void_p,
                                c_void_p, c_int, c_double, c_void_p]),
     "mgb_gfv_restrict3D": (c_int, [c_int, ctypes.POINTER(MgbGrid), c_void_p,

@@ -31,6 +31,7 @@ SOURCES = {
     "mg_precond.cu": [],
     "mg_fused.cu": [],
     "masks.cu": [],
+    "blas1_cols.cu": [],
     "contractions.cu": [],
     "comm.cu": [],
 }

@@ -303,6 +303,69 @@ static int hpsi_entry(int lap_type, int dtype, const mgb_grid* grid, const void*
     return hpsi_ghosted(a, st);
 }
 
+int mgb_apply_b(int lap_type, int dtype, const mgb_grid* grid, const void* phi, size_t ld,
+    void* bphi, size_t ldb, int nfunc, const void* xhalo_phi, void* stream)
+{
+    if (int rc = require_device()) return rc;
+    if (int rc = check_grid(grid)) return rc;
+    MGB_REQUIRE(phi && bphi && phi != bphi, "mgb_apply_b: null or aliased pointers");
+    MGB_REQUIRE(dtype == MGB_F32 || dtype == MGB_F64, "mgb_apply_b: bad dtype %d", dtype);
+    const size_t npt = (size_t)grid->dim[0] * grid->dim[1] * grid->dim[2];
+    MGB_REQUIRE(ld >= npt && ldb >= npt && nfunc >= 0, "mgb_apply_b: bad dimensions");
+    if (nfunc == 0) return MGB_OK;
+    const size_t es = dtype == MGB_F64 ? 8 : 4;
+    cudaStream_t st = as_stream(stream);
+    if (lap_type != MGB_LAP_4M)
+    {
+        // FDoper::rhs of the other operators is the identity (src/pb/Laph4.h,
+        // Laph2.h ...: B = 1); Laph4MP's B2 (src/pb/FDoper.cc:510-563) is not built
+        MGB_REQUIRE(lap_type != MGB_LAP_4MP, "mgb_apply_b: Laph4MP (rhs_4th_Mehr2) is not built");
+        MGB_CUDA(cudaMemcpy2DAsync(bphi, ldb * es, phi, ld * es, npt * es, (size_t)nfunc,
+            cudaMemcpyDeviceToDevice, st));
+        return MGB_OK;
+    }
+    const bool uniform = grid->bc[0] == grid->bc[1] && grid->bc[1] == grid->bc[2];
+    MGB_REQUIRE(uniform && grid->nproc[1] == 1 && grid->nproc[2] == 1,
+        "mgb_apply_b: mixed boundary conditions and y/z splits go through "
+        "mgb_gfv_set_with_ghosts + trade + mgb_fd_apply(MGB_FD_RHS_4TH_MEHR1)");
+    MGB_REQUIRE(grid->nproc[0] == 1 || xhalo_phi,
+        "mgb_apply_b: x is split but no x-halo buffer was given");
+    return rhs_generic(dtype, grid, phi, ld, xhalo_phi, bphi, ldb, nfunc, st);
+}
+
+int mgb_residual(int lap_type, int dtype, const mgb_grid* grid, const void* phi, size_t ld,
+    const void* hphi, size_t ldh, const double* theta, int ldt, void* res, size_t ldr,
+    int nfunc, const void* xhalo_phi, void* stream)
+{
+    if (int rc = require_device()) return rc;
+    if (int rc = check_grid(grid)) return rc;
+    MGB_REQUIRE(phi && hphi && theta && res, "mgb_residual: null pointer");
+    MGB_REQUIRE(res != phi && res != hphi, "mgb_residual: res must not alias phi or hphi");
+    MGB_REQUIRE(dtype == MGB_F32 || dtype == MGB_F64, "mgb_residual: bad dtype %d", dtype);
+    const size_t npt = (size_t)grid->dim[0] * grid->dim[1] * grid->dim[2];
+    MGB_REQUIRE(ld >= npt && ldh >= npt && ldr >= npt && ldt >= nfunc && nfunc >= 0,
+        "mgb_residual: bad dimensions");
+    if (nfunc == 0) return MGB_OK;
+    cudaStream_t st = as_stream(stream);
+    const void* a   = phi;
+    size_t lda      = ld;
+    if (lap_type == MGB_LAP_4M || lap_type == MGB_LAP_4MP)
+    {
+        // applyB (ct.Mehrstellen()): tmp = B phi  (src/MGmol.cc:1250-1260)
+        const size_t es = dtype == MGB_F64 ? 8 : 4;
+        void* tmp       = scratch(3, npt * (size_t)nfunc * es);
+        if (!tmp) return MGB_ECUDA;
+        if (int rc = mgb_apply_b(lap_type, dtype, grid, phi, ld, tmp, npt, nfunc, xhalo_phi, stream))
+            return rc;
+        a   = tmp;
+        lda = npt;
+    }
+    // res = (B phi) theta - hphi: multiplyByMatrix(localT, res) then
+    // res.axpy(-1., hphi)  (:1272, :1284), one pass
+    return gemm_nn_fused(dtype, npt, nfunc, nfunc, 1., a, lda, theta, ldt, 0., res, ldr, -1.,
+        hphi, ldh, st);
+}
+
 int mgb_hpsi(int lap_type, int dtype, const mgb_grid* grid, const void* phi,
     size_t ld, const double* vtot, void* hphi, size_t ldh, int nfunc,
     const void* xhalo_phi, const double* xhalo_v, void* stream)

@@ -420,7 +420,7 @@ template <typename T, int KCv, int ST>
 __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_nn(long long npt, int n, int k,
     const T* __restrict__ Phi, long long lda, const double* __restrict__ M, int ldm,
     double alpha, double beta, T* __restrict__ Out, long long ldc, long long nitems,
-    int jtiles)
+    int jtiles, double gamma, const T* __restrict__ D, long long ldd)
 {
     extern __shared__ __align__(16) unsigned char smraw[];
     constexpr int PITCH_K = KCv + PADK;
@@ -543,6 +543,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_nn(long long npt, int n, i
                             base = (T)(beta * (double)o[e]);
                         r[e]         = base + (T)(alpha * acc[i][j][e]);
                         acc[i][j][e] = 0.;
+                        // fused "Out.axpy(gamma, D)" (MPaxpy: y += (T)(gamma * (double)x),
+                        // mputils.cc:222-244) on the freshly rounded product
+                        if (D && jj < n && pp + e < npt)
+                            r[e] += (T)(gamma * (double)D[(long long)jj * ldd + pp + e]);
                     }
                     if (jj < n)
                     {
@@ -721,8 +725,19 @@ static int gemm_tn_t(bool syrk, int m, int n, size_t k, double alpha, const T* A
 }
 
 template <typename T>
+__global__ void k_axpy_cols(long long m, double gamma, const T* __restrict__ D, long long ldd,
+    T* __restrict__ Out, long long ldc)
+{
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= m) return;
+    const int j = blockIdx.y;
+    Out[(long long)j * ldc + p] += (T)(gamma * (double)D[(long long)j * ldd + p]);
+}
+
+template <typename T>
 static int gemm_nn_t(size_t m, int n, int k, double alpha, const T* A, size_t lda,
-    const double* M, int ldm, double beta, T* Out, size_t ldc, cudaStream_t st)
+    const double* M, int ldm, double beta, T* Out, size_t ldc, cudaStream_t st,
+    double gamma = 0., const T* D = nullptr, size_t ldd = 0)
 {
     const bool aligned = (((uintptr_t)A | (uintptr_t)M) & 15) == 0
                          && (lda * sizeof(T)) % 16 == 0 && (ldm * sizeof(double)) % 16 == 0;
@@ -732,6 +747,12 @@ static int gemm_nn_t(size_t m, int n, int k, double alpha, const T* A, size_t ld
         k_gemm_nn_ref<T><<<grid, 128, 0, st>>>((long long)m, n, k, A, (long long)lda, M,
             ldm, alpha, beta, Out, (long long)ldc);
         MGB_LAUNCHED("k_gemm_nn_ref");
+        if (D)
+        {
+            k_axpy_cols<T><<<grid, 128, 0, st>>>(
+                (long long)m, gamma, D, (long long)ldd, Out, (long long)ldc);
+            MGB_LAUNCHED("k_axpy_cols");
+        }
         return MGB_OK;
     }
     int kcv = 32;
@@ -748,17 +769,28 @@ static int gemm_nn_t(size_t m, int n, int k, double alpha, const T* A, size_t ld
         auto kern = k_gemm_nn<T, 32, 3>;
         MGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, NTHREADS, smem, st>>>((long long)m, n, k, A, (long long)lda, M, ldm, alpha,
-            beta, Out, (long long)ldc, nitems, jtiles);
+            beta, Out, (long long)ldc, nitems, jtiles, gamma, D, (long long)ldd);
     }
     else
     {
         auto kern = k_gemm_nn<T, 16, 4>;
         MGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, NTHREADS, smem, st>>>((long long)m, n, k, A, (long long)lda, M, ldm, alpha,
-            beta, Out, (long long)ldc, nitems, jtiles);
+            beta, Out, (long long)ldc, nitems, jtiles, gamma, D, (long long)ldd);
     }
     MGB_LAUNCHED("k_gemm_nn");
     return MGB_OK;
+}
+
+int gemm_nn_fused(int dtype, size_t m, int n, int k, double alpha, const void* A, size_t lda,
+    const double* M, int ldm, double beta, void* Out, size_t ldc, double gamma, const void* D,
+    size_t ldd, cudaStream_t st)
+{
+    if (dtype == MGB_F64)
+        return gemm_nn_t<double>(m, n, k, alpha, (const double*)A, lda, M, ldm, beta,
+            (double*)Out, ldc, st, gamma, (const double*)D, ldd);
+    return gemm_nn_t<float>(m, n, k, alpha, (const float*)A, lda, M, ldm, beta, (float*)Out,
+        ldc, st, gamma, (const float*)D, ldd);
 }
 
 } // namespace mgb

@@ -226,6 +226,76 @@ int hpsi_generic_t(const HpsiArgs& a, cudaStream_t st)
     return MGB_OK;
 }
 
+// B u = u/2 + (1/12) sum of the 6 face neighbours on a no-ghost block with the
+// boundary condition folded into the index: Lap<T>::rhs = FDoper::rhs_4th_Mehr1
+// / FDkernelRHS_4th_Mehr1 (src/pb/FDkernels.cc:522-584) after setDataWithGhosts
+// + trade_boundaries, as MGmol::computeResidualUsingHPhi applies it to every
+// orbital (src/MGmol.cc:1252-1260).  Bit-identical (this unit is -fmad=false).
+template <typename T>
+__global__ void k_rhs_generic(GenericView<T> view0, long long ld, long long ldo,
+    long long halo_stride, T* __restrict__ out, int tiles_z)
+{
+    const int tz = blockIdx.x % tiles_z;
+    const int ty = blockIdx.x / tiles_z;
+    const int iz = tz * blockDim.x + threadIdx.x;
+    const int iy = ty * blockDim.y + threadIdx.y;
+    const int ix = blockIdx.y;
+    const int f  = blockIdx.z;
+    GenericView<T> w = view0;
+    if (iz >= w.nz || iy >= w.ny) return;
+    w.phi += (long long)f * ld;
+    if (w.xhalo) w.xhalo += (long long)f * halo_stride;
+    const long long o = ((long long)ix * w.ny + iy) * w.nz + iz;
+    out[(long long)f * ldo + o]
+        = (T)(0.5 * (double)w.psi(ix, iy, iz)
+              + (1. / 12.)
+                    * (double)(w.psi(ix - 1, iy, iz) + w.psi(ix + 1, iy, iz)
+                               + w.psi(ix, iy - 1, iz) + w.psi(ix, iy + 1, iz)
+                               + w.psi(ix, iy, iz - 1) + w.psi(ix, iy, iz + 1)));
+}
+
+template <typename T>
+static int rhs_generic_t(const mgb_grid* gr, const T* phi, size_t ld, const T* xhalo, T* out,
+    size_t ldo, int nfunc, cudaStream_t st)
+{
+    GenericView<T> w;
+    w.phi      = phi;
+    w.xhalo    = xhalo;
+    w.v        = nullptr;
+    w.xhv      = nullptr;
+    w.nx       = gr->dim[0];
+    w.ny       = gr->dim[1];
+    w.nz       = gr->dim[2];
+    w.g        = 1;
+    w.periodic = (gr->bc[0] == 1);
+    w.split_x  = gr->nproc[0] > 1;
+    w.first_x  = gr->coord[0] == 0;
+    w.last_x   = gr->coord[0] == gr->nproc[0] - 1;
+    RowLaunch L = row_launch(w.nx, w.ny, w.nz, 1);
+    const long long halo_stride = (long long)2 * w.ny * w.nz;
+    for (int f0 = 0; f0 < nfunc; f0 += 65535)
+    {
+        const int nf = (nfunc - f0 < 65535) ? nfunc - f0 : 65535;
+        dim3 grid(L.grid.x, L.grid.y, (unsigned)nf);
+        GenericView<T> wf = w;
+        wf.phi += (long long)f0 * ld;
+        if (wf.xhalo) wf.xhalo += (long long)f0 * halo_stride;
+        k_rhs_generic<T><<<grid, L.block, 0, st>>>(wf, (long long)ld, (long long)ldo,
+            halo_stride, out + (long long)f0 * ldo, L.tiles_z);
+        MGB_LAUNCHED("k_rhs_generic");
+    }
+    return MGB_OK;
+}
+
+int rhs_generic(int dtype, const mgb_grid* gr, const void* phi, size_t ld, const void* xhalo,
+    void* out, size_t ldo, int nfunc, cudaStream_t st)
+{
+    return dtype == MGB_F64 ? rhs_generic_t<double>(gr, (const double*)phi, ld,
+                                  (const double*)xhalo, (double*)out, ldo, nfunc, st)
+                            : rhs_generic_t<float>(gr, (const float*)phi, ld,
+                                  (const float*)xhalo, (float*)out, ldo, nfunc, st);
+}
+
 int hpsi_generic(const HpsiArgs& a, cudaStream_t st)
 {
     return a.dtype == MGB_F64 ? hpsi_generic_t<double>(a, st)

@@ -257,6 +257,15 @@ class Lap:
         return hphi
 
 
+    def rhs(self, phi, bphi, xhalo_phi=None):
+        """Lap<T>::rhs (src/pb/Lap.h:32) for every orbital of a no-ghost block:
+        B phi (Mehrstellen) or a copy (B = 1)."""
+        check(lib().mgb_apply_b(
+            self.type_, _dt(phi), self.grid_.ref(), _p(phi), self.grid_.size(), _p(bphi),
+            self.grid_.size(), phi.shape[0],
+            _p(xhalo_phi) if xhalo_phi is not None else None, _stream()))
+        return bphi
+
     def applyWithPotPeer(self, comm, phi, vtot, hphi, xhalo_v):
         """applyWithPot on an x-split domain, the neighbours' boundary planes of
         phi read directly from their (registered) blocks over NVLink."""
@@ -351,6 +360,46 @@ class Orbitals:
         check(lib().mgb_scal(_dt(self.psi_), self.psi_.numel(), float(alpha),
                              _p(self.psi_), _stream()))
         self.incrementIterativeIndex()
+
+    def assign(self, other):
+        """BlockVector::assign / Orbitals::assign: copy the block."""
+        check(lib().mgb_copy_dev(_p(self.psi_), _p(other.psi_),
+                                 self.psi_.numel() * self.psi_.element_size(), _stream()))
+        self.incrementIterativeIndex()
+
+    def __isub__(self, other):
+        """operator-= (src/BlockVector.cc:289-299)."""
+        check(lib().mgb_axpy(_dt(self.psi_), self.psi_.numel(), -1.0, _p(other.psi_),
+                             _p(self.psi_), _stream()))
+        self.incrementIterativeIndex()
+        return self
+
+    def clone(self):
+        return type(self).__new__(type(self))._init_like(self)
+
+    def _init_like(self, other):
+        self.__dict__.update(other.__dict__)
+        self.psi_ = other.psi_.clone()
+        return self
+
+    def computeDiagonalElementsDotProduct(self, other, comm=None):
+        """ss[i] = vel * <phi_i, psi_i> for every orbital
+        (src/ExtendedGridOrbitals.cc:1085-1106), one launch."""
+        ss = torch.empty(self.numst_, dtype=torch.float64, device="cuda")
+        check(lib().mgb_dot_cols(_dt(self.psi_), self.grid_.size(), self.numst_,
+                                 self.grid_.vel(), _p(self.psi_), self.grid_.size(),
+                                 _p(other.psi_), self.grid_.size(), _p(ss), _stream()))
+        if comm is not None:
+            comm.allreduce(ss)
+        return ss
+
+    def dotProduct(self, other, inv_s_diag=None, comm=None):
+        """dotProductDiagonal (src/ExtendedGridOrbitals.cc:1205-1213): the trace
+        of diag(S^-1) * diag(Phi^T Psi); inv_s_diag defaults to ones."""
+        ss = self.computeDiagonalElementsDotProduct(other, comm)
+        if inv_s_diag is not None:
+            ss = ss * inv_s_diag
+        return float(ss.sum())
 
     # -- contractions ---------------------------------------------------------
     def computeLocalProduct(self, other, comm=None):
@@ -596,6 +645,21 @@ class Hamiltonian:
         if phi2 is not None:
             self.applyLocal(phi2)
         return phi1.computeLocalProduct(self.hlphi_, comm)
+
+
+def computeResidualUsingHPhi(lapOper, psi, hphi, localT, res, xhalo_phi=None):
+    """MGmol::computeResidualUsingHPhi (src/MGmol.cc:1227-1287):
+    res = (B psi) theta - hphi in [Ry]; localT[l, j] = theta (numst x numst double
+    tensor).  B psi goes into a library workspace, the contraction's epilogue
+    subtracts hphi."""
+    n = psi.chromatic_number()
+    tcol = localT.t().contiguous()  # column-major
+    g = psi.grid_
+    check(lib().mgb_residual(lapOper.type_, _dt(psi.psi_), g.ref(), _p(psi.psi_), g.size(),
+                             _p(hphi.psi_), g.size(), _p(tcol), n, _p(res.psi_), g.size(), n,
+                             _p(xhalo_phi) if xhalo_phi is not None else None, _stream()))
+    res.incrementIterativeIndex()
+    return res
 
 
 class OrbitalsPreconditioning:

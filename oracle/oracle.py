@@ -477,6 +477,23 @@ class Ref:
         return res
 
 
+    # -- AndersonMix<Solution> of the reference -------------------------------------
+    def anderson_create(self, m, beta, x0):
+        self.lib.ref_anderson_create.restype = ctypes.c_void_p
+        x0 = np.ascontiguousarray(x0, np.float64)
+        return ctypes.c_void_p(self.lib.ref_anderson_create(
+            m, ctypes.c_double(beta), len(x0), _ptr(x0)))
+
+    def anderson_update(self, h, f, invs=1.0):
+        """One AndersonMix::update; returns (x after the update, mixed f)."""
+        f = np.array(f, np.float64)
+        x = np.empty_like(f)
+        self.lib.ref_anderson_update(h, _ptr(f), len(f), ctypes.c_double(invs), _ptr(x))
+        return x, f
+
+    def anderson_destroy(self, h):
+        self.lib.ref_anderson_destroy(h)
+
     # -- localization masks (GridMask / Map2Masks of the reference) ------------
     def masks_create(self, dims, ll, ghosts, mg_levels, subdivx, op, gids, centers, radii):
         """Reference mask objects for `gids` (GridMaskMult op 0 / GridMaskMax

@@ -592,6 +592,107 @@ def test_contractions_full_size_against_cublas(H):
 
 
 # --------------------------------------------------------------------------
+# residual assembly
+# --------------------------------------------------------------------------
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("bc", [(1, 1, 1), (0, 0, 0)])
+@pytest.mark.parametrize("dims", [(12, 8, 16), (7, 9, 10), (32, 32, 32)])
+def test_apply_b_bit_exact(H, port, dt, bc, dims):
+    """Lap::rhs on a no-ghost block = FDkernelRHS_4th_Mehr1 after
+    setDataWithGhosts + trade_boundaries, bit for bit."""
+    N, ll = 3, tuple(0.3 * d for d in dims)
+    phi = synthetic_orbitals(N, dims, dt)
+    grid = H.Grid(dims, ll, 1, bc)
+    out = torch.full((N,) + dims, float("nan"), dtype=TDT[dt], device="cuda")
+    H.LapFactory.createLap(grid, 0).rhs(dev(phi), out)
+    h = tuple(l / d for l, d in zip(ll, dims))
+    ref = port.fdkernel(100, port.trade_boundaries(phi, 1, bc), 1, h, rhs_ghosts=0)
+    assert bits_equal(host(out), ref)
+    # non-compact operators: B = 1
+    out2 = torch.empty_like(out)
+    H.LapFactory.createLap(H.Grid(dims, ll, 2, bc), 2).rhs(dev(phi), out2)
+    assert bits_equal(host(out2), phi)
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("lap_type", [0, 2])
+@pytest.mark.parametrize("N,dims", [(5, (12, 8, 16)), (37, (10, 12, 14)), (130, (16, 16, 24))])
+def test_residual_using_hphi(H, port, dt, lap_type, N, dims):
+    """res = (B psi) theta - H psi  (MGmol::computeResidualUsingHPhi) against the
+    oracle's sequence: B per orbital, MPgemmNN, axpy(-1)."""
+    ll = tuple(0.3 * d for d in dims)
+    phi = synthetic_orbitals(N, dims, dt)
+    v = synthetic_potential(dims)
+    theta = np.random.default_rng(3).standard_normal((N, N)) / np.sqrt(N)
+    theta = 0.5 * (theta + theta.T)
+    grid = H.Grid(dims, ll, H.ghosts_for(lap_type))
+    psi = H.Orbitals(grid, N, TDT[dt], dev(phi))
+    ham = H.Hamiltonian()
+    ham.setup(grid, lap_type)
+    ham.potential(H.Potentials(dev(v)))
+    hphi = ham.applyLocal(psi)
+    res = H.Orbitals(grid, N, TDT[dt])
+    H.computeResidualUsingHPhi(ham.lapOper(), psi, hphi, dev(theta), res)
+    got = host(res.psi())
+    hp = host(hphi.psi())
+    if lap_type == 0:
+        h = tuple(l / d for l, d in zip(ll, dims))
+        bphi = port.fdkernel(100, port.trade_boundaries(phi, 1), 1, h, rhs_ghosts=0)
+    else:
+        bphi = phi
+    ref = port.gemm_nn(bphi, theta) - hp          # MPgemmNN then axpy(-1., hphi)
+    scale = np.abs(ref).max()
+    tol = 1e-13 if dt == np.float64 else 2e-7
+    assert np.abs(got.astype(np.float64) - ref).max() <= tol * scale * max(1, N / 64)
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_diagonal_dot_products(H, port, dt):
+    """computeDiagonalElementsDotProduct: one launch for all orbitals, double
+    accumulation like MPdot."""
+    dims, N = (12, 10, 16), 7
+    a = synthetic_orbitals(N, dims, dt)
+    b = synthetic_orbitals(N, dims, dt, first=50)
+    grid = H.Grid(dims, (3.0, 2.5, 4.0), 1)
+    A = H.Orbitals(grid, N, TDT[dt], dev(a))
+    B = H.Orbitals(grid, N, TDT[dt], dev(b))
+    ss = host(A.computeDiagonalElementsDotProduct(B))
+    ex = grid.vel() * np.einsum("ixyz,ixyz->i", a.astype(np.float64), b.astype(np.float64))
+    assert np.abs(ss - ex).max() <= 1e-13 * np.abs(ex).max() * a[0].size ** 0.5
+    assert abs(A.dotProduct(B) - ex.sum()) <= 1e-12 * np.abs(ex).sum()
+
+
+def test_anderson_mix_on_orbitals(H):
+    """AndersonMix driven with device orbitals (C-ABI BLAS-1) equals the same
+    mixer on host numpy vectors (which tests/test_anderson_cpu.py pins to the
+    reference's AndersonMix)."""
+    from mgmol_b200.mixing import AndersonMix
+    from test_anderson_cpu import Vec
+    dims, N, m, beta = (8, 8, 8), 3, 3, 0.8
+    grid = H.Grid(dims, (2.0, 2.0, 2.0), 1)
+    rng = np.random.default_rng(9)
+    x0 = rng.standard_normal((N,) + dims)
+    amat = np.abs(rng.standard_normal((N,) + dims)) + 0.5      # diagonal operator
+    X = H.Orbitals(grid, N, torch.float64, dev(x0))
+    W = H.Orbitals(grid, N, torch.float64)
+    mix = AndersonMix(m, beta, X, lambda o: o.clone())
+    xv, wv = Vec(x0.ravel()), Vec(x0.ravel())
+    Vec.invs = grid.vel()
+    mixv = AndersonMix(m, beta, xv, lambda v: Vec(v.u))
+    for it in range(8):
+        xh = host(X.psi())
+        assert np.abs(xh.ravel() - xv.u).max() <= 1e-11 * np.abs(xv.u).max(), it
+        lam = float((xh * amat * xh).sum() / (xh * xh).sum())
+        r = 0.3 * (lam * xh - amat * xh)
+        F = H.Orbitals(grid, N, torch.float64, dev(r))
+        mix.update(F, W)
+        lamv = float((xv.u * amat.ravel() * xv.u).sum() / (xv.u @ xv.u))
+        fv = Vec(0.3 * (lamv * xv.u - amat.ravel() * xv.u))
+        mixv.update(fv, wv)
+    assert mix.mm_ == mixv.mm_
+
+
+# --------------------------------------------------------------------------
 # full-size, size-independent properties (BASELINE configs: 128^3 and 256^3)
 # --------------------------------------------------------------------------
 @pytest.mark.parametrize("dt", [np.float64, np.float32])
