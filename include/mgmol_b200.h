@@ -297,6 +297,12 @@ double mgb_gamma(double inv_diag, int mg_levels, double vmax, double small_eig);
 int mgb_gemm_tn(int dtype, int m, int n, size_t k, double alpha, const void* A,
     size_t lda, const void* B, size_t ldb, double beta, double* C, int ldc,
     void* stream);
+/* ORBDTYPE float operands: 0 (default) = FP32-class tensor tiles, error-
+ * compensated 3xTF32 with chunked exact accumulation (agrees with the
+ * reference's double-accumulating loops to ~1e-6 of |a||b|, bar 1e-5); 1 = the
+ * FP64 DMMA kernel on widened operands (the reference's products and sums).
+ * Process-wide; applies to mgb_gemm_tn / mgb_syrk_t and their slab variants.  */
+int mgb_set_f32_contraction(int mode);
 /* Gram: C = alpha * A^T A (full symmetric matrix written, as
  * syrk('l','t') + fillUpperWithLower do, src/local_matrices/LocalMatrices.cc:
  * 210-247)                                                                  */

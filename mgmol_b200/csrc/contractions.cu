@@ -351,13 +351,264 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tn(TnWork W, int m, int n,
     }
 }
 
+// ---------------------------------------------------------------------------
+// ORBDTYPE float on the FP32-class tensor path: error-compensated 3xTF32
+// (mma.sync.m16n8k8.tf32).  Each operand is split a = a_hi + a_lo into two
+// TF32 numbers and a*b is formed as a_lo*b_hi + a_hi*b_lo + a_hi*b_hi, which
+// keeps ~21 bits of every product; the tensor core accumulates in FP32 over one
+// 32-point slab only, slab sums are added in FP32 over at most 64 slabs and
+// those sums in double, so the long K = npt reduction behaves like the
+// reference's double accumulation (MPgemm float path, src/linear_algebra/
+// mputils.cc:763-774) to ~1e-6 of |a||b| -- inside the 1e-5 FP32 bar of the
+// north star; mgb_set_f32_contraction(1) selects the DMMA kernel above, whose
+// products and sums are exactly those double ones.
+// Same stream-K decomposition, same fix-up; the half-work trick of diagonal
+// Gram tiles pairs 16x16 subtiles here.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t to_tf32(float x)
+{
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4],
+    const uint32_t (&b)[2])
+{
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 "
+                 "{%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+constexpr int KC32  = 32;            // K slab of the float kernel
+constexpr int P32   = KC32 + PADK;   // smem row pitch (floats): conflict-free fragments
+constexpr int ST32  = 4;             // cp.async ring depth
+
+// one k8 step of a warp (32 x 32 = 2 m16 x 4 n8): MODE 0 all blocks; on diagonal
+// warp blocks MODE 1 = even step (16x16 blocks with i >= j), MODE 2 = odd (i <= j)
+template <int MODE>
+__device__ __forceinline__ void tn_k8_tf32(float (&c)[2][4][4], const float* as, const float* bs)
+{
+    uint32_t ah[2][4], al[2][4], bh[4][2], bl[4][2];
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+        {
+            // a0 (g, t)  a1 (g+8, t)  a2 (g, t+4)  a3 (g+8, t+4)
+            const float v = as[(i * 16 + (r & 1) * 8) * P32 + (r >> 1) * 4];
+            ah[i][r]      = to_tf32(v);
+            al[i][r]      = to_tf32(v - __uint_as_float(ah[i][r]));
+        }
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+#pragma unroll
+        for (int r = 0; r < 2; r++)
+        {
+            // b0 (k = t, n = g)  b1 (k = t+4, n = g)
+            const float v = bs[(j * 8) * P32 + r * 4];
+            bh[j][r]      = to_tf32(v);
+            bl[j][r]      = to_tf32(v - __uint_as_float(bh[j][r]));
+        }
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+        {
+            const int J = j >> 1; // 16-wide block column inside the warp tile
+            if (MODE == 0 || (MODE == 1 && i >= J) || (MODE == 2 && i <= J))
+            {
+                mma_tf32(c[i][j], al[i], bh[j]);
+                mma_tf32(c[i][j], ah[i], bl[j]);
+                mma_tf32(c[i][j], ah[i], bh[j]);
+            }
+        }
+}
+
+constexpr int FOLD2 = 64; // level-1 sums folded into the double sums every FOLD2 slabs
+
+template <bool DIAG>
+__device__ __forceinline__ void tn_segment_tf32(double* __restrict__ dst, float* As, float* Bs,
+    const float* A, long long lda, const float* B, long long ldb, int m0, int m, int n0, int n,
+    long long it0, long long it1, long long kend, int tid, int wm, int wn, int g, int t)
+{
+    const int nit = (int)(it1 - it0);
+    // three levels: c = tensor-core FP32 sums of one slab (32 points), hi = FP32
+    // sums of up to FOLD2 slabs, dst = double sums (this segment's partial slot,
+    // L2-resident, touched once every FOLD2 slabs)
+    float c[2][4][4], hi[2][4][4];
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+#pragma unroll
+            for (int e = 0; e < 4; e++)
+                c[i][j][e] = hi[i][j][e] = 0.f;
+    bool first = true;
+    int pending = 0;
+    __syncthreads();
+#pragma unroll
+    for (int s = 0; s < ST32 - 1; s++)
+    {
+        if (s < nit)
+        {
+            load_kmajor<float, KC32>(As + s * 128 * P32, A, lda, m0, m, (it0 + s) * KC32, kend, tid);
+            load_kmajor<float, KC32>(Bs + s * 128 * P32, B, ldb, n0, n, (it0 + s) * KC32, kend, tid);
+        }
+        cp_async_commit();
+    }
+    for (int kt = 0; kt < nit; kt++)
+    {
+        cp_async_wait<ST32 - 2>();
+        __syncthreads();
+        {
+            const int nx = kt + ST32 - 1;
+            if (nx < nit)
+            {
+                const int s = nx % ST32;
+                load_kmajor<float, KC32>(
+                    As + s * 128 * P32, A, lda, m0, m, (it0 + nx) * KC32, kend, tid);
+                load_kmajor<float, KC32>(
+                    Bs + s * 128 * P32, B, ldb, n0, n, (it0 + nx) * KC32, kend, tid);
+            }
+            cp_async_commit();
+        }
+        const float* as = As + (kt % ST32) * 128 * P32 + (wm * 32 + g) * P32 + t;
+        const float* bs = Bs + (kt % ST32) * 128 * P32 + (wn * 32 + g) * P32 + t;
+        if (!DIAG)
+        {
+#pragma unroll
+            for (int kk = 0; kk < KC32 / 8; kk++)
+                tn_k8_tf32<0>(c, as + kk * 8, bs + kk * 8);
+        }
+        else if (wm > wn)
+        {
+#pragma unroll
+            for (int kk = 0; kk < KC32 / 8; kk += 2)
+                tn_k8_tf32<0>(c, as + kk * 8, bs + kk * 8);
+        }
+        else if (wm < wn)
+        {
+#pragma unroll
+            for (int kk = 1; kk < KC32 / 8; kk += 2)
+                tn_k8_tf32<0>(c, as + kk * 8, bs + kk * 8);
+        }
+        else
+        {
+#pragma unroll
+            for (int kk = 0; kk < KC32 / 8; kk += 2)
+            {
+                tn_k8_tf32<1>(c, as + kk * 8, bs + kk * 8);
+                tn_k8_tf32<2>(c, as + (kk + 1) * 8, bs + (kk + 1) * 8);
+            }
+        }
+        // level 1: slab sums into the FP32 running sums
+#pragma unroll
+        for (int i = 0; i < 2; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+#pragma unroll
+                for (int e = 0; e < 4; e++)
+                {
+                    hi[i][j][e] = __fadd_rn(hi[i][j][e], c[i][j][e]);
+                    c[i][j][e]  = 0.f;
+                }
+        if (++pending == FOLD2 || kt == nit - 1)
+        {
+            // level 2: into the double sums
+#pragma unroll
+            for (int i = 0; i < 2; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+#pragma unroll
+                    for (int e = 0; e < 4; e++)
+                    {
+                        const int ml = wm * 32 + i * 16 + g + 8 * (e >> 1);
+                        const int nl = wn * 32 + j * 8 + 2 * t + (e & 1);
+                        double* d    = dst + (size_t)nl * BM + ml;
+                        *d           = (first ? 0. : *d) + (double)hi[i][j][e];
+                        hi[i][j][e]  = 0.f;
+                    }
+            first   = false;
+            pending = 0;
+        }
+    }
+    cp_async_wait<0>();
+}
+
+template <bool SYRK>
+__global__ void __launch_bounds__(NTHREADS, 1) k_gemm_tn_tf32(TnWork W, int m, int n,
+    long long k, const float* __restrict__ A, long long lda, long long strideA,
+    const float* __restrict__ B, long long ldb, long long strideB, double alpha, double beta,
+    double* __restrict__ C, int ldc, long long strideC, double* __restrict__ partial)
+{
+    extern __shared__ __align__(16) unsigned char smraw[];
+    float* As = reinterpret_cast<float*>(smraw);
+    float* Bs = As + ST32 * 128 * P32;
+
+    const int gcta = blockIdx.x;
+    long long b0, b1;
+    tn_cta_bounds(W, gcta, b0, b1);
+    if (b1 <= b0) return;
+    const int u_first = tn_tile_of(W, b0), u_last = tn_tile_of(W, b1 - 1);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp >> 2, wn = warp & 3;
+    const int g = lane >> 2, t = lane & 3;
+
+    for (int u = u_first; u <= u_last; u++)
+    {
+        long long it0, it1;
+        tn_seg(W, u, b0, b1, it0, it1);
+        if (it0 >= it1) continue;
+        int batch, tile_m, tile_n;
+        tn_decode<SYRK>(W, u, batch, tile_m, tile_n);
+        const int m0 = tile_m * BM, n0 = tile_n * BN;
+        const bool diag = SYRK && u < W.ND;
+        const float* Ab = A + (long long)batch * strideA;
+        const float* Bb = B + (long long)batch * strideB;
+        double* dst = partial + ((size_t)gcta * W.smax + (size_t)(u - u_first)) * (BM * BN);
+        if (diag)
+            tn_segment_tf32<true>(dst, As, Bs, Ab, lda, Bb, ldb, m0, m, n0, n, it0, it1, k, tid,
+                wm, wn, g, t);
+        else
+            tn_segment_tf32<false>(dst, As, Bs, Ab, lda, Bb, ldb, m0, m, n0, n, it0, it1, k, tid,
+                wm, wn, g, t);
+
+        // a whole off-diagonal tile: finish it here (each thread re-reads the
+        // sums it wrote itself); everything else is left to the fix-up
+        if (!diag && it0 == 0 && it1 == W.nkt)
+        {
+            double* Cb = C + (long long)batch * strideC;
+#pragma unroll
+            for (int i = 0; i < 2; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+#pragma unroll
+                    for (int e = 0; e < 4; e++)
+                    {
+                        const int ml = wm * 32 + i * 16 + g + 8 * (e >> 1);
+                        const int nl = wn * 32 + j * 8 + 2 * t + (e & 1);
+                        const int mm = m0 + ml, nn = n0 + nl;
+                        if (mm < m && nn < n)
+                        {
+                            const double old
+                                = (beta == 0.) ? 0. : beta * Cb[(size_t)nn * ldc + mm];
+                            const double val = alpha * dst[(size_t)nl * BM + ml] + old;
+                            Cb[(size_t)nn * ldc + mm] = val;
+                            if (SYRK) Cb[(size_t)mm * ldc + nn] = val;
+                        }
+                    }
+        }
+    }
+}
+
 // Adds the partial slots of every tile that was not written directly, in CTA
 // order; for diagonal Gram tiles it also folds the mirrored half-sums,
 // S(r, c) = P(r, c) + P(c, r) unless both lie in the same 8x8 subtile.
 // grid: (tiles, 16 column blocks of 8), block 128 x 2.
 template <bool SYRK>
 __global__ void k_tn_fixup(TnWork W, int m, int n, const double* __restrict__ partial,
-    double alpha, double beta, double* __restrict__ C, int ldc, long long strideC)
+    double alpha, double beta, double* __restrict__ C, int ldc, long long strideC, int sub_shift)
 {
     const int u = blockIdx.x;
     const long long s0 = tn_tile_start(W, u);
@@ -376,7 +627,8 @@ __global__ void k_tn_fixup(TnWork W, int m, int n, const double* __restrict__ pa
     {
         const int nn = tile_n * BN + nl;
         if (diag && nl > ml) continue; // lower triangle of the diagonal tile
-        const bool fold = diag && (ml >> 3) != (nl >> 3);
+        // mirrored half-sums are folded across subtiles (8x8 DMMA / 16x16 TF32)
+        const bool fold = diag && (ml >> sub_shift) != (nl >> sub_shift);
         double s = 0.;
         bool any = false;
         for (int g = gf; g <= gl; g++)
@@ -604,6 +856,8 @@ __global__ void k_gemm_nn_ref(long long npt, int n, int k, const T* Phi, long lo
     *o     = base + (T)s;
 }
 
+static int g_f32_exact = 0; // 0: 3xTF32 tensor tiles for float operands, 1: DMMA (double products)
+
 static int num_sms()
 {
     static int n = 0;
@@ -643,9 +897,12 @@ static int gemm_tn_t(bool syrk, int m, int n, size_t k, double alpha, const T* A
     W.tm     = (m + BM - 1) / BM;
     W.tn     = (n + BN - 1) / BN;
     W.nbatch = nbatch;
+    const bool tf32 = sizeof(T) == 4 && !g_f32_exact;
+    const int sub_shift = tf32 ? 4 : 3;
     // slab width / ring depth: 16 x 4 or 32 x 3 (MGB_TN_KC, tuning hook)
     int kcv = 32;
     if (const char* env = getenv("MGB_TN_KC")) kcv = atoi(env) == 16 ? 16 : 32;
+    if (tf32) kcv = KC32;
     const int st_ = kcv == 32 ? 3 : 4;
     W.nkt    = (long long)((k + kcv - 1) / kcv);
     // cost of one k-iteration: a diagonal Gram tile issues 136 of the 256 DMMAs
@@ -687,6 +944,31 @@ static int gemm_tn_t(bool syrk, int m, int n, size_t k, double alpha, const T* A
     double* partial
         = (double*)scratch(2, (size_t)W.G * W.smax * BM * BN * sizeof(double));
     if (!partial) return MGB_ECUDA;
+    if (tf32)
+    {
+        const size_t smem32 = (size_t)2 * ST32 * 128 * P32 * sizeof(float);
+        if (syrk)
+        {
+            auto kern = k_gemm_tn_tf32<true>;
+            MGB_CUDA(cudaFuncSetAttribute(
+                kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32));
+            kern<<<W.G, NTHREADS, smem32, st>>>(W, m, n, (long long)k, (const float*)A,
+                (long long)lda, (long long)strideA, (const float*)B, (long long)ldb,
+                (long long)strideB, alpha, beta, C, ldc, (long long)strideC, partial);
+        }
+        else
+        {
+            auto kern = k_gemm_tn_tf32<false>;
+            MGB_CUDA(cudaFuncSetAttribute(
+                kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32));
+            kern<<<W.G, NTHREADS, smem32, st>>>(W, m, n, (long long)k, (const float*)A,
+                (long long)lda, (long long)strideA, (const float*)B, (long long)ldb,
+                (long long)strideB, alpha, beta, C, ldc, (long long)strideC, partial);
+        }
+        MGB_LAUNCHED("k_gemm_tn_tf32");
+    }
+    else
+    {
     const size_t smem = (size_t)2 * st_ * 128 * (kcv + PADK) * sizeof(T);
 #define MGB_TN_LAUNCH(SY, KV, STV)                                                        \
     {                                                                                     \
@@ -713,13 +995,14 @@ static int gemm_tn_t(bool syrk, int m, int n, size_t k, double alpha, const T* A
     }
 #undef MGB_TN_LAUNCH
     MGB_LAUNCHED("k_gemm_tn");
+    }
     dim3 fgrid((unsigned)W.NT, 16), fblock(128, 2);
     if (syrk)
         k_tn_fixup<true><<<fgrid, fblock, 0, st>>>(
-            W, m, n, partial, alpha, beta, C, ldc, (long long)strideC);
+            W, m, n, partial, alpha, beta, C, ldc, (long long)strideC, sub_shift);
     else
         k_tn_fixup<false><<<fgrid, fblock, 0, st>>>(
-            W, m, n, partial, alpha, beta, C, ldc, (long long)strideC);
+            W, m, n, partial, alpha, beta, C, ldc, (long long)strideC, sub_shift);
     MGB_LAUNCHED("k_tn_fixup");
     return MGB_OK;
 }
@@ -799,6 +1082,13 @@ using namespace mgb;
 
 extern "C"
 {
+
+int mgb_set_f32_contraction(int mode)
+{
+    MGB_REQUIRE(mode == 0 || mode == 1, "mgb_set_f32_contraction: mode %d", mode);
+    g_f32_exact = mode;
+    return MGB_OK;
+}
 
 int mgb_gemm_tn(int dtype, int m, int n, size_t k, double alpha, const void* A,
     size_t lda, const void* B, size_t ldb, double beta, double* C, int ldc, void* stream)

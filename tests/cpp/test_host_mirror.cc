@@ -272,7 +272,7 @@ static int run_localized(const int lap_type, const int op, const double mg_tol)
             serr = std::fmax(serr, std::fabs(ss[iloc * N * N + i] - ss_ref[i]));
         }
     }
-    const double stol = sizeof(T) == 8 ? 1e-12 : 1e-6;
+    const double stol = sizeof(T) == 8 ? 1e-12 : 3e-6; // float: 3xTF32 tensor tiles
     std::printf("lap %2d %s op %d  slab Gram   rel err %.3e (tol %.0e)\n", lap_type,
         sizeof(T) == 8 ? "f64" : "f32", op, serr / smax, stol);
     if (!(serr <= stol * smax)) fails++;

@@ -187,7 +187,7 @@ def test_locgrid_contractions_per_slab(H, port, dt):
     orb = H.LocGridOrbitals(grid, numst, gid_table, TDT[dt], dev(phi))
     oth = H.LocGridOrbitals(grid, numst, gid_table, TDT[dt], dev(other))
     s0 = dims[0] // subdivx
-    tol = 1e-12 if dt == np.float64 else 1e-6
+    tol = 1e-12 if dt == np.float64 else 3e-6   # float: 3xTF32 tensor tiles
     ss = host(orb.getLocalOverlap())
     pp = host(orb.computeLocalProduct(oth))
     pt = host(orb.computeLocalProduct(oth, transpose=True))
