@@ -909,6 +909,7 @@ static int gemm_tn_t(bool syrk, int m, int n, size_t k, double alpha, const T* A
     // of a full tile but stages the same operands (10/16 measured best on B200)
     W.cf = 16;
     W.cd = 10;
+    if (sizeof(T) == 4 && !g_f32_exact) W.cd = 12; // 3xTF32: 16x16 pairing, measured best
     if (const char* env = getenv("MGB_SYRK_DIAG_COST"))
     {
         const int c = atoi(env);
