@@ -152,7 +152,9 @@ __global__ void __launch_bounds__(MAXT, 1) k_mg_jacobi(const __grid_constant__ J
         // ---------------------------- TMA producer ----------------------------
         if (tid != 0) return;
         unsigned char* stages = smem + kMgBarBytes;
-        const uint64_t pol    = policy_evict_first();
+        // SCALE: the tile is f, which the consumers read again from L2 a few
+        // planes later as the right-hand side -> keep it there
+        const uint64_t pol    = SCALE ? policy_evict_last() : policy_evict_first();
         int norb              = P.nfunc - orb0;
         if (norb > P.NB) norb = P.NB;
         int ylo = y0 - G, yhi = y0 + P.TY;
@@ -275,24 +277,12 @@ __global__ void __launch_bounds__(MAXT, 1) k_mg_jacobi(const __grid_constant__ J
     const long long pt0    = (long long)(y0 + rr0) * P.nz + z0;
 
     const float sh = P.sh, sl = P.sl, oh = P.oh, ol = P.ol;
-    auto ldrow = [&](uint32_t a, float(&o)[4]) {
-        lds4(a, o);
-        if (SCALE)
-        {
-#pragma unroll
-            for (int e = 0; e < 4; e++)
-                o[e] = mul_split(sh, sl, o[e]);
-        }
-    };
-    auto ld1 = [&](uint32_t a, float m) {
-        float x = lds1(a);
-        if (SCALE) x = mul_split(sh, sl, x);
-        return x * m;
-    };
+    auto ldrow = [&](uint32_t a, float(&o)[4]) { lds4(a, o); };
+    auto ld1   = [&](uint32_t a, float m) { return lds1(a) * m; };
 
     // right-hand side of the first output plane (see the prefetch below)
     float4 fnext[RY];
-    if (!SCALE && active)
+    if (active)
     {
         const float* fp = P.f + (long long)orb * P.ld_f + (long long)xb * plane + pt0;
 #pragma unroll
@@ -307,6 +297,28 @@ __global__ void __launch_bounds__(MAXT, 1) k_mg_jacobi(const __grid_constant__ J
     for (int it = 0; it < nplanes; it++)
     {
         mbar_wait(&full[st_new], par_new);
+        if constexpr (SCALE)
+        {
+            // the tile is f: form v = s * f once per element, in place, as the
+            // plane arrives (every tap then reads v); the threads of one
+            // function's group share the work and meet at a named barrier
+            unsigned char* tile
+                = smem + kMgBarBytes + (size_t)st_new * P.stage_bytes + (size_t)grp * P.tile_bytes;
+            const int nvec = P.tile_bytes >> 4;
+            for (int i = lt; i < nvec; i += P.tpo)
+            {
+                float4* p4 = reinterpret_cast<float4*>(tile) + i;
+                float4 x   = *p4;
+                x.x        = mul_split(sh, sl, x.x);
+                x.y        = mul_split(sh, sl, x.y);
+                x.z        = mul_split(sh, sl, x.z);
+                x.w        = mul_split(sh, sl, x.w);
+                *p4        = x;
+            }
+            // later TMA writes into this stage must not pass these stores
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(P.tpo) : "memory");
+        }
         if (it >= 2 * G)
         {
             const int q = xb + it - 2 * G; // output plane
@@ -344,23 +356,12 @@ __global__ void __launch_bounds__(MAXT, 1) k_mg_jacobi(const __grid_constant__ J
                     }
                 }
 
-                // Right-hand side.  SCALE: the tile IS f (unscaled), read it
-                // back from shared memory.  Otherwise the values of this plane
-                // were requested one iteration ago (fnext) and the next
-                // plane's are requested now, so the global loads are in flight
-                // during a whole plane of shared-memory work.
+                // Right-hand side: the values of this plane were requested one
+                // iteration ago (fnext) and the next plane's are requested
+                // now, so the global loads are in flight during a whole plane
+                // of shared-memory work.  (SCALE: the tile was f but now holds
+                // s * f; f comes from L2, where the TMA load just put it.)
                 float4 fv[RY];
-                if constexpr (SCALE)
-                {
-#pragma unroll
-                    for (int r = 0; r < RY; r++)
-                    {
-                        float t[4];
-                        lds4(tb[G] + rowoff[r + G] + zoff, t);
-                        fv[r] = make_float4(t[0], t[1], t[2], t[3]);
-                    }
-                }
-                else
                 {
 #pragma unroll
                     for (int r = 0; r < RY; r++)
@@ -445,13 +446,6 @@ __global__ void __launch_bounds__(MAXT, 1) k_mg_jacobi(const __grid_constant__ J
                         float L2, L1, R1, R2;
                         lds2(tb[2] + ro + zloff, L2, L1);
                         lds2(tb[2] + ro + zroff, R1, R2);
-                        if (SCALE)
-                        {
-                            L2 = mul_split(sh, sl, L2);
-                            L1 = mul_split(sh, sl, L1);
-                            R1 = mul_split(sh, sl, R1);
-                            R2 = mul_split(sh, sl, R2);
-                        }
                         L2 *= ml;
                         L1 *= ml;
                         R1 *= mr;
@@ -722,20 +716,21 @@ __global__ void k_mg_prolong_correct(int nx, int ny, int nz, int perx, int pery,
     float* __restrict__ v, long long ldv, MaskView mask, const float* __restrict__ coarse_e,
     const int* __restrict__ map_e, int f0)
 {
+    // one thread: the 2 x 2 x 4 fine brick above coarse (cx0, cy0, cz0..cz0+1); the
+    // four coarse rows it needs are loaded once and shared by the 16 fine points
     const int nzv = nz >> 2;
+    const int nxc = nx >> 1, nyc = ny >> 1, nzc = nz >> 1;
     const int tz  = (nzv + blockDim.x - 1) / blockDim.x;
     const int zv  = (blockIdx.x % tz) * blockDim.x + threadIdx.x;
-    const int y   = (blockIdx.x / tz) * blockDim.y + threadIdx.y;
-    const int x   = blockIdx.y;
+    const int cy0 = (blockIdx.x / tz) * blockDim.y + threadIdx.y;
+    const int cx0 = blockIdx.y;
     const int f   = blockIdx.z;
-    if (zv >= nzv || y >= ny) return;
-    const int nxc = nx >> 1, nyc = ny >> 1, nzc = nz >> 1;
-    const int z0 = zv * 4;
-    const int ox = x & 1, oy = y & 1;
-    const int cx0 = x >> 1, cy0 = y >> 1, cz0 = z0 >> 1;
+    if (zv >= nzv || cy0 >= nyc) return;
+    const int z0  = zv * 4;
+    const int cz0 = z0 >> 1;
     int cx1 = cx0 + 1, cy1 = cy0 + 1, cz2 = cz0 + 2;
     float mx = 1.f, my = 1.f, mz = 1.f;
-    const float* C = coarse + (long long)f * ldc;
+    const float* C   = coarse + (long long)f * ldc;
     const float* Cx1 = C; // block holding coarse plane cx1
     if (cx1 == nxc)
     {
@@ -768,68 +763,76 @@ __global__ void k_mg_prolong_correct(int nx, int ny, int nz, int perx, int pery,
         o[2] = __ldg(r + cz2) * (m * mz);
     };
     row3(C, cx0, cy0, 1.f, c00);
-    if (oy) row3(C, cx0, cy1, my, c01);
-    if (ox) row3(Cx1, cx1, cy0, mx, c10);
-    if (ox && oy) row3(Cx1, cx1, cy1, mx * my, c11);
-    float w[4];
+    row3(C, cx0, cy1, my, c01);
+    row3(Cx1, cx1, cy0, mx, c10);
+    row3(Cx1, cx1, cy1, mx * my, c11);
+
 #pragma unroll
-    for (int e = 0; e < 4; e++)
-    {
-        const int k  = e >> 1;  // lower coarse index relative to cz0
-        const bool oz = e & 1;
-        // names follow k_extend3D: c[0]=lower corner, c[1]=+z, c[Y]=+y, c[X]=+x
-        const float a0 = c00[k], a1 = c00[k + 1];
-        float val;
-        if (!ox && !oy)
-            val = oz ? 0.5f * (a0 + a1) : a0;
-        else if (!ox && oy)
+    for (int ox = 0; ox < 2; ox++)
+#pragma unroll
+        for (int oy = 0; oy < 2; oy++)
         {
-            const float y0v = c01[k], y1v = c01[k + 1];
-            val = oz ? 0.25f * (((y1v + a1) + y0v) + a0) : 0.5f * (y0v + a0);
+            const int x = 2 * cx0 + ox, y = 2 * cy0 + oy;
+            float w[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++)
+            {
+                const int k   = e >> 1; // lower coarse index relative to cz0
+                const bool oz = e & 1;
+                // names follow k_extend3D: c[0]=lower corner, c[1]=+z, c[Y]=+y, c[X]=+x
+                const float a0 = c00[k], a1 = c00[k + 1];
+                float val;
+                if (!ox && !oy)
+                    val = oz ? 0.5f * (a0 + a1) : a0;
+                else if (!ox && oy)
+                {
+                    const float y0v = c01[k], y1v = c01[k + 1];
+                    val = oz ? 0.25f * (((y1v + a1) + y0v) + a0) : 0.5f * (y0v + a0);
+                }
+                else if (ox && !oy)
+                {
+                    const float x0v = c10[k], x1v = c10[k + 1];
+                    val = oz ? 0.25f * (((x1v + x0v) + a1) + a0) : 0.5f * (x0v + a0);
+                }
+                else
+                {
+                    const float y0v = c01[k], y1v = c01[k + 1];
+                    const float x0v = c10[k], x1v = c10[k + 1];
+                    const float q0v = c11[k], q1v = c11[k + 1];
+                    val = oz ? 0.125f
+                                   * (((((((q1v + q0v) + x1v) + x0v) + y1v) + y0v) + a1) + a0)
+                             : 0.25f * (((q0v + x0v) + y0v) + a0);
+                }
+                w[e] = val;
+            }
+            if (mask.off)
+            {
+                // gfv_work_[level]->app_mask(level) on P e  (Preconditioning.cc:204)
+                const int iloc = x / mask.sub0;
+                const int mo   = __ldg(mask.off + (long long)f * mask.subdivx + iloc);
+                if (mo == -2)
+                    w[0] = w[1] = w[2] = w[3] = 0.f;
+                else if (mo >= 0)
+                {
+                    const float4 m = __ldg(reinterpret_cast<const float4*>(mask.pool
+                        + (long long)mo * mask.slab
+                        + ((long long)(x - iloc * mask.sub0) * ny + y) * nz + z0));
+                    w[0] = mask_apply(mask.op, w[0], m.x);
+                    w[1] = mask_apply(mask.op, w[1], m.y);
+                    w[2] = mask_apply(mask.op, w[2], m.z);
+                    w[3] = mask_apply(mask.op, w[3], m.w);
+                }
+            }
+            float* pv = v + (long long)f * ldv + ((long long)x * ny + y) * nz + z0;
+            float4 vv = *reinterpret_cast<float4*>(pv);
+            vv.x = __fsub_rn(vv.x, w[0]);
+            vv.y = __fsub_rn(vv.y, w[1]);
+            vv.z = __fsub_rn(vv.z, w[2]);
+            vv.w = __fsub_rn(vv.w, w[3]);
+            if ((zlx && x == 0) || (zly && y == 0)) vv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (zlz && z0 == 0) vv.x = 0.f;
+            *reinterpret_cast<float4*>(pv) = vv;
         }
-        else if (ox && !oy)
-        {
-            const float x0v = c10[k], x1v = c10[k + 1];
-            val = oz ? 0.25f * (((x1v + x0v) + a1) + a0) : 0.5f * (x0v + a0);
-        }
-        else
-        {
-            const float y0v = c01[k], y1v = c01[k + 1];
-            const float x0v = c10[k], x1v = c10[k + 1];
-            const float q0v = c11[k], q1v = c11[k + 1];
-            val = oz ? 0.125f
-                           * (((((((q1v + q0v) + x1v) + x0v) + y1v) + y0v) + a1) + a0)
-                     : 0.25f * (((q0v + x0v) + y0v) + a0);
-        }
-        w[e] = val;
-    }
-    if (mask.off)
-    {
-        // gfv_work_[level]->app_mask(level) on P e  (Preconditioning.cc:204)
-        const int iloc = x / mask.sub0;
-        const int mo   = __ldg(mask.off + (long long)f * mask.subdivx + iloc);
-        if (mo == -2)
-            w[0] = w[1] = w[2] = w[3] = 0.f;
-        else if (mo >= 0)
-        {
-            const float4 m = __ldg(reinterpret_cast<const float4*>(mask.pool
-                + (long long)mo * mask.slab
-                + ((long long)(x - iloc * mask.sub0) * ny + y) * nz + z0));
-            w[0] = mask_apply(mask.op, w[0], m.x);
-            w[1] = mask_apply(mask.op, w[1], m.y);
-            w[2] = mask_apply(mask.op, w[2], m.z);
-            w[3] = mask_apply(mask.op, w[3], m.w);
-        }
-    }
-    float* pv = v + (long long)f * ldv + ((long long)x * ny + y) * nz + z0;
-    float4 vv = *reinterpret_cast<float4*>(pv);
-    vv.x = __fsub_rn(vv.x, w[0]);
-    vv.y = __fsub_rn(vv.y, w[1]);
-    vv.z = __fsub_rn(vv.z, w[2]);
-    vv.w = __fsub_rn(vv.w, w[3]);
-    if ((zlx && x == 0) || (zly && y == 0)) vv = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (zlz && z0 == 0) vv.x = 0.f;
-    *reinterpret_cast<float4*>(pv) = vv;
 }
 
 // ORBDTYPE double -> float copy of the residual (OrbitalsPreconditioning.cc:103)
@@ -1191,7 +1194,7 @@ int mg_prolong_correct(const mgb_grid& fine, const float* coarse, size_t ldc, fl
     for (int f0 = 0; f0 < nfunc; f0 += 65535)
     {
         const int nf = (nfunc - f0 < 65535) ? nfunc - f0 : 65535;
-        const VecLaunch L = vec_launch(nx, ny, nz / 4, nf);
+        const VecLaunch L = vec_launch(nx / 2, ny / 2, nz / 4, nf);
         k_mg_prolong_correct<<<L.grid, L.block, 0, st>>>(nx, ny, nz, fine.bc[0] == 1,
             fine.bc[1] == 1, fine.bc[2] == 1, zero_low[0], zero_low[1], zero_low[2],
             coarse + (size_t)f0 * ldc, (long long)ldc, v + (size_t)f0 * ldv, (long long)ldv,
