@@ -22,6 +22,7 @@
 #define MGMOL_B200_HPP
 
 #include <cassert>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <memory>
@@ -353,6 +354,42 @@ public:
         MGB_CHECK(mgb_scal(dtype_of<T>::value, psi_.size(), alpha, getPsi(), stream));
         incrementIterativeIndex();
     }
+    // Orbitals::assign and operator-= (src/BlockVector.cc:289-299, 303-311)
+    void assign(const ExtendedGridOrbitals<T>& x, void* stream = nullptr)
+    {
+        MGB_CHECK(mgb_copy_dev(getPsi(), x.getPsi(), psi_.size() * sizeof(T), stream));
+        incrementIterativeIndex();
+    }
+    ExtendedGridOrbitals<T>& operator-=(const ExtendedGridOrbitals<T>& x)
+    {
+        MGB_CHECK(mgb_axpy(dtype_of<T>::value, psi_.size(), -1., x.getPsi(), getPsi(), nullptr));
+        incrementIterativeIndex();
+        return *this;
+    }
+    // computeDiagonalElementsDotProduct (src/ExtendedGridOrbitals.cc:1085-1106):
+    // ss_dev[i] = vel <phi_i, psi_i>, one launch for all orbitals
+    void computeDiagonalElementsDotProduct(const ExtendedGridOrbitals<T>& x, double* ss_dev,
+        mgb_comm* comm = nullptr, void* stream = nullptr) const
+    {
+        MGB_CHECK(mgb_dot_cols(dtype_of<T>::value, numpt_, numst_, grid_.vel(), getPsi(), lda_,
+            x.getPsi(), x.getLda(), ss_dev, stream));
+        if (comm) MGB_CHECK(mgb_allreduce_sum_f64(comm, ss_dev, (size_t)numst_, stream));
+    }
+    // dotProductDiagonal (src/ExtendedGridOrbitals.cc:1205-1213) with the
+    // diagonal of S^-1 (host array of numst weights, null = ones)
+    double dotProduct(const ExtendedGridOrbitals<T>& x, const double* inv_s_diag = nullptr,
+        mgb_comm* comm = nullptr)
+    {
+        if (dots_.size() < (size_t)numst_) dots_.allocate((size_t)numst_);
+        computeDiagonalElementsDotProduct(x, dots_.data(), comm, nullptr);
+        std::vector<double> ss((size_t)numst_);
+        dots_.copy_to_host(ss.data(), ss.size());
+        MGB_CHECK(mgb_stream_sync(nullptr));
+        double s = 0.;
+        for (int i = 0; i < numst_; i++)
+            s += (inv_s_diag ? inv_s_diag[i] : 1.) * ss[i];
+        return s;
+    }
     // computeGram / getLocalOverlap (src/ExtendedGridOrbitals.cc:985-1010,
     // 1138-1162): ss_dev(numst x numst, column-major double) = vel Phi^T Phi
     void computeGram(double* ss_dev, mgb_comm* comm = nullptr, void* stream = nullptr) const
@@ -387,6 +424,7 @@ protected:
     int numst_;
     size_t numpt_, lda_;
     DeviceMemory<T> psi_;
+    DeviceMemory<double> dots_;
     int iterative_index_;
 };
 
@@ -693,6 +731,203 @@ private:
     double gamma_;
     short mg_levels_;
     bool is_set_;
+};
+
+// MGmol::computeResidualUsingHPhi (src/MGmol.cc:1227-1287):
+// res = (B psi) theta - hphi in [Ry]; localT_dev = theta, column-major
+// numst x numst double on the device
+template <typename T>
+void computeResidualUsingHPhi(const Lap<T>& lapOper, const ExtendedGridOrbitals<T>& psi,
+    const ExtendedGridOrbitals<T>& hphi, const double* localT_dev, ExtendedGridOrbitals<T>& res,
+    void* stream = nullptr)
+{
+    MGB_CHECK(mgb_residual(lapOper.type(), dtype_of<T>::value, psi.grid().c(), psi.getPsi(),
+        psi.getLda(), hphi.getPsi(), hphi.getLda(), localT_dev, psi.numst(), res.getPsi(),
+        res.getLda(), psi.chromatic_number(), nullptr, stream));
+    res.incrementIterativeIndex();
+}
+
+// AndersonMix<T> (src/AndersonMix.h:21-52, src/AndersonMix.cc:27-319): host
+// control flow and an m x m solve; everything grid-sized is T's assign, -=,
+// dotProduct, axpy, scal.  The m x m matrix is scaled to a unit diagonal and
+// its determinant (product of Jacobi eigenvalues) tested exactly as the
+// reference does with DSYEV, then solved by Cholesky (DPOTRF/DPOTRS).
+template <class T>
+class AndersonMix
+{
+public:
+    // make(x) must return a new T shaped like x (the reference's T("xi", x))
+    template <class Make>
+    AndersonMix(const int m, const double beta, T& x, Make make)
+        : m_(m), mm_(-1), beta_(beta), x_(x), mat_((size_t)m * m, 0.), rhs_(m, 0.), theta_(m, 0.)
+    {
+        for (int i = 0; i < m; i++)
+        {
+            xi_.emplace_back(make(x));
+            fi_.emplace_back(make(x));
+        }
+        if (m > 1) tmp_.reset(make(x));
+    }
+    void restart() { mm_ = -1; }
+    int historyLength() const { return mm_; }
+    // src/AndersonMix.cc:72-319
+    void update(T& f, T& work)
+    {
+        if (mm_ < m_) mm_++;
+        if (mm_ > 0)
+        {
+            for (int i = 0; i < mm_; i++)
+            {
+                work.assign(f);
+                work -= *fi_[i];
+                mat_[i * m_ + i] = work.dotProduct(work);
+                rhs_[i]          = work.dotProduct(f);
+                for (int j = 0; j < i; j++)
+                {
+                    tmp_->assign(f);
+                    *tmp_ -= *fi_[j];
+                    mat_[j * m_ + i] = work.dotProduct(*tmp_);
+                }
+            }
+            solve();
+        }
+        if (m_ > 0)
+        {
+            mixHistory(x_, xi_, work);
+            mixHistory(f, fi_, work);
+        }
+        x_.axpy(mm_ > 0 ? beta_ : 1., f);
+    }
+
+private:
+    static constexpr double min_det_mat = 0.01, max_theta = 0.5, min_theta = -3.;
+    void mixHistory(T& cur, std::vector<std::unique_ptr<T>>& hist, T& work)
+    {
+        work.assign(cur);
+        double factor = 1.;
+        for (int j = 0; j < mm_; j++)
+            factor -= theta_[j];
+        if (mm_ > 0) cur.scal(factor);
+        for (int j = 0; j < mm_; j++)
+            cur.axpy(theta_[j], *hist[j]);
+        std::unique_ptr<T> last = std::move(hist[m_ - 1]);
+        for (int j = m_ - 1; j > 0; j--)
+            hist[j] = std::move(hist[j - 1]);
+        hist[0] = std::move(last);
+        hist[0]->assign(work);
+    }
+    // lower triangle of mat_ (column-major, leading dimension m_) -> dense n x n
+    std::vector<double> dense(const int n) const
+    {
+        std::vector<double> a((size_t)n * n);
+        for (int i = 0; i < n; i++)
+            for (int j = 0; j <= i; j++)
+                a[i * n + j] = a[j * n + i] = mat_[j * m_ + i];
+        return a;
+    }
+    static double detScaled(std::vector<double> a, const int n)
+    {
+        std::vector<double> d(n);
+        for (int i = 0; i < n; i++)
+            d[i] = 1. / std::sqrt(a[i * n + i]);
+        for (int i = 0; i < n; i++)
+            for (int j = 0; j < n; j++)
+                a[i * n + j] *= d[i] * d[j];
+        // determinant by Gaussian elimination (= product of the eigenvalues)
+        double det = 1.;
+        for (int k = 0; k < n; k++)
+        {
+            det *= a[k * n + k];
+            if (a[k * n + k] == 0.) return 0.;
+            for (int i = k + 1; i < n; i++)
+            {
+                const double l = a[i * n + k] / a[k * n + k];
+                for (int j = k; j < n; j++)
+                    a[i * n + j] -= l * a[k * n + j];
+            }
+        }
+        return det;
+    }
+    void solve()
+    {
+        bool flag = true;
+        while (flag)
+        {
+            flag = false;
+            while (mm_ > 1)
+            {
+                if (detScaled(dense(mm_), mm_) < min_det_mat)
+                    mm_--;
+                else
+                    break;
+            }
+            const int n = mm_;
+            std::vector<double> a = dense(n), y(n);
+            // Cholesky A = L L^T, then two triangular solves
+            for (int j = 0; j < n; j++)
+            {
+                for (int k = 0; k < j; k++)
+                    a[j * n + j] -= a[j * n + k] * a[j * n + k];
+                if (!(a[j * n + j] > 0.))
+                {
+                    std::fprintf(stderr, "AndersonMix, dpotrf: matrix not positive definite\n");
+                    std::exit(0);
+                }
+                a[j * n + j] = std::sqrt(a[j * n + j]);
+                for (int i = j + 1; i < n; i++)
+                {
+                    for (int k = 0; k < j; k++)
+                        a[i * n + j] -= a[i * n + k] * a[j * n + k];
+                    a[i * n + j] /= a[j * n + j];
+                }
+            }
+            for (int i = 0; i < n; i++)
+            {
+                double s = rhs_[i];
+                for (int k = 0; k < i; k++)
+                    s -= a[i * n + k] * y[k];
+                y[i] = s / a[i * n + i];
+            }
+            for (int i = n - 1; i >= 0; i--)
+            {
+                double s = y[i];
+                for (int k = i + 1; k < n; k++)
+                    s -= a[k * n + i] * theta_[k];
+                theta_[i] = s / a[i * n + i];
+            }
+            for (int j = 0; j < mm_; j++)
+            {
+                if (theta_[j] > max_theta)
+                {
+                    if (mm_ > 1)
+                    {
+                        mm_--;
+                        flag = true;
+                        break;
+                    }
+                    theta_[j] = theta_[j] > 1. ? -0.5 : 0.;
+                }
+                else if (theta_[j] < min_theta)
+                {
+                    if (mm_ > 1)
+                    {
+                        mm_--;
+                        flag = true;
+                        break;
+                    }
+                    theta_[j] = min_theta;
+                }
+            }
+        }
+    }
+
+    const int m_;
+    int mm_;
+    double beta_;
+    T& x_;
+    std::vector<std::unique_ptr<T>> xi_, fi_;
+    std::unique_ptr<T> tmp_;
+    std::vector<double> mat_, rhs_, theta_;
 };
 
 } // namespace mgmol_b200

@@ -48,3 +48,31 @@ def test_cpp_host_mirror_parity():
     print(r.stdout)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "ok" in r.stdout
+
+
+def test_cpp_anderson_mirror_matches_reference():
+    """AndersonMix of include/mgmol_b200.hpp on host vectors against the
+    trajectories of the reference's own AndersonMix<Solution> (golden)."""
+    import numpy as np
+    from mgmol_b200 import build as b
+    b.build()
+    src = os.path.join(ROOT, "tests", "cpp", "test_anderson_mirror.cc")
+    exe = os.path.join(ROOT, "tests", "cpp", "test_anderson_mirror")
+    cmd = ["g++", "-std=c++11", "-O1", "-Wall", "-I", os.path.join(ROOT, "include"), src,
+           "-L", os.path.join(ROOT, "mgmol_b200"), "-lmgmol_b200",
+           "-Wl,-rpath,$ORIGIN/../../mgmol_b200", "-o", exe]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    g = np.load(os.path.join(ROOT, "tests", "golden", "reference_anderson.npz"))
+    for n, m, beta in ((20, 1, 1.0), (20, 3, 1.0), (50, 4, 0.7)):
+        ref = g["anderson_n%d_m%d_b%g" % (n, m, beta)]
+        rng = np.random.default_rng(42)
+        x = rng.uniform(0.0, 1.0, n)
+        x[0], x[1] = 1.0, 2.0
+        x /= np.linalg.norm(x)
+        inp = "%d %d %r %d\n%s\n" % (n, m, beta, len(ref), " ".join(repr(float(v)) for v in x))
+        r = subprocess.run([exe], input=inp, capture_output=True, text=True, timeout=60)
+        assert r.returncode == 0, r.stderr
+        got = np.array([[float(v) for v in line.split()] for line in r.stdout.strip().splitlines()])
+        assert got.shape == ref.shape
+        assert np.abs(got - ref).max() <= 1e-9 * np.abs(ref).max(), (n, m, beta)
