@@ -610,19 +610,51 @@ template <bool SYRK>
 __global__ void k_tn_fixup(TnWork W, int m, int n, const double* __restrict__ partial,
     double alpha, double beta, double* __restrict__ C, int ldc, long long strideC, int sub_shift)
 {
+    // which slots hold partials of this tile: resolved once per block (the
+    // interval arithmetic is 64-bit division heavy), in CTA order
+    __shared__ long long slot_of[256]; // element offset of the slot, or -1
+    __shared__ int nslots, is_direct;
     const int u = blockIdx.x;
     const long long s0 = tn_tile_start(W, u);
     const long long s1 = s0 + (long long)(u < W.ND ? W.cd : W.cf) * W.nkt;
-    // CTAs whose interval meets [s0, s1)
     int gf = (int)(s0 * W.G / W.tot), gl = (int)((s1 - 1) * W.G / W.tot);
     if (gf > 0) gf--;
     if (gl < W.G - 1) gl++;
     const bool diag = SYRK && u < W.ND;
+    const int tl    = threadIdx.y * blockDim.x + threadIdx.x;
+    if (tl == 0)
+    {
+        nslots    = gl - gf + 1;
+        is_direct = 0;
+    }
+    __syncthreads();
+    if (tl <= gl - gf) // G <= 256 CTAs (one per SM)
+    {
+        const int g = gf + tl;
+        long long b0, b1, it0 = 0, it1 = 0;
+        tn_cta_bounds(W, g, b0, b1);
+        long long off = -1;
+        if (b1 > b0)
+        {
+            tn_seg(W, u, b0, b1, it0, it1);
+            if (it0 < it1)
+            {
+                if (!diag && it0 == 0 && it1 == W.nkt)
+                    is_direct = 1; // written by the main kernel
+                else
+                    off = ((long long)g * W.smax + (u - tn_tile_of(W, b0))) * (BM * BN);
+            }
+        }
+        slot_of[tl] = off;
+    }
+    __syncthreads();
+    if (is_direct) return;
     int batch, tile_m, tile_n;
     tn_decode<SYRK>(W, u, batch, tile_m, tile_n);
     const int ml = threadIdx.x;
     const int mm = tile_m * BM + ml;
     double* Cb   = C + (long long)batch * strideC;
+    const int ns = nslots;
     for (int nl = blockIdx.y * 8 + threadIdx.y; nl < blockIdx.y * 8 + 8; nl += blockDim.y)
     {
         const int nn = tile_n * BN + nl;
@@ -631,16 +663,11 @@ __global__ void k_tn_fixup(TnWork W, int m, int n, const double* __restrict__ pa
         const bool fold = diag && (ml >> sub_shift) != (nl >> sub_shift);
         double s = 0.;
         bool any = false;
-        for (int g = gf; g <= gl; g++)
+        for (int i = 0; i < ns; i++)
         {
-            long long b0, b1, it0, it1;
-            tn_cta_bounds(W, g, b0, b1);
-            if (b1 <= b0) continue;
-            tn_seg(W, u, b0, b1, it0, it1);
-            if (it0 >= it1) continue;
-            if (!diag && it0 == 0 && it1 == W.nkt) return; // written directly
-            const int uf = tn_tile_of(W, b0);
-            const double* src = partial + ((size_t)g * W.smax + (size_t)(u - uf)) * (BM * BN);
+            const long long off = slot_of[i];
+            if (off < 0) continue;
+            const double* src = partial + off;
             s += src[(size_t)nl * BM + ml];
             if (fold) s += src[(size_t)ml * BM + nl];
             any = true;
@@ -668,7 +695,7 @@ struct PitchP
 // Persistent: one CTA per SM walks a contiguous range of (point tile, orbital
 // tile) items; the cp.async ring runs across item boundaries, so the operand
 // stream never drains while a tile's results are written out.
-template <typename T, int KCv, int ST>
+template <typename T, int KCv, int ST, bool HASD>
 __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_nn(long long npt, int n, int k,
     const T* __restrict__ Phi, long long lda, const double* __restrict__ M, int ldm,
     double alpha, double beta, T* __restrict__ Out, long long ldc, long long nitems,
@@ -797,7 +824,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_nn(long long npt, int n, i
                         acc[i][j][e] = 0.;
                         // fused "Out.axpy(gamma, D)" (MPaxpy: y += (T)(gamma * (double)x),
                         // mputils.cc:222-244) on the freshly rounded product
-                        if (D && jj < n && pp + e < npt)
+                        if (HASD && jj < n && pp + e < npt)
                             r[e] += (T)(gamma * (double)D[(long long)jj * ldd + pp + e]);
                     }
                     if (jj < n)
@@ -930,6 +957,7 @@ static int gemm_tn_t(bool syrk, int m, int n, size_t k, double alpha, const T* A
     long long G = W.tot / ((long long)W.cf * (512 / kcv));
     if (G < 1) G = 1;
     if (G > num_sms()) G = num_sms();
+    if (G > 256) G = 256; // k_tn_fixup resolves one CTA per thread of its block
     W.G = (int)G;
     // partial slots per CTA = the most tiles one CTA's share touches
     int smax = 1;
@@ -1048,20 +1076,29 @@ static int gemm_nn_t(size_t m, int n, int k, double alpha, const T* A, size_t ld
     const int jtiles       = (n + 127) / 128;
     const long long nitems = ptiles * jtiles;
     const unsigned grid    = (unsigned)(nitems < num_sms() ? nitems : num_sms());
+#define MGB_NN_LAUNCH(KV, STV, HD)                                                        \
+    {                                                                                     \
+        auto kern = k_gemm_nn<T, KV, STV, HD>;                                            \
+        MGB_CUDA(cudaFuncSetAttribute(                                                    \
+            kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));               \
+        kern<<<grid, NTHREADS, smem, st>>>((long long)m, n, k, A, (long long)lda, M, ldm, \
+            alpha, beta, Out, (long long)ldc, nitems, jtiles, gamma, D, (long long)ldd); \
+    }
     if (kcv == 32)
     {
-        auto kern = k_gemm_nn<T, 32, 3>;
-        MGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, NTHREADS, smem, st>>>((long long)m, n, k, A, (long long)lda, M, ldm, alpha,
-            beta, Out, (long long)ldc, nitems, jtiles, gamma, D, (long long)ldd);
+        if (D)
+            MGB_NN_LAUNCH(32, 3, true)
+        else
+            MGB_NN_LAUNCH(32, 3, false)
     }
     else
     {
-        auto kern = k_gemm_nn<T, 16, 4>;
-        MGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, NTHREADS, smem, st>>>((long long)m, n, k, A, (long long)lda, M, ldm, alpha,
-            beta, Out, (long long)ldc, nitems, jtiles, gamma, D, (long long)ldd);
+        if (D)
+            MGB_NN_LAUNCH(16, 4, true)
+        else
+            MGB_NN_LAUNCH(16, 4, false)
     }
+#undef MGB_NN_LAUNCH
     MGB_LAUNCHED("k_gemm_nn");
     return MGB_OK;
 }
