@@ -354,8 +354,16 @@ def run_ours(args):
     tdt = torch.float64 if args.dtype == "f64" else torch.float32
     S = 8 if args.dtype == "f64" else 4
     g = H.ghosts_for(lap_type)
-    gdims = (dims[0] * world, dims[1], dims[2])
-    grid = H.Grid(gdims, (cell * world, cell, cell), g, (1, 1, 1), (world, 1, 1), (rank, 0, 0))
+    if args.strong:
+        # strong scaling: the workload's own grid split along x over the ranks
+        assert dims[0] % world == 0 and (dims[0] // world) % 4 == 0, "x planes per rank"
+        gdims = dims
+        grid = H.Grid(gdims, (cell, cell, cell), g, (1, 1, 1), (world, 1, 1), (rank, 0, 0))
+        dims = (dims[0] // world, dims[1], dims[2])
+    else:
+        gdims = (dims[0] * world, dims[1], dims[2])
+        grid = H.Grid(gdims, (cell * world, cell, cell), g, (1, 1, 1), (world, 1, 1),
+                      (rank, 0, 0))
     npt = grid.size()
 
     # synthetic orbitals: plane wave along z with orbital-dependent wavevector
@@ -499,12 +507,14 @@ def run_ours(args):
         e2e = updates_per_step * e2e_steps / (e2e_ms * 1e-3)
         peak, peak_src = measured_peaks()
         achieved = 2.0 * S * npt * norb / (kern_ms * 1e-3) / 1e9
+        cpu_dims = gdims if args.strong else dims
         cpu_rate, cores, kind, sample = cpu_hpsi_rate(
-            lap_type, dims, (cell,) * 3, np.float64 if args.dtype == "f64" else np.float32)
+            lap_type, cpu_dims, (cell,) * 3, np.float64 if args.dtype == "f64" else np.float32)
         line = {
             "metric": "hpsi_gridpt_orbital_updates_per_s", "value": value, "unit": "updates/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong" if args.strong else "weak",
             "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": desc, "lap_type": lap_type, "grid_per_gpu": list(dims),
                        "orbitals": norb, "decomposition": "%dx1x1" % world,
@@ -544,6 +554,9 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--strong", action="store_true",
+                    help="split the workload's own grid over the GPUs (default: weak scaling, "
+                         "one full grid per GPU)")
     ap.add_argument("--no-cpu-iteration", action="store_true",
                     help="skip the CPU reference timing of the orbital-update iteration")
     ap.add_argument("--steps", type=int, default=20)
