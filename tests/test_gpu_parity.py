@@ -765,3 +765,43 @@ def test_full_size_linearity_and_translation(H):
     hs = torch.empty_like(psi_s)
     lap.applyWithPot(psi_s, v_s, hs)
     assert torch.equal(hs, torch.roll(hp, sh, dims=(1, 2, 3)))
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_config_si4x4nanowire_shape(H, dt):
+    """BASELINE configs[2] (examples/Si4x4nanowire): 128 x 128 x 32 grid, 40
+    orbitals, Mehrstellen, 2 multigrid levels.  H psi: TMA kernel against the
+    bit-exact generic kernel; V-cycle: fused against the literal sequence."""
+    from mgmol_b200._lib import lib, check
+    dims, N, lap_type = (128, 128, 32), 40, 0
+    ll = (40.0, 40.0, 10.26)
+    g = torch.Generator(device="cuda").manual_seed(4)
+    phi = (torch.rand((N,) + dims, generator=g, device="cuda", dtype=torch.float64) - 0.5)
+    phi = phi.to(TDT[dt]).contiguous()
+    v = torch.rand(dims, generator=g, device="cuda", dtype=torch.float64) * 2.0 - 1.5
+    grid = H.Grid(dims, ll, 1)
+    lap = H.LapFactory.createLap(grid, lap_type)
+    outs = {}
+    for path in (1, 2):
+        check(lib().mgb_hpsi_force_path(path))
+        try:
+            out = torch.empty_like(phi)
+            lap.applyWithPot(phi, v, out)
+            assert lib().mgb_hpsi_last_path() == path
+            outs[path] = out
+        finally:
+            lib().mgb_hpsi_force_path(0)
+    scale = outs[2].abs().amax(dim=(1, 2, 3), keepdim=True).double()
+    assert float(((outs[1].double() - outs[2].double()).abs() / scale).max()) <= TOL[dt]
+    res = {}
+    for mode in (1, 2):
+        orb = H.Orbitals(grid, N, TDT[dt], outs[2].clone())
+        pc = H.OrbitalsPreconditioning()
+        pc.setup(orb, 2, lap_type)
+        pc.set_mode(mode)
+        pc.gamma_ = 0.25
+        pc.precond_mg(orb)
+        res[mode] = orb.psi().double()
+        pc.close()
+    sc = res[1].abs().amax(dim=(1, 2, 3), keepdim=True)
+    assert float(((res[2] - res[1]).abs() / sc).max()) <= MG_TOL
