@@ -548,6 +548,7 @@ def run_ours(args):
             line["pieces"] = pieces
         print(json.dumps(line))
     if world > 1:
+        comm.check()
         dist.destroy_process_group()
 
 

@@ -340,6 +340,10 @@ int mgb_comm_destroy(mgb_comm* c);
 int mgb_allreduce_sum_f64(mgb_comm* c, double* data, size_t n, void* stream);
 /* Stream-ordered barrier over the ranks (a one-element all-reduce).            */
 int mgb_comm_barrier(mgb_comm* c, void* stream);
+/* Synchronises the device and reports whether a neighbour barrier of the in-place
+ * halo paths (a flag exchange through peer memory, used instead of a collective
+ * because a halo only depends on the two x neighbours) ever timed out.        */
+int mgb_comm_check(mgb_comm* c);
 /* Direct peer reads over NVLink.  Every rank registers ITS array (collective:
  * each rank passes its own pointer, e.g. its orbital block) and the library
  * maps the other ranks' arrays into this process with CUDA IPC

@@ -122,6 +122,7 @@ _SIGS = {
     "mgb_comm_destroy": (c_int, [c_void_p]),
     "mgb_allreduce_sum_f64": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "mgb_comm_barrier": (c_int, [c_void_p, c_void_p]),
+    "mgb_comm_check": (c_int, [c_void_p]),
     "mgb_peer_register": (c_int, [c_void_p, c_void_p, c_void_p]),
     "mgb_peer_unregister": (c_int, [c_void_p, c_void_p]),
     "mgb_peer_set_color_maps": (c_int, [c_void_p, c_void_p, c_void_p, c_int]),

@@ -402,7 +402,7 @@ int mgb_hpsi_peer(mgb_comm* comm, int lap_type, int dtype, const mgb_grid* grid,
         "mgb_hpsi_peer: color maps cover %d colors, the block has %d", map_n, nfunc);
     cudaStream_t st = as_stream(stream);
     // every rank's phi is complete before anybody reads boundary planes ...
-    if (int rc = comm_barrier(comm, st)) return rc;
+    if (int rc = comm_barrier_neighbors(comm, grid, st)) return rc;
     const int force = g_force_path;
     g_force_path    = 1; // only the TMA kernel reads peers
     const int rc    = hpsi_entry(lap_type, dtype, grid, phi, ld, vtot, hphi, ldh, nfunc,
@@ -410,7 +410,7 @@ int mgb_hpsi_peer(mgb_comm* comm, int lap_type, int dtype, const mgb_grid* grid,
     g_force_path = force;
     if (rc) return rc;
     // ... and nobody overwrites its phi while a neighbour still reads it
-    return comm_barrier(comm, st);
+    return comm_barrier_neighbors(comm, grid, st);
 }
 
 

@@ -11,6 +11,7 @@
 #include <cuda.h>
 #include <dlfcn.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -123,6 +124,13 @@ struct mgb_comm
     void* buf[4];
     size_t buf_sz[4];
     float* flag;                                  // 1-element all-reduce = rank barrier
+    // neighbour barrier over peer memory: inbox[0] = epoch last signalled by my
+    // west neighbour, inbox[1] = by my east neighbour; inbox[2] = timeout flag
+    unsigned long long* inbox;
+    unsigned long long* west_inbox; // the west rank's inbox, mapped here
+    unsigned long long* east_inbox;
+    int nb_west, nb_east;           // ranks the mapping was made for (-1: none)
+    unsigned long long epoch;
     int* map_w;                                   // my color -> west / east rank's color
     int* map_e;                                   // (device, ncolors each) or null = same
     int map_n;
@@ -349,6 +357,80 @@ int comm_barrier(mgb_comm* c, cudaStream_t st)
 
 int comm_rank_of(const mgb_grid* gr, int cx, int cy, int cz) { return rank_of(gr, cx, cy, cz); }
 
+// Barrier with the x neighbours only, through peer memory: publish my epoch in
+// both neighbours' inboxes (remote stores over NVLink), then wait until both of
+// mine have reached it.  One tiny kernel instead of a collective; a halo only
+// ever depends on the two neighbours.  The wait gives up after ~2 s and raises a
+// flag instead of hanging the GPU.
+__global__ void k_neighbor_sync(unsigned long long* inbox, unsigned long long* west_inbox,
+    unsigned long long* east_inbox, unsigned long long epoch)
+{
+    if (threadIdx.x != 0) return;
+    __threadfence_system();
+    if (west_inbox)
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(west_inbox + 1), "l"(epoch)
+                     : "memory");
+    if (east_inbox)
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(east_inbox + 0), "l"(epoch)
+                     : "memory");
+    const long long t0 = clock64();
+    for (int side = 0; side < 2; side++)
+    {
+        if (!(side == 0 ? west_inbox : east_inbox)) continue;
+        unsigned long long v;
+        do
+        {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(inbox + side)
+                         : "memory");
+            if (v < epoch && clock64() - t0 > 4000000000LL)
+            {
+                inbox[2] = epoch; // timed out
+                return;
+            }
+        } while (v < epoch);
+    }
+}
+
+int comm_barrier_neighbors(mgb_comm* c, const mgb_grid* gr, cudaStream_t st)
+{
+    if (!c || c->nranks == 1) return MGB_OK;
+    const bool per = gr->bc[0] == 1;
+    const int west = (per || gr->coord[0] > 0)
+                         ? rank_of(gr, gr->coord[0] - 1, gr->coord[1], gr->coord[2]) : -1;
+    const int east = (per || gr->coord[0] < gr->nproc[0] - 1)
+                         ? rank_of(gr, gr->coord[0] + 1, gr->coord[1], gr->coord[2]) : -1;
+    if (getenv("MGB_NCCL_BARRIER")) return comm_barrier(c, st);
+    if (!c->inbox)
+    {
+        // collective, once: every rank publishes its inbox
+        MGB_CUDA(cudaMalloc(&c->inbox, 4 * sizeof(unsigned long long)));
+        MGB_CUDA(cudaMemset(c->inbox, 0, 4 * sizeof(unsigned long long)));
+        if (int rc = mgb_peer_register(c, c->inbox, (void*)st))
+        {
+            cudaFree(c->inbox);
+            c->inbox = nullptr;
+            if (rc != MGB_ENOTSUP) return rc;
+            return comm_barrier(c, st);
+        }
+        c->nb_west = c->nb_east = -2;
+        // nobody signals before every inbox exists and is zero
+        if (int rc = comm_barrier(c, st)) return rc;
+    }
+    if (c->nb_west != west || c->nb_east != east)
+    {
+        c->west_inbox = west >= 0 ? (unsigned long long*)peer_view(c, c->inbox, west) : nullptr;
+        c->east_inbox = east >= 0 ? (unsigned long long*)peer_view(c, c->inbox, east) : nullptr;
+        if ((west >= 0 && !c->west_inbox) || (east >= 0 && !c->east_inbox))
+            return comm_barrier(c, st);
+        c->nb_west = west;
+        c->nb_east = east;
+    }
+    c->epoch++;
+    k_neighbor_sync<<<1, 32, 0, st>>>(c->inbox, c->west_inbox, c->east_inbox, c->epoch);
+    MGB_LAUNCHED("k_neighbor_sync");
+    return MGB_OK;
+}
+
 void comm_color_maps(mgb_comm* c, const int** map_w, const int** map_e, int* n)
 {
     *map_w = c ? c->map_w : nullptr;
@@ -368,6 +450,24 @@ int mgb_comm_barrier(mgb_comm* c, void* stream)
     if (int rc = require_device()) return rc;
     MGB_REQUIRE(c, "mgb_comm_barrier: null communicator");
     return comm_barrier(c, as_stream(stream));
+}
+
+int mgb_comm_check(mgb_comm* c)
+{
+    if (int rc = require_device()) return rc;
+    MGB_REQUIRE(c, "mgb_comm_check: null communicator");
+    MGB_CUDA(cudaDeviceSynchronize());
+    if (c->inbox)
+    {
+        unsigned long long flag = 0;
+        MGB_CUDA(cudaMemcpy(&flag, c->inbox + 2, sizeof(flag), cudaMemcpyDeviceToHost));
+        if (flag)
+        {
+            set_error("neighbour barrier %llu timed out: a rank did not reach it", flag);
+            return MGB_ENCCL;
+        }
+    }
+    return MGB_OK;
 }
 
 int mgb_peer_register(mgb_comm* c, const void* ptr, void* stream)
@@ -543,6 +643,11 @@ int mgb_comm_destroy(mgb_comm* c)
     for (int i = 0; i < 4; i++)
         if (c->buf[i]) cudaFree(c->buf[i]);
     if (c->flag) cudaFree(c->flag);
+    if (c->inbox)
+    {
+        mgb_peer_unregister(c, c->inbox);
+        cudaFree(c->inbox);
+    }
     if (c->map_w) cudaFree(c->map_w);
     if (c->map_e) cudaFree(c->map_e);
     if (c->opened)

@@ -64,6 +64,9 @@ int subbox_copy(int dtype, bool pack, const mgb_grid* gr, const int lo[3],
 // and the rank at Cartesian coordinates
 const void* peer_view(mgb_comm* c, const void* local, int rank);
 int comm_barrier(mgb_comm* c, cudaStream_t st);
+// barrier with the x neighbours of `gr` only, through peer memory (falls back
+// to comm_barrier when the inboxes cannot be mapped)
+int comm_barrier_neighbors(mgb_comm* c, const mgb_grid* gr, cudaStream_t st);
 int comm_rank_of(const mgb_grid* gr, int cx, int cy, int cz);
 // LocGridOrbitals on split domains: the color slot of my color's orbital on the
 // west / east rank (device arrays, -1 = not held there), null = same slot

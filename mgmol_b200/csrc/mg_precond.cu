@@ -466,7 +466,7 @@ static int cycle_fused(mgb_precond* p, int l, const float* f, size_t ldf, double
         a.map_e  = map_e;
         // every rank has finished writing (and reading) the blocks involved
         if (split)
-            if (int rc = comm_barrier(p->comm, st)) return rc;
+            if (int rc = comm_barrier_neighbors(p->comm, &gr, st)) return rc;
         if (int rc = mg_jacobi(a, st)) return rc;
         cur           = final_out ? nullptr : nxt;
         pending_scale = false;
@@ -487,7 +487,7 @@ static int cycle_fused(mgb_precond* p, int l, const float* f, size_t ldf, double
         XPeers xp;
         if (int rc = x_peers(p, gr, p->fw[l], xp)) return rc;
         if (split)
-            if (int rc = comm_barrier(p->comm, st)) return rc;
+            if (int rc = comm_barrier_neighbors(p->comm, &gr, st)) return rc;
         if (int rc = mg_restrict(
                 gr, p->fw[l], ld, p->ff[l + 1], npt_of(p->grid[l + 1]), nfunc, mkc, xp.w, map_w, st))
             return rc;
@@ -504,7 +504,7 @@ static int cycle_fused(mgb_precond* p, int l, const float* f, size_t ldf, double
         XPeers xp;
         if (int rc = x_peers(p, p->grid[l + 1], e, xp)) return rc;
         if (split)
-            if (int rc = comm_barrier(p->comm, st)) return rc;
+            if (int rc = comm_barrier_neighbors(p->comm, &gr, st)) return rc;
         if (int rc = mg_prolong_correct(
                 gr, e, npt_of(p->grid[l + 1]), cur, ld, nfunc, zl, mk, xp.e, map_e, st))
             return rc;
@@ -636,7 +636,7 @@ int mgb_precond_mg(mgb_precond* p, int dtype, void* res, size_t ld, int nfunc,
         if ((rc = ensure_fused(p))) return rc;
         // nobody is still reading my work blocks from the previous call
         if (gr.nproc[0] > 1)
-            if ((rc = comm_barrier(p->comm, st))) return rc;
+            if ((rc = comm_barrier_neighbors(p->comm, &gr, st))) return rc;
         const float* f = (const float*)res;
         size_t ldf     = ld;
         if (dtype == MGB_F64)

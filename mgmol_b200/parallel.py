@@ -36,6 +36,10 @@ class Communicator:
         """Stream-ordered barrier over the ranks."""
         check(lib().mgb_comm_barrier(self.handle, _stream()))
 
+    def check(self):
+        """Device sync + did any neighbour barrier time out?"""
+        check(lib().mgb_comm_check(self.handle))
+
     def register(self, t):
         """Collective: publish this rank's array so that the neighbours'
         kernels can read its boundary planes in place over NVLink (CUDA IPC).

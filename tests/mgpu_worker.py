@@ -259,6 +259,7 @@ def main():
         check("phiT A + allreduce %s" % dt,
               float((hl - exact).abs().max() / exact.abs().max()) <= tol)
 
+    comm.check()  # no neighbour barrier timed out
     torch.cuda.synchronize()
     flag = torch.tensor([len(fails)], device="cuda")
     dist.all_reduce(flag)
