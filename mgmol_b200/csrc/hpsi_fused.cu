@@ -161,7 +161,9 @@ __device__ __forceinline__ int plane_source(const FusedParams& P, int p, int& xc
     return 0;
 }
 
-template <typename T, int RY, bool PERIODIC, bool LAP4, int MAXT>
+// PEER: the x-halo planes of phi are read from the neighbours' blocks (a separate
+// instantiation, so that the single-rank kernel carries none of that code)
+template <typename T, int RY, bool PERIODIC, bool LAP4, int MAXT, bool PEER>
 __global__ void __launch_bounds__(MAXT, 1)
     k_hpsi_tma(const __grid_constant__ FusedParams P)
 {
@@ -233,7 +235,7 @@ __global__ void __launch_bounds__(MAXT, 1)
                 const CUtensorMap* ph = (src == 1) ? &P.psi_halo : &P.xpsi_halo;
                 int xcp = xc;
                 const int* cmap = nullptr;
-                if (src == 2 && P.peer)
+                if (PEER && src == 2)
                 {
                     cmap = (p < 0) ? P.map_w : P.map_e;
                     // read the neighbour's boundary plane straight from its
@@ -250,22 +252,34 @@ __global__ void __launch_bounds__(MAXT, 1)
                     tma_load_3d(sb, vh, &full[stage], 0, ylo, xc, pol_keep);
                     tma_load_3d(sb + P.off_hi, vh, &full[stage], 0, yhi, xc, pol_keep);
                 }
-                for (int o = 0; o < norb; o++)
+                if (!PEER || !cmap)
                 {
-                    unsigned char* tb = sb + (size_t)(1 + o) * P.tile_bytes;
+                    // the issue loop of the producer thread: kept minimal
+                    for (int o = 0; o < norb; o++)
+                    {
+                        unsigned char* tb = sb + (size_t)(1 + o) * P.tile_bytes;
+                        tma_load_4d(tb + P.off_mid, pm, &full[stage], 0, y0, xcp, orb0 + o,
+                            pol_stream);
+                        tma_load_4d(tb, ph, &full[stage], 0, ylo, xcp, orb0 + o, pol_stream);
+                        tma_load_4d(tb + P.off_hi, ph, &full[stage], 0, yhi, xcp, orb0 + o,
+                            pol_stream);
+                    }
+                }
+                else
+                {
                     // the orbital may sit in another color slot on the
                     // neighbour (gid-addressed packets, src/pb/GridFuncVector.cc:
                     // 1225-1246,1374-1393); absent there: an out-of-range
                     // function index makes TMA deliver zeros
-                    int fo = orb0 + o;
-                    if (cmap)
+                    for (int o = 0; o < norb; o++)
                     {
-                        fo = cmap[fo];
+                        unsigned char* tb = sb + (size_t)(1 + o) * P.tile_bytes;
+                        int fo = cmap[orb0 + o];
                         if (fo < 0) fo = P.nfunc;
+                        tma_load_4d(tb + P.off_mid, pm, &full[stage], 0, y0, xcp, fo, pol_stream);
+                        tma_load_4d(tb, ph, &full[stage], 0, ylo, xcp, fo, pol_stream);
+                        tma_load_4d(tb + P.off_hi, ph, &full[stage], 0, yhi, xcp, fo, pol_stream);
                     }
-                    tma_load_4d(tb + P.off_mid, pm, &full[stage], 0, y0, xcp, fo, pol_stream);
-                    tma_load_4d(tb, ph, &full[stage], 0, ylo, xcp, fo, pol_stream);
-                    tma_load_4d(tb + P.off_hi, ph, &full[stage], 0, yhi, xcp, fo, pol_stream);
                 }
             }
             if (++stage == S)
@@ -797,14 +811,19 @@ static int launch_ry(const FusedParams& P, dim3 grid, int threads, size_t smem,
     cudaStream_t st)
 {
     // launch-bound classes: 9 / 13 / 17 warps -> 168 / 128 / 96 registers
-#define MGB_LAUNCH_MAXT(MT)                                                    \
+#define MGB_LAUNCH_MAXT_P(MT, PEERV)                                           \
     {                                                                          \
-        auto kern = k_hpsi_tma<T, RY, PERIODIC, LAP4, MT>;                     \
+        auto kern = k_hpsi_tma<T, RY, PERIODIC, LAP4, MT, PEERV>;              \
         MGB_CUDA(cudaFuncSetAttribute(                                         \
             kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
         kern<<<grid, threads, smem, st>>>(P);                                  \
         MGB_LAUNCHED("k_hpsi_tma");                                            \
     }
+#define MGB_LAUNCH_MAXT(MT)                                                    \
+    if (P.peer)                                                                \
+        MGB_LAUNCH_MAXT_P(MT, true)                                            \
+    else                                                                       \
+        MGB_LAUNCH_MAXT_P(MT, false)
     if (threads <= 288)
         MGB_LAUNCH_MAXT(288)
     else if (threads <= 416)
@@ -812,6 +831,7 @@ static int launch_ry(const FusedParams& P, dim3 grid, int threads, size_t smem,
     else
         MGB_LAUNCH_MAXT(544)
 #undef MGB_LAUNCH_MAXT
+#undef MGB_LAUNCH_MAXT_P
     return MGB_OK;
 }
 
