@@ -388,6 +388,17 @@ int mgb_halo_exchange_x(mgb_comm* c, int dtype, const mgb_grid* grid, int g,
 int mgb_halo_exchange_ghosted(mgb_comm* c, int dtype, const mgb_grid* grid,
     void* ghosted, int nfunc, void* stream);
 
+/* The same gid addressing for the packed exchange (LocGridOrbitals on any
+ * decomposition): maps[dir][side][iloc][color] (dir 0 x, 1 y, 2 z; side 0 = the
+ * ghosts filled by the low neighbour, 1 = by the high neighbour; host array of
+ * 6*subdivx*ncolors ints) = the color of the SENDING rank whose x-slab iloc holds
+ * the orbital of my color in that slab, or -1: that slab of the ghost layer is
+ * left as it is, exactly as the reference's receiver skips it
+ * (src/pb/GridFuncVector.cc:461-513 north/south, :958-998 up/down, :1374-1419
+ * east/west; for x only iloc 0 (side 0) / subdivx-1 (side 1) is read).  NULL
+ * restores slot-for-slot copies.                                             */
+int mgb_halo_set_color_maps(mgb_comm* c, int subdivx, int ncolors, const int* maps);
+
 #ifdef __cplusplus
 }
 #endif

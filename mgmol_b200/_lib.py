@@ -131,6 +131,7 @@ _SIGS = {
                               c_void_p]),
     "mgb_halo_exchange_x": (c_int, [c_void_p, c_int, ctypes.POINTER(MgbGrid), c_int,
                                     c_void_p, c_size_t, c_void_p, c_int, c_void_p]),
+    "mgb_halo_set_color_maps": (c_int, [c_void_p, c_int, c_int, c_void_p]),
     "mgb_halo_exchange_ghosted": (c_int, [c_void_p, c_int, ctypes.POINTER(MgbGrid),
                                           c_void_p, c_int, c_void_p]),
 }

@@ -131,6 +131,10 @@ struct mgb_comm
     unsigned long long* east_inbox;
     int nb_west, nb_east;           // ranks the mapping was made for (-1: none)
     unsigned long long epoch;
+    // gid-addressed packed exchange: hmaps[dir][side][iloc][color] = the sending
+    // neighbour's color whose slab holds my color's orbital, or -1 (device)
+    int* hmaps;
+    int hm_subdivx, hm_ncolors;
     int* map_w;                                   // my color -> west / east rank's color
     int* map_e;                                   // (device, ncolors each) or null = same
     int map_n;
@@ -245,6 +249,58 @@ static int halo_x_t(mgb_comm* c, const mgb_grid* gr, int g, const T* u, size_t l
     return MGB_OK;
 }
 
+// Unpack a received face gid-addressed (src/pb/GridFuncVector.cc:461-513,
+// 958-998, 1374-1419): my color f takes, x-slab by x-slab, the face of the
+// sender's color map[iloc][f]; slabs whose orbital the sender does not hold
+// keep their ghost values, as in the reference.
+template <typename T>
+__global__ void k_unpack_mapped(Box b, int lo0, int lo1, int lo2, int e0, int e1, int e2,
+    T* __restrict__ u, const T* __restrict__ buf, const int* __restrict__ map, int ncolors,
+    int subdivx, int sub0, int fixed_iloc)
+{
+    const long long per = (long long)e0 * e1 * e2;
+    const long long t   = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= per) return;
+    const int f = blockIdx.y;
+    const int k = (int)(t % e2);
+    const int j = (int)((t / e2) % e1);
+    const int i = (int)(t / ((long long)e2 * e1));
+    int iloc    = fixed_iloc;
+    if (iloc < 0)
+    {
+        iloc = (lo0 + i - b.g) / sub0; // faces of the y / z exchange span interior x only
+        if (iloc < 0) iloc = 0;
+        if (iloc >= subdivx) iloc = subdivx - 1;
+    }
+    const int src = map[iloc * ncolors + f];
+    if (src < 0) return;
+    u[(long long)f * b.sizeg + (long long)(lo0 + i) * b.incx + (long long)(lo1 + j) * b.incy
+        + (lo2 + k)]
+        = buf[(long long)src * per + t];
+}
+
+static int unpack_mapped(mgb_comm* c, int dtype, const mgb_grid* gr, const int lo[3],
+    const int ext[3], void* u, const void* buf, int nfunc, int d, int side, cudaStream_t st)
+{
+    Box b = box_of(gr, gr->ghosts);
+    const long long per = (long long)ext[0] * ext[1] * ext[2];
+    if (per == 0 || nfunc == 0) return MGB_OK;
+    MGB_REQUIRE(nfunc <= c->hm_ncolors && nfunc <= 65535,
+        "gid-addressed exchange: %d functions, color maps cover %d", nfunc, c->hm_ncolors);
+    const int* map = c->hmaps + (size_t)(d * 2 + side) * c->hm_subdivx * c->hm_ncolors;
+    const int sub0 = gr->dim[0] / c->hm_subdivx;
+    const int fixed = d == 0 ? (side == 0 ? 0 : c->hm_subdivx - 1) : -1;
+    dim3 grid((unsigned)((per + 255) / 256), (unsigned)nfunc, 1);
+    if (dtype == MGB_F64)
+        k_unpack_mapped<double><<<grid, 256, 0, st>>>(b, lo[0], lo[1], lo[2], ext[0], ext[1],
+            ext[2], (double*)u, (const double*)buf, map, c->hm_ncolors, c->hm_subdivx, sub0, fixed);
+    else
+        k_unpack_mapped<float><<<grid, 256, 0, st>>>(b, lo[0], lo[1], lo[2], ext[0], ext[1],
+            ext[2], (float*)u, (const float*)buf, map, c->hm_ncolors, c->hm_subdivx, sub0, fixed);
+    MGB_LAUNCHED("k_unpack_mapped");
+    return MGB_OK;
+}
+
 // One direction of the ghosted exchange: faces with the reference's extents
 // (Y: interior x and z; Z: interior x, all y; X: whole planes).
 static int exchange_dir(mgb_comm* c, int dtype, const mgb_grid* gr, void* u,
@@ -292,10 +348,18 @@ static int exchange_dir(mgb_comm* c, int dtype, const mgb_grid* gr, void* u,
     MGB_NCCL(N->GroupEnd());
     l[d] = 0; // low ghosts
     if (have_lo)
-        if ((rc = subbox_copy(dtype, false, gr, l, ext, u, r_lo, nfunc, st))) return rc;
+    {
+        rc = c->hmaps ? unpack_mapped(c, dtype, gr, l, ext, u, r_lo, nfunc, d, 0, st)
+                      : subbox_copy(dtype, false, gr, l, ext, u, r_lo, nfunc, st);
+        if (rc) return rc;
+    }
     l[d] = n[d] + g; // high ghosts
     if (have_hi)
-        if ((rc = subbox_copy(dtype, false, gr, l, ext, u, r_hi, nfunc, st))) return rc;
+    {
+        rc = c->hmaps ? unpack_mapped(c, dtype, gr, l, ext, u, r_hi, nfunc, d, 1, st)
+                      : subbox_copy(dtype, false, gr, l, ext, u, r_hi, nfunc, st);
+        if (rc) return rc;
+    }
     return MGB_OK;
 }
 
@@ -559,6 +623,23 @@ int mgb_peer_set_color_maps(mgb_comm* c, const int* map_west, const int* map_eas
     return MGB_OK;
 }
 
+int mgb_halo_set_color_maps(mgb_comm* c, int subdivx, int ncolors, const int* maps)
+{
+    if (int rc = require_device()) return rc;
+    MGB_REQUIRE(c, "mgb_halo_set_color_maps: null communicator");
+    if (c->hmaps) cudaFree(c->hmaps);
+    c->hmaps      = nullptr;
+    c->hm_subdivx = c->hm_ncolors = 0;
+    if (!maps) return MGB_OK;
+    MGB_REQUIRE(subdivx > 0 && ncolors > 0, "mgb_halo_set_color_maps: bad table shape");
+    const size_t n = (size_t)6 * subdivx * ncolors;
+    MGB_CUDA(cudaMalloc(&c->hmaps, sizeof(int) * n));
+    MGB_CUDA(cudaMemcpy(c->hmaps, maps, sizeof(int) * n, cudaMemcpyHostToDevice));
+    c->hm_subdivx = subdivx;
+    c->hm_ncolors = ncolors;
+    return MGB_OK;
+}
+
 int mgb_peer_unregister(mgb_comm* c, const void* ptr)
 {
     MGB_REQUIRE(c && ptr, "mgb_peer_unregister: null pointer");
@@ -650,6 +731,7 @@ int mgb_comm_destroy(mgb_comm* c)
     }
     if (c->map_w) cudaFree(c->map_w);
     if (c->map_e) cudaFree(c->map_e);
+    if (c->hmaps) cudaFree(c->hmaps);
     if (c->opened)
         for (auto& o : *c->opened)
             if (o.refs > 0) cudaIpcCloseMemHandle(o.base);

@@ -62,6 +62,18 @@ class Communicator:
             self.handle, mw.ctypes.data_as(ctypes.c_void_p),
             me.ctypes.data_as(ctypes.c_void_p), len(mw)))
 
+    def set_ghosted_color_maps(self, maps):
+        """gid-addressed packed exchange: maps[dir][side][iloc][color] (see
+        ghosted_color_maps); None = slot-for-slot."""
+        if maps is None:
+            check(lib().mgb_halo_set_color_maps(self.handle, 0, 0, None))
+            return
+        import numpy as np
+        m = np.ascontiguousarray(maps, dtype=np.int32)
+        assert m.ndim == 4 and m.shape[:2] == (3, 2)
+        check(lib().mgb_halo_set_color_maps(self.handle, m.shape[2], m.shape[3],
+                                            m.ctypes.data_as(ctypes.c_void_p)))
+
     def halo_exchange_x(self, grid, g, noghost, xhalo):
         nfunc = noghost.shape[0]
         check(lib().mgb_halo_exchange_x(self.handle, _dt(noghost), grid.ref(), g,
@@ -197,6 +209,37 @@ def color_maps(my_gids, west_gids, east_gids):
         return out
     return (one(my_gids[0], None if west_gids is None else west_gids[-1]),
             one(my_gids[-1], None if east_gids is None else east_gids[0]))
+
+
+def ghosted_color_maps(my_gids, neighbour_gids):
+    """maps[dir][side][iloc][color] for Communicator.set_ghosted_color_maps.
+    neighbour_gids[dir][side]: the (subdivx, ncolors) gid table of the rank that
+    fills my low (side 0) / high (side 1) ghosts in direction dir, or None.
+    y / z: slab by slab, the sender's color holding the same gid in the same slab
+    (src/pb/GridFuncVector.cc:461-513, 958-998); x: the sender's boundary slab
+    against my boundary slab (:1374-1419)."""
+    import numpy as np
+    my = np.asarray(my_gids)
+    subdivx, ncolors = my.shape
+    out = -np.ones((3, 2, subdivx, ncolors), np.int32)
+    for d in range(3):
+        for side in range(2):
+            nb = neighbour_gids[d][side]
+            if nb is None:
+                continue
+            nb = np.asarray(nb)
+            for iloc in range(subdivx):
+                if d == 0:
+                    if iloc != (0 if side == 0 else subdivx - 1):
+                        continue
+                    theirs = nb[-1] if side == 0 else nb[0]
+                else:
+                    theirs = nb[iloc]
+                lookup = {int(g): i for i, g in enumerate(theirs) if g >= 0}
+                for c in range(ncolors):
+                    g = int(my[iloc, c])
+                    out[d, side, iloc, c] = lookup.get(g, -1) if g >= 0 else -1
+    return out
 
 
 def x_halo_plan(rank, nproc, g, bc_x=1):

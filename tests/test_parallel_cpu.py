@@ -121,3 +121,21 @@ def test_color_maps_follow_gid_addressed_packets():
     assert color_maps(mine, None, east)[0] == [-1, -1, -1, -1]
     ident = [[0, 1, 2]]
     assert color_maps(ident, ident, ident) == ([0, 1, 2], [0, 1, 2])
+
+
+def test_ghosted_color_maps():
+    """Per-slab gid addressing of the packed exchange."""
+    import numpy as np
+    from mgmol_b200.parallel import ghosted_color_maps
+    mine = np.array([[4, 7, -1], [4, 9, 3]])
+    south = np.array([[7, 4, 2], [3, -1, 9]])
+    west = np.array([[1, 1, 1], [7, 5, 4]])
+    nb = [[west, None], [south, south], [None, None]]
+    m = ghosted_color_maps(mine, nb)
+    assert m.shape == (3, 2, 2, 3)
+    # y, both sides: same slab of the sender
+    assert m[1, 0].tolist() == [[1, 0, -1], [-1, 2, 0]]
+    assert m[1, 1].tolist() == m[1, 0].tolist()
+    # x low side: my slab 0 against the west rank's LAST slab; other slabs unused
+    assert m[0, 0].tolist() == [[2, 0, -1], [-1, -1, -1]]
+    assert (m[0, 1] == -1).all() and (m[2] == -1).all()
