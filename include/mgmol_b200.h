@@ -77,6 +77,9 @@ typedef struct mgb_grid
     int coord[3];  /* this rank's coordinates        (PEenv::my_mpi)        */
 } mgb_grid;
 
+/* communicator of a decomposed run (section "multi-GPU" below) */
+typedef struct mgb_comm mgb_comm;
+
 const char* mgb_last_error(void);
 int mgb_version(void);
 /* number of kernels launched by this library since load (all streams) */
@@ -151,6 +154,13 @@ int mgb_residual(int lap_type, int dtype, const mgb_grid* grid, const void* phi,
 int mgb_hpsi_host(int lap_type, int dtype, const mgb_grid* grid, const void* phi_host,
     size_t ld, const double* vtot_host, void* hphi_host, size_t ldh, int nfunc,
     int chunk);
+/* The same for one rank of an x-split domain (collective over the
+ * communicator): every rank streams ITS sub-box through ITS GPU and PCIe link;
+ * the fused kernel of block i reads the neighbours' block i in place from their
+ * input rings over NVLink, fenced by the neighbour barrier.                   */
+int mgb_hpsi_host_peer(mgb_comm* comm, int lap_type, int dtype, const mgb_grid* grid,
+    const void* phi_host, size_t ld, const double* vtot_host, void* hphi_host,
+    size_t ldh, int nfunc, int chunk);
 int mgb_host_register(void* ptr, size_t bytes);
 int mgb_host_unregister(void* ptr);
 
@@ -261,7 +271,6 @@ int mgb_precond_destroy(mgb_precond* p);
  * the neighbours' boundary planes in place over NVLink; other decompositions
  * run the literal sequence with the packed Y -> Z -> X exchange.  Calls are
  * then collective over the communicator.                                     */
-typedef struct mgb_comm mgb_comm;
 int mgb_precond_set_comm(mgb_precond* p, mgb_comm* comm);
 /* OrbitalsPreconditioning::setup with currentMasks != nullptr (src/
  * OrbitalsPreconditioning.cc:59-67 -> GridFuncVector::setMasks): every

@@ -58,6 +58,8 @@ _SIGS = {
                              c_void_p, c_void_p]),
     "mgb_hpsi_host": (c_int, [c_int, c_int, ctypes.POINTER(MgbGrid), c_void_p, c_size_t,
                               c_void_p, c_void_p, c_size_t, c_int, c_int]),
+    "mgb_hpsi_host_peer": (c_int, [c_void_p, c_int, c_int, ctypes.POINTER(MgbGrid), c_void_p,
+                                   c_size_t, c_void_p, c_void_p, c_size_t, c_int, c_int]),
     "mgb_host_register": (c_int, [c_void_p, c_size_t]),
     "mgb_host_unregister": (c_int, [c_void_p]),
     "mgb_hpsi_last_path": (c_int, []),

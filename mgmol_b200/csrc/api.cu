@@ -353,7 +353,7 @@ int mgb_residual(int lap_type, int dtype, const mgb_grid* grid, const void* phi,
     {
         // applyB (ct.Mehrstellen()): tmp = B phi  (src/MGmol.cc:1250-1260)
         const size_t es = dtype == MGB_F64 ? 8 : 4;
-        void* tmp       = scratch(3, npt * (size_t)nfunc * es);
+        void* tmp       = scratch(6, npt * (size_t)nfunc * es);
         if (!tmp) return MGB_ECUDA;
         if (int rc = mgb_apply_b(lap_type, dtype, grid, phi, ld, tmp, npt, nfunc, xhalo_phi, stream))
             return rc;
@@ -430,18 +430,21 @@ int mgb_host_unregister(void* ptr)
     return MGB_OK;
 }
 
-int mgb_hpsi_host(int lap_type, int dtype, const mgb_grid* grid, const void* phi_host,
-    size_t ld, const double* vtot_host, void* hphi_host, size_t ldh, int nfunc,
-    int chunk)
+static int hpsi_host_impl(mgb_comm* comm, int lap_type, int dtype, const mgb_grid* grid,
+    const void* phi_host, size_t ld, const double* vtot_host, void* hphi_host, size_t ldh,
+    int nfunc, int chunk)
 {
     if (int rc = require_device()) return rc;
     if (int rc = check_grid(grid)) return rc;
     MGB_REQUIRE(phi_host && vtot_host && hphi_host, "mgb_hpsi_host: null pointer");
     MGB_REQUIRE(dtype == MGB_F32 || dtype == MGB_F64, "mgb_hpsi_host: bad dtype %d", dtype);
     MGB_REQUIRE(nfunc >= 0 && chunk >= 0, "mgb_hpsi_host: negative count");
-    MGB_REQUIRE(grid->nproc[0] == 1 && grid->nproc[1] == 1 && grid->nproc[2] == 1,
-        "mgb_hpsi_host: the host-buffer entry serves single-rank boxes; a split "
-        "domain keeps its orbitals resident and uses mgb_hpsi + mgb_halo_*");
+    const bool split = grid->nproc[0] > 1;
+    MGB_REQUIRE(grid->nproc[1] == 1 && grid->nproc[2] == 1 && (!split || comm),
+        "mgb_hpsi_host: the host-buffer entry serves single-rank boxes and, with a "
+        "communicator (mgb_hpsi_host_peer), x-split domains");
+    MGB_REQUIRE(!split || grid->dim[0] * grid->nproc[0] == grid->gdim[0],
+        "mgb_hpsi_host_peer: x must be split evenly");
     const size_t npt = (size_t)grid->dim[0] * grid->dim[1] * grid->dim[2];
     MGB_REQUIRE(ld >= npt && ldh >= npt, "mgb_hpsi_host: leading dimension < npt");
     if (nfunc == 0) return MGB_OK;
@@ -473,11 +476,34 @@ int mgb_hpsi_host(int lap_type, int dtype, const mgb_grid* grid, const void* phi
     }
     if (chunk > nfunc) chunk = nfunc;
     const size_t slot_bytes = (size_t)chunk * ldd * es;
+    const int g             = (lap_type == MGB_LAP_4) ? 2 : 1;
+    const size_t plane      = (size_t)grid->dim[1] * grid->dim[2];
+    unsigned char* din_old  = (unsigned char*)scratch(3, 0);
     unsigned char* din  = (unsigned char*)scratch(3, NS * slot_bytes);
     unsigned char* dout = (unsigned char*)scratch(4, NS * slot_bytes);
-    double* dv          = (double*)scratch(5, npt * sizeof(double));
+    double* dv          = (double*)scratch(5, (npt + 2 * g * plane) * sizeof(double));
     if (!din || !dout || !dv) return MGB_ECUDA;
     MGB_CUDA(cudaMemcpyAsync(dv, vtot_host, npt * sizeof(double), cudaMemcpyHostToDevice, s_in));
+    double* xv = dv + npt; // x halo of the potential (2g planes)
+    const unsigned char *din_w = nullptr, *din_e = nullptr;
+    if (split)
+    {
+        // the input ring is what the neighbours read in place: publish it (again
+        // if it was re-allocated; collective -- every rank runs the same sizes)
+        if (din != din_old || !peer_view(comm, din, comm_rank_of(grid, grid->coord[0], 0, 0)))
+            if (int rc = mgb_peer_register(comm, din, (void*)s_in)) return rc;
+        din_w = (const unsigned char*)peer_view(
+            comm, din, comm_rank_of(grid, grid->coord[0] - 1, grid->coord[1], grid->coord[2]));
+        din_e = (const unsigned char*)peer_view(
+            comm, din, comm_rank_of(grid, grid->coord[0] + 1, grid->coord[1], grid->coord[2]));
+        if (!din_w || !din_e)
+        {
+            set_error("mgb_hpsi_host_peer: the neighbours' input rings cannot be mapped");
+            return MGB_ENOTSUP;
+        }
+        if (int rc = mgb_halo_exchange_x(comm, MGB_F64, grid, g, dv, npt, xv, 1, (void*)s_in))
+            return rc;
+    }
 
     const int nchunks = (nfunc + chunk - 1) / chunk;
     for (int i = 0; i < nchunks; i++)
@@ -495,9 +521,26 @@ int mgb_hpsi_host(int lap_type, int dtype, const mgb_grid* grid, const void* phi
         MGB_CUDA(cudaStreamWaitEvent(s_k, ev_in[slot], 0));
         // the copy-out that last read this output slot must be done
         if (i >= NS) MGB_CUDA(cudaStreamWaitEvent(s_k, ev_out[slot], 0));
-        if (int rc = mgb_hpsi(lap_type, dtype, grid, in, ldd, dv, out, ldd, nf, nullptr,
-                nullptr, (void*)s_k))
-            return rc;
+        if (!split)
+        {
+            if (int rc = mgb_hpsi(lap_type, dtype, grid, in, ldd, dv, out, ldd, nf, nullptr,
+                    nullptr, (void*)s_k))
+                return rc;
+        }
+        else
+        {
+            // every rank's block i has landed in its slot -> fused kernel reading
+            // the neighbours' slots in place -> nobody refills a slot early
+            if (int rc = comm_barrier_neighbors(comm, grid, s_k)) return rc;
+            const int force = g_force_path;
+            g_force_path    = 1;
+            const int rc    = hpsi_entry(lap_type, dtype, grid, in, ldd, dv, out, ldd, nf, nullptr,
+                xv, din_w + (size_t)slot * slot_bytes, din_e + (size_t)slot * slot_bytes, nullptr,
+                nullptr, (void*)s_k);
+            g_force_path = force;
+            if (rc) return rc;
+            if (int rc2 = comm_barrier_neighbors(comm, grid, s_k)) return rc2;
+        }
         MGB_CUDA(cudaEventRecord(ev_k[slot], s_k));
         MGB_CUDA(cudaStreamWaitEvent(s_out, ev_k[slot], 0));
         MGB_CUDA(cudaMemcpy2DAsync((unsigned char*)hphi_host + (size_t)f0 * ldh * es, ldh * es, out,
@@ -508,6 +551,25 @@ int mgb_hpsi_host(int lap_type, int dtype, const mgb_grid* grid, const void* phi
     MGB_CUDA(cudaStreamSynchronize(s_k));
     MGB_CUDA(cudaStreamSynchronize(s_in));
     return MGB_OK;
+}
+
+int mgb_hpsi_host(int lap_type, int dtype, const mgb_grid* grid, const void* phi_host,
+    size_t ld, const double* vtot_host, void* hphi_host, size_t ldh, int nfunc,
+    int chunk)
+{
+    MGB_REQUIRE(grid && grid->nproc[0] == 1,
+        "mgb_hpsi_host: x is split; use mgb_hpsi_host_peer with the communicator");
+    return hpsi_host_impl(nullptr, lap_type, dtype, grid, phi_host, ld, vtot_host, hphi_host,
+        ldh, nfunc, chunk);
+}
+
+int mgb_hpsi_host_peer(mgb_comm* comm, int lap_type, int dtype, const mgb_grid* grid,
+    const void* phi_host, size_t ld, const double* vtot_host, void* hphi_host, size_t ldh,
+    int nfunc, int chunk)
+{
+    MGB_REQUIRE(comm, "mgb_hpsi_host_peer: null communicator");
+    return hpsi_host_impl(comm, lap_type, dtype, grid, phi_host, ld, vtot_host, hphi_host, ldh,
+        nfunc, chunk);
 }
 
 } // extern "C"

@@ -54,7 +54,7 @@ template <typename T>
 static int dot_cols_t(size_t n, int nfunc, double alpha, const T* x, size_t ldx, const T* y,
     size_t ldy, double* out, cudaStream_t st)
 {
-    double* partial = (double*)scratch(4, sizeof(double) * kDotBlocks * (size_t)nfunc);
+    double* partial = (double*)scratch(7, sizeof(double) * kDotBlocks * (size_t)nfunc);
     if (!partial) return MGB_ECUDA;
     for (int f0 = 0; f0 < nfunc; f0 += 65535)
     {

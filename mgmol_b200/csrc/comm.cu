@@ -105,6 +105,7 @@ struct PeerEntry
     std::vector<unsigned long long> offset; // per rank: offset of the array inside it
     std::vector<void*> mapped;              // per rank: the array in MY address space
     std::vector<int> opened_id;             // per rank: which opened allocation (-1: none)
+    size_t my_bytes;                        // bytes from my array's start to the end of its allocation
 };
 
 // one peer allocation opened with cudaIpcOpenMemHandle, shared by every
@@ -369,7 +370,21 @@ const void* peer_view(mgb_comm* c, const void* local, int rank)
 {
     if (!c || !c->peers) return nullptr;
     auto it = c->peers->find(local);
-    if (it == c->peers->end()) return nullptr;
+    if (it == c->peers->end())
+    {
+        // a position inside a registered array (e.g. a ring slot of a registered
+        // workspace): same displacement inside the neighbour's array
+        for (auto& kv : *c->peers)
+        {
+            const char* base = (const char*)kv.first;
+            if ((const char*)local > base && (const char*)local < base + kv.second.my_bytes)
+            {
+                const void* pb = peer_view(c, kv.first, rank);
+                return pb ? (const char*)pb + ((const char*)local - base) : nullptr;
+            }
+        }
+        return nullptr;
+    }
     PeerEntry& e = it->second;
     if (rank == c->rank) return local;
     if (e.mapped[rank]) return e.mapped[rank];
@@ -594,6 +609,7 @@ int mgb_peer_register(mgb_comm* c, const void* ptr, void* stream)
     e.offset.resize(c->nranks);
     e.mapped.assign(c->nranks, nullptr);
     e.opened_id.assign(c->nranks, -1);
+    e.my_bytes = size - (size_t)mine.off;
     mgb_peer_unregister(c, ptr); // a stale entry of a freed array at this address
     for (int r = 0; r < c->nranks; r++)
     {

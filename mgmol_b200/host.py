@@ -287,6 +287,19 @@ class Lap:
         return hphi_host
 
 
+    def applyWithPotHostPeer(self, comm, phi_host, vtot_host, hphi_host, chunk=0):
+        """applyWithPotHost for one rank of an x-split domain (collective): every
+        rank streams its sub-box through its own GPU; halos are read in place
+        from the neighbours' input rings (mgb_hpsi_host_peer)."""
+        assert not phi_host.is_cuda and not hphi_host.is_cuda and not vtot_host.is_cuda
+        assert phi_host.is_contiguous() and hphi_host.is_contiguous()
+        check(lib().mgb_hpsi_host_peer(
+            comm.handle, self.type_, _dt(phi_host), self.grid_.ref(), _p(phi_host),
+            self.grid_.size(), _p(vtot_host), _p(hphi_host), self.grid_.size(),
+            phi_host.shape[0], int(chunk)))
+        return hphi_host
+
+
 class LapFactory:
     """src/LapFactory.h:26-56."""
 

@@ -77,6 +77,16 @@ def main():
                     check("hpsi x-split peer reads %s lap%d bc%s" % (dt, lap, bc),
                           torch.equal(out2, ref[(slice(None),) + box]))
                     comm.unregister(mine)
+                    # ---- and from HOST buffers: per-rank pipeline, halos in
+                    # place from the neighbours' input rings
+                    if bc == (1, 1, 1):
+                        hp = mine.cpu().pin_memory()
+                        hv = vmine.cpu().pin_memory()
+                        ho = torch.empty_like(hp).pin_memory()
+                        H.LapFactory.createLap(grid, lap).applyWithPotHostPeer(
+                            comm, hp, hv, ho, chunk=4)
+                        check("hpsi x-split host pipeline %s lap%d" % (dt, lap),
+                              torch.equal(ho.cuda(), ref[(slice(None),) + box]))
                 except H.MgbError as e:
                     check("hpsi x-split peer reads %s lap%d bc%s: %s" % (dt, lap, bc, e), False)
 
