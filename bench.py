@@ -343,6 +343,20 @@ def run_ours(args):
     torch.cuda.set_device(local)
     comm = None
     if world > 1:
+        # keep this rank's host buffers (and its copy threads) on the NUMA node of
+        # its GPU: the pinned host blocks of the end-to-end leg are first-touched
+        # by this process
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(local)
+            words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+            cpus = {64 * w + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1}
+            cpus &= os.sched_getaffinity(0)
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+        except Exception:  # noqa: BLE001
+            pass
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         from mgmol_b200.parallel import Communicator
         comm = Communicator(rank, world)
