@@ -347,6 +347,8 @@ def run_ours(args):
         # its GPU: the pinned host blocks of the end-to-end leg are first-touched
         # by this process
         try:
+            if os.environ.get("MGB_BENCH_NO_BIND"):
+                raise RuntimeError("binding disabled")
             import pynvml
             pynvml.nvmlInit()
             h = pynvml.nvmlDeviceGetHandleByIndex(local)
@@ -355,6 +357,8 @@ def run_ours(args):
             cpus &= os.sched_getaffinity(0)
             if cpus:
                 os.sched_setaffinity(0, cpus)
+                if os.environ.get("MGB_BENCH_VERBOSE"):
+                    sys.stderr.write("rank %d bound to %d cpus\n" % (rank, len(cpus)))
         except Exception:  # noqa: BLE001
             pass
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
