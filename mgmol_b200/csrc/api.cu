@@ -62,8 +62,8 @@ int check_grid(const mgb_grid* gr)
 }
 
 // grow-only scratch slots
-static void* g_scratch[8]      = { nullptr };
-static size_t g_scratch_sz[8]  = { 0 };
+static void* g_scratch[12]     = { nullptr };
+static size_t g_scratch_sz[12] = { 0 };
 static std::mutex g_scratch_mu;
 void* scratch(int slot, size_t bytes)
 {

@@ -851,6 +851,198 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_nn(long long npt, int n, i
     cp_async_wait<0>();
 }
 
+// ---------------------------------------------------------------------------
+// Phi M for ORBDTYPE float on the FP32-class tensor path (3xTF32, see
+// k_gemm_tn_tf32): Out^T tile (128 orbitals x 128 points) = Mf^T tile x Phi tile
+// with Mf = (float)(alpha M) prepared once per call.  The reduction is only
+// K = numst long; the tensor core's FP32 sums are folded into a second FP32
+// accumulator every 64 terms.  Persistent CTAs like k_gemm_nn.
+// ---------------------------------------------------------------------------
+__global__ void k_scale_to_float(long long n, double alpha, const double* __restrict__ in,
+    float* __restrict__ out)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (float)(alpha * in[i]);
+}
+
+constexpr int PP32 = 128 + 8; // point-major Phi slab pitch (floats)
+
+template <bool HASD>
+__global__ void __launch_bounds__(NTHREADS, 1) k_gemm_nn_tf32(long long npt, int n, int k,
+    const float* __restrict__ Phi, long long lda, const float* __restrict__ Mf, int ldm,
+    double beta, float* __restrict__ Out, long long ldc, long long nitems, int jtiles,
+    double gamma, const float* __restrict__ D, long long ldd)
+{
+    extern __shared__ __align__(16) unsigned char smraw[];
+    float* Ms = reinterpret_cast<float*>(smraw);     // [ST32][128 j][P32]   (K-major)
+    float* Ps = Ms + ST32 * 128 * P32;               // [ST32][KC32 l][PP32] (point-major)
+
+    const long long i0 = nitems * blockIdx.x / gridDim.x;
+    const long long i1 = nitems * (blockIdx.x + 1) / gridDim.x;
+    if (i1 <= i0) return;
+    const int nkt         = (k + KC32 - 1) / KC32;
+    const long long total = (i1 - i0) * nkt;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp >> 2, wn = warp & 3;
+    const int g = lane >> 2, t = lane & 3;
+    const bool vec2 = (((uintptr_t)Out) % 8 == 0) && (ldc % 2 == 0);
+
+    float c[2][4][4], hi[2][4][4];
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+#pragma unroll
+            for (int e = 0; e < 4; e++)
+                c[i][j][e] = hi[i][j][e] = 0.f;
+
+    long long p_item = i0, p_issued = 0;
+    int p_kt = 0, p_stage = 0;
+    auto issue = [&]() {
+        if (p_issued < total)
+        {
+            const int j0       = (int)(p_item % jtiles) * 128;
+            const long long p0 = (p_item / jtiles) * 128;
+            load_kmajor<float, KC32>(
+                Ms + p_stage * 128 * P32, Mf, ldm, j0, n, (long long)p_kt * KC32, k, tid);
+            constexpr int CPR = 128 / 4; // 16-byte chunks per row of 128 points
+            constexpr int TOT = KC32 * CPR;
+            float* sm = Ps + p_stage * KC32 * PP32;
+#pragma unroll
+            for (int cidx = tid; cidx < TOT; cidx += NTHREADS)
+            {
+                const int r  = cidx / CPR;
+                const int cc = cidx % CPR;
+                const int l  = p_kt * KC32 + r;
+                const long long p = p0 + (long long)cc * 4;
+                int valid = 0;
+                if (l < k && p < npt)
+                {
+                    const long long rem = npt - p;
+                    valid = rem >= 4 ? 16 : (int)rem * 4;
+                }
+                const float* src = Phi + (long long)(l < k ? l : 0) * lda + (valid ? p : 0);
+                cp_async16(sm + r * PP32 + cc * 4, src, valid);
+            }
+            p_issued++;
+            if (++p_kt == nkt)
+            {
+                p_kt = 0;
+                p_item++;
+            }
+            if (++p_stage == ST32) p_stage = 0;
+        }
+        cp_async_commit();
+    };
+#pragma unroll
+    for (int s = 0; s < ST32 - 1; s++)
+        issue();
+
+    long long item = i0;
+    int kt = 0, stage = 0;
+    for (long long it = 0; it < total; it++)
+    {
+        cp_async_wait<ST32 - 2>();
+        __syncthreads();
+        issue();
+        const float* as = Ms + stage * 128 * P32 + (wm * 32 + g) * P32 + t;
+        const float* bs = Ps + stage * KC32 * PP32 + t * PP32 + wn * 32 + g;
+#pragma unroll
+        for (int kk = 0; kk < KC32 / 8; kk++)
+        {
+            uint32_t ah[2][4], al[2][4];
+#pragma unroll
+            for (int i = 0; i < 2; i++)
+#pragma unroll
+                for (int r = 0; r < 4; r++)
+                {
+                    const float v = as[(i * 16 + (r & 1) * 8) * P32 + kk * 8 + (r >> 1) * 4];
+                    ah[i][r]      = to_tf32(v);
+                    al[i][r]      = to_tf32(v - __uint_as_float(ah[i][r]));
+                }
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+            {
+                uint32_t bh[2], bl[2];
+#pragma unroll
+                for (int r = 0; r < 2; r++)
+                {
+                    // b0 (k = t, n = g)  b1 (k = t + 4, n = g)
+                    const float v = bs[(kk * 8 + r * 4) * PP32 + j * 8];
+                    bh[r]         = to_tf32(v);
+                    bl[r]         = to_tf32(v - __uint_as_float(bh[r]));
+                }
+#pragma unroll
+                for (int i = 0; i < 2; i++)
+                {
+                    mma_tf32(c[i][j], al[i], bh);
+                    mma_tf32(c[i][j], ah[i], bl);
+                    mma_tf32(c[i][j], ah[i], bh);
+                }
+            }
+        }
+        // slab sums into the second-level FP32 sums every two slabs (64 terms)
+        if ((kt & 1) == 1 || kt == nkt - 1)
+        {
+#pragma unroll
+            for (int i = 0; i < 2; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+#pragma unroll
+                    for (int e = 0; e < 4; e++)
+                    {
+                        hi[i][j][e] = __fadd_rn(hi[i][j][e], c[i][j][e]);
+                        c[i][j][e]  = 0.f;
+                    }
+        }
+        if (++stage == ST32) stage = 0;
+        if (++kt == nkt)
+        {
+            // thread holds Out(j0 + wm*32 + i*16 + g + 8*(e>>1), p0 + wn*32 + j*8 + 2t + (e&1))
+            const int j0       = (int)(item % jtiles) * 128;
+            const long long p0 = (item / jtiles) * 128;
+#pragma unroll
+            for (int i = 0; i < 2; i++)
+#pragma unroll
+                for (int h = 0; h < 2; h++)
+                {
+                    const int jj = j0 + wm * 32 + i * 16 + g + 8 * h;
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                    {
+                        const long long pp = p0 + wn * 32 + j * 8 + 2 * t;
+                        float* o = Out + (long long)jj * ldc + pp;
+                        float r[2];
+#pragma unroll
+                        for (int e = 0; e < 2; e++)
+                        {
+                            float base = 0.f;
+                            if (beta != 0. && jj < n && pp + e < npt)
+                                base = (float)(beta * (double)o[e]);
+                            r[e] = base + hi[i][j][2 * h + e];
+                            hi[i][j][2 * h + e] = 0.f;
+                            if (HASD && jj < n && pp + e < npt)
+                                r[e] += (float)(gamma * (double)D[(long long)jj * ldd + pp + e]);
+                        }
+                        if (jj < n)
+                        {
+                            if (vec2 && pp + 1 < npt)
+                                *reinterpret_cast<float2*>(o) = make_float2(r[0], r[1]);
+                            else
+                            {
+                                if (pp < npt) o[0] = r[0];
+                                if (pp + 1 < npt) o[1] = r[1];
+                            }
+                        }
+                    }
+                }
+            kt = 0;
+            item++;
+        }
+    }
+    cp_async_wait<0>();
+}
+
 // slow, always-applicable fallbacks (unaligned operands): one thread per
 // output element, sequential K like MPdot
 template <typename T>
@@ -1067,15 +1259,58 @@ static int gemm_nn_t(size_t m, int n, int k, double alpha, const T* A, size_t ld
         }
         return MGB_OK;
     }
+    const long long ptiles = (long long)((m + 127) / 128);
+    const int jtiles       = (n + 127) / 128;
+    const long long nitems = ptiles * jtiles;
+    const unsigned grid    = (unsigned)(nitems < num_sms() ? nitems : num_sms());
+    if (sizeof(T) == 4 && !g_f32_exact)
+    {
+        // FP32-class tensor tiles: Mf = (float)(alpha M), K-major with a 16-byte
+        // aligned leading dimension
+        const int ldf = (k + 3) / 4 * 4;
+        float* Mf     = (float*)scratch(8, (size_t)ldf * n * sizeof(float) + 256);
+        if (!Mf) return MGB_ECUDA;
+        if (ldf == ldm)
+        {
+            const long long cnt = (long long)ldm * n;
+            k_scale_to_float<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(cnt, alpha, M, Mf);
+        }
+        else
+        {
+            MGB_CUDA(cudaMemsetAsync(Mf, 0, (size_t)ldf * n * sizeof(float), st));
+            for (int j = 0; j < n; j++) // rare: odd numst
+                k_scale_to_float<<<(k + 255) / 256, 256, 0, st>>>(
+                    k, alpha, M + (size_t)j * ldm, Mf + (size_t)j * ldf);
+        }
+        MGB_LAUNCHED("k_scale_to_float");
+        const size_t smem32
+            = (size_t)ST32 * 128 * P32 * sizeof(float) + (size_t)ST32 * KC32 * PP32 * sizeof(float);
+        if (D)
+        {
+            auto kern = k_gemm_nn_tf32<true>;
+            MGB_CUDA(cudaFuncSetAttribute(
+                kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32));
+            kern<<<grid, NTHREADS, smem32, st>>>((long long)m, n, k, (const float*)A,
+                (long long)lda, Mf, ldf, beta, (float*)Out, (long long)ldc, nitems, jtiles, gamma,
+                (const float*)D, (long long)ldd);
+        }
+        else
+        {
+            auto kern = k_gemm_nn_tf32<false>;
+            MGB_CUDA(cudaFuncSetAttribute(
+                kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32));
+            kern<<<grid, NTHREADS, smem32, st>>>((long long)m, n, k, (const float*)A,
+                (long long)lda, Mf, ldf, beta, (float*)Out, (long long)ldc, nitems, jtiles, gamma,
+                (const float*)D, (long long)ldd);
+        }
+        MGB_LAUNCHED("k_gemm_nn_tf32");
+        return MGB_OK;
+    }
     int kcv = 32;
     if (const char* env = getenv("MGB_NN_KC")) kcv = atoi(env) == 16 ? 16 : 32;
     const int st_     = kcv == 32 ? 3 : 4;
     const size_t smem = (size_t)st_ * 128 * (kcv + PADK) * sizeof(double)
                         + (size_t)st_ * kcv * PitchP<T>::value * sizeof(T);
-    const long long ptiles = (long long)((m + 127) / 128);
-    const int jtiles       = (n + 127) / 128;
-    const long long nitems = ptiles * jtiles;
-    const unsigned grid    = (unsigned)(nitems < num_sms() ? nitems : num_sms());
 #define MGB_NN_LAUNCH(KV, STV, HD)                                                        \
     {                                                                                     \
         auto kern = k_gemm_nn<T, KV, STV, HD>;                                            \

@@ -215,4 +215,4 @@ def test_locgrid_contractions_per_slab(H, port, dt):
         lm = host(orb.matrixToLocalMatrix(iloc, dev(M)))
         ex = port.gemm_nn(phi[:, iloc * s0:(iloc + 1) * s0], lm)
         got = out[:, iloc * s0:(iloc + 1) * s0]
-        assert np.abs(got - ex).max() <= (1e-13 if dt == np.float64 else 1e-6) * np.abs(ex).max()
+        assert np.abs(got - ex).max() <= (1e-13 if dt == np.float64 else 3e-6) * np.abs(ex).max()
