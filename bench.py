@@ -311,6 +311,24 @@ def measure_pieces(H, grid, phi, ham, lap_type, tdt, S, norb, npt, comm=None, hs
                                            "frac": 2 * fl / (ms * 1e-3) / 1e12 / fp64_peak,
                                            "flops": "2 N^2 K"}}
 
+    if comm is None:
+        # "next" rows: residual assembly res = (B Phi) theta - H Phi in one
+        # contraction pass with a fused epilogue, and the density rho += sum_j (Phi X)_j phi_j
+        ms = _time_cuda(torch, lambda: H.computeResidualUsingHPhi(ham.lapOper(), phi, hphi, M, prod))
+        out["residual"] = {"ms": ms, "roofline": {"bound": "tensor",
+                                                  "achieved": 2 * fl / (ms * 1e-3) / 1e12,
+                                                  "peak": fp64_peak, "unit": "TFLOP/s",
+                                                  "frac": 2 * fl / (ms * 1e-3) / 1e12 / fp64_peak,
+                                                  "flops": "2 N^2 K"}}
+        rho = torch.zeros(grid.shape(), dtype=torch.float64, device="cuda")
+        ms = _time_cuda(torch, lambda: H.computeRhoUsingBlas3(phi, M, rho))
+        out["density"] = {"ms": ms, "roofline": {"bound": "tensor",
+                                                 "achieved": 2 * fl / (ms * 1e-3) / 1e12,
+                                                 "peak": fp64_peak, "unit": "TFLOP/s",
+                                                 "frac": 2 * fl / (ms * 1e-3) / 1e12 / fp64_peak,
+                                                 "flops": "2 N^2 K (+ 2 N K)"}}
+        del rho
+
     # one orbital-update iteration's worth of the in-scope path, back to back on
     # one stream the way an SCF step orders it: H psi (with the
     # halo), Phi^T H Phi (+ all-reduce), preconditioned residual, Gram

@@ -336,6 +336,16 @@ int mgb_gemm_nn(int dtype, size_t m, int n, int k, double alpha, const void* A,
     size_t lda, const double* M, int ldm, double beta, void* Cout, size_t ldc,
     void* stream);
 
+/* Rho::computeRhoSubdomainUsingBlas3 (src/Rho.cc:359-448) for one x-slab of
+ * nrows points: rho[i] += sum_j (Phi1 X)[i][j] * phi2[i][j], X = localX (column-
+ * major nfunc x nfunc double on the device), rho RHODTYPE double.  The
+ * contraction runs in point chunks through a library workspace (MPgemmNN
+ * rounding to ORBDTYPE kept), the accumulation visits j in the reference's
+ * order.                                                                     */
+int mgb_rho_blas3(int dtype, size_t nrows, int nfunc, const void* phi1, size_t ld1,
+    const double* X, int ldx, const void* phi2, size_t ld2, double* rho,
+    void* stream);
+
 /* ---- multi-GPU: one process per GPU, 3-D block decomposition of pb::PEenv.
  * The communicator wraps NCCL; the unique id (128 bytes) is created on rank 0
  * with mgb_comm_unique_id and distributed by the caller (MPI_Bcast in MGmol,

@@ -90,3 +90,68 @@ extern "C" int mgb_dot_cols(int dtype, size_t n, int nfunc, double alpha, const 
     set_error("mgb_dot_cols: bad dtype");
     return MGB_EINVAL;
 }
+
+// ---------------------------------------------------------------------------
+// Electron density from non-orthogonal orbitals:
+// Rho::computeRhoSubdomainUsingBlas3 (src/Rho.cc:359-448)
+//     product = Phi1 X            (MPgemmNN, ORBDTYPE)
+//     rho[i] += product[j][i] * phi2[j][i]   for j = 0 .. ncols-1, in this order
+// for one x-slab of nrows points.  The contraction runs on the tensor path in
+// point chunks through a library workspace; the accumulation is one pass over
+// the chunk (product and phi2 read once), the j loop sequential per point as in
+// the reference (so rho is bit-identical given the same product).
+// ---------------------------------------------------------------------------
+namespace mgb
+{
+int gemm_nn_fused(int dtype, size_t m, int n, int k, double alpha, const void* A, size_t lda,
+    const double* M, int ldm, double beta, void* Out, size_t ldc, double gamma, const void* D,
+    size_t ldd, cudaStream_t st);
+
+template <typename T>
+__global__ void k_rho_accumulate(long long n, int nfunc, const T* __restrict__ product,
+    long long ldp, const T* __restrict__ phi2, long long ld2, double* __restrict__ rho)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double s = rho[i];
+    for (int j = 0; j < nfunc; j++)
+        s += (double)(product[(long long)j * ldp + i] * phi2[(long long)j * ld2 + i]);
+    rho[i] = s;
+}
+} // namespace mgb
+
+extern "C" int mgb_rho_blas3(int dtype, size_t nrows, int nfunc, const void* phi1, size_t ld1,
+    const double* X, int ldx, const void* phi2, size_t ld2, double* rho, void* stream)
+{
+    if (int rc = require_device()) return rc;
+    MGB_REQUIRE(phi1 && phi2 && X && rho, "mgb_rho_blas3: null pointer");
+    MGB_REQUIRE(dtype == MGB_F32 || dtype == MGB_F64, "mgb_rho_blas3: bad dtype");
+    MGB_REQUIRE(nfunc >= 0 && ld1 >= nrows && ld2 >= nrows && ldx >= nfunc,
+        "mgb_rho_blas3: bad dimensions");
+    if (nfunc == 0 || nrows == 0) return MGB_OK;
+    cudaStream_t st = as_stream(stream);
+    const size_t es = dtype == MGB_F64 ? 8 : 4;
+    // point chunks of <= 2^20 points (a multiple of 128: whole tiles, aligned)
+    size_t chunk = (size_t)1 << 20;
+    if (chunk > nrows) chunk = (nrows + 127) / 128 * 128;
+    void* product = scratch(9, chunk * (size_t)nfunc * es);
+    if (!product) return MGB_ECUDA;
+    for (size_t p0 = 0; p0 < nrows; p0 += chunk)
+    {
+        const size_t m = (nrows - p0 < chunk) ? nrows - p0 : chunk;
+        if (int rc = gemm_nn_fused(dtype, m, nfunc, nfunc, 1., (const char*)phi1 + p0 * es, ld1, X,
+                ldx, 0., product, chunk, 0., nullptr, 0, st))
+            return rc;
+        const unsigned blocks = (unsigned)((m + 255) / 256);
+        if (dtype == MGB_F64)
+            k_rho_accumulate<double><<<blocks, 256, 0, st>>>((long long)m, nfunc,
+                (const double*)product, (long long)chunk, (const double*)phi2 + p0,
+                (long long)ld2, rho + p0);
+        else
+            k_rho_accumulate<float><<<blocks, 256, 0, st>>>((long long)m, nfunc,
+                (const float*)product, (long long)chunk, (const float*)phi2 + p0, (long long)ld2,
+                rho + p0);
+        MGB_LAUNCHED("k_rho_accumulate");
+    }
+    return MGB_OK;
+}

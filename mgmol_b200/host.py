@@ -660,6 +660,18 @@ class Hamiltonian:
         return phi1.computeLocalProduct(self.hlphi_, comm)
 
 
+def computeRhoUsingBlas3(orbitals1, localX, rho, orbitals2=None):
+    """Rho::computeRhoSubdomainUsingBlas3 (src/Rho.cc:359-448) on the whole local
+    box: rho (double tensor of the grid's shape) += sum_ij X_ij phi1_i phi2_j."""
+    o2 = orbitals1 if orbitals2 is None else orbitals2
+    n = orbitals1.chromatic_number()
+    g = orbitals1.grid_
+    xcol = localX.t().contiguous()
+    check(lib().mgb_rho_blas3(_dt(orbitals1.psi_), g.size(), n, _p(orbitals1.psi_), g.size(),
+                              _p(xcol), n, _p(o2.psi_), g.size(), _p(rho), _stream()))
+    return rho
+
+
 def computeResidualUsingHPhi(lapOper, psi, hphi, localT, res, xhalo_phi=None):
     """MGmol::computeResidualUsingHPhi (src/MGmol.cc:1227-1287):
     res = (B psi) theta - hphi in [Ry]; localT[l, j] = theta (numst x numst double

@@ -671,6 +671,31 @@ def test_residual_using_hphi(H, port, dt, lap_type, N, dims):
 
 
 @pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("N,dims", [(5, (12, 8, 16)), (37, (10, 12, 14)), (130, (24, 24, 24))])
+def test_density_blas3(H, port, dt, N, dims):
+    """rho += sum_j (Phi X)_j phi_j (Rho::computeRhoSubdomainUsingBlas3): the
+    oracle's MPgemmNN product, then the reference's j-ordered accumulation with
+    the product formed in ORBDTYPE."""
+    phi = synthetic_orbitals(N, dims, dt)
+    X = np.random.default_rng(12).standard_normal((N, N)) / N
+    X = 0.5 * (X + X.T)
+    grid = H.Grid(dims, (3.0, 2.5, 4.0), 1)
+    A = H.Orbitals(grid, N, TDT[dt], dev(phi))
+    rho0 = np.random.default_rng(13).uniform(0, 1, dims)
+    rho = dev(rho0.copy())
+    H.computeRhoUsingBlas3(A, dev(X), rho)
+    product = port.gemm_nn(phi, X)
+    ref = rho0.copy()
+    for j in range(N):
+        ref += (product[j] * phi[j]).astype(np.float64)
+    exact = rho0 + np.einsum("ixyz,ij,jxyz->xyz", phi.astype(np.float64), X, phi.astype(np.float64))
+    scale = np.abs(exact - rho0).max() + 1.0
+    tol = 1e-13 if dt == np.float64 else 3e-6
+    assert np.abs(host(rho) - ref).max() <= tol * scale * max(1, N / 64)
+    assert np.abs(host(rho) - exact).max() <= (1e-12 if dt == np.float64 else 1e-5) * scale
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
 def test_diagonal_dot_products(H, port, dt):
     """computeDiagonalElementsDotProduct: one launch for all orbitals, double
     accumulation like MPdot."""
