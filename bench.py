@@ -614,8 +614,8 @@ def main():
                          "one full grid per GPU)")
     ap.add_argument("--no-cpu-iteration", action="store_true",
                     help="skip the CPU reference timing of the orbital-update iteration")
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="h2o64", choices=sorted(WORKLOADS))
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])

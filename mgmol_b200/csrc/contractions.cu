@@ -807,6 +807,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_nn(long long npt, int n, i
             for (int i = 0; i < 4; i++)
             {
                 const int jj = j0 + wm * 32 + i * 8 + fr;
+                // the subtrahend of the four pairs of this row: all loads issued
+                // before any is consumed
+                T dv[4][2];
+                if (HASD)
+                {
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+#pragma unroll
+                        for (int e = 0; e < 2; e++)
+                        {
+                            const long long pp = p0 + wn * 32 + j * 8 + fc * 2 + e;
+                            dv[j][e] = (jj < n && pp < npt) ? __ldg(D + (long long)jj * ldd + pp)
+                                                            : (T)0;
+                        }
+                }
 #pragma unroll
                 for (int j = 0; j < 4; j++)
                 {
@@ -824,8 +839,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_nn(long long npt, int n, i
                         acc[i][j][e] = 0.;
                         // fused "Out.axpy(gamma, D)" (MPaxpy: y += (T)(gamma * (double)x),
                         // mputils.cc:222-244) on the freshly rounded product
-                        if (HASD && jj < n && pp + e < npt)
-                            r[e] += (T)(gamma * (double)D[(long long)jj * ldd + pp + e]);
+                        if (HASD) r[e] += (T)(gamma * (double)dv[j][e]);
                     }
                     if (jj < n)
                     {
