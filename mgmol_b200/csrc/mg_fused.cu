@@ -152,9 +152,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_mg_jacobi(const __grid_constant__ J
         // ---------------------------- TMA producer ----------------------------
         if (tid != 0) return;
         unsigned char* stages = smem + kMgBarBytes;
-        // SCALE: the tile is f, which the consumers read again from L2 a few
-        // planes later as the right-hand side -> keep it there
-        const uint64_t pol    = SCALE ? policy_evict_last() : policy_evict_first();
+        const uint64_t pol    = policy_evict_first();
         int norb              = P.nfunc - orb0;
         if (norb > P.NB) norb = P.NB;
         int ylo = y0 - G, yhi = y0 + P.TY;
@@ -282,7 +280,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_mg_jacobi(const __grid_constant__ J
 
     // right-hand side of the first output plane (see the prefetch below)
     float4 fnext[RY];
-    if (active)
+    if (!SCALE && active)
     {
         const float* fp = P.f + (long long)orb * P.ld_f + (long long)xb * plane + pt0;
 #pragma unroll
@@ -297,28 +295,6 @@ __global__ void __launch_bounds__(MAXT, 1) k_mg_jacobi(const __grid_constant__ J
     for (int it = 0; it < nplanes; it++)
     {
         mbar_wait(&full[st_new], par_new);
-        if constexpr (SCALE)
-        {
-            // the tile is f: form v = s * f once per element, in place, as the
-            // plane arrives (every tap then reads v); the threads of one
-            // function's group share the work and meet at a named barrier
-            unsigned char* tile
-                = smem + kMgBarBytes + (size_t)st_new * P.stage_bytes + (size_t)grp * P.tile_bytes;
-            const int nvec = P.tile_bytes >> 4;
-            for (int i = lt; i < nvec; i += P.tpo)
-            {
-                float4* p4 = reinterpret_cast<float4*>(tile) + i;
-                float4 x   = *p4;
-                x.x        = mul_split(sh, sl, x.x);
-                x.y        = mul_split(sh, sl, x.y);
-                x.z        = mul_split(sh, sl, x.z);
-                x.w        = mul_split(sh, sl, x.w);
-                *p4        = x;
-            }
-            // later TMA writes into this stage must not pass these stores
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(P.tpo) : "memory");
-        }
         if (it >= 2 * G)
         {
             const int q = xb + it - 2 * G; // output plane
@@ -359,9 +335,10 @@ __global__ void __launch_bounds__(MAXT, 1) k_mg_jacobi(const __grid_constant__ J
                 // Right-hand side: the values of this plane were requested one
                 // iteration ago (fnext) and the next plane's are requested
                 // now, so the global loads are in flight during a whole plane
-                // of shared-memory work.  (SCALE: the tile was f but now holds
-                // s * f; f comes from L2, where the TMA load just put it.)
+                // of shared-memory work.  (SCALE: the tile IS f -- the centre
+                // values the stencil reads anyway.)
                 float4 fv[RY];
+                if constexpr (!SCALE)
                 {
 #pragma unroll
                     for (int r = 0; r < RY; r++)
@@ -375,8 +352,30 @@ __global__ void __launch_bounds__(MAXT, 1) k_mg_jacobi(const __grid_constant__ J
                     }
                 }
 
-                auto finish = [&](int r, const float(&cen)[4], const float(&av)[4]) {
-                    const float fr[4] = { fv[r].x, fv[r].y, fv[r].z, fv[r].w };
+                auto finish = [&](int r, const float(&cen0)[4], const float(&av0)[4]) {
+                    // SCALE: the stencil ran on the tile's f values; v = s f at
+                    // the centre and A v = s (A f) (A is linear: one product with
+                    // the two-float constant per point instead of one per tap;
+                    // differs from rounding every v_k by < |c|_1 2^-24 |v|, i.e.
+                    // by less than the rounding of v' itself after the damping)
+                    float fr[4], cen[4], av[4];
+#pragma unroll
+                    for (int e = 0; e < 4; e++)
+                    {
+                        if constexpr (SCALE)
+                        {
+                            fr[e]  = cen0[e];
+                            cen[e] = mul_split(sh, sl, cen0[e]);
+                            av[e]  = mul_split(sh, sl, av0[e]);
+                        }
+                        else
+                        {
+                            fr[e]  = (e == 0) ? fv[r].x : (e == 1) ? fv[r].y : (e == 2) ? fv[r].z
+                                                                                       : fv[r].w;
+                            cen[e] = cen0[e];
+                            av[e]  = av0[e];
+                        }
+                    }
                     float vn[4], wn[4];
 #pragma unroll
                     for (int e = 0; e < 4; e++)
