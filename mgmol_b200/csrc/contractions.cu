@@ -10,11 +10,15 @@
 //
 // B200 has no tcgen05 FP64 kind; DMMA.8x8x4 is the FP64 tensor instruction
 // (mma.sync m16n8k16.f64 lowers to it).  Kernel shape: 128x128 CTA tile, 16
-// warps of 32x32, K staged through a 4-deep cp.async ring of 16-wide slabs
-// whose rows are padded to 20 elements (fragment loads conflict-free).
-// Tall-skinny shapes (K = grid points, M = N = orbitals) are split along K;
-// partial tiles are combined by a second kernel in a fixed order, so results
-// are run-to-run deterministic.
+// warps of 32x32, one CTA per SM, K staged through a 3-deep cp.async ring of
+// 32-wide slabs whose rows are padded by 4 elements (fragment loads conflict-
+// free).  The tall-skinny reductions (K = grid points, M = N = orbitals) are
+// scheduled stream-K: every CTA takes an equal share of the (tile, K) space and
+// a fix-up kernel adds the partial tiles in a fixed order, so results are
+// run-to-run deterministic; diagonal Gram tiles do half the tensor work.
+// ORBDTYPE float operands default to error-compensated 3xTF32 tensor tiles
+// (k_gemm_tn_tf32 / k_gemm_nn_tf32); mgb_set_f32_contraction(1) selects the
+// DMMA kernels on widened operands instead.
 #include <cstdint>
 #include <cstdlib>
 
