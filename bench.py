@@ -58,27 +58,62 @@ def measured_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """SM clock and throttle reasons during the timed region: NVML in-process
+    (a query every 5 ms), nvidia-smi as the fallback."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    # nvmlClocksEventReason* bits (nvml.h)
+    BITS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40),
+            ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index = index
-        self.samples = []
+        self.samples = []      # (sm_mhz, reason bitmask)
+        self.max_mhz = None
         self.stop_evt = threading.Event()
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:  # noqa: BLE001
+            self.nvml = None
+
+    def _reasons(self):
+        n = self.nvml
+        for name in ("nvmlDeviceGetCurrentClocksEventReasons",
+                     "nvmlDeviceGetCurrentClocksThrottleReasons"):
+            fn = getattr(n, name, None)
+            if fn is not None:
+                return int(fn(self.h))
+        return 0
 
     def run(self):
         while not self.stop_evt.is_set():
             try:
+                if self.nvml is not None:
+                    mhz = float(self.nvml.nvmlDeviceGetClockInfo(self.h, self.nvml.NVML_CLOCK_SM))
+                    self.samples.append((mhz, self._reasons()))
+                    self.stop_evt.wait(0.005)
+                    continue
                 out = subprocess.run(
                     ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                      "--format=csv,noheader,nounits"],
                     capture_output=True, text=True, timeout=5).stdout.strip()
                 if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
-            except Exception:
+                    f = [x.strip() for x in out.split(",")]
+                    mask = 0
+                    for i, (_, bit) in enumerate(self.BITS):
+                        if len(f) > 2 + i and f[2 + i].lower().startswith("active"):
+                            mask |= bit
+                    self.samples.append((float(f[0]), mask))
+                    if self.max_mhz is None and f[1].replace(".", "").isdigit():
+                        self.max_mhz = float(f[1])
+            except Exception:  # noqa: BLE001
                 pass
             self.stop_evt.wait(0.2)
 
@@ -87,14 +122,14 @@ class ClockSampler(threading.Thread):
         self.join(timeout=6)
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names)
-                   if any(len(s) > 2 + i and s[2 + i].lower().startswith("active")
-                          for s in self.samples)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
-                "sm_max_mhz": float(self.samples[0][1]) if self.samples[0][1].isdigit() else None,
-                "reasons": reasons, "samples": len(self.samples)}
+        sm = sorted(s[0] for s in self.samples)
+        mask = 0
+        for s_ in self.samples:
+            mask |= s_[1]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_mhz,
+                "reasons": [n for n, bit in self.BITS if mask & bit],
+                "samples": len(self.samples),
+                "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 # ---------------------------------------------------------------------------
