@@ -315,11 +315,10 @@ int mgb_apply_b(int lap_type, int dtype, const mgb_grid* grid, const void* phi, 
     if (nfunc == 0) return MGB_OK;
     const size_t es = dtype == MGB_F64 ? 8 : 4;
     cudaStream_t st = as_stream(stream);
-    if (lap_type != MGB_LAP_4M)
+    if (lap_type != MGB_LAP_4M && lap_type != MGB_LAP_4MP)
     {
-        // FDoper::rhs of the other operators is the identity (src/pb/Laph4.h,
-        // Laph2.h ...: B = 1); Laph4MP's B2 (src/pb/FDoper.cc:510-563) is not built
-        MGB_REQUIRE(lap_type != MGB_LAP_4MP, "mgb_apply_b: Laph4MP (rhs_4th_Mehr2) is not built");
+        // FDoper::rhs of the non-compact operators is the identity
+        // (src/pb/FDoper.h:68-79: B = 1)
         MGB_CUDA(cudaMemcpy2DAsync(bphi, ldb * es, phi, ld * es, npt * es, (size_t)nfunc,
             cudaMemcpyDeviceToDevice, st));
         return MGB_OK;
@@ -330,7 +329,9 @@ int mgb_apply_b(int lap_type, int dtype, const mgb_grid* grid, const void* phi, 
         "mgb_gfv_set_with_ghosts + trade + mgb_fd_apply(MGB_FD_RHS_4TH_MEHR1)");
     MGB_REQUIRE(grid->nproc[0] == 1 || xhalo_phi,
         "mgb_apply_b: x is split but no x-halo buffer was given");
-    return rhs_generic(dtype, grid, phi, ld, xhalo_phi, bphi, ldb, nfunc, st);
+    // Laph4M: B (rhs_4th_Mehr1); Laph4MP: B2 (rhs_4th_Mehr2, src/pb/Laph4MP.h:48-51)
+    return rhs_generic(
+        dtype, lap_type == MGB_LAP_4MP, grid, phi, ld, xhalo_phi, bphi, ldb, nfunc, st);
 }
 
 int mgb_residual(int lap_type, int dtype, const mgb_grid* grid, const void* phi, size_t ld,

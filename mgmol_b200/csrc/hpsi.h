@@ -33,10 +33,10 @@ struct HpsiArgs
 int hpsi_tma(const HpsiArgs& a, cudaStream_t st);
 // path 2: generic fused kernel (hpsi_generic.cu), bit-exact.
 int hpsi_generic(const HpsiArgs& a, cudaStream_t st);
-// B u (Mehrstellen right-hand-side operator) on a no-ghost block, bit-exact
+// B u (Mehrstellen right-hand-side operator; mehr2: Laph4MP's B2) on a no-ghost block, bit-exact
 // (hpsi_generic.cu); xhalo: [nfunc][2][ny][nz] on x-split boxes, else null
-int rhs_generic(int dtype, const mgb_grid* gr, const void* phi, size_t ld, const void* xhalo,
-    void* out, size_t ldo, int nfunc, cudaStream_t st);
+int rhs_generic(int dtype, bool mehr2, const mgb_grid* gr, const void* phi, size_t ld,
+    const void* xhalo, void* out, size_t ldo, int nfunc, cudaStream_t st);
 // Out = alpha A M + beta Out + gamma D (contractions.cu); D may be null
 int gemm_nn_fused(int dtype, size_t m, int n, int k, double alpha, const void* A, size_t lda,
     const double* M, int ldm, double beta, void* Out, size_t ldc, double gamma, const void* D,

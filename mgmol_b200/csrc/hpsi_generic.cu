@@ -231,7 +231,9 @@ int hpsi_generic_t(const HpsiArgs& a, cudaStream_t st)
 // / FDkernelRHS_4th_Mehr1 (src/pb/FDkernels.cc:522-584) after setDataWithGhosts
 // + trade_boundaries, as MGmol::computeResidualUsingHPhi applies it to every
 // orbital (src/MGmol.cc:1252-1260).  Bit-identical (this unit is -fmad=false).
-template <typename T>
+// MEHR2: B2 u = 2/3 u + 1/36 (faces) + 1/72 (edges), Laph4MP's operator
+// (FDoper::rhs_4th_Mehr2(GridFunc&, T*), src/pb/FDoper.cc:573-637).
+template <typename T, bool MEHR2>
 __global__ void k_rhs_generic(GenericView<T> view0, long long ld, long long ldo,
     long long halo_stride, T* __restrict__ out, int tiles_z)
 {
@@ -246,6 +248,23 @@ __global__ void k_rhs_generic(GenericView<T> view0, long long ld, long long ldo,
     w.phi += (long long)f * ld;
     if (w.xhalo) w.xhalo += (long long)f * halo_stride;
     const long long o = ((long long)ix * w.ny + iy) * w.nz + iz;
+    if (MEHR2)
+    {
+        out[(long long)f * ldo + o]
+            = (T)((2. / 3.) * (double)w.psi(ix, iy, iz)
+                  + (1. / 36.)
+                        * (double)(w.psi(ix - 1, iy, iz) + w.psi(ix + 1, iy, iz)
+                                   + w.psi(ix, iy - 1, iz) + w.psi(ix, iy + 1, iz)
+                                   + w.psi(ix, iy, iz - 1) + w.psi(ix, iy, iz + 1))
+                  + (1. / 72.)
+                        * (double)(w.psi(ix - 1, iy - 1, iz) + w.psi(ix + 1, iy - 1, iz)
+                                   + w.psi(ix - 1, iy + 1, iz) + w.psi(ix + 1, iy + 1, iz)
+                                   + w.psi(ix, iy - 1, iz - 1) + w.psi(ix, iy - 1, iz + 1)
+                                   + w.psi(ix, iy + 1, iz - 1) + w.psi(ix, iy + 1, iz + 1)
+                                   + w.psi(ix - 1, iy, iz - 1) + w.psi(ix - 1, iy, iz + 1)
+                                   + w.psi(ix + 1, iy, iz - 1) + w.psi(ix + 1, iy, iz + 1)));
+        return;
+    }
     out[(long long)f * ldo + o]
         = (T)(0.5 * (double)w.psi(ix, iy, iz)
               + (1. / 12.)
@@ -255,8 +274,8 @@ __global__ void k_rhs_generic(GenericView<T> view0, long long ld, long long ldo,
 }
 
 template <typename T>
-static int rhs_generic_t(const mgb_grid* gr, const T* phi, size_t ld, const T* xhalo, T* out,
-    size_t ldo, int nfunc, cudaStream_t st)
+static int rhs_generic_t(bool mehr2, const mgb_grid* gr, const T* phi, size_t ld, const T* xhalo,
+    T* out, size_t ldo, int nfunc, cudaStream_t st)
 {
     GenericView<T> w;
     w.phi      = phi;
@@ -280,19 +299,23 @@ static int rhs_generic_t(const mgb_grid* gr, const T* phi, size_t ld, const T* x
         GenericView<T> wf = w;
         wf.phi += (long long)f0 * ld;
         if (wf.xhalo) wf.xhalo += (long long)f0 * halo_stride;
-        k_rhs_generic<T><<<grid, L.block, 0, st>>>(wf, (long long)ld, (long long)ldo,
-            halo_stride, out + (long long)f0 * ldo, L.tiles_z);
+        if (mehr2)
+            k_rhs_generic<T, true><<<grid, L.block, 0, st>>>(wf, (long long)ld, (long long)ldo,
+                halo_stride, out + (long long)f0 * ldo, L.tiles_z);
+        else
+            k_rhs_generic<T, false><<<grid, L.block, 0, st>>>(wf, (long long)ld, (long long)ldo,
+                halo_stride, out + (long long)f0 * ldo, L.tiles_z);
         MGB_LAUNCHED("k_rhs_generic");
     }
     return MGB_OK;
 }
 
-int rhs_generic(int dtype, const mgb_grid* gr, const void* phi, size_t ld, const void* xhalo,
-    void* out, size_t ldo, int nfunc, cudaStream_t st)
+int rhs_generic(int dtype, bool mehr2, const mgb_grid* gr, const void* phi, size_t ld,
+    const void* xhalo, void* out, size_t ldo, int nfunc, cudaStream_t st)
 {
-    return dtype == MGB_F64 ? rhs_generic_t<double>(gr, (const double*)phi, ld,
+    return dtype == MGB_F64 ? rhs_generic_t<double>(mehr2, gr, (const double*)phi, ld,
                                   (const double*)xhalo, (double*)out, ldo, nfunc, st)
-                            : rhs_generic_t<float>(gr, (const float*)phi, ld,
+                            : rhs_generic_t<float>(mehr2, gr, (const float*)phi, ld,
                                   (const float*)xhalo, (float*)out, ldo, nfunc, st);
 }
 

@@ -235,6 +235,24 @@ class Port:
         getattr(self.lib, name + s)(dims, g, hh, _ptr(v), _ptr(out), nf)
         return out
 
+    def lap_rhs(self, lap_type, phi, ll, bc=(1, 1, 1)):
+        """Lap::rhs per orbital on a no-ghost block: B (Laph4M), B2 (Laph4MP)
+        or a copy."""
+        phi = np.ascontiguousarray(phi)
+        nf, nx, ny, nz = phi.shape
+        if lap_type not in (0, 10):
+            return phi.copy()
+        g = 1
+        gv = self.trade_boundaries(phi, g, bc)
+        out = np.empty_like(phi)
+        if lap_type == 0:
+            getattr(self.lib, "orc_rhs_4th_Mehr1" + _sfx(phi.dtype))(
+                _c_int3(nx, ny, nz), g, _ptr(gv), _ptr(out), 0, nf)
+        else:
+            getattr(self.lib, "orc_rhs_4th_Mehr2" + _sfx(phi.dtype))(
+                _c_int3(nx, ny, nz), g, _ptr(gv), _ptr(out), nf)
+        return out
+
     # -- fused H psi ---------------------------------------------------------
     def hpsi(self, lap_type, phi, vtot, ll, bc=(1, 1, 1)):
         phi = np.ascontiguousarray(phi)
@@ -476,6 +494,15 @@ class Ref:
             _c_dbl3(*ll), _c_int3(*bc), _ptr(res), nf, ctypes.c_double(gamma))
         return res
 
+
+    def lap_rhs(self, lap_type, phi, ll, bc=(1, 1, 1)):
+        """pb::Lap::rhs(GridFunc&, T*) per orbital (Laph4MP asserts > 1 ghost)."""
+        phi = np.ascontiguousarray(phi)
+        nf, nx, ny, nz = phi.shape
+        out = np.empty_like(phi)
+        self.lib.ref_lap_rhs(lap_type, _dt(phi.dtype), _c_int3(nx, ny, nz), 2, _c_dbl3(*ll),
+                             _c_int3(*bc), _ptr(phi), _ptr(out), nf)
+        return out
 
     # -- AndersonMix<Solution> of the reference -------------------------------------
     def anderson_create(self, m, beta, x0):

@@ -432,5 +432,37 @@ void ref_mpaxpy(int dtype, int len, double alpha, const void* x, void* y)
         LAU::MPaxpy(len, alpha, (const float*)x, (float*)y);
 }
 
-int ref_shim_version() { return 1; }
+// pb::Lap<T>::rhs(GridFunc&, T*) per orbital, as MGmol::computeResidualUsingHPhi
+// applies it (src/MGmol.cc:1252-1260): Laph4M -> FDoper::rhs_4th_Mehr1
+// (src/pb/FDoper.cc:498-508), Laph4MP -> rhs_4th_Mehr2 (:573-637; asserts more
+// than one ghost layer), others -> copy.  in / out: no-ghost blocks.
+void ref_lap_rhs(int lap_type, int dtype, const int* dims, int ghosts, const double* ll,
+    const int* bc, const void* in, void* out, int nfunc)
+{
+    Box b(dims, ll, ghosts);
+    const size_t npt = b.grid.size();
+    const std::vector<std::vector<int>> gid = identity_gids(nfunc);
+    if (dtype == 1)
+    {
+        pb::GridFuncVector<double, HostSpace> gfv(b.grid, bc[0], bc[1], bc[2], gid);
+        set_data_with_ghosts(gfv, (const double*)in, nfunc, npt);
+        gfv.trade_boundaries();
+        pb::Lap<double>* lap = LapFactory<double>::createLap(b.grid, lap_type);
+        for (int i = 0; i < nfunc; i++)
+            lap->rhs(gfv.getGridFunc(i), (double*)out + (size_t)i * npt);
+        delete lap;
+    }
+    else
+    {
+        pb::GridFuncVector<float, HostSpace> gfv(b.grid, bc[0], bc[1], bc[2], gid);
+        set_data_with_ghosts(gfv, (const float*)in, nfunc, npt);
+        gfv.trade_boundaries();
+        pb::Lap<float>* lap = LapFactory<float>::createLap(b.grid, lap_type);
+        for (int i = 0; i < nfunc; i++)
+            lap->rhs(gfv.getGridFunc(i), (float*)out + (size_t)i * npt);
+        delete lap;
+    }
+}
+
+int ref_shim_version() { return 2; }
 }

@@ -632,6 +632,10 @@ def test_apply_b_bit_exact(H, port, dt, bc, dims):
     h = tuple(l / d for l, d in zip(ll, dims))
     ref = port.fdkernel(100, port.trade_boundaries(phi, 1, bc), 1, h, rhs_ghosts=0)
     assert bits_equal(host(out), ref)
+    # Laph4MP: B2 = 2/3 + faces / 36 + edges / 72 (rhs_4th_Mehr2)
+    out10 = torch.full_like(out, float("nan"))
+    H.LapFactory.createLap(grid, 10).rhs(dev(phi), out10)
+    assert bits_equal(host(out10), port.lap_rhs(10, phi, ll, bc))
     # non-compact operators: B = 1
     out2 = torch.empty_like(out)
     H.LapFactory.createLap(H.Grid(dims, ll, 2, bc), 2).rhs(dev(phi), out2)
