@@ -30,6 +30,18 @@ void orc_app_mask_noghost_f64(const int dims[3], int subdivx, int ncolors, int o
 void orc_app_mask_noghost_f32(const int dims[3], int subdivx, int ncolors, int op,
     const int* state, const long long* voff, const double* values, float* u, size_t ld,
     int nfunc);
+void orc_add_ghosts_f64(const int dims[3], int g, const double* noghost, double* ghosted, int nfunc);
+void orc_add_ghosts_f32(const int dims[3], int g, const float* noghost, float* ghosted, int nfunc);
+void orc_trade_boundaries_f64(const int dims[3], int g, const int bc[3], double* u, int nfunc);
+void orc_trade_boundaries_f32(const int dims[3], int g, const int bc[3], float* u, int nfunc);
+void orc_rhs_4th_Mehr1_f64(const int dims[3], int g, const double* v, double* rhs, int rhs_ghosts,
+    int nfunc);
+void orc_rhs_4th_Mehr1_f32(const int dims[3], int g, const float* v, float* rhs, int rhs_ghosts,
+    int nfunc);
+void orc_gemm_nn_f64(int m, int n, int k, double alpha, const double* a, int lda, const double* b,
+    int ldb, double beta, double* c, int ldc);
+void orc_gemm_nn_f32(int m, int n, int k, double alpha, const float* a, int lda, const double* b,
+    int ldb, double beta, float* c, int ldc);
 void orc_gemm_tn_f64(int m, int n, int k, double alpha, const double* a, int lda,
     const double* b, int ldb, double* c, int ldc);
 void orc_gemm_tn_f32(int m, int n, int k, double alpha, const float* a, int lda,
@@ -57,6 +69,34 @@ static void oracle_gemm_tn(int m, int n, int k, double alpha, const float* a, co
     double* c)
 {
     orc_gemm_tn_f32(m, n, k, alpha, a, k, b, k, c, m);
+}
+
+// B psi (lap 0) or psi, then (B psi) theta with the oracle's MPgemmNN
+static void oracle_bphi_theta(int lap, const int dims[3], const int bc[3], const double* phi,
+    const double* theta, double* out, int n, size_t npt)
+{
+    std::vector<double> b(phi, phi + npt * n);
+    if (lap == 0)
+    {
+        std::vector<double> g((size_t)(dims[0] + 2) * (dims[1] + 2) * (dims[2] + 2) * n);
+        orc_add_ghosts_f64(dims, 1, phi, g.data(), n);
+        orc_trade_boundaries_f64(dims, 1, bc, g.data(), n);
+        orc_rhs_4th_Mehr1_f64(dims, 1, g.data(), b.data(), 0, n);
+    }
+    orc_gemm_nn_f64((int)npt, n, n, 1., b.data(), (int)npt, theta, n, 0., out, (int)npt);
+}
+static void oracle_bphi_theta(int lap, const int dims[3], const int bc[3], const float* phi,
+    const double* theta, float* out, int n, size_t npt)
+{
+    std::vector<float> b(phi, phi + npt * n);
+    if (lap == 0)
+    {
+        std::vector<float> g((size_t)(dims[0] + 2) * (dims[1] + 2) * (dims[2] + 2) * n);
+        orc_add_ghosts_f32(dims, 1, phi, g.data(), n);
+        orc_trade_boundaries_f32(dims, 1, bc, g.data(), n);
+        orc_rhs_4th_Mehr1_f32(dims, 1, g.data(), b.data(), 0, n);
+    }
+    orc_gemm_nn_f32((int)npt, n, n, 1., b.data(), (int)npt, theta, n, 0., out, (int)npt);
 }
 
 // deterministic inputs (LCG; no <random> so the numbers never depend on libstdc++)
@@ -135,6 +175,39 @@ static int run(const int lap_type, const double tol, const double mg_tol)
     std::printf("lap %2d %s  Phi^T H Phi rel err %.3e (tol %.0e)\n", lap_type,
         sizeof(T) == 8 ? "f64" : "f32", herr / hmax, htol);
     if (!(herr <= htol * hmax)) fails++;
+
+    // --- residual (B psi) theta - H psi  (MGmol::computeResidualUsingHPhi) ---------
+    {
+        std::vector<double> theta(N * N);
+        for (int i = 0; i < N; i++)
+            for (int j = 0; j <= i; j++)
+                theta[i * N + j] = theta[j * N + i] = 0.4 * lcg(seed);
+        DeviceMemory<double> theta_dev((size_t)N * N);
+        theta_dev.copy_to_dev(theta.data(), theta.size());
+        ExtendedGridOrbitals<T> resid(grid, N);
+        computeResidualUsingHPhi(*hamiltonian.lapOper(), orbitals, hl, theta_dev.data(), resid);
+        std::vector<T> got(npt * N), rref(npt * N);
+        resid.getPsiHost(got.data());
+        oracle_bphi_theta(lap_type, dims, bc, phi.data(), theta.data(), rref.data(), N, npt);
+        double rmax = 0., rerr = 0.;
+        for (size_t i = 0; i < npt * N; i++)
+        {
+            const double r = (double)rref[i] - (double)href[i]; // res.axpy(-1., hphi)
+            rmax           = std::fmax(rmax, std::fabs(r));
+            rerr           = std::fmax(rerr, std::fabs((double)got[i] - r));
+        }
+        const double rtol = sizeof(T) == 8 ? 1e-12 : 3e-6;
+        std::printf("lap %2d %s  residual    rel err %.3e (tol %.0e)\n", lap_type,
+            sizeof(T) == 8 ? "f64" : "f32", rerr / rmax, rtol);
+        if (!(rerr <= rtol * rmax)) fails++;
+        // residual norm through the per-orbital dot products (dotProductDiagonal)
+        const double nrm2 = resid.dotProduct(resid);
+        double ref2 = 0.;
+        for (size_t i = 0; i < npt * N; i++)
+            ref2 += (double)got[i] * (double)got[i];
+        ref2 *= grid.vel();
+        if (!(std::fabs(nrm2 - ref2) <= 1e-10 * ref2)) fails++;
+    }
 
     // --- preconditioned residual ------------------------------------------------
     ExtendedGridOrbitals<T> res(grid, N);
