@@ -312,6 +312,12 @@ int mgb_gemm_tn(int dtype, int m, int n, size_t k, double alpha, const void* A,
  * FP64 DMMA kernel on widened operands (the reference's products and sums).
  * Process-wide; applies to mgb_gemm_tn / mgb_syrk_t and their slab variants.  */
 int mgb_set_f32_contraction(int mode);
+/* Test hook (host only, no device): the stream-K decomposition of a
+ * contraction -- segments (cta, tile, first k-iteration, one past the last) for
+ * `ncta` CTAs, K slabs of `kc` points, diagonal-tile cost `cd`/16.            */
+int mgb_debug_tn_plan(int syrk, int m, int n, size_t k, int nbatch, int kc, int ncta,
+    int cd, long long* segs, int max_segs, int* nsegs, long long* nkt_out,
+    int* ntiles_out, int* ndiag_out);
 /* Gram: C = alpha * A^T A (full symmetric matrix written, as
  * syrk('l','t') + fillUpperWithLower do, src/local_matrices/LocalMatrices.cc:
  * 210-247)                                                                  */

@@ -113,6 +113,10 @@ _SIGS = {
     "mgb_syrk_t": (c_int, [c_int, c_int, c_size_t, c_double, c_void_p, c_size_t,
                            c_void_p, c_int, c_void_p]),
     "mgb_set_f32_contraction": (c_int, [c_int]),
+    "mgb_debug_tn_plan": (c_int, [c_int, c_int, c_int, c_size_t, c_int, c_int, c_int, c_int,
+                                  c_void_p, c_int, ctypes.POINTER(c_int),
+                                  ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(c_int),
+                                  ctypes.POINTER(c_int)]),
     "mgb_gemm_tn_slabs": (c_int, [c_int, c_int, c_int, c_size_t, c_int, c_double, c_void_p,
                                   c_size_t, c_void_p, c_size_t, c_double, c_void_p, c_int,
                                   c_void_p]),

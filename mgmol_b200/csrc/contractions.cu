@@ -1374,6 +1374,62 @@ using namespace mgb;
 extern "C"
 {
 
+// Host-only view of the stream-K decomposition (no device needed): the segments
+// (cta, tile, first k-iteration, one-past-last) in launch order.  Test hook.
+int mgb_debug_tn_plan(int syrk, int m, int n, size_t k, int nbatch, int kc, int ncta, int cd,
+    long long* segs, int max_segs, int* nsegs, long long* nkt_out, int* ntiles_out, int* ndiag_out)
+{
+    MGB_REQUIRE(segs && nsegs && m > 0 && n > 0 && k > 0 && nbatch > 0 && kc > 0 && ncta > 0,
+        "mgb_debug_tn_plan: bad arguments");
+    TnWork W;
+    W.tm     = (m + BM - 1) / BM;
+    W.tn     = (n + BN - 1) / BN;
+    W.nbatch = nbatch;
+    W.nkt    = (long long)((k + kc - 1) / kc);
+    W.cf     = 16;
+    W.cd     = cd;
+    if (syrk)
+    {
+        W.ND = W.tm * nbatch;
+        W.NT = W.tm * (W.tm + 1) / 2 * nbatch;
+    }
+    else
+    {
+        W.ND = 0;
+        W.NT = W.tm * W.tn * nbatch;
+    }
+    W.tot  = ((long long)W.ND * W.cd + (long long)(W.NT - W.ND) * W.cf) * W.nkt;
+    W.G    = ncta;
+    W.smax = 0;
+    int cnt = 0;
+    for (int g = 0; g < W.G; g++)
+    {
+        long long b0, b1;
+        tn_cta_bounds(W, g, b0, b1);
+        if (b1 <= b0) continue;
+        const int uf = tn_tile_of(W, b0), ul = tn_tile_of(W, b1 - 1);
+        for (int u = uf; u <= ul; u++)
+        {
+            long long it0, it1;
+            tn_seg(W, u, b0, b1, it0, it1);
+            if (it0 >= it1) continue;
+            if (cnt < max_segs)
+            {
+                segs[4 * cnt + 0] = g;
+                segs[4 * cnt + 1] = u;
+                segs[4 * cnt + 2] = it0;
+                segs[4 * cnt + 3] = it1;
+            }
+            cnt++;
+        }
+    }
+    *nsegs = cnt;
+    if (nkt_out) *nkt_out = W.nkt;
+    if (ntiles_out) *ntiles_out = W.NT;
+    if (ndiag_out) *ndiag_out = W.ND;
+    return MGB_OK;
+}
+
 int mgb_set_f32_contraction(int mode)
 {
     MGB_REQUIRE(mode == 0 || mode == 1, "mgb_set_f32_contraction: mode %d", mode);

@@ -72,3 +72,62 @@ def test_host_constants_without_gpu():
         assert tuple(out) == tuple(ref)
     assert L.mgb_lap_constants(7, h, out) != 0
     assert L.mgb_gamma(0.03, 2, 0.4, -0.3) == P.gamma(0.03, 2, 0.4, -0.3)
+
+
+def test_streamk_plan_covers_every_iteration_once():
+    """Host logic of the contraction scheduler (no device): for ragged shapes,
+    slab batches and CTA counts the segments partition the (tile, k-iteration)
+    space exactly, every CTA's cost differs from the mean by at most one
+    iteration, and no CTA touches more tiles than its partial slots allow."""
+    import ctypes
+    import numpy as np
+    from mgmol_b200._lib import lib, check
+    L = lib()
+    rng = np.random.default_rng(0)
+    cases = [(1, 256, 256, 2097152, 1, 32, 148, 10), (0, 256, 256, 2097152, 1, 32, 148, 10),
+             (1, 4096, 4096, 262144, 1, 32, 148, 10), (0, 130, 70, 9216, 1, 16, 37, 10),
+             (1, 5, 5, 4096, 4, 32, 16, 12), (0, 300, 520, 32768, 3, 32, 148, 10)]
+    for _ in range(12):
+        syrk = int(rng.integers(0, 2))
+        m = int(rng.integers(1, 700))
+        n = m if syrk else int(rng.integers(1, 700))
+        cases.append((syrk, m, n, int(rng.integers(64, 200000)), int(rng.integers(1, 5)),
+                      int(rng.choice([16, 32])), int(rng.integers(1, 149)), int(rng.integers(8, 17))))
+    for syrk, m, n, k, nb, kc, ncta, cd in cases:
+        cap = 200000
+        segs = np.zeros((cap, 4), np.int64)
+        ns, nkt, nt, nd = ctypes.c_int(), ctypes.c_longlong(), ctypes.c_int(), ctypes.c_int()
+        check(L.mgb_debug_tn_plan(syrk, m, n, k, nb, kc, ncta, cd,
+                                  segs.ctypes.data_as(ctypes.c_void_p), cap, ctypes.byref(ns),
+                                  ctypes.byref(nkt), ctypes.byref(nt), ctypes.byref(nd)))
+        assert ns.value <= cap
+        s = segs[:ns.value]
+        nkt, nt, nd = nkt.value, nt.value, nd.value
+        assert nkt == -(-k // kc)
+        tm = -(-m // 128)
+        assert nt == (tm * (tm + 1) // 2 if syrk else tm * -(-n // 128)) * nb
+        cover = np.zeros((nt, nkt), np.int32) if nt * nkt < 5_000_000 else None
+        per_tile = {}
+        for g, u, a, b in s:
+            assert 0 <= u < nt and 0 <= a < b <= nkt
+            per_tile.setdefault(int(u), []).append((int(a), int(b), int(g)))
+            if cover is not None:
+                cover[u, a:b] += 1
+        if cover is not None:
+            assert (cover == 1).all()
+        else:
+            for u in range(nt):
+                iv = sorted(per_tile[u])
+                assert iv[0][0] == 0 and iv[-1][1] == nkt
+                assert all(iv[i][1] == iv[i + 1][0] for i in range(len(iv) - 1))
+        # segments of a tile come from consecutive CTAs in ascending order (the
+        # fix-up's summation order)
+        for iv in per_tile.values():
+            gs = [g for _, _, g in sorted(iv)]
+            assert gs == sorted(gs)
+        # balance: cost per CTA within one iteration of the mean
+        cost = np.zeros(ncta)
+        for g, u, a, b in s:
+            cost[g] += (b - a) * (cd if u < nd else 16)
+        tot = cost.sum()
+        assert np.abs(cost - tot / ncta).max() <= 16 + 1e-9
