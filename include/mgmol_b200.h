@@ -146,7 +146,7 @@ int mgb_residual(int lap_type, int dtype, const mgb_grid* grid, const void* phi,
  * default MemorySpace::Host build: BlockVector storage, src/BlockVector.cc:
  * 138-218): phi_host, vtot_host and hphi_host are host pointers.  The call
  * pipelines host->device copy, fused kernel and device->host copy over blocks
- * of `chunk` orbitals (0 = automatic, ~128 MB) on three internal streams so
+ * of `chunk` orbitals (0 = automatic, ~32 MB) on three internal streams so
  * that both PCIe directions and the GPU are busy at once, and returns when
  * hphi_host holds the result (synchronous, like the reference call).  Pin the
  * buffers once with mgb_host_register (cudaHostRegister) for full PCIe rate;

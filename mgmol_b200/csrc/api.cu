@@ -470,9 +470,9 @@ static int hpsi_host_impl(mgb_comm* comm, int lap_type, int dtype, const mgb_gri
     const size_t ldd = (npt + 3) / 4 * 4;
     if (chunk == 0)
     {
-        // ~128 MB per block: large enough for full PCIe rate, small enough that
-        // the pipeline fill (one block in, one block out) stays negligible
-        chunk = (int)((size_t)(128u << 20) / (ldd * es));
+        // ~32 MB per block: still at full PCIe rate, and the pipeline fill and
+        // drain (one block in, one block out) cost 2 / (number of blocks)
+        chunk = (int)((size_t)(32u << 20) / (ldd * es));
         if (chunk < 1) chunk = 1;
     }
     if (chunk > nfunc) chunk = nfunc;
@@ -516,8 +516,13 @@ static int hpsi_host_impl(mgb_comm* comm, int lap_type, int dtype, const mgb_gri
         unsigned char* out = dout + (size_t)slot * slot_bytes;
         // the kernel that last read this input slot must be done
         if (i >= NS) MGB_CUDA(cudaStreamWaitEvent(s_in, ev_k[slot], 0));
-        MGB_CUDA(cudaMemcpy2DAsync(in, ldd * es, (const unsigned char*)phi_host + (size_t)f0 * ld * es,
-            ld * es, npt * es, (size_t)nf, cudaMemcpyHostToDevice, s_in));
+        if (ld == ldd && ldd == npt) // contiguous: one linear copy
+            MGB_CUDA(cudaMemcpyAsync(in, (const unsigned char*)phi_host + (size_t)f0 * ld * es,
+                (size_t)nf * npt * es, cudaMemcpyHostToDevice, s_in));
+        else
+            MGB_CUDA(cudaMemcpy2DAsync(in, ldd * es,
+                (const unsigned char*)phi_host + (size_t)f0 * ld * es, ld * es, npt * es,
+                (size_t)nf, cudaMemcpyHostToDevice, s_in));
         MGB_CUDA(cudaEventRecord(ev_in[slot], s_in));
         MGB_CUDA(cudaStreamWaitEvent(s_k, ev_in[slot], 0));
         // the copy-out that last read this output slot must be done
@@ -544,8 +549,12 @@ static int hpsi_host_impl(mgb_comm* comm, int lap_type, int dtype, const mgb_gri
         }
         MGB_CUDA(cudaEventRecord(ev_k[slot], s_k));
         MGB_CUDA(cudaStreamWaitEvent(s_out, ev_k[slot], 0));
-        MGB_CUDA(cudaMemcpy2DAsync((unsigned char*)hphi_host + (size_t)f0 * ldh * es, ldh * es, out,
-            ldd * es, npt * es, (size_t)nf, cudaMemcpyDeviceToHost, s_out));
+        if (ldh == ldd && ldd == npt)
+            MGB_CUDA(cudaMemcpyAsync((unsigned char*)hphi_host + (size_t)f0 * ldh * es, out,
+                (size_t)nf * npt * es, cudaMemcpyDeviceToHost, s_out));
+        else
+            MGB_CUDA(cudaMemcpy2DAsync((unsigned char*)hphi_host + (size_t)f0 * ldh * es, ldh * es,
+                out, ldd * es, npt * es, (size_t)nf, cudaMemcpyDeviceToHost, s_out));
         MGB_CUDA(cudaEventRecord(ev_out[slot], s_out));
     }
     MGB_CUDA(cudaStreamSynchronize(s_out));
