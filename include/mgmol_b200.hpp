@@ -747,6 +747,19 @@ void computeResidualUsingHPhi(const Lap<T>& lapOper, const ExtendedGridOrbitals<
     res.incrementIterativeIndex();
 }
 
+// Rho::computeRhoSubdomainUsingBlas3 (src/Rho.cc:359-448) on the whole local box:
+// rho_dev (RHODTYPE double, numpt values) += sum_ij X_ij phi1_i phi2_j, localX_dev
+// column-major numst x numst double on the device
+template <typename T>
+void computeRhoUsingBlas3(const ExtendedGridOrbitals<T>& orbitals1, const double* localX_dev,
+    double* rho_dev, const ExtendedGridOrbitals<T>* orbitals2 = nullptr, void* stream = nullptr)
+{
+    const ExtendedGridOrbitals<T>& o2 = orbitals2 ? *orbitals2 : orbitals1;
+    MGB_CHECK(mgb_rho_blas3(dtype_of<T>::value, orbitals1.getNumpt(), orbitals1.chromatic_number(),
+        orbitals1.getPsi(), orbitals1.getLda(), localX_dev, orbitals1.numst(), o2.getPsi(),
+        o2.getLda(), rho_dev, stream));
+}
+
 // AndersonMix<T> (src/AndersonMix.h:21-52, src/AndersonMix.cc:27-319): host
 // control flow and an m x m solve; everything grid-sized is T's assign, -=,
 // dotProduct, axpy, scal.  The m x m matrix is scaled to a unit diagonal and
