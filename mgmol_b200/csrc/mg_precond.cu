@@ -430,7 +430,7 @@ static int cycle_fused(mgb_precond* p, int l, const float* f, size_t ldf, double
     // unless low layers must be stored as zeros (Dirichlet) or, on a coarse
     // level, the start vector omega * f is itself masked (it is the result of
     // the reference's first sweep, followed by app_mask): then it is stored.
-    if (!periodic || (l > 0 && mk.off) || (split && l == 0 && f != p->ff[0]))
+    if (!periodic || (l > 0 && mk.off))
     {
         if (int rc = mg_scale(gr, s, f, ldf, p->fa[l], ld, nfunc, zl, l > 0 ? mk : no_mask(), st))
             return rc;
@@ -648,6 +648,17 @@ int mgb_precond_mg(mgb_precond* p, int dtype, void* res, size_t ld, int nfunc,
             if ((rc = mg_convert(npt_of(gr), (const double*)res, ld, p->ff[0], npt_of(gr),
                      nfunc, st)))
                 return rc;
+            f   = p->ff[0];
+            ldf = npt_of(gr);
+        }
+        else if (gr.nproc[0] > 1)
+        {
+            // x-split: the first sweep reads the neighbours' planes of f in place,
+            // so f must live in a registered block (same kernels, hence the same
+            // bits, as on a single rank)
+            MGB_CUDA(cudaMemcpy2DAsync(p->ff[0], npt_of(gr) * sizeof(float), res,
+                ld * sizeof(float), npt_of(gr) * sizeof(float), (size_t)nfunc,
+                cudaMemcpyDeviceToDevice, st));
             f   = p->ff[0];
             ldf = npt_of(gr);
         }
