@@ -491,6 +491,7 @@ static int hpsi_host_impl(mgb_comm* comm, int lap_type, int dtype, const mgb_gri
     {
         // the input ring is what the neighbours read in place: publish it (again
         // if it was re-allocated; collective -- every rank runs the same sizes)
+        if (din_old && din != din_old) mgb_peer_unregister(comm, din_old); // ring was re-sized
         if (din != din_old || !peer_view(comm, din, comm_rank_of(grid, grid->coord[0], 0, 0)))
             if (int rc = mgb_peer_register(comm, din, (void*)s_in)) return rc;
         din_w = (const unsigned char*)peer_view(
