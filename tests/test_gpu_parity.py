@@ -699,6 +699,41 @@ def test_density_blas3(H, port, dt, N, dims):
     assert np.abs(host(rho) - exact).max() <= (1e-12 if dt == np.float64 else 1e-5) * scale
 
 
+@pytest.mark.parametrize("dt,tag", [(np.float64, "f64"), (np.float32, "f32")])
+def test_f1_rows_against_golden(H, dt, tag):
+    """B / B2, residual assembly and density against vectors produced by the
+    compiled reference (tests/golden/make_golden_f1.py)."""
+    g = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden",
+                                  "reference_f1.npz")))
+    dims = tuple(int(x) for x in g["dims"])
+    ll = tuple(float(x) for x in g["ll"])
+    N = int(g["nfunc"])
+    theta = g["theta"]
+    phi = synthetic_orbitals(N, dims, dt)
+    v = synthetic_potential(dims)
+    for lt in (0, 10):
+        for bc in ((1, 1, 1), (0, 0, 0)):
+            out = torch.full((N,) + dims, float("nan"), dtype=TDT[dt], device="cuda")
+            H.LapFactory.createLap(H.Grid(dims, ll, 1, bc), lt).rhs(dev(phi), out)
+            assert bits_equal(host(out), g["rhs_lap%d_%s_bc%d%d%d" % ((lt, tag) + bc)])
+    tol = 1e-13 if dt == np.float64 else 2e-6
+    for lt in (0, 2):
+        grid = H.Grid(dims, ll, H.ghosts_for(lt))
+        psi = H.Orbitals(grid, N, TDT[dt], dev(phi))
+        ham = H.Hamiltonian()
+        ham.setup(grid, lt)
+        ham.potential(H.Potentials(dev(v)))
+        res = H.Orbitals(grid, N, TDT[dt])
+        H.computeResidualUsingHPhi(ham.lapOper(), psi, ham.applyLocal(psi), dev(theta), res)
+        ref = g["residual_lap%d_%s" % (lt, tag)].astype(np.float64)
+        assert np.abs(host(res.psi()) - ref).max() <= tol * np.abs(ref).max()
+    grid = H.Grid(dims, ll, 1)
+    rho = torch.zeros(dims, dtype=torch.float64, device="cuda")
+    H.computeRhoUsingBlas3(H.Orbitals(grid, N, TDT[dt], dev(phi)), dev(theta), rho)
+    ref = g["rho_%s" % tag]
+    assert np.abs(host(rho) - ref).max() <= tol * np.abs(ref).max()
+
+
 @pytest.mark.parametrize("dt", [np.float64, np.float32])
 def test_diagonal_dot_products(H, port, dt):
     """computeDiagonalElementsDotProduct: one launch for all orbitals, double

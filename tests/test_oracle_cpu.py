@@ -176,3 +176,39 @@ def test_lap_rhs_port_is_bit_exact_against_compiled_reference(port, dt, lap_type
     dims, ll = (10, 8, 12), (3.0, 2.2, 4.1)
     phi = synthetic_orbitals(3, dims, dt)
     assert bits_equal(port.lap_rhs(lap_type, phi, ll, bc), R.lap_rhs(lap_type, phi, ll, bc))
+
+
+@pytest.fixture(scope="module")
+def gf1():
+    import os
+    from conftest import ROOT
+    return dict(np.load(os.path.join(ROOT, "tests", "golden", "reference_f1.npz")))
+
+
+@pytest.mark.parametrize("dt,tag", [(np.float64, "f64"), (np.float32, "f32")])
+def test_f1_rows_match_golden(port, gf1, dt, tag):
+    """Lap::rhs (B, B2), the residual sequence and the density sequence of the
+    restatement against vectors made by the compiled reference."""
+    dims = tuple(int(x) for x in gf1["dims"])
+    ll = tuple(float(x) for x in gf1["ll"])
+    N = int(gf1["nfunc"])
+    theta = gf1["theta"]
+    phi = synthetic_orbitals(N, dims, dt)
+    v = synthetic_potential(dims)
+    for lt in (0, 10):
+        for bc in ((1, 1, 1), (0, 0, 0)):
+            assert bits_equal(port.lap_rhs(lt, phi, ll, bc),
+                              gf1["rhs_lap%d_%s_bc%d%d%d" % ((lt, tag) + bc)])
+    tol = 1e-13 if dt == np.float64 else 2e-7
+    for lt in (0, 2):
+        hphi = port.hpsi(lt, phi, v, ll)
+        bphi = port.lap_rhs(lt, phi, ll) if lt == 0 else phi
+        res = (port.gemm_nn(bphi, theta) - hphi).astype(dt)
+        ref = gf1["residual_lap%d_%s" % (lt, tag)]
+        # the FP64 product goes through the reference's (unpinned) DGEMM
+        assert np.abs(res.astype(np.float64) - ref).max() <= tol * np.abs(ref).max()
+    product = port.gemm_nn(phi, theta)
+    rho = np.zeros(dims)
+    for j in range(N):
+        rho += (product[j] * phi[j]).astype(np.float64)
+    assert np.abs(rho - gf1["rho_%s" % tag]).max() <= tol * np.abs(gf1["rho_%s" % tag]).max()
