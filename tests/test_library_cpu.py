@@ -45,6 +45,18 @@ def test_no_cpu_fallback():
     assert b"no CPU fallback" in L.mgb_last_error()
     p = ctypes.c_void_p()
     assert L.mgb_precond_create(ctypes.byref(p), 0, 2, ctypes.byref(g), 4) == -4
+    # every compute entry point refuses the same way
+    n = ctypes.c_size_t(512)
+    assert L.mgb_syrk_t(1, 1, n, 1.0, buf, n, buf, 1, None) == -4
+    assert L.mgb_gemm_tn(1, 1, 1, n, 1.0, buf, n, buf, n, 0.0, buf, 1, None) == -4
+    assert L.mgb_gemm_nn(1, n, 1, 1, 1.0, buf, n, buf, 1, 0.0, buf, n, None) == -4
+    assert L.mgb_apply_b(0, 1, ctypes.byref(g), buf, n, buf, n, 1, None, None) == -4
+    assert L.mgb_residual(0, 1, ctypes.byref(g), buf, n, buf, n, buf, 1, buf, n, 1, None,
+                          None) == -4
+    assert L.mgb_dot_cols(1, n, 1, 1.0, buf, n, buf, n, buf, None) == -4
+    assert L.mgb_rho_blas3(1, n, 1, buf, n, buf, 1, buf, n, buf, None) == -4
+    assert L.mgb_masks_create(ctypes.byref(p), ctypes.byref(g), 1, 2, 4, 0) == -4
+    assert L.mgb_hpsi_host(0, 1, ctypes.byref(g), buf, n, buf, buf, n, 1, 0) == -4
 
 
 def test_product_never_imports_oracle():
