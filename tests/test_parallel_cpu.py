@@ -139,3 +139,47 @@ def test_ghosted_color_maps():
     # x low side: my slab 0 against the west rank's LAST slab; other slabs unused
     assert m[0, 0].tolist() == [[2, 0, -1], [-1, -1, -1]]
     assert (m[0, 1] == -1).all() and (m[2] == -1).all()
+
+
+def _gid_worker(rank, world, port, out):
+    """The integration recipe for localized orbitals on a split domain: each rank
+    sends its overlapping_gids table to its x neighbours (MPI_Sendrecv in MGmol,
+    gloo here), builds the slot translations, and the halo of every color then
+    comes from the neighbour's slot holding the same global orbital."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from mgmol_b200.parallel import color_maps
+        subdivx, ncol, ngid = 2, 5, 6
+        rs = np.random.RandomState(100 + rank)
+        mine = np.stack([np.append(rs.permutation(ngid)[:ncol - 1], -1) for _ in range(subdivx)])
+        west, east = (rank - 1) % world, (rank + 1) % world
+        t = torch.from_numpy(mine.copy())
+        tw, te = torch.empty_like(t), torch.empty_like(t)
+        reqs = [dist.isend(t, west), dist.isend(t.clone(), east), dist.irecv(te, east),
+                dist.irecv(tw, west)]
+        for r in reqs:
+            r.wait()
+        mw, me = color_maps(mine, tw.numpy(), te.numpy())
+        # the data of color c in the boundary slab is just its gid: fetch through the map
+        ok = True
+        for c in range(ncol):
+            g_lo, g_hi = mine[0][c], mine[-1][c]
+            got_w = tw.numpy()[-1][mw[c]] if mw[c] >= 0 else None
+            got_e = te.numpy()[0][me[c]] if me[c] >= 0 else None
+            ok = ok and (got_w == g_lo if got_w is not None else
+                         (g_lo < 0 or g_lo not in tw.numpy()[-1]))
+            ok = ok and (got_e == g_hi if got_e is not None else
+                         (g_hi < 0 or g_hi not in te.numpy()[0]))
+        out[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gid_tables_exchange_world2():
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_gid_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    assert dict(out) == {0: True, 1: True}
