@@ -36,6 +36,17 @@ struct mgb_masks
 namespace mgb
 {
 
+// the double copy of the values is only needed to mask ORBDTYPE double blocks
+// (the V-cycle is float): uploaded on first use
+static int ensure_pool64(mgb_mask_level& L)
+{
+    if (L.pool_d) return MGB_OK;
+    const size_t n = L.values.size();
+    MGB_CUDA(cudaMalloc(&L.pool_d, sizeof(double) * n));
+    MGB_CUDA(cudaMemcpy(L.pool_d, L.values.data(), sizeof(double) * n, cudaMemcpyHostToDevice));
+    return MGB_OK;
+}
+
 MaskView mask_view(const mgb_masks* m, int level, int* rc)
 {
     MaskView v = no_mask();
@@ -237,9 +248,6 @@ int mgb_masks_commit(mgb_masks* m)
             f[i] = (float)L.values[i];
         MGB_CUDA(cudaMalloc(&L.pool_f, sizeof(float) * n));
         MGB_CUDA(cudaMemcpy(L.pool_f, f.data(), sizeof(float) * n, cudaMemcpyHostToDevice));
-        MGB_CUDA(cudaMalloc(&L.pool_d, sizeof(double) * n));
-        MGB_CUDA(cudaMemcpy(
-            L.pool_d, L.values.data(), sizeof(double) * n, cudaMemcpyHostToDevice));
     }
     m->committed = true;
     return MGB_OK;
@@ -264,6 +272,8 @@ int mgb_gfv_app_mask(int dtype, const mgb_masks* m, int level, int ghosts, void*
         nfunc, m->ncolors);
     MGB_REQUIRE(ghosts >= 0 && ghosts < 10, "mgb_gfv_app_mask: ghosts %d", ghosts);
     int rc;
+    if (dtype == MGB_F64 && m->committed && level >= 0 && level < m->nlevels)
+        if ((rc = ensure_pool64(const_cast<mgb_masks*>(m)->lev[level]))) return rc;
     const MaskView mv = mask_view(m, level, &rc);
     if (rc) return rc;
     const mgb_mask_level& L = m->lev[level];
@@ -302,6 +312,8 @@ int mgb_app_mask(int dtype, const mgb_masks* m, int level, void* noghost, size_t
     MGB_REQUIRE(nfunc > 0 && nfunc <= m->ncolors, "mgb_app_mask: nfunc %d > ncolors %d", nfunc,
         m->ncolors);
     int rc;
+    if (dtype == MGB_F64 && m->committed && level >= 0 && level < m->nlevels)
+        if ((rc = ensure_pool64(const_cast<mgb_masks*>(m)->lev[level]))) return rc;
     const MaskView mv = mask_view(m, level, &rc);
     if (rc) return rc;
     const mgb_mask_level& L = m->lev[level];
