@@ -879,3 +879,93 @@ def test_config_si4x4nanowire_shape(H, dt):
         pc.close()
     sc = res[1].abs().amax(dim=(1, 2, 3), keepdim=True)
     assert float(((res[2] - res[1]).abs() / sc).max()) <= MG_TOL
+
+
+# --------------------------------------------------------------------------
+# mputils BLAS-1 and the small utility entry points
+# --------------------------------------------------------------------------
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("n", [1, 255, 4097, 3 * 20 * 20 * 20])
+def test_blas1_against_mputils(dt, n):
+    """MPaxpy / MPscal / MPdot (src/linear_algebra/mputils.cc:53-244): products
+    in double, one rounding to the storage type per element -> axpy and scal
+    bit-exact; the dot product is a double sum in another order -> 1e-14
+    relative to sum|x y|."""
+    import ctypes
+    from mgmol_b200._lib import lib, check
+    from oracle.oracle import Ref, _dt as odt, _ptr
+    L = lib()
+    rng = np.random.default_rng(n)
+    x = rng.standard_normal(n).astype(dt)
+    y = rng.standard_normal(n).astype(dt)
+    code = 1 if dt == np.float64 else 0
+    for alpha in (-0.37, 1.0, 0.0, 2.5):
+        dx, dy = dev(x), dev(y)
+        check(L.mgb_axpy(code, n, alpha, ctypes.c_void_p(dx.data_ptr()),
+                         ctypes.c_void_p(dy.data_ptr()), None))
+        want = y + (alpha * x.astype(np.float64)).astype(dt)
+        assert bits_equal(host(dy), want)
+        if Ref.available() and dt == np.float32:
+            r = y.copy()
+            Ref().lib.ref_mpaxpy(odt(r.dtype), n, ctypes.c_double(alpha), _ptr(x), _ptr(r))
+            assert bits_equal(host(dy), r)
+        ds = dev(x)
+        check(L.mgb_scal(code, n, alpha, ctypes.c_void_p(ds.data_ptr()), None))
+        if alpha == 0.0:
+            wants = np.zeros_like(x)
+        else:
+            wants = (alpha * x.astype(np.float64)).astype(dt)
+        assert bits_equal(host(ds), wants)
+    dx, dy = dev(x), dev(y)
+    res = torch.zeros(1, dtype=torch.float64, device="cuda")
+    check(L.mgb_dot(code, n, ctypes.c_void_p(dx.data_ptr()), ctypes.c_void_p(dy.data_ptr()),
+                    ctypes.c_void_p(res.data_ptr()), None))
+    xd, yd = x.astype(np.float64), y.astype(np.float64)
+    want = float(np.dot(xd, yd))
+    assert abs(float(res.item()) - want) <= 1e-14 * float(np.abs(xd * yd).sum()) + 1e-300
+    if Ref.available():
+        r = Ref().lib.ref_mpdot(odt(x.dtype), n, _ptr(x), _ptr(y))
+        assert abs(float(res.item()) - r) <= 1e-13 * float(np.abs(xd * yd).sum())
+    assert L.mgb_axpy(7, n, 1.0, ctypes.c_void_p(dx.data_ptr()),
+                      ctypes.c_void_p(dy.data_ptr()), None) != 0
+
+
+def test_version_and_host_registration():
+    """mgb_host_register pins a caller's buffer so mgb_hpsi_host streams from it
+    without staging; results are the same bits either way."""
+    import ctypes
+    from mgmol_b200._lib import lib, check, MgbGrid
+    L = lib()
+    assert L.mgb_version() >= 100
+    dims, N = (16, 16, 16), 3
+    phi = synthetic_orbitals(N, dims, np.float64)
+    v = synthetic_potential(dims)
+    g = MgbGrid()
+    for d in range(3):
+        g.dim[d] = g.gdim[d] = dims[d]
+        g.h[d] = 0.3
+        g.bc[d] = 1
+        g.nproc[d] = 1
+        g.coord[d] = 0
+    g.ghosts = 2
+    n = int(np.prod(dims))
+    outs = []
+    for pinned in (False, True):
+        src = phi.copy()
+        out = np.full_like(src, np.nan)
+        if pinned:
+            check(L.mgb_host_register(src.ctypes.data_as(ctypes.c_void_p), src.nbytes))
+            check(L.mgb_host_register(out.ctypes.data_as(ctypes.c_void_p), out.nbytes))
+        try:
+            check(L.mgb_hpsi_host(0, 1, ctypes.byref(g), src.ctypes.data_as(ctypes.c_void_p), n,
+                                  v.ctypes.data_as(ctypes.c_void_p),
+                                  out.ctypes.data_as(ctypes.c_void_p), n, N, 0))
+        finally:
+            if pinned:
+                check(L.mgb_host_unregister(src.ctypes.data_as(ctypes.c_void_p)))
+                check(L.mgb_host_unregister(out.ctypes.data_as(ctypes.c_void_p)))
+        outs.append(out)
+    assert bits_equal(outs[0], outs[1])
+    assert np.isfinite(outs[0]).all()
+    assert L.mgb_host_register(None, 16) != 0
+    assert L.mgb_host_unregister(None) == 0

@@ -212,3 +212,29 @@ def test_f1_rows_match_golden(port, gf1, dt, tag):
     for j in range(N):
         rho += (product[j] * phi[j]).astype(np.float64)
     assert np.abs(rho - gf1["rho_%s" % tag]).max() <= tol * np.abs(gf1["rho_%s" % tag]).max()
+
+
+@pytest.mark.skipif(not Ref.available(), reason="compiled reference not present")
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_blas1_statement_against_compiled_reference(dt):
+    """The one-line statements the GPU BLAS-1 tests use (double product, one
+    rounding to the storage type) are what MPaxpy / MPdot compute
+    (src/linear_algebra/mputils.cc:130-244)."""
+    import ctypes
+    from oracle.oracle import _dt, _ptr
+    R = Ref()
+    rng = np.random.default_rng(3)
+    n = 4097
+    x = rng.standard_normal(n).astype(dt)
+    y = rng.standard_normal(n).astype(dt)
+    for alpha in (-0.37, 1.0, 0.0, 2.5):
+        r = y.copy()
+        R.lib.ref_mpaxpy(_dt(dt), n, ctypes.c_double(alpha), _ptr(x), _ptr(r))
+        want = y + (alpha * x.astype(np.float64)).astype(dt)
+        if dt == np.float32:
+            assert bits_equal(r, want)
+        else:   # DAXPY of the BLAS at hand may fuse the multiply-add
+            assert np.allclose(r, want, rtol=0, atol=4e-16 * np.abs(want).max())
+    d = R.lib.ref_mpdot(_dt(dt), n, _ptr(x), _ptr(y))
+    xd, yd = x.astype(np.float64), y.astype(np.float64)
+    assert abs(d - float(np.dot(xd, yd))) <= 1e-13 * float(np.abs(xd * yd).sum())

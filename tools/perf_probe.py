@@ -105,7 +105,9 @@ def probe_gemm(n, norb):
         fl = float(norb) * norb * npt  # syrk: N^2 K useful flops
         out(kernel="gram_syrk", dtype=str(dt), n=n, orb=norb, ms=med, ms_best=best,
             tflops_useful=fl / (med * 1e-3) / 1e12,
-            tflops_executed=fl * (1 + 1.0 / max(1, (norb + 127) // 128)) / (med * 1e-3) / 1e12)
+            # off-diagonal tiles whole, diagonal tiles 10/16 of a tile (the
+            # half-work path) -> N^2 K (1 + 1/(4 T)), T = tile rows
+            tflops_executed=fl * (1 + 0.25 / max(1, (norb + 127) // 128)) / (med * 1e-3) / 1e12)
         med, best = timeit(lambda: a.computeLocalProduct(b), reps=5, warm=2)
         out(kernel="gemm_tn", dtype=str(dt), n=n, orb=norb, ms=med, ms_best=best,
             tflops=2 * fl / (med * 1e-3) / 1e12)
