@@ -21,6 +21,7 @@
 #ifndef MGMOL_B200_HPP
 #define MGMOL_B200_HPP
 
+#include <algorithm>
 #include <cassert>
 #include <cmath>
 #include <cstdio>
@@ -105,6 +106,78 @@ private:
     T* ptr_;
     size_t size_;
 };
+
+// GramMatrix::computeLoewdinTransform (src/GramMatrix.cc:267-285) for a
+// replicated n x n matrix on the host: S = V diag(l) V^T, P = V diag(1/sqrt(l)) V^T
+// and, when asked for, sqrtS = V diag(sqrt(l)) V^T (the reference's invLoewdin).
+// The reference diagonalises with dsyev; this header needs no LAPACK, so cyclic
+// Jacobi rotations do it (n is the number of orbitals; O(n^3) per sweep, a
+// handful of sweeps).  A caller that links LAPACK can pass its own P to
+// ExtendedGridOrbitals::orthonormalizeLoewdin instead.  Matrices column-major,
+// symmetric.  Returns false when S is not positive definite.
+inline bool loewdinTransform(const int n, const double* S, double* P, double* sqrtS = nullptr)
+{
+    const size_t N = (size_t)n;
+    std::vector<double> A(S, S + N * N), V(N * N, 0.);
+    for (size_t i = 0; i < N; i++)
+        V[i + i * N] = 1.;
+    for (int sweep = 0; sweep < 60; sweep++)
+    {
+        double off = 0., diag = 0.;
+        for (size_t q = 0; q < N; q++)
+        {
+            diag += A[q + q * N] * A[q + q * N];
+            for (size_t p = 0; p < q; p++)
+                off += A[p + q * N] * A[p + q * N];
+        }
+        if (off <= 1e-32 * diag) break;
+        for (size_t q = 1; q < N; q++)
+            for (size_t p = 0; p < q; p++)
+            {
+                const double apq = A[p + q * N];
+                if (apq == 0.) continue;
+                const double theta = (A[q + q * N] - A[p + p * N]) / (2. * apq);
+                const double t
+                    = (theta >= 0. ? 1. : -1.) / (std::fabs(theta) + std::sqrt(theta * theta + 1.));
+                const double c = 1. / std::sqrt(t * t + 1.), sn = t * c;
+                for (size_t k = 0; k < N; k++) // columns p, q
+                {
+                    const double akp = A[k + p * N], akq = A[k + q * N];
+                    A[k + p * N] = c * akp - sn * akq;
+                    A[k + q * N] = sn * akp + c * akq;
+                }
+                for (size_t k = 0; k < N; k++) // rows p, q
+                {
+                    const double apk = A[p + k * N], aqk = A[q + k * N];
+                    A[p + k * N] = c * apk - sn * aqk;
+                    A[q + k * N] = sn * apk + c * aqk;
+                }
+                for (size_t k = 0; k < N; k++)
+                {
+                    const double vkp = V[k + p * N], vkq = V[k + q * N];
+                    V[k + p * N] = c * vkp - sn * vkq;
+                    V[k + q * N] = sn * vkp + c * vkq;
+                }
+            }
+    }
+    for (size_t k = 0; k < N; k++)
+        if (!(A[k + k * N] > 0.)) return false;
+    for (size_t j = 0; j < N; j++)
+        for (size_t i = 0; i < N; i++)
+        {
+            double a = 0., b = 0.;
+            for (size_t k = 0; k < N; k++)
+            {
+                const double vv = V[i + k * N] * V[j + k * N];
+                const double r  = std::sqrt(A[k + k * N]);
+                a += vv / r;
+                b += vv * r;
+            }
+            P[i + j * N] = a;
+            if (sqrtS) sqrtS[i + j * N] = b;
+        }
+    return true;
+}
 
 // GridFactory (src/GridFactory.h:23-51): ghost width per operator
 inline short ghostsFor(const int lap_type)
@@ -417,6 +490,44 @@ public:
         MGB_CHECK(mgb_gemm_nn(dtype_of<T>::value, numpt_, n, numst_, 1., getPsi(), lda_,
             matrix_dev, numst_, 0., product.getPsi(), product.getLda(), stream));
         product.incrementIterativeIndex();
+    }
+    // orthonormalizeLoewdin (src/ExtendedGridOrbitals.cc:1304-1358): Phi <- Phi P,
+    // P = S^-1/2.  The Gram matrix and Phi P are the library's kernels; the
+    // n x n transform is the reference's replicated-matrix layer
+    // (ProjectedMatrices::computeLoewdinTransform), done on the host by
+    // loewdinTransform unless the caller supplies P (column-major, host).  On
+    // return matrixTransform, when given, holds P as the reference's argument of
+    // that name does.
+    void orthonormalizeLoewdin(double* matrixTransform = nullptr, mgb_comm* comm = nullptr,
+        const bool transform_given = false)
+    {
+        const size_t nn = (size_t)numst_ * numst_;
+        std::vector<double> S(nn), P(nn);
+        DeviceMemory<double> mat(nn);
+        if (transform_given)
+        {
+            assert(matrixTransform);
+            P.assign(matrixTransform, matrixTransform + nn);
+        }
+        else
+        {
+            computeGram(mat.data(), comm);
+            mat.copy_to_host(S.data(), nn);
+            if (!loewdinTransform(numst_, S.data(), P.data()))
+            {
+                std::fprintf(stderr,
+                    "mgmol_b200: orthonormalizeLoewdin: Gram matrix not positive definite\n");
+                std::abort();
+            }
+            if (matrixTransform) std::copy(P.begin(), P.end(), matrixTransform);
+        }
+        mat.copy_to_dev(P.data(), nn);
+        DeviceMemory<T> product(psi_.size());
+        MGB_CHECK(mgb_gemm_nn(dtype_of<T>::value, numpt_, numst_, numst_, 1., getPsi(), lda_,
+            mat.data(), numst_, 0., product.data(), lda_, nullptr));
+        MGB_CHECK(mgb_copy_dev(getPsi(), product.data(), psi_.size() * sizeof(T), nullptr));
+        MGB_CHECK(mgb_stream_sync(nullptr));
+        incrementIterativeIndex();
     }
 
 protected:

@@ -458,6 +458,23 @@ class Orbitals:
             self.incrementIterativeIndex()
         return out
 
+    def orthonormalizeLoewdin(self, gram=None, comm=None):
+        """Phi <- Phi S^-1/2 (src/ExtendedGridOrbitals.cc:1304-1358).  The
+        transform is GramMatrix::computeLoewdinTransform (src/GramMatrix.cc:
+        267-285): S = V diag(l) V^T by dsyev, P = V diag(1/sqrt(l)) V^T.  The
+        N x N eigenproblem belongs to the reference's dense-matrix layer
+        (ProjectedMatrices, not part of the grid path), so it is a library call
+        (cuSOLVER through torch.linalg.eigh) on the device: S never leaves HBM.
+        The two grid-sized steps, the Gram matrix and Phi P, are this library's
+        kernels.  Returns P (the reference's matrixTransform)."""
+        S = self.computeGram(comm) if gram is None else gram
+        lam, V = torch.linalg.eigh(S)
+        if not bool(lam[0] > 0):
+            raise ArithmeticError("orthonormalizeLoewdin: Gram matrix is not positive definite")
+        P = (V * lam.rsqrt()) @ V.t()
+        self.multiplyByMatrix(P)
+        return P
+
 
 class Masks:
     """The localization masks one rank holds for its colors: what MasksSet /

@@ -233,6 +233,40 @@ static int run(const int lap_type, const double tol, const double mg_tol)
     std::printf("lap %2d %s  precond_mg  rel err %.3e (tol %.0e)\n", lap_type,
         sizeof(T) == 8 ? "f64" : "f32", worst, mg_tol);
     if (!(worst <= mg_tol)) fails++;
+
+    // --- orthonormalizeLoewdin: afterwards the Gram matrix is the identity, and
+    // the transform is the symmetric S^-1/2 of the oracle's Gram matrix
+    {
+        ExtendedGridOrbitals<T> orth(grid, N);
+        orth.setPsi(phi.data());
+        const int idx = orth.getIterativeIndex();
+        std::vector<double> P(N * N), S(N * N), G(N * N);
+        orth.orthonormalizeLoewdin(P.data());
+        if (orth.getIterativeIndex() <= idx) fails++;
+        oracle_gemm_tn(N, N, (int)npt, grid.vel(), phi.data(), phi.data(), S.data());
+        // P S P = I
+        double perr = 0.;
+        for (int i = 0; i < N; i++)
+            for (int j = 0; j < N; j++)
+            {
+                double v = 0.;
+                for (int k = 0; k < N; k++)
+                    for (int l = 0; l < N; l++)
+                        v += P[i + k * N] * S[k + l * N] * P[l + j * N];
+                perr = std::fmax(perr, std::fabs(v - (i == j ? 1. : 0.)));
+            }
+        DeviceMemory<double> g_dev((size_t)N * N);
+        orth.computeGram(g_dev.data());
+        g_dev.copy_to_host(G.data(), G.size());
+        double gerr = 0.;
+        for (int i = 0; i < N; i++)
+            for (int j = 0; j < N; j++)
+                gerr = std::fmax(gerr, std::fabs(G[i + j * N] - (i == j ? 1. : 0.)));
+        const double ptol = sizeof(T) == 8 ? 1e-11 : 2e-5;
+        std::printf("lap %2d %s  Loewdin     |PSP-I| %.3e |G-I| %.3e (tol %.0e)\n", lap_type,
+            sizeof(T) == 8 ? "f64" : "f32", perr, gerr, ptol);
+        if (!(perr <= ptol && gerr <= ptol)) fails++;
+    }
     return fails;
 }
 

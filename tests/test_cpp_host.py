@@ -76,3 +76,43 @@ def test_cpp_anderson_mirror_matches_reference():
         got = np.array([[float(v) for v in line.split()] for line in r.stdout.strip().splitlines()])
         assert got.shape == ref.shape
         assert np.abs(got - ref).max() <= 1e-9 * np.abs(ref).max(), (n, m, beta)
+
+
+def test_cpp_loewdin_transform_host():
+    """loewdinTransform of include/mgmol_b200.hpp (Jacobi rotations in place of
+    the reference's dsyev, src/GramMatrix.cc:267-299) against LAPACK: P =
+    S^-1/2 and the inverse transform S^1/2, and refusal of an indefinite S."""
+    import numpy as np
+    from mgmol_b200 import build as b
+    b.build()
+    src = os.path.join(ROOT, "tests", "cpp", "test_loewdin_host.cc")
+    exe = os.path.join(ROOT, "tests", "cpp", "test_loewdin_host")
+    cmd = ["g++", "-std=c++11", "-O2", "-Wall", "-I", os.path.join(ROOT, "include"), src,
+           "-L", os.path.join(ROOT, "mgmol_b200"), "-lmgmol_b200",
+           "-Wl,-rpath,$ORIGIN/../../mgmol_b200", "-o", exe]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+    def run(S):
+        n = S.shape[0]
+        inp = "%d\n%s\n" % (n, " ".join(repr(float(v)) for v in S.T.ravel()))
+        return subprocess.run([exe], input=inp, capture_output=True, text=True, timeout=120)
+
+    rng = np.random.default_rng(11)
+    for n, spread in ((1, 1.0), (2, 3.0), (7, 10.0), (40, 1e3), (130, 1e5)):
+        Q, _ = np.linalg.qr(rng.standard_normal((n, n)))
+        lam = np.geomspace(1.0, spread, n)
+        S = (Q * lam) @ Q.T
+        S = 0.5 * (S + S.T)
+        r = run(S)
+        assert r.returncode == 0, r.stdout + r.stderr
+        rows = np.array([[float(v) for v in line.split()] for line in r.stdout.strip().splitlines()])
+        P, R = rows[:n], rows[n:]
+        w, V = np.linalg.eigh(S)
+        assert np.abs(P - (V / np.sqrt(w)) @ V.T).max() <= 1e-12 * spread
+        assert np.abs(R - (V * np.sqrt(w)) @ V.T).max() <= 1e-12 * np.sqrt(spread) * spread
+        assert np.abs(P @ S @ P - np.eye(n)).max() <= 1e-11 * np.sqrt(spread)
+        assert np.abs(P - P.T).max() <= 1e-13 * np.abs(P).max()
+    bad = np.array([[1.0, 2.0], [2.0, 1.0]])
+    r = run(bad)
+    assert r.returncode == 3

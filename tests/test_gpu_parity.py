@@ -969,3 +969,37 @@ def test_version_and_host_registration():
     assert np.isfinite(outs[0]).all()
     assert L.mgb_host_register(None, 16) != 0
     assert L.mgb_host_unregister(None) == 0
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("N,dims", [(7, (12, 8, 16)), (40, (16, 16, 16)), (150, (16, 24, 32))])
+def test_orthonormalize_loewdin(H, port, dt, N, dims):
+    """ExtendedGridOrbitals::orthonormalizeLoewdin (src/ExtendedGridOrbitals.cc:
+    1304-1358; transform of src/GramMatrix.cc:267-285): afterwards the Gram
+    matrix is the identity, Phi moved by the symmetric S^-1/2 of the oracle's
+    Gram matrix, and the iterative index advanced."""
+    a = synthetic_orbitals(N, dims, dt)
+    grid = H.Grid(dims, (2.0, 2.5, 3.0), 1)
+    A = H.Orbitals(grid, N, TDT[dt], dev(a))
+    idx = A.getIterativeIndex()
+    P = host(A.orthonormalizeLoewdin())
+    assert A.getIterativeIndex() > idx
+    S = grid.vel() * np.einsum("ixyz,jxyz->ij", a.astype(np.float64), a.astype(np.float64))
+    lam, V = np.linalg.eigh(S)
+    Pref = (V / np.sqrt(lam)) @ V.T
+    cond = lam[-1] / lam[0]
+    eps = 1e-13 if dt == np.float64 else 2e-6
+    assert np.abs(P - P.T).max() <= 1e-12 * np.abs(P).max()
+    assert np.abs(P - Pref).max() <= eps * cond * np.abs(Pref).max()
+    want = np.einsum("lj,lxyz->jxyz", Pref, a.astype(np.float64))
+    got = host(A.psi()).astype(np.float64)
+    assert np.abs(got - want).max() <= eps * cond * np.abs(want).max() * max(1, N / 64)
+    G = host(A.computeGram())
+    tolg = 1e-11 if dt == np.float64 else 2e-5
+    assert np.abs(G - np.eye(N)).max() <= tolg * max(1.0, np.sqrt(cond))
+    if N <= 40:
+        # the same statement from the oracle's Gram matrix and Phi M
+        Sp = port.gemm_tn(a, a, grid.vel())
+        lp, Vp = np.linalg.eigh(Sp)
+        ref = port.gemm_nn(a, (Vp / np.sqrt(lp)) @ Vp.T)
+        assert np.abs(got - ref).max() <= eps * cond * np.abs(want).max()
