@@ -145,6 +145,11 @@ class GridFuncVector:
             self.grid_.size(), self.nfunc_, _stream()))
         return out
 
+    def values(self):
+        """getValues into a new no-ghost block."""
+        return self.getValues(torch.empty((self.nfunc_,) + tuple(self.grid_.shape()),
+                                          dtype=self.data.dtype, device="cuda"))
+
     def trade_boundaries(self):
         """src/pb/GridFuncVector.cc:1544-1622."""
         if self.updated_boundaries_:
@@ -215,6 +220,50 @@ class GridFuncVector:
                                      _p(ucoarse.data), _p(self.data), self.nfunc_,
                                      _stream()))
         self.updated_boundaries_ = False
+
+
+    # -- pb::GridFunc operations of the Poisson multigrid (one function) -------
+    def copy_from(self, other):
+        """GridFunc copy constructor / operator=: all values, ghosts included."""
+        assert other.data.shape == self.data.shape and other.data.dtype == self.data.dtype
+        check(lib().mgb_copy_dev(_p(self.data), _p(other.data),
+                                 self.data.numel() * self.data.element_size(), _stream()))
+        self.updated_boundaries_ = other.updated_boundaries_
+
+    def _interior(self, drop_bc_layers):
+        g = self.grid_.ghost_pt()
+        nx, ny, nz = self.grid_.shape()
+        lo = [g + (1 if (drop_bc_layers and self.grid_.bc[d] != 1
+                         and self.grid_.coord[d] == 0) else 0) for d in range(3)]
+        return self.data[:, lo[0]:g + nx, lo[1]:g + ny, lo[2]:g + nz].contiguous()
+
+    def gdot(self, other, comm=None):
+        """GridFunc::gdot (src/pb/GridFunc.cc:2745-2798): interior points, minus
+        the first layer in every non-periodic direction; double sum."""
+        a, b = self._interior(True), other._interior(True)
+        out = torch.empty(1, dtype=torch.float64, device="cuda")
+        check(lib().mgb_dot(_dt(a), a.numel(), _p(a), _p(b), _p(out), _stream()))
+        if comm is not None:
+            comm.allreduce(out)
+        return float(out.item())
+
+    def norm2(self, comm=None):
+        """GridFunc::norm2 (src/pb/GridFunc.cc:2856-2861)."""
+        return (self.gdot(self, comm) * self.grid_.vel()) ** 0.5
+
+    def get_average(self):
+        """GridFunc::get_average (src/pb/GridFunc.cc:2888-2927), one rank."""
+        a = self._interior(False)
+        ones = torch.ones_like(a)
+        out = torch.empty(1, dtype=torch.float64, device="cuda")
+        check(lib().mgb_dot(_dt(a), a.numel(), _p(a), _p(ones), _p(out), _stream()))
+        return float(out.item()) / float(self.grid_.size())
+
+    def add_scalar(self, alpha):
+        """GridFunc::operator+=(T) / operator-=(T): every stored value."""
+        ones = torch.ones_like(self.data)
+        check(lib().mgb_axpy(_dt(self.data), self.data.numel(), float(alpha), _p(ones),
+                             _p(self.data), _stream()))
 
 
 class Lap:

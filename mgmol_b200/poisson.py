@@ -1,0 +1,161 @@
+"""Poisson multigrid for the Hartree potential: the host
+control flow of pb::SolverLap<Lap<T>, T>::solve (src/pb/SolverLap.cc:62-72) =
+pb::Mgm (src/pb/Mgm.h:21-112) over pb::Vcycle (src/pb/Vcycle.h:29-250), on one
+scalar field, composed from the same C-ABI operations the orbital path uses
+with nfunc = 1: boundary trade, the Laplacians and the Mehrstellen right-hand
+side, full-weighting restriction, trilinear prolongation, axpy and dot.
+
+Operators: Laph4M (0), Laph2 (1), Laph4 (2); boundary conditions 0 (zero
+Dirichlet) and 1 (periodic) per direction.  Multipole boundary values (bc 2),
+the dielectric (PB) operators and decomposed boxes (the gather of the coarse
+level, src/pb/Vcycle.h:69-143) are not part of it.
+
+The solver works on "fields": objects with the GridFuncVector interface of
+host.py.  The default is the device class; the CPU tests drive this very
+control flow with a numpy stand-in to pin it against the compiled reference."""
+import torch
+
+from .host import Grid, GridFuncVector, Lap  # noqa: F401
+
+# ghost layers the operator needs (Laph4M / Laph2 / Laph4 ::minNumberGhosts)
+_MIN_GHOSTS = {0: 1, 1: 1, 2: 2}
+# operator used one level down: Laph4 hands the coarse levels to Laph2
+# (USE_LOWER_ORDER, src/pb/Vcycle.h:14,181-200; Laph4::getLowerOrderOp)
+_LOWER_ORDER = {0: 0, 1: 1, 2: 1}
+
+
+class PoissonMG:
+    """pb::SolverLap<T, T2> (src/pb/SolverLap.h:18-77)."""
+
+    def __init__(self, grid, lap_type, dtype=torch.float64, field=None):
+        if lap_type not in _MIN_GHOSTS:
+            raise ValueError("PoissonMG: operator %d not available" % lap_type)
+        if any(b not in (0, 1) for b in grid.bc):
+            raise ValueError("PoissonMG: boundary conditions 0 and 1 only")
+        if tuple(grid.nproc) != (1, 1, 1):
+            raise ValueError("PoissonMG: single-rank boxes only")
+        self.grid_ = grid.with_ghosts(_MIN_GHOSTS[lap_type])
+        self.type_ = lap_type
+        self.field_ = field if field is not None else (
+            lambda g: GridFuncVector(g, 1, dtype))
+        self.fully_periodic_ = tuple(grid.bc) == (1, 1, 1)
+        self.setup(2, 2, 10, 1.e-16, 10)
+        self.nb_sweeps_ = 0
+        self.final_residual_ = -1.
+        self.final_relative_residual_ = -1.
+        self.residual_reduction_ = -1.
+
+    def setup(self, nu1, nu2, max_sweeps, tol, max_nlevels, gather_coarse_level=True):
+        self.nu1_, self.nu2_ = int(nu1), int(nu2)
+        self.max_sweeps_ = int(max_sweeps)
+        self.tol_ = float(tol)
+        self.max_nlevels_ = int(max_nlevels)
+
+    def getNbSweeps(self):
+        return self.nb_sweeps_
+
+    def getFinalResidual(self):
+        return self.final_residual_
+
+    def getFinalRelativeResidual(self):
+        return self.final_relative_residual_
+
+    def getResidualReduction(self):
+        return self.residual_reduction_
+
+    # -- Lap::jacobi (src/pb/Lap.cc:26-37): W = A x - B; x += scale * W ---------
+    def _jacobi(self, lap_type, x, rhs, w, scale):
+        x.applyLap(lap_type, w)
+        w.axpy(-1.0, rhs)
+        x.axpy(scale, w)
+        x.set_updated_boundaries(False)
+        w.set_updated_boundaries(False)
+
+    def _regrid(self, src, grid):
+        """The same function on a grid with another ghost width."""
+        out = self.field_(grid)
+        out.assign(src.values())
+        return out
+
+    # -- pb::Vcycle (src/pb/Vcycle.h:29-250), x = 0 on entry --------------------
+    def _vcycle(self, lap_type, x, rhs, cogr):
+        grid = x.grid()
+        g = grid.ghost_pt()
+        lap = Lap(grid, lap_type)
+        scale = -1. * lap.jacobiFactor()
+        flag_coarsen = all(grid.dim(d) % 2 == 0 and grid.dim(d) >= 2 * g for d in range(3))
+        res = self.field_(grid)
+        for _ in range(self.nu1_):
+            self._jacobi(lap_type, x, rhs, res, scale)
+        if grid.level_ > -cogr and flag_coarsen:
+            x.applyLap(lap_type, res)
+            res.axpy(-1.0, rhs)
+            gc = max(g - 1, 1)
+            coarse_type = _LOWER_ORDER[lap_type]
+            coarse_same = grid.coarse_grid()               # ghosts of this level
+            coarse_grid = coarse_same.with_ghosts(gc)
+            if gc == g:
+                rcoarse = self.field_(coarse_grid)
+                res.restrict3D(rcoarse)
+            else:
+                tmp = self.field_(coarse_same)
+                res.restrict3D(tmp)
+                rcoarse = self._regrid(tmp, coarse_grid)
+            rcoarse.set_updated_boundaries(False)
+            ucoarse = self.field_(coarse_grid)
+            self._vcycle(coarse_type, ucoarse, rcoarse, cogr)
+            if gc == g:
+                res.extend3D(ucoarse)
+            else:
+                res.extend3D(self._regrid(ucoarse, coarse_same))
+            x.axpy(-1.0, res)
+        for _ in range(self.nu2_):
+            self._jacobi(lap_type, x, rhs, res, scale)
+
+    # -- pb::Mgm (src/pb/Mgm.h:21-112) + SolverLap::solve --------------------------
+    def solve(self, vh, rho):
+        """vh (in: initial guess, out: solution) and rho: no-ghost fields of
+        the solver's precision, shape (nx, ny, nz).  Returns `converged`."""
+        F, grid, lt = self.field_, self.grid_, self.type_
+        shape1 = (1,) + tuple(grid.shape())
+        gf_vh, gf_rho = F(grid), F(grid)
+        gf_vh.assign(vh.reshape(shape1))
+        gf_rho.assign(rho.reshape(shape1))
+        res = F(grid)
+        res.copy_from(gf_rho)
+        rhs = F(grid)
+        if lt == 0:
+            res.applyRHS(0, rhs)         # Laph4M::rhs -> rhs_4th_Mehr1
+        else:
+            rhs.copy_from(res)           # FDoper::rhs: B = A
+        lhs, work1 = F(grid), F(grid)
+        inv_rhs_norm = 1. / rhs.norm2()
+        init_residual_norm = 1.
+        converged = False
+        self.nb_sweeps_ = 0
+        for i in range(self.max_sweeps_):
+            gf_vh.applyLap(lt, lhs)
+            res.copy_from(rhs)           # res.diff(rhs, lhs)
+            res.axpy(-1.0, lhs)
+            res_norm = res.norm2()
+            if i == 0:
+                init_residual_norm = res_norm
+            if res_norm * inv_rhs_norm < self.tol_:
+                self.final_residual_ = res_norm
+                self.final_relative_residual_ = res_norm * inv_rhs_norm
+                converged = True
+                break
+            work1.resetData()
+            self._vcycle(lt, work1, res, self.max_nlevels_)
+            self.nb_sweeps_ += 1
+            gf_vh.axpy(1.0, work1)
+        if not converged:
+            gf_vh.applyLap(lt, lhs)
+            lhs.axpy(-1.0, rhs)
+            self.final_residual_ = lhs.norm2()
+            self.final_relative_residual_ = self.final_residual_ * inv_rhs_norm
+        self.residual_reduction_ = self.final_residual_ / init_residual_norm
+        if self.fully_periodic_:
+            gf_vh.add_scalar(-gf_vh.get_average())   # GridFunc::average0
+        gf_vh.getValues(vh.reshape(shape1))
+        return converged

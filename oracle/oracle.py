@@ -505,6 +505,21 @@ class Ref:
         return out
 
     # -- AndersonMix<Solution> of the reference -------------------------------------
+    def poisson_solve(self, lap_type, vh, rho, ll, bc=(1, 1, 1), nu1=2, nu2=2, max_sweeps=10,
+                      tol=1e-16, max_nlevels=10):
+        """pb::SolverLap<Lap<T>, T>::solve (src/pb/SolverLap.cc:62-72): Mgm +
+        average0.  vh: initial guess (no ghosts); returns (solution, converged,
+        (nb_sweeps, final_residual, final_relative_residual, residual_reduction))."""
+        vh = np.array(vh, order="C")
+        rho = np.ascontiguousarray(rho, dtype=vh.dtype)
+        stats = (ctypes.c_double * 4)()
+        conv = self.lib.ref_poisson_solve(
+            lap_type, _dt(vh.dtype), _c_int3(*vh.shape), _c_dbl3(*ll), _c_int3(*bc), _ptr(vh),
+            _ptr(rho), nu1, nu2, max_sweeps, ctypes.c_double(tol), max_nlevels, stats)
+        if conv < 0:
+            raise ValueError("operator %d not wired in the reference shim" % lap_type)
+        return vh, bool(conv), tuple(stats)
+
     def anderson_create(self, m, beta, x0):
         self.lib.ref_anderson_create.restype = ctypes.c_void_p
         x0 = np.ascontiguousarray(x0, np.float64)

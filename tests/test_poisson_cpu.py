@@ -1,0 +1,95 @@
+"""Poisson multigrid without a GPU: the product's control
+flow (mgmol_b200/poisson.py: SolverLap::solve -> Mgm -> Vcycle) driven by a numpy
+field whose operations are the oracle's, against the compiled reference solver
+and against the committed golden vectors."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle.oracle import Ref
+from poisson_cases import CASES, DEFAULTS, DTYPES, LAPS, charge, guess, key
+from poisson_twin import field_factory
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def gpois():
+    return dict(np.load(os.path.join(ROOT, "tests", "golden", "reference_poisson.npz")))
+
+
+def _solve_twin(port, tag, dims, ll, bc, kw, lt, dt):
+    from mgmol_b200.host import Grid
+    from mgmol_b200.poisson import PoissonMG
+    par = dict(DEFAULTS, **kw)
+    solver = PoissonMG(Grid(dims, ll, 1, bc), lt, field=field_factory(port, dt))
+    solver.setup(par["nu1"], par["nu2"], par["max_sweeps"], par["tol"], par["max_nlevels"])
+    vh = guess(dims, dt)
+    conv = solver.solve(vh, charge(dims, bc, dt))
+    return vh, conv, solver
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+@pytest.mark.parametrize("lt", LAPS)
+@pytest.mark.parametrize("dt", DTYPES, ids=["f64", "f32"])
+def test_control_flow_against_golden(port, gpois, case, lt, dt):
+    tag, dims, ll, bc, kw = case
+    vh, conv, solver = _solve_twin(port, tag, dims, ll, bc, kw, lt, dt)
+    ref = gpois[key(tag, lt, dt)]
+    st = gpois[key(tag, lt, dt) + "_stats"]
+    # same operations in the same order: differences only from the order of
+    # the sums inside norms and the average (1 ulp)
+    eps = 1e-14 if dt == np.float64 else 1e-6
+    assert np.abs(vh.astype(np.float64) - ref).max() <= eps * np.abs(ref).max()
+    assert conv == bool(st[0])
+    assert solver.getNbSweeps() == int(st[1])
+    assert solver.getFinalResidual() == pytest.approx(st[2], rel=1e-6)
+    assert solver.getFinalRelativeResidual() == pytest.approx(st[3], rel=1e-6)
+    assert solver.getResidualReduction() == pytest.approx(st[4], rel=1e-6)
+
+
+@pytest.mark.skipif(not Ref.available(), reason="compiled reference not present")
+def test_golden_is_what_the_compiled_reference_returns(gpois):
+    ref = Ref()
+    for tag, dims, ll, bc, kw in CASES[:2]:
+        for lt in LAPS:
+            for dt in DTYPES:
+                vh, conv, st = ref.poisson_solve(lt, guess(dims, dt), charge(dims, bc, dt), ll, bc,
+                                                 **dict(DEFAULTS, **kw))
+                assert np.array_equal(vh, gpois[key(tag, lt, dt)])
+                assert conv == bool(gpois[key(tag, lt, dt) + "_stats"][0])
+
+
+def test_converges_to_the_discrete_solution(port):
+    """A V(2,2) cycle contracts the residual by about an order of magnitude per
+    sweep; the converged flag, the sweep count and the analytic solution of a
+    single Fourier mode."""
+    from mgmol_b200.host import Grid
+    from mgmol_b200.poisson import PoissonMG
+    dims, ll = (16, 16, 16), (4.0, 4.0, 4.0)
+    x = np.arange(16) * 0.25
+    X, Y, Z = np.meshgrid(x, x, x, indexing="ij")
+    k = 2 * np.pi / 4
+    rho = np.sin(k * X) * np.cos(k * Y) + 0.3 * np.sin(2 * k * Z)
+    exact = np.sin(k * X) * np.cos(k * Y) / (2 * k * k) + 0.3 * np.sin(2 * k * Z) / (4 * k * k)
+    for lt, err in ((0, 1e-4), (2, 3e-4), (1, 6e-3)):
+        solver = PoissonMG(Grid(dims, ll, 1, (1, 1, 1)), lt, field=field_factory(port, np.float64))
+        solver.setup(2, 2, 40, 1e-10, 10)
+        vh = np.zeros(dims)
+        assert solver.solve(vh, rho)
+        assert solver.getNbSweeps() < 40
+        assert solver.getFinalRelativeResidual() < 1e-10
+        assert np.abs(vh - exact).max() < err
+        assert abs(vh.mean()) < 1e-14
+
+
+def test_refuses_what_is_not_built():
+    from mgmol_b200.host import Grid
+    from mgmol_b200.poisson import PoissonMG
+    with pytest.raises(ValueError):
+        PoissonMG(Grid((8, 8, 8), (1.0, 1.0, 1.0), 1), 3)
+    with pytest.raises(ValueError):
+        PoissonMG(Grid((8, 8, 8), (1.0, 1.0, 1.0), 1, (2, 2, 2)), 0)
+    with pytest.raises(ValueError):
+        PoissonMG(Grid((8, 8, 8), (1.0, 1.0, 1.0), 1, (1, 1, 1), (2, 1, 1), (0, 0, 0)), 0)
