@@ -197,6 +197,12 @@ class GridFuncVector:
         self.axpy(-1.0, other)
         return self
 
+    def scal(self, alpha):
+        """GridFunc::operator*=(double) = MPscal over every stored value
+        (src/pb/GridFunc.cc:508-514)."""
+        check(lib().mgb_scal(_dt(self.data), self.data.numel(), float(alpha), _p(self.data),
+                             _stream()))
+
     def jacobi(self, lap_type, B, w, jacobi_factor):
         """src/pb/GridFuncVector.cc:2416-2425."""
         self.trade_boundaries()

@@ -24,20 +24,42 @@ _MIN_GHOSTS = {0: 1, 1: 1, 2: 2}
 _LOWER_ORDER = {0: 0, 1: 1, 2: 1}
 
 
+def _device_field(grid, dtype):
+    return GridFuncVector(grid, 1, dtype)
+
+
+def _bind(field, dtype):
+    """field(grid, dtype) -> field of the solver's precision."""
+    make = field if field is not None else _device_field
+    return lambda grid, dt=dtype: make(grid, dt)
+
+
+def _check(grid, lap_type, who):
+    if lap_type not in _MIN_GHOSTS:
+        raise ValueError("%s: operator %d not available" % (who, lap_type))
+    if any(b not in (0, 1) for b in grid.bc):
+        raise ValueError("%s: boundary conditions 0 and 1 only" % who)
+    if tuple(grid.nproc) != (1, 1, 1):
+        raise ValueError("%s: single-rank boxes only" % who)
+
+
+# Lap::jacobi (src/pb/Lap.cc:26-37): W = A x - B; x += scale * W
+def _jacobi(lap_type, x, rhs, w, scale):
+    x.applyLap(lap_type, w)
+    w.axpy(-1.0, rhs)
+    x.axpy(scale, w)
+    x.set_updated_boundaries(False)
+    w.set_updated_boundaries(False)
+
+
 class PoissonMG:
     """pb::SolverLap<T, T2> (src/pb/SolverLap.h:18-77)."""
 
     def __init__(self, grid, lap_type, dtype=torch.float64, field=None):
-        if lap_type not in _MIN_GHOSTS:
-            raise ValueError("PoissonMG: operator %d not available" % lap_type)
-        if any(b not in (0, 1) for b in grid.bc):
-            raise ValueError("PoissonMG: boundary conditions 0 and 1 only")
-        if tuple(grid.nproc) != (1, 1, 1):
-            raise ValueError("PoissonMG: single-rank boxes only")
+        _check(grid, lap_type, "PoissonMG")
         self.grid_ = grid.with_ghosts(_MIN_GHOSTS[lap_type])
         self.type_ = lap_type
-        self.field_ = field if field is not None else (
-            lambda g: GridFuncVector(g, 1, dtype))
+        self.field_ = _bind(field, dtype)
         self.fully_periodic_ = tuple(grid.bc) == (1, 1, 1)
         self.setup(2, 2, 10, 1.e-16, 10)
         self.nb_sweeps_ = 0
@@ -63,14 +85,6 @@ class PoissonMG:
     def getResidualReduction(self):
         return self.residual_reduction_
 
-    # -- Lap::jacobi (src/pb/Lap.cc:26-37): W = A x - B; x += scale * W ---------
-    def _jacobi(self, lap_type, x, rhs, w, scale):
-        x.applyLap(lap_type, w)
-        w.axpy(-1.0, rhs)
-        x.axpy(scale, w)
-        x.set_updated_boundaries(False)
-        w.set_updated_boundaries(False)
-
     def _regrid(self, src, grid):
         """The same function on a grid with another ghost width."""
         out = self.field_(grid)
@@ -86,7 +100,7 @@ class PoissonMG:
         flag_coarsen = all(grid.dim(d) % 2 == 0 and grid.dim(d) >= 2 * g for d in range(3))
         res = self.field_(grid)
         for _ in range(self.nu1_):
-            self._jacobi(lap_type, x, rhs, res, scale)
+            _jacobi(lap_type, x, rhs, res, scale)
         if grid.level_ > -cogr and flag_coarsen:
             x.applyLap(lap_type, res)
             res.axpy(-1.0, rhs)
@@ -110,7 +124,7 @@ class PoissonMG:
                 res.extend3D(self._regrid(ucoarse, coarse_same))
             x.axpy(-1.0, res)
         for _ in range(self.nu2_):
-            self._jacobi(lap_type, x, rhs, res, scale)
+            _jacobi(lap_type, x, rhs, res, scale)
 
     # -- pb::Mgm (src/pb/Mgm.h:21-112) + SolverLap::solve --------------------------
     def solve(self, vh, rho):
@@ -158,4 +172,133 @@ class PoissonMG:
         if self.fully_periodic_:
             gf_vh.add_scalar(-gf_vh.get_average())   # GridFunc::average0
         gf_vh.getValues(vh.reshape(shape1))
+        return converged
+
+
+class PoissonPCG:
+    """PCGSolver<T, ScalarType> (src/PCGSolver.h:20-106, src/PCGSolver.cc): left
+    preconditioned conjugate gradient on A u = rhs, the preconditioner one
+    multigrid V-cycle in POISSONPRECONDTYPE = float (preconSolve,
+    src/PCGSolver.cc:112-162): the solver's operator on the fine level
+    (Control::lap_type in the reference), Laph2 below, the coarse grids keeping
+    the fine grid's ghost width."""
+
+    def __init__(self, grid, lap_type, dtype=torch.float64, field=None, precond_dtype=None):
+        _check(grid, lap_type, "PoissonPCG")
+        self.grid_ = grid.with_ghosts(_MIN_GHOSTS[lap_type])
+        self.type_ = lap_type
+        self.field_ = _bind(field, dtype)
+        if precond_dtype is None:
+            precond_dtype = torch.float32
+        self.pfield_ = _bind(field, precond_dtype)
+        self.fully_periodic_ = tuple(grid.bc) == (1, 1, 1)
+        self.final_residual_ = -1.
+        self.residual_reduction_ = -1.
+        self.grids_ = None
+        self.setup(2, 2, 10, 1.e-16, 10)
+
+    def setup(self, nu1, nu2, max_sweeps, tol, max_nlevels):
+        self.nu1_, self.nu2_ = int(nu1), int(nu2)
+        self.maxiters_ = int(max_sweeps)
+        self.tol_ = float(tol)
+        self.max_nlevels_ = int(max_nlevels)
+        self._setup_precon()
+
+    def getFinalResidual(self):
+        return self.final_residual_
+
+    def getResidualReduction(self):
+        return self.residual_reduction_
+
+    # -- setupPrecon (src/PCGSolver.cc:50-110) ------------------------------------
+    def _setup_precon(self):
+        g = self.grid_.ghost_pt()
+        grids, mygrid = [self.grid_], self.grid_
+        self.nlevels_ = self.max_nlevels_
+        for ln in range(1, self.max_nlevels_ + 1):
+            if not all(mygrid.dim(d) % 2 == 0 and mygrid.dim(d) >= 2 * g for d in range(3)):
+                self.nlevels_ = ln - 1
+                break
+            mygrid = mygrid.coarse_grid()
+            grids.append(mygrid)
+        self.grids_ = grids
+        self.ptype_ = [self.type_] + [1] * (len(grids) - 1)
+        self.pscale_ = [-1. * Lap(gr, t).jacobiFactor() for gr, t in zip(grids, self.ptype_)]
+        self.work_ = [self.pfield_(gr) for gr in grids]
+        self.rcoarse_ = [self.pfield_(gr) for gr in grids[1:]]
+        self.newv_ = [self.pfield_(gr) for gr in grids[1:]]
+
+    # -- preconSolve (src/PCGSolver.cc:112-162) ------------------------------------
+    def _precon_solve(self, v, f, level):
+        last = level == self.nlevels_
+        ncycl = max(4, self.nu1_ + self.nu2_) if last else self.nu1_
+        lt, scale, work = self.ptype_[level], self.pscale_[level], self.work_[level]
+        for _ in range(ncycl):
+            _jacobi(lt, v, f, work, scale)
+        if last:
+            return
+        rcoarse, newv = self.rcoarse_[level], self.newv_[level]
+        work.restrict3D(rcoarse)
+        rcoarse.set_updated_boundaries(False)
+        newv.resetData()
+        self._precon_solve(newv, rcoarse, level + 1)
+        work.extend3D(newv)
+        v.axpy(-1.0, work)
+        for _ in range(self.nu2_):
+            _jacobi(lt, v, f, work, scale)
+        bc = self.grid_.bc
+        if bc[0] != 1 or bc[2] != 1:      # as written at src/PCGSolver.cc:161
+            v.trade_boundaries()
+
+    # -- solve (src/PCGSolver.cc:165-252) ---------------------------------------------
+    def solve(self, vh, rho):
+        """vh (in: initial guess, out: solution) and rho (the right-hand side of
+        A u = rho): no-ghost fields, shape (nx, ny, nz).  Returns `converged`."""
+        F, P, grid, lt = self.field_, self.pfield_, self.grid_, self.type_
+        shape1 = (1,) + tuple(grid.shape())
+        gf_phi, gf_rhs = F(grid), F(grid)
+        gf_phi.assign(vh.reshape(shape1))
+        gf_rhs.assign(rho.reshape(shape1))
+        lhs = F(grid)
+        gf_phi.applyLap(lt, lhs)
+        res = F(grid)
+        res.copy_from(gf_rhs)
+        res.axpy(-1.0, lhs)
+        init_rnorm = res.norm2()
+        if init_rnorm < 1.e-24:
+            return True
+        rnorm = init_rnorm
+        prec_z, prec_res = P(grid), P(grid)
+        prec_res.assign(res.values())         # GridFunc<float>(res)
+        prec_z.resetData()
+        self._precon_solve(prec_z, prec_res, 0)
+        z, p, ap = F(grid), F(grid), F(grid)
+        z.assign(prec_z.values())
+        p.assign(prec_z.values())
+        rtz = res.gdot(z)
+        converged = False
+        for _ in range(self.maxiters_):
+            p.applyLap(lt, ap)
+            ptap = p.gdot(ap)
+            alp = rtz / ptap
+            gf_phi.axpy(alp, p)
+            res.axpy(-alp, ap)
+            rnorm = res.norm2()
+            if rnorm <= self.tol_ * init_rnorm:
+                converged = True
+                break
+            prec_z.resetData()
+            prec_res.assign(res.values())
+            self._precon_solve(prec_z, prec_res, 0)
+            z.assign(prec_z.values())
+            rtz_new = res.gdot(z)
+            bet = rtz_new / rtz
+            p.scal(bet)
+            p.axpy(1.0, z)
+            rtz = rtz_new
+        self.final_residual_ = rnorm
+        self.residual_reduction_ = rnorm / init_rnorm
+        if self.fully_periodic_:
+            gf_phi.add_scalar(-gf_phi.get_average())
+        gf_phi.getValues(vh.reshape(shape1))
         return converged

@@ -7,8 +7,16 @@
 // the minimum-image distance of the mask construction
 // (src/GridMask.cc:146,162,211).  oracle/Makefile feeds GridMask.cc to g++
 // on stdin so that this header, not src/Control.h, is the "Control.h" found.
+// src/PCGSolver.h includes "Control.h" from a header that sits next to the real
+// one; for it the Makefile pre-includes this file (-include), and the real
+// header's own guard (CONTROL_H, defined here) turns its body off.  PCGSolver
+// reads Control::lap_type (src/PCGSolver.h:74-75), the operator of the
+// preconditioner's fine level.
 #ifndef MGB_ORACLE_CONTROL_STUB_H
 #define MGB_ORACLE_CONTROL_STUB_H
+#ifndef CONTROL_H
+#define CONTROL_H
+#endif
 
 #include <fstream>
 
@@ -16,6 +24,7 @@ class Control
 {
 public:
     short bcPoisson[3];
+    short lap_type;
     static Control* instance()
     {
         static Control c;
@@ -23,7 +32,7 @@ public:
     }
 
 private:
-    Control() { bcPoisson[0] = bcPoisson[1] = bcPoisson[2] = 1; }
+    Control() : lap_type(0) { bcPoisson[0] = bcPoisson[1] = bcPoisson[2] = 1; }
 };
 
 #endif

@@ -520,6 +520,20 @@ class Ref:
             raise ValueError("operator %d not wired in the reference shim" % lap_type)
         return vh, bool(conv), tuple(stats)
 
+    def pcg_solve(self, lap_type, vh, rho, ll, bc=(1, 1, 1), nu1=2, nu2=2, max_sweeps=10,
+                  tol=1e-16, max_nlevels=10):
+        """PCGSolver<Lap<T>, T>::solve (src/PCGSolver.cc:165-252), Control::lap_type
+        = lap_type.  Returns (solution, converged, (final_residual, residual_reduction))."""
+        vh = np.array(vh, order="C")
+        rho = np.ascontiguousarray(rho, dtype=vh.dtype)
+        stats = (ctypes.c_double * 2)()
+        conv = self.lib.ref_pcg_solve(
+            lap_type, _dt(vh.dtype), _c_int3(*vh.shape), _c_dbl3(*ll), _c_int3(*bc), _ptr(vh),
+            _ptr(rho), nu1, nu2, max_sweeps, ctypes.c_double(tol), max_nlevels, stats)
+        if conv < 0:
+            raise ValueError("operator %d not wired in the reference shim" % lap_type)
+        return vh, bool(conv), tuple(stats)
+
     def anderson_create(self, m, beta, x0):
         self.lib.ref_anderson_create.restype = ctypes.c_void_p
         x0 = np.ascontiguousarray(x0, np.float64)

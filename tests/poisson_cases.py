@@ -13,6 +13,17 @@ CASES = [
     ("shallow", (16, 16, 16), (4.0, 4.0, 4.0), (1, 1, 1),
      dict(nu1=1, nu2=3, max_sweeps=4, tol=1e-16, max_nlevels=2)),
 ]
+# PCGSolver cases: few iterations, so that the comparison happens well above the
+# rounding floor of the residual (a stagnating CG is not reproducible to more
+# than its floor between two summation orders)
+PCG_CASES = [
+    ("pcg_per", (24, 16, 12), (5.0, 4.0, 3.5), (1, 1, 1), dict(max_sweeps=4)),
+    ("pcg_dir", (12, 20, 8), (3.0, 4.0, 2.0), (0, 0, 0), dict(max_sweeps=4)),
+    ("pcg_mix", (16, 16, 16), (4.0, 4.0, 4.0), (1, 1, 0), dict(max_sweeps=3)),
+    ("pcg_mix2", (16, 16, 16), (4.0, 4.0, 4.0), (0, 1, 1), dict(max_sweeps=3, nu1=1, nu2=1)),
+    ("pcg_conv", (24, 16, 12), (5.0, 4.0, 3.5), (1, 1, 1), dict(max_sweeps=30, tol=1e-5)),
+    ("pcg_shallow", (16, 16, 16), (4.0, 4.0, 4.0), (1, 1, 1), dict(max_sweeps=3, max_nlevels=1)),
+]
 LAPS = (0, 1, 2)
 DTYPES = (np.float64, np.float32)
 DEFAULTS = dict(nu1=2, nu2=2, max_sweeps=10, tol=1e-16, max_nlevels=10)

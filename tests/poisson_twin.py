@@ -34,9 +34,16 @@ class TwinField:
         nx, ny, nz = self.grid_.shape()
         return (slice(None), slice(g, g + nx), slice(g, g + ny), slice(g, g + nz))
 
+    def scal(self, alpha):
+        dt = self.data.dtype
+        if alpha == 0.0:
+            self.data = np.zeros_like(self.data)
+        elif alpha != 1.0:
+            self.data = (float(alpha) * self.data.astype(np.float64)).astype(dt)
+
     def assign(self, noghost):
         self.data[...] = 0
-        self.data[self._sl()] = noghost
+        self.data[self._sl()] = noghost          # converts to this field's precision
         self.updated_boundaries_ = False
 
     def getValues(self, out):
@@ -109,5 +116,9 @@ class TwinField:
         self.data = self.data + np.asarray(alpha, np.float64).astype(self.data.dtype)
 
 
-def field_factory(port, dtype):
-    return lambda grid: TwinField(port, grid, dtype)
+def field_factory(port, dtype=None):
+    """field(grid, dtype) as PoissonMG / PoissonPCG expect it; torch dtypes of
+    the preconditioner are mapped to numpy."""
+    import torch
+    tmap = {torch.float32: np.float32, torch.float64: np.float64}
+    return lambda grid, dt: TwinField(port, grid, tmap.get(dt, dt))

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-from poisson_cases import CASES, DEFAULTS, DTYPES, LAPS, charge, guess, key
+from poisson_cases import CASES, DEFAULTS, DTYPES, LAPS, PCG_CASES, charge, guess, key
 from poisson_twin import field_factory
 
 pytestmark = pytest.mark.gpu
@@ -62,7 +62,7 @@ def test_poisson_device_equals_oracle_control_flow(port, lt):
     dims, ll, bc = (20, 12, 28), (3.0, 2.0, 4.5), (1, 0, 1)
     for dt in DTYPES:
         got, conv, solver = _solve_device(dims, ll, bc, {}, lt, dt)
-        twin = PoissonMG(Grid(dims, ll, 1, bc), lt, field=field_factory(port, dt))
+        twin = PoissonMG(Grid(dims, ll, 1, bc), lt, dt, field=field_factory(port))
         vh = guess(dims, dt)
         conv2 = twin.solve(vh, charge(dims, bc, dt))
         eps = 1e-13 if dt == np.float64 else 2e-6
@@ -78,3 +78,33 @@ def test_poisson_larger_box_residual():
     assert solver.getNbSweeps() == 10 and not conv
     assert solver.getFinalRelativeResidual() < 1e-8
     assert abs(vh.mean()) < 1e-13 * np.abs(vh).max()
+
+
+def _pcg_device(dims, ll, bc, kw, lt, dt):
+    from mgmol_b200.host import Grid
+    from mgmol_b200.poisson import PoissonPCG
+    par = dict(DEFAULTS, **kw)
+    solver = PoissonPCG(Grid(dims, ll, 1, bc), lt, TDT[dt])
+    solver.setup(par["nu1"], par["nu2"], par["max_sweeps"], par["tol"], par["max_nlevels"])
+    vh = torch.from_numpy(guess(dims, dt)).cuda()
+    conv = solver.solve(vh, torch.from_numpy(charge(dims, bc, dt)).cuda())
+    torch.cuda.synchronize()
+    return vh.cpu().numpy(), conv, solver
+
+
+@pytest.mark.parametrize("case", PCG_CASES, ids=[c[0] for c in PCG_CASES])
+@pytest.mark.parametrize("lt", LAPS)
+@pytest.mark.parametrize("dt", DTYPES, ids=["f64", "f32"])
+def test_pcg_against_golden(gpois, case, lt, dt):
+    """PCGSolver::solve (src/PCGSolver.cc:165-252) with the float multigrid
+    preconditioner, on the device, against the compiled reference.  The CG
+    scalars are ratios of dot products the device sums in another order."""
+    tag, dims, ll, bc, kw = case
+    vh, conv, solver = _pcg_device(dims, ll, bc, kw, lt, dt)
+    ref = gpois[key(tag, lt, dt)]
+    st = gpois[key(tag, lt, dt) + "_stats"]
+    eps = 1e-11 if dt == np.float64 else 5e-6
+    assert np.abs(vh.astype(np.float64) - ref).max() <= eps * np.abs(ref).max()
+    assert conv == bool(st[0])
+    assert solver.getFinalResidual() == pytest.approx(st[1], rel=1e-4)
+    assert solver.getResidualReduction() == pytest.approx(st[2], rel=1e-4)

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 from oracle.oracle import Ref
-from poisson_cases import CASES, DEFAULTS, DTYPES, LAPS, charge, guess, key
+from poisson_cases import CASES, DEFAULTS, DTYPES, LAPS, PCG_CASES, charge, guess, key
 from poisson_twin import field_factory
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -23,7 +23,7 @@ def _solve_twin(port, tag, dims, ll, bc, kw, lt, dt):
     from mgmol_b200.host import Grid
     from mgmol_b200.poisson import PoissonMG
     par = dict(DEFAULTS, **kw)
-    solver = PoissonMG(Grid(dims, ll, 1, bc), lt, field=field_factory(port, dt))
+    solver = PoissonMG(Grid(dims, ll, 1, bc), lt, dt, field=field_factory(port))
     solver.setup(par["nu1"], par["nu2"], par["max_sweeps"], par["tol"], par["max_nlevels"])
     vh = guess(dims, dt)
     conv = solver.solve(vh, charge(dims, bc, dt))
@@ -74,7 +74,7 @@ def test_converges_to_the_discrete_solution(port):
     rho = np.sin(k * X) * np.cos(k * Y) + 0.3 * np.sin(2 * k * Z)
     exact = np.sin(k * X) * np.cos(k * Y) / (2 * k * k) + 0.3 * np.sin(2 * k * Z) / (4 * k * k)
     for lt, err in ((0, 1e-4), (2, 3e-4), (1, 6e-3)):
-        solver = PoissonMG(Grid(dims, ll, 1, (1, 1, 1)), lt, field=field_factory(port, np.float64))
+        solver = PoissonMG(Grid(dims, ll, 1, (1, 1, 1)), lt, np.float64, field=field_factory(port))
         solver.setup(2, 2, 40, 1e-10, 10)
         vh = np.zeros(dims)
         assert solver.solve(vh, rho)
@@ -82,6 +82,41 @@ def test_converges_to_the_discrete_solution(port):
         assert solver.getFinalRelativeResidual() < 1e-10
         assert np.abs(vh - exact).max() < err
         assert abs(vh.mean()) < 1e-14
+
+
+@pytest.mark.parametrize("case", PCG_CASES, ids=[c[0] for c in PCG_CASES])
+@pytest.mark.parametrize("lt", LAPS)
+@pytest.mark.parametrize("dt", DTYPES, ids=["f64", "f32"])
+def test_pcg_control_flow_against_golden(port, gpois, case, lt, dt):
+    """PoissonPCG (PCGSolver::solve + preconSolve in float) on oracle fields
+    against the compiled reference."""
+    from mgmol_b200.host import Grid
+    from mgmol_b200.poisson import PoissonPCG
+    tag, dims, ll, bc, kw = case
+    par = dict(DEFAULTS, **kw)
+    solver = PoissonPCG(Grid(dims, ll, 1, bc), lt, dt, field=field_factory(port),
+                        precond_dtype=np.float32)
+    solver.setup(par["nu1"], par["nu2"], par["max_sweeps"], par["tol"], par["max_nlevels"])
+    vh = guess(dims, dt)
+    conv = solver.solve(vh, charge(dims, bc, dt))
+    ref = gpois[key(tag, lt, dt)]
+    st = gpois[key(tag, lt, dt) + "_stats"]
+    # the CG scalars are ratios of dot products summed in another order
+    eps = 1e-12 if dt == np.float64 else 2e-6
+    assert np.abs(vh.astype(np.float64) - ref).max() <= eps * np.abs(ref).max()
+    assert conv == bool(st[0])
+    assert solver.getFinalResidual() == pytest.approx(st[1], rel=1e-5)
+    assert solver.getResidualReduction() == pytest.approx(st[2], rel=1e-5)
+
+
+def test_pcg_zero_right_hand_side_returns_at_once(port):
+    from mgmol_b200.host import Grid
+    from mgmol_b200.poisson import PoissonPCG
+    dims = (8, 8, 8)
+    solver = PoissonPCG(Grid(dims, (2.0, 2.0, 2.0), 1), 0, np.float64, field=field_factory(port),
+                        precond_dtype=np.float32)
+    vh = np.zeros(dims)
+    assert solver.solve(vh, np.zeros(dims)) and not vh.any()
 
 
 def test_refuses_what_is_not_built():
@@ -93,3 +128,6 @@ def test_refuses_what_is_not_built():
         PoissonMG(Grid((8, 8, 8), (1.0, 1.0, 1.0), 1, (2, 2, 2)), 0)
     with pytest.raises(ValueError):
         PoissonMG(Grid((8, 8, 8), (1.0, 1.0, 1.0), 1, (1, 1, 1), (2, 1, 1), (0, 0, 0)), 0)
+    from mgmol_b200.poisson import PoissonPCG
+    with pytest.raises(ValueError):
+        PoissonPCG(Grid((8, 8, 8), (1.0, 1.0, 1.0), 1), 4)
