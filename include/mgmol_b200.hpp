@@ -270,6 +270,13 @@ public:
         updated_boundaries_ = true;
     }
     void set_updated_boundaries(const bool f) { updated_boundaries_ = f; }
+    bool updated_boundaries() const { return updated_boundaries_; }
+    // GridFunc::scal = MPscal over every stored value (src/pb/GridFunc.cc:516-521)
+    void scal(const double alpha, void* stream = nullptr)
+    {
+        MGB_CHECK(mgb_scal(
+            dtype_of<T>::value, grid_.sizeg() * (size_t)nfunc_, alpha, mem_.data(), stream));
+    }
     // BlockVector::setDataWithGhosts (src/BlockVector.cc:489-517)
     template <typename T2>
     void assign(const T2* noghost_dev, const size_t ld, void* stream = nullptr)
@@ -311,14 +318,16 @@ public:
     // src/pb/GridFuncVector.cc:2400-2413
     void applyRHS(const int type, GridFuncVector<T>& rhs, void* stream = nullptr)
     {
-        trade_boundaries(stream);
         if (type == 0)
+        {
+            trade_boundaries(stream);
             MGB_CHECK(mgb_fd_apply(MGB_FD_RHS_4TH_MEHR1, dtype_of<T>::value, grid_.c(),
                 mem_.data(), rhs.data(), nfunc_, grid_.ghost_pt(), stream));
-        else
+            rhs.set_updated_boundaries(false);
+        }
+        else // as the reference has it: a memcpy of rhs INTO this (:2408-2411)
             MGB_CHECK(mgb_copy_dev(
-                rhs.data(), mem_.data(), grid_.sizeg() * nfunc_ * sizeof(T), stream));
-        rhs.set_updated_boundaries(false);
+                mem_.data(), rhs.data(), grid_.sizeg() * nfunc_ * sizeof(T), stream));
     }
     // src/pb/GridFuncVector.cc:90-136; V: ghosted double field on the device
     void pointwiseProduct(GridFuncVector<T>& A, const double* Vghost, void* stream = nullptr)

@@ -116,3 +116,86 @@ def test_cpp_loewdin_transform_host():
     bad = np.array([[1.0, 2.0], [2.0, 1.0]])
     r = run(bad)
     assert r.returncode == 3
+
+
+# -- the C++ Poisson solvers (include/mgmol_b200_poisson.hpp) ---------------------
+def _build_poisson_mirror():
+    from mgmol_b200 import build as b
+    from oracle import oracle as orc
+    b.build()
+    orc.build(ref=False, port=True)
+    src = os.path.join(ROOT, "tests", "cpp", "test_poisson_mirror.cc")
+    exe = os.path.join(ROOT, "tests", "cpp", "test_poisson_mirror")
+    cmd = ["g++", "-std=c++11", "-O2", "-Wall", "-I", os.path.join(ROOT, "include"),
+           "-I", os.path.join(ROOT, "tests", "cpp"), src,
+           "-L", os.path.join(ROOT, "mgmol_b200"), "-lmgmol_b200",
+           "-L", os.path.join(ROOT, "oracle"), "-lmgmol_oracle",
+           "-Wl,-rpath,$ORIGIN/../../mgmol_b200", "-Wl,-rpath,$ORIGIN/../../oracle", "-o", exe]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def _run_poisson_mirror(exe, mode, solver, case, lt, dt):
+    import sys
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from poisson_cases import DEFAULTS, charge, guess
+    tag, dims, ll, bc, kw = case
+    par = dict(DEFAULTS, **kw)
+    head = "%d %d %d  %d %d %d  %r %r %r  %d %d %d  %d %d %d %r %d\n" % (
+        (solver, lt, 1 if dt == np.float64 else 0) + tuple(dims) + tuple(ll) + tuple(bc)
+        + (par["nu1"], par["nu2"], par["max_sweeps"], par["tol"], par["max_nlevels"]))
+    body = "\n".join(repr(float(v)) for v in guess(dims, dt).ravel()) + "\n" + \
+        "\n".join(repr(float(v)) for v in charge(dims, bc, dt).ravel()) + "\n"
+    r = subprocess.run([exe, mode], input=head + body, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, (r.returncode, r.stdout[:300], r.stderr[:300])
+    lines = r.stdout.strip().splitlines()
+    stats = [float(v) for v in lines[0].split()]
+    vh = np.array([float(v) for v in lines[1:]]).reshape(dims)
+    return vh, stats
+
+
+def _check_poisson_mirror(mode, eps64, eps32, eps_pcg64, eps_pcg32, subset=False):
+    import sys
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from poisson_cases import CASES, PCG_CASES, key
+    exe = _build_poisson_mirror()
+    g = np.load(os.path.join(ROOT, "tests", "golden", "reference_poisson.npz"))
+    plan = ((0, CASES), (1, PCG_CASES))
+    laps = (0, 1, 2)
+    if subset:      # one process (one CUDA context) per solve: keep the device leg short
+        plan = ((0, [CASES[0], CASES[1], CASES[3]]), (1, [PCG_CASES[0], PCG_CASES[2]]))
+        laps = (0, 2)
+    for solver, cases in plan:
+        for case in cases:
+            for lt in laps:
+                for dt in (np.float64, np.float32):
+                    vh, st = _run_poisson_mirror(exe, mode, solver, case, lt, dt)
+                    ref = g[key(case[0], lt, dt)]
+                    rst = g[key(case[0], lt, dt) + "_stats"]
+                    eps = ((eps64 if dt == np.float64 else eps32) if solver == 0
+                           else (eps_pcg64 if dt == np.float64 else eps_pcg32))
+                    assert np.abs(vh - ref).max() <= eps * np.abs(ref).max(), (case[0], lt, dt)
+                    assert bool(st[0]) == bool(rst[0]), (case[0], lt, dt)
+                    if solver == 0:
+                        assert int(st[1]) == int(rst[1])
+                        assert abs(st[2] - rst[2]) <= 1e-5 * rst[2]
+                        assert abs(st[4] - rst[4]) <= 1e-5 * rst[4]
+                    else:
+                        assert abs(st[2] - rst[1]) <= 1e-4 * rst[1]
+                        assert abs(st[4] - rst[2]) <= 1e-4 * rst[2]
+
+
+def test_cpp_poisson_solvers_control_flow():
+    """PoissonMG / PoissonPCG of include/mgmol_b200_poisson.hpp instantiated with
+    host fields over the oracle's kernels, against the golden vectors of the
+    compiled reference solvers (SolverLap/Mgm/Vcycle and PCGSolver)."""
+    _check_poisson_mirror("cpu", 1e-14, 1e-6, 1e-10, 2e-6)
+
+
+@pytest.mark.gpu
+def test_cpp_poisson_solvers_on_device():
+    """The same templates with the device field GridFunc<T> over the C ABI."""
+    _check_poisson_mirror("gpu", 1e-13, 2e-6, 1e-9, 5e-6, subset=True)

@@ -103,7 +103,7 @@ def test_pcg_against_golden(gpois, case, lt, dt):
     vh, conv, solver = _pcg_device(dims, ll, bc, kw, lt, dt)
     ref = gpois[key(tag, lt, dt)]
     st = gpois[key(tag, lt, dt) + "_stats"]
-    eps = 1e-11 if dt == np.float64 else 5e-6
+    eps = 1e-9 if dt == np.float64 else 5e-6
     assert np.abs(vh.astype(np.float64) - ref).max() <= eps * np.abs(ref).max()
     assert conv == bool(st[0])
     assert solver.getFinalResidual() == pytest.approx(st[1], rel=1e-4)
