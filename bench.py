@@ -379,7 +379,40 @@ def measure_pieces(H, grid, phi, ham, lap_type, tdt, S, norb, npt, comm=None, hs
         "ms": ms, "sequence": "H psi, Phi^T H Phi, precond_mg (2 levels), Gram, Phi M"}
     pc.close()
     del res
+    if comm is None:
+        out.update(measure_poisson(H, grid, lap_type))
     return out
+
+
+def measure_poisson(H, grid, lap_type):
+    """SURVEY 8f row f4, reported next to the path: the Hartree Poisson multigrid
+    (SolverLap / Mgm / Vcycle, double) on the workload's grid, ten V(2,2) sweeps on
+    one scalar field.  Host control flow over the C-ABI grid operations; the
+    cycle is launch-bound at this size, which is what the number shows.  A failure
+    here never affects the headline line."""
+    import torch
+    try:
+        from mgmol_b200._lib import lib
+        from mgmol_b200.poisson import PoissonMG
+        lt = lap_type if lap_type in (0, 1, 2) else 0
+        rho = torch.rand(grid.shape(), dtype=torch.float64, device="cuda")
+        rho -= rho.mean()
+        solver = PoissonMG(grid, lt)
+        vh = torch.zeros_like(rho)
+
+        def solve():
+            vh.zero_()
+            solver.solve(vh, rho)
+        n0 = lib().mgb_launch_count()
+        ms = _time_cuda(torch, solve, reps=2, warm=1)
+        launches = (lib().mgb_launch_count() - n0) // 3
+        sweeps = max(1, solver.getNbSweeps())
+        return {"poisson_mg": {"ms": ms, "ms_per_sweep": ms / sweeps, "sweeps": sweeps,
+                               "relative_residual": solver.getFinalRelativeResidual(),
+                               "launches_per_solve": int(launches), "lap_type": lt,
+                               "bound": "launch latency (one field, %d kernels)" % launches}}
+    except Exception as e:  # noqa: BLE001
+        return {"poisson_mg": {"unavailable": "%s: %s" % (type(e).__name__, e)}}
 
 
 def run_ours(args):
