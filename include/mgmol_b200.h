@@ -352,6 +352,27 @@ int mgb_rho_blas3(int dtype, size_t nrows, int nfunc, const void* phi1, size_t l
     const double* X, int ldx, const void* phi2, size_t ld2, double* rho,
     void* stream);
 
+/* ---- Hartree Poisson solvers on one scalar field ------
+ * solver MGB_POISSON_MG  = pb::SolverLap<Lap<T>,T>::solve (src/pb/SolverLap.cc:
+ *                          62-72): pb::Mgm (src/pb/Mgm.h:21-112) over pb::Vcycle
+ *                          (src/pb/Vcycle.h:29-250), average0 when fully periodic;
+ *        MGB_POISSON_PCG = PCGSolver<Lap<T>,T>::solve (src/PCGSolver.cc:165-252),
+ *                          float multigrid preconditioner (preconSolve, :112-162).
+ * lap_type MGB_LAP_4M / MGB_LAP_2 / MGB_LAP_4; grid->bc 0 or 1; single rank
+ * (the solvers choose their own ghost width, grid->ghosts is not used).  vh (in:
+ * initial guess, out: solution) and rho: no-ghost device arrays of `dtype`.
+ * The parameters are those of Solver::setup (nu1, nu2, max_sweeps, tol,
+ * max_nlevels).  stats (host, 5 doubles, may be null): converged, nb_sweeps,
+ * final_residual, final_relative_residual, residual_reduction (-1 where the
+ * solver has no such getter).  The control flow runs on the host over this
+ * library's grid kernels (include/mgmol_b200_poisson.hpp holds it as C++
+ * templates); the call returns after the solution is in vh.                  */
+#define MGB_POISSON_MG 0
+#define MGB_POISSON_PCG 1
+int mgb_poisson_solve(int solver, int lap_type, int dtype, const mgb_grid* grid, void* vh,
+    const void* rho, int nu1, int nu2, int max_sweeps, double tol, int max_nlevels,
+    double* stats);
+
 /* ---- multi-GPU: one process per GPU, 3-D block decomposition of pb::PEenv.
  * The communicator wraps NCCL; the unique id (128 bytes) is created on rank 0
  * with mgb_comm_unique_id and distributed by the caller (MPI_Bcast in MGmol,

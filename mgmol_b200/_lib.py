@@ -77,6 +77,8 @@ _SIGS = {
     "mgb_dot": (c_int, [c_int, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mgb_dot_cols": (c_int, [c_int, c_size_t, c_int, c_double, c_void_p, c_size_t, c_void_p,
                              c_size_t, c_void_p, c_void_p]),
+    "mgb_poisson_solve": (c_int, [c_int, c_int, c_int, ctypes.POINTER(MgbGrid), c_void_p, c_void_p,
+                                  c_int, c_int, c_int, c_double, c_int, c_void_p]),
     "mgb_rho_blas3": (c_int, [c_int, c_size_t, c_int, c_void_p, c_size_t, c_void_p, c_int,
                               c_void_p, c_size_t, c_void_p, c_void_p]),
     "mgb_gfv_jacobi": (c_int, [c_int, ctypes.POINTER(MgbGrid), c_void_p, c_void_p,

@@ -34,6 +34,7 @@ SOURCES = {
     "blas1_cols.cu": [],
     "contractions.cu": [],
     "comm.cu": [],
+    "poisson.cu": [],
 }
 
 

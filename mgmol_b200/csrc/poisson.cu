@@ -1,0 +1,79 @@
+// C-ABI entry of the Hartree Poisson solvers.  The solvers
+// themselves are the header templates of include/mgmol_b200_poisson.hpp -- host
+// control flow of pb::SolverLap / pb::Mgm / pb::Vcycle and PCGSolver over this
+// library's own grid operations with one function; this file instantiates them
+// on the device field and gives them a plain-C face.
+#include "common.cuh"
+#include "mgmol_b200_poisson.hpp"
+
+using namespace mgb;
+
+namespace
+{
+template <typename T>
+int solve_t(int solver, int lap_type, const mgmol_b200::Grid& grid, T* vh, const T* rho, int nu1,
+    int nu2, int max_sweeps, double tol, int max_nlevels, double* stats)
+{
+    using namespace mgmol_b200;
+    bool conv;
+    if (solver == MGB_POISSON_MG)
+    {
+        PoissonMG<GridFunc<T>> s(grid, lap_type);
+        s.setup((short)nu1, (short)nu2, (short)max_sweeps, tol, (short)max_nlevels);
+        conv = s.solve(vh, rho);
+        if (stats)
+        {
+            stats[1] = s.getNbSweeps();
+            stats[2] = s.getFinalResidual();
+            stats[3] = s.getFinalRelativeResidual();
+            stats[4] = s.getResidualReduction();
+        }
+    }
+    else
+    {
+        PoissonPCG<GridFunc<T>, GridFunc<float>> s(grid, lap_type);
+        s.setup((short)nu1, (short)nu2, (short)max_sweeps, tol, (short)max_nlevels);
+        conv = s.solve(vh, rho);
+        if (stats)
+        {
+            stats[1] = -1.;
+            stats[2] = s.getFinalResidual();
+            stats[3] = -1.;
+            stats[4] = s.getResidualReduction();
+        }
+    }
+    if (stats) stats[0] = conv ? 1. : 0.;
+    return MGB_OK;
+}
+}
+
+extern "C" int mgb_poisson_solve(int solver, int lap_type, int dtype, const mgb_grid* grid,
+    void* vh, const void* rho, int nu1, int nu2, int max_sweeps, double tol, int max_nlevels,
+    double* stats)
+{
+    if (int rc = require_device()) return rc;
+    if (int rc = check_grid(grid)) return rc;
+    MGB_REQUIRE(vh && rho, "mgb_poisson_solve: null pointer");
+    MGB_REQUIRE(solver == MGB_POISSON_MG || solver == MGB_POISSON_PCG,
+        "mgb_poisson_solve: solver %d (0 = multigrid, 1 = preconditioned CG)", solver);
+    MGB_REQUIRE(lap_type == MGB_LAP_4M || lap_type == MGB_LAP_2 || lap_type == MGB_LAP_4,
+        "mgb_poisson_solve: operator %d not available (Laph4M, Laph2, Laph4)", lap_type);
+    MGB_REQUIRE(dtype == MGB_F32 || dtype == MGB_F64, "mgb_poisson_solve: bad dtype %d", dtype);
+    MGB_REQUIRE(nu1 >= 0 && nu2 >= 0 && max_sweeps >= 0 && max_nlevels >= 0,
+        "mgb_poisson_solve: negative parameter");
+    for (int d = 0; d < 3; d++)
+        MGB_REQUIRE(grid->nproc[d] == 1, "mgb_poisson_solve: single-rank boxes only");
+    unsigned gdim[3];
+    double ll[3];
+    for (int d = 0; d < 3; d++)
+    {
+        gdim[d] = (unsigned)grid->gdim[d];
+        ll[d]   = grid->h[d] * grid->gdim[d];
+    }
+    const mgmol_b200::Grid g(gdim, ll, (short)grid->ghosts, grid->bc, grid->nproc, grid->coord);
+    if (dtype == MGB_F64)
+        return solve_t<double>(solver, lap_type, g, (double*)vh, (const double*)rho, nu1, nu2,
+            max_sweeps, tol, max_nlevels, stats);
+    return solve_t<float>(solver, lap_type, g, (float*)vh, (const float*)rho, nu1, nu2,
+        max_sweeps, tol, max_nlevels, stats);
+}

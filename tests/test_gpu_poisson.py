@@ -108,3 +108,43 @@ def test_pcg_against_golden(gpois, case, lt, dt):
     assert conv == bool(st[0])
     assert solver.getFinalResidual() == pytest.approx(st[1], rel=1e-4)
     assert solver.getResidualReduction() == pytest.approx(st[2], rel=1e-4)
+
+
+@pytest.mark.parametrize("solver", [0, 1], ids=["mg", "pcg"])
+@pytest.mark.parametrize("lt", [0, 2])
+@pytest.mark.parametrize("dt", DTYPES, ids=["f64", "f32"])
+def test_poisson_c_abi_entry(gpois, solver, lt, dt):
+    """mgb_poisson_solve: the C entry over the same solver code (the C++
+    templates instantiated inside the library), against the golden vectors."""
+    import ctypes
+    from mgmol_b200._lib import lib, check
+    from mgmol_b200.host import Grid
+    cases = (CASES[0], CASES[2]) if solver == 0 else (PCG_CASES[0], PCG_CASES[2])
+    for tag, dims, ll, bc, kw in cases:
+        par = dict(DEFAULTS, **kw)
+        grid = Grid(dims, ll, 1, bc)
+        vh = torch.from_numpy(guess(dims, dt)).cuda()
+        rho = torch.from_numpy(charge(dims, bc, dt)).cuda()
+        stats = (ctypes.c_double * 5)()
+        check(lib().mgb_poisson_solve(
+            solver, lt, 1 if dt == np.float64 else 0, grid.ref(), ctypes.c_void_p(vh.data_ptr()),
+            ctypes.c_void_p(rho.data_ptr()), par["nu1"], par["nu2"], par["max_sweeps"], par["tol"],
+            par["max_nlevels"], stats))
+        torch.cuda.synchronize()
+        ref = gpois[key(tag, lt, dt)]
+        st = gpois[key(tag, lt, dt) + "_stats"]
+        if solver == 0:
+            eps = 1e-13 if dt == np.float64 else 2e-6
+            assert int(stats[1]) == int(st[1])
+            assert stats[2] == pytest.approx(st[2], rel=1e-6)
+        else:
+            eps = 1e-9 if dt == np.float64 else 5e-6
+            assert stats[2] == pytest.approx(st[1], rel=1e-4)
+        assert np.abs(vh.cpu().numpy().astype(np.float64) - ref).max() <= eps * np.abs(ref).max()
+        assert bool(stats[0]) == bool(st[0])
+    # refusals come back as error codes, not aborts
+    g3 = Grid((8, 8, 8), (1.0, 1.0, 1.0), 1)
+    z = torch.zeros((8, 8, 8), dtype=torch.float64, device="cuda")
+    p = ctypes.c_void_p(z.data_ptr())
+    assert lib().mgb_poisson_solve(0, 3, 1, g3.ref(), p, p, 2, 2, 10, 1e-16, 10, None) != 0
+    assert lib().mgb_poisson_solve(2, 0, 1, g3.ref(), p, p, 2, 2, 10, 1e-16, 10, None) != 0

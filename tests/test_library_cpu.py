@@ -57,6 +57,7 @@ def test_no_cpu_fallback():
     assert L.mgb_rho_blas3(1, n, 1, buf, n, buf, 1, buf, n, buf, None) == -4
     assert L.mgb_masks_create(ctypes.byref(p), ctypes.byref(g), 1, 2, 4, 0) == -4
     assert L.mgb_hpsi_host(0, 1, ctypes.byref(g), buf, n, buf, buf, n, 1, 0) == -4
+    assert L.mgb_poisson_solve(0, 0, 1, ctypes.byref(g), buf, buf, 2, 2, 10, 1e-16, 10, None) == -4
 
 
 def test_product_never_imports_oracle():
