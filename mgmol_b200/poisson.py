@@ -15,7 +15,7 @@ host.py.  The default is the device class; the CPU tests drive this very
 control flow with a numpy stand-in to pin it against the compiled reference."""
 import torch
 
-from .host import Grid, GridFuncVector, Lap  # noqa: F401
+from .host import GridFuncVector, Lap
 
 # ghost layers the operator needs (Laph4M / Laph2 / Laph4 ::minNumberGhosts)
 _MIN_GHOSTS = {0: 1, 1: 1, 2: 2}
