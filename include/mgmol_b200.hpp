@@ -160,6 +160,43 @@ inline bool loewdinTransform(const int n, const double* S, double* P, double* sq
                 }
             }
     }
+    // The accumulated rotations drift from orthogonality by ~n eps; the
+    // reference's own unit test asks B^-1/2 B^1/2 = 1 to 1e-14
+    // (tests/testGramMatrix.cc:92-108).  One Newton-Schulz step
+    // V <- V (3 - V^T V) / 2 squares that error; the eigenvalues are then the
+    // Rayleigh quotients of the polished vectors with the original matrix.
+    {
+        std::vector<double> W(N * N), V2(N * N);
+        for (size_t j = 0; j < N; j++)
+            for (size_t i = 0; i < N; i++)
+            {
+                double w = 0.;
+                for (size_t k = 0; k < N; k++)
+                    w += V[k + i * N] * V[k + j * N];
+                W[i + j * N] = (i == j ? 1.5 : 0.) - 0.5 * w;
+            }
+        for (size_t j = 0; j < N; j++)
+            for (size_t i = 0; i < N; i++)
+            {
+                double v = 0.;
+                for (size_t k = 0; k < N; k++)
+                    v += V[i + k * N] * W[k + j * N];
+                V2[i + j * N] = v;
+            }
+        V.swap(V2);
+        for (size_t k = 0; k < N; k++)
+        {
+            double lam = 0.;
+            for (size_t j = 0; j < N; j++)
+            {
+                double sv = 0.;
+                for (size_t i = 0; i < N; i++)
+                    sv += S[i + j * N] * V[i + k * N];
+                lam += sv * V[j + k * N];
+            }
+            A[k + k * N] = lam;
+        }
+    }
     for (size_t k = 0; k < N; k++)
         if (!(A[k + k * N] > 0.)) return false;
     for (size_t j = 0; j < N; j++)

@@ -116,6 +116,19 @@ def test_cpp_loewdin_transform_host():
     bad = np.array([[1.0, 2.0], [2.0, 1.0]])
     r = run(bad)
     assert r.returncode == 3
+    # the Loewdin part of the reference's own unit test (tests/testGramMatrix.cc:
+    # 44-58,92-121): n = 213, diagonal 2, off-diagonal elements within 1/n;
+    # B^-1/2 B^1/2 = 1 to 1e-14 and B^1/2 B^1/2 = B to 1e-12 (max norm)
+    n = 213
+    A = rng.uniform(-1.0 / n, 1.0 / n, (n, n))
+    B = 0.5 * (A + A.T)
+    np.fill_diagonal(B, 2.0)
+    r = run(B)
+    assert r.returncode == 0
+    rows = np.array([[float(v) for v in line.split()] for line in r.stdout.strip().splitlines()])
+    P, R = rows[:n], rows[n:]
+    assert np.abs(P @ R - np.eye(n)).max() <= 1e-14
+    assert np.abs(R @ R - B).max() <= 1e-12
 
 
 # -- the C++ Poisson solvers (include/mgmol_b200_poisson.hpp) ---------------------
