@@ -47,8 +47,14 @@ def _stamp(src, flags):
         if name.endswith((".h", ".cuh")):
             with open(os.path.join(CSRC, name), "rb") as f:
                 h.update(f.read())
-    with open(os.path.join(ROOT, "include", "mgmol_b200.h"), "rb") as f:
-        h.update(f.read())
+    # the C ABI header for every unit; the C++ headers for the unit that
+    # instantiates their templates
+    incs = ["mgmol_b200.h"]
+    if os.path.basename(src) == "poisson.cu":
+        incs += ["mgmol_b200.hpp", "mgmol_b200_poisson.hpp"]
+    for name in incs:
+        with open(os.path.join(ROOT, "include", name), "rb") as f:
+            h.update(f.read())
     return h.hexdigest()
 
 
