@@ -26,28 +26,40 @@ def main():
     names = [p.split("\n", 1)[0].strip() for p in parts]
     dem = subprocess.run(["c++filt"], input="\n".join(names), capture_output=True,
                          text=True).stdout.splitlines()
+    # registers / static shared memory / local-memory stack per kernel
+    res = subprocess.run(["cuobjdump", "--dump-resource-usage", LIB], capture_output=True,
+                         text=True).stdout
+    usage = {}
+    for m in re.finditer(r"Function (\S+):\s*\n\s*REG:(\d+) STACK:(\d+) SHARED:(\d+) LOCAL:(\d+)", res):
+        usage[m.group(1)] = tuple(int(m.group(i)) for i in (2, 3, 4, 5))
     fam = collections.OrderedDict()
-    for name, body in zip(dem, parts):
+    famres = collections.OrderedDict()
+    for raw, name, body in zip(names, dem, parts):
         base = re.sub(r"^void\s+", "", name)
         base = re.sub(r"[<(].*", "", base).replace("mgb::", "")
         if base.startswith("(anonymous namespace)::"):
             base = base[len("(anonymous namespace)::"):]
         counts = [len(re.findall(pat, body)) for _, pat in COLS]
         fam.setdefault(base, []).append(counts)
+        famres.setdefault(base, []).append(usage.get(raw, (0, 0, 0, 0)))
     print("# SASS make-up of the kernels in `mgmol_b200/libmgmol_b200.so` (sm_100a)\n")
     print("Produced by `python tools/sass_evidence.py` from `cuobjdump -sass` (no GPU needed). One row per "
           "kernel family; `n` = template instantiations; every other cell = min–max count of that "
           "instruction over the instantiations. UTMALDG/UTMASTG = TMA tensor loads/stores "
           "(`cp.async.bulk.tensor`), SYNCS = mbarrier operations, DMMA = FP64 tensor MMA, "
           "HMMA…TF32 = TF32 tensor MMA (`mma.sync.m16n8k8.tf32`, the 3×TF32 float contractions), "
-          "LDGSTS = `cp.async`.\n")
-    print("| kernel | n | " + " | ".join(c for c, _ in COLS) + " |")
-    print("|---|---|" + "---|" * len(COLS))
+          "LDGSTS = `cp.async`; regs / stack (local memory, i.e. spills when non-zero) / static shared "
+          "memory from `cuobjdump --dump-resource-usage` (the TMA rings are dynamic shared memory and do "
+          "not show here).\n")
+    print("| kernel | n | " + " | ".join(c for c, _ in COLS) + " | regs | stack B | static smem B |")
+    print("|---|---|" + "---|" * (len(COLS) + 3))
 
     def rng(v):
         return str(min(v)) if min(v) == max(v) else "%d–%d" % (min(v), max(v))
     for base, rows in sorted(fam.items(), key=lambda kv: kv[0]):
         cells = [rng([r[i] for r in rows]) for i in range(len(COLS))]
+        rr = famres[base]
+        cells += [rng([r[0] for r in rr]), rng([r[1] + r[3] for r in rr]), rng([r[2] for r in rr])]
         print("| `%s` | %d | %s |" % (base, len(rows), " | ".join(cells)))
     tot = len(parts)
     print("\n%d kernels in all.\n" % tot)
