@@ -3,6 +3,8 @@
 // control flow of pb::SolverLap / pb::Mgm / pb::Vcycle and PCGSolver over this
 // library's own grid operations with one function; this file instantiates them
 // on the device field and gives them a plain-C face.
+#include <cmath>
+
 #include "common.cuh"
 #include "mgmol_b200_poisson.hpp"
 
@@ -68,7 +70,21 @@ extern "C" int mgb_poisson_solve(int solver, int lap_type, int dtype, const mgb_
     for (int d = 0; d < 3; d++)
     {
         gdim[d] = (unsigned)grid->gdim[d];
-        ll[d]   = grid->h[d] * grid->gdim[d];
+        // the lattice length whose quotient by gdim is exactly the caller's h
+        // (the solver derives its coefficients from ll / gdim)
+        const double n = (double)grid->gdim[d], h = grid->h[d];
+        double cand[5] = { h * n, 0., 0., 0., 0. };
+        cand[1]        = std::nextafter(cand[0], 0.);
+        cand[2]        = std::nextafter(cand[0], 2. * cand[0]);
+        cand[3]        = std::nextafter(cand[1], 0.);
+        cand[4]        = std::nextafter(cand[2], 2. * cand[0]);
+        ll[d]          = cand[0];
+        for (int k = 0; k < 5; k++)
+            if (cand[k] / n == h)
+            {
+                ll[d] = cand[k];
+                break;
+            }
     }
     const mgmol_b200::Grid g(gdim, ll, (short)grid->ghosts, grid->bc, grid->nproc, grid->coord);
     if (dtype == MGB_F64)
