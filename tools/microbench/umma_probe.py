@@ -53,9 +53,9 @@ def main():
         for K in (32, 64, 512):
             a = rng.standard_normal((128, K)).astype(np.float32)
             b = rng.standard_normal((n, K)).astype(np.float32)
-            for name, split, aa, bb, bar in (("tf32_exact_operands", 0, tf32_exact(a), tf32_exact(b), 2e-6),
+            for name, split, aa, bb, bar in (("tf32_exact_operands", 0, tf32_exact(a), tf32_exact(b), 1e-5),
                                              ("one_tf32_product", 0, a, b, 5e-3),
-                                             ("3xtf32", 1, a, b, 3e-6)):
+                                             ("3xtf32", 1, a, b, 1e-5)):
                 da, db = torch.from_numpy(aa).cuda(), torch.from_numpy(bb).cuda()
                 dc = torch.full((128, n), float("nan"), dtype=torch.float32, device="cuda")
                 rc = L.umma_tf32_probe(da.data_ptr(), db.data_ptr(), dc.data_ptr(), n, K, split)
