@@ -43,6 +43,71 @@
 #undef T
 #undef FN
 
+int orc_lap_constants(int lap_type, const double h[3], double out[3]);
+
+/* ---- Poisson solvers of the Hartree potential ----------- */
+#define ORC_POISSON_PART 1
+#define T double
+#define FN(name) ORC_CAT(name, _f64)
+#include "mgmol_oracle_poisson.inc"
+#undef T
+#undef FN
+#define T float
+#define FN(name) ORC_CAT(name, _f32)
+#include "mgmol_oracle_poisson.inc"
+#undef T
+#undef FN
+#undef ORC_POISSON_PART
+
+/* PCGSolver::preconSolve (PCGSolver.cc:112-162) in POISSONPRECONDTYPE = float:
+ * the solver's operator on level 0, Laph2 below; max(4, nu1 + nu2) sweeps on the
+ * coarsest level; the work array of the last sweep is what gets restricted; the
+ * trailing boundary trade under the condition exactly as written at :161. */
+static void orc_pcg_precon(int lap_type, pfield_f32* v, const pfield_f32* f, int level,
+    int nlevels, int ldims[][3], int nu1, int nu2, const double ll[3], const int bc[3])
+{
+    const int last     = level == nlevels;
+    const int ncycl    = last ? (4 > nu1 + nu2 ? 4 : nu1 + nu2) : nu1;
+    const int lt       = level == 0 ? lap_type : 1;
+    const double scale = pf_scale_f32(lt, v);
+    pfield_f32 work    = pf_new_f32(v->dims, v->g, ll, 0);
+    for (int it = 0; it < ncycl; it++)
+        pf_jacobi_f32(lt, v, f, &work, scale, bc);
+    if (!last)
+    {
+        pfield_f32 rcoarse = pf_new_f32(ldims[level + 1], v->g, ll, 0);
+        pfield_f32 newv    = pf_new_f32(ldims[level + 1], v->g, ll, 0);
+        pf_trade_f32(&work, bc);
+        orc_restrict3D_f32(work.dims, work.g, work.u, rcoarse.u, 1);
+        rcoarse.upd = 0;
+        pf_zero_f32(&newv);
+        orc_pcg_precon(lap_type, &newv, &rcoarse, level + 1, nlevels, ldims, nu1, nu2, ll, bc);
+        pf_trade_f32(&newv, bc);
+        orc_extend3D_f32(work.dims, work.g, newv.u, work.u, 1);
+        work.upd = 0;
+        pf_axpy_f32(-1., &work, v);
+        for (int it = 0; it < nu2; it++)
+            pf_jacobi_f32(lt, v, f, &work, scale, bc);
+        if (bc[0] != 1 || bc[2] != 1) pf_trade_f32(v, bc);
+        pf_free_f32(&rcoarse);
+        pf_free_f32(&newv);
+    }
+    pf_free_f32(&work);
+}
+
+#define ORC_POISSON_PART 2
+#define T double
+#define FN(name) ORC_CAT(name, _f64)
+#include "mgmol_oracle_poisson.inc"
+#undef T
+#undef FN
+#define T float
+#define FN(name) ORC_CAT(name, _f32)
+#include "mgmol_oracle_poisson.inc"
+#undef T
+#undef FN
+#undef ORC_POISSON_PART
+
 /* ---- operator constants -------------------------------------------------- */
 
 /* diagEl / invDiagEl / jacobiFactor of the Lap family:

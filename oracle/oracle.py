@@ -369,6 +369,36 @@ class Port:
             ctypes.c_double(inv_diag), mg_levels, ctypes.c_double(vmax),
             ctypes.c_double(small_eig))
 
+    # -- Poisson solvers of the Hartree potential ----------------
+    def poisson_solve(self, lap_type, vh, rho, ll, bc=(1, 1, 1), nu1=2, nu2=2, max_sweeps=10,
+                      tol=1e-16, max_nlevels=10):
+        """orc_poisson_mg: SolverLap::solve = Mgm + average0.  Returns (solution,
+        converged, (nb_sweeps, final_residual, final_relative_residual,
+        residual_reduction))."""
+        vh = np.array(vh, order="C")
+        rho = np.ascontiguousarray(rho, dtype=vh.dtype)
+        stats = (ctypes.c_double * 4)()
+        conv = getattr(self.lib, "orc_poisson_mg" + _sfx(vh.dtype))(
+            lap_type, _c_int3(*vh.shape), _c_dbl3(*ll), _c_int3(*bc), _ptr(vh), _ptr(rho), nu1,
+            nu2, max_sweeps, ctypes.c_double(tol), max_nlevels, stats)
+        if conv < 0:
+            raise ValueError("operator %d is not restated" % lap_type)
+        return vh, bool(conv), tuple(stats)
+
+    def pcg_solve(self, lap_type, vh, rho, ll, bc=(1, 1, 1), nu1=2, nu2=2, max_sweeps=10,
+                  tol=1e-16, max_nlevels=10):
+        """orc_poisson_pcg: PCGSolver::solve.  Returns (solution, converged,
+        (final_residual, residual_reduction))."""
+        vh = np.array(vh, order="C")
+        rho = np.ascontiguousarray(rho, dtype=vh.dtype)
+        stats = (ctypes.c_double * 2)()
+        conv = getattr(self.lib, "orc_poisson_pcg" + _sfx(vh.dtype))(
+            lap_type, _c_int3(*vh.shape), _c_dbl3(*ll), _c_int3(*bc), _ptr(vh), _ptr(rho), nu1,
+            nu2, max_sweeps, ctypes.c_double(tol), max_nlevels, stats)
+        if conv < 0:
+            raise ValueError("operator %d is not restated" % lap_type)
+        return vh, bool(conv), tuple(stats)
+
     # -- contractions ---------------------------------------------------------
     def gemm_tn(self, a, b, alpha=1.0):
         """alpha * A^T B for blocks a (m, npt), b (n, npt) -> (m, n) double,

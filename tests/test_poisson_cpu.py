@@ -61,6 +61,29 @@ def test_golden_is_what_the_compiled_reference_returns(gpois):
                 assert conv == bool(gpois[key(tag, lt, dt) + "_stats"][0])
 
 
+@pytest.mark.parametrize("lt", LAPS)
+@pytest.mark.parametrize("dt", DTYPES, ids=["f64", "f32"])
+def test_c_restatement_against_golden(port, gpois, lt, dt):
+    """oracle/mgmol_oracle_poisson.inc (orc_poisson_mg, orc_poisson_pcg) against
+    the compiled reference's outputs: the multigrid solver to the bit, the
+    conjugate gradient within the reordering of its dot products."""
+    for tag, dims, ll, bc, kw in CASES:
+        vh, conv, st = port.poisson_solve(lt, guess(dims, dt), charge(dims, bc, dt), ll, bc,
+                                          **dict(DEFAULTS, **kw))
+        ref, rst = gpois[key(tag, lt, dt)], gpois[key(tag, lt, dt) + "_stats"]
+        assert np.array_equal(vh, ref), (tag, lt, dt)
+        assert conv == bool(rst[0]) and st[0] == rst[1]
+        assert st[1] == pytest.approx(rst[2], rel=1e-12)
+    for tag, dims, ll, bc, kw in PCG_CASES:
+        vh, conv, st = port.pcg_solve(lt, guess(dims, dt), charge(dims, bc, dt), ll, bc,
+                                      **dict(DEFAULTS, **kw))
+        ref, rst = gpois[key(tag, lt, dt)], gpois[key(tag, lt, dt) + "_stats"]
+        eps = 1e-11 if dt == np.float64 else 1e-6
+        assert np.abs(vh.astype(np.float64) - ref).max() <= eps * np.abs(ref).max(), (tag, lt, dt)
+        assert conv == bool(rst[0])
+        assert st[0] == pytest.approx(rst[1], rel=1e-6)
+
+
 def test_converges_to_the_discrete_solution(port):
     """A V(2,2) cycle contracts the residual by about an order of magnitude per
     sweep; the converged flag, the sweep count and the analytic solution of a
