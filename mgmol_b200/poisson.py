@@ -13,6 +13,8 @@ level, src/pb/Vcycle.h:69-143) are not part of it.
 The solver works on "fields": objects with the GridFuncVector interface of
 host.py.  The default is the device class; the CPU tests drive this very
 control flow with a numpy stand-in to pin it against the compiled reference."""
+import math
+
 import torch
 
 from .host import GridFuncVector, Lap
@@ -302,3 +304,82 @@ class PoissonPCG:
             gf_phi.add_scalar(-gf_phi.get_average())
         gf_phi.getValues(vh.reshape(shape1))
         return converged
+
+
+class Hartree:
+    """Hartree<T> (src/Hartree.h:18-46, src/Hartree.cc:27-112) with the state of
+    its Poisson base (src/Poisson.h:31-89): the Hartree potential vh, kept between
+    calls as the next initial guess, and the integrals of vh against the charges.
+    `solve(rho, rhoc)`: rhs = 4 pi (rho - rhoc) in the solver's precision, then the
+    Poisson solver; boundary conditions 0 / 1 (no multipole boundary values)."""
+
+    def __init__(self, grid, lap_type, dtype=torch.float64, field=None, pcg=False,
+                 rho_dtype=torch.float64, precond_dtype=None):
+        self.field_ = _bind(field, dtype)
+        self.rfield_ = _bind(field, rho_dtype)
+        if pcg:
+            self.poisson_solver_ = PoissonPCG(grid, lap_type, dtype, field, precond_dtype)
+        else:
+            self.poisson_solver_ = PoissonMG(grid, lap_type, dtype, field)
+        self.grid_ = self.poisson_solver_.grid_
+        zero = self.field_(self.grid_)
+        zero.resetData()
+        self.vh_ = zero.values()
+        self.Int_vhrho_ = self.Int_vhrhoc_ = self.Int_vhrho_old_ = 0.
+
+    def setup(self, nu1, nu2, max_sweeps, tol, max_nlevels, gather_coarse_level=True):
+        self.poisson_solver_.setup(nu1, nu2, max_sweeps, tol, max_nlevels)
+
+    def vh(self):
+        return self.vh_
+
+    def set_vh(self, vh):
+        f = self.field_(self.grid_)
+        f.assign(vh.reshape((1,) + tuple(self.grid_.shape())))
+        self.vh_ = f.values()
+
+    def resetVh(self):
+        f = self.field_(self.grid_)
+        f.resetData()
+        self.vh_ = f.values()
+
+    def IntVhRho(self):
+        return self.Int_vhrho_
+
+    def IntVhRhoc(self):
+        return self.Int_vhrhoc_
+
+    def IntVhRho_old(self):
+        return self.Int_vhrho_old_
+
+    def getResidualReduction(self):
+        return self.poisson_solver_.getResidualReduction()
+
+    def getFinalResidual(self):
+        return self.poisson_solver_.getFinalResidual()
+
+    def _vh_dot(self, charge):
+        """vel * vh_->gdot(charge), the charge converted to vh's precision the
+        way the mixed-type gdot reads both operands as double."""
+        a, b = self.field_(self.grid_), self.field_(self.grid_)
+        a.assign(self.vh_)
+        b.assign(charge)
+        return self.grid_.vel() * a.gdot(b)
+
+    def solve(self, rho, rhoc):
+        """rho, rhoc: no-ghost fields (nx, ny, nz) of the charge precision."""
+        shape1 = (1,) + tuple(self.grid_.shape())
+        rho1, rhoc1 = rho.reshape(shape1), rhoc.reshape(shape1)
+        self.Int_vhrho_old_ = self._vh_dot(rho1)
+        work_rho, gf_rhoc = self.rfield_(self.grid_), self.rfield_(self.grid_)
+        work_rho.assign(rho1)
+        gf_rhoc.assign(rhoc1)
+        work_rho.axpy(-1.0, gf_rhoc)                 # work_rho -= rhoc
+        rhs = self.field_(self.grid_)
+        rhs.assign(work_rho.values())                # GridFunc<POTDTYPE> rhs(work_rho)
+        rhs.scal(4. * math.pi)                       # Hartree units
+        conv = self.poisson_solver_.solve(self.vh_.reshape(tuple(self.grid_.shape())),
+                                          rhs.values().reshape(tuple(self.grid_.shape())))
+        self.Int_vhrho_ = self._vh_dot(rho1)
+        self.Int_vhrhoc_ = self._vh_dot(rhoc1)
+        return conv

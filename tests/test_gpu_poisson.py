@@ -148,3 +148,32 @@ def test_poisson_c_abi_entry(gpois, solver, lt, dt):
     p = ctypes.c_void_p(z.data_ptr())
     assert lib().mgb_poisson_solve(0, 3, 1, g3.ref(), p, p, 2, 2, 10, 1e-16, 10, None) != 0
     assert lib().mgb_poisson_solve(2, 0, 1, g3.ref(), p, p, 2, 2, 10, 1e-16, 10, None) != 0
+
+
+@pytest.mark.parametrize("pcg,dt", [(False, np.float64), (False, np.float32), (True, np.float64)],
+                         ids=["mg-f64", "mg-f32", "pcg-f64"])
+def test_hartree_device_equals_oracle_control_flow(port, pcg, dt):
+    """Hartree<T>::solve (src/Hartree.cc:27-112) on device fields and on oracle
+    fields: two consecutive calls (the second starts from the first vh), the
+    potential and the three integrals."""
+    from mgmol_b200.host import Grid
+    from mgmol_b200.poisson import Hartree
+    tag, dims, ll, bc, _ = CASES[2]
+    rho = charge(dims, bc, np.float64)
+    rhoc = 0.3 * charge(dims, bc, np.float64, seed=11)
+    dev_h = Hartree(Grid(dims, ll, 1, bc), 0, TDT[dt], pcg=pcg)
+    cpu_h = Hartree(Grid(dims, ll, 1, bc), 0, dt, field=field_factory(port), pcg=pcg,
+                    rho_dtype=np.float64, precond_dtype=np.float32)
+    drho, drhoc = torch.from_numpy(rho).cuda(), torch.from_numpy(rhoc).cuda()
+    eps = (1e-10 if pcg else 1e-13) if dt == np.float64 else 2e-6
+    for _ in range(2):
+        dev_h.setup(2, 2, 4, 1e-16, 10)
+        cpu_h.setup(2, 2, 4, 1e-16, 10)
+        dev_h.solve(drho, drhoc)
+        cpu_h.solve(rho, rhoc)
+        got = dev_h.vh().cpu().numpy().reshape(dims).astype(np.float64)
+        want = cpu_h.vh().reshape(dims).astype(np.float64)
+        assert np.abs(got - want).max() <= eps * np.abs(want).max()
+        for a, b in ((dev_h.IntVhRho(), cpu_h.IntVhRho()), (dev_h.IntVhRhoc(), cpu_h.IntVhRhoc()),
+                     (dev_h.IntVhRho_old(), cpu_h.IntVhRho_old())):
+            assert a == pytest.approx(b, rel=1e-6, abs=1e-12)

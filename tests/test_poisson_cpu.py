@@ -142,6 +142,48 @@ def test_pcg_zero_right_hand_side_returns_at_once(port):
     assert solver.solve(vh, np.zeros(dims)) and not vh.any()
 
 
+def _gdot(a, b, bc):
+    sl = tuple(slice(1 if c != 1 else 0, None) for c in bc)
+    return float((a[sl].astype(np.float64) * b[sl].astype(np.float64)).sum())
+
+
+@pytest.mark.skipif(not Ref.available(), reason="compiled reference not present")
+@pytest.mark.parametrize("pcg", [False, True], ids=["mg", "pcg"])
+@pytest.mark.parametrize("dt", DTYPES, ids=["f64", "f32"])
+def test_hartree_sequence(port, pcg, dt):
+    """Hartree<T>::solve (src/Hartree.cc:27-112): rhs = 4 pi (rho - rhoc) in the
+    solver's precision, the solver started from the previous vh, and the three
+    integrals -- against the same steps done with the compiled reference
+    solver, over two consecutive calls."""
+    import math
+    from mgmol_b200.host import Grid
+    from mgmol_b200.poisson import Hartree
+    ref = Ref()
+    for (tag, dims, ll, bc, _), lt in ((CASES[0], 0), (CASES[1], 2), (CASES[2], 1)):
+        rho = charge(dims, bc, np.float64)
+        rhoc = 0.3 * charge(dims, bc, np.float64, seed=11)
+        har = Hartree(Grid(dims, ll, 1, bc), lt, dt, field=field_factory(port), pcg=pcg,
+                      rho_dtype=np.float64, precond_dtype=np.float32)
+        har.setup(2, 2, 5, 1e-16, 10)
+        vel = float(np.prod([a / n for a, n in zip(ll, dims)]))
+        vref = np.zeros(dims, dt)
+        for call in range(2):
+            old = vel * _gdot(vref, rho.astype(dt), bc)
+            har.solve(rho, rhoc)
+            rhs = ((rho - rhoc).astype(dt).astype(np.float64) * (4 * math.pi)).astype(dt)
+            solve = ref.pcg_solve if pcg else ref.poisson_solve
+            vref, _, st = solve(lt, vref, rhs, ll, bc, max_sweeps=5)
+            eps = (1e-11 if pcg else 1e-14) if dt == np.float64 else 1e-6
+            got = har.vh().reshape(dims).astype(np.float64)
+            assert np.abs(got - vref).max() <= eps * np.abs(vref).max(), (tag, call)
+            assert har.IntVhRho_old() == pytest.approx(old, rel=1e-9, abs=1e-300)
+            assert har.IntVhRho() == pytest.approx(vel * _gdot(vref, rho.astype(dt), bc), rel=1e-9)
+            assert har.IntVhRhoc() == pytest.approx(vel * _gdot(vref, rhoc.astype(dt), bc), rel=1e-9)
+            assert har.getFinalResidual() == pytest.approx(st[-3] if not pcg else st[0], rel=1e-4)
+        har.resetVh()
+        assert not har.vh().any()
+
+
 def test_refuses_what_is_not_built():
     from mgmol_b200.host import Grid
     from mgmol_b200.poisson import PoissonMG
