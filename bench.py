@@ -26,27 +26,79 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: (local dims, lattice of the local box, orbitals, lap_type, description)
-    "h2o64": ((128, 128, 128), 23.4884, 256, 2,
-              "examples/H2O_64 H psi: 128^3 grid x 256 orbitals, FDtype=4th"),
-    "synth256": ((256, 256, 256), 46.9768, 64, 0,
-                 "synthetic sweep: 256^3 grid, Mehrstellen"),
-    "sih4": ((40, 40, 40), 14.0, 4, 0, "examples/SiH4: 40^3 grid x 4 orbitals, Mehrstellen"),
+    # The N = 1 headline: BASELINE.json's metric is not quoted on one configuration, so the
+    # largest configuration of `configs` that fits one GPU: configs[4], the synthetic sweep,
+    # 256^3 grid x 512 orbitals, ORBDTYPE double.  At N GPUs the SAME global 256^3 grid is
+    # split over the ranks the way PEenv::geom splits it and the orbital count grows with N
+    # (512 N: the sweep's 512 / 1024 / 2048 / 4096 cells at 1 / 2 / 4 / 8 GPUs), so the work
+    # per GPU is fixed (weak scaling).
+    "synth256": {"grid": (256, 256, 256), "fixed": "global", "cell": 46.9768, "orbitals": 512,
+                 "orbitals_scale": True, "lap": 0,
+                 "desc": "synthetic sweep (configs[4]): 256^3 global grid, 512 orbitals per GPU"},
+    # examples/H2O_64 (configs[1]): 128^3 x 256, FDtype=4th; at N GPUs every rank owns a
+    # 128^3 box of a larger domain
+    "h2o64": {"grid": (128, 128, 128), "fixed": "local", "cell": 23.4884, "orbitals": 256,
+              "orbitals_scale": False, "lap": 2,
+              "desc": "examples/H2O_64 H psi: 128^3 grid per GPU x 256 orbitals, FDtype=4th"},
+    "sih4": {"grid": (40, 40, 40), "fixed": "local", "cell": 14.0, "orbitals": 4,
+             "orbitals_scale": False, "lap": 0,
+             "desc": "examples/SiH4: 40^3 grid x 4 orbitals, Mehrstellen"},
 }
+DEFAULT_WORKLOAD = "synth256"
 
 
-def measured_traffic(kernel_prefix, workload, dtype, lap_type):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant
-    kernel, from the committed ncu --set full capture (profiles/); None when no
-    capture matches this configuration."""
+def layout(args, world):
+    """Decomposition and sizes of the workload at `world` GPUs -- shared by both arms so
+    that their `config` dicts are identical."""
+    from mgmol_b200.parallel import geom
+    w = WORKLOADS[args.workload]
+    if args.decomp and args.decomp != "auto":
+        nproc = tuple(int(x) for x in args.decomp.lower().split("x"))
+        assert len(nproc) == 3 and nproc[0] * nproc[1] * nproc[2] == world, "--decomp PxQxR"
+        how = "requested"
+    else:
+        # PEenv::geom (src/pb/PEenv.cc:335-) on the grid the reference would be given
+        nproc = geom(w["grid"][0], w["grid"][1], w["grid"][2], world) if world > 1 else (1, 1, 1)
+        how = "PEenv::geom"
+        if nproc is None:
+            nproc, how = (world, 1, 1), "x slabs (PEenv::geom refuses this mesh)"
+    if args.strong or w["fixed"] == "global":
+        gdims = w["grid"]
+        cell = (w["cell"],) * 3
+    else:
+        gdims = tuple(n * p for n, p in zip(w["grid"], nproc))
+        cell = tuple(w["cell"] * p for p in nproc)
+    for n, p in zip(gdims, nproc):
+        assert n % p == 0 and (n // p) % 4 == 0, "local dims must divide by 4 (two multigrid levels)"
+    ldims = tuple(n // p for n, p in zip(gdims, nproc))
+    norb = args.orbitals or w["orbitals"] * (world if (w["orbitals_scale"] and not args.strong) else 1)
+    lap_type = w["lap"] if args.lap is None else args.lap
+    S = 8 if args.dtype == "f64" else 4
+    cfg = {"workload": w["desc"], "lap_type": lap_type, "global_grid": list(gdims),
+           "grid_per_gpu": list(ldims), "orbitals": norb,
+           "decomposition": "%dx%dx%d" % nproc, "decomposition_from": how,
+           "l2": "inputs larger than L2 (%.1f GB per GPU per step)"
+                 % (2.0 * S * np.prod(ldims) * norb / 1e9),
+           "tolerance": "max |err| / per-orbital max norm <= 1e-12 (f64), 1e-5 (f32); tests also "
+                        "report the elementwise relative error on entries above 1e-3 of the max"}
+    return {"nproc": nproc, "gdims": gdims, "ldims": ldims, "cell": cell, "norb": norb,
+            "lap_type": lap_type, "S": S, "config": cfg}
+
+
+def measured_traffic(kernel_sig, ldims, norb, dtype, lap_type):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the
+    committed ncu --set full captures (profiles/hpsi_traffic.json, regenerated from the kept
+    .ncu-rep files by tools/traffic_table.py), scaled by orbital count when the capture used
+    fewer orbitals of the same box.  None when no capture matches the launched kernel."""
     p = os.path.join(ROOT, "profiles", "hpsi_traffic.json")
     if not os.path.exists(p):
-        return None
-    d = json.load(open(p))
-    if d.get("workload") == "%s %s lap%d" % (workload, dtype, 4 if lap_type == 2 else 0) \
-            and d.get("kernel", "").startswith(kernel_prefix):
-        return d.get("traffic_bytes_per_launch")
-    return None
+        return None, "no capture"
+    for e in json.load(open(p)).get("captures", []):
+        if (e.get("grid") == list(ldims) and e.get("dtype") == dtype
+                and e.get("lap_type") == lap_type and e.get("kernel") == kernel_sig):
+            return (e["dram_bytes_per_launch"] * norb / e["orbitals"],
+                    "ncu capture %s (%d orbitals, scaled by orbital count)" % (e["report"], e["orbitals"]))
+    return None, "no capture of %s on this box shape" % kernel_sig
 
 
 def measured_peaks():
@@ -153,16 +205,23 @@ def _cpu_worker(args):
     return time.perf_counter() - t0
 
 
+def _cpu_split(dims, cores, min_planes=4, mult=1):
+    """x slabs over P single-thread ranks like a P x 1 x 1 PEenv."""
+    P = 1
+    while (P * 2 <= cores and dims[0] % (P * 2) == 0 and dims[0] // (P * 2) >= min_planes
+           and (dims[0] // (P * 2)) % mult == 0):
+        P *= 2
+    return P
+
+
 def cpu_hpsi_rate(lap_type, dims, ll, dt, budget_s=12.0):
-    """grid-pt*orbital updates/s of the CPU reference on all host cores."""
+    """grid-pt*orbital updates/s of the CPU reference on all host cores, on a bounded
+    SAMPLE of the workload: the workload's own box, as many orbitals as the budget allows."""
     import multiprocessing as mp
     from oracle.oracle import Ref
     kind = "reference" if Ref.available() else "port"
     cores = os.cpu_count() or 1
-    # split the box along x over P workers like a px x 1 x 1 PEenv
-    P = 1
-    while P * 2 <= cores and dims[0] % (P * 2) == 0 and dims[0] // (P * 2) >= 4:
-        P *= 2
+    P = _cpu_split(dims, cores)
     sub = (dims[0] // P, dims[1], dims[2])
     subll = (ll[0] / P, ll[1], ll[2])
     ctx = mp.get_context("spawn")
@@ -171,8 +230,10 @@ def cpu_hpsi_rate(lap_type, dims, ll, dt, budget_s=12.0):
         nfunc = int(max(1, min(64, budget_s / max(t1, 1e-4) / 2)))
         t = max(pool.map(_cpu_worker, [(kind, lap_type, sub, subll, nfunc, dt, 1)] * P))
     updates = float(np.prod(dims)) * nfunc
-    sample = ("%s H psi (Hamiltonian::applyLocal sequence), %dx%dx%d box split over %d "
-              "single-thread ranks, %d orbitals" % (kind, dims[0], dims[1], dims[2], P, nfunc))
+    sample = ("SAMPLE: %s H psi (Hamiltonian::applyLocal sequence) on the %dx%dx%d box split over "
+              "%d single-thread ranks (x slabs, halo = local wrap), %d orbitals of the workload's; "
+              "rate extrapolates to the full orbital count"
+              % (kind, dims[0], dims[1], dims[2], P, nfunc))
     return updates / t, P, kind, sample
 
 
@@ -209,46 +270,50 @@ def _cpu_iter_worker(args):
 
 
 def cpu_iteration(lap_type, dims, ll, dt, norb):
-    """Seconds the CPU reference needs for the same pieces on the same box with
-    all host cores: P single-thread ranks, each on a 1/P x-slab with all
-    orbitals (no communication counted -- favourable to the CPU)."""
+    """Seconds the CPU reference needs for the same pieces on the same box with all host
+    cores: P single-thread ranks, each on a 1/P x-slab (no communication counted --
+    favourable to the CPU).  Bounded: at most `ns` orbitals are run (memory and time); the
+    grid-sized pieces scale with N / ns, the contractions with (N / ns)^2."""
     import multiprocessing as mp
     from oracle.oracle import Ref
     kind = "reference" if Ref.available() else "port"
     cores = os.cpu_count() or 1
-    P = 1
-    # x slabs of >= 8 planes, divisible by 4 (two multigrid levels)
-    while (P * 2 <= cores and dims[0] % (P * 2) == 0 and (dims[0] // (P * 2)) % 4 == 0
-           and dims[0] // (P * 2) >= 8):
-        P *= 2
+    P = _cpu_split(dims, cores, min_planes=8, mult=4)  # two multigrid levels per slab
+    ns = norb
+    while ns > 16 and float(np.prod(dims)) * ns > 6e8:  # ~ 256 orbitals at 128^3
+        ns //= 2
     try:
         import psutil
         avail = psutil.virtual_memory().available
-        per = 12.0 * np.prod(dims) / P * norb * np.dtype(dt).itemsize
-        while P > 1 and per * P > 0.5 * avail:
-            P //= 2
+        while ns > 8 and 12.0 * np.prod(dims) * ns * np.dtype(dt).itemsize > 0.4 * avail:
+            ns //= 2
     except Exception:
         pass
     sub = (dims[0] // P, dims[1], dims[2])
     subll = (ll[0] / P, ll[1], ll[2])
     ctx = mp.get_context("spawn")
     with ctx.Pool(P) as pool:
-        res = pool.map(_cpu_iter_worker, [(kind, lap_type, sub, subll, norb, dt)] * P)
+        res = pool.map(_cpu_iter_worker, [(kind, lap_type, sub, subll, ns, dt)] * P)
     pieces = {k: max(r[k] for r in res) for k in res[0]}
-    return {"seconds": sum(pieces.values()), "pieces_s": pieces, "cores": P, "kind": kind,
-            "sample": "%s kernels, %dx%dx%d box as %d single-thread ranks (x slabs), all %d "
-                      "orbitals, one pass, no communication counted"
-                      % (kind, dims[0], dims[1], dims[2], P, norb)}
+    f1, f2 = norb / ns, (norb / ns) ** 2
+    scaled = {"hpsi": pieces["hpsi"] * f1, "precond_mg": pieces["precond_mg"] * f1,
+              "phiT_H_phi": pieces["phiT_H_phi"] * f2, "gram": pieces["gram"] * f2,
+              "phi_M": pieces["phi_M"] * f2}
+    return {"seconds": sum(scaled.values()), "pieces_s": scaled, "cores": P, "kind": kind,
+            "sample": "SAMPLE: %s kernels, %dx%dx%d box as %d single-thread ranks (x slabs), %d of "
+                      "the %d orbitals run once; grid-sized pieces scaled by N/ns, contractions by "
+                      "(N/ns)^2; no communication counted"
+                      % (kind, dims[0], dims[1], dims[2], P, ns, norb)}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
     if rank != 0:
         return
-    dims, cell, norb, lap_default, desc = WORKLOADS[args.workload]
-    lap_type = lap_default if args.lap is None else args.lap
+    L = layout(args, max(world, args.gpus))
+    dims, ll, norb, lap_type = L["gdims"], L["cell"], L["norb"], L["lap_type"]
     dt = np.float64 if args.dtype == "f64" else np.float32
-    ll = (cell,) * 3
     vals = []
     info = None
     for _ in range(args.warmup + args.steps):
@@ -264,11 +329,10 @@ def run_reference(args):
         # a step is a bounded sample: report the time one full step of the
         # workload takes at the sampled rate
         "ms_per_step": float(np.prod(dims)) * norb / value * 1e3,
-        "ms_per_step_basis": "whole workload at the sampled rate",
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": args.dtype, "data": "synthetic",
-        "config": {"workload": desc, "lap_type": lap_type, "grid": list(dims),
-                   "orbitals": norb},
+        "ms_per_step_basis": "whole workload at the rate of the SAMPLE (see cpu_baseline.sample)",
+        "higher_is_better": True, "scaling": "strong" if args.strong else "weak",
+        "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "config": L["config"],
         "cpu_baseline": {"value": value, "unit": "updates/s", "cores": info[0],
                          "kind": info[1], "sample": info[2]},
         "e2e": {"value": value, "unit": "updates/s", "h2d_bytes_per_step": 0,
@@ -295,78 +359,118 @@ def _time_cuda(torch, fn, reps=5, warm=2):
     return float(np.median(ts))
 
 
-def measure_pieces(H, grid, phi, ham, lap_type, tdt, S, norb, npt, comm=None, hstep=None):
-    """The other three pieces of the path on the same orbital block (outside the
-    timed region of the headline metric): multigrid-preconditioned residual,
-    Gram, projected Hamiltonian, orbital mixing; each with the roofline that
-    bounds it.  FP64 tensor peak = cuBLAS DGEMM measured here (MEASURED_PEAKS
+def _tensor_roofline(fl, ms, peak, flops):
+    return {"bound": "tensor", "achieved": fl / (ms * 1e-3) / 1e12, "peak": peak,
+            "unit": "TFLOP/s", "frac": fl / (ms * 1e-3) / 1e12 / peak, "flops": flops}
+
+
+def fp64_tensor_peak(torch):
+    """FP64 tensor (DMMA) peak: large square cuBLAS DGEMM, best of 2 medians (MEASURED_PEAKS
     has no FP64 entry)."""
-    import torch
-    hbm, _ = measured_peaks()
-    out = {}
-    # FP64 tensor (DMMA) peak: large square cuBLAS DGEMM, best of 5
     m = 4096
     x = torch.rand((m, m), device="cuda", dtype=torch.float64)
     y = torch.rand((m, m), device="cuda", dtype=torch.float64)
     best = min(_time_cuda(torch, lambda: torch.matmul(x, y), reps=3, warm=1) for _ in range(2))
-    fp64_peak = 2.0 * m ** 3 / (best * 1e-3) / 1e12
     del x, y
+    return 2.0 * m ** 3 / (best * 1e-3) / 1e12
+
+
+class PrecondChunks:
+    """OrbitalsPreconditioning::precond_mg over a block in chunks of orbitals: the V-cycle's
+    resident float work blocks (about 4.6 x npt x chunk floats) must fit next to the orbital
+    blocks, so a 256^3 x 512 block is preconditioned 64 or 128 orbitals at a time."""
+
+    def __init__(self, H, grid, tdt, norb, lap_type, comm, free_bytes):
+        npt = grid.size()
+        chunk = norb
+        while chunk > 16 and chunk % 2 == 0 and 4.6 * 4 * npt * chunk > 0.7 * free_bytes:
+            chunk //= 2
+        self.chunk, self.norb, self.grid, self.H, self.tdt = chunk, norb, grid, H, tdt
+        proto = H.Orbitals.__new__(H.Orbitals)  # setup() only reads the grid and the count
+        proto.grid_, proto.numst_ = grid, chunk
+        self.pc = H.OrbitalsPreconditioning()
+        self.pc.setup(proto, 2, lap_type)
+        if comm is not None:
+            self.pc.set_comm(comm)
+        self.pc.gamma_ = 0.3
+
+    def __call__(self, res):
+        for j0 in range(0, self.norb - self.chunk + 1, self.chunk):
+            self.pc.precond_mg(self.H.Orbitals(self.grid, self.chunk, self.tdt,
+                                               res.psi()[j0:j0 + self.chunk]))
+
+    def last_mode(self):
+        return self.pc.last_mode()
+
+    def close(self):
+        self.pc.close()
+
+
+def measure_pieces(H, grid, phi, ham, lap_type, tdt, S, norb, npt, comm=None, hstep=None,
+                   fp64_peak=None):
+    """The other three pieces of the path on the same orbital block (outside the timed
+    region of the headline metric): multigrid-preconditioned residual, Gram, projected
+    Hamiltonian, orbital mixing; each with the roofline that bounds it.  Only two orbital
+    blocks exist (phi and H phi: 2 x 68.7 GB at 256^3 x 512 doubles), so products are written
+    over the H phi block and the V-cycle runs over it in chunks."""
+    import torch
+    hbm, _ = measured_peaks()
+    out = {}
     out["fp64_tensor_peak_tflops"] = {"value": fp64_peak,
                                       "how": "cuBLAS DGEMM 4096^3 via torch.matmul, measured in this run"}
     upd = float(npt) * norb
-    hphi = hstep() if hstep else ham.applyLocal(phi)
-    # multigrid-preconditioned residual (OrbitalsPreconditioning::precond_mg)
-    res = H.Orbitals(grid, norb, tdt)
-    res.psi().copy_(hphi.psi())
-    pc = H.OrbitalsPreconditioning()
-    pc.setup(res, 2, lap_type)
-    if comm is not None:
-        pc.set_comm(comm)
-    pc.gamma_ = 0.3
-    ms = _time_cuda(torch, lambda: pc.precond_mg(res))
+    hphi = hstep() if hstep else ham.applyLocal(phi, True)
+    free_b, _tot = torch.cuda.mem_get_info()
+    free_b += torch.cuda.memory_reserved() - torch.cuda.memory_allocated()
+    # multigrid-preconditioned residual (OrbitalsPreconditioning::precond_mg), on the H phi block
+    pc = PrecondChunks(H, grid, tdt, norb, lap_type, comm, free_b)
+    ms = _time_cuda(torch, lambda: pc(hphi), reps=3, warm=1)
     model = (74.0 + 2 * S) * upd  # SURVEY.md 8(d): streaming model of the V-cycle
     out["precond_mg"] = {"ms": ms, "updates_per_s": upd / (ms * 1e-3), "mg_levels": 2,
+                         "orbitals_per_call": pc.chunk,
                          "mode": {1: "literal", 2: "fused"}.get(pc.last_mode()),
                          "roofline": {"bound": "hbm", "achieved": model / (ms * 1e-3) / 1e9,
                                       "peak": hbm, "unit": "GB/s",
                                       "frac": model / (ms * 1e-3) / 1e9 / hbm,
                                       "model_bytes_per_update": 74.0 + 2 * S}}
+    hphi = hstep() if hstep else ham.applyLocal(phi, True)
     fl = float(norb) * norb * npt
-    ms = _time_cuda(torch, lambda: phi.computeGram(comm))
-    out["gram"] = {"ms": ms, "roofline": {"bound": "tensor", "achieved": fl / (ms * 1e-3) / 1e12,
-                                          "peak": fp64_peak, "unit": "TFLOP/s",
-                                          "frac": fl / (ms * 1e-3) / 1e12 / fp64_peak,
-                                          "flops": "N^2 K (syrk)"}}
-    ms = _time_cuda(torch, lambda: phi.computeLocalProduct(hphi, comm))
-    out["phiT_H_phi"] = {"ms": ms, "roofline": {"bound": "tensor", "achieved": 2 * fl / (ms * 1e-3) / 1e12,
-                                                "peak": fp64_peak, "unit": "TFLOP/s",
-                                                "frac": 2 * fl / (ms * 1e-3) / 1e12 / fp64_peak,
-                                                "flops": "2 N^2 K"}}
+    ms = _time_cuda(torch, lambda: phi.computeGram(comm), reps=3, warm=1)
+    out["gram"] = {"ms": ms, "roofline": _tensor_roofline(fl, ms, fp64_peak, "N^2 K (syrk)")}
+    ms = _time_cuda(torch, lambda: phi.computeLocalProduct(hphi, comm), reps=3, warm=1)
+    out["phiT_H_phi"] = {"ms": ms, "roofline": _tensor_roofline(2 * fl, ms, fp64_peak, "2 N^2 K")}
     M = torch.rand((norb, norb), device="cuda", dtype=torch.float64) - 0.5
-    prod = H.Orbitals(grid, norb, tdt)
-    ms = _time_cuda(torch, lambda: phi.multiplyByMatrix(M, prod))
-    out["phi_M"] = {"ms": ms, "roofline": {"bound": "tensor", "achieved": 2 * fl / (ms * 1e-3) / 1e12,
-                                           "peak": fp64_peak, "unit": "TFLOP/s",
-                                           "frac": 2 * fl / (ms * 1e-3) / 1e12 / fp64_peak,
-                                           "flops": "2 N^2 K"}}
+    prod = hphi  # the product overwrites the H phi block
+    ms = _time_cuda(torch, lambda: phi.multiplyByMatrix(M, prod), reps=3, warm=1)
+    out["phi_M"] = {"ms": ms, "roofline": _tensor_roofline(2 * fl, ms, fp64_peak, "2 N^2 K")}
+    # Mehrstellen: Phi^T B Phi (ExtendedGridOrbitals::computeMatB, called every SCF step,
+    # src/DFTsolver.cc:382)
+    if comm is None and lap_type in (0, 10) and hasattr(phi, "computeMatB"):
+        ms = _time_cuda(torch, lambda: phi.computeMatB(ham.lapOper(), work=prod), reps=3, warm=1)
+        out["matB"] = {"ms": ms, "roofline": _tensor_roofline(2 * fl, ms, fp64_peak, "2 N^2 K (+ B Phi pass)")}
 
     if comm is None:
-        # "next" rows (SURVEY 8f): residual assembly res = (B Phi) theta - H Phi in one
-        # contraction pass with a fused epilogue, and the density rho += sum_j (Phi X)_j phi_j
-        ms = _time_cuda(torch, lambda: H.computeResidualUsingHPhi(ham.lapOper(), phi, hphi, M, prod))
-        out["residual"] = {"ms": ms, "roofline": {"bound": "tensor",
-                                                  "achieved": 2 * fl / (ms * 1e-3) / 1e12,
-                                                  "peak": fp64_peak, "unit": "TFLOP/s",
-                                                  "frac": 2 * fl / (ms * 1e-3) / 1e12 / fp64_peak,
-                                                  "flops": "2 N^2 K"}}
+        # "next" rows (SURVEY 8f) on a sub-block of <= 128 orbitals (a third block is needed):
+        # residual assembly res = (B Phi) theta - H Phi in one contraction pass with a fused
+        # epilogue, and the density rho += sum_j (Phi X)_j phi_j
+        ns = min(norb, 128)
+        if 2 * ns <= norb:
+            sub = H.Orbitals(grid, ns, tdt, phi.psi()[:ns])
+            hsub = H.Orbitals(grid, ns, tdt, hphi.psi()[:ns])
+            rsub = H.Orbitals(grid, ns, tdt, hphi.psi()[ns:2 * ns])
+        else:
+            sub, hsub, rsub = phi, hphi, H.Orbitals(grid, ns, tdt)
+        Ms = M[:ns, :ns].contiguous()
+        fls = float(ns) * ns * npt
+        ms = _time_cuda(torch, lambda: H.computeResidualUsingHPhi(ham.lapOper(), sub, hsub, Ms, rsub),
+                        reps=3, warm=1)
+        out["residual"] = {"ms": ms, "orbitals": ns,
+                           "roofline": _tensor_roofline(2 * fls, ms, fp64_peak, "2 N^2 K")}
         rho = torch.zeros(grid.shape(), dtype=torch.float64, device="cuda")
-        ms = _time_cuda(torch, lambda: H.computeRhoUsingBlas3(phi, M, rho))
-        out["density"] = {"ms": ms, "roofline": {"bound": "tensor",
-                                                 "achieved": 2 * fl / (ms * 1e-3) / 1e12,
-                                                 "peak": fp64_peak, "unit": "TFLOP/s",
-                                                 "frac": 2 * fl / (ms * 1e-3) / 1e12 / fp64_peak,
-                                                 "flops": "2 N^2 K (+ 2 N K)"}}
-        del rho
+        ms = _time_cuda(torch, lambda: H.computeRhoUsingBlas3(sub, Ms, rho), reps=3, warm=1)
+        out["density"] = {"ms": ms, "orbitals": ns,
+                          "roofline": _tensor_roofline(2 * fls, ms, fp64_peak, "2 N^2 K (+ 2 N K)")}
+        del rho, sub, hsub, rsub
 
     # one orbital-update iteration's worth of the in-scope path, back to back on
     # one stream the way an SCF step orders it (SURVEY 3.1-3.4): H psi (with the
@@ -375,14 +479,13 @@ def measure_pieces(H, grid, phi, ham, lap_type, tdt, S, norb, npt, comm=None, hs
     def iteration():
         h = hstep() if hstep else ham.applyLocal(phi, True)
         phi.computeLocalProduct(h, comm)
-        pc.precond_mg(res)
+        pc(h)
         phi.computeGram(comm)
-        phi.multiplyByMatrix(M, prod)
+        phi.multiplyByMatrix(M, h)
     ms = _time_cuda(torch, iteration, reps=3, warm=1)
     out["orbital_update_iteration"] = {
         "ms": ms, "sequence": "H psi, Phi^T H Phi, precond_mg (2 levels), Gram, Phi M"}
     pc.close()
-    del res
     if comm is None:
         out.update(measure_poisson(H, grid, lap_type))
     return out
@@ -391,9 +494,7 @@ def measure_pieces(H, grid, phi, ham, lap_type, tdt, S, norb, npt, comm=None, hs
 def measure_poisson(H, grid, lap_type):
     """SURVEY 8f row f4, reported next to the path: the Hartree Poisson multigrid
     (SolverLap / Mgm / Vcycle, double) on the workload's grid, ten V(2,2) sweeps on
-    one scalar field.  Host control flow over the C-ABI grid operations; the
-    cycle is launch-bound at this size, which is what the number shows.  A failure
-    here never affects the headline line."""
+    one scalar field.  A failure here never affects the headline line."""
     import torch
     try:
         from mgmol_b200._lib import lib
@@ -407,23 +508,151 @@ def measure_poisson(H, grid, lap_type):
         def solve():
             vh.zero_()
             solver.solve(vh, rho)
+        solve()
         n0 = lib().mgb_launch_count()
-        ms = _time_cuda(torch, solve, reps=2, warm=1)
-        launches = (lib().mgb_launch_count() - n0) // 3
+        solve()
+        launches = lib().mgb_launch_count() - n0
+        ms = _time_cuda(torch, solve, reps=2, warm=0)
         sweeps = max(1, solver.getNbSweeps())
         return {"poisson_mg": {"ms": ms, "ms_per_sweep": ms / sweeps, "sweeps": sweeps,
                                "relative_residual": solver.getFinalRelativeResidual(),
                                "launches_per_solve": int(launches), "lap_type": lt,
-                               "bound": "launch latency (one field, %d kernels)" % launches}}
+                               "graph_replays": int(getattr(solver, "graph_replays", 0))}}
     except Exception as e:  # noqa: BLE001
         return {"poisson_mg": {"unavailable": "%s: %s" % (type(e).__name__, e)}}
+
+
+def measure_sweep(H, args, store_phi, store_out, fp64_peak):
+    """BASELINE configs[4] at one GPU: H psi on the 256^3 grid for {f64, f32} x {Mehrstellen,
+    4th order} (512 orbitals; 1024 for float, the same bytes), Gram on the same blocks.
+    The blocks are views of the headline's two allocations."""
+    import torch
+    from mgmol_b200._lib import lib
+    hbm, _ = measured_peaks()
+    cells = []
+    n = 256
+    dims = (n, n, n)
+    cell = WORKLOADS["synth256"]["cell"]
+    vt = torch.rand(dims, device="cuda", dtype=torch.float64) * 0.1 - 0.75
+    nbytes = store_phi.numel() * store_phi.element_size()
+    for dname, tdt, S in (("f64", torch.float64, 8), ("f32", torch.float32, 4)):
+        for norb in (512, 1024, 2048):
+            need = n ** 3 * norb * S
+            if need > nbytes:
+                cells.append({"dtype": dname, "orbitals": norb, "infeasible":
+                              "2 blocks of %.1f GB do not fit one 180 GB GPU" % (need / 1e9)})
+                continue
+            a = store_phi.view(torch.uint8)[:need].view(tdt).view((norb,) + dims)
+            b = store_out.view(torch.uint8)[:need].view(tdt).view((norb,) + dims)
+            if dname == "f32":
+                a.uniform_(-0.5, 0.5)
+            for lap in (0, 2):
+                grid = H.Grid(dims, (cell,) * 3, H.ghosts_for(lap))
+                op = H.LapFactory.createLap(grid, lap)
+                ms = _time_cuda(torch, lambda: op.applyWithPot(a, vt, b), reps=5, warm=2)
+                gbs = 2.0 * S * n ** 3 * norb / (ms * 1e-3) / 1e9
+                sig = lib().mgb_hpsi_last_kernel().decode()
+                tr, src = measured_traffic(sig, dims, norb, dname, lap)
+                cells.append({"dtype": dname, "lap_type": lap, "orbitals": norb, "ms": ms,
+                              "updates_per_s": float(n) ** 3 * norb / (ms * 1e-3),
+                              "kernel": sig,
+                              "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s",
+                                           "frac": gbs / hbm, "traffic": tr, "traffic_source": src}})
+            grid = H.Grid(dims, (cell,) * 3, 1)
+            o = H.Orbitals(grid, norb, tdt, a)
+            ms = _time_cuda(torch, lambda: o.computeGram(), reps=3, warm=1)
+            cells.append({"dtype": dname, "piece": "gram", "orbitals": norb, "ms": ms,
+                          "roofline": _tensor_roofline(float(norb) ** 2 * n ** 3, ms, fp64_peak,
+                                                       "N^2 K (syrk)")})
+    return cells
+
+
+def mgpu_parity(H, comm, rank, world, nproc):
+    """N > 1: before anything is timed, the multi-rank path against the ORACLE on a small
+    global box (oracle/ is used here as the checker only): H psi with in-place halos (both
+    operators), the fused V-cycle, Gram + all-reduce.  Returns the dict for the JSON line;
+    the caller exits non-zero on a failure."""
+    import torch
+    import torch.distributed as dist
+    from mgmol_b200.parallel import cart_coords, local_box
+    from oracle.oracle import Port, synthetic_orbitals, synthetic_potential
+    port = Port()
+    N = 6
+    gdims = tuple(16 * p for p in nproc)
+    gdims = (gdims[0], gdims[1], max(32, gdims[2]))
+    ll = tuple(0.25 * n for n in gdims)
+    coord = cart_coords(rank, nproc)
+    box = local_box(gdims, nproc, coord)
+    full = synthetic_orbitals(N, gdims, np.float64)
+    v = synthetic_potential(gdims)
+    res = {"global_grid": list(gdims), "orbitals": N, "checked_against": "oracle port (oracle/mgmol_oracle.c)"}
+    errs = {}
+    for lap in (0, 2):
+        g = H.ghosts_for(lap)
+        grid = H.Grid(gdims, ll, g, (1, 1, 1), nproc, coord)
+        mine = torch.from_numpy(np.ascontiguousarray(full[(slice(None),) + box])).cuda()
+        vmine = torch.from_numpy(np.ascontiguousarray(v[box])).cuda()
+        phi = H.Orbitals(grid, N, torch.float64, mine)
+        ham = H.Hamiltonian()
+        ham.setup(grid, lap)
+        ham.potential(H.Potentials(vmine))
+        vh = make_v_halo(H, comm, grid, g, vmine)
+        comm.register(mine)
+        got = ham.applyLocal(phi, True, peer_comm=comm, **vh).psi().cpu().numpy()
+        ref = port.hpsi(lap, full, v, ll)
+        scale = np.abs(ref).reshape(N, -1).max(axis=1)[:, None, None, None]
+        errs["hpsi_lap%d" % lap] = float((np.abs(got - ref[(slice(None),) + box]) / scale).max())
+        # Gram and Phi^T H Phi with the all-reduce
+        S = phi.computeGram(comm).cpu().numpy()
+        ex = grid.vel() * full.reshape(N, -1) @ full.reshape(N, -1).T
+        errs["gram_lap%d" % lap] = float(np.abs(S - ex).max() / np.abs(ex).max())
+        # multigrid-preconditioned residual on the decomposed box
+        pref = port.precond_mg(lap, 2, ref, ll, 0.3)
+        r = H.Orbitals(grid, N, torch.float64,
+                       torch.from_numpy(np.ascontiguousarray(ref[(slice(None),) + box])).cuda())
+        pc = H.OrbitalsPreconditioning()
+        pc.setup(r, 2, lap)
+        pc.set_comm(comm)
+        pc.gamma_ = 0.3
+        pc.precond_mg(r)
+        res["precond_mode_lap%d" % lap] = {1: "literal", 2: "fused"}.get(pc.last_mode())
+        gotp = r.psi().cpu().numpy()
+        errs["precond_mg_lap%d" % lap] = float(np.abs(gotp - pref[(slice(None),) + box]).max()
+                                               / np.abs(pref).max())
+        pc.close()
+        comm.unregister(mine)
+    t = torch.tensor([errs[k] for k in sorted(errs)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    errs = dict(zip(sorted(errs), t.cpu().tolist()))
+    bars = {"hpsi": 1e-12, "gram": 1e-12, "precond_mg": 5e-6}
+    ok = all(e <= bars[k.rsplit("_lap", 1)[0]] for k, e in errs.items())
+    res.update({"max_err": errs, "bars": bars, "ok": bool(ok),
+                "max_err_overall_fp64_paths": max(e for k, e in errs.items() if not k.startswith("precond"))})
+    return res
+
+
+def make_v_halo(H, comm, grid, g, vtot):
+    """The potential's halo for a decomposed box, exchanged once per potential update:
+    x-slab decompositions use the 2g packed x planes, any other one a ghosted copy of V
+    traded Y -> Z -> X like the reference's gfpot (src/Hamiltonian.cc:108-111)."""
+    import torch
+    if grid.nproc[1] == 1 and grid.nproc[2] == 1:
+        xv = torch.zeros((1, 2 * g) + tuple(grid.shape()[1:]), dtype=torch.float64, device="cuda")
+        comm.halo_exchange_x(grid, g, vtot[None], xv)
+        return {"xhalo_v": xv}
+    gg = grid.with_ghosts(g)
+    gv = H.GridFuncVector(gg, 1, torch.float64)
+    gv.assign(vtot[None].contiguous())
+    comm.trade_boundaries(gv)
+    return {"vghost": gv.data}
 
 
 def run_ours(args):
     import torch
     import torch.distributed as dist
     from mgmol_b200 import host as H
-    from mgmol_b200._lib import lib, check
+    from mgmol_b200._lib import lib, check, MgbError
+    from mgmol_b200.parallel import cart_coords
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -447,68 +676,76 @@ def run_ours(args):
             cpus &= os.sched_getaffinity(0)
             if cpus:
                 os.sched_setaffinity(0, cpus)
-                if os.environ.get("MGB_BENCH_VERBOSE"):
-                    sys.stderr.write("rank %d bound to %d cpus\n" % (rank, len(cpus)))
         except Exception:  # noqa: BLE001
             pass
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         from mgmol_b200.parallel import Communicator
         comm = Communicator(rank, world)
+    # the clock sampler (NVML init + a thread) exists before anything is timed
+    sampler = ClockSampler(local) if rank == 0 else None
 
-    dims, cell, norb, lap_default, desc = WORKLOADS[args.workload]
-    if args.orbitals:
-        norb = args.orbitals
-    lap_type = lap_default if args.lap is None else args.lap
+    L = layout(args, world)
+    parity = None
+    if world > 1:
+        # can the fused kernels read halos in place on this decomposition?  (collective)
+        try:
+            parity = mgpu_parity(H, comm, rank, world, L["nproc"])
+        except MgbError as e:
+            if L["nproc"] != (world, 1, 1) and not (args.decomp and args.decomp != "auto"):
+                if rank == 0:
+                    sys.stderr.write("bench: decomposition %s not served in place (%s); x slabs\n"
+                                     % (L["config"]["decomposition"], e))
+                args.decomp = "%dx1x1" % world
+                L = layout(args, world)
+                L["config"]["decomposition_from"] = "x slabs (fallback)"
+                parity = mgpu_parity(H, comm, rank, world, L["nproc"])
+            else:
+                raise
+    nproc, gdims, dims, cell = L["nproc"], L["gdims"], L["ldims"], L["cell"]
+    norb, lap_type, S = L["norb"], L["lap_type"], L["S"]
     tdt = torch.float64 if args.dtype == "f64" else torch.float32
-    S = 8 if args.dtype == "f64" else 4
     g = H.ghosts_for(lap_type)
-    if args.strong:
-        # strong scaling: the workload's own grid split along x over the ranks
-        assert dims[0] % world == 0 and (dims[0] // world) % 4 == 0, "x planes per rank"
-        gdims = dims
-        grid = H.Grid(gdims, (cell, cell, cell), g, (1, 1, 1), (world, 1, 1), (rank, 0, 0))
-        dims = (dims[0] // world, dims[1], dims[2])
-    else:
-        gdims = (dims[0] * world, dims[1], dims[2])
-        grid = H.Grid(gdims, (cell * world, cell, cell), g, (1, 1, 1), (world, 1, 1),
-                      (rank, 0, 0))
+    coord = cart_coords(rank, nproc)
+    grid = H.Grid(gdims, cell, g, (1, 1, 1), nproc, coord)
     npt = grid.size()
 
     # synthetic orbitals: plane wave along z with orbital-dependent wavevector
     # + 0.1 U(-1,1) noise; potential a noisy constant.  A handful of large
-    # launches (chunks of <= 64 orbitals) so the ncu launch list stays short.
+    # launches (chunks of <= 16 orbitals) so the ncu launch list stays short.
     gen = torch.Generator(device="cuda").manual_seed(1234 + rank)
-    phi = H.Orbitals(grid, norb, tdt)
+    phi = H.Orbitals(grid, norb, tdt, torch.empty((norb,) + dims, dtype=tdt, device="cuda"))
     x = torch.arange(dims[2], device="cuda", dtype=torch.float64) / dims[2]
-    for j0 in range(0, norb, 64):
-        j1 = min(norb, j0 + 64)
+    fill = max(1, min(64, int(2e9 // (npt * S))))
+    for j0 in range(0, norb, fill):
+        j1 = min(norb, j0 + fill)
         k = (torch.arange(j0, j1, device="cuda") % 5 + 1).to(torch.float64)
         wave = torch.cos(2 * np.pi * k[:, None] * x[None, :])[:, None, None, :]
-        noise = torch.rand((j1 - j0,) + dims, generator=gen, device="cuda", dtype=tdt)
-        phi.psi()[j0:j1] = (noise * 0.2 - 0.1) + wave.to(tdt)
-        del noise
+        blk = phi.psi()[j0:j1]
+        blk.uniform_(-0.1, 0.1, generator=gen)
+        blk += wave.to(tdt)
+    del wave, blk
     vtot = (torch.rand(dims, generator=gen, device="cuda", dtype=torch.float64) * 0.1 - 0.75)
     ham = H.Hamiltonian()
     ham.setup(grid, lap_type)
     ham.potential(H.Potentials(vtot))
+    ham.hlphi_ = H.Orbitals(grid, norb, tdt, torch.empty((norb,) + dims, dtype=tdt, device="cuda"))
 
-    # N > 1: V's halo is exchanged once (it is fixed over the steps); the
-    # neighbours' boundary planes of the orbitals are read in place over NVLink
-    # (peer mapping of the orbital block) -- or, if the block cannot be mapped,
-    # packed and exchanged with NCCL send/recv every step.
-    xh_phi = xh_v = None
+    # N > 1: V's halo is exchanged once (it is fixed over the steps); the neighbours'
+    # boundary layers of the orbitals are read in place over NVLink (peer mapping of the
+    # orbital block) -- or, on x slabs whose block cannot be mapped, packed and exchanged
+    # with NCCL send/recv every step.
+    xh_phi = None
+    vh = {}
     halo_mode = None
     if world > 1:
-        from mgmol_b200._lib import MgbError
-        xh_v = torch.zeros((1, 2 * g) + dims[1:], dtype=torch.float64, device="cuda")
-        comm.halo_exchange_x(grid, g, vtot[None], xh_v)
+        vh = make_v_halo(H, comm, grid, g, vtot)
         halo_mode = "peer_nvlink"
         if os.environ.get("MGB_BENCH_HALO") == "nccl":
             halo_mode = "nccl_packed"
         else:
             try:
                 comm.register(phi.psi())
-                ham.applyLocal(phi, True, None, xh_v, comm)
+                ham.applyLocal(phi, True, peer_comm=comm, **vh)
             except MgbError as e:
                 if rank == 0:
                     sys.stderr.write("bench: peer halo unavailable (%s)\n" % e)
@@ -517,14 +754,16 @@ def run_ours(args):
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         if int(ok) == 0:
             halo_mode = "nccl_packed"
+            assert nproc[1] == 1 and nproc[2] == 1, "the packed exchange feeds x slabs only"
             xh_phi = torch.zeros((norb, 2 * g) + dims[1:], dtype=tdt, device="cuda")
 
     def step():
         if world > 1 and halo_mode == "peer_nvlink":
-            return ham.applyLocal(phi, True, None, xh_v, comm)
+            return ham.applyLocal(phi, True, peer_comm=comm, **vh)
         if world > 1:
             comm.halo_exchange_x(grid, g, phi.psi(), xh_phi)
-        return ham.applyLocal(phi, True, xh_phi, xh_v)
+            return ham.applyLocal(phi, True, xh_phi, vh["xhalo_v"])
+        return ham.applyLocal(phi, True)
 
     def barrier():
         if world > 1:
@@ -533,53 +772,64 @@ def run_ours(args):
 
     for _ in range(args.warmup):
         step()
-    barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-    n0 = lib().mgb_launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for _ in range(args.steps):
+    barrier()
+    if world > 1:
+        # rank skew is absorbed on the DEVICE before the first timed event: a
+        # stream-ordered barrier over all ranks, one more untimed step, a second one
+        comm.barrier()
         step()
-    ev1.record()
+        comm.barrier()
+    n0 = lib().mgb_launch_count()
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    evs[0].record()
+    for i in range(args.steps):
+        step()
+        evs[i + 1].record()
     barrier()
     launches = lib().mgb_launch_count() - n0
-    ms = ev0.elapsed_time(ev1)
+    ms = evs[0].elapsed_time(evs[-1])
+    per_step = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
     path = lib().mgb_hpsi_last_path()
+    kernel_sig = lib().mgb_hpsi_last_kernel().decode()
+    clocks = sampler.summary() if sampler else None
 
-    # kernel-only duration (no halo exchange) for the roofline
-    evs = []
+    # kernel-only duration for the roofline: the same launches, each between its own
+    # pair of events on the launching stream (at N > 1 this includes the two neighbour
+    # flag kernels of the call)
+    kevs = []
     for _ in range(min(args.steps, 10)):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        if halo_mode == "peer_nvlink":
-            ham.applyLocal(phi, True, None, xh_v, comm)
-        else:
-            ham.applyLocal(phi, True, xh_phi, xh_v)
+        step()
         b.record()
-        evs.append((a, b))
+        kevs.append((a, b))
     torch.cuda.synchronize()
-    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
-    clocks = sampler.summary() if sampler else None
+    kern_ms = float(np.median([a.elapsed_time(b) for a, b in kevs]))
 
-    # end-to-end through the reference-facing call with HOST buffers: pinned
-    # host orbitals in, pinned host H psi out.  N = 1: one mgb_hpsi_host call per
-    # step (H2D, kernel and D2H pipelined over orbital blocks inside the
-    # library).  N > 1: copy in, halo exchange + kernel, copy out.
-    h_phi = torch.empty(phi.psi().shape, dtype=tdt).pin_memory()
-    h_phi.copy_(phi.psi())
+    # end-to-end through the reference-facing call with HOST buffers: pinned host orbitals
+    # in, pinned host H psi out (H2D, kernel and D2H pipelined over orbital blocks inside
+    # the library).  Bounded host memory: at most ~8.6 GB each way per step, i.e. the
+    # first e2e_orb orbitals of the block -- the rate is per update.
+    e2e_orb = norb
+    while e2e_orb > 8 and npt * e2e_orb * S > 9e9:
+        e2e_orb //= 2
+    h_phi = torch.empty((e2e_orb,) + dims, dtype=tdt).pin_memory()
+    h_phi.copy_(phi.psi()[:e2e_orb])
     h_out = torch.empty_like(h_phi).pin_memory()
     h_v = torch.empty(vtot.shape, dtype=torch.float64).pin_memory()
     h_v.copy_(vtot)
     e2e_steps = max(2, min(args.steps, 5))
-
     e2e_mode = "pipelined host call (mgb_hpsi_host)"
+    sub_phi = H.Orbitals(grid, e2e_orb, tdt, phi.psi()[:e2e_orb])
     if world > 1:
         e2e_mode = "pipelined host call per rank, halos in place (mgb_hpsi_host_peer)"
+        okp = 1
         try:
+            if nproc[1] != 1 or nproc[2] != 1:
+                raise RuntimeError("host pipeline serves x slabs")
             ham.lapOper().applyWithPotHostPeer(comm, h_phi, h_v, h_out)
-            okp = 1
         except Exception as e:  # noqa: BLE001
             okp = 0
             if rank == 0:
@@ -587,7 +837,7 @@ def run_ours(args):
         okt = torch.tensor([okp], device="cuda")
         dist.all_reduce(okt, op=dist.ReduceOp.MIN)
         if int(okt) == 0:
-            e2e_mode = "copy in, halo + kernel, copy out"
+            e2e_mode = "pinned host block copied in, in-place-halo kernel, H psi copied out"
 
     def e2e_step():
         if world == 1:
@@ -595,29 +845,41 @@ def run_ours(args):
         elif e2e_mode.startswith("pipelined"):
             ham.lapOper().applyWithPotHostPeer(comm, h_phi, h_v, h_out)
         else:
-            phi.psi().copy_(h_phi, non_blocking=True)
+            # every rank refreshes the first e2e_orb orbitals of its registered block,
+            # all ranks run the full in-place-halo step, the same orbitals come back
+            sub_phi.psi().copy_(h_phi, non_blocking=True)
             out = step()
-            h_out.copy_(out.psi(), non_blocking=True)
+            h_out.copy_(out.psi()[:e2e_orb], non_blocking=True)
 
     e2e_step()
     barrier()
     t0 = time.perf_counter()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(e2e_steps):
         e2e_step()
     ev1.record()
     barrier()
     e2e_ms = max(ev0.elapsed_time(ev1), (time.perf_counter() - t0) * 1e3)
+    e2e_updates = float(npt) * e2e_orb
+    if world > 1 and not e2e_mode.startswith("pipelined"):
+        # the kernel ran over the whole block; charge the copies' orbitals only if the
+        # kernel time is scaled too: report the conservative figure (whole-step time,
+        # copied orbitals only)
+        pass
+    del h_phi, h_out
 
-    t = torch.tensor([ms, e2e_ms, kern_ms], dtype=torch.float64, device="cuda")
+    t = torch.tensor([ms, e2e_ms, kern_ms] + per_step, dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, e2e_ms, kern_ms = (float(v) for v in t.cpu())
+    tl = t.cpu().tolist()
+    ms, e2e_ms, kern_ms, per_step = tl[0], tl[1], tl[2], tl[3:]
 
+    fp64_peak = fp64_tensor_peak(torch)
     pieces = None
     if not args.no_pieces:
         pieces = measure_pieces(H, grid, phi, ham, lap_type, tdt, S, norb, npt, comm,
-                                step if world > 1 else None)
+                                step if world > 1 else None, fp64_peak)
         if world > 1:
             # max over ranks of every timing
             keys = ["precond_mg", "gram", "phiT_H_phi", "phi_M", "orbital_update_iteration"]
@@ -625,76 +887,91 @@ def run_ours(args):
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             for k, v in zip(keys, tt.cpu().tolist()):
                 pieces[k]["ms_max_over_ranks"] = v
+        elif args.workload == "synth256" and not args.no_sweep and args.dtype == "f64":
+            pieces["sweep_256"] = measure_sweep(H, args, phi.psi(), ham.hlphi_.psi(), fp64_peak)
 
     if rank == 0:
         updates_per_step = float(npt) * norb * world
         value = updates_per_step * args.steps / (ms * 1e-3)
-        e2e = updates_per_step * e2e_steps / (e2e_ms * 1e-3)
+        e2e = e2e_updates * world * e2e_steps / (e2e_ms * 1e-3)
         peak, peak_src = measured_peaks()
         achieved = 2.0 * S * npt * norb / (kern_ms * 1e-3) / 1e9
-        cpu_dims = gdims if args.strong else dims
-        cpu_rate, cores, kind, sample = cpu_hpsi_rate(
-            lap_type, cpu_dims, (cell,) * 3, np.float64 if args.dtype == "f64" else np.float32)
+        np_dt = np.float64 if args.dtype == "f64" else np.float32
+        cpu_rate, cores, kind, sample = cpu_hpsi_rate(lap_type, gdims, cell, np_dt)
+        traffic, traffic_src = (measured_traffic(kernel_sig, dims, norb, args.dtype, lap_type)
+                                if path == 1 else (None, "no capture"))
+        cfg = dict(L["config"])
         line = {
             "metric": "hpsi_gridpt_orbital_updates_per_s", "value": value, "unit": "updates/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "ms_per_step": ms / args.steps,
+            "ms_per_step_median": float(np.median(per_step)), "first_step_ms": per_step[0],
+            "higher_is_better": True,
             "scaling": "strong" if args.strong else "weak",
             "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-            "config": {"workload": desc, "lap_type": lap_type, "grid_per_gpu": list(dims),
-                       "orbitals": norb, "decomposition": "%dx1x1" % world,
-                       "halo": halo_mode,
-                       "hpsi_path": {1: "tma_fused", 2: "generic_fused", 3: "ghosted"}.get(path),
-                       "l2": "inputs larger than L2 (%.1f GB per step)" %
-                             (2.0 * S * npt * norb / 1e9)},
+            "config": cfg,
+            "path": {"halo": halo_mode,
+                     "hpsi_path": {1: "tma_fused", 2: "generic_fused", 3: "ghosted"}.get(path),
+                     "kernel": kernel_sig},
             "e2e": {"value": e2e, "unit": "updates/s",
-                    "h2d_bytes_per_step": int(S * npt * norb) * world,
-                    "d2h_bytes_per_step": int(S * npt * norb) * world,
-                    "how": e2e_mode},
+                    "h2d_bytes_per_step": int(S * npt * e2e_orb) * world,
+                    "d2h_bytes_per_step": int(S * npt * e2e_orb) * world,
+                    "orbitals_per_step": e2e_orb,
+                    "how": e2e_mode + "; host memory bounded: %d of the %d orbitals per step"
+                           % (e2e_orb, norb)},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak,
-                         "traffic": measured_traffic("k_hpsi_tma" if path == 1 else "k_hpsi_generic",
-                                                     args.workload, args.dtype, lap_type)
-                         if world == 1 and not args.orbitals else None,
+                         "frac": achieved / peak, "traffic": traffic,
+                         "traffic_source": traffic_src,
                          "kernel": "k_hpsi_tma" if path == 1 else "k_hpsi_generic",
                          "kernel_ms": kern_ms, "peak_source": peak_src,
                          "algorithmic_bytes_per_update": 2 * S},
             "cpu_baseline": {"value": cpu_rate, "unit": "updates/s", "cores": cores,
                              "kind": kind, "sample": sample},
         }
+        if parity is not None:
+            line["parity_mgpu"] = parity
         if pieces:
             if world == 1 and not args.no_cpu_iteration:
-                ci = cpu_iteration(lap_type, dims, (cell,) * 3,
-                                   np.float64 if args.dtype == "f64" else np.float32, norb)
+                ci = cpu_iteration(lap_type, dims, cell, np_dt, norb)
                 it = pieces["orbital_update_iteration"]
                 it["cpu_reference"] = ci
                 it["speedup_vs_cpu_reference"] = ci["seconds"] * 1e3 / it["ms"]
             line["pieces"] = pieces
         print(json.dumps(line))
+    rc = 0
+    if parity is not None and not parity["ok"]:
+        sys.stderr.write("bench: multi-GPU parity check FAILED: %s\n" % json.dumps(parity))
+        rc = 3
     if world > 1:
         comm.check()
         dist.destroy_process_group()
+    if rc:
+        sys.exit(rc)
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--strong", action="store_true",
-                    help="split the workload's own grid over the GPUs (default: weak scaling, "
-                         "one full grid per GPU)")
+                    help="split the workload's own grid over the GPUs and keep its orbital count "
+                         "(default: weak scaling, fixed work per GPU)")
+    ap.add_argument("--decomp", default="auto",
+                    help="auto (PEenv::geom) or PxQxR ranks along x, y, z")
     ap.add_argument("--no-cpu-iteration", action="store_true",
                     help="skip the CPU reference timing of the orbital-update iteration")
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="h2o64", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--lap", type=int, default=None)
     ap.add_argument("--orbitals", type=int, default=0)
     ap.add_argument("--no-pieces", action="store_true",
                     help="skip the per-piece measurements (V-cycle, contractions)")
+    ap.add_argument("--no-sweep", action="store_true",
+                    help="skip the dtype x operator sweep of the 256^3 workload")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -168,6 +168,9 @@ int mgb_host_unregister(void* ptr);
  * 1 TMA-pipelined fused kernel, 2 generic fused kernel, 3 ghosted-block
  * composition.                                                              */
 int mgb_hpsi_last_path(void);
+/* Template arguments and tile configuration of the kernel mgb_hpsi launched last (the
+ * signature the ncu captures under profiles/ are keyed by).                    */
+const char* mgb_hpsi_last_kernel(void);
 /* Force a path (0 = automatic).  Test hook. */
 int mgb_hpsi_force_path(int path);
 
@@ -422,6 +425,21 @@ int mgb_peer_set_color_maps(mgb_comm* c, const int* map_west, const int* map_eas
 int mgb_hpsi_peer(mgb_comm* c, int lap_type, int dtype, const mgb_grid* grid,
     const void* phi, size_t ld, const double* vtot, void* hphi, size_t ldh,
     int nfunc, const double* xhalo_v, void* stream);
+/* The same on ANY px x py x pz decomposition (pb::PEenv::geom, src/pb/PEenv.cc:335-, gives
+ * 2 x 2 x 2 for a cubic grid on 8 ranks): the g planes, rows and columns outside the box --
+ * and the edge lines the Mehrstellen stencil reaches -- are fetched by the kernel's TMA
+ * producer from the blocks of the up to 26 neighbouring ranks, in place over NVLink
+ * (GridFuncVector::trade_boundaries' N/S, U/D and E/W exchanges, src/pb/GridFuncVector.cc:
+ * 232-315, 748-830, 1195-1256, without any packed copy).  phi must be registered
+ * (mgb_peer_register) and have the same shape on every rank; orbitals keep their slots
+ * (ExtendedGridOrbitals).  vghost: the potential as a ghosted double field of the stencil's
+ * width whose boundaries were traded (mgb_gfv_set_with_ghosts + mgb_halo_exchange_ghosted once
+ * per potential update: gfpot of src/Hamiltonian.cc:108-111); may be null for MGB_LAP_4,
+ * which multiplies by V at the centre only.  comm may be null on a single rank (every
+ * neighbour is the box itself: the periodic wrap).                                     */
+int mgb_hpsi_peer3d(mgb_comm* comm, int lap_type, int dtype, const mgb_grid* grid,
+    const void* phi, size_t ld, const double* vtot, const double* vghost, void* hphi, size_t ldh,
+    int nfunc, void* stream);
 /* x-direction halo for the fused H path: sends this rank's first/last g
  * planes of every function to the west/east neighbours and fills
  * xhalo[nfunc][2g][ny][nz] (replaces initiate/finishEastWestComm,

@@ -528,6 +528,40 @@ public:
         if (comm)
             MGB_CHECK(mgb_allreduce_sum_f64(comm, ss_dev, (size_t)numst_ * A.numst(), stream));
     }
+    // addDotWithNcol2Matrix (src/ExtendedGridOrbitals.cc:1704-1752): mat_dev
+    // (numst x numst, column-major double) += vel Phi^T A summed over the ranks;
+    // work_dev: numst x numst doubles
+    void addDotWithNcol2Matrix(const ExtendedGridOrbitals<T>& A, double* mat_dev, double* work_dev,
+        mgb_comm* comm = nullptr, void* stream = nullptr) const
+    {
+        computeLocalProduct(A, work_dev, comm, stream);
+        MGB_CHECK(mgb_axpy(MGB_F64, (size_t)numst_ * A.numst(), 1., work_dev, mat_dev, stream));
+    }
+    // computeMatB (src/ExtendedGridOrbitals.cc:901-967): matB_dev(i, j) = vel <orbitals_i | B |
+    // this_j>, B the operator's right-hand-side stencil (Lap::rhs; the identity unless
+    // Mehrstellen), in blocks of `bcolor` columns through a work block like the reference
+    // (bcolor = 32 there).  LapT: Lap<T> (defined below).
+    template <class LapT>
+    void computeMatB(const ExtendedGridOrbitals<T>& orbitals, const LapT& LapOper,
+        double* matB_dev, mgb_comm* comm = nullptr, void* stream = nullptr,
+        const int bcolor = 32) const
+    {
+        if (numst_ == 0) return;
+        DeviceMemory<T> work;
+        work.allocate(lda_ * (size_t)bcolor);
+        for (int icolor = 0; icolor < numst_; icolor += bcolor)
+        {
+            const int nf = (icolor + bcolor > numst_) ? numst_ - icolor : bcolor;
+            LapOper.rhs(getPsi(icolor), lda_, work.data(), lda_, nf, nullptr, stream);
+            MGB_CHECK(mgb_gemm_tn(dtype_of<T>::value, orbitals.numst(), nf, numpt_, grid_.vel(),
+                orbitals.getPsi(), orbitals.getLda(), work.data(), lda_, 0.,
+                matB_dev + (size_t)icolor * orbitals.numst(), orbitals.numst(), stream));
+        }
+        if (comm)
+            MGB_CHECK(mgb_allreduce_sum_f64(
+                comm, matB_dev, (size_t)numst_ * orbitals.numst(), stream));
+        MGB_CHECK(mgb_stream_sync(stream)); // work is freed on return
+    }
     // multiplyByMatrix (src/ExtendedGridOrbitals.cc:448-498): product = Phi M,
     // M column-major numst x n on the device
     void multiplyByMatrix(const double* matrix_dev, const int n,
@@ -752,6 +786,14 @@ public:
         MGB_CHECK(mgb_hpsi(type_, dtype_of<T>::value, grid_.c(), phi, ld, vtot, hphi, ldh,
             nfunc, xhalo_phi, xhalo_v, stream));
     }
+    // Lap<T>::rhs (src/pb/Lap.h:32) for nfunc orbitals of a no-ghost block: B phi
+    // (Mehrstellen, src/pb/FDkernels.cc:522-584) or a copy (B = 1)
+    void rhs(const T* phi, const size_t ld, T* bphi, const size_t ldb, const int nfunc,
+        const void* xhalo_phi = nullptr, void* stream = nullptr) const
+    {
+        MGB_CHECK(mgb_apply_b(type_, dtype_of<T>::value, grid_.c(), phi, ld, bphi, ldb, nfunc,
+            xhalo_phi, stream));
+    }
 
 private:
     Grid grid_;
@@ -820,6 +862,14 @@ public:
         lapOper_->applyWithPot(phi.getPsi(), phi.getLda(), pot_->vtot(), hphi.getPsi(),
             hphi.getLda(), ncolors, nullptr, nullptr, stream);
         hphi.incrementIterativeIndex();
+    }
+    // src/Hamiltonian.cc:163-212: hij_dev += vel Phi1^T (H_loc Phi2), summed over ranks
+    void addHlocal2matrix(ExtendedGridOrbitals<T>& phi1, ExtendedGridOrbitals<T>& phi2,
+        double* hij_dev, double* work_dev, const bool force = false, mgb_comm* comm = nullptr,
+        void* stream = nullptr)
+    {
+        applyLocal(phi2, force, stream);
+        phi1.addDotWithNcol2Matrix(*hlphi_, hij_dev, work_dev, comm, stream);
     }
     // src/Hamiltonian.cc:214-239: hij_dev = vel Phi1^T (H_loc Phi2)
     void addHlocalij(ExtendedGridOrbitals<T>& phi1, ExtendedGridOrbitals<T>& phi2,

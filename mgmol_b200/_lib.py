@@ -63,6 +63,7 @@ _SIGS = {
     "mgb_host_register": (c_int, [c_void_p, c_size_t]),
     "mgb_host_unregister": (c_int, [c_void_p]),
     "mgb_hpsi_last_path": (c_int, []),
+    "mgb_hpsi_last_kernel": (ctypes.c_char_p, []),
     "mgb_hpsi_force_path": (c_int, [c_int]),
     "mgb_gfv_set_with_ghosts": (c_int, [c_int, c_int, ctypes.POINTER(MgbGrid),
                                         c_void_p, c_size_t, c_void_p, c_int, c_void_p]),
@@ -139,6 +140,9 @@ _SIGS = {
     "mgb_hpsi_peer": (c_int, [c_void_p, c_int, c_int, ctypes.POINTER(MgbGrid), c_void_p,
                               c_size_t, c_void_p, c_void_p, c_size_t, c_int, c_void_p,
                               c_void_p]),
+    "mgb_hpsi_peer3d": (c_int, [c_void_p, c_int, c_int, ctypes.POINTER(MgbGrid), c_void_p,
+                                c_size_t, c_void_p, c_void_p, c_void_p, c_size_t, c_int,
+                                c_void_p]),
     "mgb_halo_exchange_x": (c_int, [c_void_p, c_int, ctypes.POINTER(MgbGrid), c_int,
                                     c_void_p, c_size_t, c_void_p, c_int, c_void_p]),
     "mgb_halo_set_color_maps": (c_int, [c_void_p, c_int, c_int, c_void_p]),

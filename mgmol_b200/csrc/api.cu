@@ -213,6 +213,7 @@ int mgb_stream_sync(void* stream)
 }
 
 int mgb_hpsi_last_path(void) { return g_last_path; }
+const char* mgb_hpsi_last_kernel(void) { return g_last_path == 1 ? hpsi_last_kernel() : (g_last_path == 2 ? "k_hpsi_generic" : "ghosted composition"); }
 int mgb_hpsi_force_path(int path)
 {
     MGB_REQUIRE(path >= 0 && path <= 3, "mgb_hpsi_force_path: path %d", path);
@@ -223,7 +224,8 @@ int mgb_hpsi_force_path(int path)
 static int hpsi_entry(int lap_type, int dtype, const mgb_grid* grid, const void* phi,
     size_t ld, const double* vtot, void* hphi, size_t ldh, int nfunc,
     const void* xhalo_phi, const double* xhalo_v, const void* peer_w, const void* peer_e,
-    const int* map_w, const int* map_e, void* stream)
+    const int* map_w, const int* map_e, void* stream, const void* const* nb3d = nullptr,
+    const double* vghost = nullptr)
 {
     if (int rc = require_device()) return rc;
     if (int rc = check_grid(grid)) return rc;
@@ -258,11 +260,25 @@ static int hpsi_entry(int lap_type, int dtype, const mgb_grid* grid, const void*
     a.peer_e    = peer_e;
     a.map_w     = map_w;
     a.map_e     = map_e;
+    a.nb3d      = nb3d;
+    a.vghost    = vghost;
     cudaStream_t st = as_stream(stream);
+    if (nb3d)
+    {
+        // every halo read in place from the neighbours' blocks: the TMA kernel only
+        MGB_REQUIRE(grid->bc[0] == grid->bc[1] && grid->bc[1] == grid->bc[2],
+            "mgb_hpsi_peer3d: mixed boundary conditions are served by the ghosted-block entry points");
+        const int rc = hpsi_tma(a, st);
+        if (rc == MGB_OK) g_last_path = 1;
+        if (rc == MGB_ENOTSUP)
+            set_error("mgb_hpsi_peer3d: box not eligible for the TMA kernel (nz <= 256, z rows a "
+                      "multiple of 32 bytes, 16-byte aligned blocks)");
+        return rc;
+    }
 
     const bool uniform_bc = (grid->bc[0] == grid->bc[1] && grid->bc[1] == grid->bc[2]);
     const bool yz_single  = grid->nproc[1] == 1 && grid->nproc[2] == 1;
-    MGB_REQUIRE(grid->nproc[0] == 1 || ((xhalo_phi || (peer_w && peer_e)) && xhalo_v),
+    MGB_REQUIRE(nb3d || grid->nproc[0] == 1 || ((xhalo_phi || (peer_w && peer_e)) && xhalo_v),
         "mgb_hpsi: x is split over %d ranks but no x-halo buffers were given",
         grid->nproc[0]);
     MGB_REQUIRE(grid->dim[0] >= a.g && grid->dim[1] >= a.g && grid->dim[2] >= a.g,
@@ -414,6 +430,48 @@ int mgb_hpsi_peer(mgb_comm* comm, int lap_type, int dtype, const mgb_grid* grid,
     return comm_barrier_neighbors(comm, grid, st);
 }
 
+
+int mgb_hpsi_peer3d(mgb_comm* comm, int lap_type, int dtype, const mgb_grid* grid,
+    const void* phi, size_t ld, const double* vtot, const double* vghost, void* hphi, size_t ldh,
+    int nfunc, void* stream)
+{
+    if (int rc = require_device()) return rc;
+    if (int rc = check_grid(grid)) return rc;
+    MGB_REQUIRE(phi, "mgb_hpsi_peer3d: null pointer");
+    const int np = grid->nproc[0] * grid->nproc[1] * grid->nproc[2];
+    MGB_REQUIRE(comm || np == 1, "mgb_hpsi_peer3d: a decomposed grid needs the communicator");
+    for (int d = 0; d < 3; d++)
+        MGB_REQUIRE(grid->dim[d] * grid->nproc[d] == grid->gdim[d],
+            "mgb_hpsi_peer3d: direction %d must be split evenly (neighbours' blocks have my shape)", d);
+    MGB_REQUIRE(lap_type == MGB_LAP_4 || vghost,
+        "mgb_hpsi_peer3d: the Mehrstellen operator needs the ghosted copy of the potential");
+    // the blocks of the 26 neighbours (myself across a direction that is not split; null
+    // beyond a non-periodic end -- never read: those boxes are out of range by coordinate)
+    const void* nb[27];
+    for (int dx = -1; dx <= 1; dx++)
+        for (int dy = -1; dy <= 1; dy++)
+            for (int dz = -1; dz <= 1; dz++)
+            {
+                const int i = ((dx + 1) * 3 + (dy + 1)) * 3 + (dz + 1);
+                const int r = comm_rank_of(
+                    grid, grid->coord[0] + dx, grid->coord[1] + dy, grid->coord[2] + dz);
+                nb[i] = (np == 1) ? phi : peer_view(comm, phi, r);
+                if (!nb[i])
+                {
+                    set_error("mgb_hpsi_peer3d: phi is not registered with mgb_peer_register (or "
+                              "rank %d's block cannot be mapped)", r);
+                    return MGB_ENOTSUP;
+                }
+            }
+    cudaStream_t st = as_stream(stream);
+    // every rank's phi is complete before anybody reads boundary layers ...
+    if (int rc = comm_barrier_neighbors(comm, grid, st)) return rc;
+    const int rc = hpsi_entry(lap_type, dtype, grid, phi, ld, vtot, hphi, ldh, nfunc, nullptr,
+        nullptr, nullptr, nullptr, nullptr, nullptr, stream, nb, vghost);
+    if (rc) return rc;
+    // ... and nobody overwrites its phi while a neighbour still reads it
+    return comm_barrier_neighbors(comm, grid, st);
+}
 
 /* ---- host-buffer entry: H2D copy, fused kernel and D2H copy pipelined over
  * blocks of orbitals on three streams (full-duplex PCIe) ------------------- */

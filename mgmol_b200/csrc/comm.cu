@@ -125,12 +125,13 @@ struct mgb_comm
     void* buf[4];
     size_t buf_sz[4];
     float* flag;                                  // 1-element all-reduce = rank barrier
-    // neighbour barrier over peer memory: inbox[0] = epoch last signalled by my
-    // west neighbour, inbox[1] = by my east neighbour; inbox[2] = timeout flag
+    // neighbour barrier over peer memory: inbox[r] = epoch last signalled by rank r
+    // (only my Cartesian neighbours ever write theirs)
     unsigned long long* inbox;
-    unsigned long long* west_inbox; // the west rank's inbox, mapped here
-    unsigned long long* east_inbox;
-    int nb_west, nb_east;           // ranks the mapping was made for (-1: none)
+    unsigned long long** d_peer_inbox; // device table [nranks]: the neighbours' inboxes mapped here
+    int nb_key[9];                     // nproc, coord, bc the table was built for
+    int nb_mode;                       // 0 not agreed yet, 1 peer flags, 2 NCCL all-reduce (every rank)
+    int nb_count;                      // distinct neighbour ranks
     unsigned long long epoch;
     // gid-addressed packed exchange: hmaps[dir][side][iloc][color] = the sending
     // neighbour's color whose slab holds my color's orbital, or -1 (device)
@@ -436,76 +437,124 @@ int comm_barrier(mgb_comm* c, cudaStream_t st)
 
 int comm_rank_of(const mgb_grid* gr, int cx, int cy, int cz) { return rank_of(gr, cx, cy, cz); }
 
-// Barrier with the x neighbours only, through peer memory: publish my epoch in
-// both neighbours' inboxes (remote stores over NVLink), then wait until both of
-// mine have reached it.  One tiny kernel instead of a collective; a halo only
-// ever depends on the two neighbours.  The wait gives up after ~2 s and raises a
-// flag instead of hanging the GPU.
-__global__ void k_neighbor_sync(unsigned long long* inbox, unsigned long long* west_inbox,
-    unsigned long long* east_inbox, unsigned long long epoch)
+// Barrier with the Cartesian neighbours only (every rank within one step in each
+// split direction: the ranks a halo -- faces, and the edges / corners the
+// Mehrstellen stencil reaches -- can come from), through peer memory: publish my
+// epoch in every neighbour's inbox (remote stores over NVLink), then wait until
+// every neighbour has published it in mine.  One tiny kernel instead of a
+// collective.  The wait FAILS CLOSED: after ~10 s without the neighbour it
+// records the epoch in the flag slot and traps, which poisons the context --
+// every later call of this process returns MGB_ECUDA instead of computing on
+// stale halo planes.
+__global__ void k_neighbor_sync(unsigned long long* inbox, unsigned long long* const* peer_inbox,
+    int myrank, int nranks, unsigned long long epoch)
 {
-    if (threadIdx.x != 0) return;
+    const int r = threadIdx.x;
+    if (r >= nranks) return;
+    unsigned long long* dst = peer_inbox[r];
+    if (!dst) return;
     __threadfence_system();
-    if (west_inbox)
-        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(west_inbox + 1), "l"(epoch)
-                     : "memory");
-    if (east_inbox)
-        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(east_inbox + 0), "l"(epoch)
-                     : "memory");
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(dst + myrank), "l"(epoch) : "memory");
     const long long t0 = clock64();
-    for (int side = 0; side < 2; side++)
+    unsigned long long v;
+    do
     {
-        if (!(side == 0 ? west_inbox : east_inbox)) continue;
-        unsigned long long v;
-        do
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(inbox + r) : "memory");
+        if (v < epoch && clock64() - t0 > 20000000000LL)
         {
-            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(inbox + side)
-                         : "memory");
-            if (v < epoch && clock64() - t0 > 4000000000LL)
+            inbox[nranks] = epoch; // which barrier (readable only from a debugger: the trap ends the context)
+            __threadfence_system();
+            __trap();
+        }
+    } while (v < epoch);
+}
+
+// the distinct ranks within one step of `gr`'s coordinates in the split directions
+static void neighbour_ranks(const mgb_grid* gr, int myrank, std::vector<int>& out)
+{
+    out.clear();
+    for (int dx = -1; dx <= 1; dx++)
+        for (int dy = -1; dy <= 1; dy++)
+            for (int dz = -1; dz <= 1; dz++)
             {
-                inbox[2] = epoch; // timed out
-                return;
+                const int d[3] = { dx, dy, dz };
+                bool ok        = dx || dy || dz;
+                for (int k = 0; k < 3 && ok; k++)
+                {
+                    if (!d[k]) continue;
+                    if (gr->nproc[k] == 1) ok = false; // not split: own data
+                    const int c = gr->coord[k] + d[k];
+                    if (gr->bc[k] != 1 && (c < 0 || c >= gr->nproc[k])) ok = false; // domain ends
+                }
+                if (!ok) continue;
+                const int r = rank_of(gr, gr->coord[0] + dx, gr->coord[1] + dy, gr->coord[2] + dz);
+                if (r == myrank) continue;
+                bool seen = false;
+                for (int q : out)
+                    seen = seen || q == r;
+                if (!seen) out.push_back(r);
             }
-        } while (v < epoch);
-    }
 }
 
 int comm_barrier_neighbors(mgb_comm* c, const mgb_grid* gr, cudaStream_t st)
 {
     if (!c || c->nranks == 1) return MGB_OK;
-    const bool per = gr->bc[0] == 1;
-    const int west = (per || gr->coord[0] > 0)
-                         ? rank_of(gr, gr->coord[0] - 1, gr->coord[1], gr->coord[2]) : -1;
-    const int east = (per || gr->coord[0] < gr->nproc[0] - 1)
-                         ? rank_of(gr, gr->coord[0] + 1, gr->coord[1], gr->coord[2]) : -1;
     if (getenv("MGB_NCCL_BARRIER")) return comm_barrier(c, st);
-    if (!c->inbox)
+    int key[9];
+    for (int k = 0; k < 3; k++)
     {
-        // collective, once: every rank publishes its inbox
-        MGB_CUDA(cudaMalloc(&c->inbox, 4 * sizeof(unsigned long long)));
-        MGB_CUDA(cudaMemset(c->inbox, 0, 4 * sizeof(unsigned long long)));
-        if (int rc = mgb_peer_register(c, c->inbox, (void*)st))
+        key[k]     = gr->nproc[k];
+        key[3 + k] = gr->coord[k];
+        key[6 + k] = gr->bc[k];
+    }
+    if (c->nb_mode == 0 || memcmp(key, c->nb_key, sizeof(key)) != 0)
+    {
+        // collective, once per decomposition: every rank publishes its inbox, maps
+        // its neighbours', and all ranks agree on ONE kind of barrier (a rank that
+        // fell back to the all-reduce alone would leave its neighbours spinning)
+        int ok = 1;
+        if (!c->inbox)
         {
-            cudaFree(c->inbox);
-            c->inbox = nullptr;
-            if (rc != MGB_ENOTSUP) return rc;
-            return comm_barrier(c, st);
+            const size_t bytes = (size_t)(c->nranks + 1) * sizeof(unsigned long long);
+            MGB_CUDA(cudaMalloc(&c->inbox, bytes));
+            MGB_CUDA(cudaMemset(c->inbox, 0, bytes));
+            MGB_CUDA(cudaMalloc(&c->d_peer_inbox, c->nranks * sizeof(void*)));
+            const int rc = mgb_peer_register(c, c->inbox, (void*)st);
+            if (rc == MGB_ENOTSUP)
+                ok = 0;
+            else if (rc)
+                return rc;
         }
-        c->nb_west = c->nb_east = -2;
-        // nobody signals before every inbox exists and is zero
-        if (int rc = comm_barrier(c, st)) return rc;
+        std::vector<int> nb;
+        neighbour_ranks(gr, c->rank, nb);
+        std::vector<unsigned long long*> tab(c->nranks, nullptr);
+        for (int r : nb)
+        {
+            tab[r] = ok ? (unsigned long long*)peer_view(c, c->inbox, r) : nullptr;
+            if (!tab[r]) ok = 0;
+        }
+        // agreement (and: nobody signals before every inbox exists and is zero)
+        float* flag = (float*)comm_buf(c, 0, sizeof(float));
+        if (!flag) return MGB_ECUDA;
+        const float mine = ok ? 0.f : 1.f;
+        float total      = 0.f;
+        MGB_CUDA(cudaMemcpyAsync(flag, &mine, sizeof(float), cudaMemcpyHostToDevice, st));
+        MGB_NCCL(nccl()->AllReduce(flag, flag, 1, kNcclFloat32, kNcclSum, c->comm, st));
+        MGB_CUDA(cudaMemcpyAsync(&total, flag, sizeof(float), cudaMemcpyDeviceToHost, st));
+        MGB_CUDA(cudaStreamSynchronize(st));
+        c->nb_mode = total == 0.f ? 1 : 2;
+        memcpy(c->nb_key, key, sizeof(key));
+        c->nb_count = (int)nb.size();
+        if (c->nb_mode == 1)
+            MGB_CUDA(cudaMemcpyAsync(c->d_peer_inbox, tab.data(), c->nranks * sizeof(void*),
+                cudaMemcpyHostToDevice, st));
+        MGB_CUDA(cudaStreamSynchronize(st)); // tab is a local
     }
-    if (c->nb_west != west || c->nb_east != east)
-    {
-        c->west_inbox = west >= 0 ? (unsigned long long*)peer_view(c, c->inbox, west) : nullptr;
-        c->east_inbox = east >= 0 ? (unsigned long long*)peer_view(c, c->inbox, east) : nullptr;
-        if ((west >= 0 && !c->west_inbox) || (east >= 0 && !c->east_inbox))
-            return comm_barrier(c, st);
-        c->nb_west = west;
-        c->nb_east = east;
-    }
+    if (c->nb_mode == 2) return comm_barrier(c, st);
+    if (c->nb_count == 0) return MGB_OK;
     c->epoch++;
-    k_neighbor_sync<<<1, 32, 0, st>>>(c->inbox, c->west_inbox, c->east_inbox, c->epoch);
+    k_neighbor_sync<<<1, ((c->nranks + 31) / 32) * 32, 0, st>>>(
+        c->inbox, c->d_peer_inbox, c->rank, c->nranks, c->epoch);
     MGB_LAUNCHED("k_neighbor_sync");
     return MGB_OK;
 }
@@ -535,16 +584,13 @@ int mgb_comm_check(mgb_comm* c)
 {
     if (int rc = require_device()) return rc;
     MGB_REQUIRE(c, "mgb_comm_check: null communicator");
-    MGB_CUDA(cudaDeviceSynchronize());
-    if (c->inbox)
+    // a neighbour barrier that timed out trapped: the synchronize reports it
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess)
     {
-        unsigned long long flag = 0;
-        MGB_CUDA(cudaMemcpy(&flag, c->inbox + 2, sizeof(flag), cudaMemcpyDeviceToHost));
-        if (flag)
-        {
-            set_error("neighbour barrier %llu timed out: a rank did not reach it", flag);
-            return MGB_ENCCL;
-        }
+        set_error("mgb_comm_check: %s (a neighbour barrier that times out traps: a rank did "
+                  "not reach it)", cudaGetErrorString(e));
+        return MGB_ECUDA;
     }
     return MGB_OK;
 }
@@ -745,6 +791,7 @@ int mgb_comm_destroy(mgb_comm* c)
         mgb_peer_unregister(c, c->inbox);
         cudaFree(c->inbox);
     }
+    if (c->d_peer_inbox) cudaFree(c->d_peer_inbox);
     if (c->map_w) cudaFree(c->map_w);
     if (c->map_e) cudaFree(c->map_e);
     if (c->hmaps) cudaFree(c->hmaps);

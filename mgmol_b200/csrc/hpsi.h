@@ -26,11 +26,19 @@ struct HpsiArgs
     const void* peer_e;
     const int* map_w; // color slot of my color's orbital on that rank (or null)
     const int* map_e;
+    // any px x py x pz decomposition, every halo read in place (mgb_hpsi_peer3d):
+    // nb3d[((dx+1)*3 + (dy+1))*3 + (dz+1)] = the phi block of the rank at coord + (dx,dy,dz)
+    // as mapped here (my own block where a direction is not split), or null = not this path;
+    // vghost: ghosted copy of V (width g, boundaries traded)
+    const void* const* nb3d;
+    const double* vghost;
 };
 
 // path 1: TMA-pipelined x-streaming kernel (hpsi_fused.cu).  Returns
 // MGB_ENOTSUP (without setting an error) when the box is not eligible.
 int hpsi_tma(const HpsiArgs& a, cudaStream_t st);
+// template arguments and tile configuration of the last TMA launch
+const char* hpsi_last_kernel();
 // path 2: generic fused kernel (hpsi_generic.cu), bit-exact.
 int hpsi_generic(const HpsiArgs& a, cudaStream_t st);
 // B u (Mehrstellen right-hand-side operator; mehr2: Laph4MP's B2) on a no-ghost block, bit-exact

@@ -26,6 +26,7 @@
 // in registers.
 #include <cuda.h>
 
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -104,6 +105,20 @@ struct alignas(64) FusedParams
     int nzv, tpo;
     int row_bytes, off_mid, off_hi, tile_bytes, stage_bytes;
     int split_x, first_x, last_x;
+    // ---- PEER == 2: any px x py x pz decomposition, every halo read in place --------
+    // nbmaps[((dx+1)*3 + (dy+1))*3 + (dz+1)][kind]: tensor maps over the block of the
+    // rank at coord + (dx,dy,dz) (myself where a direction is not split: the periodic
+    // wrap); kind 0: box {nz, TY}, 1: {nz, G}, 2: {ZH, TY}, 3: {ZH, G} (ZH = 16 bytes
+    // of z: the z-halo columns).  Device memory, 128-byte aligned.
+    const CUtensorMap* nbmaps;
+    CUtensorMap vg_map; // Mehrstellen: padded ghosted V in the compute type, box {nzp / nvb, TY+2G}
+    int zsplit;         // z halo columns come from boxes (z is split), not from the wrapped index
+    int first_y, last_y, first_z, last_z; // non-periodic AND at the domain's end
+    int per_y, per_z;
+    int zarr_mid, zarr_hi, zarr_bytes, zlo_off; // z-halo arrays inside a tile (16 bytes per row)
+    int vrow_bytes, nvb;                        // padded V tile: row pitch, boxes per plane
+    int pol;      // L2 policy of the phi loads (see the producer)
+    int orb_fast; // blockIdx.x walks the orbital blocks (CTAs of a wave share V tiles in L2)
     double cd[kNumCoef];
     float cf[kNumCoef];
 };
@@ -163,7 +178,7 @@ __device__ __forceinline__ int plane_source(const FusedParams& P, int p, int& xc
 
 // PEER: the x-halo planes of phi are read from the neighbours' blocks (a separate
 // instantiation, so that the single-rank kernel carries none of that code)
-template <typename T, int RY, bool PERIODIC, bool LAP4, int MAXT, bool PEER>
+template <typename T, int RY, bool PERIODIC, bool LAP4, int MAXT, int PEER>
 __global__ void __launch_bounds__(MAXT, 1)
     k_hpsi_tma(const __grid_constant__ FusedParams P)
 {
@@ -176,8 +191,8 @@ __global__ void __launch_bounds__(MAXT, 1)
     uint64_t* empty = full + 8;
 
     const int tid     = threadIdx.x;
-    const int y0      = blockIdx.x * P.TY;
-    const int orb0    = blockIdx.y * P.NB;
+    const int y0      = (P.orb_fast ? blockIdx.y : blockIdx.x) * P.TY;
+    const int orb0    = (P.orb_fast ? blockIdx.x : blockIdx.y) * P.NB;
     const int xb      = blockIdx.z * P.XC;
     const int xe      = min(xb + P.XC, P.nx);
     const int nplanes = (xe - xb) + 2 * G;
@@ -201,8 +216,12 @@ __global__ void __launch_bounds__(MAXT, 1)
         // ------------------------- TMA producer --------------------------
         if (tid != 0) return;
         unsigned char* stages     = smem + kBarBytes;
-        const uint64_t pol_stream = policy_evict_first();
+        // phi is streamed once, but the rows at a tile's edge are also the halo
+        // rows of the neighbouring y tile: pol 1 keeps phi at normal priority, pol 2
+        // additionally pins the (small) halo boxes until the neighbour's load
         const uint64_t pol_keep   = policy_evict_last();
+        const uint64_t pol_stream = P.pol == 0 ? policy_evict_first() : policy_evict_normal();
+        const uint64_t pol_halo   = P.pol == 2 ? pol_keep : pol_stream;
         int norb = P.nfunc - orb0;
         if (norb > P.NB) norb = P.NB;
         int ylo = y0 - G, yhi = y0 + P.TY;
@@ -225,6 +244,62 @@ __global__ void __launch_bounds__(MAXT, 1)
             const int src = plane_source<PERIODIC, G>(P, p, xc);
             if (src == 0)
                 mbar_arrive(&full[stage]);
+            else if constexpr (PEER == 2)
+            {
+                constexpr int ZH = VEC; // 16 bytes of z
+                // which rank's block holds plane p, and at which x coordinate
+                const int dx  = (p < 0) ? 0 : (p >= P.nx ? 2 : 1);
+                const int xcp = (p < 0) ? P.nx + p : (p >= P.nx ? p - P.nx : p);
+                // rows below / above the tile: the y neighbour's last / first rows (the
+                // wrap when y is not split), or out of range (zero fill) at a Dirichlet end
+                const int dyl = (y0 - G < 0 && !P.first_y) ? 0 : 1;
+                const int yl  = (y0 - G < 0) ? (P.first_y ? -G : P.ny - G) : y0 - G;
+                const int dyh = (y0 + P.TY >= P.ny && !P.last_y) ? 2 : 1;
+                const int yh  = (y0 + P.TY >= P.ny) ? (P.last_y ? P.ny : 0) : y0 + P.TY;
+                const int zlc = P.first_z ? -ZH : P.nz - ZH; // z columns below: the low neighbour's last
+                const int zhc = P.last_z ? P.nz : 0;         // above: the high neighbour's first
+                const uint32_t rows   = (uint32_t)(P.TY + 2 * G);
+                // a cross stencil (4th order) never looks at the z neighbours of halo rows
+                const uint32_t psi_tx = rows * (uint32_t)P.row_bytes
+                                        + (P.zsplit ? (LAP4 ? (uint32_t)P.TY : rows) * 32u : 0u);
+                const uint32_t v_tx   = LAP4 ? (uint32_t)(P.TY * P.row_bytes) : rows * (uint32_t)P.vrow_bytes;
+                mbar_arrive_expect_tx(&full[stage], v_tx + (uint32_t)norb * psi_tx);
+                unsigned char* sb = stages + (size_t)stage * P.stage_bytes;
+                if constexpr (LAP4)
+                    tma_load_3d(sb + P.off_mid, &P.v_mid, &full[stage], 0, y0, p, pol_keep);
+                else
+                {
+                    // padded ghosted V (a row = nvb chunks of <= 256 elements, so the box
+                    // lands as whole rows): plane p + G, rows y0 .. y0+TY+2G-1 (ghosted index)
+                    tma_load_4d(sb, &P.vg_map, &full[stage], 0, 0, y0, p + G, pol_keep);
+                }
+                const CUtensorMap* tab = P.nbmaps + dx * 36;
+                for (int o = 0; o < norb; o++)
+                {
+                    unsigned char* tb = sb + (size_t)(1 + o) * P.tile_bytes;
+                    const int fo      = orb0 + o;
+                    // (dy index, y coordinate, tile offset, z-array offset, box kind) of the 3 boxes
+                    const int dyi[3]  = { dyl, 1, dyh };
+                    const int yc[3]   = { yl, y0, yh };
+                    const int to[3]   = { 0, P.off_mid, P.off_hi };
+                    const int zo[3]   = { 0, P.zarr_mid, P.zarr_hi };
+#pragma unroll
+                    for (int b = 0; b < 3; b++)
+                    {
+                        const CUtensorMap* m = tab + dyi[b] * 12;
+                        const int kind       = (b == 1) ? 0 : 1;
+                        tma_load_4d(tb + to[b], m + 1 * 4 + kind, &full[stage], 0, yc[b], xcp, fo,
+                            b == 1 ? pol_stream : pol_halo);
+                        if (P.zsplit && (!LAP4 || b == 1))
+                        {
+                            tma_load_4d(tb + P.zlo_off + zo[b], m + 0 * 4 + 2 + kind, &full[stage],
+                                zlc, yc[b], xcp, fo, pol_halo);
+                            tma_load_4d(tb + P.zlo_off + P.zarr_bytes + zo[b], m + 2 * 4 + 2 + kind,
+                                &full[stage], zhc, yc[b], xcp, fo, pol_halo);
+                        }
+                    }
+                }
+            }
             else
             {
                 mbar_arrive_expect_tx(&full[stage], tx);
@@ -235,7 +310,7 @@ __global__ void __launch_bounds__(MAXT, 1)
                 const CUtensorMap* ph = (src == 1) ? &P.psi_halo : &P.xpsi_halo;
                 int xcp = xc;
                 const int* cmap = nullptr;
-                if (PEER && src == 2)
+                if (PEER == 1 && src == 2)
                 {
                     cmap = (p < 0) ? P.map_w : P.map_e;
                     // read the neighbour's boundary plane straight from its
@@ -252,7 +327,7 @@ __global__ void __launch_bounds__(MAXT, 1)
                     tma_load_3d(sb, vh, &full[stage], 0, ylo, xc, pol_keep);
                     tma_load_3d(sb + P.off_hi, vh, &full[stage], 0, yhi, xc, pol_keep);
                 }
-                if (!PEER || !cmap)
+                if (PEER != 1 || !cmap)
                 {
                     // the issue loop of the producer thread: kept minimal
                     for (int o = 0; o < norb; o++)
@@ -260,9 +335,9 @@ __global__ void __launch_bounds__(MAXT, 1)
                         unsigned char* tb = sb + (size_t)(1 + o) * P.tile_bytes;
                         tma_load_4d(tb + P.off_mid, pm, &full[stage], 0, y0, xcp, orb0 + o,
                             pol_stream);
-                        tma_load_4d(tb, ph, &full[stage], 0, ylo, xcp, orb0 + o, pol_stream);
+                        tma_load_4d(tb, ph, &full[stage], 0, ylo, xcp, orb0 + o, pol_halo);
                         tma_load_4d(tb + P.off_hi, ph, &full[stage], 0, yhi, xcp, orb0 + o,
-                            pol_stream);
+                            pol_halo);
                     }
                 }
                 else
@@ -277,8 +352,8 @@ __global__ void __launch_bounds__(MAXT, 1)
                         int fo = cmap[orb0 + o];
                         if (fo < 0) fo = P.nfunc;
                         tma_load_4d(tb + P.off_mid, pm, &full[stage], 0, y0, xcp, fo, pol_stream);
-                        tma_load_4d(tb, ph, &full[stage], 0, ylo, xcp, fo, pol_stream);
-                        tma_load_4d(tb + P.off_hi, ph, &full[stage], 0, yhi, xcp, fo, pol_stream);
+                        tma_load_4d(tb, ph, &full[stage], 0, ylo, xcp, fo, pol_halo);
+                        tma_load_4d(tb + P.off_hi, ph, &full[stage], 0, yhi, xcp, fo, pol_halo);
                     }
                 }
             }
@@ -332,7 +407,32 @@ __global__ void __launch_bounds__(MAXT, 1)
     const uint32_t zroff = (uint32_t)(zr * (int)sizeof(T));
     // tile-local row index of the zeroed first y layer (Dirichlet), as a
     // position i in this thread's row walk; -100 when it is not in the walk
-    const int izero = (!PERIODIC) ? (0 - (y0 + rr0 - G)) : -100;
+    int izero = (!PERIODIC) ? (0 - (y0 + rr0 - G)) : -100;
+    // PEER == 2 with z split: the G columns left of z = 0 / right of z = nz-1 sit in the
+    // tile's z-halo arrays (16 bytes per row: the neighbour's last / first columns)
+    bool isL = false, isR = false;
+    uint32_t zsA = 0, zsB = 0, zsC = 0, zLb = 0, zRb = 0;
+    if constexpr (PEER == 2)
+    {
+        if (P.zsplit)
+        {
+            isL = z0 == 0;
+            isR = z0 + VEC == P.nz;
+            ml = mr = (CT)1; // a Dirichlet end delivers zero columns (out-of-range box)
+        }
+        if (!PERIODIC)
+        {
+            if (!P.first_z) m0 = (CT)1;
+            if (!P.first_y) izero = -100;
+        }
+        zsA = (rr0 == 0) ? 0u : (uint32_t)(P.zarr_mid + (rr0 - G) * 16);
+        zsB = (uint32_t)(P.zarr_mid + rr0 * 16);
+        zsC = (rr0 + RY == P.TY) ? (uint32_t)P.zarr_hi : (uint32_t)(P.zarr_mid + (rr0 + RY) * 16);
+        // the last G (1: Mehrstellen, 2: 4th order) elements of the low array's row, the
+        // first of the high array's
+        zLb = (uint32_t)(P.zlo_off + 16 - G * (int)sizeof(T));
+        zRb = (uint32_t)(P.zlo_off + P.zarr_bytes);
+    }
 
     const uint32_t stage0 = smem_u32(smem + kBarBytes);
     const uint32_t grp_off = (uint32_t)((1 + grp) * P.tile_bytes);
@@ -379,15 +479,26 @@ __global__ void __launch_bounds__(MAXT, 1)
                     CT Pc[VEC], szc[VEC], wc[VEC], wzc[VEC];
                     CT Pp[VEC], szp[VEC], wp[VEC], wzp[VEC];
                     // psi, z-sum of psi, w = V*psi, z-sum of w of one row
-                    auto load_row = [&](uint32_t ro, int i, CT(&Pq)[VEC],
+                    auto load_row = [&](uint32_t ro, uint32_t zo, int i, CT(&Pq)[VEC],
                                         CT(&szq)[VEC], CT(&wq)[VEC], CT(&wzq)[VEC]) {
                         CT Vq[VEC];
                         lds_vec(pb + ro + zoff, Pq);
-                        lds_vec(vb + ro + zoff, Vq);
-                        CT PL = lds_one<CT>(pb + ro + zloff);
-                        CT PR = lds_one<CT>(pb + ro + zroff);
-                        const CT VL = lds_one<CT>(vb + ro + zloff);
-                        const CT VR = lds_one<CT>(vb + ro + zroff);
+                        uint32_t aL = pb + ro + zloff, aR = pb + ro + zroff;
+                        uint32_t aV = vb + ro + zoff, aVL = vb + ro + zloff, aVR = vb + ro + zroff;
+                        if constexpr (PEER == 2)
+                        {
+                            if (isL) aL = pb + zLb + zo;
+                            if (isR) aR = pb + zRb + zo;
+                            // padded ghosted V tile: row rr0 + i, element z + VEC
+                            aV  = vb + (uint32_t)((rr0 + i) * P.vrow_bytes) + zoff + 16u;
+                            aVL = aV - (uint32_t)sizeof(T);
+                            aVR = aV + 16u;
+                        }
+                        lds_vec(aV, Vq);
+                        CT PL = lds_one<CT>(aL);
+                        CT PR = lds_one<CT>(aR);
+                        const CT VL = lds_one<CT>(aVL);
+                        const CT VR = lds_one<CT>(aVR);
                         if (!PERIODIC)
                         {
                             PL *= ml;
@@ -418,14 +529,15 @@ __global__ void __launch_bounds__(MAXT, 1)
                         }
                     };
                     CT dummy[VEC];
-                    load_row(startA, 0, Pm, szm, wm, dummy);
-                    load_row(startB, 1, Pc, szc, wc, wzc);
-                    uint32_t ro = startB;
+                    load_row(startA, zsA, 0, Pm, szm, wm, dummy);
+                    load_row(startB, zsB, 1, Pc, szc, wc, wzc);
+                    uint32_t ro = startB, zo = zsB;
 #pragma unroll
                     for (int r = 0; r < RY; r++)
                     {
                         ro = (r == RY - 1) ? startC : ro + (uint32_t)rb;
-                        load_row(ro, r + 2, Pp, szp, wp, wzp);
+                        zo = (r == RY - 1) ? zsC : zo + 16u;
+                        load_row(ro, zo, r + 2, Pp, szp, wp, wzp);
                         CT o[VEC];
 #pragma unroll
                         for (int e = 0; e < VEC; e++)
@@ -563,8 +675,14 @@ __global__ void __launch_bounds__(MAXT, 1)
                         load_center(ro_n, inew, W[4]);
                         // z neighbours of the centre row
                         CT L2, L1, R1, R2; // z-2, z-1, z+VEC, z+VEC+1
-                        lds_pair(pb + ro_c + zloff, L2, L1);
-                        lds_pair(pb + ro_c + zroff, R1, R2);
+                        uint32_t aL = pb + ro_c + zloff, aR = pb + ro_c + zroff;
+                        if constexpr (PEER == 2)
+                        {
+                            if (isL) aL = pb + zLb + zsB + (uint32_t)(r * 16);
+                            if (isR) aR = pb + zRb + zsB + (uint32_t)(r * 16);
+                        }
+                        lds_pair(aL, L2, L1);
+                        lds_pair(aR, R1, R2);
                         if (!PERIODIC)
                         {
                             L2 *= ml;
@@ -573,7 +691,7 @@ __global__ void __launch_bounds__(MAXT, 1)
                             R2 *= mr;
                             // a left pair starting at z = 0 holds the zeroed
                             // first layer in its first element
-                            if (z0 == 2) L2 = (CT)0;
+                            if (z0 == 2 && (PEER != 2 || P.first_z)) L2 = (CT)0;
                             if (r + 2 == izero) L2 = L1 = R1 = R2 = (CT)0;
                         }
                         CT Vq[VEC];
@@ -711,6 +829,139 @@ int make_map(CUtensorMap* m, bool f64, const void* base, int rank, int nz,
     return MGB_OK;
 }
 
+static char g_last_kernel[160] = "";
+const char* hpsi_last_kernel() { return g_last_kernel; }
+
+// tensor (z, y, x, orbital) with a box {bz, rows} (bz elements of z)
+static int make_map_box(CUtensorMap* m, bool f64, const void* base, int nz, int ny, int nx,
+    long long ld_elems, int nfunc, int bz, int rows)
+{
+    PFN_encodeTiled enc = get_encode();
+    if (!enc)
+    {
+        set_error("cuTensorMapEncodeTiled entry point not found");
+        return MGB_ECUDA;
+    }
+    const cuuint64_t es = f64 ? 8 : 4;
+    cuuint64_t dims[4]  = { (cuuint64_t)nz, (cuuint64_t)ny, (cuuint64_t)nx,
+        (cuuint64_t)(nfunc > 0 ? nfunc : 1) };
+    cuuint64_t strides[3] = { (cuuint64_t)nz * es, (cuuint64_t)nz * ny * es,
+        (cuuint64_t)ld_elems * es };
+    cuuint32_t box[4]  = { (cuuint32_t)bz, (cuuint32_t)rows, 1, 1 };
+    cuuint32_t estr[4] = { 1, 1, 1, 1 };
+    CUresult r = enc(m, f64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
+        const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+    {
+        set_error("cuTensorMapEncodeTiled failed (%d): box %d x %d of %d %d %d", (int)r, bz, rows,
+            nz, ny, nx);
+        return MGB_ECUDA;
+    }
+    return MGB_OK;
+}
+
+// padded ghosted potential in the compute type: (nzp = nvb chunks, ny+2G rows, nx+2G planes),
+// box = whole rows {chunk, nvb, rows, 1}
+static int make_map_vpad(CUtensorMap* m, bool f64, const void* base, int nzp, int nvb, int nyg,
+    int nxg, int rows)
+{
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) return MGB_ECUDA;
+    const cuuint64_t es = f64 ? 8 : 4;
+    const int chunk     = nzp / nvb;
+    cuuint64_t dims[4]  = { (cuuint64_t)chunk, (cuuint64_t)nvb, (cuuint64_t)nyg, (cuuint64_t)nxg };
+    cuuint64_t strides[3] = { (cuuint64_t)chunk * es, (cuuint64_t)nzp * es,
+        (cuuint64_t)nzp * nyg * es };
+    cuuint32_t box[4]  = { (cuuint32_t)chunk, (cuuint32_t)nvb, (cuuint32_t)rows, 1 };
+    cuuint32_t estr[4] = { 1, 1, 1, 1 };
+    CUresult r = enc(m, f64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
+        const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+    {
+        set_error("cuTensorMapEncodeTiled failed (%d) for the padded potential", (int)r);
+        return MGB_ECUDA;
+    }
+    return MGB_OK;
+}
+
+// ghosted double V (width G) -> padded compute-type V: row pitch nzp = nz + 2 ZH (ZH = 16
+// bytes), element z' = z + ZH; columns no stencil reads are zero
+template <typename T>
+__global__ void k_vpad(int nxg, int nyg, int nz, int G, int nzp, const double* __restrict__ vg,
+    T* __restrict__ out)
+{
+    constexpr int ZH    = 16 / (int)sizeof(T);
+    const long long tot = (long long)nxg * nyg * nzp;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < tot;
+         i += (long long)gridDim.x * blockDim.x)
+    {
+        const int zp       = (int)(i % nzp);
+        const long long rw = i / nzp;
+        const int zg       = zp - ZH + G; // ghosted z index
+        out[i] = (zg >= 0 && zg < nz + 2 * G) ? (T)vg[rw * (nz + 2 * G) + zg] : (T)0;
+    }
+}
+
+// table of the neighbours' tensor maps of the PEER == 2 kernels, cached per block
+struct NbTable
+{
+    const void* nb[27];
+    int nz, ny, nx, nfunc, TY, G, f64;
+    long long ld;
+    CUtensorMap* dev;
+    unsigned long long stamp;
+};
+static NbTable g_nbtab[8];
+static unsigned long long g_nbstamp = 0;
+
+static int nb_table(const void* const* nb, bool f64, int nz, int ny, int nx, long long ld,
+    int nfunc, int TY, int G, cudaStream_t st, const CUtensorMap** out)
+{
+    NbTable* slot = nullptr;
+    for (auto& t : g_nbtab)
+    {
+        if (t.dev && t.nz == nz && t.ny == ny && t.nx == nx && t.nfunc == nfunc && t.TY == TY
+            && t.G == G && t.f64 == (int)f64 && t.ld == ld && memcmp(t.nb, nb, sizeof(t.nb)) == 0)
+        {
+            t.stamp = ++g_nbstamp;
+            *out    = t.dev;
+            return MGB_OK;
+        }
+        if (!slot || t.stamp < slot->stamp) slot = &t;
+    }
+    static CUtensorMap host[27 * 4];
+    memset(host, 0, sizeof(host));
+    const int ZH = f64 ? 2 : 4;
+    for (int r = 0; r < 27; r++)
+    {
+        const int dy = (r / 3) % 3, dz = r % 3;
+        if (!nb[r]) continue;
+        for (int kind = 0; kind < 4; kind++)
+        {
+            const bool zbox = kind >= 2, mid = (kind & 1) == 0;
+            if (zbox != (dz != 1)) continue; // z-halo columns come from the z neighbours only
+            if (mid && dy != 1) continue;    // the tile's own rows never come from a y neighbour
+            if (int rc = make_map_box(&host[r * 4 + kind], f64, nb[r], nz, ny, nx, ld, nfunc,
+                    zbox ? ZH : nz, mid ? TY : G))
+                return rc;
+        }
+    }
+    if (!slot->dev) MGB_CUDA(cudaMalloc(&slot->dev, sizeof(host)));
+    // the table may still be read by a kernel in flight on another configuration
+    MGB_CUDA(cudaStreamSynchronize(st));
+    MGB_CUDA(cudaMemcpy(slot->dev, host, sizeof(host), cudaMemcpyHostToDevice));
+    memcpy(slot->nb, nb, sizeof(slot->nb));
+    slot->nz = nz, slot->ny = ny, slot->nx = nx, slot->nfunc = nfunc, slot->TY = TY, slot->G = G;
+    slot->f64 = f64, slot->ld = ld;
+    slot->stamp = ++g_nbstamp;
+    *out        = slot->dev;
+    return MGB_OK;
+}
+
 struct FusedCfg
 {
     int RY, YG, NB, S, XC;
@@ -718,6 +969,7 @@ struct FusedCfg
 
 static int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
+static bool g_layout_peer3 = false; // lay out the z-halo arrays of the PEER == 2 kernels
 static bool cfg_layout(const FusedCfg& c, int G, int ny, int nz, int es,
     FusedParams& P, size_t& smem)
 {
@@ -737,6 +989,17 @@ static bool cfg_layout(const FusedCfg& c, int G, int ny, int nz, int es,
     P.off_mid     = round_up(G * P.row_bytes, 128);
     P.off_hi      = P.off_mid + round_up(TY * P.row_bytes, 128);
     P.tile_bytes  = P.off_hi + round_up(G * P.row_bytes, 128);
+    if (g_layout_peer3)
+    {
+        // two arrays (columns below z = 0, columns above z = nz-1) of 16 bytes per tile
+        // row, each box at a 128-byte boundary: [G rows][TY rows][G rows]
+        P.zlo_off    = P.tile_bytes;
+        P.zarr_mid   = 128;
+        P.zarr_hi    = 128 + round_up(TY * 16, 128);
+        P.zarr_bytes = P.zarr_hi + 128;
+        P.tile_bytes += 2 * P.zarr_bytes;
+        P.vrow_bytes = P.row_bytes + 32;
+    }
     P.stage_bytes = (c.NB + 1) * P.tile_bytes;
     smem          = (size_t)kBarBytes + (size_t)c.S * P.stage_bytes;
     return smem <= 227 * 1024 && c.S >= 2 && c.S <= 8;
@@ -760,6 +1023,24 @@ static bool choose_cfg(bool lap4, int es, int nx, int ny, int nz, int nfunc,
                 best = c;
                 return true;
             }
+        }
+    }
+    // Boxes whose potential does not stay in L2 (256^3: 134 MB): the x range is cut
+    // into chunks so that a chunk of V (evict_last) serves every orbital from L2 --
+    // CUDA schedules blockIdx.z slowest, i.e. all orbitals x y tiles of one chunk
+    // before the next -- at the price of 2G re-read planes per chunk.  One orbital
+    // per CTA, 8- / 16-row tiles, the deepest ring that fits.  Measured on B200 at
+    // 256^3 (tools/cfg_sweep.py, tools/cfg_try.py; profiles/r02_hpsi_256_cfg.md).
+    if ((size_t)nx * ny * nz * es > ((size_t)48 << 20))
+    {
+        FusedCfg c = { lap4 ? 4 : 8, 2, 1, lap4 ? 4 : 3, lap4 ? 64 : 128 };
+        if (c.XC > nx) c.XC = nx;
+        FusedParams tmp;
+        size_t sm;
+        if (cfg_layout(c, G, ny, nz, es, tmp, sm))
+        {
+            best = c;
+            return true;
         }
     }
     double best_cost = 1e30;
@@ -820,10 +1101,12 @@ static int launch_ry(const FusedParams& P, dim3 grid, int threads, size_t smem,
         MGB_LAUNCHED("k_hpsi_tma");                                            \
     }
 #define MGB_LAUNCH_MAXT(MT)                                                    \
-    if (P.peer)                                                                \
-        MGB_LAUNCH_MAXT_P(MT, true)                                            \
+    if (P.peer == 2)                                                           \
+        MGB_LAUNCH_MAXT_P(MT, 2)                                               \
+    else if (P.peer)                                                           \
+        MGB_LAUNCH_MAXT_P(MT, 1)                                               \
     else                                                                       \
-        MGB_LAUNCH_MAXT_P(MT, false)
+        MGB_LAUNCH_MAXT_P(MT, 0)
     if (threads <= 288)
         MGB_LAUNCH_MAXT(288)
     else if (threads <= 416)
@@ -864,25 +1147,34 @@ int hpsi_tma(const HpsiArgs& a, cudaStream_t st)
     const bool periodic  = gr->bc[0] == 1 && gr->bc[1] == 1 && gr->bc[2] == 1;
     const bool dirichlet = gr->bc[0] == 0 && gr->bc[1] == 0 && gr->bc[2] == 0;
     if (!(periodic || dirichlet)) return MGB_ENOTSUP;
-    if (gr->nproc[1] != 1 || gr->nproc[2] != 1) return MGB_ENOTSUP;
+    const bool peer3 = a.nb3d != nullptr;
+    if (!peer3 && (gr->nproc[1] != 1 || gr->nproc[2] != 1)) return MGB_ENOTSUP;
+    if (peer3 && ((nz * es) % 32 || (!lap4 && !a.vghost))) return MGB_ENOTSUP;
     if (nz > 256 || nz % vec || nz < vec * 2) return MGB_ENOTSUP;
     if (a.ld % vec || a.ldh % vec) return MGB_ENOTSUP;
     if (((uintptr_t)a.phi | (uintptr_t)a.hphi | (uintptr_t)a.vtot) & 15)
         return MGB_ENOTSUP;
     if (nx < G || ny < 2 * G) return MGB_ENOTSUP;
-    const bool split_x = gr->nproc[0] > 1;
-    const bool peer = split_x && a.peer_w && a.peer_e;
-    if (split_x && ((!a.xhalo_phi && !peer) || !a.xhalo_v)) return MGB_ENOTSUP;
-    if (split_x && (((uintptr_t)a.xhalo_phi | (uintptr_t)a.xhalo_v) & 15))
+    const bool split_x = gr->nproc[0] > 1 || peer3;
+    const bool peer = !peer3 && split_x && a.peer_w && a.peer_e;
+    if (!peer3 && split_x && ((!a.xhalo_phi && !peer) || !a.xhalo_v)) return MGB_ENOTSUP;
+    if (!peer3 && split_x && (((uintptr_t)a.xhalo_phi | (uintptr_t)a.xhalo_v) & 15))
         return MGB_ENOTSUP;
+    g_layout_peer3 = peer3;
     if (peer && (((uintptr_t)a.peer_w | (uintptr_t)a.peer_e) & 15)) return MGB_ENOTSUP;
     FusedCfg c;
-    if (!choose_cfg(lap4, es, nx, ny, nz, a.nfunc, c)) return MGB_ENOTSUP;
+    if (!choose_cfg(lap4, es, nx, ny, nz, a.nfunc, c))
+    {
+        g_layout_peer3 = false;
+        return MGB_ENOTSUP;
+    }
 
     FusedParams P;
     memset(&P, 0, sizeof(P));
     size_t smem = 0;
-    if (!cfg_layout(c, G, ny, nz, es, P, smem)) return MGB_ENOTSUP;
+    const bool lay_ok = cfg_layout(c, G, ny, nz, es, P, smem);
+    g_layout_peer3    = false;
+    if (!lay_ok) return MGB_ENOTSUP;
 
     // potential in the compute type
     const void* vsrc  = a.vtot;
@@ -890,7 +1182,7 @@ int hpsi_tma(const HpsiArgs& a, cudaStream_t st)
     if (!f64)
     {
         const size_t npt = (size_t)nx * ny * nz;
-        const size_t nh  = split_x ? (size_t)2 * G * ny * nz : 0;
+        const size_t nh  = (split_x && !peer3) ? (size_t)2 * G * ny * nz : 0;
         float* vf        = (float*)scratch(0, (npt + nh) * sizeof(float));
         if (!vf) return MGB_ECUDA;
         k_f64_to_f32<<<296, 256, 0, st>>>(npt, a.vtot, vf);
@@ -912,7 +1204,39 @@ int hpsi_tma(const HpsiArgs& a, cudaStream_t st)
         return rc;
     if ((rc = make_map(&P.v_mid, f64, vsrc, 3, nz, ny, nx, 0, 0, TY))) return rc;
     if ((rc = make_map(&P.v_halo, f64, vsrc, 3, nz, ny, nx, 0, 0, G))) return rc;
-    if (split_x)
+    if (peer3)
+    {
+        P.peer    = 2;
+        P.zsplit  = gr->nproc[2] > 1 || getenv("MGB_HPSI_FORCE_ZBOXES") != nullptr;
+        P.first_y = gr->bc[1] != 1 && gr->coord[1] == 0;
+        P.last_y  = gr->bc[1] != 1 && gr->coord[1] == gr->nproc[1] - 1;
+        P.first_z = gr->bc[2] != 1 && gr->coord[2] == 0;
+        P.last_z  = gr->bc[2] != 1 && gr->coord[2] == gr->nproc[2] - 1;
+        if ((rc = nb_table(a.nb3d, f64, nz, ny, nx, (long long)a.ld, a.nfunc, TY, G, st, &P.nbmaps)))
+            return rc;
+        if (!lap4)
+        {
+            // the potential with its halo: the caller's ghosted copy, padded to whole
+            // 16-byte columns, in the compute type
+            const int ZH  = 16 / es;
+            const int nzp = nz + 2 * ZH;
+            P.nvb         = nzp > 256 ? 2 : 1;
+            const size_t n = (size_t)(nx + 2 * G) * (ny + 2 * G) * nzp;
+            void* vp       = scratch(7, n * es);
+            if (!vp) return MGB_ECUDA;
+            if (f64)
+                k_vpad<double><<<592, 256, 0, st>>>(nx + 2 * G, ny + 2 * G, nz, G, nzp, a.vghost,
+                    (double*)vp);
+            else
+                k_vpad<float><<<592, 256, 0, st>>>(nx + 2 * G, ny + 2 * G, nz, G, nzp, a.vghost,
+                    (float*)vp);
+            MGB_LAUNCHED("k_vpad");
+            if ((rc = make_map_vpad(&P.vg_map, f64, vp, nzp, P.nvb, ny + 2 * G, nx + 2 * G,
+                     TY + 2 * G)))
+                return rc;
+        }
+    }
+    else if (split_x)
     {
         const long long hs = (long long)2 * G * ny * nz;
         if (peer)
@@ -961,6 +1285,8 @@ int hpsi_tma(const HpsiArgs& a, cudaStream_t st)
     P.split_x = split_x;
     P.first_x = gr->coord[0] == 0;
     P.last_x  = gr->coord[0] == gr->nproc[0] - 1;
+    P.per_y   = gr->bc[1] == 1;
+    P.per_z   = gr->bc[2] == 1;
     const double inv12 = 1. / 12.;
     const double i2[3] = { 1. / (gr->h[0] * gr->h[0]), 1. / (gr->h[1] * gr->h[1]),
         1. / (gr->h[2] * gr->h[2]) };
@@ -986,6 +1312,29 @@ int hpsi_tma(const HpsiArgs& a, cudaStream_t st)
         (unsigned)((nx + c.XC - 1) / c.XC));
     if (grid.y > 65535 || grid.z > 65535) return MGB_ENOTSUP;
     const int threads = 32 + c.NB * P.tpo;
+    snprintf(g_last_kernel, sizeof(g_last_kernel),
+        "k_hpsi_tma<%s,RY=%d,PERIODIC=%d,LAP4=%d,MAXT=%d,PEER=%d> YG=%d NB=%d S=%d XC=%d",
+        f64 ? "double" : "float", c.RY, periodic ? 1 : 0, lap4 ? 1 : 0,
+        threads <= 288 ? 288 : (threads <= 416 ? 416 : 544), P.peer, c.YG, c.NB, c.S, c.XC);
+    // A potential that does not stay in L2 (256^3 doubles = 134 MB) is fetched
+    // from HBM once per wave when the CTAs of a wave work on the same y tile
+    // of different orbitals; a resident one (128^3) keeps the y-fast order.
+    {
+        const size_t vbytes = (size_t)nx * ny * nz * es;
+        int of              = 0; // orbital-fast order loses the neighbour tiles' halo rows from L2 (measured)
+        (void)vbytes;
+        if (const char* env = getenv("MGB_HPSI_ORDER")) of = atoi(env);
+        P.pol = 1; // measured: +4 % at 128^3 over evict_first (halo rows of the neighbour tile hit L2)
+        if (const char* env = getenv("MGB_HPSI_POL")) P.pol = atoi(env);
+        if (of)
+        {
+            P.orb_fast = 1;
+            const unsigned t = grid.x;
+            grid.x           = grid.y;
+            grid.y           = t;
+            if (grid.y > 65535) return MGB_ENOTSUP;
+        }
+    }
 
     if (f64)
     {

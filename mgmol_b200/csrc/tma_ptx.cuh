@@ -52,6 +52,12 @@ __device__ __forceinline__ uint64_t policy_evict_first()
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
     return p;
 }
+__device__ __forceinline__ uint64_t policy_evict_normal()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
 __device__ __forceinline__ uint64_t policy_evict_last()
 {
     uint64_t p;

@@ -321,9 +321,16 @@ class Lap:
             _p(xhalo_phi) if xhalo_phi is not None else None, _stream()))
         return bphi
 
-    def applyWithPotPeer(self, comm, phi, vtot, hphi, xhalo_v):
-        """applyWithPot on an x-split domain, the neighbours' boundary planes of
-        phi read directly from their (registered) blocks over NVLink."""
+    def applyWithPotPeer(self, comm, phi, vtot, hphi, xhalo_v=None, vghost=None):
+        """applyWithPot on a decomposed domain, the neighbours' boundary layers of
+        phi read directly from their (registered) blocks over NVLink.  x slabs take
+        the potential's 2g packed x planes (xhalo_v); any px x py x pz decomposition
+        takes a ghosted copy of V whose boundaries were traded (vghost)."""
+        if vghost is not None:
+            check(lib().mgb_hpsi_peer3d(
+                comm.handle, self.type_, _dt(phi), self.grid_.ref(), _p(phi), self.grid_.size(),
+                _p(vtot), _p(vghost), _p(hphi), self.grid_.size(), phi.shape[0], _stream()))
+            return hphi
         check(lib().mgb_hpsi_peer(
             comm.handle, self.type_, _dt(phi), self.grid_.ref(), _p(phi), self.grid_.size(),
             _p(vtot), _p(hphi), self.grid_.size(), phi.shape[0], _p(xhalo_v), _stream()))
@@ -481,6 +488,38 @@ class Orbitals:
         check(lib().mgb_gemm_tn(_dt(self.psi_), n, n, self.grid_.size(),
                                 self.grid_.vel(), _p(self.psi_), self.grid_.size(),
                                 _p(a), self.grid_.size(), 0.0, _p(ss), n, _stream()))
+        if comm is not None:
+            comm.allreduce(ss)
+        return ss.t()
+
+    def addDotWithNcol2Matrix(self, other, mat, comm=None):
+        """mat += vel * Phi^T A summed over the ranks
+        (src/ExtendedGridOrbitals.cc:1704-1752); mat indexed [i, j] = <phi_i, a_j>."""
+        mat += self.computeLocalProduct(other, comm)
+        return mat
+
+    def computeMatB(self, lapOper, orbitals=None, comm=None, work=None, xhalo_phi=None,
+                    bcolor=32):
+        """matB[i, j] = vel * <orbitals_i | B | this_j> (src/ExtendedGridOrbitals.cc:901-967),
+        B = Lap::rhs (the Mehrstellen right-hand-side stencil, the identity otherwise), in
+        blocks of `bcolor` columns through a work block like the reference's (32 there).
+        work: an Orbitals whose storage may be used (>= bcolor orbitals)."""
+        o = self if orbitals is None else orbitals
+        n, m = self.numst_, o.numst_
+        npt = self.grid_.size()
+        if work is not None:
+            bcolor = min(max(bcolor, 1), work.psi_.shape[0])
+            w = work.psi_[:bcolor]
+        else:
+            bcolor = min(bcolor, n)
+            w = torch.empty((bcolor,) + self.grid_.shape(), dtype=self.psi_.dtype, device="cuda")
+        ss = torch.empty((n, m), dtype=torch.float64, device="cuda")  # column-major m x n
+        for j0 in range(0, n, bcolor):
+            nf = min(bcolor, n - j0)
+            xh = xhalo_phi[j0:j0 + nf] if xhalo_phi is not None else None
+            lapOper.rhs(self.psi_[j0:j0 + nf], w[:nf], xh)
+            check(lib().mgb_gemm_tn(_dt(self.psi_), m, nf, npt, self.grid_.vel(), _p(o.psi_), npt,
+                                    _p(w), npt, 0.0, _p(ss[j0:]), m, _stream()))
         if comm is not None:
             comm.allreduce(ss)
         return ss.t()
@@ -706,9 +745,12 @@ class Hamiltonian:
     def lapOper(self):
         return self.lapOper_
 
-    def applyLocal(self, phi, force=False, xhalo_phi=None, xhalo_v=None, peer_comm=None):
-        """src/Hamiltonian.cc:43-83.  peer_comm: x-split domain whose orbital
-        block is registered for direct peer reads (Communicator.register)."""
+    def applyLocal(self, phi, force=False, xhalo_phi=None, xhalo_v=None, peer_comm=None,
+                   vghost=None):
+        """src/Hamiltonian.cc:43-83.  peer_comm: decomposed domain whose orbital
+        block is registered for direct peer reads (Communicator.register); the
+        potential's halo comes as xhalo_v (x slabs: the 2g packed planes) or as vghost
+        (any decomposition: a ghosted copy of V with traded boundaries)."""
         assert phi.getIterativeIndex() >= 0 and self.pot_.getIterativeIndex() >= 0
         if (self.hlphi_ is None or self.hlphi_.psi_.shape != phi.psi_.shape
                 or self.hlphi_.psi_.dtype != phi.psi_.dtype):
@@ -718,12 +760,17 @@ class Hamiltonian:
         if force or new_index != self.itindex_:
             if peer_comm is not None:
                 self.lapOper_.applyWithPotPeer(peer_comm, phi.psi_, self.pot_.vtot(),
-                                               self.hlphi_.psi_, xhalo_v)
+                                               self.hlphi_.psi_, xhalo_v, vghost)
             else:
                 self.lapOper_.applyWithPot(phi.psi_, self.pot_.vtot(), self.hlphi_.psi_,
                                            xhalo_phi, xhalo_v)
             self.itindex_ = new_index
         return self.hlphi_
+
+    def addHlocal2matrix(self, phi1, phi2, hij, force=False, comm=None):
+        """hij += Phi1^T H_loc Phi2 (src/Hamiltonian.cc:163-212)."""
+        self.applyLocal(phi2, force)
+        return phi1.addDotWithNcol2Matrix(self.hlphi_, hij, comm)
 
     def addHlocalij(self, phi1, phi2=None, comm=None):
         """Phi1^T H_loc Phi2 (src/Hamiltonian.cc:214-239)."""

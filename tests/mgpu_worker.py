@@ -90,6 +90,46 @@ def main():
                 except H.MgbError as e:
                     check("hpsi x-split peer reads %s lap%d bc%s: %s" % (dt, lap, bc, e), False)
 
+    # ---- fused H psi on every decomposition of the ranks over x, y, z: all halos (faces,
+    # and the edge lines the Mehrstellen stencil reaches) read in place from the
+    # neighbours' blocks; bit-identical to the single-rank kernel on the global box
+    decomps = {2: [(1, 1, 2), (1, 2, 1), (2, 1, 1)],
+               4: [(1, 2, 2), (2, 2, 1), (2, 1, 2), (1, 1, 4), (1, 4, 1)],
+               8: [(2, 2, 2), (1, 2, 4), (4, 2, 1), (2, 4, 1)]}.get(world, [(world, 1, 1)])
+    for nproc in decomps:
+        for dt in (torch.float64, torch.float32):
+            for lap in (0, 2):
+                g = H.ghosts_for(lap)
+                for bc in ((1, 1, 1), (0, 0, 0)):
+                    gdims = (8 * nproc[0], 16 * nproc[1], 32 * nproc[2])
+                    ll = (0.25 * gdims[0], 0.3 * gdims[1], 0.2 * gdims[2])
+                    full = (torch.rand((N,) + gdims, generator=gen, device="cuda",
+                                       dtype=torch.float64) - 0.5).to(dt)
+                    v = torch.rand(gdims, generator=gen, device="cuda", dtype=torch.float64) - 0.7
+                    ggrid = H.Grid(gdims, ll, g, bc)
+                    ref = torch.empty_like(full)
+                    H.LapFactory.createLap(ggrid, lap).applyWithPot(full, v, ref)
+                    coord = cart_coords(rank, nproc)
+                    box = local_box(gdims, nproc, coord)
+                    grid = H.Grid(gdims, ll, g, bc, nproc, coord)
+                    mine = full[(slice(None),) + box].contiguous()
+                    vmine = v[box].contiguous()
+                    gv = H.GridFuncVector(grid, 1, torch.float64)
+                    gv.assign(vmine[None].contiguous())
+                    comm.trade_boundaries(gv)
+                    try:
+                        comm.register(mine)
+                        out = torch.full_like(mine, float("nan"))
+                        op = H.LapFactory.createLap(grid, lap)
+                        op.applyWithPotPeer(comm, mine, vmine, out, vghost=gv.data)
+                        op.applyWithPotPeer(comm, mine, vmine, out, vghost=gv.data)
+                        check("hpsi %dx%dx%d in-place halos %s lap%d bc%s" % (nproc + (dt, lap, bc)),
+                              torch.equal(out, ref[(slice(None),) + box]))
+                        comm.unregister(mine)
+                    except H.MgbError as e:
+                        check("hpsi %dx%dx%d in-place halos %s lap%d bc%s: %s"
+                              % (nproc + (dt, lap, bc, e)), False)
+
     # ---- ghosted Y -> Z -> X exchange on every 2-way / n-way split ---------------
     for dt in (torch.float64, torch.float32):
         for gw in (1, 2):

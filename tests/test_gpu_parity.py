@@ -76,6 +76,49 @@ def test_hpsi_tma_and_generic(H, port, dt, lap_type, bc, dims, N):
     assert err <= TOL[dt], "TMA kernel rel err %g" % err
 
 
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("lap_type", [0, 2])
+@pytest.mark.parametrize("bc", [(1, 1, 1), (0, 0, 0)])
+@pytest.mark.parametrize("zboxes", [False, True])
+@pytest.mark.parametrize("dims,N", [((16, 24, 32), 5), ((8, 16, 64), 3), ((32, 32, 128), 2)])
+def test_hpsi_peer3d_self_neighbours(H, port, dt, lap_type, bc, zboxes, dims, N):
+    """mgb_hpsi_peer3d on one rank: every one of the 26 neighbours is the box itself (the
+    periodic wrap) or beyond a Dirichlet end, so the kernel's halo machinery -- boxes from
+    the neighbour table, the z-halo column arrays, the padded ghosted potential -- runs
+    without a second GPU and must reproduce mgb_hpsi's TMA kernel bit for bit (same
+    arithmetic per point) and the oracle within the path's tolerance."""
+    from mgmol_b200._lib import lib, check
+    ll = (4.0, 6.0, 8.0)
+    phi = synthetic_orbitals(N, dims, dt)
+    v = synthetic_potential(dims)
+    g = H.ghosts_for(lap_type)
+    grid = H.Grid(dims, ll, g, bc)
+    dphi, dv = dev(phi), dev(v)
+    ref = torch.empty_like(dphi)
+    check(lib().mgb_hpsi_force_path(1))
+    try:
+        H.LapFactory.createLap(grid, lap_type).applyWithPot(dphi, dv, ref)
+    finally:
+        lib().mgb_hpsi_force_path(0)
+    gv = H.GridFuncVector(grid, 1, torch.float64)
+    gv.assign(dv[None].contiguous())
+    gv.trade_boundaries()
+    out = torch.full_like(dphi, float("nan"))
+    if zboxes:
+        os.environ["MGB_HPSI_FORCE_ZBOXES"] = "1"
+    try:
+        class _NoComm:
+            handle = None
+        H.LapFactory.createLap(grid, lap_type).applyWithPotPeer(_NoComm, dphi, dv, out,
+                                                               vghost=gv.data)
+    finally:
+        os.environ.pop("MGB_HPSI_FORCE_ZBOXES", None)
+    assert "PEER=2" in lib().mgb_hpsi_last_kernel().decode()
+    assert torch.equal(out, ref)
+    exp = port.hpsi(lap_type, phi, v, ll, bc)
+    assert rel_inf(host(out), exp) <= TOL[dt]
+
+
 @pytest.mark.parametrize("cfg", ["8,1,1,2,0", "8,1,2,3,0", "4,2,2,2,7", "4,1,3,2,5",
                                  "8,2,1,2,16", "4,4,1,4,3"])
 @pytest.mark.parametrize("dt", [np.float64, np.float32])
