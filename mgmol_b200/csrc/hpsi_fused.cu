@@ -915,10 +915,10 @@ struct NbTable
     CUtensorMap* dev;
     unsigned long long stamp;
 };
-static NbTable g_nbtab[8];
+static NbTable g_nbtab[48];
 static unsigned long long g_nbstamp = 0;
 
-static int nb_table(const void* const* nb, bool f64, int nz, int ny, int nx, long long ld,
+int nb_table(const void* const* nb, bool f64, int nz, int ny, int nx, long long ld,
     int nfunc, int TY, int G, cudaStream_t st, const CUtensorMap** out)
 {
     NbTable* slot = nullptr;

@@ -60,6 +60,14 @@ struct alignas(64) JacobiParams
     CUtensorMap pw_mid, pw_halo; // west / east neighbour's source block (peer
     CUtensorMap pe_mid, pe_halo; // memory over NVLink) on an x-split domain
     int split_x, have_w, have_e;
+    // P3: any px x py x pz decomposition, every halo read in place.  nbmaps[dx*36 + dy*12 +
+    // dz*4 + kind] (dx, dy, dz in 0..2 = -1, 0, +1): tensor maps over the source block of the
+    // rank at coord + (dx,dy,dz) (myself across a direction that is not split); kind 0: box
+    // {nz, TY}, 1: {nz, G}, 2: {4, TY}, 3: {4, G} (16 bytes of z: the z-halo columns)
+    const CUtensorMap* nbmaps;
+    int zsplit;                  // z-halo columns come from boxes
+    int end_lo[3], end_hi[3];    // non-periodic direction and this rank holds the domain's end
+    int zlo_off, zarr_mid, zarr_hi, zarr_bytes; // z-halo arrays inside a tile
     const int* map_w;            // color slot of my color's orbital on that rank
     const int* map_e;            // (-1: absent), or null = same slot
     const float* f;              // right-hand side
@@ -116,7 +124,7 @@ __device__ __forceinline__ float dd(float a, float b, float c)
 // chunk.  Warp 0 is the TMA producer; the consumers keep the 2G+1 planes a
 // stencil needs resident in a ring of S stages and read every tap from shared
 // memory.
-template <int LAP, int RY, bool SCALE, int MAXT, bool MASK>
+template <int LAP, int RY, bool SCALE, int MAXT, bool MASK, bool P3>
 __global__ void __launch_bounds__(MAXT, 1) k_mg_jacobi(const __grid_constant__ JacobiParams P)
 {
     constexpr int G  = (LAP == kLap4) ? 2 : 1;
@@ -161,12 +169,61 @@ __global__ void __launch_bounds__(MAXT, 1) k_mg_jacobi(const __grid_constant__ J
             if (ylo < 0) ylo += P.ny;
             if (yhi >= P.ny) yhi -= P.ny;
         }
-        const uint32_t tx = (uint32_t)norb * (uint32_t)((P.TY + 2 * G) * P.row_bytes);
+        uint32_t tx = (uint32_t)norb * (uint32_t)((P.TY + 2 * G) * P.row_bytes);
+        // only the 19-point operator looks at the z neighbours of halo rows
+        constexpr bool ZALL = (LAP == kLapMehr);
+        if (P3 && P.zsplit) tx += (uint32_t)norb * (uint32_t)((ZALL ? P.TY + 2 * G : P.TY) * 32);
         int stage = 0;
         uint32_t par = 0;
         for (int it = 0; it < nplanes; it++)
         {
             int xc = xb - G + it;
+            if constexpr (P3)
+            {
+                // the rank holding plane xc and the coordinate there; beyond a Dirichlet
+                // end the box stays out of range on my own block (zero fill)
+                const int dx  = (xc < 0 && !P.end_lo[0]) ? 0 : ((xc >= P.nx && !P.end_hi[0]) ? 2 : 1);
+                const int xcp = dx == 0 ? xc + P.nx : (dx == 2 ? xc - P.nx : xc);
+                const int dyl = (y0 - G < 0 && !P.end_lo[1]) ? 0 : 1;
+                const int yl  = (y0 - G < 0 && !P.end_lo[1]) ? P.ny - G : y0 - G;
+                const int dyh = (y0 + P.TY >= P.ny && !P.end_hi[1]) ? 2 : 1;
+                const int yh  = (y0 + P.TY >= P.ny && !P.end_hi[1]) ? 0 : y0 + P.TY;
+                const int zlc = P.end_lo[2] ? -4 : P.nz - 4;
+                const int zhc = P.end_hi[2] ? P.nz : 0;
+                mbar_wait(&empty[stage], par ^ 1u);
+                mbar_arrive_expect_tx(&full[stage], tx);
+                unsigned char* sb      = stages + (size_t)stage * P.stage_bytes;
+                const CUtensorMap* tab = P.nbmaps + dx * 36;
+                const int dyi[3]       = { dyl, 1, dyh };
+                const int yc[3]        = { yl, y0, yh };
+                const int to[3]        = { 0, P.off_mid, P.off_hi };
+                const int zo[3]        = { 0, P.zarr_mid, P.zarr_hi };
+                for (int o = 0; o < norb; o++)
+                {
+                    unsigned char* tb = sb + (size_t)o * P.tile_bytes;
+                    const int fo      = orb0 + o;
+#pragma unroll
+                    for (int b = 0; b < 3; b++)
+                    {
+                        const CUtensorMap* m = tab + dyi[b] * 12;
+                        const int kind       = (b == 1) ? 0 : 1;
+                        tma_load_4d(tb + to[b], m + 4 + kind, &full[stage], 0, yc[b], xcp, fo, pol);
+                        if (P.zsplit && (ZALL || b == 1))
+                        {
+                            tma_load_4d(tb + P.zlo_off + zo[b], m + 2 + kind, &full[stage], zlc,
+                                yc[b], xcp, fo, pol);
+                            tma_load_4d(tb + P.zlo_off + P.zarr_bytes + zo[b], m + 8 + 2 + kind,
+                                &full[stage], zhc, yc[b], xcp, fo, pol);
+                        }
+                    }
+                }
+                if (++stage == S)
+                {
+                    stage = 0;
+                    par ^= 1u;
+                }
+                continue;
+            }
             const CUtensorMap* mm = &P.in_mid;
             const CUtensorMap* mh = &P.in_halo;
             const int* cmap       = nullptr;
@@ -268,6 +325,41 @@ __global__ void __launch_bounds__(MAXT, 1) k_mg_jacobi(const __grid_constant__ J
     const uint32_t zoff  = (uint32_t)(z0 * 4);
     const uint32_t zloff = (uint32_t)(zl * 4);
     const uint32_t zroff = (uint32_t)(zr * 4);
+    // P3 with z split: the G columns left of z = 0 / right of z = nz-1 sit in the tile's
+    // z-halo arrays (16 bytes per tile row); per walked row the offset of its entry
+    bool isL = false, isR = false;
+    uint32_t zrow[P3 ? NW : 1];
+    uint32_t zLb = 0, zRb = 0;
+    if constexpr (P3)
+    {
+        if (P.zsplit)
+        {
+            isL = z0 == 0;
+            isR = z0 + 4 == P.nz;
+            ml = mr = 1.f; // a Dirichlet end delivers zero columns (out-of-range box)
+        }
+#pragma unroll
+        for (int i = 0; i < NW; i++)
+        {
+            const int t = rr0 - G + i;
+            zrow[i]     = (uint32_t)(t < 0 ? (t + G) * 16
+                                           : (t < P.TY ? P.zarr_mid + t * 16
+                                                       : P.zarr_hi + (t - P.TY) * 16));
+        }
+        zLb = (uint32_t)(P.zlo_off + 16 - G * 4);
+        zRb = (uint32_t)(P.zlo_off + P.zarr_bytes);
+    }
+    // address of the left / right z neighbours of walked row i in the tile at `base`
+    auto zl_addr = [&](uint32_t base, int i) -> uint32_t {
+        if constexpr (P3)
+            if (isL) return base + zLb + zrow[i];
+        return base + rowoff[i] + zloff;
+    };
+    auto zr_addr = [&](uint32_t base, int i) -> uint32_t {
+        if constexpr (P3)
+            if (isR) return base + zRb + zrow[i];
+        return base + rowoff[i] + zroff;
+    };
 
     const uint32_t stage0  = smem_u32(smem + kMgBarBytes);
     const uint32_t grp_off = (uint32_t)(grp * P.tile_bytes);
@@ -443,8 +535,8 @@ __global__ void __launch_bounds__(MAXT, 1) k_mg_jacobi(const __grid_constant__ J
                         ldrow(tb[2] + rowoff[r + 4] + zoff, W[4]);
                         const uint32_t ro = rowoff[r + 2];
                         float L2, L1, R1, R2;
-                        lds2(tb[2] + ro + zloff, L2, L1);
-                        lds2(tb[2] + ro + zroff, R1, R2);
+                        lds2(zl_addr(tb[2], r + 2), L2, L1);
+                        lds2(zr_addr(tb[2], r + 2), R1, R2);
                         L2 *= ml;
                         L1 *= ml;
                         R1 *= mr;
@@ -490,8 +582,8 @@ __global__ void __launch_bounds__(MAXT, 1) k_mg_jacobi(const __grid_constant__ J
                     {
                         ldrow(tb[1] + rowoff[r + 2] + zoff, W[2]);
                         const uint32_t ro = rowoff[r + 1];
-                        const float L = ld1(tb[1] + ro + zloff, ml);
-                        const float R = ld1(tb[1] + ro + zroff, mr);
+                        const float L = ld1(zl_addr(tb[1], r + 1), ml);
+                        const float R = ld1(zr_addr(tb[1], r + 1), mr);
                         float Xm[4], Xp[4];
                         ldrow(tb[0] + ro + zoff, Xm);
                         ldrow(tb[2] + ro + zoff, Xp);
@@ -526,8 +618,8 @@ __global__ void __launch_bounds__(MAXT, 1) k_mg_jacobi(const __grid_constant__ J
                     auto load = [&](int d, int slot, int i) {
                         const uint32_t a = tb[d] + rowoff[i];
                         ldrow(a + zoff, V[d][slot]);
-                        L[d][slot] = ld1(a + zloff, ml);
-                        R[d][slot] = ld1(a + zroff, mr);
+                        L[d][slot] = ld1(zl_addr(tb[d], i), ml);
+                        R[d][slot] = ld1(zr_addr(tb[d], i), mr);
                     };
 #pragma unroll
                     for (int d = 0; d < 3; d++)
@@ -703,6 +795,101 @@ __global__ void k_mg_restrict(int nxc, int nyc, int nzc, int perx, int pery, int
     *reinterpret_cast<float4*>(C) = make_float4(r[0], r[1], r[2], r[3]);
 }
 
+
+// the blocks a transfer kernel may touch on a decomposed box: index bit 2 = across x,
+// bit 1 = across y, bit 0 = across z (the low side for the restriction, the high side for
+// the prolongation); my own block where a direction is not split (periodic wrap)
+struct Nb8
+{
+    const float* p[8];
+};
+
+// k_mg_restrict on any px x py x pz decomposition: fine plane / row / column -1 is read in
+// place from the low neighbour's block (its last one); beyond a Dirichlet end it weighs 0
+__global__ void k_mg_restrict3(int nxc, int nyc, int nzc, int endx, int endy, int endz, Nb8 nb,
+    long long ldf, float* __restrict__ coarse, long long ldc, MaskView mask, int f0)
+{
+    const int nzv = nzc >> 2;
+    const int tz  = (nzv + blockDim.x - 1) / blockDim.x;
+    const int kv  = (blockIdx.x % tz) * blockDim.x + threadIdx.x;
+    const int j   = (blockIdx.x / tz) * blockDim.y + threadIdx.y;
+    const int i   = blockIdx.y;
+    const int f   = blockIdx.z;
+    if (kv >= nzv || j >= nyc) return;
+    const int nx = 2 * nxc, ny = 2 * nyc, nz = 2 * nzc;
+    const long long fo = (long long)(f + f0) * ldf;
+    const int k0 = kv * 4;
+    float acc[4] = { 0.f, 0.f, 0.f, 0.f };
+#pragma unroll
+    for (int dx = -1; dx <= 1; dx++)
+    {
+        int x = 2 * i + dx, bx = 0;
+        float wx = (dx == 0) ? 2.f : 1.f;
+        if (x < 0)
+        {
+            if (endx)
+                wx = 0.f, x = 0;
+            else
+                x += nx, bx = 4;
+        }
+        float ay[4] = { 0.f, 0.f, 0.f, 0.f };
+#pragma unroll
+        for (int dy = -1; dy <= 1; dy++)
+        {
+            int y = 2 * j + dy, by = 0;
+            float wy = (dy == 0) ? 2.f : 1.f;
+            if (y < 0)
+            {
+                if (endy)
+                    wy = 0.f, y = 0;
+                else
+                    y += ny, by = 2;
+            }
+            const long long ro = fo + ((long long)x * ny + y) * nz;
+            const float* row   = nb.p[bx | by] + ro;
+            const float4 a = __ldg(reinterpret_cast<const float4*>(row + 2 * k0));
+            const float4 b = __ldg(reinterpret_cast<const float4*>(row + 2 * k0 + 4));
+            float lft;
+            if (k0 > 0)
+                lft = __ldg(row + 2 * k0 - 1);
+            else
+                lft = endz ? 0.f : __ldg(nb.p[bx | by | 1] + ro + nz - 1);
+            const float t0 = (lft + a.y) + 2.f * a.x;
+            const float t1 = (a.y + a.w) + 2.f * a.z;
+            const float t2 = (a.w + b.y) + 2.f * b.x;
+            const float t3 = (b.y + b.w) + 2.f * b.z;
+            ay[0] = fmaf(wy, t0, ay[0]);
+            ay[1] = fmaf(wy, t1, ay[1]);
+            ay[2] = fmaf(wy, t2, ay[2]);
+            ay[3] = fmaf(wy, t3, ay[3]);
+        }
+#pragma unroll
+        for (int e = 0; e < 4; e++)
+            acc[e] = fmaf(wx, ay[e], acc[e]);
+    }
+    float* C = coarse + (long long)f * ldc + ((long long)i * nyc + j) * nzc + k0;
+    float r[4] = { acc[0] * 0.015625f, acc[1] * 0.015625f, acc[2] * 0.015625f,
+        acc[3] * 0.015625f };
+    if (mask.off)
+    {
+        const int iloc = i / mask.sub0;
+        const int mo   = __ldg(mask.off + (long long)f * mask.subdivx + iloc);
+        if (mo == -2)
+            r[0] = r[1] = r[2] = r[3] = 0.f;
+        else if (mo >= 0)
+        {
+            const float4 m = __ldg(reinterpret_cast<const float4*>(mask.pool
+                + (long long)mo * mask.slab
+                + ((long long)(i - iloc * mask.sub0) * nyc + j) * nzc + k0));
+            r[0] = mask_apply(mask.op, r[0], m.x);
+            r[1] = mask_apply(mask.op, r[1], m.y);
+            r[2] = mask_apply(mask.op, r[2], m.z);
+            r[3] = mask_apply(mask.op, r[3], m.w);
+        }
+    }
+    *reinterpret_cast<float4*>(C) = make_float4(r[0], r[1], r[2], r[3]);
+}
+
 // ---------------------------------------------------------------------------
 // v -= P e: trilinear prolongation in the reference's float operand order
 // (MGkernels.cc:60-198 collapse to a closed form per fine point, cf.
@@ -710,10 +897,11 @@ __global__ void k_mg_restrict(int nxc, int nyc, int nzc, int perx, int pery, int
 // handles 4 consecutive fine z.  The result is stored with zero low layers
 // where requested.
 // ---------------------------------------------------------------------------
+template <bool P3>
 __global__ void k_mg_prolong_correct(int nx, int ny, int nz, int perx, int pery, int perz,
     int zlx, int zly, int zlz, const float* __restrict__ coarse, long long ldc,
     float* __restrict__ v, long long ldv, MaskView mask, const float* __restrict__ coarse_e,
-    const int* __restrict__ map_e, int f0)
+    const int* __restrict__ map_e, int f0, Nb8 nb)
 {
     // one thread: the 2 x 2 x 4 fine brick above coarse (cx0, cy0, cz0..cz0+1); the
     // four coarse rows it needs are loaded once and shared by the 16 fine points
@@ -731,7 +919,28 @@ __global__ void k_mg_prolong_correct(int nx, int ny, int nz, int perx, int pery,
     float mx = 1.f, my = 1.f, mz = 1.f;
     const float* C   = coarse + (long long)f * ldc;
     const float* Cx1 = C; // block holding coarse plane cx1
-    if (cx1 == nxc)
+    int bx = 0, by = 0, bz = 0; // P3: which neighbour holds plane cx1 / row cy1 / column cz2
+    if constexpr (P3)
+    {
+        // perx / pery / perz here mean "not a Dirichlet end of the domain": coarse plane
+        // nxc, row nyc, column nzc are the high neighbour's first ones, read in place
+        if (cx1 == nxc)
+        {
+            cx1 = 0;
+            if (perx) bx = 4; else mx = 0.f;
+        }
+        if (cy1 == nyc)
+        {
+            cy1 = 0;
+            if (pery) by = 2; else my = 0.f;
+        }
+        if (cz2 == nzc)
+        {
+            cz2 = 0;
+            if (perz) bz = 1; else mz = 0.f;
+        }
+    }
+    else if (cx1 == nxc)
     {
         // coarse plane nxc: my own plane 0 (periodic, x not split), the east
         // neighbour's plane 0 (x split), or nothing (Dirichlet)
@@ -742,29 +951,31 @@ __global__ void k_mg_prolong_correct(int nx, int ny, int nz, int perx, int pery,
         else if (coarse_e || !perx)
             mx = 0.f; // the east rank does not hold it, or the domain ends
     }
-    if (cy1 == nyc)
+    if (!P3 && cy1 == nyc)
     {
         cy1 = 0;
         if (!pery) my = 0.f;
     }
-    if (cz2 == nzc)
+    if (!P3 && cz2 == nzc)
     {
         cz2 = 0;
         if (!perz) mz = 0.f;
     }
     // coarse rows (x0,y0), (x0,y1), (x1,y0), (x1,y1): values at cz0, cz0+1, cz0+2
     float c00[3], c01[3], c10[3], c11[3];
-    auto row3 = [&](const float* Cb, int cx, int cy, float m, float(&o)[3]) {
-        const float* r = Cb + ((long long)cx * nyc + cy) * nzc;
+    auto row3 = [&](const float* Cb, int bits, int cx, int cy, float m, float(&o)[3]) {
+        const long long ro = ((long long)cx * nyc + cy) * nzc;
+        const float* r     = (P3 ? nb.p[bits] + (long long)(f + f0) * ldc : Cb) + ro;
+        const float* rz    = (P3 ? nb.p[bits | bz] + (long long)(f + f0) * ldc : Cb) + ro;
         const float2 a = __ldg(reinterpret_cast<const float2*>(r + cz0));
         o[0] = a.x * m;
         o[1] = a.y * m;
-        o[2] = __ldg(r + cz2) * (m * mz);
+        o[2] = __ldg(rz + cz2) * (m * mz);
     };
-    row3(C, cx0, cy0, 1.f, c00);
-    row3(C, cx0, cy1, my, c01);
-    row3(Cx1, cx1, cy0, mx, c10);
-    row3(Cx1, cx1, cy1, mx * my, c11);
+    row3(C, 0, cx0, cy0, 1.f, c00);
+    row3(C, by, cx0, cy1, my, c01);
+    row3(Cx1, bx, cx1, cy0, mx, c10);
+    row3(Cx1, bx | by, cx1, cy1, mx * my, c11);
 
 #pragma unroll
     for (int ox = 0; ox < 2; ox++)
@@ -899,6 +1110,7 @@ struct JacobiCfg
     int RY, YG, NB, S, XC;
 };
 
+static bool g_jacobi_p3 = false; // lay out the z-halo arrays of the P3 kernels
 static bool jacobi_layout(const JacobiCfg& c, int G, int ny, int nz, JacobiParams& P,
     size_t& smem)
 {
@@ -917,6 +1129,14 @@ static bool jacobi_layout(const JacobiCfg& c, int G, int ny, int nz, JacobiParam
     P.off_mid     = round_up_i(G * P.row_bytes, 128);
     P.off_hi      = P.off_mid + round_up_i(TY * P.row_bytes, 128);
     P.tile_bytes  = P.off_hi + round_up_i(G * P.row_bytes, 128);
+    if (g_jacobi_p3)
+    {
+        P.zlo_off    = P.tile_bytes;
+        P.zarr_mid   = 128;
+        P.zarr_hi    = 128 + round_up_i(TY * 16, 128);
+        P.zarr_bytes = P.zarr_hi + 128;
+        P.tile_bytes += 2 * P.zarr_bytes;
+    }
     P.stage_bytes = c.NB * P.tile_bytes;
     smem          = (size_t)kMgBarBytes + (size_t)c.S * P.stage_bytes;
     return smem <= 227 * 1024 && c.S >= 2 * G + 2 && c.S <= 16;
@@ -1007,13 +1227,18 @@ static int launch_jacobi(const JacobiParams& P, const JacobiCfg& c, dim3 grid, i
     size_t smem, cudaStream_t st)
 {
     // launch-bound classes: 9 / 13 / 17 warps -> 168 / 128 / 96 registers
-#define MGB_LAUNCH_J(RYV, MT)                                                  \
+#define MGB_LAUNCH_JP(RYV, MT, P3V)                                            \
     {                                                                          \
-        auto kern = k_mg_jacobi<LAP, RYV, SCALE, MT, MASK>;                    \
+        auto kern = k_mg_jacobi<LAP, RYV, SCALE, MT, MASK, P3V>;               \
         MGB_CUDA(cudaFuncSetAttribute(                                         \
             kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
         kern<<<grid, threads, smem, st>>>(P);                                  \
     }
+#define MGB_LAUNCH_J(RYV, MT)                                                  \
+    if (P.nbmaps)                                                              \
+        MGB_LAUNCH_JP(RYV, MT, true)                                           \
+    else                                                                       \
+        MGB_LAUNCH_JP(RYV, MT, false)
 #define MGB_LAUNCH_JR(RYV)                                                     \
     if (threads <= 288)                                                        \
         MGB_LAUNCH_J(RYV, 288)                                                 \
@@ -1031,6 +1256,7 @@ static int launch_jacobi(const JacobiParams& P, const JacobiCfg& c, dim3 grid, i
     }
 #undef MGB_LAUNCH_JR
 #undef MGB_LAUNCH_J
+#undef MGB_LAUNCH_JP
     MGB_LAUNCHED("k_mg_jacobi");
     return MGB_OK;
 }
@@ -1041,21 +1267,37 @@ int mg_jacobi(const MgJacobiArgs& a, cudaStream_t st)
     const int nx = gr.dim[0], ny = gr.dim[1], nz = gr.dim[2];
     const int G = (a.lap_type == MGB_LAP_4) ? 2 : 1;
     JacobiCfg c;
+    g_jacobi_p3 = a.nb3d != nullptr;
     if (!jacobi_choose(G, nx, ny, nz, a.nfunc, c))
     {
+        g_jacobi_p3 = false;
         set_error("mg_jacobi: no tile configuration for %d x %d x %d", nx, ny, nz);
         return MGB_ENOTSUP;
     }
     JacobiParams P;
     memset(&P, 0, sizeof(P));
-    size_t smem = 0;
-    if (!jacobi_layout(c, G, ny, nz, P, smem)) return MGB_ENOTSUP;
+    size_t smem       = 0;
+    const bool lay_ok = jacobi_layout(c, G, ny, nz, P, smem);
+    g_jacobi_p3       = false;
+    if (!lay_ok) return MGB_ENOTSUP;
     int rc;
+    if (a.nb3d)
+    {
+        if ((rc = nb_table(reinterpret_cast<const void* const*>(a.nb3d), false, nz, ny, nx, (long long)a.ld_in, a.nfunc, P.TY, G, st,
+                 &P.nbmaps)))
+            return rc;
+        P.zsplit = gr.nproc[2] > 1 || getenv("MGB_HPSI_FORCE_ZBOXES") != nullptr;
+        for (int d = 0; d < 3; d++)
+        {
+            P.end_lo[d] = gr.bc[d] != 1 && gr.coord[d] == 0;
+            P.end_hi[d] = gr.bc[d] != 1 && gr.coord[d] == gr.nproc[d] - 1;
+        }
+    }
     if ((rc = make_map(&P.in_mid, false, a.in, 4, nz, ny, nx, (long long)a.ld_in, a.nfunc, P.TY)))
         return rc;
     if ((rc = make_map(&P.in_halo, false, a.in, 4, nz, ny, nx, (long long)a.ld_in, a.nfunc, G)))
         return rc;
-    P.split_x = gr.nproc[0] > 1;
+    P.split_x = gr.nproc[0] > 1 && !a.nb3d;
     if (P.split_x)
     {
         const bool per = gr.bc[0] == 1;
@@ -1168,10 +1410,34 @@ static MaskView mask_from(const MaskView& m, int f0)
     return v;
 }
 
+// nb3d (27 blocks, index ((dx+1)*3 + (dy+1))*3 + (dz+1)) -> the 8 a transfer kernel touches
+static Nb8 nb8_of(const float* const* nb3d, int side)
+{
+    Nb8 n;
+    for (int b = 0; b < 8; b++)
+    {
+        const int dx = (b & 4) ? side : 0, dy = (b & 2) ? side : 0, dz = (b & 1) ? side : 0;
+        n.p[b]       = nb3d[((dx + 1) * 3 + (dy + 1)) * 3 + (dz + 1)];
+    }
+    return n;
+}
+
 int mg_restrict(const mgb_grid& fine, const float* w, size_t ldf, float* coarse, size_t ldc,
-    int nfunc, const MaskView& mask, const float* w_west, const int* map_w, cudaStream_t st)
+    int nfunc, const MaskView& mask, const float* w_west, const int* map_w, cudaStream_t st,
+    const float* const* nb3d)
 {
     const int nxc = fine.dim[0] / 2, nyc = fine.dim[1] / 2, nzc = fine.dim[2] / 2;
+    for (int f0 = 0; nb3d && f0 < nfunc; f0 += 65535)
+    {
+        const int nf = (nfunc - f0 < 65535) ? nfunc - f0 : 65535;
+        const VecLaunch L = vec_launch(nxc, nyc, nzc / 4, nf);
+        k_mg_restrict3<<<L.grid, L.block, 0, st>>>(nxc, nyc, nzc,
+            fine.bc[0] != 1 && fine.coord[0] == 0, fine.bc[1] != 1 && fine.coord[1] == 0,
+            fine.bc[2] != 1 && fine.coord[2] == 0, nb8_of(nb3d, -1), (long long)ldf,
+            coarse + (size_t)f0 * ldc, (long long)ldc, mask_from(mask, f0), f0);
+        MGB_LAUNCHED("k_mg_restrict3");
+    }
+    if (nb3d) return MGB_OK;
     for (int f0 = 0; f0 < nfunc; f0 += 65535)
     {
         const int nf = (nfunc - f0 < 65535) ? nfunc - f0 : 65535;
@@ -1187,17 +1453,31 @@ int mg_restrict(const mgb_grid& fine, const float* w, size_t ldf, float* coarse,
 
 int mg_prolong_correct(const mgb_grid& fine, const float* coarse, size_t ldc, float* v,
     size_t ldv, int nfunc, const int zero_low[3], const MaskView& mask, const float* coarse_east,
-    const int* map_e, cudaStream_t st)
+    const int* map_e, cudaStream_t st, const float* const* nb3d)
 {
     const int nx = fine.dim[0], ny = fine.dim[1], nz = fine.dim[2];
+    Nb8 none;
+    memset(&none, 0, sizeof(none));
     for (int f0 = 0; f0 < nfunc; f0 += 65535)
     {
         const int nf = (nfunc - f0 < 65535) ? nfunc - f0 : 65535;
         const VecLaunch L = vec_launch(nx / 2, ny / 2, nz / 4, nf);
-        k_mg_prolong_correct<<<L.grid, L.block, 0, st>>>(nx, ny, nz, fine.bc[0] == 1,
-            fine.bc[1] == 1, fine.bc[2] == 1, zero_low[0], zero_low[1], zero_low[2],
-            coarse + (size_t)f0 * ldc, (long long)ldc, v + (size_t)f0 * ldv, (long long)ldv,
-            mask_from(mask, f0), coarse_east, map_e ? map_e + f0 : nullptr, f0);
+        if (nb3d)
+        {
+            // "periodic" = the high neighbour exists (not a Dirichlet end of the domain)
+            int cont[3];
+            for (int d = 0; d < 3; d++)
+                cont[d] = !(fine.bc[d] != 1 && fine.coord[d] == fine.nproc[d] - 1);
+            k_mg_prolong_correct<true><<<L.grid, L.block, 0, st>>>(nx, ny, nz, cont[0], cont[1],
+                cont[2], zero_low[0], zero_low[1], zero_low[2], coarse + (size_t)f0 * ldc,
+                (long long)ldc, v + (size_t)f0 * ldv, (long long)ldv, mask_from(mask, f0),
+                nullptr, nullptr, f0, nb8_of(nb3d, +1));
+        }
+        else
+            k_mg_prolong_correct<false><<<L.grid, L.block, 0, st>>>(nx, ny, nz, fine.bc[0] == 1,
+                fine.bc[1] == 1, fine.bc[2] == 1, zero_low[0], zero_low[1], zero_low[2],
+                coarse + (size_t)f0 * ldc, (long long)ldc, v + (size_t)f0 * ldv, (long long)ldv,
+                mask_from(mask, f0), coarse_east, map_e ? map_e + f0 : nullptr, f0, none);
         MGB_LAUNCHED("k_mg_prolong_correct");
     }
     return MGB_OK;

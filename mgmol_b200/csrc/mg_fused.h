@@ -35,6 +35,10 @@ struct MgJacobiArgs
     // arrays, -1 = absent), or null = same slot
     const int* map_w;
     const int* map_e;
+    // any px x py x pz decomposition: nb3d[((dx+1)*3 + (dy+1))*3 + (dz+1)] = the copy of `in`
+    // of the rank at coord + (dx,dy,dz) (my own across a direction that is not split), every
+    // halo read in place; null = not this path
+    const float* const* nb3d;
 };
 
 // true when the fused kernels can run this level (z extent a multiple of 4,
@@ -43,14 +47,17 @@ bool mg_fused_level_ok(const mgb_grid& g, int lap_type);
 
 int mg_jacobi(const MgJacobiArgs& a, cudaStream_t st);
 // `mask`: of the COARSE level (applied to the restricted block)
+// nb3d (both transfers): the copies of the source block on the 27 Cartesian neighbours (any
+// decomposition, halos read in place; see MgJacobiArgs::nb3d), or null
 // w_west: the west neighbour's copy of `w` on an x-split domain (its last
 // fine plane is my plane -1), or null
 int mg_restrict(const mgb_grid& fine, const float* w, size_t ldf, float* coarse, size_t ldc,
-    int nfunc, const MaskView& mask, const float* w_west, const int* map_w, cudaStream_t st);
+    int nfunc, const MaskView& mask, const float* w_west, const int* map_w, cudaStream_t st,
+    const float* const* nb3d = nullptr);
 // `mask`: of the fine level (applied to P e before the subtraction)
 int mg_prolong_correct(const mgb_grid& fine, const float* coarse, size_t ldc, float* v,
     size_t ldv, int nfunc, const int zero_low[3], const MaskView& mask, const float* coarse_east,
-    const int* map_e, cudaStream_t st);
+    const int* map_e, cudaStream_t st, const float* const* nb3d = nullptr);
 int mg_convert(size_t npt, const double* in, size_t ldi, float* out, size_t ldo, int nfunc,
     cudaStream_t st);
 int mg_scale(const mgb_grid& gr, double c, const float* f, size_t ldf, float* v, size_t ldv,

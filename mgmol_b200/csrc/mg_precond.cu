@@ -245,9 +245,14 @@ int mgb_precond_create(mgb_precond** out, int lap_type, int mg_levels,
     p->fused_ok = (grid->bc[0] == grid->bc[1] && grid->bc[1] == grid->bc[2]);
     // the fused kernels read x neighbours in place; y / z splits go through
     // the ghosted exchange of the literal sequence
-    if (grid->nproc[1] != 1 || grid->nproc[2] != 1) p->fused_ok = false;
-    if (grid->nproc[0] > 1 && grid->dim[0] * grid->nproc[0] != grid->gdim[0])
-        p->fused_ok = false;
+    // decomposed boxes: the neighbours' blocks must have my shape (halos are read in place)
+    for (int d = 0; d < 3; d++)
+        if (grid->nproc[d] > 1 && grid->dim[d] * grid->nproc[d] != grid->gdim[d])
+            p->fused_ok = false;
+    // y / z splits take the in-place kernels of any decomposition, which need whole
+    // 16-byte z-halo columns on every level (nz of the coarsest level a multiple of 4 is
+    // checked per level below) and do not translate color slots
+    if (getenv("MGB_MG_NO_3D") && (grid->nproc[1] != 1 || grid->nproc[2] != 1)) p->fused_ok = false;
     for (int l = 0; l <= mg_levels && rc == MGB_OK; l++)
     {
         if (l > 0)
@@ -342,7 +347,7 @@ static int ensure_fused(mgb_precond* p)
         p->fw.push_back(w);
         p->ff.push_back(f); // level 0: allocated on the first double-precision call
         // (x-split domains: always, so that it is registered with the others)
-        if (l > 0 || p->grid[0].nproc[0] > 1)
+        if (l > 0 || multi_rank(p->grid[0]))
             if (int rc = dev_alloc(&p->ff[l], bytes)) return rc;
     }
     p->fused_ready = true;
@@ -353,7 +358,7 @@ static int ensure_fused(mgb_precond* p)
 // kernels can read boundary planes in place (collective, once per handle)
 static int ensure_peers(mgb_precond* p, cudaStream_t st)
 {
-    if (p->peers_ready || p->grid[0].nproc[0] == 1) return MGB_OK;
+    if (p->peers_ready || !multi_rank(p->grid[0])) return MGB_OK;
     for (int l = 0; l <= p->max_levels; l++)
         for (float* q : { p->fa[l], p->fb[l], p->fw[l], p->ff[l] })
             if (q)
@@ -392,6 +397,38 @@ fail:
     return MGB_ENOTSUP;
 }
 
+// y / z splits: the copies of a registered work block on the 27 Cartesian neighbours (my
+// own block across a direction that is not split)
+static bool use_3d(const mgb_grid& gr)
+{
+    // MGB_MG_FORCE_3D: test hook -- a single rank runs the any-decomposition kernels with
+    // itself as every neighbour
+    return gr.nproc[1] > 1 || gr.nproc[2] > 1 || getenv("MGB_MG_FORCE_3D") != nullptr;
+}
+static int nb_peers(mgb_precond* p, const mgb_grid& gr, const float* q, const float* out[27])
+{
+    if (!multi_rank(gr))
+    {
+        for (int i = 0; i < 27; i++)
+            out[i] = q;
+        return MGB_OK;
+    }
+    for (int dx = -1; dx <= 1; dx++)
+        for (int dy = -1; dy <= 1; dy++)
+            for (int dz = -1; dz <= 1; dz++)
+            {
+                const int i = ((dx + 1) * 3 + (dy + 1)) * 3 + (dz + 1);
+                out[i]      = (const float*)peer_view(p->comm, q,
+                    comm_rank_of(&gr, gr.coord[0] + dx, gr.coord[1] + dy, gr.coord[2] + dz));
+                if (!out[i])
+                {
+                    set_error("mgb_precond: a neighbour's work block cannot be mapped (CUDA IPC)");
+                    return MGB_ENOTSUP;
+                }
+            }
+    return MGB_OK;
+}
+
 // One level of Preconditioning<float>::mg (src/Preconditioning.cc:155-216) on
 // no-ghost blocks with the fused kernels.  The start vector of the level is
 // s * f: gamma * res at level 0 (OrbitalsPreconditioning.cc:104) and, on the
@@ -410,10 +447,13 @@ static int cycle_fused(mgb_precond* p, int l, const float* f, size_t ldf, double
     int zl[3], nozero[3] = { 0, 0, 0 };
     for (int d = 0; d < 3; d++)
         zl[d] = gr.bc[d] != 1 && gr.coord[d] == 0; // the rank owning the low face
-    const bool split = gr.nproc[0] > 1;
+    const bool split = multi_rank(gr);
+    const bool d3    = use_3d(gr);
     const int *map_w = nullptr, *map_e = nullptr;
     int map_n = 0;
     if (split) comm_color_maps(p->comm, &map_w, &map_e, &map_n);
+    MGB_REQUIRE(!(d3 && map_w),
+        "mgb_precond_mg: color-slot translation (LocGridOrbitals) is served on x slabs only");
     MGB_REQUIRE(!map_w || map_n >= nfunc, "mgb_precond_mg: color maps cover %d colors, need %d",
         map_n, nfunc);
     // the last sweep of level 0 is followed by a trade only on the path through
@@ -459,7 +499,16 @@ static int cycle_fused(mgb_precond* p, int l, const float* f, size_t ldf, double
             a.zero_low[d] = z[d];
         a.mask = mk;
         XPeers xp;
-        if (int rc = x_peers(p, gr, a.in, xp)) return rc;
+        const float* nb[27];
+        a.nb3d = nullptr;
+        if (d3)
+        {
+            if (int rc = nb_peers(p, gr, a.in, nb)) return rc;
+            a.nb3d = nb;
+            xp.w = xp.e = nullptr;
+        }
+        else if (int rc = x_peers(p, gr, a.in, xp))
+            return rc;
         a.peer_w = xp.w;
         a.peer_e = xp.e;
         a.map_w  = map_w;
@@ -485,11 +534,18 @@ static int cycle_fused(mgb_precond* p, int l, const float* f, size_t ldf, double
     // :189-192 restriction of the residual of the last pre-smoothing sweep
     {
         XPeers xp;
-        if (int rc = x_peers(p, gr, p->fw[l], xp)) return rc;
+        const float* nb[27];
+        if (d3)
+        {
+            if (int rc = nb_peers(p, gr, p->fw[l], nb)) return rc;
+            xp.w = xp.e = nullptr;
+        }
+        else if (int rc = x_peers(p, gr, p->fw[l], xp))
+            return rc;
         if (split)
             if (int rc = comm_barrier_neighbors(p->comm, &gr, st)) return rc;
-        if (int rc = mg_restrict(
-                gr, p->fw[l], ld, p->ff[l + 1], npt_of(p->grid[l + 1]), nfunc, mkc, xp.w, map_w, st))
+        if (int rc = mg_restrict(gr, p->fw[l], ld, p->ff[l + 1], npt_of(p->grid[l + 1]), nfunc, mkc,
+                xp.w, map_w, st, d3 ? nb : nullptr))
             return rc;
     }
     // :198-199 coarse correction from a zero start: its first sweep gives
@@ -502,11 +558,18 @@ static int cycle_fused(mgb_precond* p, int l, const float* f, size_t ldf, double
     // :201-206 v -= P e
     {
         XPeers xp;
-        if (int rc = x_peers(p, p->grid[l + 1], e, xp)) return rc;
+        const float* nb[27];
+        if (d3)
+        {
+            if (int rc = nb_peers(p, p->grid[l + 1], e, nb)) return rc;
+            xp.w = xp.e = nullptr;
+        }
+        else if (int rc = x_peers(p, p->grid[l + 1], e, xp))
+            return rc;
         if (split)
             if (int rc = comm_barrier_neighbors(p->comm, &gr, st)) return rc;
-        if (int rc = mg_prolong_correct(
-                gr, e, npt_of(p->grid[l + 1]), cur, ld, nfunc, zl, mk, xp.e, map_e, st))
+        if (int rc = mg_prolong_correct(gr, e, npt_of(p->grid[l + 1]), cur, ld, nfunc, zl, mk, xp.e,
+                map_e, st, d3 ? nb : nullptr))
             return rc;
     }
     for (int it = 0; it < 2; it++) // :209-213
@@ -618,7 +681,7 @@ int mgb_precond_mg(mgb_precond* p, int dtype, void* res, size_t ld, int nfunc,
         gr.nproc[0], gr.nproc[1], gr.nproc[2]);
     bool can_fuse = p->fused_ok && ld % 4 == 0 && ((uintptr_t)res & 15) == 0
                     && ld * es % 16 == 0;
-    if (can_fuse && gr.nproc[0] > 1)
+    if (can_fuse && multi_rank(gr))
     {
         // x-split: the neighbours' work blocks must be mappable (CUDA IPC);
         // otherwise the literal sequence with the packed exchange serves
@@ -635,7 +698,7 @@ int mgb_precond_mg(mgb_precond* p, int dtype, void* res, size_t ld, int nfunc,
     {
         if ((rc = ensure_fused(p))) return rc;
         // nobody is still reading my work blocks from the previous call
-        if (gr.nproc[0] > 1)
+        if (multi_rank(gr))
             if ((rc = comm_barrier_neighbors(p->comm, &gr, st))) return rc;
         const float* f = (const float*)res;
         size_t ldf     = ld;
@@ -651,9 +714,9 @@ int mgb_precond_mg(mgb_precond* p, int dtype, void* res, size_t ld, int nfunc,
             f   = p->ff[0];
             ldf = npt_of(gr);
         }
-        else if (gr.nproc[0] > 1)
+        else if (multi_rank(gr))
         {
-            // x-split: the first sweep reads the neighbours' planes of f in place,
+            // decomposed box: the first sweep reads the neighbours' planes of f in place,
             // so f must live in a registered block (same kernels, hence the same
             // bits, as on a single rank)
             MGB_CUDA(cudaMemcpy2DAsync(p->ff[0], npt_of(gr) * sizeof(float), res,

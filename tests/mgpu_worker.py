@@ -173,14 +173,12 @@ def main():
         for lap in (0, 2):
             g = H.ghosts_for(lap)
             for bc in ((1, 1, 1), (0, 0, 0)):
-                for axis, modes in ((0, (2, 1)), (1, (1,))):
-                    gdims = [16, 16, 32]
-                    gdims[axis] *= world
-                    gdims = tuple(gdims)
+                cases = [((world, 1, 1), (2, 1)), ((1, world, 1), (2, 1)), ((1, 1, world), (2,))]
+                cases += [(d, (2,)) for d in decomps if sum(1 for q in d if q > 1) > 1]
+                for nproc, modes in cases:
+                    gdims = (16 * nproc[0], 16 * nproc[1], 32 * nproc[2])
                     ll = tuple(0.25 * d for d in gdims)
-                    nproc = [1, 1, 1]
-                    nproc[axis] = world
-                    nproc = tuple(nproc)
+                    axis = "%dx%dx%d" % nproc
                     coord = cart_coords(rank, nproc)
                     box = local_box(gdims, nproc, coord)
                     full = (torch.rand((4,) + gdims, generator=gen, device="cuda",
@@ -209,7 +207,7 @@ def main():
                         pc2.gamma_ = 0.3
                         pc2.precond_mg(gorb)
                         pc2.close()
-                        check("precond_mg axis%d mode%d %s lap%d bc%s" % (axis, mode, dt, lap, bc),
+                        check("precond_mg %s mode%d %s lap%d bc%s" % (axis, mode, dt, lap, bc),
                               pcl.last_mode() == mode
                               and torch.equal(orb.psi(), gorb.psi()[(slice(None),) + box]))
                         pcl.close()

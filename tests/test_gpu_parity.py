@@ -433,6 +433,43 @@ def test_precond_mg_fused(H, port, dt, lap_type, bc, levels, dims):
     pc.close()
 
 
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("lap_type", [0, 2])
+@pytest.mark.parametrize("bc", [(1, 1, 1), (0, 0, 0)])
+@pytest.mark.parametrize("zboxes", [False, True])
+@pytest.mark.parametrize("levels,dims", [(1, (16, 24, 32)), (2, (16, 24, 32)), (2, (32, 32, 64))])
+def test_precond_mg_fused_3d_self_neighbours(H, dt, lap_type, bc, zboxes, levels, dims):
+    """The any-decomposition variants of the fused V-cycle kernels (Jacobi with the neighbour
+    table and z-halo column arrays, restriction and prolongation through the 8 neighbour
+    blocks) on one rank, with the box itself as every neighbour: bit-identical to the
+    single-rank fused kernels."""
+    ll = (4.0, 6.0, 8.0)
+    N = 3
+    res = synthetic_orbitals(N, dims, dt)
+    grid = H.Grid(dims, ll, H.ghosts_for(lap_type), bc)
+
+    def run():
+        r = H.Orbitals(grid, N, TDT[dt], dev(res))
+        pc = H.OrbitalsPreconditioning()
+        pc.setup(r, levels, lap_type)
+        pc.set_mode(2)
+        pc.gamma_ = 0.3
+        pc.precond_mg(r)
+        pc.close()
+        return r.psi()
+
+    ref = run()
+    os.environ["MGB_MG_FORCE_3D"] = "1"
+    if zboxes:
+        os.environ["MGB_HPSI_FORCE_ZBOXES"] = "1"
+    try:
+        got = run()
+    finally:
+        os.environ.pop("MGB_MG_FORCE_3D", None)
+        os.environ.pop("MGB_HPSI_FORCE_ZBOXES", None)
+    assert torch.equal(got, ref)
+
+
 @pytest.mark.parametrize("bc", [(1, 0, 1), (0, 1, 1), (1, 1, 0)])
 def test_precond_mg_mixed_bc_stays_literal(H, port, bc):
     """Mixed periodic/Dirichlet boxes: the reference's result depends on ghost
