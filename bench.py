@@ -50,7 +50,7 @@ DEFAULT_WORKLOAD = "synth256"
 def layout(args, world):
     """Decomposition and sizes of the workload at `world` GPUs -- shared by both arms so
     that their `config` dicts are identical."""
-    from mgmol_b200.parallel import geom
+    from mgmol_b200.parallel import geom_b200
     w = WORKLOADS[args.workload]
     if args.decomp and args.decomp != "auto":
         nproc = tuple(int(x) for x in args.decomp.lower().split("x"))
@@ -58,8 +58,9 @@ def layout(args, world):
         how = "requested"
     else:
         # PEenv::geom (src/pb/PEenv.cc:335-) on the grid the reference would be given
-        nproc = geom(w["grid"][0], w["grid"][1], w["grid"][2], world) if world > 1 else (1, 1, 1)
-        how = "PEenv::geom"
+        nproc = (geom_b200(w["grid"][0], w["grid"][1], w["grid"][2], world) if world > 1
+                 else (1, 1, 1))
+        how = "PEenv::geom factors (2x2x2 at 8 ranks), ties between equal directions broken toward x"
         if nproc is None:
             nproc, how = (world, 1, 1), "x slabs (PEenv::geom refuses this mesh)"
     if args.strong or w["fixed"] == "global":
@@ -542,8 +543,8 @@ def measure_sweep(H, args, store_phi, store_out, fp64_peak):
                 cells.append({"dtype": dname, "orbitals": norb, "infeasible":
                               "2 blocks of %.1f GB do not fit one 180 GB GPU" % (need / 1e9)})
                 continue
-            a = store_phi.view(torch.uint8)[:need].view(tdt).view((norb,) + dims)
-            b = store_out.view(torch.uint8)[:need].view(tdt).view((norb,) + dims)
+            a = store_phi.reshape(-1).view(torch.uint8)[:need].view(tdt).view((norb,) + dims)
+            b = store_out.reshape(-1).view(torch.uint8)[:need].view(tdt).view((norb,) + dims)
             if dname == "f32":
                 a.uniform_(-0.5, 0.5)
             for lap in (0, 2):
@@ -812,8 +813,9 @@ def run_ours(args):
     # in, pinned host H psi out (H2D, kernel and D2H pipelined over orbital blocks inside
     # the library).  Bounded host memory: at most ~8.6 GB each way per step, i.e. the
     # first e2e_orb orbitals of the block -- the rate is per update.
+    quick = bool(os.environ.get("MGB_BENCH_QUICK"))  # development: no e2e leg, no CPU arm
     e2e_orb = norb
-    while e2e_orb > 8 and npt * e2e_orb * S > 9e9:
+    while e2e_orb > 8 and npt * e2e_orb * S > (1e8 if quick else 9e9):
         e2e_orb //= 2
     h_phi = torch.empty((e2e_orb,) + dims, dtype=tdt).pin_memory()
     h_phi.copy_(phi.psi()[:e2e_orb])
@@ -897,7 +899,8 @@ def run_ours(args):
         peak, peak_src = measured_peaks()
         achieved = 2.0 * S * npt * norb / (kern_ms * 1e-3) / 1e9
         np_dt = np.float64 if args.dtype == "f64" else np.float32
-        cpu_rate, cores, kind, sample = cpu_hpsi_rate(lap_type, gdims, cell, np_dt)
+        cpu_rate, cores, kind, sample = ((0.0, 0, "skipped", "MGB_BENCH_QUICK") if quick else
+                                         cpu_hpsi_rate(lap_type, gdims, cell, np_dt))
         traffic, traffic_src = (measured_traffic(kernel_sig, dims, norb, args.dtype, lap_type)
                                 if path == 1 else (None, "no capture"))
         cfg = dict(L["config"])

@@ -225,7 +225,7 @@ static int hpsi_entry(int lap_type, int dtype, const mgb_grid* grid, const void*
     size_t ld, const double* vtot, void* hphi, size_t ldh, int nfunc,
     const void* xhalo_phi, const double* xhalo_v, const void* peer_w, const void* peer_e,
     const int* map_w, const int* map_e, void* stream, const void* const* nb3d = nullptr,
-    const double* vghost = nullptr)
+    const double* vghost = nullptr, const void* const* nbz = nullptr)
 {
     if (int rc = require_device()) return rc;
     if (int rc = check_grid(grid)) return rc;
@@ -262,6 +262,7 @@ static int hpsi_entry(int lap_type, int dtype, const mgb_grid* grid, const void*
     a.map_e     = map_e;
     a.nb3d      = nb3d;
     a.vghost    = vghost;
+    a.nbz       = nbz;
     cudaStream_t st = as_stream(stream);
     if (nb3d)
     {
@@ -464,10 +465,17 @@ int mgb_hpsi_peer3d(mgb_comm* comm, int lap_type, int dtype, const mgb_grid* gri
                 }
             }
     cudaStream_t st = as_stream(stream);
-    // every rank's phi is complete before anybody reads boundary layers ...
+    // z split: the z-edge columns are pushed into the z neighbours' dense buffers first
+    const void* nbz[9];
+    const bool zsplit = grid->nproc[2] > 1 || getenv("MGB_HPSI_FORCE_ZBOXES") != nullptr;
+    if (zsplit)
+        if (int rc = comm_zhalo(comm, grid, dtype == MGB_F64 ? 8 : 4, phi, ld, nfunc, st, nbz))
+            return rc;
+    // every rank's phi is complete (and its columns have landed) before anybody reads
+    // boundary layers ...
     if (int rc = comm_barrier_neighbors(comm, grid, st)) return rc;
     const int rc = hpsi_entry(lap_type, dtype, grid, phi, ld, vtot, hphi, ldh, nfunc, nullptr,
-        nullptr, nullptr, nullptr, nullptr, nullptr, stream, nb, vghost);
+        nullptr, nullptr, nullptr, nullptr, nullptr, stream, nb, vghost, zsplit ? nbz : nullptr);
     if (rc) return rc;
     // ... and nobody overwrites its phi while a neighbour still reads it
     return comm_barrier_neighbors(comm, grid, st);

@@ -32,6 +32,7 @@ struct HpsiArgs
     // vghost: ghosted copy of V (width g, boundaries traded)
     const void* const* nb3d;
     const double* vghost;
+    const void* const* nbz; // z split: the 9 z-halo column buffers (comm_zhalo), else null
 };
 
 // path 1: TMA-pipelined x-streaming kernel (hpsi_fused.cu).  Returns
@@ -76,6 +77,10 @@ int comm_barrier(mgb_comm* c, cudaStream_t st);
 // to comm_barrier when the inboxes cannot be mapped)
 int comm_barrier_neighbors(mgb_comm* c, const mgb_grid* gr, cudaStream_t st);
 int comm_rank_of(const mgb_grid* gr, int cx, int cy, int cz);
+// push the z-edge columns of a block to the z neighbours' dense buffers; nbz[(dx+1)*3 +
+// (dy+1)]: the buffers ([function][x][y][32 bytes]) the consuming kernel reads (comm.cu)
+int comm_zhalo(mgb_comm* c, const mgb_grid* gr, int es, const void* src, size_t ld, int nfunc,
+    cudaStream_t st, const void* nbz[9]);
 // LocGridOrbitals on split domains: the color slot of my color's orbital on the
 // west / east rank (device arrays, -1 = not held there), null = same slot
 void comm_color_maps(mgb_comm* c, const int** map_w, const int** map_e, int* n);

@@ -115,7 +115,7 @@ struct alignas(64) FusedParams
     int zsplit;         // z halo columns come from boxes (z is split), not from the wrapped index
     int first_y, last_y, first_z, last_z; // non-periodic AND at the domain's end
     int per_y, per_z;
-    int zarr_mid, zarr_hi, zarr_bytes, zlo_off; // z-halo arrays inside a tile (16 bytes per row)
+    int zarr_mid, zarr_hi, zarr_bytes, zlo_off; // z-halo entries inside a tile (32 bytes per row)
     int vrow_bytes, nvb;                        // padded V tile: row pitch, boxes per plane
     int pol;      // L2 policy of the phi loads (see the producer)
     int orb_fast; // blockIdx.x walks the orbital blocks (CTAs of a wave share V tiles in L2)
@@ -214,7 +214,9 @@ __global__ void __launch_bounds__(MAXT, 1)
     if (tid < 32)
     {
         // ------------------------- TMA producer --------------------------
-        if (tid != 0) return;
+        // (PEER == 2: up to 3 NB lanes issue, one per orbital and box)
+        if (PEER != 2 && tid != 0) return;
+        if (PEER == 2 && tid >= 3 * P.NB) return;
         unsigned char* stages     = smem + kBarBytes;
         // phi is streamed once, but the rows at a tile's edge are also the halo
         // rows of the neighbouring y tile: pol 1 keeps phi at normal priority, pol 2
@@ -243,61 +245,58 @@ __global__ void __launch_bounds__(MAXT, 1)
             int xc        = 0;
             const int src = plane_source<PERIODIC, G>(P, p, xc);
             if (src == 0)
-                mbar_arrive(&full[stage]);
+            {
+                if (tid == 0) mbar_arrive(&full[stage]);
+            }
             else if constexpr (PEER == 2)
             {
-                constexpr int ZH = VEC; // 16 bytes of z
                 // which rank's block holds plane p, and at which x coordinate
                 const int dx  = (p < 0) ? 0 : (p >= P.nx ? 2 : 1);
                 const int xcp = (p < 0) ? P.nx + p : (p >= P.nx ? p - P.nx : p);
-                // rows below / above the tile: the y neighbour's last / first rows (the
-                // wrap when y is not split), or out of range (zero fill) at a Dirichlet end
-                const int dyl = (y0 - G < 0 && !P.first_y) ? 0 : 1;
-                const int yl  = (y0 - G < 0) ? (P.first_y ? -G : P.ny - G) : y0 - G;
-                const int dyh = (y0 + P.TY >= P.ny && !P.last_y) ? 2 : 1;
-                const int yh  = (y0 + P.TY >= P.ny) ? (P.last_y ? P.ny : 0) : y0 + P.TY;
-                const int zlc = P.first_z ? -ZH : P.nz - ZH; // z columns below: the low neighbour's last
-                const int zhc = P.last_z ? P.nz : 0;         // above: the high neighbour's first
                 const uint32_t rows   = (uint32_t)(P.TY + 2 * G);
                 // a cross stencil (4th order) never looks at the z neighbours of halo rows
                 const uint32_t psi_tx = rows * (uint32_t)P.row_bytes
                                         + (P.zsplit ? (LAP4 ? (uint32_t)P.TY : rows) * 32u : 0u);
                 const uint32_t v_tx   = LAP4 ? (uint32_t)(P.TY * P.row_bytes) : rows * (uint32_t)P.vrow_bytes;
-                mbar_arrive_expect_tx(&full[stage], v_tx + (uint32_t)norb * psi_tx);
                 unsigned char* sb = stages + (size_t)stage * P.stage_bytes;
-                if constexpr (LAP4)
-                    tma_load_3d(sb + P.off_mid, &P.v_mid, &full[stage], 0, y0, p, pol_keep);
-                else
+                if (tid == 0)
                 {
-                    // padded ghosted V (a row = nvb chunks of <= 256 elements, so the box
-                    // lands as whole rows): plane p + G, rows y0 .. y0+TY+2G-1 (ghosted index)
-                    tma_load_4d(sb, &P.vg_map, &full[stage], 0, 0, y0, p + G, pol_keep);
+                    mbar_arrive_expect_tx(&full[stage], v_tx + (uint32_t)norb * psi_tx);
+                    if constexpr (LAP4)
+                        tma_load_3d(sb + P.off_mid, &P.v_mid, &full[stage], 0, y0, p, pol_keep);
+                    else
+                        // padded ghosted V (a row = nvb chunks of <= 256 elements, so the box
+                        // lands as whole rows): plane p + G, rows y0 .. y0+TY+2G-1 (ghosted)
+                        tma_load_4d(sb, &P.vg_map, &full[stage], 0, 0, y0, p + G, pol_keep);
                 }
-                const CUtensorMap* tab = P.nbmaps + dx * 36;
-                for (int o = 0; o < norb; o++)
+                // one lane per (orbital, box): the rows below the tile, the tile's rows, the
+                // rows above -- the y neighbour's last / first rows (the wrap when y is not
+                // split), or out of range (zero fill) at a Dirichlet end -- each with the
+                // 32-byte z-halo entries of its rows
+                if (tid < 3 * norb)
                 {
+                    const int o = tid / 3, b = tid - 3 * o;
                     unsigned char* tb = sb + (size_t)(1 + o) * P.tile_bytes;
-                    const int fo      = orb0 + o;
-                    // (dy index, y coordinate, tile offset, z-array offset, box kind) of the 3 boxes
-                    const int dyi[3]  = { dyl, 1, dyh };
-                    const int yc[3]   = { yl, y0, yh };
-                    const int to[3]   = { 0, P.off_mid, P.off_hi };
-                    const int zo[3]   = { 0, P.zarr_mid, P.zarr_hi };
-#pragma unroll
-                    for (int b = 0; b < 3; b++)
+                    int dyi = 1, yc = y0, to = P.off_mid, zo = P.zarr_mid;
+                    if (b == 0)
                     {
-                        const CUtensorMap* m = tab + dyi[b] * 12;
-                        const int kind       = (b == 1) ? 0 : 1;
-                        tma_load_4d(tb + to[b], m + 1 * 4 + kind, &full[stage], 0, yc[b], xcp, fo,
-                            b == 1 ? pol_stream : pol_halo);
-                        if (P.zsplit && (!LAP4 || b == 1))
-                        {
-                            tma_load_4d(tb + P.zlo_off + zo[b], m + 0 * 4 + 2 + kind, &full[stage],
-                                zlc, yc[b], xcp, fo, pol_halo);
-                            tma_load_4d(tb + P.zlo_off + P.zarr_bytes + zo[b], m + 2 * 4 + 2 + kind,
-                                &full[stage], zhc, yc[b], xcp, fo, pol_halo);
-                        }
+                        dyi = (y0 - G < 0 && !P.first_y) ? 0 : 1;
+                        yc  = (y0 - G < 0) ? (P.first_y ? -G : P.ny - G) : y0 - G;
+                        to = 0, zo = 0;
                     }
+                    else if (b == 2)
+                    {
+                        dyi = (y0 + P.TY >= P.ny && !P.last_y) ? 2 : 1;
+                        yc  = (y0 + P.TY >= P.ny) ? (P.last_y ? P.ny : 0) : y0 + P.TY;
+                        to = P.off_hi, zo = P.zarr_hi;
+                    }
+                    const CUtensorMap* m = P.nbmaps + dx * 36 + dyi * 12;
+                    const int kind       = (b == 1) ? 0 : 1;
+                    tma_load_4d(tb + to, m + 4 + kind, &full[stage], 0, yc, xcp, orb0 + o,
+                        b == 1 ? pol_stream : pol_halo);
+                    if (P.zsplit && (!LAP4 || b == 1))
+                        tma_load_4d(tb + P.zlo_off + zo, m + 2 + kind, &full[stage], 0, yc, xcp,
+                            orb0 + o, pol_halo);
                 }
             }
             else
@@ -425,13 +424,13 @@ __global__ void __launch_bounds__(MAXT, 1)
             if (!P.first_z) m0 = (CT)1;
             if (!P.first_y) izero = -100;
         }
-        zsA = (rr0 == 0) ? 0u : (uint32_t)(P.zarr_mid + (rr0 - G) * 16);
-        zsB = (uint32_t)(P.zarr_mid + rr0 * 16);
-        zsC = (rr0 + RY == P.TY) ? (uint32_t)P.zarr_hi : (uint32_t)(P.zarr_mid + (rr0 + RY) * 16);
+        zsA = (rr0 == 0) ? 0u : (uint32_t)(P.zarr_mid + (rr0 - G) * 32);
+        zsB = (uint32_t)(P.zarr_mid + rr0 * 32);
+        zsC = (rr0 + RY == P.TY) ? (uint32_t)P.zarr_hi : (uint32_t)(P.zarr_mid + (rr0 + RY) * 32);
         // the last G (1: Mehrstellen, 2: 4th order) elements of the low array's row, the
         // first of the high array's
         zLb = (uint32_t)(P.zlo_off + 16 - G * (int)sizeof(T));
-        zRb = (uint32_t)(P.zlo_off + P.zarr_bytes);
+        zRb = (uint32_t)(P.zlo_off + 16);
     }
 
     const uint32_t stage0 = smem_u32(smem + kBarBytes);
@@ -536,7 +535,7 @@ __global__ void __launch_bounds__(MAXT, 1)
                     for (int r = 0; r < RY; r++)
                     {
                         ro = (r == RY - 1) ? startC : ro + (uint32_t)rb;
-                        zo = (r == RY - 1) ? zsC : zo + 16u;
+                        zo = (r == RY - 1) ? zsC : zo + 32u;
                         load_row(ro, zo, r + 2, Pp, szp, wp, wzp);
                         CT o[VEC];
 #pragma unroll
@@ -678,8 +677,8 @@ __global__ void __launch_bounds__(MAXT, 1)
                         uint32_t aL = pb + ro_c + zloff, aR = pb + ro_c + zroff;
                         if constexpr (PEER == 2)
                         {
-                            if (isL) aL = pb + zLb + zsB + (uint32_t)(r * 16);
-                            if (isR) aR = pb + zRb + zsB + (uint32_t)(r * 16);
+                            if (isL) aL = pb + zLb + zsB + (uint32_t)(r * 32);
+                            if (isR) aR = pb + zRb + zsB + (uint32_t)(r * 32);
                         }
                         lds_pair(aL, L2, L1);
                         lds_pair(aR, R1, R2);
@@ -910,6 +909,7 @@ __global__ void k_vpad(int nxg, int nyg, int nz, int G, int nzp, const double* _
 struct NbTable
 {
     const void* nb[27];
+    const void* nbz[9];
     int nz, ny, nx, nfunc, TY, G, f64;
     long long ld;
     CUtensorMap* dev;
@@ -918,14 +918,17 @@ struct NbTable
 static NbTable g_nbtab[48];
 static unsigned long long g_nbstamp = 0;
 
-int nb_table(const void* const* nb, bool f64, int nz, int ny, int nx, long long ld,
-    int nfunc, int TY, int G, cudaStream_t st, const CUtensorMap** out)
+int nb_table(const void* const* nb, const void* const* nbz, bool f64, int nz, int ny, int nx,
+    long long ld, int nfunc, int TY, int G, cudaStream_t st, const CUtensorMap** out)
 {
     NbTable* slot = nullptr;
+    const void* nozb[9] = { nullptr };
+    if (!nbz) nbz = nozb;
     for (auto& t : g_nbtab)
     {
         if (t.dev && t.nz == nz && t.ny == ny && t.nx == nx && t.nfunc == nfunc && t.TY == TY
-            && t.G == G && t.f64 == (int)f64 && t.ld == ld && memcmp(t.nb, nb, sizeof(t.nb)) == 0)
+            && t.G == G && t.f64 == (int)f64 && t.ld == ld && memcmp(t.nb, nb, sizeof(t.nb)) == 0
+            && memcmp(t.nbz, nbz, sizeof(t.nbz)) == 0)
         {
             t.stamp = ++g_nbstamp;
             *out    = t.dev;
@@ -938,15 +941,26 @@ int nb_table(const void* const* nb, bool f64, int nz, int ny, int nx, long long 
     const int ZH = f64 ? 2 : 4;
     for (int r = 0; r < 27; r++)
     {
-        const int dy = (r / 3) % 3, dz = r % 3;
-        if (!nb[r]) continue;
+        const int dx = r / 9, dy = (r / 3) % 3, dz = r % 3;
         for (int kind = 0; kind < 4; kind++)
         {
             const bool zbox = kind >= 2, mid = (kind & 1) == 0;
-            if (zbox != (dz != 1)) continue; // z-halo columns come from the z neighbours only
+            if (zbox != (dz == 0)) continue; // z-halo columns: kept in the dz = -1 entries
             if (mid && dy != 1) continue;    // the tile's own rows never come from a y neighbour
-            if (int rc = make_map_box(&host[r * 4 + kind], f64, nb[r], nz, ny, nx, ld, nfunc,
-                    zbox ? ZH : nz, mid ? TY : G))
+            if (!zbox)
+            {
+                if (!nb[r]) continue;
+                if (int rc = make_map_box(&host[r * 4 + kind], f64, nb[r], nz, ny, nx, ld, nfunc, nz,
+                        mid ? TY : G))
+                    return rc;
+                continue;
+            }
+            // the dense buffer of pushed columns of the rank at (dx, dy, 0): 32 bytes per
+            // row, the columns below z = 0 then the columns above z = nz-1
+            const void* zb = nbz[dx * 3 + dy];
+            if (!zb) continue;
+            if (int rc = make_map_box(&host[r * 4 + kind], f64, zb, 2 * ZH, ny, nx,
+                    (long long)2 * ZH * ny * nx, nfunc, 2 * ZH, mid ? TY : G))
                 return rc;
         }
     }
@@ -955,6 +969,7 @@ int nb_table(const void* const* nb, bool f64, int nz, int ny, int nx, long long 
     MGB_CUDA(cudaStreamSynchronize(st));
     MGB_CUDA(cudaMemcpy(slot->dev, host, sizeof(host), cudaMemcpyHostToDevice));
     memcpy(slot->nb, nb, sizeof(slot->nb));
+    memcpy(slot->nbz, nbz, sizeof(slot->nbz));
     slot->nz = nz, slot->ny = ny, slot->nx = nx, slot->nfunc = nfunc, slot->TY = TY, slot->G = G;
     slot->f64 = f64, slot->ld = ld;
     slot->stamp = ++g_nbstamp;
@@ -991,13 +1006,13 @@ static bool cfg_layout(const FusedCfg& c, int G, int ny, int nz, int es,
     P.tile_bytes  = P.off_hi + round_up(G * P.row_bytes, 128);
     if (g_layout_peer3)
     {
-        // two arrays (columns below z = 0, columns above z = nz-1) of 16 bytes per tile
-        // row, each box at a 128-byte boundary: [G rows][TY rows][G rows]
+        // 32 bytes per tile row (the 16 bytes of columns below z = 0, the 16 bytes above
+        // z = nz-1), each box at a 128-byte boundary: [G rows][TY rows][G rows]
         P.zlo_off    = P.tile_bytes;
         P.zarr_mid   = 128;
-        P.zarr_hi    = 128 + round_up(TY * 16, 128);
+        P.zarr_hi    = 128 + round_up(TY * 32, 128);
         P.zarr_bytes = P.zarr_hi + 128;
-        P.tile_bytes += 2 * P.zarr_bytes;
+        P.tile_bytes += P.zarr_bytes;
         P.vrow_bytes = P.row_bytes + 32;
     }
     P.stage_bytes = (c.NB + 1) * P.tile_bytes;
@@ -1033,14 +1048,23 @@ static bool choose_cfg(bool lap4, int es, int nx, int ny, int nz, int nfunc,
     // 256^3 (tools/cfg_sweep.py, tools/cfg_try.py; profiles/r02_hpsi_256_cfg.md).
     if ((size_t)nx * ny * nz * es > ((size_t)48 << 20))
     {
-        FusedCfg c = { lap4 ? 4 : 8, 2, 1, lap4 ? 4 : 3, lap4 ? 64 : 128 };
-        if (c.XC > nx) c.XC = nx;
-        FusedParams tmp;
-        size_t sm;
-        if (cfg_layout(c, G, ny, nz, es, tmp, sm))
+        // 8 consumer warps: as many orbitals per CTA as 256 threads cover
+        const int tpo = round_up(2 * (nz / (16 / es)), 32);
+        int nb        = 256 / tpo;
+        if (nb < 1) nb = 1;
+        if (nb > 4) nb = 4;
+        if (nb > nfunc) nb = nfunc;
+        for (int s = lap4 ? 4 : 3; s >= 2; s--)
         {
-            best = c;
-            return true;
+            FusedCfg c = { lap4 ? 4 : 8, 2, nb, s, lap4 ? 64 : 128 };
+            if (c.XC > nx) c.XC = nx;
+            FusedParams tmp;
+            size_t sm;
+            if (cfg_layout(c, G, ny, nz, es, tmp, sm))
+            {
+                best = c;
+                return true;
+            }
         }
     }
     double best_cost = 1e30;
@@ -1207,12 +1231,13 @@ int hpsi_tma(const HpsiArgs& a, cudaStream_t st)
     if (peer3)
     {
         P.peer    = 2;
-        P.zsplit  = gr->nproc[2] > 1 || getenv("MGB_HPSI_FORCE_ZBOXES") != nullptr;
         P.first_y = gr->bc[1] != 1 && gr->coord[1] == 0;
         P.last_y  = gr->bc[1] != 1 && gr->coord[1] == gr->nproc[1] - 1;
         P.first_z = gr->bc[2] != 1 && gr->coord[2] == 0;
         P.last_z  = gr->bc[2] != 1 && gr->coord[2] == gr->nproc[2] - 1;
-        if ((rc = nb_table(a.nb3d, f64, nz, ny, nx, (long long)a.ld, a.nfunc, TY, G, st, &P.nbmaps)))
+        P.zsplit = a.nbz != nullptr;
+        if ((rc = nb_table(a.nb3d, a.nbz, f64, nz, ny, nx, (long long)a.ld, a.nfunc, TY, G, st,
+                 &P.nbmaps)))
             return rc;
         if (!lap4)
         {

@@ -158,7 +158,8 @@ __global__ void __launch_bounds__(MAXT, 1) k_mg_jacobi(const __grid_constant__ J
     if (tid < 32)
     {
         // ---------------------------- TMA producer ----------------------------
-        if (tid != 0) return;
+        // (P3: every lane issues, one (function, box) each)
+        if (!P3 && tid != 0) return;
         unsigned char* stages = smem + kMgBarBytes;
         const uint64_t pol    = policy_evict_first();
         int norb              = P.nfunc - orb0;
@@ -184,38 +185,36 @@ __global__ void __launch_bounds__(MAXT, 1) k_mg_jacobi(const __grid_constant__ J
                 // end the box stays out of range on my own block (zero fill)
                 const int dx  = (xc < 0 && !P.end_lo[0]) ? 0 : ((xc >= P.nx && !P.end_hi[0]) ? 2 : 1);
                 const int xcp = dx == 0 ? xc + P.nx : (dx == 2 ? xc - P.nx : xc);
-                const int dyl = (y0 - G < 0 && !P.end_lo[1]) ? 0 : 1;
-                const int yl  = (y0 - G < 0 && !P.end_lo[1]) ? P.ny - G : y0 - G;
-                const int dyh = (y0 + P.TY >= P.ny && !P.end_hi[1]) ? 2 : 1;
-                const int yh  = (y0 + P.TY >= P.ny && !P.end_hi[1]) ? 0 : y0 + P.TY;
-                const int zlc = P.end_lo[2] ? -4 : P.nz - 4;
-                const int zhc = P.end_hi[2] ? P.nz : 0;
                 mbar_wait(&empty[stage], par ^ 1u);
-                mbar_arrive_expect_tx(&full[stage], tx);
-                unsigned char* sb      = stages + (size_t)stage * P.stage_bytes;
-                const CUtensorMap* tab = P.nbmaps + dx * 36;
-                const int dyi[3]       = { dyl, 1, dyh };
-                const int yc[3]        = { yl, y0, yh };
-                const int to[3]        = { 0, P.off_mid, P.off_hi };
-                const int zo[3]        = { 0, P.zarr_mid, P.zarr_hi };
-                for (int o = 0; o < norb; o++)
+                if (tid == 0) mbar_arrive_expect_tx(&full[stage], tx);
+                unsigned char* sb = stages + (size_t)stage * P.stage_bytes;
+                // one lane per (function, box): rows below the tile, the tile's rows, rows
+                // above, each with the 32-byte z-halo entries of its rows
+                for (int l = tid; l < 3 * norb; l += 32)
                 {
+                    const int o = l / 3, b = l - 3 * o;
                     unsigned char* tb = sb + (size_t)o * P.tile_bytes;
-                    const int fo      = orb0 + o;
-#pragma unroll
-                    for (int b = 0; b < 3; b++)
+                    int dyi = 1, yc = y0, to = P.off_mid, zo = P.zarr_mid;
+                    if (b == 0)
                     {
-                        const CUtensorMap* m = tab + dyi[b] * 12;
-                        const int kind       = (b == 1) ? 0 : 1;
-                        tma_load_4d(tb + to[b], m + 4 + kind, &full[stage], 0, yc[b], xcp, fo, pol);
-                        if (P.zsplit && (ZALL || b == 1))
-                        {
-                            tma_load_4d(tb + P.zlo_off + zo[b], m + 2 + kind, &full[stage], zlc,
-                                yc[b], xcp, fo, pol);
-                            tma_load_4d(tb + P.zlo_off + P.zarr_bytes + zo[b], m + 8 + 2 + kind,
-                                &full[stage], zhc, yc[b], xcp, fo, pol);
-                        }
+                        const bool nbr = y0 - G < 0 && !P.end_lo[1];
+                        dyi = nbr ? 0 : 1;
+                        yc  = nbr ? P.ny - G : y0 - G;
+                        to = 0, zo = 0;
                     }
+                    else if (b == 2)
+                    {
+                        const bool nbr = y0 + P.TY >= P.ny && !P.end_hi[1];
+                        dyi = nbr ? 2 : 1;
+                        yc  = nbr ? 0 : y0 + P.TY;
+                        to = P.off_hi, zo = P.zarr_hi;
+                    }
+                    const CUtensorMap* m = P.nbmaps + dx * 36 + dyi * 12;
+                    const int kind       = (b == 1) ? 0 : 1;
+                    tma_load_4d(tb + to, m + 4 + kind, &full[stage], 0, yc, xcp, orb0 + o, pol);
+                    if (P.zsplit && (ZALL || b == 1))
+                        tma_load_4d(tb + P.zlo_off + zo, m + 2 + kind, &full[stage], 0, yc, xcp,
+                            orb0 + o, pol);
                 }
                 if (++stage == S)
                 {
@@ -342,12 +341,12 @@ __global__ void __launch_bounds__(MAXT, 1) k_mg_jacobi(const __grid_constant__ J
         for (int i = 0; i < NW; i++)
         {
             const int t = rr0 - G + i;
-            zrow[i]     = (uint32_t)(t < 0 ? (t + G) * 16
-                                           : (t < P.TY ? P.zarr_mid + t * 16
-                                                       : P.zarr_hi + (t - P.TY) * 16));
+            zrow[i]     = (uint32_t)(t < 0 ? (t + G) * 32
+                                           : (t < P.TY ? P.zarr_mid + t * 32
+                                                       : P.zarr_hi + (t - P.TY) * 32));
         }
         zLb = (uint32_t)(P.zlo_off + 16 - G * 4);
-        zRb = (uint32_t)(P.zlo_off + P.zarr_bytes);
+        zRb = (uint32_t)(P.zlo_off + 16);
     }
     // address of the left / right z neighbours of walked row i in the tile at `base`
     auto zl_addr = [&](uint32_t base, int i) -> uint32_t {
@@ -1133,9 +1132,9 @@ static bool jacobi_layout(const JacobiCfg& c, int G, int ny, int nz, JacobiParam
     {
         P.zlo_off    = P.tile_bytes;
         P.zarr_mid   = 128;
-        P.zarr_hi    = 128 + round_up_i(TY * 16, 128);
+        P.zarr_hi    = 128 + round_up_i(TY * 32, 128);
         P.zarr_bytes = P.zarr_hi + 128;
-        P.tile_bytes += 2 * P.zarr_bytes;
+        P.tile_bytes += P.zarr_bytes;
     }
     P.stage_bytes = c.NB * P.tile_bytes;
     smem          = (size_t)kMgBarBytes + (size_t)c.S * P.stage_bytes;
@@ -1283,10 +1282,10 @@ int mg_jacobi(const MgJacobiArgs& a, cudaStream_t st)
     int rc;
     if (a.nb3d)
     {
-        if ((rc = nb_table(reinterpret_cast<const void* const*>(a.nb3d), false, nz, ny, nx, (long long)a.ld_in, a.nfunc, P.TY, G, st,
-                 &P.nbmaps)))
+        if ((rc = nb_table(reinterpret_cast<const void* const*>(a.nb3d), a.nbz, false, nz, ny, nx,
+                 (long long)a.ld_in, a.nfunc, P.TY, G, st, &P.nbmaps)))
             return rc;
-        P.zsplit = gr.nproc[2] > 1 || getenv("MGB_HPSI_FORCE_ZBOXES") != nullptr;
+        P.zsplit = a.nbz != nullptr;
         for (int d = 0; d < 3; d++)
         {
             P.end_lo[d] = gr.bc[d] != 1 && gr.coord[d] == 0;

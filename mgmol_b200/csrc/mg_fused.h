@@ -39,6 +39,7 @@ struct MgJacobiArgs
     // of the rank at coord + (dx,dy,dz) (my own across a direction that is not split), every
     // halo read in place; null = not this path
     const float* const* nb3d;
+    const void* const* nbz; // z split: the 9 buffers of pushed z-edge columns (comm_zhalo)
 };
 
 // true when the fused kernels can run this level (z extent a multiple of 4,

@@ -501,11 +501,22 @@ static int cycle_fused(mgb_precond* p, int l, const float* f, size_t ldf, double
         XPeers xp;
         const float* nb[27];
         a.nb3d = nullptr;
+        const void* nbz[9];
+        a.nbz = nullptr;
         if (d3)
         {
             if (int rc = nb_peers(p, gr, a.in, nb)) return rc;
             a.nb3d = nb;
             xp.w = xp.e = nullptr;
+            if (gr.nproc[2] > 1 || getenv("MGB_HPSI_FORCE_ZBOXES"))
+            {
+                // z split: nobody is still reading its buffer of pushed columns, then the
+                // source's z-edge columns go to the z neighbours
+                if (split)
+                    if (int rc = comm_barrier_neighbors(p->comm, &gr, st)) return rc;
+                if (int rc = comm_zhalo(p->comm, &gr, 4, a.in, a.ld_in, nfunc, st, nbz)) return rc;
+                a.nbz = nbz;
+            }
         }
         else if (int rc = x_peers(p, gr, a.in, xp))
             return rc;

@@ -95,7 +95,9 @@ int make_map(CUtensorMap* m, bool f64, const void* base, int rank, int nz, int n
 // Device table of the tensor maps over the blocks of the 27 Cartesian neighbours (hpsi_fused.cu;
 // cached per block): index dx*36 + dy*12 + dz*4 + kind, kind 0: box {nz, TY}, 1: {nz, G},
 // 2: {16 bytes of z, TY}, 3: {16 bytes of z, G}
-int nb_table(const void* const* nb, bool f64, int nz, int ny, int nx, long long ld, int nfunc,
-    int TY, int G, cudaStream_t st, const CUtensorMap** out);
+// nbz[side*9 + dx*3 + dy] (or null): the dense buffers of pushed z-edge columns (comm_zhalo)
+// the kind 2 / 3 maps are laid over
+int nb_table(const void* const* nb, const void* const* nbz, bool f64, int nz, int ny, int nx,
+    long long ld, int nfunc, int TY, int G, cudaStream_t st, const CUtensorMap** out);
 
 } // namespace mgb

@@ -508,8 +508,8 @@ class Orbitals:
         n, m = self.numst_, o.numst_
         npt = self.grid_.size()
         if work is not None:
-            bcolor = min(max(bcolor, 1), work.psi_.shape[0])
-            w = work.psi_[:bcolor]
+            bcolor = work.psi_.shape[0]  # the whole work block: one B pass, one contraction
+            w = work.psi_
         else:
             bcolor = min(bcolor, n)
             w = torch.empty((bcolor,) + self.grid_.shape(), dtype=self.psi_.dtype, device="cuda")

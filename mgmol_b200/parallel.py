@@ -155,6 +155,25 @@ def geom(nx, ny, nz, ntasks, bias=1):
     return tuple(ndir)
 
 
+def geom_b200(nx, ny, nz, ntasks):
+    """The decomposition used on an NVLink box: PEenv::geom's factors, but among directions
+    of EQUAL extent -- where the reference's assignment is only a tie-break (z first for a
+    cubic grid) -- the larger factors go to x, then y.  x planes and y rows of a neighbour
+    are contiguous in its memory and are read in place; the z halo is 16 bytes out of every
+    row and has to be pushed into dense buffers first (comm_zhalo), so z is split last."""
+    g = geom(nx, ny, nz, ntasks)
+    if g is None:
+        return None
+    n = (nx, ny, nz)
+    out = list(g)
+    for ext in set(n):
+        idx = [d for d in range(3) if n[d] == ext]
+        fac = sorted((g[d] for d in idx), reverse=True)
+        for d, f in zip(idx, fac):
+            out[d] = f
+    return tuple(out)
+
+
 def cart_coords(rank, nproc):
     """MPI_Cart_coords on the row-major communicator of MPI_Cart_create
     (src/pb/PEenv.cc:89): rank = (cx * py + cy) * pz + cz."""
