@@ -50,7 +50,7 @@ DEFAULT_WORKLOAD = "synth256"
 def layout(args, world):
     """Decomposition and sizes of the workload at `world` GPUs -- shared by both arms so
     that their `config` dicts are identical."""
-    from mgmol_b200.parallel import geom_b200
+    from mgmol_b200.parallel import geom, geom_b200
     w = WORKLOADS[args.workload]
     if args.decomp and args.decomp != "auto":
         nproc = tuple(int(x) for x in args.decomp.lower().split("x"))
@@ -60,7 +60,8 @@ def layout(args, world):
         # PEenv::geom (src/pb/PEenv.cc:335-) on the grid the reference would be given
         nproc = (geom_b200(w["grid"][0], w["grid"][1], w["grid"][2], world) if world > 1
                  else (1, 1, 1))
-        how = "PEenv::geom factors (2x2x2 at 8 ranks), ties between equal directions broken toward x"
+        how = ("factors of the rank count over x and y (z, the contiguous direction, last); "
+               "PEenv::geom would split %s" % "x".join(str(q) for q in (geom(*w["grid"], world) or ())))
         if nproc is None:
             nproc, how = (world, 1, 1), "x slabs (PEenv::geom refuses this mesh)"
     if args.strong or w["fixed"] == "global":
@@ -948,6 +949,8 @@ def run_ours(args):
         sys.stderr.write("bench: multi-GPU parity check FAILED: %s\n" % json.dumps(parity))
         rc = 3
     if world > 1:
+        if os.environ.get("MGB_HPSI_TIMING"):
+            lib().mgb_hpsi_timing_report(rank)
         comm.check()
         dist.destroy_process_group()
     if rc:

@@ -437,6 +437,9 @@ int mgb_hpsi_peer(mgb_comm* c, int lap_type, int dtype, const mgb_grid* grid,
  * per potential update: gfpot of src/Hamiltonian.cc:108-111); may be null for MGB_LAP_4,
  * which multiplies by V at the centre only.  comm may be null on a single rank (every
  * neighbour is the box itself: the periodic wrap).                                     */
+/* With MGB_HPSI_TIMING set in the environment: mean phase times (z push, barrier, kernel,
+ * barrier) of the last mgb_hpsi_peer3d calls of this process, to stderr.  Development aid. */
+void mgb_hpsi_timing_report(int rank);
 int mgb_hpsi_peer3d(mgb_comm* comm, int lap_type, int dtype, const mgb_grid* grid,
     const void* phi, size_t ld, const double* vtot, const double* vghost, void* hphi, size_t ldh,
     int nfunc, void* stream);

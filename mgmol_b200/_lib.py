@@ -140,6 +140,7 @@ _SIGS = {
     "mgb_hpsi_peer": (c_int, [c_void_p, c_int, c_int, ctypes.POINTER(MgbGrid), c_void_p,
                               c_size_t, c_void_p, c_void_p, c_size_t, c_int, c_void_p,
                               c_void_p]),
+    "mgb_hpsi_timing_report": (None, [c_int]),
     "mgb_hpsi_peer3d": (c_int, [c_void_p, c_int, c_int, ctypes.POINTER(MgbGrid), c_void_p,
                                 c_size_t, c_void_p, c_void_p, c_void_p, c_size_t, c_int,
                                 c_void_p]),

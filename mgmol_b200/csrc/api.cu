@@ -1,6 +1,7 @@
 // C-ABI glue: error state, device memory (MemorySpace::Memory<T,Device>), the
 // mgb_hpsi dispatcher and its reference-shaped composition on ghosted blocks.
 #include <cstdarg>
+#include <cstdio>
 #include <cstring>
 #include <mutex>
 
@@ -432,6 +433,9 @@ int mgb_hpsi_peer(mgb_comm* comm, int lap_type, int dtype, const mgb_grid* grid,
 }
 
 
+static cudaEvent_t g_tev[32][5];
+static unsigned long long g_tcall = 0;
+
 int mgb_hpsi_peer3d(mgb_comm* comm, int lap_type, int dtype, const mgb_grid* grid,
     const void* phi, size_t ld, const double* vtot, const double* vghost, void* hphi, size_t ldh,
     int nfunc, void* stream)
@@ -465,20 +469,58 @@ int mgb_hpsi_peer3d(mgb_comm* comm, int lap_type, int dtype, const mgb_grid* gri
                 }
             }
     cudaStream_t st = as_stream(stream);
+    // MGB_HPSI_TIMING: phase times of the last calls (push, barrier, kernel, barrier), printed
+    // by mgb_hpsi_timing_report -- development aid for multi-rank runs
+    static const bool timing = getenv("MGB_HPSI_TIMING") != nullptr;
+    cudaEvent_t* ev = nullptr;
+    if (timing)
+    {
+        if (!g_tev[0][0])
+            for (auto& row : g_tev)
+                for (auto& e : row)
+                    cudaEventCreate(&e);
+        ev = g_tev[g_tcall++ % 32];
+        cudaEventRecord(ev[0], st);
+    }
     // z split: the z-edge columns are pushed into the z neighbours' dense buffers first
     const void* nbz[9];
-    const bool zsplit = grid->nproc[2] > 1 || getenv("MGB_HPSI_FORCE_ZBOXES") != nullptr;
+    // MGB_ZHALO=inplace: the kernel reads the columns from the z neighbours' blocks itself
+    const char* zmode = getenv("MGB_ZHALO");
+    const bool zsplit = (grid->nproc[2] > 1 || getenv("MGB_HPSI_FORCE_ZBOXES") != nullptr)
+                        && !(zmode && zmode[0] == 'i');
     if (zsplit)
         if (int rc = comm_zhalo(comm, grid, dtype == MGB_F64 ? 8 : 4, phi, ld, nfunc, st, nbz))
             return rc;
     // every rank's phi is complete (and its columns have landed) before anybody reads
     // boundary layers ...
+    if (ev) cudaEventRecord(ev[1], st);
     if (int rc = comm_barrier_neighbors(comm, grid, st)) return rc;
+    if (ev) cudaEventRecord(ev[2], st);
     const int rc = hpsi_entry(lap_type, dtype, grid, phi, ld, vtot, hphi, ldh, nfunc, nullptr,
         nullptr, nullptr, nullptr, nullptr, nullptr, stream, nb, vghost, zsplit ? nbz : nullptr);
     if (rc) return rc;
+    if (ev) cudaEventRecord(ev[3], st);
     // ... and nobody overwrites its phi while a neighbour still reads it
-    return comm_barrier_neighbors(comm, grid, st);
+    const int rc2 = comm_barrier_neighbors(comm, grid, st);
+    if (ev) cudaEventRecord(ev[4], st);
+    return rc2;
+}
+
+void mgb_hpsi_timing_report(int rank)
+{
+    if (!g_tev[0][0] || g_tcall < 4) return;
+    cudaDeviceSynchronize();
+    const int n = g_tcall < 32 ? (int)g_tcall : 32;
+    double acc[4] = { 0, 0, 0, 0 };
+    for (int i = 0; i < n; i++)
+        for (int k = 0; k < 4; k++)
+        {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, g_tev[i][k], g_tev[i][k + 1]);
+            acc[k] += ms / n;
+        }
+    fprintf(stderr, "[mgb timing] rank %d: z push %.3f ms, barrier %.3f ms, kernel %.3f ms, barrier %.3f ms "
+                    "(mean of the last %d mgb_hpsi_peer3d calls)\n", rank, acc[0], acc[1], acc[2], acc[3], n);
 }
 
 /* ---- host-buffer entry: H2D copy, fused kernel and D2H copy pipelined over

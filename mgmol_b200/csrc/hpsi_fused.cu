@@ -115,7 +115,8 @@ struct alignas(64) FusedParams
     int zsplit;         // z halo columns come from boxes (z is split), not from the wrapped index
     int first_y, last_y, first_z, last_z; // non-periodic AND at the domain's end
     int per_y, per_z;
-    int zarr_mid, zarr_hi, zarr_bytes, zlo_off; // z-halo entries inside a tile (32 bytes per row)
+    int zarr_mid, zarr_hi, zarr_bytes, zlo_off; // z-halo entries inside a tile
+    int zstride, zhi_off; // 32, 16: pushed buffers (one 32-byte entry per row); 16, zarr_bytes: in place (two arrays)
     int vrow_bytes, nvb;                        // padded V tile: row pitch, boxes per plane
     int pol;      // L2 policy of the phi loads (see the producer)
     int orb_fast; // blockIdx.x walks the orbital blocks (CTAs of a wave share V tiles in L2)
@@ -295,8 +296,21 @@ __global__ void __launch_bounds__(MAXT, 1)
                     tma_load_4d(tb + to, m + 4 + kind, &full[stage], 0, yc, xcp, orb0 + o,
                         b == 1 ? pol_stream : pol_halo);
                     if (P.zsplit && (!LAP4 || b == 1))
-                        tma_load_4d(tb + P.zlo_off + zo, m + 2 + kind, &full[stage], 0, yc, xcp,
-                            orb0 + o, pol_halo);
+                    {
+                        if (P.zstride == 32)
+                            tma_load_4d(tb + P.zlo_off + zo, m + 2 + kind, &full[stage], 0, yc, xcp,
+                                orb0 + o, pol_halo);
+                        else
+                        {
+                            // in place: the z neighbours' last / first 16 bytes of these rows
+                            // (beyond a Dirichlet end: out of range, zero fill)
+                            constexpr int ZH = VEC;
+                            tma_load_4d(tb + P.zlo_off + zo, m + 2 + kind, &full[stage],
+                                P.first_z ? -ZH : P.nz - ZH, yc, xcp, orb0 + o, pol_halo);
+                            tma_load_4d(tb + P.zlo_off + P.zarr_bytes + zo, m + 8 + 2 + kind,
+                                &full[stage], P.last_z ? P.nz : 0, yc, xcp, orb0 + o, pol_halo);
+                        }
+                    }
                 }
             }
             else
@@ -424,13 +438,14 @@ __global__ void __launch_bounds__(MAXT, 1)
             if (!P.first_z) m0 = (CT)1;
             if (!P.first_y) izero = -100;
         }
-        zsA = (rr0 == 0) ? 0u : (uint32_t)(P.zarr_mid + (rr0 - G) * 32);
-        zsB = (uint32_t)(P.zarr_mid + rr0 * 32);
-        zsC = (rr0 + RY == P.TY) ? (uint32_t)P.zarr_hi : (uint32_t)(P.zarr_mid + (rr0 + RY) * 32);
+        zsA = (rr0 == 0) ? 0u : (uint32_t)(P.zarr_mid + (rr0 - G) * P.zstride);
+        zsB = (uint32_t)(P.zarr_mid + rr0 * P.zstride);
+        zsC = (rr0 + RY == P.TY) ? (uint32_t)P.zarr_hi
+                                 : (uint32_t)(P.zarr_mid + (rr0 + RY) * P.zstride);
         // the last G (1: Mehrstellen, 2: 4th order) elements of the low array's row, the
         // first of the high array's
         zLb = (uint32_t)(P.zlo_off + 16 - G * (int)sizeof(T));
-        zRb = (uint32_t)(P.zlo_off + 16);
+        zRb = (uint32_t)(P.zlo_off + P.zhi_off);
     }
 
     const uint32_t stage0 = smem_u32(smem + kBarBytes);
@@ -535,7 +550,7 @@ __global__ void __launch_bounds__(MAXT, 1)
                     for (int r = 0; r < RY; r++)
                     {
                         ro = (r == RY - 1) ? startC : ro + (uint32_t)rb;
-                        zo = (r == RY - 1) ? zsC : zo + 32u;
+                        zo = (r == RY - 1) ? zsC : zo + (uint32_t)P.zstride;
                         load_row(ro, zo, r + 2, Pp, szp, wp, wzp);
                         CT o[VEC];
 #pragma unroll
@@ -677,8 +692,8 @@ __global__ void __launch_bounds__(MAXT, 1)
                         uint32_t aL = pb + ro_c + zloff, aR = pb + ro_c + zroff;
                         if constexpr (PEER == 2)
                         {
-                            if (isL) aL = pb + zLb + zsB + (uint32_t)(r * 32);
-                            if (isR) aR = pb + zRb + zsB + (uint32_t)(r * 32);
+                            if (isL) aL = pb + zLb + zsB + (uint32_t)(r * P.zstride);
+                            if (isR) aR = pb + zRb + zsB + (uint32_t)(r * P.zstride);
                         }
                         lds_pair(aL, L2, L1);
                         lds_pair(aR, R1, R2);
@@ -922,8 +937,10 @@ int nb_table(const void* const* nb, const void* const* nbz, bool f64, int nz, in
     long long ld, int nfunc, int TY, int G, cudaStream_t st, const CUtensorMap** out)
 {
     NbTable* slot = nullptr;
-    const void* nozb[9] = { nullptr };
-    if (!nbz) nbz = nozb;
+    // no buffers of pushed columns: the z maps lie over the z neighbours' blocks themselves
+    const void* inpl[9] = { (const void*)1, nullptr };
+    const bool inplace_z = nbz == nullptr;
+    if (!nbz) nbz = inpl;
     for (auto& t : g_nbtab)
     {
         if (t.dev && t.nz == nz && t.ny == ny && t.nx == nx && t.nfunc == nfunc && t.TY == TY
@@ -945,7 +962,16 @@ int nb_table(const void* const* nb, const void* const* nbz, bool f64, int nz, in
         for (int kind = 0; kind < 4; kind++)
         {
             const bool zbox = kind >= 2, mid = (kind & 1) == 0;
-            if (zbox != (dz == 0)) continue; // z-halo columns: kept in the dz = -1 entries
+            if (zbox && inplace_z)
+            {
+                // z-halo columns read in place: 16 bytes of the rows of the rank across z
+                if (dz == 1 || !nb[r]) continue;
+                if (int rc = make_map_box(&host[r * 4 + kind], f64, nb[r], nz, ny, nx, ld, nfunc, ZH,
+                        mid ? TY : G))
+                    return rc;
+                continue;
+            }
+            if (zbox != (dz == 0)) continue; // pushed z-halo columns: kept in the dz = -1 entries
             if (mid && dy != 1) continue;    // the tile's own rows never come from a y neighbour
             if (!zbox)
             {
@@ -1012,7 +1038,7 @@ static bool cfg_layout(const FusedCfg& c, int G, int ny, int nz, int es,
         P.zarr_mid   = 128;
         P.zarr_hi    = 128 + round_up(TY * 32, 128);
         P.zarr_bytes = P.zarr_hi + 128;
-        P.tile_bytes += P.zarr_bytes;
+        P.tile_bytes += 2 * P.zarr_bytes;
         P.vrow_bytes = P.row_bytes + 32;
     }
     P.stage_bytes = (c.NB + 1) * P.tile_bytes;
@@ -1046,7 +1072,10 @@ static bool choose_cfg(bool lap4, int es, int nx, int ny, int nz, int nfunc,
     // before the next -- at the price of 2G re-read planes per chunk.  One orbital
     // per CTA, 8- / 16-row tiles, the deepest ring that fits.  Measured on B200 at
     // 256^3 (tools/cfg_sweep.py, tools/cfg_try.py; profiles/r02_hpsi_256_cfg.md).
-    if ((size_t)nx * ny * nz * es > ((size_t)48 << 20))
+    const bool big_v = (size_t)nx * ny * nz * es > ((size_t)48 << 20);
+    // ... and the same tile family for any box with 2 KB rows (nz = 256 doubles), whose
+    // tiles the search below would make 8 rows x 3 orbitals with a 2-deep ring
+    if (big_v || nz * es >= 2048)
     {
         // 8 consumer warps: as many orbitals per CTA as 256 threads cover
         const int tpo = round_up(2 * (nz / (16 / es)), 32);
@@ -1056,7 +1085,7 @@ static bool choose_cfg(bool lap4, int es, int nx, int ny, int nz, int nfunc,
         if (nb > nfunc) nb = nfunc;
         for (int s = lap4 ? 4 : 3; s >= 2; s--)
         {
-            FusedCfg c = { lap4 ? 4 : 8, 2, nb, s, lap4 ? 64 : 128 };
+            FusedCfg c = { lap4 ? 4 : 8, 2, nb, s, big_v ? (lap4 ? 64 : 128) : nx };
             if (c.XC > nx) c.XC = nx;
             FusedParams tmp;
             size_t sm;
@@ -1235,7 +1264,9 @@ int hpsi_tma(const HpsiArgs& a, cudaStream_t st)
         P.last_y  = gr->bc[1] != 1 && gr->coord[1] == gr->nproc[1] - 1;
         P.first_z = gr->bc[2] != 1 && gr->coord[2] == 0;
         P.last_z  = gr->bc[2] != 1 && gr->coord[2] == gr->nproc[2] - 1;
-        P.zsplit = a.nbz != nullptr;
+        P.zsplit  = gr->nproc[2] > 1 || getenv("MGB_HPSI_FORCE_ZBOXES") != nullptr;
+        P.zstride = a.nbz ? 32 : 16;
+        P.zhi_off = a.nbz ? 16 : P.zarr_bytes;
         if ((rc = nb_table(a.nb3d, a.nbz, f64, nz, ny, nx, (long long)a.ld, a.nfunc, TY, G, st,
                  &P.nbmaps)))
             return rc;

@@ -156,21 +156,36 @@ def geom(nx, ny, nz, ntasks, bias=1):
 
 
 def geom_b200(nx, ny, nz, ntasks):
-    """The decomposition used on an NVLink box: PEenv::geom's factors, but among directions
-    of EQUAL extent -- where the reference's assignment is only a tie-break (z first for a
-    cubic grid) -- the larger factors go to x, then y.  x planes and y rows of a neighbour
-    are contiguous in its memory and are read in place; the z halo is 16 bytes out of every
-    row and has to be pushed into dense buffers first (comm_zhalo), so z is split last."""
-    g = geom(nx, ny, nz, ntasks)
-    if g is None:
+    """The decomposition used on an NVLink box.  PEenv::geom (above) hands the prime factors
+    of the rank count to the currently largest direction, z first on ties: 1x1x2, 1x2x2,
+    2x2x2 for a cubic grid.  Here the same factors go to x and y only -- the largest local
+    extent first, x on ties -- and to z only when neither can take one (local extents stay
+    multiples of 4 for the two multigrid levels): 2x1x1, 2x2x1, 4x2x1.  Reason, measured on
+    8 x B200 (profiles/r02_decomposition.md): x planes and y rows of a neighbour are
+    contiguous in its memory and the fused kernels read them in place at no measurable
+    cost, while the z halo is 16 bytes out of every row -- 134 M DRAM page activations per
+    step on the 256^3 x 4096 block, 7 ms whether the columns are pushed into dense buffers
+    (comm_zhalo) or fetched in place.  Every px x py x pz decomposition, 2x2x2 included, is
+    served by the same kernels (bench.py --decomp)."""
+    local = [nx, ny, nz]
+    out = [1, 1, 1]
+    m = ntasks
+    primes = []
+    for p in _PRIMES:
+        while m % p == 0:
+            primes.append(p)
+            m //= p
+    if m != 1:
         return None
-    n = (nx, ny, nz)
-    out = list(g)
-    for ext in set(n):
-        idx = [d for d in range(3) if n[d] == ext]
-        fac = sorted((g[d] for d in idx), reverse=True)
-        for d, f in zip(idx, fac):
-            out[d] = f
+    for p in sorted(primes, reverse=True):
+        cands = [d for d in (0, 1) if local[d] % (4 * p) == 0]
+        if not cands and local[2] % (4 * p) == 0:
+            cands = [2]
+        if not cands:
+            return None
+        d = max(cands, key=lambda q: (local[q], -q))
+        out[d] *= p
+        local[d] //= p
     return tuple(out)
 
 

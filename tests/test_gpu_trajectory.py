@@ -18,9 +18,11 @@ GOLD = dict(np.load(os.path.join(ROOT, "tests", "golden", "reference_trajectory.
 
 
 @pytest.mark.parametrize("name", ["sih4", "sih4_4th", "nanowire"])
-@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("mode", [1, 0])
 def test_abpg_trajectory_against_compiled_reference(name, mode):
-    """mode 1: V-cycle in its reference-shaped (bit-identical) form, 2: fused float kernels."""
+    """mode 1: V-cycle in its reference-shaped (bit-identical) form; 0: automatic, i.e. the
+    fused float kernels wherever the grid is eligible (the nanowire box; 40^3 coarsens to
+    10^3, whose z rows are not whole 16-byte vectors, and stays reference-shaped)."""
     from mgmol_b200 import host as H
     c = ap.CASES[name]
     phi, v = ap.inputs(name)
