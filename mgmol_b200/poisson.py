@@ -14,6 +14,7 @@ The solver works on "fields": objects with the GridFuncVector interface of
 host.py.  The default is the device class; the CPU tests drive this very
 control flow with a numpy stand-in to pin it against the compiled reference."""
 import math
+import os
 
 import torch
 
@@ -62,6 +63,12 @@ class PoissonMG:
         self.grid_ = grid.with_ghosts(_MIN_GHOSTS[lap_type])
         self.type_ = lap_type
         self.field_ = _bind(field, dtype)
+        # device fields: the V-cycle -- a fixed sequence of ~200 small kernels down to the
+        # 1^3 level -- is captured once in a CUDA graph and replayed every sweep, so the
+        # host launches one graph instead of ~200 kernels (MGB_POISSON_GRAPH=0: eager)
+        self.use_graph_ = field is None and os.environ.get("MGB_POISSON_GRAPH", "1") != "0"
+        self.graph_ = None
+        self.graph_replays = 0
         self.fully_periodic_ = tuple(grid.bc) == (1, 1, 1)
         self.setup(2, 2, 10, 1.e-16, 10)
         self.nb_sweeps_ = 0
@@ -74,6 +81,35 @@ class PoissonMG:
         self.max_sweeps_ = int(max_sweeps)
         self.tol_ = float(tol)
         self.max_nlevels_ = int(max_nlevels)
+        self.graph_ = None  # the captured cycle depends on nu1, nu2 and the level count
+
+    def _cycle(self, work1, res):
+        """work1 = Vcycle(0, res): eager the first time (warm-up), then a captured graph
+        over two static fields."""
+        if not self.use_graph_ or not torch.cuda.is_available():
+            work1.resetData()
+            self._vcycle(self.type_, work1, res, self.max_nlevels_)
+            return work1
+        if self.graph_ is None:
+            F, grid = self.field_, self.grid_
+            self.g_res_, self.g_work_ = F(grid), F(grid)
+            # the residual always arrives with stale ghosts: the captured sequence trades them
+            self.g_res_.copy_from(res)
+            self.g_res_.set_updated_boundaries(False)
+            self.g_work_.resetData()
+            self._vcycle(self.type_, self.g_work_, self.g_res_, self.max_nlevels_)  # warm-up
+            torch.cuda.synchronize()
+            self.graph_ = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_):
+                self.g_res_.set_updated_boundaries(False)
+                self.g_work_.resetData()
+                self._vcycle(self.type_, self.g_work_, self.g_res_, self.max_nlevels_)
+        self.g_res_.copy_from(res)
+        self.g_res_.set_updated_boundaries(False)
+        self.graph_.replay()
+        self.graph_replays += 1
+        self.g_work_.set_updated_boundaries(False)
+        return self.g_work_
 
     def getNbSweeps(self):
         return self.nb_sweeps_
@@ -161,10 +197,9 @@ class PoissonMG:
                 self.final_relative_residual_ = res_norm * inv_rhs_norm
                 converged = True
                 break
-            work1.resetData()
-            self._vcycle(lt, work1, res, self.max_nlevels_)
+            corr = self._cycle(work1, res)
             self.nb_sweeps_ += 1
-            gf_vh.axpy(1.0, work1)
+            gf_vh.axpy(1.0, corr)
         if not converged:
             gf_vh.applyLap(lt, lhs)
             lhs.axpy(-1.0, rhs)

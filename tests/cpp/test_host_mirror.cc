@@ -234,6 +234,39 @@ static int run(const int lap_type, const double tol, const double mg_tol)
         sizeof(T) == 8 ? "f64" : "f32", worst, mg_tol);
     if (!(worst <= mg_tol)) fails++;
 
+    // --- computeMatB (src/ExtendedGridOrbitals.cc:901-967): vel Phi^T (B Phi), and
+    // addHlocal2matrix (src/Hamiltonian.cc:163-212): hij += vel Phi^T (H_loc Phi)
+    {
+        std::vector<T> bref(npt * N);
+        std::vector<double> ident(N * N, 0.), mb(N * N), mb_ref(N * N);
+        for (int i = 0; i < N; i++)
+            ident[i + i * N] = 1.;
+        oracle_bphi_theta(lap_type, dims, bc, phi.data(), ident.data(), bref.data(), N, npt);
+        oracle_gemm_tn(N, N, (int)npt, grid.vel(), phi.data(), bref.data(), mb_ref.data());
+        DeviceMemory<double> mb_dev((size_t)N * N), acc_dev((size_t)N * N), wk_dev((size_t)N * N);
+        orbitals.computeMatB(orbitals, *hamiltonian.lapOper(), mb_dev.data(), nullptr, nullptr, 2);
+        mb_dev.copy_to_host(mb.data(), mb.size());
+        double bmax = 0., berr = 0.;
+        for (int i = 0; i < N * N; i++)
+        {
+            bmax = std::fmax(bmax, std::fabs(mb_ref[i]));
+            berr = std::fmax(berr, std::fabs(mb[i] - mb_ref[i]));
+        }
+        // hij = 2 * (Phi^T H Phi) after two accumulating calls
+        acc_dev.set(0);
+        hamiltonian.addHlocal2matrix(orbitals, orbitals, acc_dev.data(), wk_dev.data());
+        hamiltonian.addHlocal2matrix(orbitals, orbitals, acc_dev.data(), wk_dev.data(), true);
+        std::vector<double> acc(N * N);
+        acc_dev.copy_to_host(acc.data(), acc.size());
+        double aerr = 0.;
+        for (int i = 0; i < N * N; i++)
+            aerr = std::fmax(aerr, std::fabs(acc[i] - 2. * hij[i]));
+        const double btol = sizeof(T) == 8 ? 1e-11 : 1e-4;
+        std::printf("lap %2d %s  matB        rel err %.3e, addHlocal2matrix %.3e (tol %.0e)\n", lap_type,
+            sizeof(T) == 8 ? "f64" : "f32", berr / bmax, aerr / hmax, btol);
+        if (!(berr <= btol * bmax && aerr <= btol * hmax)) fails++;
+    }
+
     // --- orthonormalizeLoewdin: afterwards the Gram matrix is the identity, and
     // the transform is the symmetric S^-1/2 of the oracle's Gram matrix
     {

@@ -699,6 +699,42 @@ def test_contractions_full_size_against_cublas(H):
 # residual assembly
 # --------------------------------------------------------------------------
 @pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("lap_type", [0, 2])
+@pytest.mark.parametrize("N,dims,bcolor", [(5, (12, 8, 16), 2), (37, (10, 12, 14), 32),
+                                           (130, (16, 16, 24), 64)])
+def test_compute_matB_and_addHlocal2matrix(H, port, dt, lap_type, N, dims, bcolor):
+    """ExtendedGridOrbitals::computeMatB (src/ExtendedGridOrbitals.cc:901-967): matB = vel *
+    Phi^T (B Phi), B the Mehrstellen right-hand-side stencil (identity for the 4th-order
+    operator) applied in blocks of bcolor columns; Hamiltonian::addHlocal2matrix
+    (src/Hamiltonian.cc:163-212): hij += Phi^T H_loc Phi."""
+    ll = (3.0, 2.5, 4.0)
+    phi = synthetic_orbitals(N, dims, dt)
+    v = synthetic_potential(dims)
+    grid = H.Grid(dims, ll, H.ghosts_for(lap_type))
+    orb = H.Orbitals(grid, N, TDT[dt], dev(phi))
+    lap = H.LapFactory.createLap(grid, lap_type)
+    got = host(orb.computeMatB(lap, bcolor=bcolor))
+    bphi = port.lap_rhs(lap_type, phi, ll)
+    f = phi.reshape(N, -1).astype(np.float64)
+    exact = grid.vel() * f @ bphi.reshape(N, -1).astype(np.float64).T
+    scale = grid.vel() * np.abs(f) @ np.abs(bphi.reshape(N, -1).astype(np.float64)).T
+    tol = 1e-13 if dt == np.float64 else 3e-6
+    assert (np.abs(got - exact) / scale).max() <= tol
+    # with a work block: one pass
+    work = H.Orbitals(grid, N, TDT[dt])
+    got2 = host(orb.computeMatB(lap, work=work))
+    assert (np.abs(got2 - exact) / scale).max() <= tol
+    ham = H.Hamiltonian()
+    ham.setup(grid, lap_type)
+    ham.potential(H.Potentials(dev(v)))
+    hij = torch.zeros((N, N), dtype=torch.float64, device="cuda")
+    ham.addHlocal2matrix(orb, orb, hij)
+    ham.addHlocal2matrix(orb, orb, hij, force=True)
+    once = host(ham.addHlocalij(orb))
+    assert np.abs(host(hij) - 2 * once).max() <= 1e-12 * np.abs(once).max()
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
 @pytest.mark.parametrize("bc", [(1, 1, 1), (0, 0, 0)])
 @pytest.mark.parametrize("dims", [(12, 8, 16), (7, 9, 10), (32, 32, 32)])
 def test_apply_b_bit_exact(H, port, dt, bc, dims):
