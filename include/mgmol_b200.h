@@ -299,6 +299,36 @@ int mgb_lap_constants(int lap_type, const double h[3], double out[3]);
 /* OrbitalsPreconditioning::setGamma arithmetic (host)                       */
 double mgb_gamma(double inv_diag, int mg_levels, double vmax, double small_eig);
 
+/* ---- non-local Kleinman-Bylander projectors: the sparse projector
+ *      vectors of KBprojectorSparse (src/KBprojectorSparse.h:39-52) and the two grid-sized
+ *      steps that follow Hamiltonian::applyLocal in MGmol::getHpsiAndTheta
+ *      (src/computeHij.cc:404-455).                                               */
+typedef struct mgb_kb mgb_kb;
+/* dtype: KBPROJDTYPE = ORBDTYPE (src/global.h:38); npt: points of the local box        */
+int mgb_kb_create(mgb_kb** out, int dtype, size_t npt);
+/* One ion overlapping the box (Ions::overlappingNL_ions order): its node list nlindex
+ * (positions in the no-ghost orbital storage; KBprojectorSparse::nlindex_), nproj value
+ * arrays of size_nl values each (host, `dtype`), coeff[p] = kbcoeff_p * sign_p
+ * (src/get_vnlpsi.cc:48-74).  *first_row: the row of its first projector in kbpsi.      */
+int mgb_kb_add_ion(mgb_kb* kb, int size_nl, const int* nlindex, int nproj, const void* proj,
+    const double* coeff, int* first_row);
+int mgb_kb_commit(mgb_kb* kb); /* upload; builds the point-major view of the scatter       */
+int mgb_kb_nrows(const mgb_kb* kb);
+int mgb_kb_destroy(mgb_kb* kb);
+/* KBPsiMatrixSparse::computeKBpsi (src/KBPsiMatrixSparse.cc:136-212; computeLocalElement,
+ * src/KBPsiMatrixInterface.cc:20-60): kbpsi[row * nfunc + f] = vel * <beta_row | psi_f>,
+ * double, device.  psi: the orbitals, or B phi for the Mehrstellen flag.  The sum over the
+ * ranks (globalSumKBpsi) is mgb_allreduce_sum_f64 on kbpsi.                             */
+int mgb_kb_psi(const mgb_kb* kb, int dtype, double vel, const void* psi, size_t ld, int nfunc,
+    double* kbpsi, void* stream);
+/* get_vnlpsi (src/get_vnlpsi.cc:24-87) for every function: vnlpsi_f = sum over the ions, in
+ * order, of (T)(sum_p kbpsi[row_p, f] coeff_p beta_p) with the roundings of axpySKet /
+ * axpyKet (src/KBprojectorSparse.cc:865-908).  add != 0: out_f += vnlpsi_f, the MPaxpy of
+ * computeHnlPhiAndAdd2HPhi (src/computeHij.cc:346-372: H phi += V_nl phi); add == 0:
+ * out_f = vnlpsi_f (Mehrstellen: the caller applies B, mgb_apply_b, then adds).          */
+int mgb_kb_vnlpsi(const mgb_kb* kb, int dtype, const double* kbpsi, void* out, size_t ldo,
+    int nfunc, int add, void* stream);
+
 /* ---- dense contractions: LinearAlgebraUtils<Device>::MPgemm / MPsyrk /
  *      MPgemmNN (src/linear_algebra/mputils.cc:295-1067), as the Orbitals
  *      classes call them.                                                   */

@@ -141,6 +141,16 @@ _SIGS = {
                               c_size_t, c_void_p, c_void_p, c_size_t, c_int, c_void_p,
                               c_void_p]),
     "mgb_hpsi_timing_report": (None, [c_int]),
+    "mgb_kb_create": (c_int, [ctypes.POINTER(c_void_p), c_int, c_size_t]),
+    "mgb_kb_add_ion": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p,
+                               ctypes.POINTER(c_int)]),
+    "mgb_kb_commit": (c_int, [c_void_p]),
+    "mgb_kb_nrows": (c_int, [c_void_p]),
+    "mgb_kb_destroy": (c_int, [c_void_p]),
+    "mgb_kb_psi": (c_int, [c_void_p, c_int, c_double, c_void_p, c_size_t, c_int, c_void_p,
+                           c_void_p]),
+    "mgb_kb_vnlpsi": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_int, c_int,
+                              c_void_p]),
     "mgb_hpsi_peer3d": (c_int, [c_void_p, c_int, c_int, ctypes.POINTER(MgbGrid), c_void_p,
                                 c_size_t, c_void_p, c_void_p, c_void_p, c_size_t, c_int,
                                 c_void_p]),

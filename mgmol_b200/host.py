@@ -779,6 +779,91 @@ class Hamiltonian:
         return phi1.computeLocalProduct(self.hlphi_, comm)
 
 
+class KBProjectors:
+    """The non-local Kleinman-Bylander projectors overlapping the local box, as the sparse
+    vectors KBprojectorSparse holds (src/KBprojectorSparse.h:39-52), with the two grid-sized
+    steps that follow applyLocal in MGmol::getHpsiAndTheta (src/computeHij.cc:404-455):
+    computeKBpsi (src/KBPsiMatrixSparse.cc:136-212) and computeHnlPhiAndAdd2HPhi
+    (src/computeHij.cc:294-375)."""
+
+    def __init__(self, grid, dtype=torch.float64):
+        self.grid_, self.dtype_ = grid, dtype
+        h = ctypes.c_void_p()
+        check(lib().mgb_kb_create(ctypes.byref(h), MGB_F64 if dtype == torch.float64 else MGB_F32,
+                                  grid.size()))
+        self.handle_ = h
+
+    def add_ion(self, nlindex, proj, coeff):
+        """nlindex: node positions in the no-ghost storage; proj: (nproj, size_nl) values;
+        coeff[p] = kbcoeff_p * sign_p.  Returns the row of the ion's first projector."""
+        import numpy as np
+        npdt = np.float64 if self.dtype_ == torch.float64 else np.float32
+        idx = np.ascontiguousarray(nlindex, dtype=np.int32)
+        pr = np.ascontiguousarray(proj, dtype=npdt).reshape(-1, len(idx))
+        cf = np.ascontiguousarray(coeff, dtype=np.float64)
+        assert len(cf) == pr.shape[0]
+        row = ctypes.c_int(0)
+        check(lib().mgb_kb_add_ion(self.handle_, len(idx), idx.ctypes.data_as(ctypes.c_void_p),
+                                   pr.shape[0], pr.ctypes.data_as(ctypes.c_void_p),
+                                   cf.ctypes.data_as(ctypes.c_void_p), ctypes.byref(row)))
+        return row.value
+
+    def commit(self):
+        check(lib().mgb_kb_commit(self.handle_))
+
+    def nrows(self):
+        return lib().mgb_kb_nrows(self.handle_)
+
+    def computeKBpsi(self, orbitals, comm=None, lapOper=None):
+        """kbpsi[row, f] = vel <beta_row | psi_f>, summed over the ranks (globalSumKBpsi).
+        lapOper: the `flag` of the reference -- project B phi instead of phi (Mehrstellen,
+        kbBpsi)."""
+        psi = orbitals.psi_ if isinstance(orbitals, Orbitals) else orbitals
+        if lapOper is not None:
+            psi = lapOper.rhs(psi, torch.empty_like(psi))
+        nf = psi.shape[0]
+        kbpsi = torch.zeros((self.nrows(), nf), dtype=torch.float64, device="cuda")
+        check(lib().mgb_kb_psi(self.handle_, _dt(psi), self.grid_.vel(), _p(psi),
+                               self.grid_.size(), nf, _p(kbpsi), _stream()))
+        if comm is not None:
+            comm.allreduce(kbpsi)
+        return kbpsi
+
+    def getVnlPsi(self, kbpsi, nfunc):
+        """get_vnlpsi (src/get_vnlpsi.cc:24-87) for every function."""
+        out = torch.empty((nfunc,) + tuple(self.grid_.shape()), dtype=self.dtype_, device="cuda")
+        check(lib().mgb_kb_vnlpsi(self.handle_, _dt(out), _p(kbpsi), _p(out), self.grid_.size(),
+                                  nfunc, 0, _stream()))
+        return out
+
+    def computeHnlPhiAndAdd2HPhi(self, kbpsi, hphi, lapOper=None):
+        """src/computeHij.cc:294-375: H phi += V_nl phi (one pass over the touched points), or
+        with the Mehrstellen operator H phi += B (V_nl phi)."""
+        h = hphi.psi_ if isinstance(hphi, Orbitals) else hphi
+        nf = h.shape[0]
+        if lapOper is not None and lapOper.type_ in (0, 10):
+            work = self.getVnlPsi(kbpsi, nf)
+            bw = lapOper.rhs(work, torch.empty_like(work))
+            check(lib().mgb_axpy(_dt(h), h.numel(), 1.0, _p(bw), _p(h), _stream()))
+        else:
+            check(lib().mgb_kb_vnlpsi(self.handle_, _dt(h), _p(kbpsi), _p(h), self.grid_.size(),
+                                      nf, 1, _stream()))
+        if isinstance(hphi, Orbitals):
+            hphi.incrementIterativeIndex()
+        return hphi
+
+    def close(self):
+        if self.handle_ is not None:
+            lib().mgb_kb_destroy(self.handle_)
+            self.handle_ = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def computeRhoUsingBlas3(orbitals1, localX, rho, orbitals2=None):
     """Rho::computeRhoSubdomainUsingBlas3 (src/Rho.cc:359-448) on the whole local
     box: rho (double tensor of the grid's shape) += sum_ij X_ij phi1_i phi2_j."""

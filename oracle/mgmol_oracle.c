@@ -4,7 +4,7 @@
  * and bench.py's cpu_baseline / --impl reference legs may load this; the
  * product library (libmgmol_b200.so) never does.
  *
- * Parity status: PINNED.  tests/test_oracle_vs_ref.py checks every function
+ * Parity status: PINNED.  tests/test_oracle_cpu.py checks every function
  * here bit-for-bit (integer compare of the float/double bit patterns) against
  * the reference's own compiled sources (oracle/_ref/libmgmol_ref.so, built by
  * oracle/Makefile from /root/reference/src, unmodified), and
@@ -44,6 +44,18 @@
 #undef FN
 
 int orc_lap_constants(int lap_type, const double h[3], double out[3]);
+
+/* ---- non-local Kleinman-Bylander projectors (parity unpinned) ---- */
+#define T double
+#define FN(name) ORC_CAT(name, _f64)
+#include "mgmol_oracle_kb.inc"
+#undef T
+#undef FN
+#define T float
+#define FN(name) ORC_CAT(name, _f32)
+#include "mgmol_oracle_kb.inc"
+#undef T
+#undef FN
 
 /* ---- Poisson solvers of the Hartree potential ----------- */
 #define ORC_POISSON_PART 1

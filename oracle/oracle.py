@@ -400,6 +400,47 @@ class Port:
         return vh, bool(conv), tuple(stats)
 
     # -- contractions ---------------------------------------------------------
+    # -- non-local Kleinman-Bylander projectors (row f3; parity unpinned) ------
+    @staticmethod
+    def _kb_pack(ions, dtype):
+        node0, row0, idx, vals, coeff = [0], [0], [], [], []
+        for ion in ions:
+            n = len(ion["nlindex"])
+            pr = np.ascontiguousarray(ion["proj"], dtype=dtype).reshape(-1, n)
+            node0.append(node0[-1] + n)
+            row0.append(row0[-1] + pr.shape[0])
+            idx.append(np.asarray(ion["nlindex"], np.int32))
+            vals.append(pr.reshape(-1))
+            coeff.append(np.asarray(ion["coeff"], np.float64))
+        cat = lambda a, dt: (np.ascontiguousarray(np.concatenate(a), dtype=dt) if a  # noqa: E731
+                             else np.zeros(0, dt))
+        return (np.asarray(node0, np.int64), np.asarray(row0, np.int32), cat(idx, np.int32),
+                cat(vals, dtype), cat(coeff, np.float64))
+
+    def kb_psi(self, ions, psi, vel):
+        """kbpsi[row, f] = vel <beta_row | psi_f> (KBPsiMatrixSparse::computeKBpsi)."""
+        psi = np.ascontiguousarray(psi)
+        nf = psi.shape[0]
+        npt = int(np.prod(psi.shape[1:]))
+        node0, row0, idx, vals, _ = self._kb_pack(ions, psi.dtype)
+        out = np.zeros((int(row0[-1]), nf), np.float64)
+        getattr(self.lib, "orc_kb_psi" + _sfx(psi.dtype))(
+            len(ions), _ptr(node0), _ptr(row0), _ptr(idx), _ptr(vals), ctypes.c_double(vel),
+            _ptr(psi), ctypes.c_size_t(npt), nf, _ptr(out))
+        return out
+
+    def kb_vnlpsi(self, ions, kbpsi, out, add):
+        """get_vnlpsi for every function; add: out += vnlpsi (computeHnlPhiAndAdd2HPhi)."""
+        out = np.array(out, order="C")
+        nf = out.shape[0]
+        npt = int(np.prod(out.shape[1:]))
+        node0, row0, idx, vals, coeff = self._kb_pack(ions, out.dtype)
+        kbpsi = np.ascontiguousarray(kbpsi, np.float64)
+        getattr(self.lib, "orc_kb_vnlpsi" + _sfx(out.dtype))(
+            len(ions), _ptr(node0), _ptr(row0), _ptr(idx), _ptr(vals), _ptr(coeff), _ptr(kbpsi),
+            ctypes.c_size_t(npt), _ptr(out), ctypes.c_size_t(npt), nf, int(bool(add)))
+        return out
+
     def gemm_tn(self, a, b, alpha=1.0):
         """alpha * A^T B for blocks a (m, npt), b (n, npt) -> (m, n) double,
         returned as C[i, j] = alpha * <a_i, b_j>."""
@@ -683,6 +724,41 @@ class Ref:
 # ---------------------------------------------------------------------------
 # Deterministic synthetic inputs
 # ---------------------------------------------------------------------------
+def synthetic_kb_projectors(dims, ll, nions, radius, dtype=np.float64, seed=5):
+    """Sparse projector vectors shaped like KBprojectorSparse's: per ion a ball of nodes
+    around a random centre (periodic wrap, so neighbouring balls overlap) and 1 (s only) or
+    4 (s + three p) value arrays over it: a radial profile times 1, x, y, z.  coeff =
+    kbcoeff * sign.  Ions: list of dicts nlindex / proj (nproj, size_nl) / coeff."""
+    rng = np.random.default_rng(seed)
+    nx, ny, nz = dims
+    h = [l / n for l, n in zip(ll, dims)]
+    ions = []
+    for j in range(nions):
+        c = rng.uniform(0, 1, 3) * np.asarray(ll)
+        r = [int(np.ceil(radius / h[d])) for d in range(3)]
+        c0 = [int(round(c[d] / h[d])) for d in range(3)]
+        ix = np.arange(c0[0] - r[0], c0[0] + r[0] + 1)
+        iy = np.arange(c0[1] - r[1], c0[1] + r[1] + 1)
+        iz = np.arange(c0[2] - r[2], c0[2] + r[2] + 1)
+        X, Y, Z = np.meshgrid(ix * h[0] - c[0], iy * h[1] - c[1], iz * h[2] - c[2], indexing="ij")
+        R2 = X * X + Y * Y + Z * Z
+        inside = R2 <= radius * radius
+        IX, IY, IZ = np.meshgrid(ix % nx, iy % ny, iz % nz, indexing="ij")
+        idx = ((IX * ny + IY) * nz + IZ)[inside].astype(np.int32)
+        idx, first = np.unique(idx, return_index=True)  # a ball wider than the box wraps onto itself
+        prof = np.exp(-2.0 * R2[inside][first] / radius ** 2) * (1.0 - R2[inside][first] / radius ** 2)
+        x, y, z = X[inside][first], Y[inside][first], Z[inside][first]
+        if j % 3 == 0:
+            proj = np.stack([prof, prof * x, prof * y, prof * z])
+            coeff = np.array([1.7, -0.9, -0.9, -0.9]) * (1.0 + 0.1 * j)
+        else:
+            proj = prof[None, :]
+            coeff = np.array([-1.3 if j % 2 else 2.1])
+        ions.append({"nlindex": idx, "proj": proj.astype(dtype), "coeff": coeff})
+    return ions
+
+
+
 H2O512_CELL = 46.9768  # bohr, cubic cell of examples/H2O_512 (h = 0.1835 @256)
 
 

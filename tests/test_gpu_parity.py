@@ -1119,3 +1119,48 @@ def test_orthonormalize_loewdin(H, port, dt, N, dims):
         lp, Vp = np.linalg.eigh(Sp)
         ref = port.gemm_nn(a, (Vp / np.sqrt(lp)) @ Vp.T)
         assert np.abs(got - ref).max() <= eps * cond * np.abs(want).max()
+
+
+# --------------------------------------------------------------------------
+# non-local Kleinman-Bylander projectors (row f3)
+# --------------------------------------------------------------------------
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("lap_type", [0, 2])
+@pytest.mark.parametrize("dims,N,nions,radius", [((12, 10, 16), 5, 7, 0.9),
+                                                 ((32, 32, 32), 9, 20, 1.4)])
+def test_kb_projectors_against_oracle(H, port, dt, lap_type, dims, N, nions, radius):
+    """computeKBpsi and computeHnlPhiAndAdd2HPhi (src/KBPsiMatrixSparse.cc:136-212,
+    src/computeHij.cc:294-375) against the oracle's restatement of the same loops: the
+    projections to a sum-order tolerance, the scatter BIT-IDENTICAL for float (the
+    reference's (T) roundings are reproduced; for double its DAXPY is an un-vendored BLAS)."""
+    from oracle.oracle import synthetic_kb_projectors
+    ll = tuple(0.25 * n for n in dims)
+    ions = synthetic_kb_projectors(dims, ll, nions, radius, dt)
+    grid = H.Grid(dims, ll, H.ghosts_for(lap_type))
+    kbp = H.KBProjectors(grid, TDT[dt])
+    rows = [kbp.add_ion(i["nlindex"], i["proj"], i["coeff"]) for i in ions]
+    kbp.commit()
+    assert rows[0] == 0 and kbp.nrows() == sum(len(i["coeff"]) for i in ions)
+    phi = synthetic_orbitals(N, dims, dt)
+    lap = H.LapFactory.createLap(grid, lap_type)
+    mehr = lap_type == 0
+    # <beta | phi> (or <beta | B phi> with the Mehrstellen flag)
+    kb = host(kbp.computeKBpsi(dev(phi), lapOper=lap if mehr else None))
+    src = port.lap_rhs(lap_type, phi, ll) if mehr else phi
+    kb_ref = port.kb_psi(ions, src, grid.vel())
+    scale = np.abs(kb_ref).max()
+    assert np.abs(kb - kb_ref).max() <= (1e-13 if dt == np.float64 else 1e-6) * scale
+    # H phi += V_nl phi, fed with the ORACLE's projections so that the scatter is compared alone
+    h0 = synthetic_orbitals(N, dims, dt, first=40)
+    dh = dev(h0)
+    kbp.computeHnlPhiAndAdd2HPhi(dev(kb_ref), dh, lapOper=lap)
+    if mehr:
+        v = port.kb_vnlpsi(ions, kb_ref, np.zeros_like(h0), add=False)
+        exp = h0 + port.lap_rhs(0, v, ll)
+    else:
+        exp = port.kb_vnlpsi(ions, kb_ref, h0, add=True)
+    if dt == np.float32:
+        assert bits_equal(host(dh), exp)
+    else:
+        assert rel_inf(host(dh), exp) <= 1e-15
+    kbp.close()
