@@ -474,6 +474,9 @@ def measure_pieces(H, grid, phi, ham, lap_type, tdt, S, norb, npt, comm=None, hs
                           "roofline": _tensor_roofline(2 * fls, ms, fp64_peak, "2 N^2 K (+ 2 N K)")}
         del rho, sub, hsub, rsub
 
+    if comm is None:
+        out.update(measure_kb(H, grid, phi, hphi, tdt, S, norb))
+
     # one orbital-update iteration's worth of the in-scope path, back to back on
     # one stream the way an SCF step orders it: H psi (with the
     # halo), Phi^T H Phi (+ all-reduce), preconditioned residual, Gram
@@ -491,6 +494,38 @@ def measure_pieces(H, grid, phi, ham, lap_type, tdt, S, norb, npt, comm=None, hs
     if comm is None:
         out.update(measure_poisson(H, grid, lap_type))
     return out
+
+
+def measure_kb(H, grid, phi, hphi, tdt, S, norb):
+    """the non-local Kleinman-Bylander projectors on the same block --
+    <beta|phi> for every projector and orbital, then H phi += sum beta c -- on a synthetic
+    ion set shaped like the reference's sparse projectors (balls of ~2 bohr radius, 1 or 4
+    projectors per ion).  A failure here never affects the headline line."""
+    import torch
+    try:
+        from mgmol_b200.synthetic import synthetic_kb_projectors
+        npdt = np.float64 if tdt == torch.float64 else np.float32
+        ll = tuple(grid.ll_)
+        ions = synthetic_kb_projectors(grid.shape(), ll, 96, 2.0, npdt)
+        kbp = H.KBProjectors(grid, tdt)
+        for i in ions:
+            kbp.add_ion(i["nlindex"], i["proj"], i["coeff"])
+        kbp.commit()
+        nodes = sum(len(i["nlindex"]) for i in ions)
+        vals = sum(i["proj"].size for i in ions)
+        kb = kbp.computeKBpsi(phi)
+        ms1 = _time_cuda(torch, lambda: kbp.computeKBpsi(phi), reps=3, warm=1)
+        ms2 = _time_cuda(torch, lambda: kbp.computeHnlPhiAndAdd2HPhi(kb, hphi), reps=3, warm=1)
+        res = {"kb_nonlocal": {
+            "ions": len(ions), "projectors": kbp.nrows(), "nodes": int(nodes),
+            "kbpsi_ms": ms1, "vnlpsi_ms": ms2,
+            "gathered_GBps": norb * (nodes * S + vals * S) / (ms1 * 1e-3) / 1e9,
+            "scattered_GBps": norb * (2 * nodes * S + vals * S) / (ms2 * 1e-3) / 1e9,
+            "bound": "gather / scatter over the ions' balls (sector-granular HBM access)"}}
+        kbp.close()
+        return res
+    except Exception as e:  # noqa: BLE001
+        return {"kb_nonlocal": {"unavailable": "%s: %s" % (type(e).__name__, e)}}
 
 
 def measure_poisson(H, grid, lap_type):
