@@ -604,6 +604,73 @@ def measure_sweep(H, args, store_phi, store_out, fp64_peak):
     return cells
 
 
+def measure_iteration_e2e(H, store_phi, store_out, fp64_peak, with_cpu):
+    """INTEGRATION level 2 end to end, host to host, on the H2O_64 block (128^3 x 256
+    doubles; the 256^3 x 512 block would need 137 GB of pinned host memory): the orbitals
+    go to the device ONCE, one orbital-update iteration's worth of the path runs resident
+    (H psi, Phi^T H Phi, precond_mg on the residual block, Gram, Phi M), and the new orbitals
+    plus the two N x N matrices come back ONCE.  Timed with the host clock around the whole
+    thing, next to the compiled reference's own kernels on the host cores."""
+    import torch
+    n, norb, lap, tdt, S = 128, 256, 2, torch.float64, 8
+    dims = (n, n, n)
+    cell = WORKLOADS["h2o64"]["cell"]
+    need = n ** 3 * norb * S
+    grid = H.Grid(dims, (cell,) * 3, H.ghosts_for(lap))
+    dphi = store_phi.reshape(-1).view(torch.uint8)[:need].view(tdt).view((norb,) + dims)
+    dwork = store_out.reshape(-1).view(torch.uint8)[:need].view(tdt).view((norb,) + dims)
+    dres = store_out.reshape(-1).view(torch.uint8)[need:2 * need].view(tdt).view((norb,) + dims)
+    h_phi = torch.empty((norb,) + dims, dtype=tdt).pin_memory()
+    h_phi.copy_(dphi)
+    h_new = torch.empty_like(h_phi).pin_memory()
+    h_v = (torch.rand(dims, dtype=torch.float64) * 0.1 - 0.75).pin_memory()
+    h_mat = torch.empty((2, norb, norb), dtype=torch.float64).pin_memory()
+    dv = torch.empty(dims, dtype=torch.float64, device="cuda")
+    M = torch.rand((norb, norb), device="cuda", dtype=torch.float64) - 0.5
+    phi = H.Orbitals(grid, norb, tdt, dphi)
+    res = H.Orbitals(grid, norb, tdt, dres)
+    out = H.Orbitals(grid, norb, tdt, dwork)
+    ham = H.Hamiltonian()
+    ham.setup(grid, lap)
+    ham.potential(H.Potentials(dv))
+    pc = H.OrbitalsPreconditioning()
+    pc.setup(phi, 2, lap)
+    pc.gamma_ = 0.3
+
+    def once():
+        dphi.copy_(h_phi, non_blocking=True)
+        dv.copy_(h_v, non_blocking=True)
+        h = ham.applyLocal(phi, True)
+        hij = phi.computeLocalProduct(h)
+        res.psi().copy_(h.psi())
+        pc.precond_mg(res)
+        gram = phi.computeGram()
+        phi.multiplyByMatrix(M, out)
+        h_new.copy_(out.psi(), non_blocking=True)
+        h_mat[0].copy_(hij, non_blocking=True)
+        h_mat[1].copy_(gram, non_blocking=True)
+        torch.cuda.synchronize()
+    once()
+    ts = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        once()
+        ts.append(time.perf_counter() - t0)
+    pc.close()
+    sec = float(np.median(ts))
+    r = {"seconds": sec, "block": "128^3 x 256 orbitals, f64, FDtype=4th (H2O_64)",
+         "h2d_bytes": int(need + n ** 3 * 8), "d2h_bytes": int(need + 2 * norb * norb * 8),
+         "host_GBps_both_ways": (2 * need + n ** 3 * 8) / 1e9 / sec,
+         "sequence": "H2D Phi, V; H psi, Phi^T H Phi, precond_mg, Gram, Phi M; D2H Phi', H, S",
+         "how": "host clock around the whole sequence, median of 3"}
+    if with_cpu:
+        ci = cpu_iteration(lap, dims, (cell,) * 3, np.float64, norb)
+        r["cpu_reference"] = ci
+        r["speedup_vs_cpu_reference"] = ci["seconds"] / sec
+    del h_phi, h_new
+    return r
+
+
 def mgpu_parity(H, comm, rank, world, nproc):
     """N > 1: before anything is timed, the multi-rank path against the ORACLE on a small
     global box (oracle/ is used here as the checker only): H psi with in-place halos (both
@@ -927,6 +994,8 @@ def run_ours(args):
                 pieces[k]["ms_max_over_ranks"] = v
         elif args.workload == "synth256" and not args.no_sweep and args.dtype == "f64":
             pieces["sweep_256"] = measure_sweep(H, args, phi.psi(), ham.hlphi_.psi(), fp64_peak)
+            pieces["iteration_e2e"] = measure_iteration_e2e(
+                H, phi.psi(), ham.hlphi_.psi(), fp64_peak, not args.no_cpu_iteration)
 
     if rank == 0:
         updates_per_step = float(npt) * norb * world
