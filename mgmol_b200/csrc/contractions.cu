@@ -23,6 +23,7 @@
 #include <cstdlib>
 
 #include "hpsi.h"
+#include "tma_ptx.cuh"
 
 namespace mgb
 {
@@ -1093,7 +1094,13 @@ __global__ void k_gemm_nn_ref(long long npt, int n, int k, const T* Phi, long lo
     *o     = base + (T)s;
 }
 
-static int g_f32_exact = 0; // 0: 3xTF32 tensor tiles for float operands, 1: DMMA (double products)
+// tcgen05 (kind::tf32, TMEM) kernel of the float contractions, inside namespace mgb
+#include "tn_umma.cuh"
+
+// float operands: 0 = 3xTF32 tensor tiles (tcgen05 where the kernel takes the shape, else
+// mma.sync), 1 = DMMA (double products), 2 = 3xTF32 on mma.sync only
+static int g_f32_mode = 0;
+#define g_f32_exact (g_f32_mode == 1)
 
 static int num_sms()
 {
@@ -1135,7 +1142,10 @@ static int gemm_tn_t(bool syrk, int m, int n, size_t k, double alpha, const T* A
     W.tn     = (n + BN - 1) / BN;
     W.nbatch = nbatch;
     const bool tf32 = sizeof(T) == 4 && !g_f32_exact;
-    const int sub_shift = tf32 ? 4 : 3;
+    // tcgen05 kernel: TMA needs 16-byte pitches (checked above); MGB_TN_UMMA=0 is a tuning hook
+    bool use_umma = tf32 && g_f32_mode == 0;
+    if (const char* env = getenv("MGB_TN_UMMA")) use_umma = use_umma && atoi(env) != 0;
+    const int sub_shift = use_umma ? 7 : tf32 ? 4 : 3;
     // slab width / ring depth: 16 x 4 or 32 x 3 (MGB_TN_KC, tuning hook)
     int kcv = 32;
     if (const char* env = getenv("MGB_TN_KC")) kcv = atoi(env) == 16 ? 16 : 32;
@@ -1183,7 +1193,57 @@ static int gemm_tn_t(bool syrk, int m, int n, size_t k, double alpha, const T* A
     double* partial
         = (double*)scratch(2, (size_t)W.G * W.smax * BM * BN * sizeof(double));
     if (!partial) return MGB_ECUDA;
-    if (tf32)
+    if (use_umma)
+    {
+        CUtensorMap mapA, mapB;
+        if (int rc = umma::make_map_kmajor(&mapA, (const float*)A, k, m, lda, strideA, nbatch))
+            return rc;
+        if (int rc = umma::make_map_kmajor(&mapB, (const float*)B, k, n, ldb, strideB, nbatch))
+            return rc;
+        // chunk = slabs summed in TMEM, fold = chunk sums added in FP32 before the double sums
+        int ch = 4, fold = 16, trunc = 1, ts = 1, perm = 1;
+        if (const char* env = getenv("MGB_UMMA_PERM")) perm = atoi(env);
+        if (const char* env = getenv("MGB_UMMA_TS")) ts = atoi(env);
+        if (const char* env = getenv("MGB_UMMA_CH")) ch = atoi(env) > 0 ? atoi(env) : ch;
+        if (const char* env = getenv("MGB_UMMA_FOLD")) fold = atoi(env) > 0 ? atoi(env) : fold;
+        if (const char* env = getenv("MGB_UMMA_TRUNC")) trunc = atoi(env);
+        int dbg = 0;
+        if (const char* env = getenv("MGB_UMMA_DBG")) dbg = atoi(env);
+#define MGB_UMMA_LAUNCH(SY, TR)                                                           \
+    if (ts)                                                                               \
+    {                                                                                     \
+        auto kern = umma::k_gemm_tn_umma_ts<SY, TR>;                                      \
+        MGB_CUDA(cudaFuncSetAttribute(                                                    \
+            kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)umma::SMEM));         \
+        kern<<<W.G, umma::NTHR, umma::SMEM, st>>>(mapA, mapB, W, m, n, alpha, beta, C,   \
+            ldc, (long long)strideC, partial, ch, fold, perm, dbg);                       \
+    }                                                                                     \
+    else                                                                                  \
+    {                                                                                     \
+        auto kern = umma::k_gemm_tn_umma<SY, TR>;                                         \
+        MGB_CUDA(cudaFuncSetAttribute(                                                    \
+            kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)umma::SMEM));         \
+        kern<<<W.G, umma::NTHR, umma::SMEM, st>>>(mapA, mapB, W, m, n, alpha, beta, C,   \
+            ldc, (long long)strideC, partial, ch, fold, perm);                            \
+    }
+        if (syrk)
+        {
+            if (trunc)
+                MGB_UMMA_LAUNCH(true, true)
+            else
+                MGB_UMMA_LAUNCH(true, false)
+        }
+        else
+        {
+            if (trunc)
+                MGB_UMMA_LAUNCH(false, true)
+            else
+                MGB_UMMA_LAUNCH(false, false)
+        }
+#undef MGB_UMMA_LAUNCH
+        MGB_LAUNCHED("k_gemm_tn_umma");
+    }
+    else if (tf32)
     {
         const size_t smem32 = (size_t)2 * ST32 * 128 * P32 * sizeof(float);
         if (syrk)
@@ -1432,8 +1492,8 @@ int mgb_debug_tn_plan(int syrk, int m, int n, size_t k, int nbatch, int kc, int 
 
 int mgb_set_f32_contraction(int mode)
 {
-    MGB_REQUIRE(mode == 0 || mode == 1, "mgb_set_f32_contraction: mode %d", mode);
-    g_f32_exact = mode;
+    MGB_REQUIRE(mode >= 0 && mode <= 2, "mgb_set_f32_contraction: mode %d", mode);
+    g_f32_mode = mode;
     return MGB_OK;
 }
 

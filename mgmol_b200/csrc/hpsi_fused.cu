@@ -793,12 +793,7 @@ __global__ void k_f64_to_f32(size_t n, const double* __restrict__ in,
 // ---------------------------------------------------------------------------
 // Host side
 // ---------------------------------------------------------------------------
-typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
-    void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static PFN_encodeTiled get_encode()
+PFN_encodeTiled get_encode()
 {
     static PFN_encodeTiled fn = nullptr;
     if (!fn)

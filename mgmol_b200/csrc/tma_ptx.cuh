@@ -86,6 +86,13 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map,
 }
 
 
+// Host: the driver's cuTensorMapEncodeTiled, resolved through the runtime (hpsi_fused.cu);
+// null when the entry point is missing
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+PFN_encodeTiled get_encode();
+
 // Host: tiled tensor map of a no-ghost block viewed as (z, y, x [, function])
 // with a box of `rows` full z-rows of one plane (hpsi_fused.cu).  Out-of-range
 // coordinates are zero-filled.
