@@ -665,7 +665,9 @@ __global__ void k_tn_fixup(TnWork W, int m, int n, const double* __restrict__ pa
         const int nn = tile_n * BN + nl;
         if (diag && nl > ml) continue; // lower triangle of the diagonal tile
         // mirrored half-sums are folded across subtiles (8x8 DMMA / 16x16 TF32)
-        const bool fold = diag && (ml >> sub_shift) != (nl >> sub_shift);
+        // sub_shift < 0 (tcgen05 kernel): the tile holds P with S = (P + P^T) / 2
+        const bool fold = diag && (sub_shift < 0 || (ml >> sub_shift) != (nl >> sub_shift));
+        const double fs = (diag && sub_shift < 0) ? 0.5 : 1.;
         double s = 0.;
         bool any = false;
         for (int i = 0; i < ns; i++)
@@ -679,7 +681,7 @@ __global__ void k_tn_fixup(TnWork W, int m, int n, const double* __restrict__ pa
         }
         if (!any || mm >= m || nn >= n) continue;
         const double old = (beta == 0.) ? 0. : beta * Cb[(size_t)nn * ldc + mm];
-        const double val = alpha * s + old;
+        const double val = alpha * (fs * s) + old;
         Cb[(size_t)nn * ldc + mm] = val;
         if (SYRK) Cb[(size_t)mm * ldc + nn] = val;
     }
@@ -1145,11 +1147,21 @@ static int gemm_tn_t(bool syrk, int m, int n, size_t k, double alpha, const T* A
     // tcgen05 kernel: TMA needs 16-byte pitches (checked above); MGB_TN_UMMA=0 is a tuning hook
     bool use_umma = tf32 && g_f32_mode == 0;
     if (const char* env = getenv("MGB_TN_UMMA")) use_umma = use_umma && atoi(env) != 0;
-    const int sub_shift = use_umma ? 7 : tf32 ? 4 : 3;
+    const int sub_shift = use_umma ? -1 : tf32 ? 4 : 3;
     // slab width / ring depth: 16 x 4 or 32 x 3 (MGB_TN_KC, tuning hook)
     int kcv = 32;
     if (const char* env = getenv("MGB_TN_KC")) kcv = atoi(env) == 16 ? 16 : 32;
     if (tf32) kcv = KC32;
+    // tcgen05 kernel: one k-iteration = one TMA box of KO 32-point slabs (5-D maps: whole 8-row
+    // groups and whole slabs only; any other shape takes one slab per box)
+    int ko = 1;
+    if (use_umma)
+    {
+        ko = (m % 8 == 0 && n % 8 == 0 && k % 32 == 0) ? 2 : 1;
+        if (const char* env = getenv("MGB_UMMA_KO"))
+            if (ko > 1 && atoi(env) >= 1 && atoi(env) <= 2) ko = atoi(env);
+        kcv = 32 * ko;
+    }
     const int st_ = kcv == 32 ? 3 : 4;
     W.nkt    = (long long)((k + kcv - 1) / kcv);
     // cost of one k-iteration: a diagonal Gram tile issues 136 of the 256 DMMAs
@@ -1157,6 +1169,7 @@ static int gemm_tn_t(bool syrk, int m, int n, size_t k, double alpha, const T* A
     W.cf = 16;
     W.cd = 10;
     if (sizeof(T) == 4 && !g_f32_exact) W.cd = 12; // 3xTF32: 16x16 pairing, measured best
+    if (use_umma) W.cd = 11;                       // 2 of 3 MMAs, one operand box, no low tile of B
     if (const char* env = getenv("MGB_SYRK_DIAG_COST"))
     {
         const int c = atoi(env);
@@ -1179,6 +1192,14 @@ static int gemm_tn_t(bool syrk, int m, int n, size_t k, double alpha, const T* A
     if (G > num_sms()) G = num_sms();
     if (G > 256) G = 256; // k_tn_fixup resolves one CTA per thread of its block
     W.G = (int)G;
+    // tcgen05 kernel, tiles of equal cost: give every tile the same number of CTAs when that
+    // idles at most 1/16 of them -- CTA g then works on tile g / ng and K range g % ng, and the NT
+    // CTAs of a K range start on the same operand boxes together (reuse through L2)
+    if (use_umma && !syrk && W.NT >= 2 && W.G >= W.NT)
+    {
+        const int gm = W.NT * (W.G / W.NT);
+        if ((W.G - gm) * 16 <= W.G) W.G = gm;
+    }
     // partial slots per CTA = the most tiles one CTA's share touches
     int smax = 1;
     for (int g = 0; g < W.G; g++)
@@ -1196,50 +1217,44 @@ static int gemm_tn_t(bool syrk, int m, int n, size_t k, double alpha, const T* A
     if (use_umma)
     {
         CUtensorMap mapA, mapB;
-        if (int rc = umma::make_map_kmajor(&mapA, (const float*)A, k, m, lda, strideA, nbatch))
+        if (int rc = umma::make_map_kmajor(&mapA, (const float*)A, k, m, lda, strideA, nbatch, ko))
             return rc;
-        if (int rc = umma::make_map_kmajor(&mapB, (const float*)B, k, n, ldb, strideB, nbatch))
+        if (int rc = umma::make_map_kmajor(&mapB, (const float*)B, k, n, ldb, strideB, nbatch, ko))
             return rc;
-        // chunk = slabs summed in TMEM, fold = chunk sums added in FP32 before the double sums
-        int ch = 4, fold = 16, trunc = 1, ts = 1, perm = 1;
-        if (const char* env = getenv("MGB_UMMA_PERM")) perm = atoi(env);
-        if (const char* env = getenv("MGB_UMMA_TS")) ts = atoi(env);
-        if (const char* env = getenv("MGB_UMMA_CH")) ch = atoi(env) > 0 ? atoi(env) : ch;
+        // fold = chunk (box) sums added in FP32 registers before they go into the double sums
+        int fold = 32, trunc = 1;
         if (const char* env = getenv("MGB_UMMA_FOLD")) fold = atoi(env) > 0 ? atoi(env) : fold;
         if (const char* env = getenv("MGB_UMMA_TRUNC")) trunc = atoi(env);
-        int dbg = 0;
-        if (const char* env = getenv("MGB_UMMA_DBG")) dbg = atoi(env);
-#define MGB_UMMA_LAUNCH(SY, TR)                                                           \
-    if (ts)                                                                               \
+#define MGB_UMMA_LAUNCH(SY, TR, KOV)                                                      \
     {                                                                                     \
-        auto kern = umma::k_gemm_tn_umma_ts<SY, TR>;                                      \
+        auto kern = umma::k_gemm_tn_umma<SY, TR, KOV>;                                    \
         MGB_CUDA(cudaFuncSetAttribute(                                                    \
             kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)umma::SMEM));         \
         kern<<<W.G, umma::NTHR, umma::SMEM, st>>>(mapA, mapB, W, m, n, alpha, beta, C,   \
-            ldc, (long long)strideC, partial, ch, fold, perm, dbg);                       \
-    }                                                                                     \
-    else                                                                                  \
+            ldc, (long long)strideC, partial, fold);                                      \
+    }
+#define MGB_UMMA_KO(SY, TR)                                                               \
     {                                                                                     \
-        auto kern = umma::k_gemm_tn_umma<SY, TR>;                                         \
-        MGB_CUDA(cudaFuncSetAttribute(                                                    \
-            kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)umma::SMEM));         \
-        kern<<<W.G, umma::NTHR, umma::SMEM, st>>>(mapA, mapB, W, m, n, alpha, beta, C,   \
-            ldc, (long long)strideC, partial, ch, fold, perm);                            \
+        if (ko == 2)                                                                      \
+            MGB_UMMA_LAUNCH(SY, TR, 2)                                                    \
+        else                                                                              \
+            MGB_UMMA_LAUNCH(SY, TR, 1)                                                    \
     }
         if (syrk)
         {
             if (trunc)
-                MGB_UMMA_LAUNCH(true, true)
+                MGB_UMMA_KO(true, true)
             else
-                MGB_UMMA_LAUNCH(true, false)
+                MGB_UMMA_KO(true, false)
         }
         else
         {
             if (trunc)
-                MGB_UMMA_LAUNCH(false, true)
+                MGB_UMMA_KO(false, true)
             else
-                MGB_UMMA_LAUNCH(false, false)
+                MGB_UMMA_KO(false, false)
         }
+#undef MGB_UMMA_KO
 #undef MGB_UMMA_LAUNCH
         MGB_LAUNCHED("k_gemm_tn_umma");
     }

@@ -97,24 +97,24 @@ def main():
     ap.add_argument("--big", action="store_true")
     ap.add_argument("--trunc", default="1,0")
     ap.add_argument("--ch", default="8")
-    ap.add_argument("--fold", default="16")
-    ap.add_argument("--ts", default="1")
-    ap.add_argument("--perm", default="1")
+    ap.add_argument("--fold", default="32")
+    ap.add_argument("--ko", default="2")
+    ap.add_argument("--lock", default="1")
     ap.add_argument("--legacy", action="store_true")
     ap.add_argument("--nosmall", action="store_true")
     ap.add_argument("--shapes", default="256x2097152,512x2097152,1024x884736")
     args = ap.parse_args()
     modes = []
-    for ts, pm in [(t_, p_) for t_ in args.ts.split(",") for p_ in args.perm.split(",")]:
+    for ko, lk in [(k_, l_) for k_ in args.ko.split(",") for l_ in args.lock.split(",")]:
         for tr in args.trunc.split(","):
             for ch in args.ch.split(","):
                 for fo in args.fold.split(","):
-                    modes.append((f"umma ts={ts} perm={pm} trunc={tr} ch={ch} fold={fo}", 0,
+                    modes.append((f"umma ko={ko} lock={lk} trunc={tr} fold={fo}", 0,
                                   {"MGB_UMMA_TRUNC": tr, "MGB_UMMA_CH": ch, "MGB_UMMA_FOLD": fo,
-                                   "MGB_UMMA_TS": ts, "MGB_UMMA_PERM": pm}))
+                                   "MGB_UMMA_KO": ko, "MGB_UMMA_LOCK": lk}))
     if args.legacy:
         modes += [("mma.sync 3xTF32", 2, {}), ("DMMA widened", 1, {})]
-    small = [(128, 4096), (130, 6144), (256, 32768), (300, 65536), (37, 1680)]
+    small = [(128, 4096), (130, 6144), (256, 32768), (304, 65536), (37, 1680), (136, 4000)]
     for N, K in ([] if args.nosmall else small):
         for positive in (False, True):
             run_case(N, K, positive, modes, False)
