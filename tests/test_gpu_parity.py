@@ -580,12 +580,13 @@ def test_gram_and_projection(H, port, dt, N, dims):
     na = np.sqrt(np.diag(ex))
     exp = _exact_tn(a, b, grid.vel())
     nb = np.sqrt(np.diag(_exact_tn(b, b, grid.vel())))
-    # float operands: mode 0 = 3xTF32 tensor tiles (F32_TC_TOL of |a||b|, bar
-    # 1e-5), mode 1 = DMMA on widened operands (double products and sums)
-    for mode in ((0, 1) if dt == np.float32 else (0,)):
+    # float operands: mode 0 = 3xTF32 tensor tiles on tcgen05 (F32_TC_TOL of |a||b|, bar
+    # 1e-5), mode 2 = the same arithmetic on mma.sync, mode 1 = DMMA on widened operands
+    # (double products and sums)
+    for mode in ((0, 2, 1) if dt == np.float32 else (0,)):
         check(lib().mgb_set_f32_contraction(mode))
         try:
-            rel = F32_TC_TOL if (dt == np.float32 and mode == 0) else 4 * K * eps
+            rel = F32_TC_TOL if (dt == np.float32 and mode != 1) else 4 * K * eps
             S = host(A.computeGram())
             assert (np.abs(S - ex) <= rel * np.outer(na, na) + 1e-300).all()
             assert np.array_equal(S, S.T), "Gram must be exactly symmetric"
@@ -665,6 +666,90 @@ def test_contractions_many_tiles_streamk(H, dt, N, dims):
                             c.data_ptr(), N, None))
     got = host(c).T
     assert (np.abs(got - (0.5 * exp - 2.0 * C0)) <= bound + 4 * eps * np.abs(C0)).all()
+
+
+@pytest.mark.parametrize("N,K,lda", [(128, 4096, 4096), (136, 4000, 4000), (130, 6144, 6148),
+                                     (256, 32768, 32768), (304, 65536, 65600), (37, 1680, 1680),
+                                     (8, 64, 64), (264, 2080, 2080)])
+@pytest.mark.parametrize("positive", [False, True])
+def test_f32_contractions_tcgen05(N, K, lda, positive):
+    """k_gemm_tn_umma (tcgen05 kind::tf32, A from TMEM, TMA boxes of two K slabs) through
+    mgb_syrk_t / mgb_gemm_tn: shapes that take the 5-D maps (rows % 8 == 0, K % 32 == 0) and
+    shapes that take one slab per box, ragged tiles, a padded leading dimension, all-positive
+    operands (the tensor core's truncating FP32 sums bias those), against the exact FP64
+    contraction and against the mma.sync 3xTF32 kernel; exact symmetry, run-to-run determinism,
+    beta accumulation.  Arithmetic of the reference: src/linear_algebra/mputils.cc:848-948."""
+    from mgmol_b200._lib import lib, check
+    g = torch.Generator(device="cuda").manual_seed(1000 + N)
+    a = torch.rand((N, lda), generator=g, device="cuda", dtype=torch.float32)
+    b = torch.rand((N, lda), generator=g, device="cuda", dtype=torch.float32)
+    if not positive:
+        a -= 0.5
+        b -= 0.5
+    ad, bd = a[:, :K].double(), b[:, :K].double()
+    exg, exp = ad @ ad.t(), ad @ bd.t()
+    na, nb = torch.sqrt(torch.diag(exg)), torch.sqrt((bd * bd).sum(1))
+    S = torch.full((N, N), float("nan"), device="cuda", dtype=torch.float64)
+    P = torch.full((N, N), float("nan"), device="cuda", dtype=torch.float64)
+    res = {}
+    for mode in (0, 2):
+        check(lib().mgb_set_f32_contraction(mode))
+        try:
+            check(lib().mgb_syrk_t(0, N, K, 1.0, a.data_ptr(), lda, S.data_ptr(), N, None))
+            check(lib().mgb_gemm_tn(0, N, N, K, 1.0, a.data_ptr(), lda, b.data_ptr(), lda, 0.0,
+                                    P.data_ptr(), N, None))
+            torch.cuda.synchronize()
+            # column-major C(i, j): the row-major torch view is C^T
+            assert bool(((S.t() - exg).abs() <= F32_TC_TOL * torch.outer(na, na)).all()), mode
+            assert bool(((P.t() - exp).abs() <= F32_TC_TOL * torch.outer(na, nb)).all()), mode
+            assert torch.equal(S, S.t())
+            res[mode] = (S.clone(), P.clone())
+            if mode == 0:
+                S2, P2 = torch.empty_like(S), torch.empty_like(P)
+                check(lib().mgb_syrk_t(0, N, K, 1.0, a.data_ptr(), lda, S2.data_ptr(), N, None))
+                check(lib().mgb_gemm_tn(0, N, N, K, 1.0, a.data_ptr(), lda, b.data_ptr(), lda, 0.0,
+                                        P2.data_ptr(), N, None))
+                assert torch.equal(S, S2) and torch.equal(P, P2), "deterministic summation order"
+                C0 = torch.randn((N, N), generator=g, device="cuda", dtype=torch.float64)
+                Cb = C0.clone()
+                check(lib().mgb_gemm_tn(0, N, N, K, 0.5, a.data_ptr(), lda, b.data_ptr(), lda, -2.0,
+                                        Cb.data_ptr(), N, None))
+                want = 0.5 * exp.t() - 2.0 * C0
+                bound = F32_TC_TOL * torch.outer(nb, na) + 1e-15 * C0.abs()
+                assert bool(((Cb - want).abs() <= bound).all())
+        finally:
+            check(lib().mgb_set_f32_contraction(0))
+    # both kernels implement the same 3xTF32 arithmetic
+    assert bool(((res[0][1] - res[2][1]).abs() <= 2 * F32_TC_TOL * torch.outer(nb, na)).all())
+
+
+def test_f32_contractions_tcgen05_full_size():
+    """128^3 x 256 float (the ORBDTYPE float shape of H2O_64): Gram and Phi^T (H Phi) on the
+    tcgen05 kernel against FP64 cuBLAS on the widened operands."""
+    from mgmol_b200._lib import lib, check
+    N, K = 256, 128 ** 3
+    g = torch.Generator(device="cuda").manual_seed(3)
+    a = torch.rand((N, K), generator=g, device="cuda", dtype=torch.float32) - 0.5
+    b = torch.rand((N, K), generator=g, device="cuda", dtype=torch.float32) - 0.25
+    exg = torch.zeros((N, N), device="cuda", dtype=torch.float64)
+    exp = torch.zeros((N, N), device="cuda", dtype=torch.float64)
+    nb2 = torch.zeros(N, device="cuda", dtype=torch.float64)
+    step = 1 << 19
+    for k0 in range(0, K, step):
+        ad, bd = a[:, k0:k0 + step].double(), b[:, k0:k0 + step].double()
+        exg += ad @ ad.t()
+        exp += ad @ bd.t()
+        nb2 += (bd * bd).sum(1)
+    na, nb = torch.sqrt(torch.diag(exg)), torch.sqrt(nb2)
+    S = torch.empty((N, N), device="cuda", dtype=torch.float64)
+    P = torch.empty((N, N), device="cuda", dtype=torch.float64)
+    check(lib().mgb_syrk_t(0, N, K, 1.0, a.data_ptr(), K, S.data_ptr(), N, None))
+    check(lib().mgb_gemm_tn(0, N, N, K, 1.0, a.data_ptr(), K, b.data_ptr(), K, 0.0, P.data_ptr(), N,
+                            None))
+    torch.cuda.synchronize()
+    assert bool(((S.t() - exg).abs() <= F32_TC_TOL * torch.outer(na, na)).all())
+    assert bool(((P.t() - exp).abs() <= F32_TC_TOL * torch.outer(na, nb)).all())
+    assert torch.equal(S, S.t())
 
 
 def test_contractions_full_size_against_cublas(H):
