@@ -598,10 +598,93 @@ def measure_sweep(H, args, store_phi, store_out, fp64_peak):
             grid = H.Grid(dims, (cell,) * 3, 1)
             o = H.Orbitals(grid, norb, tdt, a)
             ms = _time_cuda(torch, lambda: o.computeGram(), reps=3, warm=1)
-            cells.append({"dtype": dname, "piece": "gram", "orbitals": norb, "ms": ms,
-                          "roofline": _tensor_roofline(float(norb) ** 2 * n ** 3, ms, fp64_peak,
-                                                       "N^2 K (syrk)")})
+            if dname == "f64":
+                rf = _tensor_roofline(float(norb) ** 2 * n ** 3, ms, fp64_peak, "N^2 K (syrk)")
+            else:
+                # 3xTF32 on tcgen05: three tensor products per pair (pieces.f32_contractions has
+                # the measured TF32 peak and the issued-flop count)
+                rf = {"bound": "tensor", "unit": "TFLOP/s", "flops": "N^2 K (syrk), useful",
+                      "achieved": float(norb) ** 2 * n ** 3 / (ms * 1e-3) / 1e12}
+            cells.append({"dtype": dname, "piece": "gram", "orbitals": norb, "ms": ms, "roofline": rf})
     return cells
+
+
+def tf32_tensor_peak(torch):
+    """TF32 tensor peak: large square cuBLAS SGEMM with TF32 allowed, best of 2 medians
+    (MEASURED_PEAKS holds bf16 only)."""
+    m = 8192
+    x = torch.rand((m, m), device="cuda", dtype=torch.float32)
+    y = torch.rand((m, m), device="cuda", dtype=torch.float32)
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        best = min(_time_cuda(torch, lambda: torch.matmul(x, y), reps=3, warm=1) for _ in range(2))
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    del x, y
+    return 2.0 * m ** 3 / (best * 1e-3) / 1e12
+
+
+def measure_f32_contractions(H, store_phi, store_out):
+    """ORBDTYPE float contractions (north star: FP32 tensor-core tiles): Gram, Phi^T (H Phi) and
+    Phi M on the H2O_64 block shape (128^3 x 256) and on the 256^3 x 512 sweep block, in views
+    of the headline's two allocations.  Gram and Phi^T H Phi run on tcgen05 (kind::tf32, 3xTF32
+    split, TMEM accumulators): `executed` counts the tensor flops actually issued (3 products
+    per pair, 2 on diagonal Gram tiles) against the TF32 tensor peak cuBLAS reaches in this
+    run; `useful` is the contraction itself; the operand stream against the HBM peak is the
+    other bound.  Phi M is the mma.sync 3xTF32 kernel.  A failure here never affects the
+    headline line."""
+    import torch
+    from mgmol_b200._lib import lib, check
+    hbm, _ = measured_peaks()
+    try:
+        peak = tf32_tensor_peak(torch)
+        out = {"tf32_tensor_peak_tflops": {"value": peak,
+                                           "how": "cuBLAS SGEMM 8192^3 with TF32 allowed, measured in this run"},
+               "arithmetic": "3xTF32 split products, chunked FP32 sums folded into double "
+                             "(<= 3e-6 of |a||b| against the exact contraction in the tests)",
+               "cells": []}
+        for n, norb in ((128, 256), (256, 512)):
+            K = n ** 3
+            need = K * norb * 4
+            if need > store_phi.numel() * store_phi.element_size():
+                continue
+            a = store_phi.reshape(-1).view(torch.uint8)[:need].view(torch.float32).view(norb, K)
+            b = store_out.reshape(-1).view(torch.uint8)[:need].view(torch.float32).view(norb, K)
+            a.uniform_(-0.5, 0.5)
+            b.uniform_(-0.5, 0.5)
+            C = torch.empty((norb, norb), device="cuda", dtype=torch.float64)
+            M = torch.rand((norb, norb), device="cuda", dtype=torch.float64) - 0.5
+            fl = float(norb) * norb * K
+            tm = (norb + 127) // 128
+            tile = 2.0 * 128 * 128 * K
+
+            def cell(piece, ms, useful, executed, bytes_, kernel):
+                r = {"grid": [n, n, n], "orbitals": norb, "dtype": "f32", "piece": piece, "ms": ms,
+                     "kernel": kernel, "useful_tflops": useful / (ms * 1e-3) / 1e12,
+                     "operand_GBps": bytes_ / (ms * 1e-3) / 1e9,
+                     "operand_frac_of_hbm": bytes_ / (ms * 1e-3) / 1e9 / hbm}
+                if executed:
+                    r["roofline"] = _tensor_roofline(executed, ms, peak,
+                                                     "tensor flops issued (3xTF32), TF32 peak")
+                return r
+            ms = _time_cuda(torch, lambda: check(lib().mgb_syrk_t(
+                0, norb, K, 1.0, a.data_ptr(), K, C.data_ptr(), norb, None)), reps=5, warm=2)
+            out["cells"].append(cell("gram", ms, fl, tile * (3 * tm * (tm - 1) / 2 + 2 * tm),
+                                     4.0 * K * norb, "k_gemm_tn_umma<SYRK>"))
+            ms = _time_cuda(torch, lambda: check(lib().mgb_gemm_tn(
+                0, norb, norb, K, 1.0, a.data_ptr(), K, b.data_ptr(), K, 0.0, C.data_ptr(), norb,
+                None)), reps=5, warm=2)
+            out["cells"].append(cell("phiT_H_phi", ms, 2 * fl, 3 * tile * tm * tm,
+                                     8.0 * K * norb, "k_gemm_tn_umma"))
+            ms = _time_cuda(torch, lambda: check(lib().mgb_gemm_nn(
+                0, K, norb, norb, 1.0, a.data_ptr(), K, M.data_ptr(), norb, 0.0, b.data_ptr(), K,
+                None)), reps=5, warm=2)
+            out["cells"].append(cell("phi_M", ms, 2 * fl, None, 8.0 * K * norb,
+                                     "k_gemm_nn_tf32 (mma.sync)"))
+        return out
+    except Exception as e:  # noqa: BLE001
+        return {"error": repr(e)}
 
 
 def measure_iteration_e2e(H, store_phi, store_out, fp64_peak, with_cpu):
@@ -994,6 +1077,7 @@ def run_ours(args):
                 pieces[k]["ms_max_over_ranks"] = v
         elif args.workload == "synth256" and not args.no_sweep and args.dtype == "f64":
             pieces["sweep_256"] = measure_sweep(H, args, phi.psi(), ham.hlphi_.psi(), fp64_peak)
+            pieces["f32_contractions"] = measure_f32_contractions(H, phi.psi(), ham.hlphi_.psi())
             pieces["iteration_e2e"] = measure_iteration_e2e(
                 H, phi.psi(), ham.hlphi_.psi(), fp64_peak, not args.no_cpu_iteration)
 
