@@ -632,8 +632,8 @@ def measure_f32_contractions(H, store_phi, store_out):
     split, TMEM accumulators): `executed` counts the tensor flops actually issued (3 products
     per pair, 2 on diagonal Gram tiles) against the TF32 tensor peak cuBLAS reaches in this
     run; `useful` is the contraction itself; the operand stream against the HBM peak is the
-    other bound.  Phi M is the mma.sync 3xTF32 kernel.  A failure here never affects the
-    headline line."""
+    other bound.  Phi M (k_gemm_nn_umma: the Phi tile in TMEM, coefficient tiles by TMA) moves
+    the block once in and once out.  A failure here never affects the headline line."""
     import torch
     from mgmol_b200._lib import lib, check
     hbm, _ = measured_peaks()
@@ -680,8 +680,8 @@ def measure_f32_contractions(H, store_phi, store_out):
             ms = _time_cuda(torch, lambda: check(lib().mgb_gemm_nn(
                 0, K, norb, norb, 1.0, a.data_ptr(), K, M.data_ptr(), norb, 0.0, b.data_ptr(), K,
                 None)), reps=5, warm=2)
-            out["cells"].append(cell("phi_M", ms, 2 * fl, None, 8.0 * K * norb,
-                                     "k_gemm_nn_tf32 (mma.sync)"))
+            out["cells"].append(cell("phi_M", ms, 2 * fl, 3 * tile * tm * tm, 8.0 * K * norb,
+                                     "k_gemm_nn_umma"))
         return out
     except Exception as e:  # noqa: BLE001
         return {"error": repr(e)}

@@ -343,9 +343,9 @@ int mgb_gemm_tn(int dtype, int m, int n, size_t k, double alpha, const void* A,
  * compensated 3xTF32 with chunked exact accumulation (agrees with the
  * reference's double-accumulating loops to ~1e-6 of |a||b|, bar 1e-5) on the
  * 5th-generation tensor cores (tcgen05.mma kind::tf32, TMEM accumulators) for
- * mgb_gemm_tn / mgb_syrk_t and their slab variants, on mma.sync for
- * mgb_gemm_nn; 1 = the FP64 DMMA kernels on widened operands (the reference's
- * products and sums); 2 = the 3xTF32 arithmetic on mma.sync everywhere.
+ * mgb_gemm_tn / mgb_syrk_t, their slab variants and mgb_gemm_nn; 1 = the FP64
+ * DMMA kernels on widened operands (the reference's products and sums); 2 =
+ * the 3xTF32 arithmetic on mma.sync (the previous generation's kernels).
  * Process-wide.  */
 int mgb_set_f32_contraction(int mode);
 /* Test hook (host only, no device): the stream-K decomposition of a

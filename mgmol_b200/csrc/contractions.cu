@@ -1096,8 +1096,9 @@ __global__ void k_gemm_nn_ref(long long npt, int n, int k, const T* Phi, long lo
     *o     = base + (T)s;
 }
 
-// tcgen05 (kind::tf32, TMEM) kernel of the float contractions, inside namespace mgb
+// tcgen05 (kind::tf32, TMEM) kernels of the float contractions, inside namespace mgb
 #include "tn_umma.cuh"
+#include "nn_umma.cuh"
 
 // float operands: 0 = 3xTF32 tensor tiles (tcgen05 where the kernel takes the shape, else
 // mma.sync), 1 = DMMA (double products), 2 = 3xTF32 on mma.sync only
@@ -1376,6 +1377,42 @@ static int gemm_nn_t(size_t m, int n, int k, double alpha, const T* A, size_t ld
                     k, alpha, M + (size_t)j * ldm, Mf + (size_t)j * ldf);
         }
         MGB_LAUNCHED("k_scale_to_float");
+        bool use_umma = g_f32_mode == 0 && ((uintptr_t)A & 15) == 0;
+        if (const char* env = getenv("MGB_NN_UMMA")) use_umma = use_umma && atoi(env) != 0;
+        if (use_umma)
+        {
+            // tcgen05 kernel, one CTA per SM: the low parts of Mf, three tensor maps
+            int chk = 2; // k-blocks per tensor-core accumulation chunk (MGB_NN_CHK: tuning hook)
+            if (const char* env = getenv("MGB_NN_CHK")) chk = atoi(env) > 0 ? atoi(env) : chk;
+            float* Ml = (float*)scratch(10, (size_t)ldf * n * sizeof(float) + 256);
+            if (!Ml) return MGB_ECUDA;
+            const long long cnt = (long long)ldf * n;
+            umma::k_tf32_low_parts<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(cnt, Mf, Ml);
+            MGB_LAUNCHED("k_tf32_low_parts");
+            CUtensorMap mapPhi, mapMh, mapMl;
+            if (int rc = umma::make_map_2d(&mapPhi, (const float*)A, m, (size_t)k, lda, 128, 32, false))
+                return rc;
+            if (int rc = umma::make_map_2d(&mapMh, Mf, (size_t)k, (size_t)n, (size_t)ldf, 32, 128, true))
+                return rc;
+            if (int rc = umma::make_map_2d(&mapMl, Ml, (size_t)k, (size_t)n, (size_t)ldf, 32, 128, true))
+                return rc;
+#define MGB_NN_UMMA(HD)                                                                   \
+    {                                                                                     \
+        auto kern = umma::k_gemm_nn_umma<HD>;                                             \
+        MGB_CUDA(cudaFuncSetAttribute(                                                    \
+            kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)umma::NN_SMEM));      \
+        kern<<<grid, umma::NTHR, umma::NN_SMEM, st>>>(mapPhi, mapMh, mapMl, (long long)m, \
+            n, k, beta, (float*)Out, (long long)ldc, nitems, jtiles, gamma,               \
+            (const float*)D, (long long)ldd, chk);                                        \
+    }
+            if (D)
+                MGB_NN_UMMA(true)
+            else
+                MGB_NN_UMMA(false)
+#undef MGB_NN_UMMA
+            MGB_LAUNCHED("k_gemm_nn_umma");
+            return MGB_OK;
+        }
         const size_t smem32
             = (size_t)ST32 * 128 * P32 * sizeof(float) + (size_t)ST32 * KC32 * PP32 * sizeof(float);
         if (D)

@@ -84,6 +84,15 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map,
         "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map,
+    uint64_t* bar, int c0, int c1, uint64_t policy)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+        ".L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy)
+        : "memory");
+}
 __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map,
     uint64_t* bar, int c0, int c1, int c2, int c3, int c4, uint64_t policy)
 {

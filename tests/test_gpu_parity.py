@@ -723,6 +723,46 @@ def test_f32_contractions_tcgen05(N, K, lda, positive):
     assert bool(((res[0][1] - res[2][1]).abs() <= 2 * F32_TC_TOL * torch.outer(nb, na)).all())
 
 
+@pytest.mark.parametrize("m,n,k", [(4096, 128, 128), (5000, 130, 130), (32768, 256, 256),
+                                   (8192, 70, 130), (1159, 264, 200), (640, 8, 8)])
+@pytest.mark.parametrize("positive", [False, True])
+def test_f32_multiply_tcgen05(m, n, k, positive):
+    """k_gemm_nn_umma (Phi tile in TMEM with the points on the lanes, coefficient tiles by
+    TMA) through mgb_gemm_nn: ragged point / orbital tiles, k not a multiple of 32, beta, against
+    the exact FP64 product and the mma.sync 3xTF32 kernel (same arithmetic), deterministic.
+    ExtendedGridOrbitals::multiplyByMatrix (src/ExtendedGridOrbitals.cc:448-498)."""
+    from mgmol_b200._lib import lib, check
+    g = torch.Generator(device="cuda").manual_seed(50 + n)
+    a = torch.rand((k, m), generator=g, device="cuda", dtype=torch.float32)
+    mc = torch.rand((n, k), generator=g, device="cuda", dtype=torch.float64)  # column-major k x n
+    if not positive:
+        a -= 0.5
+        mc -= 0.5
+    out0 = torch.rand((n, m), generator=g, device="cuda", dtype=torch.float32)
+    alpha, beta = 0.75, -0.5
+    ex = alpha * (mc @ a.double()) + beta * out0.double()
+    scale = alpha * (mc.abs() @ a.double().abs()) + out0.double().abs()
+    got = {}
+    for mode in (0, 2):
+        check(lib().mgb_set_f32_contraction(mode))
+        try:
+            out = out0.clone()
+            check(lib().mgb_gemm_nn(0, m, n, k, alpha, a.data_ptr(), m, mc.data_ptr(), k, beta,
+                                    out.data_ptr(), m, None))
+            torch.cuda.synchronize()
+            # 3xTF32 products + the rounding of the float result
+            assert bool(((out.double() - ex).abs() <= F32_TC_TOL * scale).all()), mode
+            got[mode] = out
+            if mode == 0:
+                out2 = out0.clone()
+                check(lib().mgb_gemm_nn(0, m, n, k, alpha, a.data_ptr(), m, mc.data_ptr(), k, beta,
+                                        out2.data_ptr(), m, None))
+                assert torch.equal(out, out2), "deterministic"
+        finally:
+            check(lib().mgb_set_f32_contraction(0))
+    assert bool(((got[0].double() - got[2].double()).abs() <= 2 * F32_TC_TOL * scale).all())
+
+
 def test_f32_contractions_tcgen05_full_size():
     """128^3 x 256 float (the ORBDTYPE float shape of H2O_64): Gram and Phi^T (H Phi) on the
     tcgen05 kernel against FP64 cuBLAS on the widened operands."""
@@ -750,6 +790,18 @@ def test_f32_contractions_tcgen05_full_size():
     assert bool(((S.t() - exg).abs() <= F32_TC_TOL * torch.outer(na, na)).all())
     assert bool(((P.t() - exp).abs() <= F32_TC_TOL * torch.outer(na, nb)).all())
     assert torch.equal(S, S.t())
+    # Phi M over the block written by nothing else: b <- a M
+    mc = torch.rand((N, N), generator=g, device="cuda", dtype=torch.float64) - 0.5
+    check(lib().mgb_gemm_nn(0, K, N, N, 1.0, a.data_ptr(), K, mc.data_ptr(), N, 0.0, b.data_ptr(), K,
+                            None))
+    torch.cuda.synchronize()
+    worst = 0.0
+    for k0 in range(0, K, step):
+        ad = a[:, k0:k0 + step].double()
+        exm = mc @ ad
+        scm = mc.abs() @ ad.abs()
+        worst = max(worst, float(((b[:, k0:k0 + step].double() - exm).abs() / scm).max()))
+    assert worst <= F32_TC_TOL
 
 
 def test_contractions_full_size_against_cublas(H):
