@@ -682,6 +682,32 @@ def measure_f32_contractions(H, store_phi, store_out):
                 None)), reps=5, warm=2)
             out["cells"].append(cell("phi_M", ms, 2 * fl, 3 * tile * tm * tm, 8.0 * K * norb,
                                      "k_gemm_nn_umma"))
+            # the whole orbital-update iteration with float orbitals (the reference's ORBDTYPE
+            # float build): H psi, Phi^T H Phi, precond_mg, Gram, Phi M back to back
+            lap = 0 if n == 256 else 2
+            dims = (n, n, n)
+            grid = H.Grid(dims, (WORKLOADS["synth256" if n == 256 else "h2o64"]["cell"],) * 3,
+                          H.ghosts_for(lap))
+            phi = H.Orbitals(grid, norb, torch.float32, a.view((norb,) + dims))
+            work = H.Orbitals(grid, norb, torch.float32, b.view((norb,) + dims))
+            op = H.LapFactory.createLap(grid, lap)
+            vt = torch.rand(dims, device="cuda", dtype=torch.float64) * 0.1 - 0.75
+            free_b, _tot = torch.cuda.mem_get_info()
+            free_b += torch.cuda.memory_reserved() - torch.cuda.memory_allocated()
+            pc = PrecondChunks(H, grid, torch.float32, norb, lap, None, free_b)
+
+            def iteration():
+                op.applyWithPot(phi.psi(), vt, work.psi())
+                phi.computeLocalProduct(work)
+                pc(work)
+                phi.computeGram()
+                phi.multiplyByMatrix(M, work)
+            ms = _time_cuda(torch, iteration, reps=3, warm=1)
+            pc.close()
+            out["cells"].append({"grid": [n, n, n], "orbitals": norb, "dtype": "f32", "lap_type": lap,
+                                 "piece": "orbital_update_iteration", "ms": ms,
+                                 "sequence": "H psi, Phi^T H Phi, precond_mg (2 levels), Gram, Phi M"})
+            del vt, phi, work
         return out
     except Exception as e:  # noqa: BLE001
         return {"error": repr(e)}

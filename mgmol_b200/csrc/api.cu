@@ -101,7 +101,8 @@ int hpsi_ghosted(const HpsiArgs& a, cudaStream_t st)
     gr.ghosts   = a.g;
     Box b       = box_of(&gr, a.g);
     const size_t es   = a.dtype == MGB_F64 ? 8 : 4;
-    const size_t blk  = (size_t)b.sizeg * a.nfunc * es;
+    // sub-buffers on 16-byte boundaries (the double potential block follows three float blocks)
+    const size_t blk  = ((size_t)b.sizeg * a.nfunc * es + 15) & ~(size_t)15;
     void* stream      = (void*)st;
     unsigned char* ws = (unsigned char*)scratch(1, 3 * blk + (size_t)b.sizeg * 8);
     if (!ws) return MGB_ECUDA;
