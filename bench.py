@@ -437,6 +437,12 @@ def measure_pieces(H, grid, phi, ham, lap_type, tdt, S, norb, npt, comm=None, hs
                                       "model_bytes_per_update": 74.0 + 2 * S}}
     hphi = hstep() if hstep else ham.applyLocal(phi, True)
     fl = float(norb) * norb * npt
+    if S == 4:
+        # float orbitals: 3xTF32 on tcgen05 -- useful flops against a third of the TF32 tensor
+        # peak (three tensor products per pair)
+        fp64_peak = tf32_tensor_peak(torch) / 3.0
+        out["f32_tensor_peak_tflops"] = {"value": fp64_peak,
+                                         "how": "cuBLAS SGEMM 8192^3 with TF32 allowed / 3 products, measured in this run"}
     ms = _time_cuda(torch, lambda: phi.computeGram(comm), reps=3, warm=1)
     out["gram"] = {"ms": ms, "roofline": _tensor_roofline(fl, ms, fp64_peak, "N^2 K (syrk)")}
     ms = _time_cuda(torch, lambda: phi.computeLocalProduct(hphi, comm), reps=3, warm=1)

@@ -1223,8 +1223,11 @@ static int gemm_tn_t(bool syrk, int m, int n, size_t k, double alpha, const T* A
         if (int rc = umma::make_map_kmajor(&mapB, (const float*)B, k, n, ldb, strideB, nbatch, ko))
             return rc;
         // fold = chunk (box) sums added in FP32 registers before they go into the double sums
-        int fold = 32, trunc = 1;
+        // chb = boxes per tensor-core accumulation chunk (1: the truncation bias of the FP32 sums
+        // stays at 1e-6; MGB_UMMA_CHB: tuning hook)
+        int fold = 32, trunc = 1, chb = 1;
         if (const char* env = getenv("MGB_UMMA_FOLD")) fold = atoi(env) > 0 ? atoi(env) : fold;
+        if (const char* env = getenv("MGB_UMMA_CHB")) chb = atoi(env) > 0 ? atoi(env) : chb;
         if (const char* env = getenv("MGB_UMMA_TRUNC")) trunc = atoi(env);
 #define MGB_UMMA_LAUNCH(SY, TR, KOV)                                                      \
     {                                                                                     \
@@ -1232,7 +1235,7 @@ static int gemm_tn_t(bool syrk, int m, int n, size_t k, double alpha, const T* A
         MGB_CUDA(cudaFuncSetAttribute(                                                    \
             kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)umma::SMEM));         \
         kern<<<W.G, umma::NTHR, umma::SMEM, st>>>(mapA, mapB, W, m, n, alpha, beta, C,   \
-            ldc, (long long)strideC, partial, fold);                                      \
+            ldc, (long long)strideC, partial, fold, chb);                                 \
     }
 #define MGB_UMMA_KO(SY, TR)                                                               \
     {                                                                                     \

@@ -318,7 +318,8 @@ __device__ __forceinline__ void write_whole_tile(const double* __restrict__ dst,
 template <bool SYRK, bool TRUNC, int KO>
 __global__ void __launch_bounds__(NTHR, 1) k_gemm_tn_umma(const __grid_constant__ CUtensorMap mapA,
     const __grid_constant__ CUtensorMap mapB, TnWork W, int m, int n, double alpha, double beta,
-    double* __restrict__ C, int ldc, long long strideC, double* __restrict__ partial, int FOLD)
+    double* __restrict__ C, int ldc, long long strideC, double* __restrict__ partial, int FOLD,
+    int CHB)
 {
     constexpr int NSS      = Ring<KO>::NSS;
     constexpr int NSLOT    = NSS * KO;        // slab slots of the raw ring
@@ -420,7 +421,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_gemm_tn_umma(const __grid_constant_
         const uint32_t tmem_u  = __shfl_sync(0xffffffffu, tmem, 0);
         const uint32_t ring_u  = __shfl_sync(0xffffffffu, smem_u32(ring), 0);
         const uint32_t lring_u = __shfl_sync(0xffffffffu, smem_u32(lring), 0);
-        uint32_t gb = 0;
+        uint32_t gb = 0, gc = 0; // boxes, chunks (CHB boxes, never across segments)
         for (int u = u_first; u <= u_last; u++)
         {
             long long it0, it1;
@@ -429,8 +430,10 @@ __global__ void __launch_bounds__(NTHR, 1) k_gemm_tn_umma(const __grid_constant_
             const bool diag = SYRK && u < W.ND;
             for (long long it = it0; it < it1; it++, gb++)
             {
-                const int ab = gb & 1, ss = gb % NSS;
-                if (gb >= 2) mbar_wait(&acce[ab], ((gb >> 1) & 1) ^ 1);
+                const int cpos   = (int)((it - it0) % CHB);        // box of the chunk
+                const bool clast = cpos == CHB - 1 || it == it1 - 1;
+                const int ab = gc & 1, ss = gb % NSS;
+                if (cpos == 0 && gc >= 2) mbar_wait(&acce[ab], ((gc >> 1) & 1) ^ 1);
                 const uint32_t tacc = tmem_u + (uint32_t)(ab * ACC_COLS);
 #pragma unroll
                 for (int ko = 0; ko < KO; ko++)
@@ -450,7 +453,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_gemm_tn_umma(const __grid_constant_
                         {
                             const uint64_t adv = (uint64_t)(ks * 2); // 32 bytes along K
                             const uint32_t ak  = ah + (uint32_t)(ks * 8);
-                            mma_tf32_ts(tacc, ak + 32, dbh + adv, (ko > 0 || ks > 0) ? 1u : 0u);
+                            mma_tf32_ts(tacc, ak + 32, dbh + adv, (cpos > 0 || ko > 0 || ks > 0) ? 1u : 0u);
                             if (!diag) mma_tf32_ts(tacc, ak, dbl + adv, 1u);
                             mma_tf32_ts(tacc, ak, dbh + adv, 1u);
                         }
@@ -458,11 +461,12 @@ __global__ void __launch_bounds__(NTHR, 1) k_gemm_tn_umma(const __grid_constant_
                         if (ko == KO - 1)
                         {
                             commit(&empty[ss]);
-                            commit(&accf[ab]);
+                            if (clast) commit(&accf[ab]);
                         }
                     }
                     __syncwarp();
                 }
+                if (clast) gc++;
             }
         }
     }
@@ -527,7 +531,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_gemm_tn_umma(const __grid_constant_
             const bool diag = SYRK && u < W.ND;
             const int nit   = (int)(it1 - it0);
             double* dst = partial + ((size_t)gcta * W.smax + (size_t)(u - u_first)) * (BM * BN);
-            drain_segment<SYRK>(dst, tmem, accf, acce, gc, nit, 1, FOLD, q, half, ml, lane);
+            drain_segment<SYRK>(dst, tmem, accf, acce, gc, nit, CHB, FOLD, q, half, ml, lane);
             if (!diag && it0 == 0 && it1 == W.nkt)
                 write_whole_tile<SYRK>(dst, C + (long long)batch * strideC, ldc, alpha, beta, tile_m,
                     tile_n, m, n, half, ml);

@@ -96,7 +96,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--big", action="store_true")
     ap.add_argument("--trunc", default="1,0")
-    ap.add_argument("--ch", default="8")
+    ap.add_argument("--ch", default="1")
     ap.add_argument("--fold", default="32")
     ap.add_argument("--ko", default="2")
     ap.add_argument("--lock", default="1")
@@ -109,8 +109,8 @@ def main():
         for tr in args.trunc.split(","):
             for ch in args.ch.split(","):
                 for fo in args.fold.split(","):
-                    modes.append((f"umma ko={ko} lock={lk} trunc={tr} fold={fo}", 0,
-                                  {"MGB_UMMA_TRUNC": tr, "MGB_UMMA_CH": ch, "MGB_UMMA_FOLD": fo,
+                    modes.append((f"umma ko={ko} chb={ch} trunc={tr} fold={fo}", 0,
+                                  {"MGB_UMMA_TRUNC": tr, "MGB_UMMA_CHB": ch, "MGB_UMMA_FOLD": fo,
                                    "MGB_UMMA_KO": ko, "MGB_UMMA_LOCK": lk}))
     if args.legacy:
         modes += [("mma.sync 3xTF32", 2, {}), ("DMMA widened", 1, {})]
