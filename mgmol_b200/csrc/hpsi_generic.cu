@@ -273,6 +273,96 @@ __global__ void k_rhs_generic(GenericView<T> view0, long long ld, long long ldo,
                                + w.psi(ix, iy, iz - 1) + w.psi(ix, iy, iz + 1)));
 }
 
+// B u on whole rows, 16 bytes of z per thread (the common case: box owned by one rank, z
+// extent a multiple of the vector, 16-byte aligned blocks).  Same expression, operand order and
+// roundings as k_rhs_generic -- bit-identical -- but the five row loads are coalesced vector
+// loads (the y neighbours hit L1, the x neighbours L2: CUDA runs the y tiles of a plane, then the
+// next plane of the same function) and there is no per-tap index logic: k_rhs_generic spends its
+// time on that and moves 1.3 TB/s at 256^3 x 512.
+template <typename T>
+struct RowVec;
+template <>
+struct RowVec<double>
+{
+    typedef double2 type;
+    static constexpr int V = 2;
+};
+template <>
+struct RowVec<float>
+{
+    typedef float4 type;
+    static constexpr int V = 4;
+};
+
+template <typename T, bool PERIODIC>
+__global__ void k_rhs_rows(const T* __restrict__ phi, long long ld, T* __restrict__ out,
+    long long ldo, int nx, int ny, int nz, int tiles_z)
+{
+    constexpr int V = RowVec<T>::V;
+    typedef typename RowVec<T>::type VT;
+    const int zc = (blockIdx.x % tiles_z) * blockDim.x + threadIdx.x;
+    const int iy = (blockIdx.x / tiles_z) * blockDim.y + threadIdx.y;
+    const int ix = blockIdx.y;
+    const int z0 = zc * V;
+    if (z0 >= nz || iy >= ny) return;
+    const T* p = phi + (long long)blockIdx.z * ld;
+    // row (jx, jy) of the boundary-traded field, or null where it is zero (Dirichlet-0: ghosts
+    // and the first low layer, src/pb/GridFunc.cc:2188-2336)
+    auto row = [&](int jx, int jy) -> const T* {
+        if (PERIODIC)
+        {
+            jx = jx < 0 ? jx + nx : (jx >= nx ? jx - nx : jx);
+            jy = jy < 0 ? jy + ny : (jy >= ny ? jy - ny : jy);
+        }
+        else if (jx <= 0 || jx >= nx || jy <= 0 || jy >= ny)
+            return nullptr;
+        return p + ((long long)jx * ny + jy) * nz;
+    };
+    T c[V], xm[V], xp[V], ym[V], yp[V];
+    auto loadv = [&](const T* r, T (&d)[V]) {
+        if (r)
+        {
+            const VT v = *reinterpret_cast<const VT*>(r + z0);
+            const T* e = reinterpret_cast<const T*>(&v);
+#pragma unroll
+            for (int i = 0; i < V; i++) d[i] = e[i];
+        }
+        else
+        {
+#pragma unroll
+            for (int i = 0; i < V; i++) d[i] = (T)0;
+        }
+    };
+    const T* rc = row(ix, iy);
+    loadv(rc, c);
+    loadv(row(ix - 1, iy), xm);
+    loadv(row(ix + 1, iy), xp);
+    loadv(row(ix, iy - 1), ym);
+    loadv(row(ix, iy + 1), yp);
+    T zlo, zhi; // the z neighbours outside this thread's vector
+    if (PERIODIC)
+    {
+        zlo = rc[z0 == 0 ? nz - 1 : z0 - 1];
+        zhi = rc[z0 + V == nz ? 0 : z0 + V];
+    }
+    else
+    {
+        zlo = (rc && z0 - 1 > 0) ? rc[z0 - 1] : (T)0;
+        zhi = (rc && z0 + V < nz) ? rc[z0 + V] : (T)0;
+        if (z0 == 0) c[0] = xm[0] = xp[0] = ym[0] = yp[0] = (T)0; // first low layer in z
+    }
+    T o[V];
+#pragma unroll
+    for (int i = 0; i < V; i++)
+    {
+        const T zm = i == 0 ? zlo : c[i - 1];
+        const T zp = i == V - 1 ? zhi : c[i + 1];
+        o[i] = (T)(0.5 * (double)c[i] + (1. / 12.) * (double)(xm[i] + xp[i] + ym[i] + yp[i] + zm + zp));
+    }
+    *reinterpret_cast<VT*>(out + (long long)blockIdx.z * ldo + ((long long)ix * ny + iy) * nz + z0)
+        = *reinterpret_cast<const VT*>(o);
+}
+
 template <typename T>
 static int rhs_generic_t(bool mehr2, const mgb_grid* gr, const T* phi, size_t ld, const T* xhalo,
     T* out, size_t ldo, int nfunc, cudaStream_t st)
@@ -290,6 +380,31 @@ static int rhs_generic_t(bool mehr2, const mgb_grid* gr, const T* phi, size_t ld
     w.split_x  = gr->nproc[0] > 1;
     w.first_x  = gr->coord[0] == 0;
     w.last_x   = gr->coord[0] == gr->nproc[0] - 1;
+    constexpr int V = RowVec<T>::V;
+    if (!mehr2 && !w.split_x && !xhalo && w.nz % V == 0
+        && (((uintptr_t)phi | (uintptr_t)out) & 15) == 0 && (ld * sizeof(T)) % 16 == 0
+        && (ldo * sizeof(T)) % 16 == 0)
+    {
+        const int nzv = w.nz / V;
+        int bx = 32;
+        while (bx < nzv && bx < 128) bx *= 2;
+        const int by      = 256 / bx;
+        const int tiles_z = (nzv + bx - 1) / bx;
+        dim3 block(bx, by);
+        for (int f0 = 0; f0 < nfunc; f0 += 65535)
+        {
+            const int nf = (nfunc - f0 < 65535) ? nfunc - f0 : 65535;
+            dim3 grid((unsigned)(tiles_z * ((w.ny + by - 1) / by)), (unsigned)w.nx, (unsigned)nf);
+            if (w.periodic)
+                k_rhs_rows<T, true><<<grid, block, 0, st>>>(phi + (long long)f0 * ld, (long long)ld,
+                    out + (long long)f0 * ldo, (long long)ldo, w.nx, w.ny, w.nz, tiles_z);
+            else
+                k_rhs_rows<T, false><<<grid, block, 0, st>>>(phi + (long long)f0 * ld, (long long)ld,
+                    out + (long long)f0 * ldo, (long long)ldo, w.nx, w.ny, w.nz, tiles_z);
+            MGB_LAUNCHED("k_rhs_rows");
+        }
+        return MGB_OK;
+    }
     RowLaunch L = row_launch(w.nx, w.ny, w.nz, 1);
     const long long halo_stride = (long long)2 * w.ny * w.nz;
     for (int f0 = 0; f0 < nfunc; f0 += 65535)
