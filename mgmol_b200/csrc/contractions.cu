@@ -1170,7 +1170,9 @@ static int gemm_tn_t(bool syrk, int m, int n, size_t k, double alpha, const T* A
     W.cf = 16;
     W.cd = 10;
     if (sizeof(T) == 4 && !g_f32_exact) W.cd = 12; // 3xTF32: 16x16 pairing, measured best
-    if (use_umma) W.cd = 11;                       // 2 of 3 MMAs, one operand box, no low tile of B
+    // tcgen05: 2 of 3 MMAs, one operand box, no low tile of B -- but a slab of this kernel is
+    // bound by its hand-offs more than by its MMAs: 14/16 measured best (N = 256, 512, 1024)
+    if (use_umma) W.cd = 14;
     if (const char* env = getenv("MGB_SYRK_DIAG_COST"))
     {
         const int c = atoi(env);
