@@ -252,22 +252,21 @@ __device__ __forceinline__ void drain_segment(double* __restrict__ dst, uint32_t
         if (lane == 0) mbar_arrive(&acce[b]);
         if (++pending == FOLD || c0 + CH >= nit)
         {
-            // the slot is L2-resident: 16 independent loads in flight, not one round trip
-            // per element
+            // the slot is L2-resident: 8 independent loads in flight, not one round trip per
+            // element (16 would cost the registers that the per-chunk path needs)
 #pragma unroll
-            for (int j0 = 0; j0 < 64; j0 += 16)
+            for (int j0 = 0; j0 < 64; j0 += 8)
             {
-                double old[16];
+                double old[8];
 #pragma unroll
-                for (int j = 0; j < 16; j++)
+                for (int j = 0; j < 8; j++)
                     old[j] = first ? 0. : __ldcg(dst + (size_t)(half * 64 + j0 + j) * BM + ml);
 #pragma unroll
-                for (int j = 0; j < 16; j++)
-                {
+                for (int j = 0; j < 8; j++)
                     __stcg(dst + (size_t)(half * 64 + j0 + j) * BM + ml, old[j] + (double)hi[j0 + j]);
-                    hi[j0 + j] = 0.f;
-                }
             }
+#pragma unroll
+            for (int j = 0; j < 64; j++) hi[j] = 0.f;
             first   = false;
             pending = 0;
         }
