@@ -15,7 +15,9 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "mgmol_b200", "libmgmol_b200.so")
 COLS = [("UTMALDG", r"\bUTMALDG"), ("UTMASTG", r"\bUTMASTG"), ("UBLKCP", r"\bUBLKCP"),
-        ("SYNCS", r"\bSYNCS"), ("DMMA", r"\bDMMA"), ("HMMA.TF32", r"\bHMMA[.\w]*TF32"),
+        ("SYNCS", r"\bSYNCS"), ("UTCHMMA", r"\bUTCHMMA"), ("UTCBAR", r"\bUTCBAR"),
+        ("LDTM", r"\bLDTM"), ("STTM", r"\bSTTM"), ("DMMA", r"\bDMMA"),
+        ("HMMA.TF32", r"\bHMMA[.\w]*TF32"),
         ("LDGSTS", r"\bLDGSTS"), ("DFMA", r"\bDFMA"), ("FFMA", r"\bFFMA"),
         ("instr", r"/\*[0-9a-f]{4}\*/")]
 
@@ -46,7 +48,9 @@ def main():
     print("Produced by `python tools/sass_evidence.py` from `cuobjdump -sass` (no GPU needed). One row per "
           "kernel family; `n` = template instantiations; every other cell = min–max count of that "
           "instruction over the instantiations. UTMALDG/UTMASTG = TMA tensor loads/stores "
-          "(`cp.async.bulk.tensor`), SYNCS = mbarrier operations, DMMA = FP64 tensor MMA, "
+          "(`cp.async.bulk.tensor`), SYNCS = mbarrier operations, UTCHMMA = `tcgen05.mma` (5th-generation "
+          "tensor cores; `kind::tf32` here), UTCBAR = `tcgen05.commit`, LDTM / STTM = `tcgen05.ld` / "
+          "`tcgen05.st` (TMEM), DMMA = FP64 tensor MMA, "
           "HMMA…TF32 = TF32 tensor MMA (`mma.sync.m16n8k8.tf32`, the 3×TF32 float contractions), "
           "LDGSTS = `cp.async`; regs / stack (local memory, i.e. spills when non-zero) / static shared "
           "memory from `cuobjdump --dump-resource-usage` (the TMA rings are dynamic shared memory and do "
@@ -67,8 +71,10 @@ def main():
           "mbarrier pipelines; the `true` PEER instantiations of `k_hpsi_tma` carry the extra tensor maps "
           "of the neighbours' blocks (93 vs 48 UTMALDG). The contractions are tensor-pipe kernels fed by "
           "`cp.async` rings: DMMA for `ORBDTYPE double` (FP64 has no tcgen05 form; DMMA is the FP64 tensor "
-          "instruction of sm_100a) and TF32 `mma.sync` for the error-compensated float path -- a "
-          "`tcgen05.mma kind::tf32` version of the float contractions is the open item there. The "
+          "instruction of sm_100a). For `ORBDTYPE float` the error-compensated 3xTF32 contractions run "
+          "on tcgen05 (`k_gemm_tn_umma`, `k_gemm_nn_umma`: UTCHMMA with the A operand in TMEM, UTCBAR "
+          "commits, LDTM drains, STTM operand stores, TMA-fed); the `mma.sync` TF32 kernels "
+          "(`k_gemm_*_tf32`) remain as `mgb_set_f32_contraction(2)`. The "
           "\"literal\" kernels (`k_del2_*`, `k_rhs_*`, `k_axpy`, `k_hpsi_generic` ...) are compiled with "
           "`-fmad=false` on purpose: they reproduce the reference's separately rounded multiply and add, "
           "hence no FMA in them.")
