@@ -1401,9 +1401,37 @@ static int gemm_nn_t(size_t m, int n, int k, double alpha, const T* A, size_t ld
                 return rc;
             if (int rc = umma::make_map_2d(&mapMl, Ml, (size_t)k, (size_t)n, (size_t)ldf, 32, 128, true))
                 return rc;
+            // clusters of two CTAs that share the coefficient tiles by TMA multicast: one point-
+            // tile pair per cluster at a time (MGB_NN_MC=0: independent CTAs)
+            int mc = ptiles >= 2 ? 1 : 0;
+            if (const char* env = getenv("MGB_NN_MC")) mc = mc && atoi(env) != 0;
+            unsigned grid_mc = (unsigned)(num_sms() & ~1);
+            if ((long long)grid_mc > 2 * ((ptiles + 1) / 2)) grid_mc = (unsigned)(2 * ((ptiles + 1) / 2));
 #define MGB_NN_UMMA(HD)                                                                   \
+    if (mc)                                                                               \
     {                                                                                     \
-        auto kern = umma::k_gemm_nn_umma<HD>;                                             \
+        auto kern = umma::k_gemm_nn_umma<HD, true>;                                       \
+        MGB_CUDA(cudaFuncSetAttribute(                                                    \
+            kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)umma::NN_SMEM));      \
+        cudaLaunchConfig_t cfg = {};                                                      \
+        cfg.gridDim          = dim3(grid_mc);                                             \
+        cfg.blockDim         = dim3(umma::NTHR);                                          \
+        cfg.dynamicSmemBytes = umma::NN_SMEM;                                             \
+        cfg.stream           = st;                                                        \
+        cudaLaunchAttribute at[1];                                                        \
+        at[0].id               = cudaLaunchAttributeClusterDimension;                     \
+        at[0].val.clusterDim.x = 2;                                                       \
+        at[0].val.clusterDim.y = 1;                                                       \
+        at[0].val.clusterDim.z = 1;                                                       \
+        cfg.attrs    = at;                                                                \
+        cfg.numAttrs = 1;                                                                 \
+        MGB_CUDA(cudaLaunchKernelEx(&cfg, kern, mapPhi, mapMh, mapMl, (long long)m, n, k, \
+            beta, (float*)Out, (long long)ldc, nitems, jtiles, gamma, (const float*)D,    \
+            (long long)ldd, chk));                                                        \
+    }                                                                                     \
+    else                                                                                  \
+    {                                                                                     \
+        auto kern = umma::k_gemm_nn_umma<HD, false>;                                      \
         MGB_CUDA(cudaFuncSetAttribute(                                                    \
             kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)umma::NN_SMEM));      \
         kern<<<grid, umma::NTHR, umma::NN_SMEM, st>>>(mapPhi, mapMh, mapMl, (long long)m, \

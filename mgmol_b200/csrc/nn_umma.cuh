@@ -24,6 +24,13 @@
 // epilogue (beta Out, gamma D, coalesced stores: a warp stores 32 consecutive points of one
 // orbital) overlaps the next item's MMAs.
 //
+// MC (cluster of two CTAs).  The coefficient tiles are two thirds of what a CTA pulls through
+// the L2 -> SM fabric (12.9 GB of TMA traffic for a 4.3 GB block at 128^3 x 256, ncu), and every
+// CTA that works on the same column tile wants the same ones.  Two CTAs of a cluster take two
+// neighbouring point tiles, walk the column tiles and k-blocks in the same order, and split the
+// coefficient loads: rank 0 loads the Mf tile, rank 1 the Ml tile, each with .multicast::cluster
+// into both CTAs' stage; a stage is released by both MMA warps (multicast commit, count 2).
+//
 // Roles (14 warps): 0 TMA producer, 1 MMA issuer (warp-converged, one elected lane), 2-5 split,
 // 6-13 drain / epilogue (warp w: TMEM lane quarter w % 4, 64 of the 128 columns).
 #pragma once
@@ -34,7 +41,80 @@ constexpr int NN_ST    = 4;                 // ring depth: smem stage s <-> TMEM
 constexpr int NN_STAGE = 3 * TILE_B;        // Phi box, Mf tile, Ml tile
 constexpr size_t NN_SMEM = (size_t)NN_ST * NN_STAGE + 1024;
 
-template <bool HASD>
+__device__ __forceinline__ void commit_mc(uint64_t* bar, uint16_t mask)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
+                 "[%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* map, uint64_t* bar, int c0,
+    int c1, uint16_t mask, uint64_t policy)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+                 ".multicast::cluster.L2::cache_hint [%0], [%1, {%4, %5}], [%2], %3, %6;" ::"r"(smem_u32(dst)),
+                 "l"(map), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1), "l"(policy)
+                 : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// The items of a CTA.  !MC: items blockIdx.x, + gridDim.x, ... of the (point tile, column tile)
+// list, column tile fastest.  MC: cluster c = blockIdx.x / 2 takes the point-tile pairs c, c + NC,
+// ...; rank r = blockIdx.x % 2 the r-th tile of the pair (clamped to the last tile when the count
+// is odd: that CTA computes a duplicate and stores nothing), all column tiles in turn.
+template <bool MC>
+struct NnItems
+{
+    long long ptiles, nitems;
+    int jtiles;
+    long long cur, step; // !MC: item; MC: pair index
+    int jt;
+    int rank;
+    __device__ __forceinline__ NnItems(long long nitems_, int jtiles_) : nitems(nitems_), jtiles(jtiles_)
+    {
+        ptiles = nitems / jtiles;
+        if (MC)
+        {
+            cur  = blockIdx.x >> 1;
+            step = gridDim.x >> 1;
+            rank = blockIdx.x & 1;
+        }
+        else
+        {
+            cur  = blockIdx.x;
+            step = gridDim.x;
+            rank = 0;
+        }
+        jt = 0;
+    }
+    __device__ __forceinline__ bool valid() const { return MC ? 2 * cur < ptiles : cur < nitems; }
+    __device__ __forceinline__ long long ptile() const
+    {
+        if (!MC) return cur / jtiles;
+        const long long p = 2 * cur + rank;
+        return p < ptiles ? p : ptiles - 1;
+    }
+    __device__ __forceinline__ bool stores() const { return !MC || 2 * cur + rank < ptiles; }
+    __device__ __forceinline__ int jtile() const { return MC ? jt : (int)(cur % jtiles); }
+    __device__ __forceinline__ void next()
+    {
+        if (MC)
+        {
+            if (++jt == jtiles)
+            {
+                jt = 0;
+                cur += step;
+            }
+        }
+        else
+            cur += step;
+    }
+};
+
+template <bool HASD, bool MC>
 __global__ void __launch_bounds__(NTHR, 1) k_gemm_nn_umma(const __grid_constant__ CUtensorMap mapPhi,
     const __grid_constant__ CUtensorMap mapMh, const __grid_constant__ CUtensorMap mapMl,
     long long npt, int n, int k, double beta, float* __restrict__ Out, long long ldc,
@@ -48,10 +128,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_gemm_nn_umma(const __grid_constant_
     uint8_t* ring = smraw + ((1024u - (smem_u32(smraw) & 1023u)) & 1023u);
     const int nkb = (k + 31) / 32;                 // k-blocks per item
     const int nch = (nkb + NN_CHK - 1) / NN_CHK;   // chunks per item
-    // items blockIdx.x, blockIdx.x + gridDim.x, ...: neighbouring CTAs work on the column tiles
-    // of the same point tile at the same time (its Phi boxes are then shared through L2)
-    const long long item0 = blockIdx.x, istep = gridDim.x;
-    if (item0 >= nitems) return;
+    if (!NnItems<MC>(nitems, jtiles).valid()) return; // never in a cluster launch (grid <= pairs)
 
     if (tid == 0)
     {
@@ -59,7 +136,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_gemm_nn_umma(const __grid_constant_
         {
             mbar_init(&full[s], 1);
             mbar_init(&conv[s], 4);
-            mbar_init(&empty[s], 1);
+            mbar_init(&empty[s], MC ? 2 : 1);
         }
         for (int b = 0; b < 2; b++)
         {
@@ -78,6 +155,8 @@ __global__ void __launch_bounds__(NTHR, 1) k_gemm_nn_umma(const __grid_constant_
     }
     fence_before();
     __syncthreads();
+    // the partner's barriers must exist before anything is multicast into its stages
+    if (MC) cluster_sync_all();
     fence_after();
     const uint32_t tmem   = tmem_base_s;
     const uint32_t tmem_a = tmem + 2 * ACC_COLS; // NN_ST stages of 64 columns
@@ -89,10 +168,10 @@ __global__ void __launch_bounds__(NTHR, 1) k_gemm_nn_umma(const __grid_constant_
         {
             const uint64_t pol_phi = policy_evict_normal(), pol_m = policy_evict_last();
             uint32_t gs = 0;
-            for (long long item = item0; item < nitems; item += istep)
+            for (NnItems<MC> I(nitems, jtiles); I.valid(); I.next())
             {
-                const int j0       = (int)(item % jtiles) * 128;
-                const long long p0 = (item / jtiles) * 128;
+                const int j0       = I.jtile() * 128;
+                const long long p0 = I.ptile() * 128;
                 for (int kb = 0; kb < nkb; kb++, gs++)
                 {
                     const int s = gs % NN_ST;
@@ -100,8 +179,15 @@ __global__ void __launch_bounds__(NTHR, 1) k_gemm_nn_umma(const __grid_constant_
                     uint8_t* st = ring + (size_t)s * NN_STAGE;
                     mbar_arrive_expect_tx(&full[s], NN_STAGE);
                     tma_load_2d(st, &mapPhi, &full[s], (int)p0, kb * 32, pol_phi);
-                    tma_load_2d(st + TILE_B, &mapMh, &full[s], kb * 32, j0, pol_m);
-                    tma_load_2d(st + 2 * TILE_B, &mapMl, &full[s], kb * 32, j0, pol_m);
+                    if (!MC)
+                    {
+                        tma_load_2d(st + TILE_B, &mapMh, &full[s], kb * 32, j0, pol_m);
+                        tma_load_2d(st + 2 * TILE_B, &mapMl, &full[s], kb * 32, j0, pol_m);
+                    }
+                    else if (I.rank == 0)
+                        tma_load_2d_mc(st + TILE_B, &mapMh, &full[s], kb * 32, j0, (uint16_t)3, pol_m);
+                    else
+                        tma_load_2d_mc(st + 2 * TILE_B, &mapMl, &full[s], kb * 32, j0, (uint16_t)3, pol_m);
                 }
             }
         }
@@ -112,7 +198,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_gemm_nn_umma(const __grid_constant_
         const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
         const uint32_t ring_u = __shfl_sync(0xffffffffu, smem_u32(ring), 0);
         uint32_t gs = 0, gc = 0;
-        for (long long item = item0; item < nitems; item += istep)
+        for (NnItems<MC> I(nitems, jtiles); I.valid(); I.next())
         {
             for (int c = 0; c < nch; c++, gc++)
             {
@@ -140,7 +226,10 @@ __global__ void __launch_bounds__(NTHR, 1) k_gemm_nn_umma(const __grid_constant_
                             mma_tf32_ts(tacc, ak, dbl + adv, 1u);
                             mma_tf32_ts(tacc, ak, dbh + adv, 1u);
                         }
-                        commit(&empty[s]);
+                        if (MC)
+                            commit_mc(&empty[s], (uint16_t)3);
+                        else
+                            commit(&empty[s]);
                         if (kb == kb1 - 1) commit(&accf[ab]);
                     }
                     __syncwarp();
@@ -153,7 +242,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_gemm_nn_umma(const __grid_constant_
         // ---------------- split warps: Phi box -> a_hi, a_lo in TMEM ----------------
         const int p = (warp & 3) * 32 + lane; // point of the tile = TMEM lane
         uint32_t gs = 0;
-        for (long long item = item0; item < nitems; item += istep)
+        for (NnItems<MC> I(nitems, jtiles); I.valid(); I.next())
         {
             for (int kb = 0; kb < nkb; kb++, gs++)
             {
@@ -186,10 +275,10 @@ __global__ void __launch_bounds__(NTHR, 1) k_gemm_nn_umma(const __grid_constant_
         const int half = (warp - 6) >> 2;
         const int pl   = q * 32 + lane;
         uint32_t gc    = 0;
-        for (long long item = item0; item < nitems; item += istep)
+        for (NnItems<MC> I(nitems, jtiles); I.valid(); I.next())
         {
-            const int j0       = (int)(item % jtiles) * 128 + half * 64;
-            const long long pp = (item / jtiles) * 128 + pl;
+            const int j0       = I.jtile() * 128 + half * 64;
+            const long long pp = I.ptile() * 128 + pl;
             float hi[64];
 #pragma unroll
             for (int j = 0; j < 64; j++) hi[j] = 0.f;
@@ -214,7 +303,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_gemm_nn_umma(const __grid_constant_
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&acce[ab]);
             }
-            if (pp < npt)
+            if (pp < npt && I.stores())
             {
 #pragma unroll
                 for (int j = 0; j < 64; j++)
@@ -235,6 +324,8 @@ __global__ void __launch_bounds__(NTHR, 1) k_gemm_nn_umma(const __grid_constant_
 
     fence_before();
     __syncthreads();
+    // nobody leaves while the partner may still multicast into this CTA or arrive on its barriers
+    if (MC) cluster_sync_all();
     if (warp == 1)
     {
         __syncwarp();
