@@ -41,13 +41,6 @@ constexpr int NN_ST    = 4;                 // ring depth: smem stage s <-> TMEM
 constexpr int NN_STAGE = 3 * TILE_B;        // Phi box, Mf tile, Ml tile
 constexpr size_t NN_SMEM = (size_t)NN_ST * NN_STAGE + 1024;
 
-__device__ __forceinline__ void commit_mc(uint64_t* bar, uint16_t mask)
-{
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
-                 "[%0], %1;" ::"r"(smem_u32(bar)),
-                 "h"(mask)
-                 : "memory");
-}
 __device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* map, uint64_t* bar, int c0,
     int c1, uint16_t mask, uint64_t policy)
 {
@@ -56,11 +49,6 @@ __device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* map
                  "l"(map), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1), "l"(policy)
                  : "memory");
 }
-__device__ __forceinline__ void cluster_sync_all()
-{
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-
 // The items of a CTA.  !MC: items blockIdx.x, + gridDim.x, ... of the (point tile, column tile)
 // list, column tile fastest.  MC: cluster c = blockIdx.x / 2 takes the point-tile pairs c, c + NC,
 // ...; rank r = blockIdx.x % 2 the r-th tile of the pair (clamped to the last tile when the count

@@ -91,6 +91,31 @@ __device__ __forceinline__ bool elect_one()
     return pred != 0;
 }
 
+// clusters: a commit that arrives on the same barrier of every CTA in `mask`, a multicast TMA
+// load, and the cluster-wide barrier
+__device__ __forceinline__ void commit_mc(uint64_t* bar, uint16_t mask)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
+                 "[%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_mc(void* dst, const CUtensorMap* map, uint64_t* bar, int c0,
+    int c1, int c2, int c3, int c4, uint16_t mask, uint64_t policy)
+{
+    asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes"
+                 ".multicast::cluster.L2::cache_hint [%0], [%1, {%4, %5, %6, %7, %8}], [%2], %3, %9;" ::"r"(
+                     smem_u32(dst)),
+                 "l"(map), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4),
+                 "l"(policy)
+                 : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+
 // D[tmem_c] (+)= A[tmem_a] * B[db]^T, A from TMEM (lane = row, one k per 32-bit column)
 __device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_c, uint32_t tmem_a, uint64_t db, uint32_t acc)
 {
@@ -314,7 +339,14 @@ __device__ __forceinline__ void write_whole_tile(const double* __restrict__ dst,
 // own -- waits behind the SM's outstanding TMA traffic and made the kernel 2-4x slower
 // (gpurun_out/r02_umma_lock*.log); the remedy left is a cluster with remote mbarrier arrivals
 // (or TMA multicast), not built.
-template <bool SYRK, bool TRUNC, int KO>
+// MC (KO == 2, no SYRK, tile grid with even tm and tn, G = NT * ng): clusters of four CTAs = the
+// 2 x 2 tiles {m0, m1} x {n0, n1} over the same K range.  Every operand box is wanted by two of
+// them: rank r loads one half (8 of the 16 row groups) of its A box and of its B box and
+// multicasts each to the CTA that shares it (A: r ^ 2, B: r ^ 1), so a box crosses the L2 -> SM
+// fabric -- and comes from DRAM -- once per cluster instead of once per tile.  mapA / mapB then
+// carry {32, 8, KO, 8, 1} boxes; a stage is released by the three CTAs that write into it
+// (multicast commit, barrier count 3).
+template <bool SYRK, bool TRUNC, int KO, bool MC = false>
 __global__ void __launch_bounds__(NTHR, 1) k_gemm_tn_umma(const __grid_constant__ CUtensorMap mapA,
     const __grid_constant__ CUtensorMap mapB, TnWork W, int m, int n, double alpha, double beta,
     double* __restrict__ C, int ldc, long long strideC, double* __restrict__ partial, int FOLD,
@@ -328,10 +360,19 @@ __global__ void __launch_bounds__(NTHR, 1) k_gemm_tn_umma(const __grid_constant_
     __shared__ __align__(8) uint64_t full[NSS], empty[NSS], conv[NSLOT], cempty[CST], accf[2], acce[2];
     __shared__ uint32_t tmem_base_s;
 
-    const int gcta = blockIdx.x;
+    // the CTA's index in the plan; in a cluster launch rank r of cluster (quad q, K range j)
+    // is tile (2 qm + (r & 1), 2 qn + (r >> 1)), i.e. plan index tile * ng + j
+    int gcta       = blockIdx.x;
+    const int rank = MC ? (int)(blockIdx.x & 3) : 0;
+    if (MC)
+    {
+        const int ng = W.G / W.NT, cid = blockIdx.x >> 2;
+        const int q = cid / ng, j = cid % ng, hm = W.tm / 2;
+        gcta = ((2 * (q % hm) + (rank & 1)) + W.tm * (2 * (q / hm) + (rank >> 1))) * ng + j;
+    }
     long long b0, b1;
     tn_cta_bounds(W, gcta, b0, b1);
-    if (b1 <= b0) return;
+    if (b1 <= b0) return; // never in a cluster launch
     const int u_first = tn_tile_of(W, b0), u_last = tn_tile_of(W, b1 - 1);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // tiles must sit on 1024-byte boundaries (swizzle atom; descriptor base offset 0)
@@ -343,7 +384,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_gemm_tn_umma(const __grid_constant_
         for (int s = 0; s < NSS; s++)
         {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], 1);
+            mbar_init(&empty[s], MC ? 3 : 1);
         }
         for (int s = 0; s < NSLOT; s++) mbar_init(&conv[s], 4);
         for (int s = 0; s < CST; s++) mbar_init(&cempty[s], 1);
@@ -364,9 +405,14 @@ __global__ void __launch_bounds__(NTHR, 1) k_gemm_tn_umma(const __grid_constant_
     }
     fence_before();
     __syncthreads();
+    // the partners' barriers must exist before anything is multicast into their stages
+    if (MC) cluster_sync_all();
     fence_after();
     const uint32_t tmem   = tmem_base_s;
     const uint32_t tmem_a = tmem + 2 * ACC_COLS; // CST stages of 64 columns
+    // CTAs that write into my stages and into whose stages I write: myself, the one sharing my
+    // A box (rank ^ 2) and the one sharing my B box (rank ^ 1)
+    const uint16_t mc_mask = (uint16_t)((1u << rank) | (1u << (rank ^ 1)) | (1u << (rank ^ 2)));
 
     // Every role walks the same list of segments (tile, boxes [it0, it1)); gb counts the boxes
     // of this CTA, gs = gb * KO + ko its slabs.
@@ -398,13 +444,24 @@ __global__ void __launch_bounds__(NTHR, 1) k_gemm_tn_umma(const __grid_constant_
                             tma_load_3d(st + OPER_B, &mapB, &full[ss], (int)(it * 32), tile_n * BN, batch,
                                 pol);
                     }
-                    else
+                    else if (!MC)
                     {
                         tma_load_5d(st, &mapA, &full[ss], 0, 0, (int)(it * KO), tile_m * (BM / 8), batch,
                             pol);
                         if (!diag)
                             tma_load_5d(st + OPER_B, &mapB, &full[ss], 0, 0, (int)(it * KO),
                                 tile_n * (BN / 8), batch, pol);
+                    }
+                    else
+                    {
+                        // my half of the A box to me and to rank ^ 2, of the B box to me and rank ^ 1
+                        const int ha = rank >> 1, hb = rank & 1;
+                        tma_load_5d_mc(st + ha * (OPER_B / 2), &mapA, &full[ss], 0, 0, (int)(it * KO),
+                            tile_m * (BM / 8) + 8 * ha, batch, (uint16_t)((1u << rank) | (1u << (rank ^ 2))),
+                            pol);
+                        tma_load_5d_mc(st + OPER_B + hb * (OPER_B / 2), &mapB, &full[ss], 0, 0,
+                            (int)(it * KO), tile_n * (BN / 8) + 8 * hb, batch,
+                            (uint16_t)((1u << rank) | (1u << (rank ^ 1))), pol);
                     }
                 }
             }
@@ -459,7 +516,10 @@ __global__ void __launch_bounds__(NTHR, 1) k_gemm_tn_umma(const __grid_constant_
                         commit(&cempty[cs]);
                         if (ko == KO - 1)
                         {
-                            commit(&empty[ss]);
+                            if (MC)
+                                commit_mc(&empty[ss], mc_mask);
+                            else
+                                commit(&empty[ss]);
                             if (clast) commit(&accf[ab]);
                         }
                     }
@@ -539,6 +599,8 @@ __global__ void __launch_bounds__(NTHR, 1) k_gemm_tn_umma(const __grid_constant_
 
     fence_before();
     __syncthreads();
+    // nobody leaves while a partner may still multicast into this CTA or arrive on its barriers
+    if (MC) cluster_sync_all();
     if (warp == 1)
     {
         __syncwarp();
@@ -553,7 +615,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_gemm_tn_umma(const __grid_constant_
 // box {32, 8, ko, 16, 1}: needs rows % 8 == 0 and K % 32 == 0 (whole groups / slabs only; slabs
 // and groups beyond the extents are zero-filled).  Both under the 128-byte swizzle.
 static int make_map_kmajor(CUtensorMap* mp, const float* base, size_t K, int rows, size_t ld,
-    size_t stride, int nbatch, int ko)
+    size_t stride, int nbatch, int ko, int groups = 16)
 {
     PFN_encodeTiled enc = get_encode();
     if (!enc)
@@ -577,7 +639,7 @@ static int make_map_kmajor(CUtensorMap* mp, const float* base, size_t K, int row
     {
         cuuint64_t dims[5]    = { 32, 8, (cuuint64_t)(K / 32), (cuuint64_t)(rows / 8), (cuuint64_t)nbatch };
         cuuint64_t strides[4] = { (cuuint64_t)ld * 4, 128, (cuuint64_t)ld * 4 * 8, bstride };
-        cuuint32_t box[5]     = { 32, 8, (cuuint32_t)ko, 16, 1 };
+        cuuint32_t box[5]     = { 32, 8, (cuuint32_t)ko, (cuuint32_t)groups, 1 };
         cuuint32_t estr[5]    = { 1, 1, 1, 1, 1 };
         r = enc(mp, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(base), dims, strides, box,
             estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,

@@ -99,19 +99,19 @@ def main():
     ap.add_argument("--ch", default="1")
     ap.add_argument("--fold", default="32")
     ap.add_argument("--ko", default="2")
-    ap.add_argument("--lock", default="1")
+    ap.add_argument("--mc", default="1")
     ap.add_argument("--legacy", action="store_true")
     ap.add_argument("--nosmall", action="store_true")
     ap.add_argument("--shapes", default="256x2097152,512x2097152,1024x884736")
     args = ap.parse_args()
     modes = []
-    for ko, lk in [(k_, l_) for k_ in args.ko.split(",") for l_ in args.lock.split(",")]:
+    for ko, lk in [(k_, l_) for k_ in args.ko.split(",") for l_ in args.mc.split(",")]:
         for tr in args.trunc.split(","):
             for ch in args.ch.split(","):
                 for fo in args.fold.split(","):
-                    modes.append((f"umma ko={ko} chb={ch} trunc={tr} fold={fo}", 0,
+                    modes.append((f"umma ko={ko} mc={lk} chb={ch} trunc={tr} fold={fo}", 0,
                                   {"MGB_UMMA_TRUNC": tr, "MGB_UMMA_CHB": ch, "MGB_UMMA_FOLD": fo,
-                                   "MGB_UMMA_KO": ko, "MGB_UMMA_LOCK": lk}))
+                                   "MGB_UMMA_KO": ko, "MGB_TN_MC": lk}))
     if args.legacy:
         modes += [("mma.sync 3xTF32", 2, {}), ("DMMA widened", 1, {})]
     small = [(128, 4096), (130, 6144), (256, 32768), (304, 65536), (37, 1680), (136, 4000)]
