@@ -293,18 +293,31 @@ __global__ void __launch_bounds__(NTHR, 1) k_gemm_nn_umma(const __grid_constant_
             }
             if (pp < npt && I.stores())
             {
-#pragma unroll
-                for (int j = 0; j < 64; j++)
+                // the epilogue sits between two drains of the same warps: keep it short (the
+                // first version spent 22 instructions per column on addressing and tests)
+                float* o       = Out + (long long)j0 * ldc + pp;
+                const float* d = HASD ? D + (long long)j0 * ldd + pp : nullptr;
+                if (n - j0 >= 64 && beta == 0.)
                 {
-                    const int jj = j0 + j;
-                    if (jj < n)
+#pragma unroll
+                    for (int j = 0; j < 64; j++)
                     {
-                        float* o = Out + (long long)jj * ldc + pp;
-                        float r  = hi[j];
-                        if (beta != 0.) r += (float)(beta * (double)*o);
-                        if (HASD) r += (float)(gamma * (double)D[(long long)jj * ldd + pp]);
-                        *o = r;
+                        float r = hi[j];
+                        if (HASD) r += (float)(gamma * (double)d[(long long)j * ldd]);
+                        o[(long long)j * ldc] = r;
                     }
+                }
+                else
+                {
+#pragma unroll
+                    for (int j = 0; j < 64; j++)
+                        if (j0 + j < n)
+                        {
+                            float r = hi[j];
+                            if (beta != 0.) r += (float)(beta * (double)o[(long long)j * ldc]);
+                            if (HASD) r += (float)(gamma * (double)d[(long long)j * ldd]);
+                            o[(long long)j * ldc] = r;
+                        }
                 }
             }
         }
