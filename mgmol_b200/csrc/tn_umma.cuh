@@ -6,10 +6,10 @@
 // Arithmetic (src/linear_algebra/mputils.cc:848-948 sums (double)a*(double)b): error-compensated
 // 3xTF32.  Every operand is split a = a_hi + a_lo into two TF32 numbers and a*b is formed as
 // a_lo b_hi + a_hi b_lo + a_hi b_hi (the dropped a_lo b_lo is 2^-22 of |a||b|).  The tensor
-// core sums in FP32 -- truncating, measured: a sum of CH slabs of positive terms comes out low by
-// ~3e-7 CH -- over one chunk of CH 32-point slabs only; chunk sums are added in FP32 registers
-// (round to nearest) over at most FOLD chunks and those in double (the segment's partial slot,
-// L2-resident), so the K = 10^6..10^7 reduction behaves like a double sum.
+// core sums in FP32 -- truncating, measured: a sum of S slabs of positive terms comes out low by
+// ~5e-7 S -- over one chunk only (one TMA box = 2 slabs by default); chunk sums are added in FP32
+// registers (round to nearest) over at most FOLD chunks and those in double (the segment's
+// partial slot, L2-resident), so the K = 10^6..10^7 reduction behaves like a double sum.
 //
 // One CTA per SM, 14 warps, each with one role:
 //   warp 0      TMA producer: raw 128 x 32 float tiles of A and B (K-major, 128-byte swizzle =
@@ -20,8 +20,9 @@
 //               offsets (the swizzle never has to be undone); B's high part is the raw tile
 //               itself (TRUNC: the tensor core ignores the 13 low mantissa bits, so b_hi =
 //               trunc(b) costs nothing and b_lo = b - trunc(b) is exact) or is rounded in place
-//   warp 1      one lane issues the 12 tcgen05.mma of a slab (4 k8 steps x 3 products; A from
-//               TMEM, B from shared memory) and commits the stage back; owns the TMEM allocation
+//   warp 1      walks the loops converged; one elected lane issues the 12 tcgen05.mma of a slab
+//               (4 k8 steps x 3 products; A from TMEM, B from shared memory) and the commits that
+//               hand the stages back; owns the TMEM allocation
 //   warps 6-13  drain: tcgen05.ld of a finished chunk accumulator (two 128-column accumulators
 //               alternate, so the drain overlaps the next chunk's MMAs), the two upper summation
 //               levels, the partial slot / direct write of C
@@ -39,7 +40,11 @@
 //     [row group][ko][8 rows][128 B] -- each slab's tile is a regular SWIZZLE_128B tile with
 //     its 8-row atoms KO KB apart (the descriptor's stride byte offset).
 //   * L2 -> SM: 32 KB per slab and SM is ~0.45 us at the fabric's per-SM share; the MMA floor of
-//     a slab (12 x 64 cycles) is 0.40 us.
+//     a slab (12 x 64 cycles) is 0.40 us at 1.9 GHz.
+//   * TMEM: tcgen05.ld moves ~64 B/clk per SM, so draining a 64 KB accumulator takes ~1000
+//     cycles, and drains and MMAs take turns: a box is 1536 cycles of MMAs + ~1000 of drain, which
+//     is what the kernel runs at (tensor pipe 61-63 % active, ncu).  Longer chunks would halve
+//     that share and double the truncation bias.
 #pragma once
 
 namespace umma
