@@ -144,3 +144,34 @@ def test_streamk_plan_covers_every_iteration_once():
             cost[g] += (b - a) * (cd if u < nd else 16)
         tot = cost.sum()
         assert np.abs(cost - tot / ncta).max() <= 16 + 1e-9
+
+
+def test_tn_plan_with_tile_aligned_cta_groups():
+    """The tcgen05 kernels' plan: with G = NT * ng CTAs and tiles of equal cost, CTA g works on
+    tile g / ng only, and the CTAs of one K range (same g % ng) hold exactly the same range of
+    k-iterations -- what the L2 reuse of the operand boxes and the 2 x 2-tile multicast clusters
+    (k_gemm_tn_umma<MC>) rely on."""
+    import ctypes
+    import numpy as np
+    from mgmol_b200._lib import lib, check
+    L = lib()
+    for m, n, k, kc, ng in ((256, 256, 2097152, 64, 37), (512, 512, 2097152, 64, 9),
+                            (384, 256, 100000, 64, 7), (1024, 1024, 884736, 64, 2),
+                            (256, 512, 12345 * 64 + 17, 64, 18)):
+        nt = -(-m // 128) * -(-n // 128)
+        ncta = nt * ng
+        segs = np.zeros((4 * ncta, 4), np.int64)
+        ns, nkt, ntile, nd = ctypes.c_int(), ctypes.c_longlong(), ctypes.c_int(), ctypes.c_int()
+        check(L.mgb_debug_tn_plan(0, m, n, k, 1, kc, ncta, 16,
+                                  segs.ctypes.data_as(ctypes.c_void_p), len(segs), ctypes.byref(ns),
+                                  ctypes.byref(nkt), ctypes.byref(ntile), ctypes.byref(nd)))
+        assert ntile.value == nt and ns.value == ncta, "one segment per CTA"
+        s = segs[:ns.value]
+        rng = {}
+        for g, u, a, b in s:
+            assert u == g // ng
+            rng.setdefault(int(g % ng), set()).add((int(a), int(b)))
+        assert all(len(v) == 1 for v in rng.values()), "same k-iterations for every tile of a K range"
+        ends = sorted(next(iter(v)) for v in rng.values())
+        assert ends[0][0] == 0 and ends[-1][1] == nkt.value
+        assert all(ends[i][1] == ends[i + 1][0] for i in range(len(ends) - 1))
