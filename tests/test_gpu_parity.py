@@ -763,6 +763,32 @@ def test_f32_multiply_tcgen05(m, n, k, positive):
     assert bool(((got[0].double() - got[2].double()).abs() <= 2 * F32_TC_TOL * scale).all())
 
 
+@pytest.mark.parametrize("N,ks,nslabs", [(16, 512, 3), (136, 2048, 2), (8, 96, 5), (12, 480, 4)])
+def test_f32_slab_contractions_tcgen05(N, ks, nslabs):
+    """mgb_syrk_t_slabs / mgb_gemm_tn_slabs (LocGridOrbitals: one contraction per x-slab, all slabs
+    in one launch, src/LocGridOrbitals.cc:1504-1604) for float blocks on the tcgen05 kernel: the
+    slab is the last index of the 5-D tensor maps (rows % 8 == 0 and K % 32 == 0) or of the 3-D
+    maps (any shape)."""
+    from mgmol_b200._lib import lib, check
+    g = torch.Generator(device="cuda").manual_seed(77 + N)
+    lda = ks * nslabs
+    a = torch.rand((N, lda), generator=g, device="cuda", dtype=torch.float32) - 0.3
+    b = torch.rand((N, lda), generator=g, device="cuda", dtype=torch.float32) - 0.6
+    S = torch.full((nslabs, N, N), float("nan"), device="cuda", dtype=torch.float64)
+    P = torch.full((nslabs, N, N), float("nan"), device="cuda", dtype=torch.float64)
+    check(lib().mgb_syrk_t_slabs(0, N, ks, nslabs, 2.0, a.data_ptr(), lda, S.data_ptr(), N, None))
+    check(lib().mgb_gemm_tn_slabs(0, N, N, ks, nslabs, 2.0, a.data_ptr(), lda, b.data_ptr(), lda, 0.0,
+                                  P.data_ptr(), N, None))
+    torch.cuda.synchronize()
+    for i in range(nslabs):
+        ad = a[:, i * ks:(i + 1) * ks].double()
+        bd = b[:, i * ks:(i + 1) * ks].double()
+        na, nb = torch.sqrt((ad * ad).sum(1)), torch.sqrt((bd * bd).sum(1))
+        assert bool(((S[i].t() - 2.0 * ad @ ad.t()).abs() <= 2.0 * F32_TC_TOL * torch.outer(na, na)).all())
+        assert torch.equal(S[i], S[i].t())
+        assert bool(((P[i].t() - 2.0 * ad @ bd.t()).abs() <= 2.0 * F32_TC_TOL * torch.outer(na, nb)).all())
+
+
 def test_f32_contractions_tcgen05_full_size():
     """128^3 x 256 float (the ORBDTYPE float shape of H2O_64): Gram and Phi^T (H Phi) on the
     tcgen05 kernel against FP64 cuBLAS on the widened operands."""
