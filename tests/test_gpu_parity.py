@@ -789,6 +789,25 @@ def test_f32_slab_contractions_tcgen05(N, ks, nslabs):
         assert bool(((P[i].t() - 2.0 * ad @ bd.t()).abs() <= 2.0 * F32_TC_TOL * torch.outer(na, nb)).all())
 
 
+@pytest.mark.parametrize("m,n,K", [(264, 136, 4096), (8, 392, 2048), (130, 70, 6144), (384, 128, 65536)])
+def test_f32_rectangular_projection_tcgen05(m, n, K):
+    """mgb_gemm_tn with different row counts for A and B (computeLocalProduct against a block of
+    other columns, addDotWithNcol2Matrix, src/ExtendedGridOrbitals.cc:1704-1752) on the tcgen05
+    kernel, beta accumulation included."""
+    from mgmol_b200._lib import lib, check
+    g = torch.Generator(device="cuda").manual_seed(m + n)
+    a = torch.rand((m, K), generator=g, device="cuda", dtype=torch.float32) - 0.4
+    b = torch.rand((n, K), generator=g, device="cuda", dtype=torch.float32) - 0.6
+    C0 = torch.randn((n, m), generator=g, device="cuda", dtype=torch.float64)  # column-major m x n
+    C = C0.clone()
+    check(lib().mgb_gemm_tn(0, m, n, K, 0.5, a.data_ptr(), K, b.data_ptr(), K, 1.5, C.data_ptr(), m, None))
+    torch.cuda.synchronize()
+    ad, bd = a.double(), b.double()
+    want = 0.5 * (bd @ ad.t()) + 1.5 * C0
+    na, nb = torch.sqrt((ad * ad).sum(1)), torch.sqrt((bd * bd).sum(1))
+    assert bool(((C - want).abs() <= F32_TC_TOL * torch.outer(nb, na) + 1e-15 * C0.abs()).all())
+
+
 def test_f32_contractions_tcgen05_full_size():
     """128^3 x 256 float (the ORBDTYPE float shape of H2O_64): Gram and Phi^T (H Phi) on the
     tcgen05 kernel against FP64 cuBLAS on the widened operands."""
