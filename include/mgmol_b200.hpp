@@ -35,7 +35,25 @@ namespace mgmol_b200
 {
 
 // The reference has no error codes on this path: a failed precondition ends
-// the run.  Same here, with the library's message.
+// the run.  Same here, with the library's message.  A host that must survive a
+// failure (the library's own C entry over these templates, csrc/poisson.cu)
+// defines MGMOL_B200_ERRORS_THROW before including this header: every failed
+// call then throws mgmol_b200::Error carrying the MGB_E* code instead.
+#ifdef MGMOL_B200_ERRORS_THROW
+struct Error
+{
+    int rc;
+    const char* where;
+};
+inline void check(int rc, const char* where)
+{
+    if (rc != MGB_OK) throw Error{ rc, where };
+}
+[[noreturn]] inline void fail(const char* /*message already printed*/)
+{
+    throw Error{ MGB_EINVAL, "precondition" };
+}
+#else
 inline void check(int rc, const char* where)
 {
     if (rc != MGB_OK)
@@ -44,6 +62,8 @@ inline void check(int rc, const char* where)
         std::abort();
     }
 }
+[[noreturn]] inline void fail(const char*) { std::abort(); }
+#endif
 #define MGB_CHECK(call) ::mgmol_b200::check((call), #call)
 
 template <typename T>
@@ -79,7 +99,9 @@ public:
     }
     void free()
     {
-        if (ptr_) MGB_CHECK(mgb_free(ptr_));
+        // runs in destructors (possibly while an Error unwinds): never throws
+        if (ptr_ && mgb_free(ptr_) != MGB_OK)
+            std::fprintf(stderr, "mgmol_b200: mgb_free failed: %s\n", mgb_last_error());
         ptr_  = nullptr;
         size_ = 0;
     }
@@ -247,7 +269,7 @@ public:
             {
                 std::fprintf(stderr, "Grid: gdim[%d]=%u not divisible by %d tasks\n", d,
                     gdim[d], c_.nproc[d]);
-                std::abort();
+                ::mgmol_b200::fail("precondition");
             }
             c_.dim[d] = (int)gdim[d] / c_.nproc[d];
             ll_[d]    = lattice[d];
@@ -345,7 +367,7 @@ public:
         if (type < 0 || type > 4)
         {
             std::fprintf(stderr, "GridFuncVector::applyLap: option invalid: %d\n", type);
-            std::abort();
+            ::mgmol_b200::fail("precondition");
         }
         trade_boundaries(stream);
         MGB_CHECK(mgb_fd_apply(kinds[type], dtype_of<T>::value, grid_.c(), mem_.data(),
@@ -597,7 +619,7 @@ public:
             {
                 std::fprintf(stderr,
                     "mgmol_b200: orthonormalizeLoewdin: Gram matrix not positive definite\n");
-                std::abort();
+                ::mgmol_b200::fail("precondition");
             }
             if (matrixTransform) std::copy(P.begin(), P.end(), matrixTransform);
         }
@@ -818,7 +840,7 @@ struct LapFactory
                 return new Lap<T>(grid, lap_type);
             default:
                 std::fprintf(stderr, "LapFactory::createLap() --- option invalid:%d\n", lap_type);
-                std::abort();
+                ::mgmol_b200::fail("precondition");
         }
         return nullptr;
     }

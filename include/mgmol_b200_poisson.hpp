@@ -161,7 +161,7 @@ inline void check(const Grid& grid, const int lap_type, const char* who)
     {
         std::fprintf(stderr,
             "%s: operators 0/1/2, boundary conditions 0/1 and single-rank boxes only\n", who);
-        std::abort();
+        ::mgmol_b200::fail("precondition");
     }
 }
 inline bool canCoarsen(const Grid& grid, const int ghosts)

@@ -4,8 +4,15 @@
 // library's own grid operations with one function; this file instantiates them
 // on the device field and gives them a plain-C face.
 #include <cmath>
+#include <cstring>
+
+#include <new>
 
 #include "common.cuh"
+// The header templates end the run on a failed call, like the reference; behind
+// a C entry that returns codes they must not: every failure throws
+// mgmol_b200::Error here and becomes the return value below.
+#define MGMOL_B200_ERRORS_THROW
 #include "mgmol_b200_poisson.hpp"
 
 using namespace mgb;
@@ -86,10 +93,29 @@ extern "C" int mgb_poisson_solve(int solver, int lap_type, int dtype, const mgb_
                 break;
             }
     }
-    const mgmol_b200::Grid g(gdim, ll, (short)grid->ghosts, grid->bc, grid->nproc, grid->coord);
-    if (dtype == MGB_F64)
-        return solve_t<double>(solver, lap_type, g, (double*)vh, (const double*)rho, nu1, nu2,
+    try
+    {
+        const mgmol_b200::Grid g(
+            gdim, ll, (short)grid->ghosts, grid->bc, grid->nproc, grid->coord);
+        if (dtype == MGB_F64)
+            return solve_t<double>(solver, lap_type, g, (double*)vh, (const double*)rho, nu1, nu2,
+                max_sweeps, tol, max_nlevels, stats);
+        return solve_t<float>(solver, lap_type, g, (float*)vh, (const float*)rho, nu1, nu2,
             max_sweeps, tol, max_nlevels, stats);
-    return solve_t<float>(solver, lap_type, g, (float*)vh, (const float*)rho, nu1, nu2,
-        max_sweeps, tol, max_nlevels, stats);
+    }
+    catch (const mgmol_b200::Error& e)
+    {
+        // mgb_last_error() already holds the failing call's message (e.g. the
+        // cudaMalloc of a level's work field); the level fields allocated so
+        // far were released while the exception unwound
+        if (e.rc == MGB_EINVAL && std::strcmp(e.where, "precondition") == 0)
+            set_error("mgb_poisson_solve: a precondition of the solver templates failed "
+                      "(message on stderr)");
+        return e.rc;
+    }
+    catch (const std::bad_alloc&)
+    {
+        set_error("mgb_poisson_solve: host allocation failed");
+        return MGB_ECUDA;
+    }
 }

@@ -212,3 +212,28 @@ def test_cpp_poisson_solvers_control_flow():
 def test_cpp_poisson_solvers_on_device():
     """The same templates with the device field GridFunc<T> over the C ABI."""
     _check_poisson_mirror("gpu", 1e-13, 2e-6, 1e-9, 5e-6, subset=True)
+
+
+def test_cpp_error_policy_throws_behind_c_entries():
+    """the header templates end the run on a failed call (as the
+    reference does); instantiated behind a C entry that returns codes
+    (csrc/poisson.cu) they throw mgmol_b200::Error instead
+    (MGMOL_B200_ERRORS_THROW) and the entry returns the MGB_E* code."""
+    from mgmol_b200 import build as b
+    b.build()
+    src = os.path.join(ROOT, "tests", "cpp", "test_error_policy.cc")
+    exe = os.path.join(ROOT, "tests", "cpp", "test_error_policy")
+    cmd = ["g++", "-std=c++11", "-O1", "-Wall", "-I", os.path.join(ROOT, "include"), src,
+           "-L", os.path.join(ROOT, "mgmol_b200"), "-lmgmol_b200",
+           "-Wl,-rpath,$ORIGIN/../../mgmol_b200", "-o", exe]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    assert "ok 3" in r.stdout
+    # and the library's own instantiation is the throwing one
+    with open(os.path.join(ROOT, "mgmol_b200", "csrc", "poisson.cu")) as f:
+        text = f.read()
+    assert text.index("#define MGMOL_B200_ERRORS_THROW") < text.index(
+        '#include "mgmol_b200_poisson.hpp"')
+    assert "catch (const mgmol_b200::Error&" in text
