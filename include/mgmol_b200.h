@@ -20,6 +20,16 @@
  *    stream).  Calls are asynchronous with respect to the host; like the
  *    reference's single MAGMA queue (src/magma_singleton.h:32-33) all work
  *    of one call is ordered on that one stream.
+ *  - Concurrency contract: ONE device and ONE stream of work per process, as
+ *    in the reference (one MPI rank = one device = one queue).  The library
+ *    keeps grow-only scratch blocks (work arrays of the ghosted composition,
+ *    stream-K partial tiles, host-pipeline staging) and a few settings
+ *    (mgb_hpsi_force_path, mgb_set_f32_contraction) per PROCESS, not per
+ *    stream or handle: two calls that use scratch must not overlap on
+ *    different streams or host threads, and the current device must not
+ *    change between calls.  Entry points are not
+ *    re-entrant; handles (mgb_precond, mgb_masks, mgb_kb, mgb_comm) own their
+ *    work blocks and may coexist.
  *  - Return value: MGB_OK (0) or a negative MGB_E* code; mgb_last_error()
  *    gives the message.  The reference aborts on these conditions
  *    (src/pb/Lap.h:37-38, src/pb/FDkernels.h:42-45); the C++ shim is expected
