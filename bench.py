@@ -6,10 +6,15 @@
                     [--workload h2o64|synth256|sih4] [--dtype f64|f32] [--lap 0|2]
 
 A step is one Hamiltonian::applyLocal over the whole orbital block (the fused
-H psi kernel).  Default workload = BASELINE configs[1], examples/H2O_64:
-128^3 grid, 256 orbitals, ORBDTYPE double, FDtype=4th (lap_type 2); at N > 1
-GPUs every rank owns a 128^3 box of a domain split along x (weak scaling) and
-exchanges x-halo planes over NCCL every step.  Prints ONE JSON line.
+H psi kernel).  Default workload = the largest single-GPU configuration of
+BASELINE.json: configs[4], the synthetic sweep block, 256^3 grid x 512 orbitals
+per GPU, ORBDTYPE double, Mehrstellen (`--workload h2o64` = configs[1],
+examples/H2O_64: 128^3 x 256, FDtype=4th).  At N > 1 GPUs the same global 256^3
+grid is split px x py x pz (`--decomp`, default: the factors PEenv::geom finds,
+placed on x and y) with 512 N orbitals, every rank reads its neighbours' halo
+layers in place over NVLink, and a small decomposed box is checked against the
+oracle before anything is timed (`parity_mgpu`).  `--impl reference` times the
+compiled reference on the host cores.  Prints ONE JSON line.
 """
 import argparse
 import ctypes
@@ -424,6 +429,13 @@ def measure_pieces(H, grid, phi, ham, lap_type, tdt, S, norb, npt, comm=None, hs
     hphi = hstep() if hstep else ham.applyLocal(phi, True)
     free_b, _tot = torch.cuda.mem_get_info()
     free_b += torch.cuda.memory_reserved() - torch.cuda.memory_allocated()
+    if comm is not None:
+        # every rank must pick the same chunk (the V-cycle's neighbour barriers are
+        # collective): size it for the rank with the least free memory
+        import torch.distributed as dist
+        fb = torch.tensor([free_b], dtype=torch.int64, device="cuda")
+        dist.all_reduce(fb, op=dist.ReduceOp.MIN)
+        free_b = int(fb)
     # multigrid-preconditioned residual (OrbitalsPreconditioning::precond_mg), on the H phi block
     pc = PrecondChunks(H, grid, tdt, norb, lap_type, comm, free_b)
     ms = _time_cuda(torch, lambda: pc(hphi), reps=3, warm=1)
@@ -1043,6 +1055,10 @@ def run_ours(args):
     e2e_steps = max(2, min(args.steps, 5))
     e2e_mode = "pipelined host call (mgb_hpsi_host)"
     sub_phi = H.Orbitals(grid, e2e_orb, tdt, phi.psi()[:e2e_orb])
+    # page-locking ~17 GB per rank takes seconds and the ranks compete for the host's
+    # memory system: realign them on the host before the next neighbour barrier on the
+    # device (which fails closed after ~10 s)
+    barrier()
     if world > 1:
         e2e_mode = "pipelined host call per rank, halos in place (mgb_hpsi_host_peer)"
         okp = 1
