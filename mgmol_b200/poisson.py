@@ -6,9 +6,15 @@ with nfunc = 1: boundary trade, the Laplacians and the Mehrstellen right-hand
 side, full-weighting restriction, trilinear prolongation, axpy and dot.
 
 Operators: Laph4M (0), Laph2 (1), Laph4 (2); boundary conditions 0 (zero
-Dirichlet) and 1 (periodic) per direction.  Multipole boundary values (bc 2),
-the dielectric (PB) operators and decomposed boxes (the gather of the coarse
-level, src/pb/Vcycle.h:69-143) are not part of it.
+Dirichlet) and 1 (periodic) per direction.  Multipole boundary values (bc 2)
+and the dielectric (PB) operators are not part of it.
+
+Decomposed boxes (px x py x pz ranks, one GPU each): pass the rank's
+`Communicator`.  Fields then trade their boundaries with the neighbour ranks
+(mgb_halo_exchange_ghosted: Y, Z, X faces as src/pb/GridFuncVector.cc:1544-1622),
+dot products, norms and the average are all-reduced, and the level the local
+boxes cannot coarsen any more is gathered on every rank and solved replicated,
+as src/pb/Vcycle.h:66-143 does ("gather and solve on all PEs").
 
 The solver works on "fields": objects with the GridFuncVector interface of
 host.py.  The default is the device class; the CPU tests drive this very
@@ -27,23 +33,66 @@ _MIN_GHOSTS = {0: 1, 1: 1, 2: 2}
 _LOWER_ORDER = {0: 0, 1: 1, 2: 1}
 
 
-def _device_field(grid, dtype):
-    return GridFuncVector(grid, 1, dtype)
+def _nranks(grid):
+    return grid.nproc[0] * grid.nproc[1] * grid.nproc[2]
 
 
-def _bind(field, dtype):
-    """field(grid, dtype) -> field of the solver's precision."""
-    make = field if field is not None else _device_field
+class DecomposedField(GridFuncVector):
+    """pb::GridFunc<T> of a rank of a decomposed box: the boundary trade goes to
+    the neighbour ranks, the reductions over the grid are all-reduced
+    (GridFunc::gdot / norm2 / get_average with n_mpi_tasks() > 1,
+    src/pb/GridFunc.cc:2745-2798, 2856-2861, 2888-2927)."""
+
+    def __init__(self, grid, dtype, comm):
+        super().__init__(grid, 1, dtype)
+        self.comm_ = comm
+
+    def trade_boundaries(self):
+        self.comm_.trade_boundaries(self)
+
+    def gdot(self, other, comm=None):
+        return super().gdot(other, self.comm_)
+
+    def get_average(self):
+        # local sum / local size, summed over the ranks, / n_mpi_tasks
+        t = torch.tensor([super().get_average()], dtype=torch.float64, device="cuda")
+        self.comm_.allreduce(t)
+        return float(t.item()) / _nranks(self.grid_)
+
+    def gather(self):
+        """GridFunc::init_vect(global, 'g'): the function on the whole box, on
+        every rank, without ghosts (shape (1, gx, gy, gz)).  Every point is owned
+        by one rank, so the sum over zero-padded contributions is exact."""
+        from .parallel import local_box
+        gr = self.grid_
+        glob = torch.zeros((1,) + tuple(gr.gdim_), dtype=torch.float64, device="cuda")
+        glob[(slice(None),) + local_box(gr.gdim_, gr.nproc, gr.coord)] = self.values().double()
+        self.comm_.allreduce(glob)
+        return glob.to(self.data.dtype)
+
+
+def _device_field(comm):
+    def make(grid, dtype):
+        if _nranks(grid) > 1:
+            return DecomposedField(grid, dtype, comm)
+        return GridFuncVector(grid, 1, dtype)
+    return make
+
+
+def _bind(field, dtype, comm=None):
+    """field(grid, dtype) -> field of the solver's precision.  A field factory
+    serves single-rank grids (the replicated coarse levels) and decomposed ones."""
+    make = field if field is not None else _device_field(comm)
     return lambda grid, dt=dtype: make(grid, dt)
 
 
-def _check(grid, lap_type, who):
+def _check(grid, lap_type, who, decomposed=False):
     if lap_type not in _MIN_GHOSTS:
         raise ValueError("%s: operator %d not available" % (who, lap_type))
     if any(b not in (0, 1) for b in grid.bc):
         raise ValueError("%s: boundary conditions 0 and 1 only" % who)
-    if tuple(grid.nproc) != (1, 1, 1):
-        raise ValueError("%s: single-rank boxes only" % who)
+    if _nranks(grid) > 1 and not decomposed:
+        raise ValueError("%s: a decomposed box needs the ranks' communicator" % who)
 
 
 # Lap::jacobi (src/pb/Lap.cc:26-37): W = A x - B; x += scale * W
@@ -58,15 +107,18 @@ def _jacobi(lap_type, x, rhs, w, scale):
 class PoissonMG:
     """pb::SolverLap<T, T2> (src/pb/SolverLap.h:18-77)."""
 
-    def __init__(self, grid, lap_type, dtype=torch.float64, field=None):
-        _check(grid, lap_type, "PoissonMG")
+    def __init__(self, grid, lap_type, dtype=torch.float64, field=None, comm=None):
+        _check(grid, lap_type, "PoissonMG", comm is not None or field is not None)
         self.grid_ = grid.with_ghosts(_MIN_GHOSTS[lap_type])
         self.type_ = lap_type
-        self.field_ = _bind(field, dtype)
+        self.field_ = _bind(field, dtype, comm)
+        self.gather_coarse_level_ = True
         # device fields: the V-cycle -- a fixed sequence of ~200 small kernels down to the
         # 1^3 level -- is captured once in a CUDA graph and replayed every sweep, so the
-        # host launches one graph instead of ~200 kernels (MGB_POISSON_GRAPH=0: eager)
-        self.use_graph_ = field is None and os.environ.get("MGB_POISSON_GRAPH", "1") != "0"
+        # host launches one graph instead of ~200 kernels (MGB_POISSON_GRAPH=0: eager).
+        # Decomposed boxes run it eagerly (the exchanges are NCCL calls).
+        self.use_graph_ = (field is None and _nranks(grid) == 1
+                           and os.environ.get("MGB_POISSON_GRAPH", "1") != "0")
         self.graph_ = None
         self.graph_replays = 0
         self.fully_periodic_ = tuple(grid.bc) == (1, 1, 1)
@@ -81,6 +133,7 @@ class PoissonMG:
         self.max_sweeps_ = int(max_sweeps)
         self.tol_ = float(tol)
         self.max_nlevels_ = int(max_nlevels)
+        self.gather_coarse_level_ = bool(gather_coarse_level)
         self.graph_ = None  # the captured cycle depends on nu1, nu2 and the level count
 
     def _cycle(self, work1, res):
@@ -130,12 +183,28 @@ class PoissonMG:
         return out
 
     # -- pb::Vcycle (src/pb/Vcycle.h:29-250), x = 0 on entry --------------------
-    def _vcycle(self, lap_type, x, rhs, cogr):
+    def _vcycle(self, lap_type, x, rhs, cogr, gather=None):
         grid = x.grid()
         g = grid.ghost_pt()
+        flag_coarsen = all(grid.dim(d) % 2 == 0 and grid.dim(d) >= 2 * g for d in range(3))
+        if gather is None:
+            gather = self.gather_coarse_level_
+        if (not flag_coarsen or grid.level_ <= -cogr) and gather and _nranks(grid) > 1:
+            # src/pb/Vcycle.h:66-143: the local boxes cannot be coarsened any further --
+            # gather this level on every rank, run the rest of the cycle replicated on
+            # the whole box, keep the local part ("gather and solve on all PEs")
+            from .host import Grid
+            from .parallel import local_box
+            rgrid = Grid(grid.gdim_, grid.ll_, g, grid.bc, (1, 1, 1), (0, 0, 0), grid.level_)
+            rrhs, rx = self.field_(rgrid), self.field_(rgrid)
+            rrhs.assign(rhs.gather())
+            self._vcycle(lap_type, rx, rrhs, cogr - grid.level_, gather=False)
+            box = (slice(None),) + local_box(grid.gdim_, grid.nproc, grid.coord)
+            mine = rx.values()[box]
+            x.assign(mine.contiguous() if hasattr(mine, "contiguous") else mine.copy())
+            return
         lap = Lap(grid, lap_type)
         scale = -1. * lap.jacobiFactor()
-        flag_coarsen = all(grid.dim(d) % 2 == 0 and grid.dim(d) >= 2 * g for d in range(3))
         res = self.field_(grid)
         for _ in range(self.nu1_):
             _jacobi(lap_type, x, rhs, res, scale)
@@ -155,7 +224,7 @@ class PoissonMG:
                 rcoarse = self._regrid(tmp, coarse_grid)
             rcoarse.set_updated_boundaries(False)
             ucoarse = self.field_(coarse_grid)
-            self._vcycle(coarse_type, ucoarse, rcoarse, cogr)
+            self._vcycle(coarse_type, ucoarse, rcoarse, cogr, gather)
             if gc == g:
                 res.extend3D(ucoarse)
             else:
@@ -220,14 +289,17 @@ class PoissonPCG:
     (Control::lap_type in the reference), Laph2 below, the coarse grids keeping
     the fine grid's ghost width."""
 
-    def __init__(self, grid, lap_type, dtype=torch.float64, field=None, precond_dtype=None):
-        _check(grid, lap_type, "PoissonPCG")
+    def __init__(self, grid, lap_type, dtype=torch.float64, field=None, precond_dtype=None,
+                 comm=None):
+        _check(grid, lap_type, "PoissonPCG", comm is not None or field is not None)
         self.grid_ = grid.with_ghosts(_MIN_GHOSTS[lap_type])
         self.type_ = lap_type
-        self.field_ = _bind(field, dtype)
+        self.field_ = _bind(field, dtype, comm)
         if precond_dtype is None:
             precond_dtype = torch.float32
-        self.pfield_ = _bind(field, precond_dtype)
+        # the preconditioner's levels are the local boxes' own (setupPrecon coarsens
+        # mygrid without a gather, src/PCGSolver.cc:50-110)
+        self.pfield_ = _bind(field, precond_dtype, comm)
         self.fully_periodic_ = tuple(grid.bc) == (1, 1, 1)
         self.final_residual_ = -1.
         self.residual_reduction_ = -1.
@@ -349,13 +421,13 @@ class Hartree:
     Poisson solver; boundary conditions 0 / 1 (no multipole boundary values)."""
 
     def __init__(self, grid, lap_type, dtype=torch.float64, field=None, pcg=False,
-                 rho_dtype=torch.float64, precond_dtype=None):
-        self.field_ = _bind(field, dtype)
-        self.rfield_ = _bind(field, rho_dtype)
+                 rho_dtype=torch.float64, precond_dtype=None, comm=None):
+        self.field_ = _bind(field, dtype, comm)
+        self.rfield_ = _bind(field, rho_dtype, comm)
         if pcg:
-            self.poisson_solver_ = PoissonPCG(grid, lap_type, dtype, field, precond_dtype)
+            self.poisson_solver_ = PoissonPCG(grid, lap_type, dtype, field, precond_dtype, comm)
         else:
-            self.poisson_solver_ = PoissonMG(grid, lap_type, dtype, field)
+            self.poisson_solver_ = PoissonMG(grid, lap_type, dtype, field, comm)
         self.grid_ = self.poisson_solver_.grid_
         zero = self.field_(self.grid_)
         zero.resetData()
@@ -363,7 +435,10 @@ class Hartree:
         self.Int_vhrho_ = self.Int_vhrhoc_ = self.Int_vhrho_old_ = 0.
 
     def setup(self, nu1, nu2, max_sweeps, tol, max_nlevels, gather_coarse_level=True):
-        self.poisson_solver_.setup(nu1, nu2, max_sweeps, tol, max_nlevels)
+        if isinstance(self.poisson_solver_, PoissonMG):
+            self.poisson_solver_.setup(nu1, nu2, max_sweeps, tol, max_nlevels, gather_coarse_level)
+        else:  # Hartree_CG ignores the flag (src/Hartree_CG.h:35-37)
+            self.poisson_solver_.setup(nu1, nu2, max_sweeps, tol, max_nlevels)
 
     def vh(self):
         return self.vh_

@@ -122,3 +122,85 @@ def field_factory(port, dtype=None):
     import torch
     tmap = {torch.float32: np.float32, torch.float64: np.float64}
     return lambda grid, dt: TwinField(port, grid, tmap.get(dt, dt))
+
+
+# ---------------------------------------------------------------------------
+# Decomposed boxes (world_size > 1 over gloo): the stand-in for
+# mgmol_b200.poisson.DecomposedField.  A decomposed boundary trade leaves on
+# every rank the matching piece of the single-rank trade of the whole box (that
+# is what the device exchange is tested for in tests/mgpu_worker.py), so the twin
+# gathers the box, lets the oracle trade it, and cuts its piece out again.
+# ---------------------------------------------------------------------------
+class DecomposedTwinField(TwinField):
+    def _box(self, ghosts=0):
+        gr = self.grid_
+        return tuple(slice(c * n, c * n + n + 2 * ghosts) for c, n in zip(gr.coord, gr.dim_))
+
+    def _allreduce(self, a):
+        import torch
+        import torch.distributed as dist
+        t = torch.from_numpy(np.ascontiguousarray(a, np.float64))
+        dist.all_reduce(t)
+        return t.numpy()
+
+    def gather(self):
+        glob = np.zeros((1,) + tuple(self.grid_.gdim_), np.float64)
+        glob[(slice(None),) + self._box()] = self.data[self._sl()]
+        return self._allreduce(glob).astype(self.data.dtype)
+
+    def trade_boundaries(self):
+        if self.updated_boundaries_:
+            return
+        g = self.grid_.ghost_pt()
+        traded = self.port_.trade_boundaries(self.gather(), g, self.grid_.bc)
+        self.data = np.ascontiguousarray(traded[(slice(None),) + self._box(g)])
+        self.updated_boundaries_ = True
+
+    def _raw(self, name, *args):
+        from oracle.oracle import _sfx
+        return getattr(self.port_.lib, name + _sfx(self.data.dtype))(*args)
+
+    def restrict3D(self, ucoarse):
+        from oracle.oracle import _c_int3, _ptr
+        self.trade_boundaries()
+        g = self.grid_.ghost_pt()
+        fine = np.ascontiguousarray(self.data)
+        out = np.zeros((1,) + tuple(d // 2 + 2 * g for d in self.grid_.shape()), fine.dtype)
+        self._raw("orc_restrict3D", _c_int3(*self.grid_.shape()), g, _ptr(fine), _ptr(out), 1)
+        ucoarse.data = out
+
+    def extend3D(self, ucoarse):
+        from oracle.oracle import _c_int3, _ptr
+        ucoarse.trade_boundaries()
+        g = self.grid_.ghost_pt()
+        coarse = np.ascontiguousarray(ucoarse.data)
+        fine = np.ascontiguousarray(self.data)
+        self._raw("orc_extend3D", _c_int3(*self.grid_.shape()), g, _ptr(coarse), _ptr(fine), 1)
+        self.data = fine
+        self.updated_boundaries_ = False
+
+    def _interior(self, drop):
+        g = self.grid_.ghost_pt()
+        nx, ny, nz = self.grid_.shape()
+        lo = [g + (1 if (drop and self.grid_.bc[d] != 1 and self.grid_.coord[d] == 0) else 0)
+              for d in range(3)]
+        return self.data[0, lo[0]:g + nx, lo[1]:g + ny, lo[2]:g + nz].astype(np.float64)
+
+    def gdot(self, other):
+        return float(self._allreduce(np.array([super().gdot(other)]))[0])
+
+    def get_average(self):
+        gr = self.grid_
+        n = gr.nproc[0] * gr.nproc[1] * gr.nproc[2]
+        return float(self._allreduce(np.array([super().get_average()]))[0]) / n
+
+
+def decomposed_field_factory(port):
+    """Single-rank grids (the replicated coarse levels) get the plain twin."""
+    import torch
+    tmap = {torch.float32: np.float32, torch.float64: np.float64}
+
+    def make(grid, dt):
+        cls = DecomposedTwinField if tuple(grid.nproc) != (1, 1, 1) else TwinField
+        return cls(port, grid, tmap.get(dt, dt))
+    return make
