@@ -17,7 +17,6 @@ oracle before anything is timed (`parity_mgpu`).  `--impl reference` times the
 compiled reference on the host cores.  Prints ONE JSON line.
 """
 import argparse
-import ctypes
 import json
 import os
 import subprocess
