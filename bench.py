@@ -1156,6 +1156,11 @@ def run_ours(args):
                     "h2d_bytes_per_step": int(S * npt * e2e_orb) * world,
                     "d2h_bytes_per_step": int(S * npt * e2e_orb) * world,
                     "orbitals_per_step": e2e_orb,
+                    # both PCIe directions of all ranks together: what the host's memory
+                    # system serves (the limiter of this figure at N > 1, where the per-rank
+                    # pipelines share one host)
+                    "host_GBps_both_ways": 2.0 * S * npt * e2e_orb * world * e2e_steps
+                                           / (e2e_ms * 1e-3) / 1e9,
                     "how": e2e_mode + "; host memory bounded: %d of the %d orbitals per step"
                            % (e2e_orb, norb)},
             "gpu_launches": int(launches),
