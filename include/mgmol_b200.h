@@ -124,9 +124,10 @@ int mgb_fd_apply(int kind, int dtype, const mgb_grid* grid, const void* v,
  * phi, hphi: no-ghost npt x nfunc blocks (ld elements apart); vtot: POTDTYPE
  * double[npt] without ghosts (src/Potentials.h:141).  One pass over phi: the
  * ghost-add, halo, V*psi, B, Laplacian, axpy and ghost-strip sweeps of the
- * reference are fused.  Directions with nproc > 1 take their neighbour planes
- * from the halo set given by mgb_halo_* (x split only on the fused path; y/z
- * splits go through the ghosted-block composition below).
+ * reference are fused.  On an x-split box this entry takes the neighbour planes
+ * from the packed halo buffers below; every decomposition, x slabs included, is
+ * served without any packed copy by mgb_hpsi_peer / mgb_hpsi_peer3d (section
+ * "multi-GPU"), which read the neighbours' blocks in place.
  * xhalo_phi / xhalo_v: NULL when grid->nproc[0]==1; otherwise device buffers
  * [nfunc][2g][ny][nz] (phi) and [2g][ny][nz] (vtot): the g planes below the
  * box then the g planes above it, as filled by mgb_halo_exchange_x.         */
@@ -280,10 +281,12 @@ int mgb_precond_destroy(mgb_precond* p);
 /* Boxes that are one rank of a decomposition (grid->nproc): the communicator the
  * V-cycle exchanges ghosts over -- every GridFuncVector::trade_boundaries of
  * Preconditioning<float>::mg (MPI_Isend/Irecv in the reference, src/pb/
- * GridFuncVector.cc:1544-1622).  x-split boxes run the fused kernels, reading
- * the neighbours' boundary planes in place over NVLink; other decompositions
- * run the literal sequence with the packed Y -> Z -> X exchange.  Calls are
- * then collective over the communicator.                                     */
+ * GridFuncVector.cc:1544-1622).  Any px x py x pz decomposition runs the fused
+ * kernels, reading the neighbours' boundary planes, rows and (pushed) columns of
+ * the work blocks in place over NVLink; boxes the fused kernels do not take
+ * (mixed boundary conditions, blocks the neighbours cannot map) run the literal
+ * sequence with the packed Y -> Z -> X exchange.  Calls are then collective
+ * over the communicator.                                                     */
 int mgb_precond_set_comm(mgb_precond* p, mgb_comm* comm);
 /* OrbitalsPreconditioning::setup with currentMasks != nullptr (src/
  * OrbitalsPreconditioning.cc:59-67 -> GridFuncVector::setMasks): every

@@ -18,6 +18,9 @@
 //   ExtendedGridOrbitals (ExtendedGridOrbitals.h:43-404)          ExtendedGridOrbitals<T>
 //   Hamiltonian<T> (Hamiltonian.h:20-52)                          Hamiltonian<T>
 //   OrbitalsPreconditioning<T> (OrbitalsPreconditioning.h:27-70)  OrbitalsPreconditioning<T>
+//   pb::PEenv / MGmol_MPI, the decomposed path (pb/PEenv.h:34-203)  Communicator
+//   KBPsiMatrixSparse + get_vnlpsi (KBPsiMatrixSparse.cc:136-212,  KBProjectors<T>
+//     get_vnlpsi.cc:24-87, computeHij.cc:294-375)
 #ifndef MGMOL_B200_HPP
 #define MGMOL_B200_HPP
 
@@ -778,6 +781,68 @@ private:
     const Masks* masks_;
 };
 
+// The slice of pb::PEenv / MGmol_MPI the decomposed path needs (src/pb/PEenv.h:34-203,
+// src/tools/MGmol_MPI.h): one process per GPU, the 3-D block decomposition carried by
+// Grid (nproc, coord).  The 128-byte id is created on rank 0 (uniqueId) and handed to
+// the other ranks by the caller -- MPI_Bcast inside MGmol.
+class Communicator
+{
+public:
+    static void uniqueId(unsigned char id128[128]) { MGB_CHECK(mgb_comm_unique_id(id128)); }
+    Communicator(const unsigned char id128[128], const int rank, const int nranks)
+        : handle_(nullptr), rank_(rank), nranks_(nranks)
+    {
+        MGB_CHECK(mgb_comm_create(&handle_, id128, rank, nranks));
+    }
+    ~Communicator()
+    {
+        if (handle_) mgb_comm_destroy(handle_);
+    }
+    Communicator(const Communicator&) = delete;
+    Communicator& operator=(const Communicator&) = delete;
+    mgb_comm* handle() const { return handle_; }
+    int rank() const { return rank_; }
+    int nranks() const { return nranks_; }
+    // MGmol_MPI::allreduce(double*, n, MPI_SUM) on a device array
+    void allreduce(double* dev, const size_t n, void* stream = nullptr)
+    {
+        MGB_CHECK(mgb_allreduce_sum_f64(handle_, dev, n, stream));
+    }
+    void barrier(void* stream = nullptr) { MGB_CHECK(mgb_comm_barrier(handle_, stream)); }
+    // device sync + did a neighbour barrier of the in-place halo paths time out?
+    void check() { MGB_CHECK(mgb_comm_check(handle_)); }
+    // collective: publish this rank's resident array (its orbital block) so that the
+    // neighbours' kernels read its boundary layers in place over NVLink
+    void registerArray(const void* dev, void* stream = nullptr)
+    {
+        MGB_CHECK(mgb_peer_register(handle_, dev, stream));
+    }
+    void unregisterArray(const void* dev) { MGB_CHECK(mgb_peer_unregister(handle_, dev)); }
+    // GridFuncVector::trade_boundaries on a px x py x pz decomposition: Y, Z, X faces
+    // (src/pb/GridFuncVector.cc:1544-1622)
+    template <typename T>
+    void trade_boundaries(GridFuncVector<T>& gfv, void* stream = nullptr)
+    {
+        if (gfv.updated_boundaries()) return;
+        MGB_CHECK(mgb_halo_exchange_ghosted(
+            handle_, dtype_of<T>::value, gfv.grid().c(), gfv.data(), gfv.size(), stream));
+        gfv.set_updated_boundaries(true);
+    }
+    // the packed x halo of a no-ghost block: xhalo[nfunc][2g][ny][nz]
+    // (initiate/finishEastWestComm, src/pb/GridFuncVector.cc:1195-1256)
+    template <typename T>
+    void haloExchangeX(const Grid& grid, const int g, const T* noghost, const size_t ld, T* xhalo,
+        const int nfunc, void* stream = nullptr)
+    {
+        MGB_CHECK(mgb_halo_exchange_x(
+            handle_, dtype_of<T>::value, grid.c(), g, noghost, ld, xhalo, nfunc, stream));
+    }
+
+private:
+    mgb_comm* handle_;
+    int rank_, nranks_;
+};
+
 // pb::Lap<T> as LapFactory creates it
 template <typename T>
 class Lap
@@ -807,6 +872,25 @@ public:
     {
         MGB_CHECK(mgb_hpsi(type_, dtype_of<T>::value, grid_.c(), phi, ld, vtot, hphi, ldh,
             nfunc, xhalo_phi, xhalo_v, stream));
+    }
+    // applyWithPot on one rank of a decomposed domain: the neighbours' boundary planes,
+    // rows, columns and Mehrstellen edge lines of phi are read in place from their
+    // registered blocks (Communicator::registerArray) by the same fused kernel.
+    // vghost: the potential as a ghosted double field with traded boundaries (gfpot of
+    // src/Hamiltonian.cc:108-111; Hamiltonian::updatePotentialHalo); may be null for
+    // MGB_LAP_4.  Collective over the communicator.
+    void applyWithPotPeer(Communicator& comm, const T* phi, const size_t ld, const double* vtot,
+        const double* vghost, T* hphi, const size_t ldh, const int nfunc, void* stream = nullptr)
+    {
+        MGB_CHECK(mgb_hpsi_peer3d(comm.handle(), type_, dtype_of<T>::value, grid_.c(), phi, ld,
+            vtot, vghost, hphi, ldh, nfunc, stream));
+    }
+    // the x-slab form: V's halo as the 2g packed x planes (Communicator::haloExchangeX)
+    void applyWithPotPeerX(Communicator& comm, const T* phi, const size_t ld, const double* vtot,
+        const double* xhalo_v, T* hphi, const size_t ldh, const int nfunc, void* stream = nullptr)
+    {
+        MGB_CHECK(mgb_hpsi_peer(comm.handle(), type_, dtype_of<T>::value, grid_.c(), phi, ld, vtot,
+            hphi, ldh, nfunc, xhalo_v, stream));
     }
     // Lap<T>::rhs (src/pb/Lap.h:32) for nfunc orbitals of a no-ghost block: B phi
     // (Mehrstellen, src/pb/FDkernels.cc:522-584) or a copy (B = 1)
@@ -885,6 +969,41 @@ public:
             hphi.getLda(), ncolors, nullptr, nullptr, stream);
         hphi.incrementIterativeIndex();
     }
+    // Decomposed domains.  Once per potential update: the ghosted copy of vtot with
+    // boundaries traded over the ranks (gfpot, src/Hamiltonian.cc:108-111).
+    void updatePotentialHalo(const Grid& myGrid, Communicator& comm, void* stream = nullptr)
+    {
+        const Grid gg = myGrid.with_ghosts(lapOper_->minNumberGhosts());
+        vghost_.reset(new GridFuncVector<double>(gg, 1));
+        vghost_->assign(pot_->vtot(), gg.size(), stream);
+        comm.trade_boundaries(*vghost_, stream);
+    }
+    // applyLocal with phi's halo read in place from the neighbour ranks: phi's block must
+    // be registered (comm.registerArray(phi.getPsi())); same cache key as above
+    const ExtendedGridOrbitals<T>& applyLocal(ExtendedGridOrbitals<T>& phi, Communicator& comm,
+        const bool force = false, void* stream = nullptr)
+    {
+        if (!vghost_)
+        {
+            std::fprintf(stderr, "Hamiltonian::applyLocal: updatePotentialHalo was not called\n");
+            ::mgmol_b200::fail("precondition");
+        }
+        if (!hlphi_ || hlphi_->numst() != phi.numst())
+        {
+            hlphi_.reset(new ExtendedGridOrbitals<T>(phi.grid(), phi.numst()));
+            itindex_ = -1;
+        }
+        const int new_index = 100 * phi.getIterativeIndex() + pot_->getIterativeIndex();
+        if (force || new_index != itindex_)
+        {
+            lapOper_->applyWithPotPeer(comm, phi.getPsi(), phi.getLda(), pot_->vtot(),
+                vghost_->data(), hlphi_->getPsi(), hlphi_->getLda(), phi.chromatic_number(),
+                stream);
+            hlphi_->incrementIterativeIndex();
+            itindex_ = new_index;
+        }
+        return *hlphi_;
+    }
     // src/Hamiltonian.cc:163-212: hij_dev += vel Phi1^T (H_loc Phi2), summed over ranks
     void addHlocal2matrix(ExtendedGridOrbitals<T>& phi1, ExtendedGridOrbitals<T>& phi2,
         double* hij_dev, double* work_dev, const bool force = false, mgb_comm* comm = nullptr,
@@ -905,6 +1024,7 @@ private:
     std::unique_ptr<Lap<T>> lapOper_;
     std::unique_ptr<Potentials> pot_;
     std::unique_ptr<ExtendedGridOrbitals<T>> hlphi_;
+    std::unique_ptr<GridFuncVector<double>> vghost_;
     int itindex_;
 };
 
@@ -953,6 +1073,13 @@ public:
             orbitals.getLda(), orbitals.chromatic_number(), gamma_, stream));
         orbitals.incrementIterativeIndex();
     }
+    // decomposed domains: the communicator the V-cycle reads / exchanges its ghosts
+    // over (every trade_boundaries of Preconditioning<float>::mg); calls are then
+    // collective.  nullptr: single rank.
+    void setComm(Communicator* comm)
+    {
+        MGB_CHECK(mgb_precond_set_comm(handle_, comm ? comm->handle() : nullptr));
+    }
     mgb_precond* handle() { return handle_; }
 
 private:
@@ -960,6 +1087,99 @@ private:
     double gamma_;
     short mg_levels_;
     bool is_set_;
+};
+
+// The non-local Kleinman-Bylander projectors overlapping the local box, as the sparse
+// vectors KBprojectorSparse holds (src/KBprojectorSparse.h:39-52), with the two grid-sized
+// steps that follow applyLocal in MGmol::getHpsiAndTheta (src/computeHij.cc:404-455):
+// KBPsiMatrixSparse::computeKBpsi (src/KBPsiMatrixSparse.cc:136-212) and
+// computeHnlPhiAndAdd2HPhi (src/computeHij.cc:294-375) over get_vnlpsi
+// (src/get_vnlpsi.cc:24-87).  KBPROJDTYPE = ORBDTYPE (src/global.h:38).
+template <typename T>
+class KBProjectors
+{
+public:
+    explicit KBProjectors(const Grid& grid) : grid_(grid), handle_(nullptr)
+    {
+        MGB_CHECK(mgb_kb_create(&handle_, dtype_of<T>::value, grid.size()));
+    }
+    ~KBProjectors()
+    {
+        if (handle_) mgb_kb_destroy(handle_);
+    }
+    KBProjectors(const KBProjectors&) = delete;
+    KBProjectors& operator=(const KBProjectors&) = delete;
+    // One ion (Ions::overlappingNL_ions order): nlindex = node positions in the no-ghost
+    // storage, proj = nproj arrays of nlindex.size() values (host), coeff[p] = kbcoeff_p *
+    // sign_p.  Returns the row of the ion's first projector in kbpsi.
+    int addIon(const std::vector<int>& nlindex, const T* proj, const std::vector<double>& coeff)
+    {
+        int row = 0;
+        MGB_CHECK(mgb_kb_add_ion(handle_, (int)nlindex.size(), nlindex.data(), (int)coeff.size(),
+            proj, coeff.data(), &row));
+        return row;
+    }
+    void commit() { MGB_CHECK(mgb_kb_commit(handle_)); }
+    int nrows() const { return mgb_kb_nrows(handle_); }
+    // kbpsi_dev[row * nfunc + f] = vel <beta_row | psi_f> (double, device, nrows x nfunc),
+    // summed over the ranks (globalSumKBpsi).  lapOper: the reference's `flag` -- project
+    // B phi instead of phi (Mehrstellen, kbBpsi); work_dev then holds B phi (numpt x nfunc).
+    void computeKBpsi(const ExtendedGridOrbitals<T>& orbitals, double* kbpsi_dev,
+        Communicator* comm = nullptr, const Lap<T>* lapOper = nullptr, T* work_dev = nullptr,
+        void* stream = nullptr)
+    {
+        const T* psi    = orbitals.getPsi();
+        const int nfunc = orbitals.chromatic_number();
+        if (lapOper)
+        {
+            if (!work_dev)
+            {
+                std::fprintf(stderr, "KBProjectors::computeKBpsi: B phi needs a work block\n");
+                ::mgmol_b200::fail("precondition");
+            }
+            lapOper->rhs(psi, orbitals.getLda(), work_dev, orbitals.getLda(), nfunc, nullptr, stream);
+            psi = work_dev;
+        }
+        MGB_CHECK(mgb_kb_psi(handle_, dtype_of<T>::value, grid_.vel(), psi, orbitals.getLda(), nfunc,
+            kbpsi_dev, stream));
+        if (comm) comm->allreduce(kbpsi_dev, (size_t)nrows() * nfunc, stream);
+    }
+    // get_vnlpsi for every function: out_f = sum over the ions of (T)(sum_p alpha_p beta_p)
+    void getVnlPsi(const double* kbpsi_dev, T* out_dev, const size_t ldo, const int nfunc,
+        void* stream = nullptr)
+    {
+        MGB_CHECK(mgb_kb_vnlpsi(
+            handle_, dtype_of<T>::value, kbpsi_dev, out_dev, ldo, nfunc, 0, stream));
+    }
+    // H phi += V_nl phi in one pass over the touched points; with the Mehrstellen operator
+    // H phi += B (V_nl phi) (src/computeHij.cc:346-372), through two work blocks
+    void computeHnlPhiAndAdd2HPhi(const double* kbpsi_dev, ExtendedGridOrbitals<T>& hphi,
+        const Lap<T>* lapOper = nullptr, T* work_dev = nullptr, T* bwork_dev = nullptr,
+        void* stream = nullptr)
+    {
+        const int nfunc = hphi.chromatic_number();
+        if (lapOper && (lapOper->type() == MGB_LAP_4M || lapOper->type() == MGB_LAP_4MP))
+        {
+            if (!work_dev || !bwork_dev)
+            {
+                std::fprintf(stderr, "KBProjectors::computeHnlPhiAndAdd2HPhi: two work blocks\n");
+                ::mgmol_b200::fail("precondition");
+            }
+            getVnlPsi(kbpsi_dev, work_dev, hphi.getLda(), nfunc, stream);
+            lapOper->rhs(work_dev, hphi.getLda(), bwork_dev, hphi.getLda(), nfunc, nullptr, stream);
+            MGB_CHECK(mgb_axpy(dtype_of<T>::value, hphi.getLda() * (size_t)nfunc, 1., bwork_dev,
+                hphi.getPsi(), stream));
+        }
+        else
+            MGB_CHECK(mgb_kb_vnlpsi(handle_, dtype_of<T>::value, kbpsi_dev, hphi.getPsi(),
+                hphi.getLda(), nfunc, 1, stream));
+        hphi.incrementIterativeIndex();
+    }
+    mgb_kb* handle() { return handle_; }
+
+private:
+    Grid grid_;
+    mgb_kb* handle_;
 };
 
 // MGmol::computeResidualUsingHPhi (src/MGmol.cc:1227-1287):

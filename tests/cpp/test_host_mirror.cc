@@ -30,6 +30,16 @@ void orc_app_mask_noghost_f64(const int dims[3], int subdivx, int ncolors, int o
 void orc_app_mask_noghost_f32(const int dims[3], int subdivx, int ncolors, int op,
     const int* state, const long long* voff, const double* values, float* u, size_t ld,
     int nfunc);
+void orc_kb_psi_f64(int nions, const long long* node0, const int* row0, const int* nlindex,
+    const double* proj, double vel, const double* psi, size_t ld, int nfunc, double* kbpsi);
+void orc_kb_psi_f32(int nions, const long long* node0, const int* row0, const int* nlindex,
+    const float* proj, double vel, const float* psi, size_t ld, int nfunc, double* kbpsi);
+void orc_kb_vnlpsi_f64(int nions, const long long* node0, const int* row0, const int* nlindex,
+    const double* proj, const double* coeff, const double* kbpsi, size_t npt, double* out,
+    size_t ldo, int nfunc, int add);
+void orc_kb_vnlpsi_f32(int nions, const long long* node0, const int* row0, const int* nlindex,
+    const float* proj, const double* coeff, const double* kbpsi, size_t npt, float* out,
+    size_t ldo, int nfunc, int add);
 void orc_add_ghosts_f64(const int dims[3], int g, const double* noghost, double* ghosted, int nfunc);
 void orc_add_ghosts_f32(const int dims[3], int g, const float* noghost, float* ghosted, int nfunc);
 void orc_trade_boundaries_f64(const int dims[3], int g, const int bc[3], double* u, int nfunc);
@@ -442,6 +452,130 @@ static int run_localized(const int lap_type, const int op, const double mg_tol)
     return fails;
 }
 
+
+// KBProjectors (row f3): the sparse projectors of three synthetic ions -- balls of grid
+// points around a centre, one or four projectors each, two of them overlapping -- through
+// computeKBpsi and computeHnlPhiAndAdd2HPhi against the oracle's restatement of
+// KBPsiMatrixSparse::computeKBpsi / get_vnlpsi (oracle/mgmol_oracle_kb.inc).
+static void oracle_kb_psi(int nions, const long long* node0, const int* row0, const int* idx,
+    const double* proj, double vel, const double* psi, size_t ld, int nf, double* kbpsi)
+{
+    orc_kb_psi_f64(nions, node0, row0, idx, proj, vel, psi, ld, nf, kbpsi);
+}
+static void oracle_kb_psi(int nions, const long long* node0, const int* row0, const int* idx,
+    const float* proj, double vel, const float* psi, size_t ld, int nf, double* kbpsi)
+{
+    orc_kb_psi_f32(nions, node0, row0, idx, proj, vel, psi, ld, nf, kbpsi);
+}
+static void oracle_kb_vnlpsi(int nions, const long long* node0, const int* row0, const int* idx,
+    const double* proj, const double* coeff, const double* kbpsi, size_t npt, double* out,
+    size_t ldo, int nf, int add)
+{
+    orc_kb_vnlpsi_f64(nions, node0, row0, idx, proj, coeff, kbpsi, npt, out, ldo, nf, add);
+}
+static void oracle_kb_vnlpsi(int nions, const long long* node0, const int* row0, const int* idx,
+    const float* proj, const double* coeff, const double* kbpsi, size_t npt, float* out,
+    size_t ldo, int nf, int add)
+{
+    orc_kb_vnlpsi_f32(nions, node0, row0, idx, proj, coeff, kbpsi, npt, out, ldo, nf, add);
+}
+
+template <typename T>
+static int run_kb()
+{
+    const int dims[3]      = { 16, 24, 32 };
+    const unsigned gdim[3] = { 16, 24, 32 };
+    const double ll[3]     = { 4.0, 6.0, 8.0 };
+    const int N            = 5;
+    const size_t npt       = (size_t)dims[0] * dims[1] * dims[2];
+    unsigned long long seed = 4321;
+    std::vector<T> phi(npt * N), h0(npt * N);
+    for (size_t i = 0; i < phi.size(); i++)
+    {
+        phi[i] = (T)(lcg(seed) + 0.2);
+        h0[i]  = (T)lcg(seed);
+    }
+    const int centre[3][3] = { { 4, 6, 8 }, { 6, 7, 10 }, { 15, 23, 31 } }; // the last wraps
+    const int nproj[3]     = { 1, 4, 4 };
+    std::vector<long long> node0(1, 0);
+    std::vector<int> row0(1, 0), nlindex;
+    std::vector<T> proj;
+    std::vector<double> coeff;
+    Grid grid(gdim, ll, 1);
+    KBProjectors<T> kb(grid);
+    int fails = 0;
+    for (int j = 0; j < 3; j++)
+    {
+        std::vector<int> idx;
+        for (int dx = -3; dx <= 3; dx++)
+            for (int dy = -3; dy <= 3; dy++)
+                for (int dz = -3; dz <= 3; dz++)
+                    if (dx * dx + dy * dy + dz * dz <= 9)
+                    {
+                        const int ix = (centre[j][0] + dx + dims[0]) % dims[0];
+                        const int iy = (centre[j][1] + dy + dims[1]) % dims[1];
+                        const int iz = (centre[j][2] + dz + dims[2]) % dims[2];
+                        idx.push_back((ix * dims[1] + iy) * dims[2] + iz);
+                    }
+        std::vector<T> pr((size_t)nproj[j] * idx.size());
+        for (size_t i = 0; i < pr.size(); i++)
+            pr[i] = (T)lcg(seed);
+        std::vector<double> cf(nproj[j]);
+        for (int p = 0; p < nproj[j]; p++)
+            cf[p] = (p & 1 ? -1. : 1.) * (0.5 + 0.1 * p);
+        const int row = kb.addIon(idx, pr.data(), cf);
+        if (row != row0.back()) fails++;
+        nlindex.insert(nlindex.end(), idx.begin(), idx.end());
+        proj.insert(proj.end(), pr.begin(), pr.end());
+        coeff.insert(coeff.end(), cf.begin(), cf.end());
+        node0.push_back(node0.back() + (long long)idx.size());
+        row0.push_back(row0.back() + nproj[j]);
+    }
+    kb.commit();
+    const int nrows = kb.nrows();
+    if (nrows != row0.back()) fails++;
+
+    ExtendedGridOrbitals<T> orbitals(grid, N), hphi(grid, N);
+    orbitals.setPsi(phi.data());
+    hphi.setPsi(h0.data());
+    DeviceMemory<double> kbpsi_dev((size_t)nrows * N);
+    kb.computeKBpsi(orbitals, kbpsi_dev.data());
+    std::vector<double> kbpsi((size_t)nrows * N), kref((size_t)nrows * N);
+    kbpsi_dev.copy_to_host(kbpsi.data(), kbpsi.size());
+    oracle_kb_psi(3, node0.data(), row0.data(), nlindex.data(), proj.data(), grid.vel(), phi.data(),
+        npt, N, kref.data());
+    double scale = 0., kerr = 0.;
+    for (size_t i = 0; i < kref.size(); i++)
+        scale = std::fmax(scale, std::fabs(kref[i]));
+    for (size_t i = 0; i < kref.size(); i++)
+        kerr = std::fmax(kerr, std::fabs(kbpsi[i] - kref[i]) / scale);
+    const double ktol = sizeof(T) == 8 ? 1e-13 : 1e-6;
+    // the scatter alone: fed with the oracle's projections; float bit for bit (the (T)
+    // roundings of axpySKet / axpyKet are reproduced), double to 1e-15
+    kbpsi_dev.copy_to_dev(kref.data(), kref.size());
+    const int idx0 = hphi.getIterativeIndex();
+    kb.computeHnlPhiAndAdd2HPhi(kbpsi_dev.data(), hphi);
+    if (hphi.getIterativeIndex() <= idx0) fails++;
+    std::vector<T> got(npt * N), exp(h0);
+    hphi.getPsiHost(got.data());
+    oracle_kb_vnlpsi(3, node0.data(), row0.data(), nlindex.data(), proj.data(), coeff.data(),
+        kref.data(), npt, exp.data(), npt, N, 1);
+    double verr = 0., vmax = 0.;
+    size_t nbits = 0;
+    for (size_t i = 0; i < got.size(); i++)
+    {
+        vmax = std::fmax(vmax, std::fabs((double)exp[i]));
+        verr = std::fmax(verr, std::fabs((double)got[i] - (double)exp[i]));
+        if (got[i] != exp[i]) nbits++;
+    }
+    std::printf("       %s  KB projectors  kbpsi %.3e (tol %.0e)  H phi += Vnl phi %.3e, %zu values "
+                "differ\n",
+        sizeof(T) == 8 ? "f64" : "f32", kerr, ktol, verr / vmax, nbits);
+    if (!(kerr <= ktol)) fails++;
+    if (sizeof(T) == 4 ? nbits != 0 : !(verr <= 1e-15 * vmax)) fails++;
+    return fails;
+}
+
 int main()
 {
     if (mgb_device_count() < 1)
@@ -460,6 +594,8 @@ int main()
             fails += run_localized<float>(lap, op, 5e-6);
         }
     }
+    fails += run_kb<double>();
+    fails += run_kb<float>();
     std::printf(fails ? "FAILED (%d)\n" : "ok\n", fails);
     return fails ? 1 : 0;
 }
