@@ -419,6 +419,10 @@ class Orbitals:
     def incrementIterativeIndex(self):
         self.iterative_index_ += 1
 
+    def resetIterativeIndex(self):
+        """src/Orbitals.h:43 (after read_func_hdf5)."""
+        self.iterative_index_ = 0
+
     def psi(self):
         return self.psi_
 
