@@ -85,8 +85,9 @@ def layout(args, world):
            "decomposition": "%dx%dx%d" % nproc, "decomposition_from": how,
            "l2": "inputs larger than L2 (%.1f GB per GPU per step)"
                  % (2.0 * S * np.prod(ldims) * norb / 1e9),
-           "tolerance": "max |err| / per-orbital max norm <= 1e-12 (f64), 1e-5 (f32); tests also "
-                        "report the elementwise relative error on entries above 1e-3 of the max"}
+           "tolerance": "max |err| / per-orbital max norm <= 1e-12 (f64), 1e-5 (f32); the tests "
+                        "(and parity_mgpu at N > 1) also report the elementwise relative error on "
+                        "entries above 1e-3 of the orbital's max norm"}
     return {"nproc": nproc, "gdims": gdims, "ldims": ldims, "cell": cell, "norb": norb,
             "lap_type": lap_type, "S": S, "config": cfg}
 
@@ -831,7 +832,12 @@ def mgpu_parity(H, comm, rank, world, nproc):
         got = ham.applyLocal(phi, True, peer_comm=comm, **vh).psi().cpu().numpy()
         ref = port.hpsi(lap, full, v, ll)
         scale = np.abs(ref).reshape(N, -1).max(axis=1)[:, None, None, None]
-        errs["hpsi_lap%d" % lap] = float((np.abs(got - ref[(slice(None),) + box]) / scale).max())
+        mine_ref = ref[(slice(None),) + box]
+        errs["hpsi_lap%d" % lap] = float((np.abs(got - mine_ref) / scale).max())
+        # north_star's elementwise figure on the entries that are not cancellation residue
+        big = np.abs(mine_ref) >= 1e-3 * scale
+        errs["hpsi_elementwise_lap%d" % lap] = (
+            float((np.abs(got - mine_ref)[big] / np.abs(mine_ref)[big]).max()) if big.any() else 0.0)
         # Gram and Phi^T H Phi with the all-reduce
         S = phi.computeGram(comm).cpu().numpy()
         ex = grid.vel() * full.reshape(N, -1) @ full.reshape(N, -1).T
@@ -854,10 +860,13 @@ def mgpu_parity(H, comm, rank, world, nproc):
     t = torch.tensor([errs[k] for k in sorted(errs)], dtype=torch.float64, device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     errs = dict(zip(sorted(errs), t.cpu().tolist()))
-    bars = {"hpsi": 1e-12, "gram": 1e-12, "precond_mg": 5e-6}
+    # hpsi_elementwise: relative error on entries >= 1e-3 of the orbital's max norm (bounded
+    # by the max-norm bar / 1e-3)
+    bars = {"hpsi": 1e-12, "hpsi_elementwise": 1e-9, "gram": 1e-12, "precond_mg": 5e-6}
     ok = all(e <= bars[k.rsplit("_lap", 1)[0]] for k, e in errs.items())
     res.update({"max_err": errs, "bars": bars, "ok": bool(ok),
-                "max_err_overall_fp64_paths": max(e for k, e in errs.items() if not k.startswith("precond"))})
+                "max_err_overall_fp64_paths": max(e for k, e in errs.items()
+                                                  if not k.startswith("precond") and "elementwise" not in k)})
     return res
 
 

@@ -57,3 +57,18 @@ def rel_inf(a, b):
     scale = np.abs(b).max(axis=ax, keepdims=True) if b.ndim > 1 else np.abs(b).max()
     scale = np.where(scale > 0, scale, 1.0)
     return float((np.abs(a - b) / scale).max())
+
+
+def rel_elem(a, b, floor=1e-3):
+    """max elementwise |a-b| / |b| over the entries with |b| >= floor x the per-function
+    max norm of the reference b -- north_star's "elementwise relative" figure on the
+    entries that are not cancellation residue.  A max-norm error e (rel_inf) bounds it by
+    e / floor."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    ax = tuple(range(1, b.ndim))
+    scale = np.abs(b).max(axis=ax, keepdims=True) if b.ndim > 1 else np.abs(b).max()
+    big = np.abs(b) >= floor * np.where(scale > 0, scale, 1.0)
+    if not big.any():
+        return 0.0
+    return float((np.abs(a - b)[big] / np.abs(b)[big]).max())

@@ -15,7 +15,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import bits_equal, rel_inf
+from conftest import bits_equal, rel_elem, rel_inf
 from oracle.oracle import synthetic_orbitals, synthetic_potential
 
 pytestmark = pytest.mark.gpu
@@ -74,6 +74,13 @@ def test_hpsi_tma_and_generic(H, port, dt, lap_type, bc, dims, N):
     assert used1 == 1
     err = rel_inf(got1, ref)
     assert err <= TOL[dt], "TMA kernel rel err %g" % err
+    # the elementwise relative error on the entries above 1e-3 of the orbital's max (the
+    # others are cancellation residue of the stencil's large terms): reported, and bounded
+    # by the max-norm bar / 1e-3
+    el = rel_elem(got1, ref, 1e-3)
+    print("H psi %s lap %d bc %s: max-norm rel %.2e, elementwise rel (|ref| >= 1e-3 max) %.2e"
+          % (np.dtype(dt).name, lap_type, bc, err, el))
+    assert el <= TOL[dt] / 1e-3
 
 
 @pytest.mark.parametrize("dt", [np.float64, np.float32])
