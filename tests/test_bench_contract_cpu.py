@@ -54,3 +54,40 @@ def test_gpu_arm_refuses_without_a_device():
     r = _run(["--steps", "1", "--warmup", "1"])
     assert r.returncode != 0
     assert "no CUDA device" in (r.stderr + r.stdout)
+
+
+def test_layout_is_shared_by_both_arms_and_follows_the_decomposition_rule():
+    """bench.layout: the `config` dict both arms print (identical by construction), the
+    default workload = the largest single-GPU configuration (256^3 x 512 doubles per GPU),
+    the rank count's factors placed on x and y (z, the contiguous direction, last)."""
+    import argparse
+    sys.path.insert(0, ROOT)
+    import bench
+    want = {1: "1x1x1", 2: "2x1x1", 4: "2x2x1", 8: "4x2x1"}
+    for world, dec in want.items():
+        args = argparse.Namespace(workload=bench.DEFAULT_WORKLOAD, decomp="auto", strong=False,
+                                  orbitals=0, lap=None, dtype="f64")
+        L = bench.layout(args, world)
+        cfg = L["config"]
+        assert cfg["decomposition"] == dec
+        assert cfg["global_grid"] == [256, 256, 256] and cfg["orbitals"] == 512 * world
+        assert np_prod(cfg["grid_per_gpu"]) * world == 256 ** 3
+        # fixed work per GPU: weak scaling
+        assert np_prod(cfg["grid_per_gpu"]) * cfg["orbitals"] == 256 ** 3 * 512
+        assert "workload" in cfg and "tolerance" in cfg and "l2" in cfg
+        assert json.dumps(bench.layout(args, world)["config"]) == json.dumps(cfg)
+    args = argparse.Namespace(workload=bench.DEFAULT_WORKLOAD, decomp="2x2x2", strong=False,
+                              orbitals=0, lap=None, dtype="f64")
+    assert bench.layout(args, 8)["config"]["decomposition"] == "2x2x2"
+    args.decomp = "auto"
+    args.workload = "h2o64"
+    L = bench.layout(args, 2)
+    assert L["config"]["grid_per_gpu"] == [128, 128, 128] and L["config"]["orbitals"] == 256
+    assert L["lap_type"] == 2
+
+
+def np_prod(v):
+    out = 1
+    for x in v:
+        out *= int(x)
+    return out
