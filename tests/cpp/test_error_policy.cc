@@ -9,6 +9,30 @@
 
 #include <cstdio>
 
+// Every member of the host mirror compiles (members of class templates are otherwise only
+// checked when used): the decomposed-domain entry points, the KB projectors, the solvers.
+template class mgmol_b200::GridFuncVector<double>;
+template class mgmol_b200::GridFuncVector<float>;
+template class mgmol_b200::ExtendedGridOrbitals<double>;
+template class mgmol_b200::ExtendedGridOrbitals<float>;
+template class mgmol_b200::LocGridOrbitals<double>;
+template class mgmol_b200::Lap<double>;
+template class mgmol_b200::Lap<float>;
+template class mgmol_b200::Hamiltonian<double>;
+template class mgmol_b200::Hamiltonian<float>;
+template class mgmol_b200::OrbitalsPreconditioning<double>;
+template class mgmol_b200::OrbitalsPreconditioning<float>;
+template class mgmol_b200::KBProjectors<double>;
+template class mgmol_b200::KBProjectors<float>;
+template class mgmol_b200::PoissonMG<mgmol_b200::GridFunc<double>>;
+template class mgmol_b200::PoissonPCG<mgmol_b200::GridFunc<double>, mgmol_b200::GridFunc<float>>;
+template void mgmol_b200::Communicator::trade_boundaries<double>(
+    mgmol_b200::GridFuncVector<double>&, void*);
+template void mgmol_b200::Communicator::trade_boundaries<float>(
+    mgmol_b200::GridFuncVector<float>&, void*);
+template void mgmol_b200::Communicator::haloExchangeX<double>(
+    const mgmol_b200::Grid&, int, const double*, size_t, double*, int, void*);
+
 int main()
 {
     using namespace mgmol_b200;
