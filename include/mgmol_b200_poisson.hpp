@@ -32,6 +32,14 @@ class GridFunc
 {
 public:
     typedef T value_type;
+    // a no-ghost array in this field's memory space (what solve() takes)
+    typedef DeviceMemory<T> buffer_type;
+    // the same kind of field in another precision
+    template <typename U>
+    struct rebind
+    {
+        typedef GridFunc<U> type;
+    };
     explicit GridFunc(const Grid& grid) : gfv_(grid, 1), have_weights_(false)
     {
         gfv_.set_updated_boundaries(false);
@@ -457,6 +465,89 @@ private:
     double final_residual_, residual_reduction_;
     std::vector<Grid> grids_;
     std::vector<std::unique_ptr<PField>> work_, rcoarse_, newv_;
+};
+
+// Hartree<T> (src/Hartree.h:18-46, src/Hartree.cc:27-112) with the state of its Poisson
+// base (src/Poisson.h:31-89): the Hartree potential, kept between calls as the next
+// initial guess, and the integrals of vh against the charges.  Field = the potential's
+// precision (POTDTYPE), RField = the charges' (RHODTYPE), Solver = PoissonMG<Field>
+// (Hartree) or PoissonPCG<Field, PField> (Hartree_CG).  Boundary conditions 0 / 1: no
+// multipole boundary values.
+template <class Field, class RField, class Solver>
+class Hartree
+{
+public:
+    typedef typename Field::value_type T;
+    typedef typename RField::value_type RT;
+    Hartree(const Grid& grid, const int lap_type)
+        : grid_(grid.with_ghosts(poisson_detail::minGhosts(lap_type))), solver_(grid, lap_type),
+          vh_(grid.size()), Int_vhrho_(0.), Int_vhrhoc_(0.), Int_vhrho_old_(0.)
+    {
+        resetVh();
+    }
+    void setup(const short nu1, const short nu2, const short max_sweeps, const double tol,
+        const short max_nlevels, const bool gather_coarse_level = true)
+    {
+        (void)gather_coarse_level;
+        solver_.setup(nu1, nu2, max_sweeps, tol, max_nlevels);
+    }
+    // the potential without ghosts, in Field's memory space
+    T* vh() { return vh_.data(); }
+    void resetVh()
+    {
+        Field zero(grid_);
+        zero.resetData();
+        zero.getValues(vh_.data());
+    }
+    template <typename T2>
+    void set_vh(const T2* vh)
+    {
+        Field f(grid_);
+        f.assign(vh);
+        f.getValues(vh_.data());
+    }
+    double IntVhRho() const { return Int_vhrho_; }
+    double IntVhRhoc() const { return Int_vhrhoc_; }
+    double IntVhRho_old() const { return Int_vhrho_old_; }
+    double getFinalResidual() const { return solver_.getFinalResidual(); }
+    double getResidualReduction() const { return solver_.getResidualReduction(); }
+    Solver& solver() { return solver_; }
+
+    // Hartree::solve (src/Hartree.cc:27-112): rhs = 4 pi (rho - rhoc) in the solver's
+    // precision, the Poisson solve from the kept vh, the integrals.  rho, rhoc: no-ghost
+    // arrays of the charge precision in Field's memory space.
+    bool solve(const RT* rho, const RT* rhoc)
+    {
+        Int_vhrho_old_ = vhDot(rho);
+        RField work_rho(grid_), gf_rhoc(grid_);
+        work_rho.assign(rho);
+        gf_rhoc.assign(rhoc);
+        work_rho.axpy(-1., gf_rhoc); // work_rho -= rhoc
+        Field rhs(grid_);
+        rhs.assignFrom(work_rho); // GridFunc<POTDTYPE> rhs(work_rho)
+        rhs.scal(4. * M_PI);      // Hartree units
+        typename Field::buffer_type rhs_values(grid_.size());
+        rhs.getValues(rhs_values.data());
+        const bool conv = solver_.solve(vh_.data(), rhs_values.data());
+        Int_vhrho_      = vhDot(rho);
+        Int_vhrhoc_     = vhDot(rhoc);
+        return conv;
+    }
+
+private:
+    // vel * vh_->gdot(charge): the charge converted to vh's precision
+    double vhDot(const RT* charge)
+    {
+        Field a(grid_), b(grid_);
+        a.assign(vh_.data());
+        b.assign(charge);
+        return grid_.vel() * a.gdot(b);
+    }
+
+    Grid grid_;
+    Solver solver_;
+    typename Field::buffer_type vh_;
+    double Int_vhrho_, Int_vhrhoc_, Int_vhrho_old_;
 };
 
 } // namespace mgmol_b200

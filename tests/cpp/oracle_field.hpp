@@ -58,6 +58,12 @@ class OracleField
 {
 public:
     typedef T value_type;
+    typedef std::vector<T> buffer_type; // a no-ghost array in this field's memory space
+    template <typename U>
+    struct rebind
+    {
+        typedef OracleField<U> type;
+    };
     explicit OracleField(const mgmol_b200::Grid& grid)
         : grid_(grid), u_(grid.sizeg(), (T)0), upd_(false)
     {

@@ -2,11 +2,15 @@
 // read from stdin:
 //   <cpu|gpu> as argv[1]: host fields over the oracle's kernels (no device), or
 //   device fields over the C ABI
-//   stdin: solver(0 = SolverLap/Mgm, 1 = PCGSolver) lap_type dtype(0 f32, 1 f64)
+//   stdin: solver(0 = SolverLap/Mgm, 1 = PCGSolver, 2 = Hartree over Mgm, 3 = Hartree
+//          over PCGSolver) lap_type dtype(0 f32, 1 f64)
 //          nx ny nz  lx ly lz  bcx bcy bcz  nu1 nu2 max_sweeps tol max_nlevels
-//          then vh0 (nx*ny*nz values) and rho (nx*ny*nz values)
+//          then vh0 (nx*ny*nz values) and rho (nx*ny*nz values); Hartree: rho then rhoc
+//          (double charges; vh0 is the kept potential of the first solve)
 //   stdout: converged nb_sweeps final_residual final_relative_residual
 //           residual_reduction, then the solution, one value per line.
+//           Hartree: two consecutive solves with the same charges, one line each
+//           (converged IntVhRho_old IntVhRho IntVhRhoc final_residual), then vh.
 #include <cstdio>
 #include <cstring>
 #include <vector>
@@ -69,6 +73,49 @@ static void solve(const Problem& p, bool device)
     }
 }
 
+// Hartree<T>::solve twice: the second solve starts from the first one's potential
+template <typename T, class Field, class PField, class Solver>
+static void solve_hartree(const Problem& p, const std::vector<double>& rhoc, bool device)
+{
+    Grid grid(p.dims, p.ll, 1, p.bc);
+    typedef typename Field::template rebind<double>::type RField;
+    Hartree<Field, RField, Solver> h(grid, p.lap);
+    h.setup(p.nu1, p.nu2, p.max_sweeps, p.tol, p.max_nlevels);
+    const size_t n = p.vh.size();
+    std::vector<T> vh0(p.vh.begin(), p.vh.end()), vh(n);
+    if (!device)
+    {
+        h.set_vh(vh0.data());
+        for (int k = 0; k < 2; k++)
+        {
+            const bool conv = h.solve(p.rho.data(), rhoc.data());
+            std::printf("%d %.17g %.17g %.17g %.17g\n", (int)conv, h.IntVhRho_old(), h.IntVhRho(),
+                h.IntVhRhoc(), h.getFinalResidual());
+        }
+        std::copy(h.vh(), h.vh() + n, vh.begin());
+    }
+    else
+    {
+        DeviceMemory<T> dvh(n);
+        DeviceMemory<double> drho(n), drhoc(n);
+        dvh.copy_to_dev(vh0.data(), n);
+        drho.copy_to_dev(p.rho.data(), n);
+        drhoc.copy_to_dev(rhoc.data(), n);
+        MGB_CHECK(mgb_stream_sync(nullptr));
+        h.set_vh(dvh.data());
+        for (int k = 0; k < 2; k++)
+        {
+            const bool conv = h.solve(drho.data(), drhoc.data());
+            std::printf("%d %.17g %.17g %.17g %.17g\n", (int)conv, h.IntVhRho_old(), h.IntVhRho(),
+                h.IntVhRhoc(), h.getFinalResidual());
+        }
+        MGB_CHECK(mgb_copy_to_host(vh.data(), h.vh(), n * sizeof(T), nullptr));
+        MGB_CHECK(mgb_stream_sync(nullptr));
+    }
+    for (size_t i = 0; i < n; i++)
+        std::printf("%.17g\n", (double)vh[i]);
+}
+
 int main(int argc, char** argv)
 {
     if (argc != 2) return 2;
@@ -91,6 +138,32 @@ int main(int argc, char** argv)
         if (std::scanf("%lf", &p.vh[i]) != 1) return 2;
     for (size_t i = 0; i < n; i++)
         if (std::scanf("%lf", &p.rho[i]) != 1) return 2;
+    if (p.solver >= 2)
+    {
+        std::vector<double> rhoc(n);
+        for (size_t i = 0; i < n; i++)
+            if (std::scanf("%lf", &rhoc[i]) != 1) return 2;
+        const bool pcg = p.solver == 3;
+#define HARTREE(T, F, PF)                                                                      \
+    (pcg ? solve_hartree<T, F<T>, PF<float>, PoissonPCG<F<T>, PF<float>>>(p, rhoc, device)      \
+         : solve_hartree<T, F<T>, PF<float>, PoissonMG<F<T>>>(p, rhoc, device))
+        if (device)
+        {
+            if (p.dtype == 1)
+                HARTREE(double, GridFunc, GridFunc);
+            else
+                HARTREE(float, GridFunc, GridFunc);
+        }
+        else
+        {
+            if (p.dtype == 1)
+                HARTREE(double, OracleField, OracleField);
+            else
+                HARTREE(float, OracleField, OracleField);
+        }
+#undef HARTREE
+        return 0;
+    }
     if (device)
     {
         if (p.dtype == 1)

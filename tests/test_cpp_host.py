@@ -237,3 +237,84 @@ def test_cpp_error_policy_throws_behind_c_entries():
     assert text.index("#define MGMOL_B200_ERRORS_THROW") < text.index(
         '#include "mgmol_b200_poisson.hpp"')
     assert "catch (const mgmol_b200::Error&" in text
+
+
+def _hartree_inputs(dims, bc, dt):
+    import numpy as np
+    from poisson_cases import charge, guess
+    rho = charge(dims, bc, np.float64) + 0.3
+    rhoc = np.full(dims, rho.mean()) + 0.05 * charge(dims, bc, np.float64, seed=11)
+    if tuple(bc) == (1, 1, 1):
+        rhoc += rho.mean() - rhoc.mean()          # neutral cell
+    return guess(dims, dt), rho, rhoc
+
+
+def _run_hartree_mirror(exe, mode, pcg, case, lt, dt):
+    import sys
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from poisson_cases import DEFAULTS
+    tag, dims, ll, bc, kw = case
+    par = dict(DEFAULTS, **kw)
+    vh0, rho, rhoc = _hartree_inputs(dims, bc, dt)
+    head = "%d %d %d  %d %d %d  %r %r %r  %d %d %d  %d %d %d %r %d\n" % (
+        (3 if pcg else 2, lt, 1 if dt == np.float64 else 0) + tuple(dims) + tuple(ll) + tuple(bc)
+        + (par["nu1"], par["nu2"], par["max_sweeps"], par["tol"], par["max_nlevels"]))
+    body = "".join("\n".join(repr(float(v)) for v in a.ravel()) + "\n" for a in (vh0, rho, rhoc))
+    r = subprocess.run([exe, mode], input=head + body, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, (r.returncode, r.stdout[:300], r.stderr[:300])
+    lines = r.stdout.strip().splitlines()
+    stats = [[float(v) for v in lines[k].split()] for k in range(2)]
+    return np.array([float(v) for v in lines[2:]]).reshape(dims), stats
+
+
+def _check_hartree_mirror(mode, cases, eps64, eps32):
+    """Hartree<Field, RField, Solver> of include/mgmol_b200_poisson.hpp, two consecutive
+    solves (the second from the kept potential), against the Python host's Hartree over the
+    oracle's field operations (mgmol_b200/poisson.py, itself compared with the device in
+    tests/test_gpu_poisson.py): potential and the three integrals."""
+    import sys
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from mgmol_b200.host import Grid
+    from mgmol_b200.poisson import Hartree
+    from oracle.oracle import Port
+    from poisson_cases import CASES, DEFAULTS, PCG_CASES
+    from poisson_twin import field_factory
+    exe = _build_poisson_mirror()
+    port = Port()
+    byname = {c[0]: c for c in CASES + PCG_CASES}
+    for tag, lt, dt, pcg in cases:
+        case = byname[tag]
+        _, dims, ll, bc, kw = case
+        par = dict(DEFAULTS, **kw)
+        vh, stats = _run_hartree_mirror(exe, mode, pcg, case, lt, dt)
+        vh0, rho, rhoc = _hartree_inputs(dims, bc, dt)
+        h = Hartree(Grid(dims, ll, 1, bc), lt, dt, field=field_factory(port), pcg=pcg,
+                    rho_dtype=np.float64, precond_dtype=np.float32)
+        h.setup(par["nu1"], par["nu2"], par["max_sweeps"], par["tol"], par["max_nlevels"])
+        h.set_vh(vh0)
+        eps = eps64 if dt == np.float64 else eps32
+        for k in range(2):
+            conv = h.solve(rho, rhoc)
+            want = [float(conv), h.IntVhRho_old(), h.IntVhRho(), h.IntVhRhoc()]
+            scale = max(abs(w) for w in want[1:]) + 1e-300
+            assert stats[k][0] == want[0], (tag, lt, dt, pcg, k)
+            for a, b in zip(stats[k][1:4], want[1:]):
+                assert abs(a - b) <= 10 * eps * scale, (tag, lt, dt, pcg, k, a, b)
+        ref = np.asarray(h.vh()).reshape(dims).astype(np.float64)
+        assert np.abs(vh - ref).max() <= eps * np.abs(ref).max(), (tag, lt, dt, pcg)
+
+
+def test_cpp_hartree_control_flow():
+    import numpy as np
+    _check_hartree_mirror("cpu", [("per", 0, np.float64, False), ("mix", 2, np.float64, False),
+                                  ("dir", 1, np.float32, False), ("pcg_per", 0, np.float64, True),
+                                  ("pcg_mix", 2, np.float32, True)], 1e-13, 2e-6)
+
+
+@pytest.mark.gpu
+def test_cpp_hartree_on_device():
+    import numpy as np
+    _check_hartree_mirror("gpu", [("per", 0, np.float64, False), ("pcg_mix", 0, np.float64, True)],
+                          1e-12, 5e-6)
