@@ -19,12 +19,19 @@
 #endif
 
 #include <fstream>
+#include <string>
 
 class Control
 {
 public:
     short bcPoisson[3];
     short lap_type;
+    // src/Species.cc and src/radial/RadialMeshFunction.cc (row f3: the sparse KB
+    // projectors) read the verbosity, whether this is a restart (both only gate
+    // printing) and the output file name helper
+    short verbose;
+    bool restart_run;
+    std::string getFullFilename(const std::string& name) const { return name; }
     static Control* instance()
     {
         static Control c;
@@ -32,7 +39,10 @@ public:
     }
 
 private:
-    Control() : lap_type(0) { bcPoisson[0] = bcPoisson[1] = bcPoisson[2] = 1; }
+    Control() : lap_type(0), verbose(0), restart_run(false)
+    {
+        bcPoisson[0] = bcPoisson[1] = bcPoisson[2] = 1;
+    }
 };
 
 #endif

@@ -400,13 +400,14 @@ class Port:
         return vh, bool(conv), tuple(stats)
 
     # -- contractions ---------------------------------------------------------
-    # -- non-local Kleinman-Bylander projectors (row f3; parity unpinned) ------
+    # -- non-local Kleinman-Bylander projectors (row f3; pinned against RefKB below and
+    #    tests/golden/reference_kb.npz) --------------------------------------------
     @staticmethod
     def _kb_pack(ions, dtype):
         node0, row0, idx, vals, coeff = [0], [0], [], [], []
         for ion in ions:
             n = len(ion["nlindex"])
-            pr = np.ascontiguousarray(ion["proj"], dtype=dtype).reshape(-1, n)
+            pr = np.ascontiguousarray(ion["proj"], dtype=dtype).reshape(len(ion["coeff"]), n)
             node0.append(node0[-1] + n)
             row0.append(row0[-1] + pr.shape[0])
             idx.append(np.asarray(ion["nlindex"], np.int32))
@@ -762,3 +763,77 @@ def synthetic_potential(dims, noise=0.05):
          + 0.4 * np.cos(4 * np.pi * z) + 0.25 * np.cos(2 * np.pi * (x + y + z)))
     rng = np.random.default_rng(99)
     return np.ascontiguousarray(v + noise * rng.uniform(-1, 1, size=(nx, ny, nz)))
+
+
+class RefKB:
+    """The reference's own sparse Kleinman-Bylander projector code (KBprojectorSparse.cc,
+    Species.cc, Mesh.cc, radial/*.cc compiled unmodified, oracle/ref_shim_kb.cc) for one
+    ORBDTYPE: real pseudopotentials from the reference's potentials/ directory, the
+    projector of an ion as KBprojectorSparse::setup builds it, <beta|psi> as
+    computeLocalElement forms it and get_vnlpsi's loop.  Only where /root/reference
+    exists (the pseudopotential files are read from there); the GPU box uses the golden
+    vectors generated from it (tests/golden/make_golden_kb.py)."""
+
+    POTENTIALS = "/root/reference/potentials"
+
+    def __init__(self, dtype):
+        self.dtype = np.dtype(dtype)
+        so = os.path.join(HERE, "_ref", "libmgmol_refkb_f%d.so" % (8 * self.dtype.itemsize))
+        if not os.path.exists(so):
+            raise FileNotFoundError(so + " missing: run `make -C oracle ref`")
+        self.lib = ctypes.CDLL(so, mode=getattr(os, "RTLD_LOCAL", 0))
+        assert self.lib.refkb_orbdtype_bytes() == self.dtype.itemsize
+        self.nions = 0
+
+    @staticmethod
+    def available(dtype=np.float64):
+        so = os.path.join(HERE, "_ref", "libmgmol_refkb_f%d.so" % (8 * np.dtype(dtype).itemsize))
+        return os.path.exists(so) and os.path.isdir(RefKB.POTENTIALS)
+
+    def setup(self, dims, ll, lap_type, pseudo, filter_flag="n", origin=(0.0, 0.0, 0.0)):
+        """Mesh + species.  Returns dict(nlradius, dim_nl, max_l, llocal, nproj)."""
+        info = (ctypes.c_double * 5)()
+        path = pseudo if os.path.isabs(pseudo) else os.path.join(self.POTENTIALS, pseudo)
+        rc = self.lib.refkb_setup(_c_int3(*dims), _c_dbl3(*origin), _c_dbl3(*ll), lap_type,
+                                  path.encode(), ctypes.c_char(filter_flag.encode()), info)
+        if rc:
+            raise FileNotFoundError(path)
+        self.dims, self.nions = tuple(dims), 0
+        return dict(zip(("nlradius", "dim_nl", "max_l", "llocal", "nproj"), list(info)))
+
+    def add_ion(self, center):
+        """KBprojectorSparse(species).setup(center); returns the ion as the dict the
+        product and the port take (nlindex, proj (nproj, size_nl), coeff = kbcoeff * sign)."""
+        j = self.lib.refkb_add_ion(_c_dbl3(*center))
+        assert j == self.nions
+        self.nions += 1
+        n, npj = self.lib.refkb_ion_size(j), self.lib.refkb_ion_nproj(j)
+        idx = np.zeros(n, np.int32)
+        proj = np.zeros((npj, n), self.dtype)
+        coeff = np.zeros(npj, np.float64)
+        rc = self.lib.refkb_ion_data(j, _ptr(idx), _ptr(proj), _ptr(coeff))
+        assert rc == 0, rc
+        return {"nlindex": idx, "proj": proj, "coeff": coeff,
+                "single": bool(self.lib.refkb_ion_single(j))}
+
+    def kb_psi(self, psi):
+        """kbpsi[row, f] for every ion added so far (rows ion after ion)."""
+        psi = np.ascontiguousarray(psi, self.dtype)
+        rows = []
+        for j in range(self.nions):
+            out = np.zeros((self.lib.refkb_ion_nproj(j), psi.shape[0]), np.float64)
+            col = np.zeros(out.shape[0], np.float64)
+            for f in range(psi.shape[0]):
+                self.lib.refkb_psi(j, _ptr(psi[f]), _ptr(col))
+                out[:, f] = col
+            rows.append(out)
+        return np.concatenate(rows, axis=0)
+
+    def kb_vnlpsi(self, kbpsi, out, add):
+        out = np.array(out, dtype=self.dtype, order="C")
+        kbpsi = np.ascontiguousarray(kbpsi, np.float64)
+        for f in range(out.shape[0]):
+            rows = np.ascontiguousarray(kbpsi[:, f])
+            n = self.lib.refkb_vnlpsi(_ptr(rows), _ptr(out[f]), int(bool(add)))
+            assert n == kbpsi.shape[0]
+        return out
