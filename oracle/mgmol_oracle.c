@@ -45,7 +45,8 @@
 
 int orc_lap_constants(int lap_type, const double h[3], double out[3]);
 
-/* ---- non-local Kleinman-Bylander projectors (parity unpinned) ---- */
+/* ---- non-local Kleinman-Bylander projectors (pinned against the compiled
+ *      KBprojectorSparse, tests/test_kb_cpu.py) ---- */
 #define T double
 #define FN(name) ORC_CAT(name, _f64)
 #include "mgmol_oracle_kb.inc"
