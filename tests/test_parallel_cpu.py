@@ -38,6 +38,32 @@ def test_geom_matches_reference_heuristic():
     assert geom(30, 32, 32, 2) is None
 
 
+def test_geom_against_the_compiled_reference():
+    """parallel.geom against pb::PEenv::geom itself (compiled unmodified, called through
+    oracle/ref_shim_geom.cc): 15360 meshes x task counts from the committed table
+    (tests/golden/make_golden_geom.py), and live where the compiled reference exists.  The
+    port returns None where the reference refuses the mesh (0 tasks placed) or places
+    fewer tasks than it was given (it would then shrink the communicator)."""
+    import ctypes
+    table = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden",
+                                 "reference_geom.npz"))["table"]
+    assert len(table) == 15360
+    refused = shrunk = 0
+    for nx, ny, nz, nt, placed, px, py, pz in table.tolist():
+        want = (px, py, pz) if placed == nt else None
+        refused += placed == 0
+        shrunk += 0 < placed < nt
+        assert geom(nx, ny, nz, nt) == want, (nx, ny, nz, nt, placed, (px, py, pz))
+    assert refused > 0 and shrunk > 0          # both kinds of refusal are in the table
+    from oracle.oracle import REF_SO, Ref
+    if Ref.available():
+        lib = ctypes.CDLL(REF_SO)
+        out = (ctypes.c_int * 3)()
+        for nx, ny, nz, nt, placed, px, py, pz in table[::37].tolist():
+            assert lib.ref_geom(nx, ny, nz, nt, 1, out) == placed
+            assert tuple(out) == (px, py, pz)
+
+
 def test_cartesian_topology():
     nproc = (2, 2, 2)
     for r in range(8):
